@@ -1,0 +1,86 @@
+"""ctypes binding of libbackpack_b200.so (the C ABI declared in include/backpack_b200.h).
+
+There is no fallback: if the shared library is missing, or a call returns a non-zero status, this module
+raises.  Build the library with ``python -m backpacks_flash_attn_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbackpack_b200.so")
+
+BP_DTYPE_F16, BP_DTYPE_BF16, BP_DTYPE_F32 = 0, 1, 2
+BP_ACT_NONE, BP_ACT_GELU_TANH = 0, 1
+
+_DTYPES = {torch.float16: BP_DTYPE_F16, torch.bfloat16: BP_DTYPE_BF16, torch.float32: BP_DTYPE_F32}
+
+# name -> argtypes; every function returns int (bp_status_t) unless listed in _RESTYPES
+SIGNATURES = {
+    "bp_abi_version": [],
+    "bp_last_error": [],
+    "bp_check_device": [],
+    "bp_fmha_fwd": [c_void_p] * 7 + [c_int32] * 7 + [c_int64] * 8 + [c_int32, c_float, c_int32, c_int32, c_void_p],
+    "bp_sense_lse_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p],
+    "bp_sense_mix_fwd": [c_void_p] * 4 + [c_int32] * 5 + [c_int64] * 3 + [c_float, c_int32, c_void_p],
+    "bp_ln_residual_fwd": [c_void_p] * 8 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
+    "bp_linear_bias_act_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    "bp_rotary_qk_inplace": [c_void_p] * 5 + [c_int32] * 6 + [c_void_p],
+}
+_RESTYPES = {"bp_last_error": c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA library is required (no CPU/PyTorch fallback exists). "
+                "Build it with `python -m backpacks_flash_attn_b200.build`.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        if lib.bp_abi_version() != 1:
+            raise RuntimeError("libbackpack_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().bp_last_error().decode()
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {dtype}") from None
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("backpacks_flash_attn_b200 operators need CUDA tensors on a B200 "
+                               "(there is no CPU path; the CPU oracle lives under oracle/ for tests only)")

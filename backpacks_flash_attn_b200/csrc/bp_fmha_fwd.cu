@@ -1,0 +1,448 @@
+// FlashAttention forward for sm_100a: softmax(scale * Q K^T [+ causal mask]) V, fp32 accumulate.
+//
+// Replaces the reference's FlashAttention-1 forward (csrc/flash_attn/fmha_api.cpp:189-325 ->
+// src/fmha_fprop_kernel_1xN.h:199-696).  That kernel walks K/V blocks in the outer loop and bounces a
+// fp32 O through HBM between blocks; this one is written for Blackwell from scratch:
+//
+//   * Q-outer / KV-inner: one CTA owns 2 x 128 query rows of one (batch, head); O stays in TMEM for the
+//     whole KV sweep, so Q, K, V are read once and O written once (the algorithmic traffic).
+//   * warp-specialised, 384 threads:  warp 0 = TMA producer (Q once, K/V double-buffered rings),
+//     warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warpgroups 1 and 2 = softmax for query tile
+//     0 / 1 (one thread per query row -> row max / row sum need no shuffles; TMEM lane == row).
+//   * S = Q K^T (M=128, N=BN) lands in TMEM; softmax threads tcgen05.ld it, apply the mask, keep a running
+//     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8), write
+//     P = exp2(...) as bf16/f16 into a 128B-swizzled smem tile; O += P V is a second tcgen05.mma with
+//     V consumed as an MN-major B operand straight from the TMA tile (no transpose).
+//   * the two query tiles ping-pong: while the softmax of tile 0 runs, the tensor core works for tile 1.
+//
+// Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
+// are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill
+// to a padded width DP of 64 or 128.
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace fmha {
+
+constexpr int BM = 128;           // query rows per tile (= TMEM lanes)
+constexpr int kThreads = 384;     // 3 warpgroups
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <int DP>
+struct Cfg {
+  static constexpr int BN = (DP == 64) ? 128 : 64;  // keys per block
+  static constexpr int kStages = 2;
+  static constexpr int kPanelsD = DP / 64;           // 64-column (128 B) panels along head dim
+  static constexpr int kPanelsN = BN / 64;           // panels of P along the key dim
+  static constexpr uint32_t kQTileBytes = BM * DP * 2;
+  static constexpr uint32_t kKVTileBytes = BN * DP * 2;
+  static constexpr uint32_t kPTileBytes = BM * BN * 2;
+  static constexpr uint32_t kKVPanelBytes = BN * 128;  // one 64-column panel of a K/V tile
+  // shared memory map (all tile bases 1024-aligned)
+  static constexpr uint32_t offQ = 0;
+  static constexpr uint32_t offK = offQ + 2 * kQTileBytes;
+  static constexpr uint32_t offV = offK + kStages * kKVTileBytes;
+  static constexpr uint32_t offP = offV + kStages * kKVTileBytes;
+  static constexpr uint32_t offBar = offP + 2 * kPTileBytes;
+  static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;  // + barriers + alignment slack
+  // TMEM columns
+  static constexpr uint32_t colS = 0;            // S_t at colS + t*BN
+  static constexpr uint32_t colO = 2 * BN;       // O_t at colO + t*DP
+  static constexpr uint32_t kTmemCols = 512;
+};
+
+struct Params {
+  void* out;
+  float* lse;
+  const int32_t* cu_q;
+  const int32_t* cu_k;
+  int64_t o_row_stride, o_head_stride;
+  int32_t lse_stride;
+  int32_t nheads, headdim;
+  int32_t num_pairs;  // ceil(max_seqlen_q / 256)
+  int32_t is_causal;
+  float scale;        // softmax scale
+  float scale_log2;   // scale * log2(e)
+};
+
+struct Barriers {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], p_ready[2], pv_done[2];
+  uint32_t tmem_base;
+};
+
+template <int DP, bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const Params p) {
+  using C = Cfg<DP>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers& bars = *reinterpret_cast<Barriers*>(smem + C::offBar);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pair = p.num_pairs - 1 - static_cast<int>(blockIdx.x);  // heaviest (most KV blocks) first
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+
+  const int q_begin = p.cu_q[batch];
+  const int len_q = p.cu_q[batch + 1] - q_begin;
+  const int k_begin = p.cu_k[batch];
+  const int len_k = p.cu_k[batch + 1] - k_begin;
+  const int row0 = pair * 2 * BM;  // first query row (within the sequence) of this CTA
+  if (row0 >= len_q) return;       // uniform for the CTA; nothing allocated yet
+
+  // number of key blocks each query tile visits
+  int n_blk[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r0 = row0 + t * BM;
+    int n = 0;
+    if (r0 < len_q) {
+      int kmax = len_k;
+      if (p.is_causal) kmax = min(kmax, r0 + BM);
+      n = (kmax + BN - 1) / BN;
+    }
+    n_blk[t] = n;
+  }
+  const int n_max = max(n_blk[0], n_blk[1]);
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&bars.q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.k_full[i], 1);
+      mbar_init(&bars.k_empty[i], 1);
+      mbar_init(&bars.v_full[i], 1);
+      mbar_init(&bars.v_empty[i], 1);
+      mbar_init(&bars.s_full[i], 1);
+      mbar_init(&bars.p_ready[i], 128);
+      mbar_init(&bars.pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars.tmem_base, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp < 4) {
+    reg_dealloc<56>();
+    if (warp == 0 && n_max > 0) {
+      // ===================== TMA producer (whole warp walks the loop, lane 0 issues) =====================
+      const int n_q_tiles = (row0 + BM < len_q) ? 2 : 1;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars.q_full, n_q_tiles * C::kQTileBytes);
+        for (int t = 0; t < n_q_tiles; ++t)
+          for (int pn = 0; pn < C::kPanelsD; ++pn)
+            tma_load_3d(smem + C::offQ + t * C::kQTileBytes + pn * (BM * 128), &tmQ, &bars.q_full, pn * 64, head,
+                        q_begin + row0 + t * BM);
+      }
+      for (int j = 0; j < n_max; ++j) {
+        const int slot = j & 1;
+        const int krow = k_begin + j * BN;
+        if (j >= 2) mbar_wait(&bars.k_empty[slot], ((j >> 1) - 1) & 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKVTileBytes);
+          for (int pn = 0; pn < C::kPanelsD; ++pn)
+            tma_load_3d(smem + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK, &bars.k_full[slot],
+                        pn * 64, head, krow);
+        }
+        if (j >= 2) mbar_wait(&bars.v_empty[slot], ((j >> 1) - 1) & 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&bars.v_full[slot], C::kKVTileBytes);
+          for (int pn = 0; pn < C::kPanelsD; ++pn)
+            tma_load_3d(smem + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV, &bars.v_full[slot],
+                        pn * 64, head, krow);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 && n_max > 0) {
+      // ===================== MMA issuer (whole warp waits, lane 0 issues) =====================
+      constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
+      constexpr uint32_t idesc_pv = make_idesc(kBF16, BM, DP, false, true);
+      const uint32_t sQ = smem_u32(smem + C::offQ);
+      const uint32_t sK = smem_u32(smem + C::offK);
+      const uint32_t sV = smem_u32(smem + C::offV);
+      const uint32_t sP = smem_u32(smem + C::offP);
+
+      // S_t(j) = Q_t K_j^T ; optionally hands the K slot back to the producer
+      auto issue_s = [&](int t, int j, bool release_k) {
+        if (lane == 0) {
+          const uint32_t a_base = sQ + t * C::kQTileBytes;
+          const uint32_t b_base = sK + (j & 1) * C::kKVTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < DP / 16; ++kk) {
+            const uint32_t a = a_base + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+            const uint32_t b = b_base + (kk >> 2) * C::kKVPanelBytes + (kk & 3) * 32;
+            umma_ss(tmem_base + C::colS + t * BN, make_smem_desc_sw128(a, 16, 1024),
+                    make_smem_desc_sw128(b, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+          }
+          if (release_k) umma_commit(&bars.k_empty[j & 1]);
+          umma_commit(&bars.s_full[t]);
+        }
+        __syncwarp();
+      };
+      // O_t (+)= P_t V_j ; V is the MN-major B operand
+      auto issue_pv = [&](int t, int j, bool release_v) {
+        if (lane == 0) {
+          const uint32_t a_base = sP + t * C::kPTileBytes;
+          const uint32_t b_base = sV + (j & 1) * C::kKVTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint32_t a = a_base + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+            const uint32_t b = b_base + kk * 2048;  // 16 key rows x 128 B
+            umma_ss(tmem_base + C::colO + t * DP, make_smem_desc_sw128(a, 16, 1024),
+                    make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          if (release_v) umma_commit(&bars.v_empty[j & 1]);
+          umma_commit(&bars.pv_done[t]);
+        }
+        __syncwarp();
+      };
+      // tile 1 visits a superset of tile 0's key blocks, so it is the last reader whenever it exists
+      auto last_user = [&](int j) { return j < n_blk[1] ? 1 : 0; };
+
+      mbar_wait(&bars.q_full, 0);
+      mbar_wait(&bars.k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < 2; ++t)
+        if (n_blk[t] > 0) issue_s(t, 0, t == last_user(0));
+      for (int j = 0; j < n_max; ++j) {
+        for (int t = 0; t < 2; ++t) {
+          if (j >= n_blk[t]) continue;
+          mbar_wait(&bars.p_ready[t], j & 1);
+          tc_fence_after();
+          if (j + 1 < n_blk[t]) {
+            mbar_wait(&bars.k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_s(t, j + 1, t == last_user(j + 1));
+          }
+          mbar_wait(&bars.v_full[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          issue_pv(t, j, t == last_user(j));
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    reg_alloc<224>();
+    const int t = (warp >> 2) - 1;                 // query tile of this warpgroup
+    const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
+    const int n = n_blk[t];
+    if (n > 0) {
+      const int qrow = row0 + t * BM + r;          // query index within the sequence
+      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN;
+      const uint32_t tO = tmem_base + lane_addr + C::colO + t * DP;
+      uint8_t* sP = smem + C::offP + t * C::kPTileBytes;
+      const float scale_log2 = p.scale_log2;
+      float m_used = 0.f;  // running max (raw score units) the exponentials are taken against
+      float l = 0.f;
+
+      for (int j = 0; j < n; ++j) {
+        mbar_wait(&bars.s_full[t], j & 1);
+        tc_fence_after();
+        float s[BN];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t u[32];
+          tmem_ld32(tS + c * 32, u);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(u[i]);
+        }
+        tmem_ld_wait();
+
+        const int col0 = j * BN;
+        const bool partial = (col0 + BN > len_k) || (p.is_causal && (col0 + BN - 1 > row0 + t * BM));
+        if (partial) {
+          const int limit = p.is_causal ? min(len_k, qrow + 1) : len_k;  // visible keys: col < limit
+#pragma unroll
+          for (int c = 0; c < BN; ++c)
+            if (col0 + c >= limit) s[c] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int c = 1; c < BN; ++c) mx = fmaxf(mx, s[c]);
+
+        if (j == 0) {
+          m_used = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          float alpha = 1.f;
+          const bool grow = (mx - m_used) * scale_log2 > kRescaleThreshold;
+          if (grow) {
+            alpha = fast_exp2((m_used - mx) * scale_log2);
+            m_used = mx;
+          }
+          // P tile and O accumulator are free once the previous PV MMA has completed
+          mbar_wait(&bars.pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+            for (int c = 0; c < DP / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+        }
+
+        const float neg_m = -m_used * scale_log2;
+        float sum = 0.f;
+#pragma unroll
+        for (int c8 = 0; c8 < BN / 8; ++c8) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = fast_exp2(fmaf(s[c8 * 8 + i], scale_log2, neg_m));
+            sum += e[i];
+          }
+          uint4 w;
+          w.x = pack2<kBF16>(e[0], e[1]);
+          w.y = pack2<kBF16>(e[2], e[3]);
+          w.z = pack2<kBF16>(e[4], e[5]);
+          w.w = pack2<kBF16>(e[6], e[7]);
+          *reinterpret_cast<uint4*>(sP + (c8 >> 3) * (BM * 128) + sw128_offset(r, c8 & 7)) = w;
+        }
+        l += sum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bars.p_ready[t]);
+      }
+
+      // ---- epilogue: O / l -> global, LSE ----
+      mbar_wait(&bars.pv_done[t], (n - 1) & 1);
+      tc_fence_after();
+      const bool valid = qrow < len_q;
+      const float inv_l = 1.f / l;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
+                      2 * (static_cast<int64_t>(q_begin + qrow) * p.o_row_stride + head * p.o_head_stride);
+#pragma unroll
+      for (int c = 0; c < DP / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c * 32 + g * 8 < p.headdim) {
+              uint4 w;
+              w.x = pack2<kBF16>(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+              w.y = pack2<kBF16>(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+              w.z = pack2<kBF16>(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+              w.w = pack2<kBF16>(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + (c * 32 + g * 8) * 2) = w;
+            }
+          }
+        }
+      }
+      if (valid)
+        p.lse[(static_cast<int64_t>(batch) * p.nheads + head) * p.lse_stride + qrow] = m_used * p.scale + logf(l);
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int DP, bool kBF16>
+int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Params& p, int batch,
+           cudaStream_t stream) {
+  using C = Cfg<DP>;
+  auto kern = fmha_fwd_kernel<DP, kBF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaFuncSetAttribute(%u B smem): %s", C::kSmemBytes,
+                cudaGetErrorString(e));
+  }
+  dim3 grid(p.num_pairs, p.nheads, batch);
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("bp_fmha_fwd launch");
+}
+
+}  // namespace fmha
+}  // namespace bp
+
+extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
+                           const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
+                           int32_t nheads, int32_t headdim, int32_t total_q, int32_t total_k,
+                           int32_t max_seqlen_q, int32_t max_seqlen_k, int64_t q_row_stride,
+                           int64_t q_head_stride, int64_t k_row_stride, int64_t k_head_stride,
+                           int64_t v_row_stride, int64_t v_head_stride, int64_t o_row_stride,
+                           int64_t o_head_stride, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                           int32_t dtype, void* stream) {
+  using namespace bp;
+  if (!q || !k || !v || !out || !softmax_lse || !cu_seqlens_q || !cu_seqlens_k)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: null pointer argument");
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: only fp16 and bf16 are supported (dtype=%d)", dtype);
+  if (batch <= 0 || nheads <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: batch and nheads must be positive");
+  if (headdim <= 0 || headdim % 8 != 0 || headdim > 128)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: head dim must be a multiple of 8 and <= 128 (got %d)", headdim);
+  if (total_q <= 0 || total_k <= 0 || max_seqlen_q <= 0 || max_seqlen_k <= 0)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: empty input (total_q=%d total_k=%d)", total_q, total_k);
+  if (lse_stride < max_seqlen_q)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: lse_stride %d < max_seqlen_q %d", lse_stride, max_seqlen_q);
+  const int64_t strides[] = {q_row_stride, q_head_stride, k_row_stride, k_head_stride,
+                             v_row_stride, v_head_stride, o_row_stride, o_head_stride};
+  for (int64_t s : strides)
+    if (s <= 0 || s % 8 != 0)
+      return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: row/head strides must be positive multiples of 8 elements (got %lld)",
+                  (long long)s);
+  const uintptr_t ptrs[] = {(uintptr_t)q, (uintptr_t)k, (uintptr_t)v, (uintptr_t)out};
+  for (uintptr_t a : ptrs)
+    if (a % 16 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: q/k/v/out must be 16-byte aligned");
+
+  const int DP = headdim <= 64 ? 64 : 128;
+  const int BN = DP == 64 ? 128 : 64;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    const uint64_t dq[3] = {(uint64_t)headdim, (uint64_t)nheads, (uint64_t)total_q};
+    const uint64_t sq[2] = {(uint64_t)q_head_stride * 2, (uint64_t)q_row_stride * 2};
+    const uint32_t bq[3] = {64, 1, (uint32_t)fmha::BM};
+    if (int rc = encode_tensor_map(&tmQ, dtype, 3, q, dq, sq, bq, true)) return rc;
+    const uint64_t dk[3] = {(uint64_t)headdim, (uint64_t)nheads, (uint64_t)total_k};
+    const uint64_t sk[2] = {(uint64_t)k_head_stride * 2, (uint64_t)k_row_stride * 2};
+    const uint32_t bk[3] = {64, 1, (uint32_t)BN};
+    if (int rc = encode_tensor_map(&tmK, dtype, 3, k, dk, sk, bk, true)) return rc;
+    const uint64_t sv[2] = {(uint64_t)v_head_stride * 2, (uint64_t)v_row_stride * 2};
+    if (int rc = encode_tensor_map(&tmV, dtype, 3, v, dk, sv, bk, true)) return rc;
+  }
+  fmha::Params p;
+  p.out = out;
+  p.lse = softmax_lse;
+  p.cu_q = cu_seqlens_q;
+  p.cu_k = cu_seqlens_k;
+  p.o_row_stride = o_row_stride;
+  p.o_head_stride = o_head_stride;
+  p.lse_stride = lse_stride;
+  p.nheads = nheads;
+  p.headdim = headdim;
+  p.num_pairs = (max_seqlen_q + 2 * fmha::BM - 1) / (2 * fmha::BM);
+  p.is_causal = is_causal ? 1 : 0;
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * fmha::kLog2e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf16 = dtype == BP_DTYPE_BF16;
+  if (DP == 64) return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, p, batch, st) : fmha::launch<64, false>(tmQ, tmK, tmV, p, batch, st);
+  return bf16 ? fmha::launch<128, true>(tmQ, tmK, tmV, p, batch, st) : fmha::launch<128, false>(tmQ, tmK, tmV, p, batch, st);
+}

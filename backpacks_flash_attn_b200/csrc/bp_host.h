@@ -1,0 +1,26 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA tensor-map encoding.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/backpack_b200.h"
+
+namespace bp {
+
+// printf-style; stores the message returned by bp_last_error() (thread local) and returns `code`.
+int fail(int code, const char* fmt, ...);
+
+// Encode a tiled tensor map without linking libcuda: the driver entry point is resolved through
+// cudaGetDriverEntryPoint the first time it is needed.  `dims`/`box` are innermost-first,
+// `strides_bytes` has rank-1 entries (stride of dims 1..rank-1).  Returns 0 or a negative bp error.
+int encode_tensor_map(CUtensorMap* out, int elem_bytes_log2_dtype /*bp_dtype_t*/, int rank, const void* base,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      bool swizzle128);
+
+int check_launch(const char* what);
+
+inline int dtype_size(int dtype) { return dtype == BP_DTYPE_F32 ? 4 : 2; }
+
+}  // namespace bp

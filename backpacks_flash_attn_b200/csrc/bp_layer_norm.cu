@@ -1,0 +1,240 @@
+// Residual add + LayerNorm forward (eval mode) for sm_100a.
+//
+// Replaces dropout_add_ln_fwd (csrc/layer_norm/ln_api.cpp:83-251, ln_fwd_kernels.cuh:20-191) for the
+// inference path: dropout_p = 0, no rowscale / colscale / subset.  Semantics kept from the reference:
+// x = x0 + x1 in fp32, x stored in the residual dtype, statistics from the fp32 sum (mean, then the
+// centred second moment), z = gamma * (x - mu) * rsigma + beta rounded once to the input dtype.
+//
+// HBM-bound: one warp owns one row and keeps it in registers (cols/32 values per lane), so every byte is
+// read once and written once; 16-byte vector loads/stores, warp-shuffle reductions only, no smem, no
+// block barrier.  Grid is a multiple of the SM count and warps stride over rows.
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace ln {
+
+constexpr int kWarpsPerCta = 8;
+
+template <typename T>
+struct Vec8;  // 8 consecutive elements
+template <>
+struct Vec8<float> {
+  float4 a, b;
+  __device__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ void to(float (&f)[8]) const {
+    f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+  }
+  __device__ void from(const float (&f)[8]) {
+    a = make_float4(f[0], f[1], f[2], f[3]);
+    b = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  uint4 u;
+  __device__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ void to(float (&f)[8]) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ void from(const float (&f)[8]) {
+    u.x = pack2<true>(f[0], f[1]);
+    u.y = pack2<true>(f[2], f[3]);
+    u.z = pack2<true>(f[4], f[5]);
+    u.w = pack2<true>(f[6], f[7]);
+  }
+};
+template <>
+struct Vec8<__half> {
+  uint4 u;
+  __device__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ void to(float (&f)[8]) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ void from(const float (&f)[8]) {
+    u.x = pack2<false>(f[0], f[1]);
+    u.y = pack2<false>(f[2], f[3]);
+    u.z = pack2<false>(f[4], f[5]);
+    u.w = pack2<false>(f[6], f[7]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// NV = 8-element vectors per lane; a row has cols/8 vectors, vector index = i*32 + lane.
+template <typename X, typename R, typename W, int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const W* __restrict__ gamma,
+                       const W* __restrict__ beta, X* __restrict__ z, R* __restrict__ x_out,
+                       float* __restrict__ mu_out, float* __restrict__ rs_out, int64_t rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = cols >> 3;
+  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kWarpsPerCta;
+  const float inv_cols = 1.f / static_cast<float>(cols);
+
+  // gamma / beta are reused by every row this warp handles
+  float g[NV][8], b[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      Vec8<W> t;
+      t.load(gamma + v * 8);
+      t.to(g[i]);
+      t.load(beta + v * 8);
+      t.to(b[i]);
+    }
+  }
+
+  for (int64_t row = warp_global; row < rows; row += warp_stride) {
+    const int64_t base = row * cols;
+    float x[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = i * 32 + lane;
+      if (v < nvec) {
+        Vec8<X> t;
+        t.load(x0 + base + v * 8);
+        t.to(x[i]);
+        if (x1 != nullptr) {
+          Vec8<R> r;
+          float rf[8];
+          r.load(x1 + base + v * 8);
+          r.to(rf);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[i][k] += rf[k];
+        }
+        if (x_out != nullptr) {
+          Vec8<R> r;
+          r.from(x[i]);
+          r.store(x_out + base + v * 8);
+          // the reference normalises the value it stored (ln_fwd_kernels.cuh keeps x in compute type;
+          // with a 16-bit residual stream the stored value is the rounded one) -- keep fp32 here.
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += x[i][k];
+      }
+    }
+    const float mu = warp_sum(sum) * inv_cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < nvec) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = x[i][k] - mu;
+          sq += d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(sq) * inv_cols + eps);
+    if (lane == 0) {
+      if (mu_out) mu_out[row] = mu;
+      if (rs_out) rs_out[row] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = i * 32 + lane;
+      if (v < nvec) {
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = g[i][k] * ((x[i][k] - mu) * rs) + b[i][k];
+        Vec8<X> t;
+        t.from(y);
+        t.store(z + base + v * 8);
+      }
+    }
+  }
+}
+
+template <typename X, typename R, typename W, int NV>
+int launch_nv(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
+              float* rs, int64_t rows, int cols, float eps, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ctas_needed = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int64_t cap = static_cast<int64_t>(sms) * 8;  // 8 resident CTAs of 256 threads per SM
+  const int grid = static_cast<int>(ctas_needed < cap ? ctas_needed : cap);
+  ln_residual_fwd_kernel<X, R, W, NV><<<grid, kWarpsPerCta * 32, 0, st>>>(
+      static_cast<const X*>(x0), static_cast<const R*>(x1), static_cast<const W*>(gamma),
+      static_cast<const W*>(beta), static_cast<X*>(z), static_cast<R*>(x_out), mu, rs, rows, cols, eps);
+  return check_launch("bp_ln_residual_fwd launch");
+}
+
+template <typename X, typename R, typename W>
+int launch(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
+           float* rs, int64_t rows, int cols, float eps, cudaStream_t st) {
+  const int nv = (cols / 8 + 31) / 32;
+#define BP_LN_CASE(N) \
+  if (nv <= N) return launch_nv<X, R, W, N>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, st)
+  BP_LN_CASE(1);
+  BP_LN_CASE(2);
+  BP_LN_CASE(3);
+  BP_LN_CASE(4);
+  BP_LN_CASE(6);
+  BP_LN_CASE(8);
+  BP_LN_CASE(16);
+  BP_LN_CASE(32);
+#undef BP_LN_CASE
+  return fail(BP_ERR_UNSUPPORTED, "bp_ln_residual_fwd: hidden size %d > 8192 is not supported", cols);
+}
+
+}  // namespace ln
+}  // namespace bp
+
+extern "C" int bp_ln_residual_fwd(const void* x0, const void* x1, const void* gamma, const void* beta, void* z,
+                                  void* x_out, float* mu, float* rsigma, int64_t rows, int32_t cols,
+                                  float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype,
+                                  void* stream) {
+  using namespace bp;
+  if (!x0 || !gamma || !beta || !z) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_fwd: null pointer argument");
+  if (rows <= 0 || cols <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_fwd: empty input");
+  if (cols % 8 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_fwd: hidden size must be a multiple of 8 (got %d)", cols);
+  const uintptr_t ptrs[] = {(uintptr_t)x0, (uintptr_t)x1, (uintptr_t)gamma, (uintptr_t)beta, (uintptr_t)z, (uintptr_t)x_out};
+  for (uintptr_t a : ptrs)
+    if (a % 16 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int key = x0_dtype * 100 + residual_dtype * 10 + weight_dtype;
+#define BP_LN_DISPATCH(XD, RD, WD, X, R, W) \
+  if (key == XD * 100 + RD * 10 + WD)       \
+  return ln::launch<X, R, W>(x0, x1, gamma, beta, z, x_out, mu, rsigma, rows, cols, epsilon, st)
+  using bf = __nv_bfloat16;
+  using hf = __half;
+  BP_LN_DISPATCH(BP_DTYPE_BF16, BP_DTYPE_F32, BP_DTYPE_BF16, bf, float, bf);
+  BP_LN_DISPATCH(BP_DTYPE_F16, BP_DTYPE_F32, BP_DTYPE_F16, hf, float, hf);
+  BP_LN_DISPATCH(BP_DTYPE_BF16, BP_DTYPE_BF16, BP_DTYPE_BF16, bf, bf, bf);
+  BP_LN_DISPATCH(BP_DTYPE_F16, BP_DTYPE_F16, BP_DTYPE_F16, hf, hf, hf);
+  BP_LN_DISPATCH(BP_DTYPE_F32, BP_DTYPE_F32, BP_DTYPE_F32, float, float, float);
+  BP_LN_DISPATCH(BP_DTYPE_BF16, BP_DTYPE_F32, BP_DTYPE_F32, bf, float, float);
+  BP_LN_DISPATCH(BP_DTYPE_F16, BP_DTYPE_F32, BP_DTYPE_F32, hf, float, float);
+#undef BP_LN_DISPATCH
+  return fail(BP_ERR_UNSUPPORTED, "bp_ln_residual_fwd: dtype combination (x0=%d, residual=%d, weight=%d) not built",
+              x0_dtype, residual_dtype, weight_dtype);
+}

@@ -1,0 +1,115 @@
+"""FlashAttention forward operators with the reference's Python signatures
+(flash_attn/flash_attn_interface.py:242-380), backed by bp_fmha_fwd instead of flash_attn_cuda.fwd.
+
+Forward / inference only: dropout must be 0 and tensors must not require grad (the reference's autograd
+backward, flash_attn_interface.py:31-47, is out of scope for this path).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _check_common(dropout_p, return_attn_probs, *tensors):
+    if dropout_p != 0.0:
+        raise RuntimeError("bp_fmha_fwd is the inference path: dropout_p must be 0.0")
+    if return_attn_probs:
+        raise RuntimeError("return_attn_probs is not supported (the S matrix is never materialised)")
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+
+
+def _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                        softmax_scale, causal):
+    """q, k, v: (total, nheads, headdim) views with unit last stride (fmha_api.cpp:72-80).
+    Returns (out, softmax_lse (batch, nheads, max_seqlen_q rounded up to 16) fp32)."""
+    _lib.require_cuda(q, k, v, out, cu_seqlens_q, cu_seqlens_k)
+    if q.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("FlashAttention only support fp16 and bf16 data type")      # fmha_api.cpp:215-217
+    if k.dtype != q.dtype or v.dtype != q.dtype or out.dtype != q.dtype:
+        raise RuntimeError("query, key, value and out must have the same dtype")       # fmha_api.cpp:218-221
+    if cu_seqlens_q.dtype != torch.int32 or cu_seqlens_k.dtype != torch.int32:
+        raise RuntimeError("cu_seqlens must have dtype int32")                         # fmha_api.cpp:222-223
+    for t in (q, k, v, out):
+        if t.dim() != 3 or t.stride(-1) != 1:
+            raise RuntimeError("q, k, v, out must be (total, nheads, headdim) with contiguous last dimension")
+    if not (cu_seqlens_q.is_contiguous() and cu_seqlens_k.is_contiguous()):
+        raise RuntimeError("cu_seqlens must be contiguous")
+    total_q, nheads, d = q.shape
+    total_k = k.shape[0]
+    if k.shape != (total_k, nheads, d) or v.shape != (total_k, nheads, d) or out.shape != q.shape:
+        raise RuntimeError("q/k/v/out shape mismatch")
+    batch = cu_seqlens_q.numel() - 1
+    if batch <= 0 or cu_seqlens_k.numel() != batch + 1:
+        raise RuntimeError("cu_seqlens_q and cu_seqlens_k must both have batch+1 entries")
+    if d % 8 != 0 or d > 128:
+        raise RuntimeError("head dimension must be a multiple of 8 and at most 128")   # fmha_api.cpp:245
+    lse_stride = (max_seqlen_q + 15) // 16 * 16                                        # fmha_api.cpp:254,276
+    lse = torch.empty((batch, nheads, lse_stride), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        st = _lib.load().bp_fmha_fwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
+            cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr(),
+            batch, nheads, d, total_q, total_k, max_seqlen_q, max_seqlen_k,
+            q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+            out.stride(0), out.stride(1), lse_stride, float(softmax_scale), int(bool(causal)),
+            _lib.dtype_code(q.dtype), _lib.stream_ptr(q.device))
+    _lib.check(st, "bp_fmha_fwd")
+    return out, lse
+
+
+def flash_attn_unpadded_qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p, softmax_scale=None,
+                                       causal=False, return_attn_probs=False):
+    """qkv: (total, 3, nheads, headdim); cu_seqlens: (batch+1,) int32.  Returns (total, nheads, headdim).
+    Mirrors flash_attn_interface.py:242-267."""
+    _check_common(dropout_p, return_attn_probs, qkv)
+    if softmax_scale is None:
+        softmax_scale = qkv.shape[-1] ** (-0.5)
+    out = torch.empty_like(qkv[:, 0])
+    _flash_attn_forward(qkv[:, 0], qkv[:, 1], qkv[:, 2], out, cu_seqlens, cu_seqlens, max_seqlen, max_seqlen,
+                        softmax_scale, causal)
+    return out
+
+
+def flash_attn_unpadded_kvpacked_func(q, kv, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                                      dropout_p, softmax_scale=None, causal=False, return_attn_probs=False):
+    """q: (total_q, nheads, headdim); kv: (total_k, 2, nheads, headdim).  flash_attn_interface.py:270-303."""
+    _check_common(dropout_p, return_attn_probs, q, kv)
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** (-0.5)
+    out = torch.empty_like(q)
+    _flash_attn_forward(q, kv[:, 0], kv[:, 1], out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                        softmax_scale, causal)
+    return out
+
+
+def flash_attn_unpadded_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p,
+                             softmax_scale=None, causal=False, return_attn_probs=False):
+    """q: (total_q, nheads, headdim); k, v: (total_k, nheads, headdim).  flash_attn_interface.py:306-340."""
+    _check_common(dropout_p, return_attn_probs, q, k, v)
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** (-0.5)
+    out = torch.empty_like(q)
+    _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                        softmax_scale, causal)
+    return out
+
+
+def flash_attn_unpadded_with_lse(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                                 softmax_scale=None, causal=False):
+    """Like flash_attn_unpadded_func but also returns softmax_lse, as _flash_attn_forward does in the
+    reference (flash_attn_interface.py:13-28)."""
+    _check_common(0.0, False, q, k, v)
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** (-0.5)
+    out = torch.empty_like(q)
+    return _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                               softmax_scale, causal)
+
+
+def flash_attn_func(qkv, cu_seqlens, dropout_p, max_s, softmax_scale=None, causal=False,
+                    return_attn_probs=False):
+    """Back-compat alias with the old argument order (flash_attn_interface.py:374-380)."""
+    return flash_attn_unpadded_qkvpacked_func(qkv, cu_seqlens, max_s, dropout_p, softmax_scale, causal,
+                                              return_attn_probs)

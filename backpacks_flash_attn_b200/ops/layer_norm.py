@@ -1,0 +1,77 @@
+"""`dropout_add_layer_norm` with the reference's signature (flash_attn/ops/layer_norm.py:207-252),
+running bp_ln_residual_fwd.  Inference path: dropout_p must be 0 and rowscale / layerscale are rejected."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+def _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, want_residual):
+    _lib.require_cuda(x0, x1, gamma, beta)
+    cols = x0.shape[-1]
+    x0m = x0.reshape(-1, cols)
+    if not x0m.is_contiguous():
+        x0m = x0m.contiguous()
+    x1m = None
+    if x1 is not None:
+        if x1.shape != x0.shape:
+            raise RuntimeError("x1 must have the same shape as x0")
+        x1m = x1.reshape(-1, cols)
+        if not x1m.is_contiguous():
+            x1m = x1m.contiguous()
+    # residual dtype rule of the reference (ln_api.cpp:101-104): x1's dtype if given, else fp32 when
+    # residual_in_fp32, else the input dtype.
+    rdtype = x1.dtype if x1 is not None else (torch.float32 if residual_in_fp32 else x0.dtype)
+    gamma, beta = gamma.contiguous(), beta.contiguous()
+    if gamma.dtype != beta.dtype or gamma.shape != (cols,) or beta.shape != (cols,):
+        raise RuntimeError("gamma and beta must both be (hidden,) with the same dtype")
+    rows = x0m.shape[0]
+    z = torch.empty_like(x0m)
+    # the residual stream only has to be written when it differs from x0 or the caller wants it back
+    need_x = want_residual and (x1 is not None or rdtype != x0.dtype)
+    x_out = torch.empty((rows, cols), dtype=rdtype, device=x0.device) if need_x else None
+    with torch.cuda.device(x0.device):
+        st = _lib.load().bp_ln_residual_fwd(
+            x0m.data_ptr(), _lib.ptr(x1m), gamma.data_ptr(), beta.data_ptr(), z.data_ptr(), _lib.ptr(x_out),
+            None, None, rows, cols, float(epsilon), _lib.dtype_code(x0.dtype), _lib.dtype_code(rdtype),
+            _lib.dtype_code(gamma.dtype), _lib.stream_ptr(x0.device))
+    _lib.check(st, "bp_ln_residual_fwd")
+    z = z.reshape(x0.shape)
+    if not want_residual:
+        return z, None
+    return z, (x_out.reshape(x0.shape) if need_x else x0)
+
+
+def dropout_add_layer_norm(x0, x1, weight, bias, dropout_p, epsilon, rowscale=None, layerscale=None,
+                           prenorm=False, residual_in_fp32=False, return_dropout_mask=False):
+    """z = LayerNorm(x0 + x1) (and the fp32/16-bit residual x0 + x1 when prenorm=True).
+    residual_in_fp32 only matters when x1 is None (layer_norm.py:209-212)."""
+    if dropout_p != 0.0:
+        raise RuntimeError("inference path: dropout_p must be 0.0")
+    if rowscale is not None or layerscale is not None or return_dropout_mask:
+        raise RuntimeError("rowscale / layerscale / dropout mask are training-only features (out of scope)")
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x0, x1, weight, bias)):
+        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+    z, res = _ln_residual_forward(x0, x1, weight, bias, epsilon, residual_in_fp32, prenorm)
+    return (z, res) if prenorm else z
+
+
+class DropoutAddLayerNorm(nn.Module):
+    """Module form (layer_norm.py:232-252); parameters `weight`, `bias`."""
+
+    def __init__(self, hidden_size, prenorm=False, p=0.0, eps=1e-5, residual_in_fp32=False, device=None,
+                 dtype=None):
+        factory_kwargs = {"device": device, "dtype": dtype}
+        super().__init__()
+        self.prenorm = prenorm
+        self.p = p
+        self.epsilon = eps
+        self.residual_in_fp32 = residual_in_fp32
+        self.weight = nn.Parameter(torch.ones(hidden_size, **factory_kwargs))
+        self.bias = nn.Parameter(torch.zeros(hidden_size, **factory_kwargs))
+
+    def forward(self, x0, x1=None):
+        return dropout_add_layer_norm(x0, x1, self.weight, self.bias, self.p if self.training else 0.0,
+                                      self.epsilon, prenorm=self.prenorm, residual_in_fp32=self.residual_in_fp32)

@@ -1,0 +1,124 @@
+/* backpack_b200.h -- C ABI of libbackpack_b200.so
+ *
+ * The drop-in boundary for the Backpack forward hot path on B200 (sm_100a).  These entry points
+ * replace, for the forward pass, the four pybind11 extensions the reference's Python op wrappers
+ * import (paths relative to the reference repository):
+ *
+ *   flash_attn_cuda.fwd                       csrc/flash_attn/fmha_api.cpp:189-325      -> bp_fmha_fwd
+ *   dropout_layer_norm.dropout_add_ln_fwd     csrc/layer_norm/ln_api.cpp:83-251         -> bp_ln_residual_fwd
+ *   fused_dense_lib.linear_gelu_forward       csrc/fused_dense_lib/fused_dense.cpp:88-142 -> bp_linear_bias_act_fwd
+ *   rotary_emb.apply_rotary                   csrc/rotary/rotary.cpp:12-33              -> bp_rotary_qk_inplace
+ *   (no reference kernel; eager PyTorch at    training/src/models/backpack.py:111-122,313) -> bp_sense_lse_fwd,
+ *                                                                                            bp_sense_mix_fwd
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, strides (in ELEMENTS), a cudaStream_t passed as void*.
+ *   - every function is asynchronous on `stream`, never allocates device memory and never synchronises;
+ *     the caller owns every buffer (the reference allocates inside the extension, fmha_api.cpp:273-280).
+ *   - return value 0 = success, negative = bp_status_t; bp_last_error() gives a thread-local message.
+ *     (The reference raises C++ exceptions through TORCH_CHECK, fmha_api.cpp:210-252; the Python
+ *     binding turns a non-zero status into RuntimeError with that message.)
+ *   - the launch targets the CUDA device current on the calling thread.
+ *   - dtype: activations are f16 or bf16 (fmha_api.cpp:215-221); statistics and residual streams f32.
+ */
+#ifndef BACKPACK_B200_H_
+#define BACKPACK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_ABI_VERSION 1
+
+typedef enum bp_dtype { BP_DTYPE_F16 = 0, BP_DTYPE_BF16 = 1, BP_DTYPE_F32 = 2 } bp_dtype_t;
+
+typedef enum bp_status {
+  BP_OK = 0,
+  BP_ERR_INVALID_ARGUMENT = -1, /* shape / stride / dtype / alignment rejected */
+  BP_ERR_UNSUPPORTED = -2,      /* valid in the reference but not implemented here */
+  BP_ERR_CUDA = -3,             /* a CUDA runtime / driver call failed (message has the error string) */
+  BP_ERR_ARCH = -4              /* device is not compute capability 10.x */
+} bp_status_t;
+
+typedef enum bp_activation { BP_ACT_NONE = 0, BP_ACT_GELU_TANH = 1 } bp_activation_t;
+
+/* Library identification. */
+int bp_abi_version(void);
+const char* bp_last_error(void);
+/* Compute capability check for the current device (0 when sm_100-class, BP_ERR_ARCH otherwise). */
+int bp_check_device(void);
+
+/* FlashAttention forward (replaces mha_fwd, csrc/flash_attn/fmha_api.cpp:189-325).
+ *   q, k, v, out : (total_tokens, nheads, headdim) views, last-dim stride 1, row/head strides in elements
+ *                  (packed qkv views are passed un-copied, as flash_attn_interface.py:59 does).
+ *   softmax_lse  : (batch, nheads, lse_stride) f32, natural-log sum-exp of the scaled scores.
+ *   cu_seqlens_* : (batch+1) int32 device arrays (fmha_api.cpp:230-233); sequence i occupies rows
+ *                  [cu[i], cu[i+1]).  Causal masking is top-left aligned: key j visible to query i iff j<=i
+ *                  (csrc/flash_attn/src/fmha/mask.h:70).
+ *   headdim % 8 == 0 and headdim <= 128 (fmha_api.cpp:245).  No dropout (inference path).
+ */
+int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
+                const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                int32_t batch, int32_t nheads, int32_t headdim,
+                int32_t total_q, int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                int64_t q_row_stride, int64_t q_head_stride,
+                int64_t k_row_stride, int64_t k_head_stride,
+                int64_t v_row_stride, int64_t v_head_stride,
+                int64_t o_row_stride, int64_t o_head_stride,
+                int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                int32_t dtype /* bp_dtype_t */, void* stream);
+
+/* Backpack sense-mix, pass 1: per-sense causal softmax statistics.
+ *   qk  : (batch, seqlen, 2, nv, dk) contiguous -- the output of ContextSelfAttn.Wqkv reshaped as
+ *         training/src/models/backpack.py:111-116 (q = [:, :, 0], k = [:, :, 1]).
+ *   lse : (batch, nv, seqlen) f32; lse[b,l,i] = log sum_{j<=i} exp(scale * q_li . k_lj).
+ */
+int bp_sense_lse_fwd(const void* qk, float* lse, int32_t batch, int32_t seqlen, int32_t nv, int32_t dk,
+                     float softmax_scale, int32_t dtype, void* stream);
+
+/* Backpack sense-mix, pass 2: out[b,i,:] = sum_l sum_{j<=i} softmax_j(scale q_li.k_lj) * content[b,l,j,:]
+ * (backpack.py:117-122 + :313 fused; alpha (b,nv,s,s) is never materialised).
+ *   content : element (b,l,j,c) at content + b*c_batch_stride + l*c_sense_stride + j*c_row_stride + c
+ *             (the reference hands a transposed view of (b,s,nv,d), backpack.py:276).
+ *   out     : (batch, seqlen, d) contiguous, same dtype.   lse: from bp_sense_lse_fwd.
+ */
+int bp_sense_mix_fwd(const void* qk, const void* content, const float* lse, void* out,
+                     int32_t batch, int32_t seqlen, int32_t nv, int32_t dk, int32_t d,
+                     int64_t c_batch_stride, int64_t c_sense_stride, int64_t c_row_stride,
+                     float softmax_scale, int32_t dtype, void* stream);
+
+/* Residual add + LayerNorm forward, eval mode (replaces dropout_add_ln_fwd with dropout_p = 0, no
+ * rowscale/colscale/subset; csrc/layer_norm/ln_api.cpp:83-251, ln_fwd_kernels.cuh:98-188).
+ *   x0 (rows, cols) x0_dtype; x1 (rows, cols) residual_dtype or NULL;
+ *   x_out = x0 + x1 written in residual_dtype (may be NULL when not needed: prenorm=False);
+ *   z = gamma * (x_out - mean) * rstd + beta in x0_dtype;  mu / rsigma (rows) f32, may be NULL.
+ */
+int bp_ln_residual_fwd(const void* x0, const void* x1, const void* gamma, const void* beta,
+                       void* z, void* x_out, float* mu, float* rsigma,
+                       int64_t rows, int32_t cols, float epsilon,
+                       int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype, void* stream);
+
+/* out = act(x W^T + bias)  (replaces linear_gelu_forward, csrc/fused_dense_lib/fused_dense.cpp:88-142,
+ * and the plain F.linear of FusedDense, flash_attn/ops/fused_dense.py:52).
+ *   x (m, k) row-major, W (n, k) row-major (nn.Linear layout), bias (n) or NULL, out (m, n) row-major.
+ *   k % 8 == 0, n % 8 == 0.
+ */
+int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void* out,
+                           int64_t m, int32_t n, int32_t k, int32_t activation /* bp_activation_t */,
+                           int32_t dtype, void* stream);
+
+/* In-place rotary embedding on q and k of a packed qkv tensor (replaces apply_rotary as driven by
+ * ApplyRotaryEmbQKV_.forward, flash_attn/layers/rotary.py:81-105; csrc/rotary/rotary_cuda.cu:5-41).
+ *   qkv (batch, seqlen, 3, nheads, headdim) contiguous; cos/sin (seqlen, rotary_dim/2) in qkv's dtype;
+ *   cos_k/sin_k: tables for k (XPos), or NULL to reuse cos/sin.  Non-interleaved (GPT-NeoX) pairing.
+ */
+int bp_rotary_qk_inplace(void* qkv, const void* cos, const void* sin, const void* cos_k, const void* sin_k,
+                         int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim, int32_t rotary_dim,
+                         int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BACKPACK_B200_H_ */

@@ -142,7 +142,7 @@ def attention_fp32_ref(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[
     scores = torch.einsum("bthd,bshd->bhts", q, k) * scale
     if causal:
         sq, sk = scores.shape[-2:]
-        keep = torch.ones(sq, sk, dtype=torch.bool).tril()  # top-left aligned, col <= row (mask.h:70)
+        keep = torch.ones(sq, sk, dtype=torch.bool, device=scores.device).tril()  # top-left aligned, col <= row (mask.h:70)
         scores = scores.masked_fill(~keep, float("-inf"))
     lse = torch.logsumexp(scores, dim=-1)
     p = torch.softmax(scores, dim=-1)
@@ -160,7 +160,7 @@ def self_attention_eager(qkv: Tensor, softmax_scale: Optional[float] = None,
     scores = torch.einsum("bthd,bshd->bhts", q, k * scale)
     if causal:
         s = qkv.shape[1]
-        mask = torch.full((s, s), MASK_VALUE).triu(1)
+        mask = torch.full((s, s), MASK_VALUE, device=scores.device).triu(1)
         scores = scores + mask.to(scores.dtype)
     probs = torch.softmax(scores, dim=-1, dtype=v.dtype)
     return torch.einsum("bhts,bshd->bthd", probs, v)
@@ -174,7 +174,7 @@ def context_weights_eager(hidden: Tensor, wqk: Tensor, bqk: Tensor, nv: int) -> 
     q, k = qk.unbind(dim=2)
     scale = 1.0 / math.sqrt(d // nv)
     scores = torch.einsum("bthd,bshd->bhts", q, k * scale)
-    scores = scores + torch.full((s, s), MASK_VALUE).triu(1).to(scores.dtype)
+    scores = scores + torch.full((s, s), MASK_VALUE, device=scores.device).triu(1).to(scores.dtype)
     return torch.softmax(scores, dim=-1, dtype=q.dtype)
 
 
@@ -195,7 +195,7 @@ def sense_mix_fp32_ref(qk: Tensor, content: Tensor, softmax_scale: Optional[floa
     scale = softmax_scale if softmax_scale is not None else q.shape[-1] ** -0.5
     s = q.shape[1]
     scores = torch.einsum("bthd,bshd->bhts", q, k) * scale
-    scores = scores.masked_fill(~torch.ones(s, s, dtype=torch.bool).tril(), float("-inf"))
+    scores = scores.masked_fill(~torch.ones(s, s, dtype=torch.bool, device=scores.device).tril(), float("-inf"))
     lse = torch.logsumexp(scores, dim=-1)
     alpha = torch.softmax(scores, dim=-1)
     return torch.sum(alpha @ content.float(), dim=1), lse
@@ -262,7 +262,7 @@ def gpt_trunk(ids: Tensor, w: Dict[str, Tensor], cfg: OracleConfig, fused_ln: bo
     b, s = ids.shape
     eps = cfg.layer_norm_epsilon
     emb = w[g + "embeddings.word_embeddings.weight"][ids] \
-        + w[g + "embeddings.position_embeddings.weight"][torch.arange(s)]  # embedding.py:27-39
+        + w[g + "embeddings.position_embeddings.weight"][torch.arange(s, device=ids.device)]  # embedding.py:27-39
     h, res = add_layer_norm(emb, None, *_ln(w, g + "ln_0"), eps, fused=fused_ln)
     for i in range(cfg.n_layer):
         p = f"{g}layers.{i}."
