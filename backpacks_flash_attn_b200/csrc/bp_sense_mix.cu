@@ -1,0 +1,592 @@
+// Backpack sense-mix for sm_100a:
+//     out[b,i,:] = sum_l sum_{j<=i} softmax_j(scale * q_li . k_lj) * C_l(x_j)[:]
+//
+// The reference runs this as un-fused PyTorch (training/src/models/backpack.py:111-122 + :313): it
+// materialises alpha (b,nv,s,s) and alpha@C (b,nv,s,d) in HBM (~17.8 GB of traffic at config 3) and does
+// the dense (non-causal) batched GEMM.  Here it is two tcgen05 kernels that never materialise alpha:
+//
+//   pass 1  sense_lse_kernel : per (b, l, i) log-sum-exp of the causal scores (S = Q_l K_l^T on the tensor
+//           core, online max/sum by one thread per row).  4 B per (b,l,i) of output.
+//   pass 2  sense_mix_kernel : recomputes S, forms the *normalised* probabilities P = exp2(S*c - lse) (so
+//           no running max, no rescaling, and every sense can be added into ONE accumulator), and issues
+//           O += P C_l over all senses l and causal key blocks j into a single TMEM accumulator.
+//
+// Normalising per sense needs the row statistics before the first P.C product, hence two passes; pass 1
+// costs 1/17 of the MMA work.  The accumulator of a 128-row tile at d=768 is 384 KB fp32 -- more than
+// the 256 KB of TMEM -- so one CTA owns a 384-column chunk of the output (O: 384 TMEM columns, S: 2 x 64).
+// Layout per CTA (384 threads): warp 0 = TMA producer for C, warp 3 = TMA producer for Q_l / K_l,
+// warp 1 = MMA issuer, warp 2 = TMEM allocator, warpgroups 1/2 = softmax for even/odd steps + epilogue.
+// C_l(x_j) tiles are consumed as MN-major B operands exactly as TMA wrote them (no transpose).
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace sense {
+
+constexpr int BM = 128;
+constexpr int kThreads = 384;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// =============================================================================================
+// pass 1: row statistics
+// =============================================================================================
+template <int PK>  // 64-column panels covering dk
+struct LseCfg {
+  static constexpr int BN = 128;
+  static constexpr int kStages = 4;
+  static constexpr uint32_t kQTileBytes = BM * 128 * PK;
+  static constexpr uint32_t kKTileBytes = BN * 128 * PK;
+  static constexpr uint32_t offQ = 0;
+  static constexpr uint32_t offK = offQ + 2 * kQTileBytes;
+  static constexpr uint32_t offBar = offK + kStages * kKTileBytes;
+  static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+  static constexpr uint32_t kTmemCols = 512;  // S_t[buf] at (t*2+buf)*128
+};
+
+struct LseBarriers {
+  uint64_t q_full;
+  uint64_t k_full[4], k_empty[4];
+  uint64_t s_full[2][2], s_free[2][2];
+  uint32_t tmem_base;
+};
+
+struct LseParams {
+  float* lse;  // (b, nv, s)
+  int32_t seqlen, nv, dk, ksteps, num_pairs;
+  float scale, scale_log2;
+};
+
+template <int PK, bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
+  using C = LseCfg<PK>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  LseBarriers& bars = *reinterpret_cast<LseBarriers*>(smem + C::offBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = p.num_pairs - 1 - static_cast<int>(blockIdx.x);
+  const int sense = blockIdx.y, batch = blockIdx.z;
+  const int S = p.seqlen;
+  const int row0 = pair * 2 * BM;
+  int n_blk[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r0 = row0 + t * BM;
+    n_blk[t] = r0 < S ? (min(S, r0 + BM) + BN - 1) / BN : 0;
+  }
+  const int n_max = max(n_blk[0], n_blk[1]);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    mbar_init(&bars.q_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
+    for (int t = 0; t < 2; ++t)
+      for (int i = 0; i < 2; ++i) mbar_init(&bars.s_full[t][i], 1), mbar_init(&bars.s_free[t][i], 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars.tmem_base, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+  const int tok0 = batch * S;  // first row of this batch in the flattened (b*s) token dimension
+
+  if (warp < 4) {
+    reg_dealloc<56>();
+    if (warp == 0) {
+      // ---- producer: Q tiles of both query tiles (coordinate 1 = which*nv + sense), K ring ----
+      const int n_q_tiles = (row0 + BM < S) ? 2 : 1;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars.q_full, n_q_tiles * C::kQTileBytes);
+        for (int t = 0; t < n_q_tiles; ++t)
+          for (int pn = 0; pn < PK; ++pn)
+            tma_load_3d(smem + C::offQ + t * C::kQTileBytes + pn * (BM * 128), &tmQK, &bars.q_full, pn * 64, sense,
+                        tok0 + row0 + t * BM);
+      }
+      for (int j = 0; j < n_max; ++j) {
+        const int slot = j % C::kStages;
+        if (j >= C::kStages) mbar_wait(&bars.k_empty[slot], ((j / C::kStages) - 1) & 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKTileBytes);
+          for (int pn = 0; pn < PK; ++pn)
+            tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmQK, &bars.k_full[slot], pn * 64,
+                        p.nv + sense, tok0 + j * BN);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---- MMA issuer: S_t(j) into buffer j&1 of tile t ----
+      constexpr uint32_t idesc = make_idesc(kBF16, BM, BN, false, false);
+      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
+      auto last_user = [&](int j) { return j < n_blk[1] ? 1 : 0; };
+      mbar_wait(&bars.q_full, 0);
+      for (int j = 0; j < n_max; ++j) {
+        const int slot = j % C::kStages;
+        mbar_wait(&bars.k_full[slot], (j / C::kStages) & 1);
+        for (int t = 0; t < 2; ++t) {
+          if (j >= n_blk[t]) continue;
+          if (j >= 2) mbar_wait(&bars.s_free[t][j & 1], ((j >> 1) - 1) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            for (int kk = 0; kk < p.ksteps; ++kk) {
+              const uint32_t a = sQ + t * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+              const uint32_t b = sK + slot * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
+              umma_ss(tmem_base + (t * 2 + (j & 1)) * BN, make_smem_desc_sw128(a, 16, 1024),
+                      make_smem_desc_sw128(b, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+            }
+            if (t == last_user(j)) umma_commit(&bars.k_empty[slot]);
+            umma_commit(&bars.s_full[t][j & 1]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    reg_alloc<224>();
+    const int t = (warp >> 2) - 1;
+    const int r = (warp & 3) * 32 + lane;
+    const int n = n_blk[t];
+    if (n > 0) {
+      const int qrow = row0 + t * BM + r;
+      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const float c2 = p.scale_log2;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < n; ++j) {
+        mbar_wait(&bars.s_full[t][j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        float s[BN];
+        const uint32_t tS = tmem_base + lane_addr + (t * 2 + (j & 1)) * BN;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t u[32];
+          tmem_ld32(tS + c * 32, u);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(u[i]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.s_free[t][j & 1]);
+        const int col0 = j * BN;
+        if (col0 + BN - 1 > row0 + t * BM) {  // block touches the diagonal (also covers cols >= seqlen)
+#pragma unroll
+          for (int c = 0; c < BN; ++c)
+            if (col0 + c > qrow) s[c] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int c = 1; c < BN; ++c) mx = fmaxf(mx, s[c]);
+        const float m_new = fmaxf(m, mx);  // column 0 is always visible, so m_new is finite
+        const float neg = -m_new * c2;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < BN; ++c) sum += fast_exp2(fmaf(s[c], c2, neg));
+        l = l * fast_exp2((m - m_new) * c2) + sum;
+        m = m_new;
+      }
+      if (qrow < S)
+        p.lse[(static_cast<int64_t>(batch) * p.nv + sense) * S + qrow] = m * p.scale + logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// =============================================================================================
+// pass 2: O += P_l C_l over senses and key blocks
+// =============================================================================================
+template <int PK>
+struct MixCfg {
+  static constexpr int BN = 64;    // keys per step
+  static constexpr int DC = 384;   // output columns per CTA (TMEM: 384 for O + 2 x 64 for S)
+  static constexpr int QS = PK == 1 ? 2 : 1;
+  static constexpr int KS = 2;
+  static constexpr int CS = PK == 1 ? 3 : 2;
+  static constexpr uint32_t kQTileBytes = BM * 128 * PK;
+  static constexpr uint32_t kKTileBytes = BN * 128 * PK;
+  static constexpr uint32_t kCPanelBytes = BN * 128;           // 64 keys x 64 columns
+  static constexpr uint32_t kCTileBytes = (DC / 64) * kCPanelBytes;
+  static constexpr uint32_t kPTileBytes = BM * BN * 2;
+  static constexpr uint32_t offQ = 0;
+  static constexpr uint32_t offK = offQ + QS * kQTileBytes;
+  static constexpr uint32_t offC = offK + KS * kKTileBytes;
+  static constexpr uint32_t offP = offC + CS * kCTileBytes;
+  static constexpr uint32_t offBar = offP + 2 * kPTileBytes;
+  static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+  static constexpr uint32_t colO = 0, colS = DC;
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct MixBarriers {
+  uint64_t q_full[2], q_empty[2];
+  uint64_t k_full[2], k_empty[2];
+  uint64_t c_full[3], c_empty[3];
+  uint64_t s_full[2], p_ready[2], p_free[2];
+  uint64_t o_full;
+  uint32_t tmem_base;
+};
+
+struct MixParams {
+  const float* lse;  // (b, nv, s), natural log
+  void* out;         // (b, s, d)
+  int32_t seqlen, nv, dk, ksteps, d, num_qtiles, num_chunks;
+  int32_t c_sense_inner;  // content tensor-map dims are (d, nv, s, b) instead of (d, s, nv, b)
+  float scale_log2;
+};
+
+template <int PK, bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmC, const MixParams p) {
+  using C = MixCfg<PK>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  MixBarriers& bars = *reinterpret_cast<MixBarriers*>(smem + C::offBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = p.num_qtiles - 1 - static_cast<int>(blockIdx.x) / p.num_chunks;  // heaviest first
+  const int chunk = static_cast<int>(blockIdx.x) % p.num_chunks;
+  const int batch = blockIdx.y;
+  const int S = p.seqlen;
+  const int row0 = qtile * BM;
+  const int nj = (min(S, row0 + BM) + BN - 1) / BN;  // causal key blocks of this query tile
+  const int n_steps = p.nv * nj;                      // step n = sense * nj + j
+  const int col_base = chunk * C::DC;
+  const int ncols = min(C::DC, p.d - col_base);       // multiple of 64
+  const int n1 = min(ncols, 256), n2 = ncols - n1;    // the two MMA N extents per k-step
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
+      mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
+      mbar_init(&bars.s_full[i], 1), mbar_init(&bars.p_ready[i], 128), mbar_init(&bars.p_free[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&bars.c_full[i], 1), mbar_init(&bars.c_empty[i], 1);
+    mbar_init(&bars.o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars.tmem_base, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+  const int tok0 = batch * S;
+
+  if (warp < 4) {
+    reg_dealloc<56>();
+    if (warp == 0) {
+      // ---- producer A: content tiles C_l[j] : (ncols/64) panels of [64 keys x 64 columns] ----
+      for (int n = 0; n < n_steps; ++n) {
+        const int slot = n % C::CS;
+        if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
+        if (lane == 0) {
+          const int sense = n / nj, j = n - sense * nj;
+          mbar_arrive_expect_tx(&bars.c_full[slot], (ncols / 64) * C::kCPanelBytes);
+          for (int pn = 0; pn < ncols / 64; ++pn) {
+            uint8_t* dst = smem + C::offC + slot * C::kCTileBytes + pn * C::kCPanelBytes;
+            if (p.c_sense_inner)
+              tma_load_4d(dst, &tmC, &bars.c_full[slot], col_base + pn * 64, sense, j * BN, batch);
+            else
+              tma_load_4d(dst, &tmC, &bars.c_full[slot], col_base + pn * 64, j * BN, sense, batch);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 3) {
+      // ---- producer B: Q_l (once per sense) and K_l[j] ----
+      for (int n = 0; n < n_steps; ++n) {
+        const int sense = n / nj, j = n - sense * nj;
+        if (j == 0) {
+          const int qs = sense % C::QS;
+          if (sense >= C::QS) mbar_wait(&bars.q_empty[qs], ((sense / C::QS) - 1) & 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&bars.q_full[qs], C::kQTileBytes);
+            for (int pn = 0; pn < PK; ++pn)
+              tma_load_3d(smem + C::offQ + qs * C::kQTileBytes + pn * (BM * 128), &tmQ, &bars.q_full[qs], pn * 64,
+                          sense, tok0 + row0);
+          }
+        }
+        const int slot = n % C::KS;
+        if (n >= C::KS) mbar_wait(&bars.k_empty[slot], ((n / C::KS) - 1) & 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKTileBytes);
+          for (int pn = 0; pn < PK; ++pn)
+            tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmK, &bars.k_full[slot], pn * 64,
+                        p.nv + sense, tok0 + j * BN);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---- MMA issuer ----
+      constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
+      const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
+      const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
+      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
+      const uint32_t sC = smem_u32(smem + C::offC), sP = smem_u32(smem + C::offP);
+
+      auto issue_s = [&](int n) {
+        const int sense = n / nj, j = n - sense * nj;
+        const int qs = sense % C::QS, ks = n % C::KS;
+        if (j == 0) mbar_wait(&bars.q_full[qs], (sense / C::QS) & 1);
+        mbar_wait(&bars.k_full[ks], (n / C::KS) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int kk = 0; kk < p.ksteps; ++kk) {
+            const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+            const uint32_t b = sK + ks * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
+            umma_ss(tmem_base + C::colS + (n & 1) * BN, make_smem_desc_sw128(a, 16, 1024),
+                    make_smem_desc_sw128(b, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&bars.k_empty[ks]);
+          if (j == nj - 1) umma_commit(&bars.q_empty[qs]);
+          umma_commit(&bars.s_full[n & 1]);
+        }
+        __syncwarp();
+      };
+
+      issue_s(0);
+      if (n_steps > 1) issue_s(1);
+      for (int n = 0; n < n_steps; ++n) {
+        mbar_wait(&bars.p_ready[n & 1], (n >> 1) & 1);
+        tc_fence_after();
+        if (n + 2 < n_steps) issue_s(n + 2);
+        const int cs = n % C::CS;
+        mbar_wait(&bars.c_full[cs], (n / C::CS) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = sP + (n & 1) * C::kPTileBytes;
+          const uint32_t b_base = sC + cs * C::kCTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint64_t a = make_smem_desc_sw128(a_base + kk * 32, 16, 1024);
+            umma_ss(tmem_base + C::colO, a, make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024),
+                    idesc_pv1, (n > 0 || kk > 0) ? 1u : 0u);
+            if (n2 > 0)
+              umma_ss(tmem_base + C::colO + 256, a,
+                      make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024), idesc_pv2,
+                      (n > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars.c_empty[cs]);
+          umma_commit(&bars.p_free[n & 1]);
+          if (n == n_steps - 1) umma_commit(&bars.o_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- softmax warpgroups: w handles steps n = 2i + w ----
+    reg_alloc<224>();
+    const int w = (warp >> 2) - 1;
+    const int r = (warp & 3) * 32 + lane;
+    const int qrow = row0 + r;
+    const bool valid = qrow < S;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + C::colS + w * BN;
+    uint8_t* sP = smem + C::offP + w * C::kPTileBytes;
+    const float c2 = p.scale_log2;
+    const float* lse_row = p.lse + static_cast<int64_t>(batch) * p.nv * S + (valid ? qrow : S - 1);
+    int cur_sense = -1;
+    float neg_lse2 = 0.f;
+    int i = 0;
+    for (int n = w; n < n_steps; n += 2, ++i) {
+      const int sense = n / nj, j = n - sense * nj;
+      if (sense != cur_sense) {
+        cur_sense = sense;
+        neg_lse2 = -__ldg(lse_row + static_cast<int64_t>(sense) * S) * kLog2e;
+      }
+      mbar_wait(&bars.s_full[w], i & 1);
+      tc_fence_after();
+      float s[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tS + c * 32, u);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[c * 32 + k] = __uint_as_float(u[k]);
+      }
+      tmem_ld_wait();
+      const int col0 = j * BN;
+      if (col0 + BN - 1 > row0) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c)
+          if (col0 + c > qrow) s[c] = -INFINITY;
+      }
+      if (i >= 1) mbar_wait(&bars.p_free[w], (i - 1) & 1);  // PV of step n-2 has drained this P tile
+#pragma unroll
+      for (int c8 = 0; c8 < BN / 8; ++c8) {
+        float e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = fast_exp2(fmaf(s[c8 * 8 + k], c2, neg_lse2));
+        uint4 v;
+        v.x = pack2<kBF16>(e[0], e[1]);
+        v.y = pack2<kBF16>(e[2], e[3]);
+        v.z = pack2<kBF16>(e[4], e[5]);
+        v.w = pack2<kBF16>(e[6], e[7]);
+        *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bars.p_ready[w]);
+    }
+    // ---- epilogue: warpgroup w stores columns [w*ncols/2, (w+1)*ncols/2) of its row ----
+    mbar_wait(&bars.o_full, 0);
+    tc_fence_after();
+    const int half_cols = ncols / 2;  // multiple of 32
+    const uint32_t tO = tmem_base + lane_addr + C::colO + w * half_cols;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
+                    2 * ((static_cast<int64_t>(tok0) + qrow) * p.d + col_base + w * half_cols);
+    for (int c = 0; c < half_cols / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack2<kBF16>(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+          v.y = pack2<kBF16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+          v.z = pack2<kBF16>(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+          v.w = pack2<kBF16>(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(orow + (c * 32 + g * 8) * 2) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int make_qk_map(CUtensorMap* tm, const void* qk, int batch, int seqlen, int nv, int dk, int dtype,
+                       int box_rows) {
+  // qk (b, s, 2, nv, dk) viewed as [dk, 2*nv, b*s]; panels beyond dk are zero-filled by TMA
+  const uint64_t dims[3] = {(uint64_t)dk, (uint64_t)2 * nv, (uint64_t)batch * seqlen};
+  const uint64_t str[2] = {(uint64_t)dk * 2, (uint64_t)2 * nv * dk * 2};
+  const uint32_t box[3] = {64, 1, (uint32_t)box_rows};
+  return encode_tensor_map(tm, dtype, 3, qk, dims, str, box, true);
+}
+
+static int check_common(const char* fn, int batch, int seqlen, int nv, int dk, int dtype) {
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: only fp16 and bf16 are supported", fn);
+  if (batch <= 0 || seqlen <= 0 || nv <= 0 || dk <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "%s: empty input", fn);
+  if (dk % 8 != 0)
+    return fail(BP_ERR_UNSUPPORTED, "%s: sense key width d/nv = %d must be a multiple of 8 (TMA 16-byte stride rule)", fn, dk);
+  if (dk > 192) return fail(BP_ERR_UNSUPPORTED, "%s: sense key width %d > 192 is not supported", fn, dk);
+  if ((int64_t)batch * seqlen > 0x7fffffff / 2) return fail(BP_ERR_INVALID_ARGUMENT, "%s: batch*seqlen too large", fn);
+  return BP_OK;
+}
+
+template <int PK, bool kBF16>
+static int launch_lse(const CUtensorMap& tm, const LseParams& p, int batch, cudaStream_t st) {
+  using C = LseCfg<PK>;
+  auto kern = sense_lse_kernel<PK, kBF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_sense_lse_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  kern<<<dim3(p.num_pairs, p.nv, batch), kThreads, C::kSmemBytes, st>>>(tm, p);
+  return check_launch("bp_sense_lse_fwd launch");
+}
+
+template <int PK, bool kBF16>
+static int launch_mix(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmC, const MixParams& p,
+                      int batch, cudaStream_t st) {
+  using C = MixCfg<PK>;
+  auto kern = sense_mix_kernel<PK, kBF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_sense_mix_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  kern<<<dim3(p.num_qtiles * p.num_chunks, batch), kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmC, p);
+  return check_launch("bp_sense_mix_fwd launch");
+}
+
+}  // namespace sense
+}  // namespace bp
+
+extern "C" int bp_sense_lse_fwd(const void* qk, float* lse, int32_t batch, int32_t seqlen, int32_t nv, int32_t dk,
+                                float softmax_scale, int32_t dtype, void* stream) {
+  using namespace bp;
+  if (!qk || !lse) return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_lse_fwd: null pointer argument");
+  if (int rc = sense::check_common("bp_sense_lse_fwd", batch, seqlen, nv, dk, dtype)) return rc;
+  CUtensorMap tm;
+  if (int rc = sense::make_qk_map(&tm, qk, batch, seqlen, nv, dk, dtype, 128)) return rc;
+  sense::LseParams p;
+  p.lse = lse;
+  p.seqlen = seqlen, p.nv = nv, p.dk = dk, p.ksteps = (dk + 15) / 16;
+  p.num_pairs = (seqlen + 255) / 256;
+  p.scale = softmax_scale, p.scale_log2 = softmax_scale * sense::kLog2e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int pk = (dk + 63) / 64;
+  const bool bf = dtype == BP_DTYPE_BF16;
+  switch (pk) {
+    case 1: return bf ? sense::launch_lse<1, true>(tm, p, batch, st) : sense::launch_lse<1, false>(tm, p, batch, st);
+    case 2: return bf ? sense::launch_lse<2, true>(tm, p, batch, st) : sense::launch_lse<2, false>(tm, p, batch, st);
+    default: return bf ? sense::launch_lse<3, true>(tm, p, batch, st) : sense::launch_lse<3, false>(tm, p, batch, st);
+  }
+}
+
+extern "C" int bp_sense_mix_fwd(const void* qk, const void* content, const float* lse, void* out, int32_t batch,
+                                int32_t seqlen, int32_t nv, int32_t dk, int32_t d, int64_t c_batch_stride,
+                                int64_t c_sense_stride, int64_t c_row_stride, float softmax_scale, int32_t dtype,
+                                void* stream) {
+  using namespace bp;
+  if (!qk || !content || !lse || !out) return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_mix_fwd: null pointer argument");
+  if (int rc = sense::check_common("bp_sense_mix_fwd", batch, seqlen, nv, dk, dtype)) return rc;
+  if (d <= 0 || d % 64 != 0)
+    return fail(BP_ERR_UNSUPPORTED, "bp_sense_mix_fwd: model width d = %d must be a multiple of 64", d);
+  if (c_batch_stride % 8 || c_sense_stride % 8 || c_row_stride % 8 || c_row_stride < d)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_mix_fwd: content strides must be multiples of 8 elements with unit column stride");
+  if ((uintptr_t)content % 16 || (uintptr_t)qk % 16 || (uintptr_t)out % 16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_mix_fwd: pointers must be 16-byte aligned");
+  CUtensorMap tmQ, tmK, tmC;  // Q tiles are 128 rows, K tiles 64 rows: same tensor, two box heights
+  if (int rc = sense::make_qk_map(&tmQ, qk, batch, seqlen, nv, dk, dtype, 128)) return rc;
+  if (int rc = sense::make_qk_map(&tmK, qk, batch, seqlen, nv, dk, dtype, 64)) return rc;
+  // The reference hands content as a transposed view of (b, s, nv, d) (backpack.py:276), i.e. the sense
+  // stride is smaller than the row stride; keep the tensor-map dimensions ordered by increasing stride.
+  const bool sense_inner = c_sense_stride < c_row_stride;
+  if (sense_inner) {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)nv, (uint64_t)seqlen, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)c_sense_stride * 2, (uint64_t)c_row_stride * 2, (uint64_t)c_batch_stride * 2};
+    const uint32_t box[4] = {64, 1, 64, 1};
+    if (int rc = encode_tensor_map(&tmC, dtype, 4, content, dims, str, box, true)) return rc;
+  } else {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)seqlen, (uint64_t)nv, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)c_row_stride * 2, (uint64_t)c_sense_stride * 2, (uint64_t)c_batch_stride * 2};
+    const uint32_t box[4] = {64, 64, 1, 1};
+    if (int rc = encode_tensor_map(&tmC, dtype, 4, content, dims, str, box, true)) return rc;
+  }
+  sense::MixParams p;
+  p.c_sense_inner = sense_inner ? 1 : 0;
+  p.lse = lse;
+  p.out = out;
+  p.seqlen = seqlen, p.nv = nv, p.dk = dk, p.ksteps = (dk + 15) / 16, p.d = d;
+  p.num_qtiles = (seqlen + sense::BM - 1) / sense::BM;
+  p.num_chunks = (d + 383) / 384;
+  p.scale_log2 = softmax_scale * sense::kLog2e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int pk = (dk + 63) / 64;
+  const bool bf = dtype == BP_DTYPE_BF16;
+  switch (pk) {
+    case 1: return bf ? sense::launch_mix<1, true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix<1, false>(tmQ, tmK, tmC, p, batch, st);
+    case 2: return bf ? sense::launch_mix<2, true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix<2, false>(tmQ, tmK, tmC, p, batch, st);
+    default: return bf ? sense::launch_mix<3, true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix<3, false>(tmQ, tmK, tmC, p, batch, st);
+  }
+}

@@ -184,6 +184,19 @@ def sense_sum(alpha: Tensor, content: Tensor) -> Tensor:
     return torch.sum(alpha @ content, dim=1)
 
 
+def sense_mix_eager(qk: Tensor, content: Tensor) -> Tensor:
+    """The reference's own composition from the projected (q, k) on (backpack.py:116-122 + :313), in the
+    tensors' dtype: k pre-scaled, additive -10000 mask, softmax in that dtype, alpha @ content, sum over
+    senses.  qk (b, s, 2, nv, dk); content (b, nv, s, d)."""
+    q, k = qk.unbind(dim=2)
+    s = qk.shape[1]
+    scale = 1.0 / math.sqrt(q.shape[-1])
+    scores = torch.einsum("bthd,bshd->bhts", q, k * scale)
+    scores = scores + torch.full((s, s), MASK_VALUE, device=scores.device).triu(1).to(scores.dtype)
+    alpha = torch.softmax(scores, dim=-1, dtype=q.dtype)
+    return torch.sum(alpha @ content, dim=1)
+
+
 def sense_mix_fp32_ref(qk: Tensor, content: Tensor, softmax_scale: Optional[float] = None
                        ) -> tuple[Tensor, Tensor]:
     """fp32 judge for the fused sense-mix operator: exact causal softmax (-inf mask, scale

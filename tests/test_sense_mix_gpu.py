@@ -1,0 +1,108 @@
+"""GPU parity of the fused sense-mix (bp_sense_lse_fwd + bp_sense_mix_fwd) against the oracle.
+
+The reference has no test for this operator; the criterion is the one its fmha tests use:
+    max|ours - fp32| <= 2 * max|reference eager in the same precision - fp32|
+with the eager composition restated from backpack.py:116-122 + :313 and pinned by tests/golden/ops.npz.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backpack_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(b, s, nv, d, dtype, seed=0, transposed=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    qk = torch.randn(b, s, 2, nv, d // nv, device="cuda", generator=g).to(dtype)
+    if transposed:   # the layout the reference's content model returns (backpack.py:276)
+        content = torch.randn(b, s, nv, d, device="cuda", generator=g).to(dtype).transpose(1, 2)
+    else:
+        content = torch.randn(b, nv, s, d, device="cuda", generator=g).to(dtype)
+    return qk, content
+
+
+def _check(qk, content):
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    out, lse = sense_mix(qk, content, return_lse=True)
+    ref, lse_ref = O.sense_mix_fp32_ref(qk, content)
+    eager = O.sense_mix_eager(qk, content)
+    err, err_eager = O.max_abs(out, ref), O.max_abs(eager, ref)
+    assert O.max_abs(lse, lse_ref) < 1e-3
+    assert err <= 2 * err_eager + 1e-5, f"max err {err:.3e} vs eager {err_eager:.3e}"
+    assert O.mean_abs(out, ref) <= 2 * O.mean_abs(eager, ref) + 1e-6
+    return err, err_eager
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("s", [64, 97, 128, 200, 256, 257, 512, 1024])
+@pytest.mark.parametrize("nv,d", [(16, 768), (16, 384), (4, 768), (8, 128), (1, 64)])
+def test_sense_mix_matches_oracle(s, nv, d, dtype):
+    qk, content = _inputs(2, s, nv, d, dtype, seed=s + nv)
+    _check(qk, content)
+
+
+def test_sense_mix_contiguous_content_and_determinism():
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    qk, content = _inputs(3, 384, 16, 768, torch.bfloat16, seed=5, transposed=False)
+    _check(qk, content)
+    first = sense_mix(qk, content)
+    for _ in range(5):
+        assert torch.equal(first, sense_mix(qk, content))
+    # same values through the transposed layout give bit-identical output
+    c2 = content.transpose(1, 2).contiguous().transpose(1, 2)
+    assert torch.equal(first, sense_mix(qk, c2))
+
+
+def test_sense_mix_linearity_in_content():
+    """Size-independent property: the operator is linear in `content` (what the intervention wrappers
+    rely on, intervened_models.py:78-101): mix(qk, a*C1 + C2) == a*mix(qk, C1) + mix(qk, C2) up to rounding."""
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    qk, c1 = _inputs(2, 512, 16, 768, torch.bfloat16, seed=11)
+    _, c2 = _inputs(2, 512, 16, 768, torch.bfloat16, seed=12)
+    lhs = sense_mix(qk, (2.0 * c1 + c2))
+    rhs = 2.0 * sense_mix(qk, c1).float() + sense_mix(qk, c2).float()
+    assert (lhs.float() - rhs).abs().max() < 0.25 and (lhs.float() - rhs).abs().mean() < 1e-2
+    zero = sense_mix(qk, torch.zeros_like(c1))
+    assert zero.abs().max() == 0
+
+
+def test_sense_mix_rows_of_alpha_sum_to_one():
+    """content == 1 everywhere  =>  out == nv (every alpha row sums to one, for every sense)."""
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    qk, c = _inputs(2, 1024, 16, 768, torch.bfloat16, seed=13)
+    out = sense_mix(qk, torch.ones_like(c))
+    assert (out.float() - 16.0).abs().max() < 0.15
+
+
+def test_sense_mix_golden_reference_fixture(golden_dir):
+    """Fixture generated from the real reference (tests/golden/make_golden.py): ContextSelfAttn -> sense sum."""
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    g = np.load(f"{golden_dir}/ops.npz")
+    h, w, b = (torch.from_numpy(g[k]).cuda() for k in ("ctx_h", "ctx_w", "ctx_b"))
+    content = torch.from_numpy(g["ctx_content_bsnd"]).cuda().transpose(1, 2)
+    qk = torch.nn.functional.linear(h, w, b).reshape(2, 64, 2, 8, 16)
+    out = sense_mix(qk.bfloat16(), content.bfloat16())
+    ref = torch.from_numpy(g["ctx_sense_sum"]).cuda()
+    eager = O.sense_mix_eager(qk.bfloat16(), content.bfloat16())
+    assert O.max_abs(out, ref) <= 2 * O.max_abs(eager, ref) + 1e-5
+
+
+def test_sense_mix_config3_shape():
+    """BASELINE config 3 operator shape (b=64 is exercised by bench.py; b=8 keeps the oracle cheap)."""
+    qk, content = _inputs(8, 1024, 16, 768, torch.bfloat16, seed=3)
+    err, err_eager = _check(qk, content)
+    print(f"sense-mix s1024 k16 d768: max err {err:.3e} (eager bf16 reference {err_eager:.3e})")
+
+
+def test_sense_mix_rejects_bad_arguments():
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    qk, content = _inputs(1, 64, 16, 768, torch.bfloat16)
+    with pytest.raises(RuntimeError, match="same dtype"):
+        sense_mix(qk, content.half())
+    with pytest.raises(RuntimeError, match="content must be"):
+        sense_mix(qk, content[:, :8])
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        sense_mix(torch.zeros(1, 64, 2, 64, 12, device="cuda", dtype=torch.bfloat16),
+                  torch.zeros(1, 64, 64, 768, device="cuda", dtype=torch.bfloat16))
