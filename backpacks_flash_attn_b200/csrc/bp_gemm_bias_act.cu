@@ -1,0 +1,253 @@
+// out = act(x W^T + bias) for sm_100a: persistent, warp-specialised tcgen05 GEMM with a fused epilogue.
+//
+// Replaces fused_dense_lib.linear_gelu_forward (csrc/fused_dense_lib/fused_dense.cpp:88-142, a cuBLASLt
+// matmul with the GELU_BIAS epilogue, fused_dense_cuda.cu:97-216) for the forward pass.  x is (m, k)
+// row-major and W is (n, k) row-major (nn.Linear layout), so both operands are K-major and feed UMMA
+// straight from 128B-swizzled TMA tiles.
+//
+//   CTA tile 128 x 256, K step 64, 3-stage TMA ring (48 KB per stage), fp32 accumulator in TMEM,
+//   two accumulator buffers (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+//   (tcgen05.ld -> + bias -> tanh-GELU -> bf16/f16 -> swizzled smem -> TMA store, 64 columns at a time).
+//   Persistent grid = #SMs; tiles are walked n-fastest so the CTAs running together share rows of x
+//   while W stays L2-resident.
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace gemm {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kStages = 3;
+constexpr int kThreads = 256;
+constexpr uint32_t kABytes = BM * BK * 2;          // 16 KB
+constexpr uint32_t kBBytes = BN * BK * 2;          // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kOutChunkBytes = BM * 64 * 2;   // 128 rows x 64 columns staging (16 KB)
+constexpr uint32_t offOut = kStages * kStageBytes;
+constexpr uint32_t offBar = offOut + 2 * kOutChunkBytes;
+constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+constexpr uint32_t kTmemCols = 512;
+
+struct Barriers {
+  uint64_t full[kStages], empty[kStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct Params {
+  const void* bias;  // (n) or null
+  int64_t m;
+  int32_t n, k;
+  int32_t m_tiles, n_tiles, k_blocks;
+  int32_t act;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.f + t);
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers& bars = *reinterpret_cast<Barriers*>(smem + offBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t num_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars.full[i], 1), mbar_init(&bars.empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars.tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = static_cast<int>(tile / p.n_tiles) * BM;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t slot = it % kStages;
+        if (it >= kStages) mbar_wait(&bars.empty[slot], ((it / kStages) - 1) & 1);
+        if (lane == 0) {
+          uint8_t* a = smem + slot * kStageBytes;
+          mbar_arrive_expect_tx(&bars.full[slot], kStageBytes);
+          tma_load_2d(a, &tmA, &bars.full[slot], kb * BK, m0);
+          tma_load_2d(a + kABytes, &tmB, &bars.full[slot], kb * BK, n0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(kBF16, BM, BN, false, false);
+    uint32_t it = 0, local = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t buf = local & 1;
+      if (local >= 2) mbar_wait(&bars.acc_empty[buf], ((local >> 1) - 1) & 1);
+      tc_fence_after();
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t slot = it % kStages;
+        mbar_wait(&bars.full[slot], (it / kStages) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a = smem_u32(smem + slot * kStageBytes);
+          const uint32_t b = a + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_ss(tmem_base + buf * BN, make_smem_desc_sw128(a + kk * 32, 16, 1024),
+                    make_smem_desc_sw128(b + kk * 32, 16, 1024), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&bars.empty[slot]);
+          if (kb == p.k_blocks - 1) umma_commit(&bars.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int r = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const bool leader = threadIdx.x == 128;
+    uint32_t local = 0, chunk_it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m0 = static_cast<int>(tile / p.n_tiles) * BM;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * BN;
+      const uint32_t buf = local & 1;
+      mbar_wait(&bars.acc_full[buf], (local >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_it) {
+        if (n0 + c64 * 64 >= p.n) break;  // uniform: whole 64-column chunk outside the matrix
+        uint8_t* stage = smem + offOut + (chunk_it & 1) * kOutChunkBytes;
+        // the TMA store that last read this staging buffer (two chunks ago) must have finished reading
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_addr + buf * BN + c64 * 64 + h * 32, v);
+          tmem_ld_wait();
+          const int col = n0 + c64 * 64 + h * 32;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+            const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              if (col + i < p.n) {  // n % 8 == 0, so pairs are all-or-nothing
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + i));
+                if constexpr (kBF16) {
+                  f[i] += __uint_as_float(w << 16);
+                  f[i + 1] += __uint_as_float(w & 0xFFFF0000u);
+                } else {
+                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                  f[i] += t.x;
+                  f[i + 1] += t.y;
+                }
+              }
+            }
+          }
+          if (p.act == BP_ACT_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
+            w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
+            w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
+            w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(stage + sw128_offset(r, h * 4 + g)) = w;
+          }
+        }
+        if (c64 == BN / 64 - 1 || n0 + (c64 + 1) * 64 >= p.n) {
+          // last chunk of this accumulator: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&bars.acc_empty[buf]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (leader) {
+          tma_store_2d(&tmO, stage, n0 + c64 * 64, m0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (leader) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace gemm
+}  // namespace bp
+
+extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void* out, int64_t m,
+                                      int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream) {
+  using namespace bp;
+  if (!x || !w || !out) return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: null pointer argument");
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: only fp16 and bf16 are supported");
+  if (m <= 0 || n <= 0 || k <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: empty input");
+  if (n % 8 != 0 || k % 8 != 0)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: n and k must be multiples of 8 (got n=%d k=%d)", n, k);
+  if (m > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: m too large");
+  if (activation != BP_ACT_NONE && activation != BP_ACT_GELU_TANH)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: unknown activation %d", activation);
+  if ((uintptr_t)x % 16 || (uintptr_t)w % 16 || (uintptr_t)out % 16 || (uintptr_t)bias % 4)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t da[2] = {(uint64_t)k, (uint64_t)m}, sa[1] = {(uint64_t)k * 2};
+    const uint32_t ba[2] = {gemm::BK, gemm::BM};
+    if (int rc = encode_tensor_map(&tmA, dtype, 2, x, da, sa, ba, true)) return rc;
+    const uint64_t db[2] = {(uint64_t)k, (uint64_t)n};
+    const uint32_t bb[2] = {gemm::BK, gemm::BN};
+    if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sa, bb, true)) return rc;
+    const uint64_t dout[2] = {(uint64_t)n, (uint64_t)m}, so[1] = {(uint64_t)n * 2};
+    const uint32_t bo[2] = {64, gemm::BM};
+    if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
+  }
+  gemm::Params p;
+  p.bias = bias;
+  p.m = m, p.n = n, p.k = k;
+  p.m_tiles = static_cast<int32_t>((m + gemm::BM - 1) / gemm::BM);
+  p.n_tiles = (n + gemm::BN - 1) / gemm::BN;
+  p.k_blocks = (k + gemm::BK - 1) / gemm::BK;
+  p.act = activation;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto kern = dtype == BP_DTYPE_BF16 ? gemm::gemm_bias_act_kernel<true> : gemm::gemm_bias_act_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_linear_bias_act_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  kern<<<grid, gemm::kThreads, gemm::kSmemBytes, st>>>(tmA, tmB, tmO, p);
+  return check_launch("bp_linear_bias_act_fwd launch");
+}

@@ -33,7 +33,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <int PK>  // 64-column panels covering dk
 struct LseCfg {
   static constexpr int BN = 128;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = PK == 3 ? 2 : 4;
   static constexpr uint32_t kQTileBytes = BM * 128 * PK;
   static constexpr uint32_t kKTileBytes = BN * 128 * PK;
   static constexpr uint32_t offQ = 0;
@@ -41,6 +41,7 @@ struct LseCfg {
   static constexpr uint32_t offBar = offK + kStages * kKTileBytes;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
   static constexpr uint32_t kTmemCols = 512;  // S_t[buf] at (t*2+buf)*128
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct LseBarriers {

@@ -1,0 +1,96 @@
+"""`FusedDense` / `FusedDenseGeluDense` with the reference's interface (flash_attn/ops/fused_dense.py:116-129,
+357-402), forward only.
+
+* `FusedDense.forward` is a plain GEMM + bias in the reference too (F.linear, fused_dense.py:52,112): it
+  stays a library GEMM (cuBLASLt picks its own tcgen05 kernels on B200).
+* `FusedDenseGeluDense`: fc1 + bias + tanh-GELU is ONE kernel, bp_linear_bias_act_fwd -- the replacement of
+  fused_dense_lib.linear_gelu_forward (csrc/fused_dense_lib/fused_dense.cpp:88-142) -- followed by the fc2
+  library GEMM (fused_dense.py:225).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+
+
+def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
+                    activation: str = "gelu_tanh") -> torch.Tensor:
+    """act(x @ weight.T + bias) through the hand-written tcgen05 GEMM (weight in nn.Linear layout)."""
+    _lib.require_cuda(x, weight, bias)
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
+        raise RuntimeError("linear_bias_act needs fp16/bf16 activations and weights of the same dtype")
+    if bias is not None and bias.dtype != x.dtype:
+        raise RuntimeError("bias must have the activation dtype")
+    n, k = weight.shape
+    if x.shape[-1] != k:
+        raise RuntimeError("shape mismatch between x and weight")
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+    x2 = x.reshape(-1, k)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    weight = weight.contiguous()
+    out = torch.empty((x2.shape[0], n), dtype=x.dtype, device=x.device)
+    act = {"none": _lib.BP_ACT_NONE, "gelu_tanh": _lib.BP_ACT_GELU_TANH}[activation]
+    with torch.cuda.device(x.device):
+        st = _lib.load().bp_linear_bias_act_fwd(x2.data_ptr(), weight.data_ptr(), _lib.ptr(bias), out.data_ptr(),
+                                                x2.shape[0], n, k, act, _lib.dtype_code(x.dtype),
+                                                _lib.stream_ptr(x.device))
+    _lib.check(st, "bp_linear_bias_act_fwd")
+    return out.reshape(*x.shape[:-1], n)
+
+
+def fused_dense_func(x, weight, bias=None, return_residual=False, process_group=None):
+    if process_group is not None:
+        raise RuntimeError("tensor parallelism is out of scope for this path (batch sharding only)")
+    out = F.linear(x, weight, bias)
+    return out if not return_residual else (out, x)
+
+
+class FusedDense(nn.Linear):
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, return_residual: bool = False,
+                 device=None, dtype=None) -> None:
+        super().__init__(in_features, out_features, bias=bias, device=device, dtype=dtype)
+        self.return_residual = return_residual
+
+    def forward(self, x, process_group=None):
+        return fused_dense_func(x, self.weight, self.bias, return_residual=self.return_residual,
+                                process_group=process_group)
+
+
+def fused_dense_gelu_dense_func(x, weight1, weight2, bias1=None, bias2=None, save_pre_act=False,
+                                return_residual=False, checkpoint_lvl=0, heuristic=0, process_group=None):
+    """fc2(gelu_tanh(fc1(x))) (fused_dense.py:332-354); save_pre_act / checkpoint_lvl / heuristic only matter to
+    the reference's backward and cuBLASLt algo choice and are accepted for signature compatibility."""
+    if process_group is not None:
+        raise RuntimeError("tensor parallelism is out of scope for this path (batch sharding only)")
+    hidden = linear_bias_act(x, weight1, bias1, "gelu_tanh")
+    out = F.linear(hidden, weight2, bias2)
+    return out if not return_residual else (out, x)
+
+
+class FusedDenseGeluDense(nn.Module):
+
+    def __init__(self, in_features, hidden_features, out_features=None, bias1=True, bias2=True,
+                 return_residual=False, checkpoint_lvl=0, heuristic=0, device=None, dtype=None):
+        if checkpoint_lvl not in (0, 1, 2):
+            raise ValueError("checkpoint_lvl must be 0, 1 or 2")
+        factory_kwargs = {"device": device, "dtype": dtype}
+        super().__init__()
+        if out_features is None:
+            out_features = in_features
+        self.return_residual = return_residual
+        self.checkpoint_lvl = checkpoint_lvl
+        self.heuristic = heuristic
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=bias1, **factory_kwargs)
+        self.fc2 = nn.Linear(hidden_features, out_features, bias=bias2, **factory_kwargs)
+
+    def forward(self, x, process_group=None):
+        return fused_dense_gelu_dense_func(x, self.fc1.weight, self.fc2.weight, self.fc1.bias, self.fc2.bias,
+                                           save_pre_act=self.training, return_residual=self.return_residual,
+                                           checkpoint_lvl=self.checkpoint_lvl, heuristic=self.heuristic,
+                                           process_group=process_group)

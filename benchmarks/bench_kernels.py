@@ -1,0 +1,130 @@
+"""Kernel-level timings (CUDA events, rotating inputs larger than L2, median of N) with roofline fractions.
+
+    python benchmarks/bench_kernels.py [--which fmha,sense,ln,gemm] [--iters 20]
+
+Algorithmic work per launch follows SURVEY.md §8(d) / BASELINE.md §3.  Peaks come from MEASURED_PEAKS.json
+when present (else the fallback stated in B200_PROFILING.md).  Prints one JSON line per kernel.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def time_fn(fn, variants, iters, warmup=5):
+    """fn(i) runs variant i; variants rotate so that consecutive launches never see a warm L2."""
+    for i in range(warmup):
+        fn(i % variants)
+    torch.cuda.synchronize()
+    times = []
+    for i in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(i % variants)
+        b.record()
+        b.synchronize()
+        times.append(a.elapsed_time(b) * 1e-3)
+    return statistics.median(times), min(times)
+
+
+def report(name, t_med, t_min, flops, nbytes, extra=None):
+    hbm, tf_burst, tf_sus, src = peaks()
+    rec = {"kernel": name, "ms_median": t_med * 1e3, "ms_min": t_min * 1e3,
+           "tflops": flops / t_med / 1e12, "gbs": nbytes / t_med / 1e9,
+           "frac_tensor_burst": flops / t_med / 1e12 / tf_burst, "frac_hbm": nbytes / t_med / 1e9 / hbm,
+           "peaks": src}
+    if extra:
+        rec.update(extra)
+    print(json.dumps(rec))
+    return rec
+
+
+def bench_fmha(iters, b=32, s=1024, h=12, d=64):
+    from backpacks_flash_attn_b200.flash_attn_interface import flash_attn_unpadded_qkvpacked_func
+    nvar = 3  # 3 x 75 MB of qkv + outputs > 126 MB L2
+    qkvs = [torch.randn(b * s, 3, h, d, device="cuda").bfloat16() for _ in range(nvar)]
+    cu = torch.arange(0, (b + 1) * s, s, dtype=torch.int32, device="cuda")
+    fn = lambda i: flash_attn_unpadded_qkvpacked_func(qkvs[i], cu, s, 0.0, causal=True)
+    t_med, t_min = time_fn(fn, nvar, iters)
+    flops = 4 * b * h * s * s * d / 2
+    nbytes = 4 * b * s * h * d * 2 + 4 * b * h * s
+    return report(f"fmha_fwd b{b} h{h} s{s} d{d} causal bf16", t_med, t_min, flops, nbytes)
+
+
+def bench_sense(iters, b=64, s=1024, nv=16, d=768):
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    from backpacks_flash_attn_b200 import _lib
+    qk = torch.randn(b, s, 2, nv, d // nv, device="cuda").bfloat16()
+    content = torch.randn(b, s, nv, d, device="cuda").bfloat16().transpose(1, 2)   # 1.6 GB >> L2
+    fn = lambda i: sense_mix(qk, content)
+    t_med, t_min = time_fn(fn, 1, iters)
+    flops = b * s * s * d * (1 + nv)
+    nbytes = (2 * b * s * d + nv * b * s * d + b * s * d) * 2
+    rec = report(f"sense_mix(lse+mix) b{b} s{s} k{nv} d{d} bf16", t_med, t_min, flops, nbytes)
+    # split the two passes
+    lib = _lib.load()
+    lse = torch.empty(b, nv, s, device="cuda", dtype=torch.float32)
+    out = torch.empty(b, s, d, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    scale = (d // nv) ** -0.5
+    f1 = lambda i: lib.bp_sense_lse_fwd(qk.data_ptr(), lse.data_ptr(), b, s, nv, d // nv, scale, 1, st)
+    f2 = lambda i: lib.bp_sense_mix_fwd(qk.data_ptr(), content.data_ptr(), lse.data_ptr(), out.data_ptr(), b, s, nv,
+                                        d // nv, d, content.stride(0), content.stride(1), content.stride(2), scale, 1, st)
+    t1, _ = time_fn(f1, 1, iters)
+    t2, _ = time_fn(f2, 1, iters)
+    report("  sense_lse pass", t1, t1, b * nv * s * s * (d // nv), 2 * b * s * d * 2)
+    report("  sense_mix pass", t2, t2, b * s * s * d * (1 + nv), nbytes)
+    return rec
+
+
+def bench_ln(iters, rows=65536, cols=768):
+    from backpacks_flash_attn_b200.ops.layer_norm import dropout_add_layer_norm
+    nvar = 2
+    x0 = [torch.randn(rows, cols, device="cuda").bfloat16() for _ in range(nvar)]
+    x1 = [torch.randn(rows, cols, device="cuda") for _ in range(nvar)]
+    g = torch.ones(cols, device="cuda").bfloat16()
+    bta = torch.zeros(cols, device="cuda").bfloat16()
+    fn = lambda i: dropout_add_layer_norm(x0[i], x1[i], g, bta, 0.0, 1e-5, prenorm=True)
+    t_med, t_min = time_fn(fn, nvar, iters)
+    return report(f"ln_residual_fwd rows{rows} cols{cols}", t_med, t_min, 0, rows * cols * (2 + 4) * 2)
+
+
+def bench_gemm(iters, m=65536, n=3072, k=768):
+    from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_act
+    x = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * k ** -0.5).bfloat16()
+    bias = torch.randn(n, device="cuda").bfloat16()
+    fn = lambda i: linear_bias_act(x, w, bias, "gelu_tanh")
+    t_med, t_min = time_fn(fn, 1, iters)
+    rec = report(f"linear_bias_gelu m{m} n{n} k{k}", t_med, t_min, 2 * m * n * k, (m * k + n * k + m * n) * 2)
+    lib_fn = lambda i: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, bias), approximate="tanh")
+    t_lib, _ = time_fn(lib_fn, 1, iters)
+    report("  (cuBLAS F.linear + F.gelu, for comparison)", t_lib, t_lib, 2 * m * n * k, (m * k + n * k + 3 * m * n) * 2)
+    lin_fn = lambda i: torch.nn.functional.linear(x, w, bias)
+    t_lin, _ = time_fn(lin_fn, 1, iters)
+    report("  (cuBLAS F.linear only, for comparison)", t_lin, t_lin, 2 * m * n * k, (m * k + n * k + m * n) * 2)
+    return rec
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="fmha,sense,ln,gemm")
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    for w in a.which.split(","):
+        {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm}[w](a.iters)
