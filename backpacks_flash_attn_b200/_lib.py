@@ -59,9 +59,54 @@ def last_error() -> str:
     return load().bp_last_error().decode()
 
 
+# Every successful C-ABI call launches exactly one kernel of this library; bench.py reads these counters
+# for its `gpu_launches` claim.
+launch_counts: dict[str, int] = {}
+
+
 def check(status: int, what: str) -> None:
     if status != 0:
         raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+    launch_counts[what] = launch_counts.get(what, 0) + 1
+
+
+def total_launches() -> int:
+    return sum(launch_counts.values())
+
+
+class KernelTimer:
+    """Optional CUDA-event bracket around one C-ABI entry point (used by bench.py to time the dominant
+    kernel live inside the timed region, on the launching stream).  Usage:
+        with KernelTimer("bp_fmha_fwd") as t: ...run steps...;  t.mean_ms()"""
+
+    def __init__(self, name: str):
+        self.name = name
+        self.events: list = []
+        self._orig = None
+
+    def __enter__(self):
+        lib = load()
+        self._orig = getattr(lib, self.name)
+        orig, events = self._orig, self.events
+
+        def timed(*args):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            st = orig(*args)
+            b.record()
+            events.append((a, b))
+            return st
+
+        setattr(lib, self.name, timed)
+        return self
+
+    def __exit__(self, *exc):
+        setattr(load(), self.name, self._orig)
+        return False
+
+    def mean_ms(self) -> float:
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self.events) / max(1, len(self.events))
 
 
 def dtype_code(dtype: torch.dtype) -> int:

@@ -1,0 +1,201 @@
+"""Backpack language model with the reference's interface (training/src/models/backpack.py):
+`BackpackConfig` (:146-154), `ContextSelfAttn` (:94-122), `BackpackContentModule` (:207-276),
+`BackpackModel` (:278-314), `BackpackLMHeadModel` (:318-351).
+
+What differs from the reference is only HOW `BackpackModel.forward` evaluates
+`torch.sum(contextualization @ content, dim=1)` (:313): with `use_flash_attn` (or the explicit
+`fused_sense_mix` config attribute) the (b, nv, s, s) weights are never materialised -- the projected
+(q, k) of `ContextSelfAttn` and the content tensor go straight into the fused sense-mix kernels.  The
+sub-module API the analysis scripts use (training/src/models/intervened_models.py:77-101,
+training/src/run_simlex.py:179-184) is preserved: `transformer.gpt2_model(ids)`,
+`transformer.contextualization_attn(h) -> (b, nv, s, s)` (eager), `transformer.content_model(ids) ->
+(b, nv, s, d)`, and `transformer.sense_mix(h, content)` is offered for edited content tensors.
+State-dict keys are identical to the reference's.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+from transformers import GPT2Config
+
+from ..modules.block import Block
+from ..ops.fused_dense import FusedDense
+from ..ops.sense_mix import sense_mix
+from .gpt import (CausalLMOutput, GPTModel, GPTPreTrainedModel, _init_weights, _no_tp, create_mlp_cls,
+                  first_layer_norm, pad_vocab)
+
+
+class BackpackConfig(GPT2Config):
+
+    def __init__(self, num_content_vectors=16, **kwargs):
+        self.num_content_vectors = num_content_vectors
+        super().__init__(**kwargs)
+
+
+def create_content_mlp_cls(config, layer_idx=None, expand_out=False, process_group=None, device=None, dtype=None):
+    """MLP factory of the content model (backpack.py:53-92): inner = n_inner or 4d, or d when
+    `shrink_final_inner`; out = nv*d when expand_out else d."""
+    _no_tp(process_group)
+    inner_dim = config.n_inner if config.n_inner is not None else 4 * config.hidden_size
+    inner_dim = config.hidden_size if getattr(config, "shrink_final_inner", None) else inner_dim
+    outer_dim = config.num_content_vectors * config.hidden_size if expand_out else config.hidden_size
+    return create_mlp_cls(config, layer_idx, device=device, dtype=dtype, inner_dim=inner_dim, out_features=outer_dim)
+
+
+class ContextSelfAttn(nn.Module):
+    """num_content_vectors causal attention maps per token pair (backpack.py:94-122).
+    Parameter: Wqkv (embed_dim -> 2*embed_dim), q = first half, k = second half, split into nv senses."""
+
+    def __init__(self, num_content_vectors, embed_dim, device=None, dtype=None):
+        super().__init__()
+        self.Wqkv = FusedDense(embed_dim, 2 * embed_dim, device=device, dtype=dtype)
+        self.num_content_vectors = num_content_vectors
+        self.softmax_scale = None
+
+    def project_qk(self, encoded):
+        """(b, s, d) -> (b, s, 2, nv, d // nv)"""
+        b, s, d = encoded.shape
+        return self.Wqkv(encoded).reshape(b, s, 2, self.num_content_vectors, d // self.num_content_vectors)
+
+    def forward(self, encoded):
+        """Eager contextualisation weights alpha (b, nv, s, s), exactly the reference's composition."""
+        qk = self.project_qk(encoded)
+        s = qk.shape[1]
+        q, k = qk.unbind(dim=2)
+        softmax_scale = self.softmax_scale or 1.0 / math.sqrt(q.shape[-1])
+        scores = torch.einsum("bthd,bshd->bhts", q, k * softmax_scale)
+        causal_mask = torch.triu(torch.full((s, s), -10000.0, device=scores.device), 1)
+        scores = scores + causal_mask.to(dtype=scores.dtype)
+        return torch.softmax(scores, dim=-1, dtype=q.dtype)
+
+
+class Identity(nn.Identity):
+
+    def forward(self, x, **kwargs):
+        return x
+
+
+def create_nomix_block(config, expand_out=False, layer_idx=None, process_group=None, device=None, dtype=None):
+    """A Block whose mixer is the identity (backpack.py:130-143): residual = LN0(e) + e, then the MLP half."""
+    _no_tp(process_group)
+    factory_kwargs = {"device": device, "dtype": dtype}
+    mlp_cls = create_content_mlp_cls(config, layer_idx, expand_out, **factory_kwargs)
+    norm_cls = partial(nn.LayerNorm, eps=config.layer_norm_epsilon, **factory_kwargs)
+    block = Block(config.hidden_size, Identity, mlp_cls, norm_cls=norm_cls, prenorm=True,
+                  resid_dropout=config.resid_pdrop, fused_dropout_add_ln=getattr(config, "fused_dropout_add_ln", False))
+    block.layer_idx = layer_idx
+    return block
+
+
+class BackpackPreTrainedModel(nn.Module):
+
+    def __init__(self, config, *inputs, **kwargs):
+        super().__init__()
+        if not isinstance(config, BackpackConfig):
+            raise ValueError(f"Parameter config in `{self.__class__.__name__}(config)` should be a BackpackConfig")
+        self.config = config
+
+
+class BackpackContentModule(nn.Module):
+    """Context-free sense vectors C(x) (backpack.py:207-276): word embedding (no positions) -> ln_0 ->
+    one Identity-mixer block -> final MLP to nv*d, returned as the (b, nv, s, d) transposed view."""
+
+    def __init__(self, config, num_content_vectors, embeddings, process_group=None, device=None, dtype=None):
+        super().__init__()
+        _no_tp(process_group)
+        factory_kwargs = {"device": device, "dtype": dtype}
+        self.num_content_vectors = num_content_vectors
+        self.embeddings = embeddings
+        self.process_group = None
+        self.n_embd = config.n_embd
+        self.fused_dropout_add_ln = getattr(config, "fused_dropout_add_ln", False)
+        self.ln_0 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_epsilon, **factory_kwargs)
+        n_layers = 1
+        self.layers = nn.ModuleList([create_nomix_block(config, layer_idx=i, expand_out=False, **factory_kwargs)
+                                     for i in range(n_layers)])
+        self.final_mlp = create_content_mlp_cls(config, layer_idx=n_layers + 1, expand_out=True,
+                                                **factory_kwargs)(config.n_embd)
+        self.emb_drop = nn.Dropout(config.embd_pdrop)
+        self.apply(partial(_init_weights, n_layer=n_layers, initializer_range=config.initializer_range))
+
+    def forward(self, input_ids, position_ids=None, inference_params=None):
+        hidden_states = self.embeddings.word_embeddings(input_ids)  # no positions (backpack.py:258)
+        hidden_states, residual = first_layer_norm(hidden_states, self.ln_0, self.emb_drop,
+                                                   self.fused_dropout_add_ln, self.training)
+        for layer in self.layers:
+            hidden_states, residual = layer(hidden_states, residual)
+        hidden_states = self.final_mlp(hidden_states)  # (b, s, nv*d)
+        b, s, _ = hidden_states.shape
+        return hidden_states.reshape(b, s, self.num_content_vectors, self.n_embd).transpose(1, 2)
+
+
+class BackpackModel(GPTPreTrainedModel):
+
+    def __init__(self, config: BackpackConfig, process_group=None, device=None, dtype=None):
+        super().__init__(config)
+        _no_tp(process_group)
+        factory_kwargs = {"device": device, "dtype": dtype}
+        self.process_group = None
+        self.pad_vocab_size_multiple = pad_vocab(config)
+        self.num_content_vectors = config.num_content_vectors
+        self.gpt2_model = GPTModel(config, **factory_kwargs)
+        self.content_model = BackpackContentModule(config, self.num_content_vectors, self.gpt2_model.embeddings,
+                                                   **factory_kwargs)
+        self.embeddings = self.gpt2_model.embeddings  # shared with the contextualisation trunk
+        self.contextualization_attn = ContextSelfAttn(self.num_content_vectors, config.n_embd, **factory_kwargs)
+        # fused sense-mix follows use_flash_attn unless the config says otherwise
+        self.fused_sense_mix = getattr(config, "fused_sense_mix", getattr(config, "use_flash_attn", False))
+
+    def sense_mix(self, contextl_hidden_states, content):
+        """sum_l alpha_l(contextl_hidden_states) @ content_l without materialising alpha; `content` may be any
+        (b, nv, s, d) tensor (e.g. edited sense vectors)."""
+        qk = self.contextualization_attn.project_qk(contextl_hidden_states)
+        return sense_mix(qk, content, softmax_scale=self.contextualization_attn.softmax_scale)
+
+    def forward(self, input_ids, position_ids=None, inference_params=None):
+        contextl_hidden_states = self.gpt2_model(input_ids, position_ids=position_ids,
+                                                 inference_params=inference_params)
+        content = self.content_model(input_ids, position_ids, inference_params)  # (b, nv, s, d)
+        if self.fused_sense_mix:
+            return self.sense_mix(contextl_hidden_states, content)
+        contextualization = self.contextualization_attn(contextl_hidden_states)  # (b, nv, s, s)
+        return torch.sum(contextualization @ content, dim=1)
+
+
+class BackpackLMHeadModel(BackpackPreTrainedModel):
+
+    def __init__(self, config: BackpackConfig, process_group=None, device=None, dtype=None):
+        super().__init__(config)
+        _no_tp(process_group)
+        factory_kwargs = {"device": device, "dtype": dtype}
+        self.process_group = None
+        self.transformer = BackpackModel(config, **factory_kwargs)
+        self.lm_head = nn.Linear(config.n_embd, config.vocab_size, bias=False, **factory_kwargs)
+        self.apply(partial(_init_weights, n_layer=config.num_hidden_layers,
+                           initializer_range=config.initializer_range))
+        self.tie_weights()
+
+    def tie_weights(self):
+        self.lm_head.weight = self.transformer.embeddings.word_embeddings.weight
+
+    def forward(self, input_ids, position_ids=None, inference_params=None):
+        hidden_states = self.transformer(input_ids, position_ids=position_ids, inference_params=inference_params)
+        return CausalLMOutput(logits=self.lm_head(hidden_states))
+
+
+def flash_config(**kwargs) -> BackpackConfig:
+    """The reference's optimised configuration (training/configs/experiment/owt/backpack-small-flash.yaml:10-14,
+    training/configs/model/backpack.yaml:11-13) with every fused flag on."""
+    base = dict(num_content_vectors=16, vocab_size=50257, activation_function="gelu_new",
+                scale_attn_by_inverse_layer_idx=True, reorder_and_upcast_attn=False)
+    base.update(kwargs)
+    cfg = BackpackConfig(**base)
+    cfg.use_flash_attn = True
+    cfg.fused_bias_fc = True
+    cfg.fused_dense_gelu_dense = True
+    cfg.fused_dropout_add_ln = True
+    cfg.pad_vocab_size_multiple = 8
+    return cfg

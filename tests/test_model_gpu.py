@@ -1,0 +1,97 @@
+"""End-to-end GPU parity of the Backpack forward (all fused kernels on) against the golden vectors that were
+generated from the real reference, using the reference's model-level rule (tests/models/test_gpt.py:60,70):
+our error against fp32 must stay below 3x the error of the reference's own same-precision eager path."""
+import numpy as np
+import pytest
+import torch
+
+from backpacks_flash_attn_b200 import _lib
+from backpacks_flash_attn_b200.models.backpack import BackpackConfig, BackpackLMHeadModel, flash_config
+from backpacks_flash_attn_b200.utils.weights import name_seeded_
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(dims):
+    fused = name_seeded_(BackpackLMHeadModel(flash_config(**dims)).eval()).to("cuda", torch.bfloat16)
+    eager = name_seeded_(BackpackLMHeadModel(BackpackConfig(
+        num_content_vectors=16, vocab_size=50257, activation_function="gelu_new", reorder_and_upcast_attn=False,
+        scale_attn_by_inverse_layer_idx=True, pad_vocab_size_multiple=8, **dims)).eval()).to("cuda", torch.bfloat16)
+    return fused, eager
+
+
+def _rule(ours, eager, ref, what):
+    e_ours, e_eager = (ours.float() - ref).abs(), (eager.float() - ref).abs()
+    print(f"{what}: ours max {e_ours.max():.3e} mean {e_ours.mean():.3e} | eager-bf16 max {e_eager.max():.3e} "
+          f"mean {e_eager.mean():.3e} | max|ref| {ref.abs().max():.2f}")
+    assert e_ours.max() <= 3 * e_eager.max() + 1e-3
+    assert e_ours.mean() <= 3 * e_eager.mean() + 1e-4
+
+
+def test_backpack_micro_matches_reference_golden(golden_dir):
+    g = np.load(f"{golden_dir}/micro_model.npz")
+    fused, eager = _pair(dict(n_embd=384, n_head=6, n_layer=6, n_positions=512))
+    ids = torch.from_numpy(g["ids"]).cuda()
+    before = _lib.total_launches()
+    with torch.inference_mode():
+        hid, hid_e = fused.transformer(ids), eager.transformer(ids)
+        logits, logits_e = fused(ids).logits, eager(ids).logits
+        ctx_h, ctx_e = fused.transformer.gpt2_model(ids), eager.transformer.gpt2_model(ids)
+        content, content_e = fused.transformer.content_model(ids), eager.transformer.content_model(ids)
+    assert _lib.total_launches() > before          # the CUDA path is the one that ran
+    _rule(ctx_h, ctx_e, torch.from_numpy(g["ctx_h"]).cuda(), "trunk hidden")
+    _rule(content[1, 15], content_e[1, 15], torch.from_numpy(g["content_1_15"]).cuda(), "content[1,15]")
+    _rule(hid, hid_e, torch.from_numpy(g["hid"]).cuda(), "backpack hidden")
+    _rule(logits[1, 127], logits_e[1, 127], torch.from_numpy(g["logits_last"]).cuda(), "logits[1,127]")
+    _rule(logits[:, :, :64], logits_e[:, :, :64], torch.from_numpy(g["logits_head"]).cuda(), "logits[:,:,:64]")
+    agree = (logits.argmax(-1).cpu() == torch.from_numpy(g["argmax"])).float().mean().item()
+    agree_e = (logits_e.argmax(-1).cpu() == torch.from_numpy(g["argmax"])).float().mean().item()
+    print(f"greedy argmax agreement with fp32 reference: ours {agree:.3f}, eager bf16 {agree_e:.3f}")
+    assert agree >= agree_e - 0.05
+    assert list(content.shape) == [2, 16, 128, 384] and list(content.stride()) == g["content_strides"].tolist()
+
+
+def test_backpack_small_matches_reference_golden(golden_dir):
+    g = np.load(f"{golden_dir}/small_model.npz")
+    fused, eager = _pair(dict(n_embd=768, n_head=12, n_layer=12, n_positions=1024))
+    ids = torch.from_numpy(g["ids"]).cuda()
+    with torch.inference_mode():
+        hid, hid_e = fused.transformer(ids), eager.transformer(ids)
+        logits, logits_e = fused(ids).logits, eager(ids).logits
+    _rule(hid, hid_e, torch.from_numpy(g["hid"]).cuda(), "small hidden")
+    _rule(logits[0, 255, :256], logits_e[0, 255, :256], torch.from_numpy(g["logits_last_head"]).cuda(), "small logits")
+
+
+def test_fused_and_eager_sense_mix_agree_inside_the_model():
+    """transformer.sense_mix(h, C) (fused) vs torch.sum(contextualization_attn(h) @ C, 1) (reference composition,
+    backpack.py:305-313), including an edited content tensor as the intervention wrappers build
+    (intervened_models.py:78-101)."""
+    fused, _ = _pair(dict(n_embd=384, n_head=6, n_layer=2, n_positions=512))
+    ids = torch.randint(0, 50257, (3, 300), device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    with torch.inference_mode():
+        t = fused.transformer
+        h = t.gpt2_model(ids)
+        content = t.content_model(ids)
+        alpha = t.contextualization_attn(h)
+        assert alpha.shape == (3, 16, 300, 300)
+        want = torch.sum(alpha @ content, dim=1)
+        got = t.sense_mix(h, content)
+        assert torch.equal(got, t(ids))
+        assert (got.float() - want.float()).abs().max() < 0.1
+        edited = content.clone()
+        edited[:, 3] *= 0.0            # knock one sense out
+        got2 = t.sense_mix(h, edited)
+        want2 = torch.sum(alpha @ edited, dim=1)
+        assert (got2.float() - want2.float()).abs().max() < 0.1
+        assert (got2.float() - got.float()).abs().max() > 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_non_default_device():
+    """Launches follow the tensors' device (the reference guards with CUDAGuard, fmha_api.cpp:267)."""
+    fused, _ = _pair(dict(n_embd=128, n_head=2, n_layer=1, n_positions=128))
+    ids = torch.randint(0, 50257, (2, 128), generator=torch.Generator().manual_seed(1))
+    with torch.inference_mode():
+        a = fused(ids.cuda(0)).logits
+        b = fused.to("cuda:1")(ids.to("cuda:1")).logits
+    assert torch.equal(a.cpu(), b.cpu())
