@@ -30,7 +30,7 @@ __device__ __forceinline__ bool elect_one() {
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 

@@ -4,16 +4,20 @@
 // src/fmha_fprop_kernel_1xN.h:199-696).  That kernel walks K/V blocks in the outer loop and bounces a
 // fp32 O through HBM between blocks; this one is written for Blackwell from scratch:
 //
-//   * Q-outer / KV-inner: one CTA owns 2 x 128 query rows of one (batch, head); O stays in TMEM for the
+//   * Q-outer / KV-inner: a work item is 2 x 128 query rows of one (batch, head); O stays in TMEM for the
 //     whole KV sweep, so Q, K, V are read once and O written once (the algorithmic traffic).
-//   * warp-specialised, 384 threads:  warp 0 = TMA producer (Q once, K/V double-buffered rings),
-//     warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warpgroups 1 and 2 = softmax for query tile
-//     0 / 1 (one thread per query row -> row max / row sum need no shuffles; TMEM lane == row).
-//   * S = Q K^T (M=128, N=BN) lands in TMEM; softmax threads tcgen05.ld it, apply the mask, keep a running
-//     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8), write
-//     P = exp2(...) as bf16/f16 into a 128B-swizzled smem tile; O += P V is a second tcgen05.mma with
-//     V consumed as an MN-major B operand straight from the TMA tile (no transpose).
-//   * the two query tiles ping-pong: while the softmax of tile 0 runs, the tensor core works for tile 1.
+//   * persistent: one CTA per SM walks the work items (heaviest causal tiles first, round-robin), barrier
+//     phases run on across items, Q is double-buffered per item and the K/V rings never drain, so the loads
+//     and the first S = Q K^T of the next item overlap the epilogue of the current one.
+//   * warp-specialised, 384 threads:  warp 0 = TMA producer, warps 1 / 2 = tcgen05.mma issuers for query
+//     tile 0 / 1 (two independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator,
+//     warpgroups 1 / 2 = softmax for query tile 0 / 1 (one thread per query row; TMEM lane == row, so
+//     row max / row sum need no shuffles).
+//   * S (M=128, N=BN) lands in TMEM; the softmax threads tcgen05.ld their row and hand the S buffer back at
+//     once (s_free), so S of the next key block is computed while this block's exponentials run; running
+//     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8), P = exp2(...) as
+//     bf16/f16 into a 128B-swizzled smem tile; O += P V is a second tcgen05.mma with V consumed as an
+//     MN-major B operand straight from the TMA tile (no transpose).
 //
 // Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
 // are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill
@@ -32,20 +36,21 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 template <int DP>
 struct Cfg {
   static constexpr int BN = (DP == 64) ? 128 : 64;  // keys per block
-  static constexpr int kStages = 2;
+  static constexpr int kStages = 2;                  // K and V rings
+  static constexpr int kQBufs = 2;                   // Q double-buffered across work items
   static constexpr int kPanelsD = DP / 64;           // 64-column (128 B) panels along head dim
-  static constexpr int kPanelsN = BN / 64;           // panels of P along the key dim
   static constexpr uint32_t kQTileBytes = BM * DP * 2;
   static constexpr uint32_t kKVTileBytes = BN * DP * 2;
   static constexpr uint32_t kPTileBytes = BM * BN * 2;
   static constexpr uint32_t kKVPanelBytes = BN * 128;  // one 64-column panel of a K/V tile
   // shared memory map (all tile bases 1024-aligned)
   static constexpr uint32_t offQ = 0;
-  static constexpr uint32_t offK = offQ + 2 * kQTileBytes;
+  static constexpr uint32_t offK = offQ + kQBufs * 2 * kQTileBytes;
   static constexpr uint32_t offV = offK + kStages * kKVTileBytes;
   static constexpr uint32_t offP = offV + kStages * kKVTileBytes;
   static constexpr uint32_t offBar = offP + 2 * kPTileBytes;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;  // + barriers + alignment slack
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
   // TMEM columns
   static constexpr uint32_t colS = 0;            // S_t at colS + t*BN
   static constexpr uint32_t colO = 2 * BN;       // O_t at colO + t*DP
@@ -59,19 +64,54 @@ struct Params {
   const int32_t* cu_k;
   int64_t o_row_stride, o_head_stride;
   int32_t lse_stride;
-  int32_t nheads, headdim;
+  int32_t batch, nheads, headdim;
   int32_t num_pairs;  // ceil(max_seqlen_q / 256)
+  int32_t num_items;  // num_pairs * batch * nheads
   int32_t is_causal;
   float scale;        // softmax scale
   float scale_log2;   // scale * log2(e)
 };
 
 struct Barriers {
-  uint64_t q_full;
+  uint64_t q_full[2], q_empty[2];
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[2], p_ready[2], pv_done[2];
+  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2];
   uint32_t tmem_base;
 };
+
+// One work item = (pair of query tiles, head, batch).  Every role decodes the same sequence of items.
+struct Item {
+  int head, batch, q_begin, k_begin, len_q, len_k, row0;
+  int n0, n1, n_max;   // key blocks visited by query tile 0 / 1
+  bool valid;
+  __device__ __forceinline__ int n_of(int t) const { return t == 0 ? n0 : n1; }
+};
+
+template <int BN>
+__device__ __forceinline__ Item decode_item(const Params& p, int w) {
+  Item it;
+  const int bh = p.batch * p.nheads;
+  const int pair = p.num_pairs - 1 - w / bh;  // heaviest (most key blocks) first
+  const int rem = w % bh;
+  it.batch = rem / p.nheads;
+  it.head = rem % p.nheads;
+  it.q_begin = p.cu_q[it.batch];
+  it.len_q = p.cu_q[it.batch + 1] - it.q_begin;
+  it.k_begin = p.cu_k[it.batch];
+  it.len_k = p.cu_k[it.batch + 1] - it.k_begin;
+  it.row0 = pair * 2 * BM;
+  auto blocks = [&](int r0) {
+    if (r0 >= it.len_q) return 0;
+    int kmax = it.len_k;
+    if (p.is_causal) kmax = min(kmax, r0 + BM);
+    return (kmax + BN - 1) / BN;
+  };
+  it.n0 = blocks(it.row0);
+  it.n1 = blocks(it.row0 + BM);
+  it.n_max = max(it.n0, it.n1);
+  it.valid = it.n_max > 0;
+  return it;
+}
 
 template <int DP, bool kBF16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -85,50 +125,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int pair = p.num_pairs - 1 - static_cast<int>(blockIdx.x);  // heaviest (most KV blocks) first
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-
-  const int q_begin = p.cu_q[batch];
-  const int len_q = p.cu_q[batch + 1] - q_begin;
-  const int k_begin = p.cu_k[batch];
-  const int len_k = p.cu_k[batch + 1] - k_begin;
-  const int row0 = pair * 2 * BM;  // first query row (within the sequence) of this CTA
-  if (row0 >= len_q) return;       // uniform for the CTA; nothing allocated yet
-
-  // number of key blocks each query tile visits
-  int n_blk[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int r0 = row0 + t * BM;
-    int n = 0;
-    if (r0 < len_q) {
-      int kmax = len_k;
-      if (p.is_causal) kmax = min(kmax, r0 + BM);
-      n = (kmax + BN - 1) / BN;
-    }
-    n_blk[t] = n;
-  }
-  const int n_max = max(n_blk[0], n_blk[1]);
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(&bars.q_full, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.q_full[i], 1);
+      mbar_init(&bars.q_empty[i], 2);   // both MMA warps release a Q buffer
       mbar_init(&bars.k_full[i], 1);
-      mbar_init(&bars.k_empty[i], 1);
+      mbar_init(&bars.k_empty[i], 2);   // both MMA warps release a K / V slot
       mbar_init(&bars.v_full[i], 1);
-      mbar_init(&bars.v_empty[i], 1);
+      mbar_init(&bars.v_empty[i], 2);
       mbar_init(&bars.s_full[i], 1);
+      mbar_init(&bars.s_free[i], 128);
       mbar_init(&bars.p_ready[i], 128);
       mbar_init(&bars.pv_done[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 3) {
     tmem_alloc(&bars.tmem_base, C::kTmemCols);
     tmem_relinquish();
   }
@@ -139,100 +156,118 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 4) {
     reg_dealloc<56>();
-    if (warp == 0 && n_max > 0) {
+    if (warp == 0) {
       // ===================== TMA producer (whole warp walks the loop, lane 0 issues) =====================
-      const int n_q_tiles = (row0 + BM < len_q) ? 2 : 1;
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&bars.q_full, n_q_tiles * C::kQTileBytes);
-        for (int t = 0; t < n_q_tiles; ++t)
-          for (int pn = 0; pn < C::kPanelsD; ++pn)
-            tma_load_3d(smem + C::offQ + t * C::kQTileBytes + pn * (BM * 128), &tmQ, &bars.q_full, pn * 64, head,
-                        q_begin + row0 + t * BM);
-      }
-      for (int j = 0; j < n_max; ++j) {
-        const int slot = j & 1;
-        const int krow = k_begin + j * BN;
-        if (j >= 2) mbar_wait(&bars.k_empty[slot], ((j >> 1) - 1) & 1);
+      uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no & 1, K/V slot = blk & 1
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+        const Item it = decode_item<BN>(p, w);
+        if (!it.valid) continue;
+        const uint32_t qb = item_no & 1;
+        if (item_no >= 2) mbar_wait(&bars.q_empty[qb], ((item_no >> 1) - 1) & 1);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKVTileBytes);
-          for (int pn = 0; pn < C::kPanelsD; ++pn)
-            tma_load_3d(smem + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK, &bars.k_full[slot],
-                        pn * 64, head, krow);
+          const int n_q_tiles = (it.row0 + BM < it.len_q) ? 2 : 1;
+          mbar_arrive_expect_tx(&bars.q_full[qb], n_q_tiles * C::kQTileBytes);
+          for (int t = 0; t < n_q_tiles; ++t)
+            for (int pn = 0; pn < C::kPanelsD; ++pn)
+              tma_load_3d(smem + C::offQ + (qb * 2 + t) * C::kQTileBytes + pn * (BM * 128), &tmQ, &bars.q_full[qb],
+                          pn * 64, it.head, it.q_begin + it.row0 + t * BM);
         }
-        if (j >= 2) mbar_wait(&bars.v_empty[slot], ((j >> 1) - 1) & 1);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&bars.v_full[slot], C::kKVTileBytes);
-          for (int pn = 0; pn < C::kPanelsD; ++pn)
-            tma_load_3d(smem + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV, &bars.v_full[slot],
-                        pn * 64, head, krow);
+        for (int j = 0; j < it.n_max; ++j, ++blk) {
+          const uint32_t slot = blk & 1;
+          const int krow = it.k_begin + j * BN;
+          if (blk >= 2) mbar_wait(&bars.k_empty[slot], ((blk >> 1) - 1) & 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&bars.k_full[slot], C::kKVTileBytes);
+            for (int pn = 0; pn < C::kPanelsD; ++pn)
+              tma_load_3d(smem + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK,
+                          &bars.k_full[slot], pn * 64, it.head, krow);
+          }
+          if (blk >= 2) mbar_wait(&bars.v_empty[slot], ((blk >> 1) - 1) & 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&bars.v_full[slot], C::kKVTileBytes);
+            for (int pn = 0; pn < C::kPanelsD; ++pn)
+              tma_load_3d(smem + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV,
+                          &bars.v_full[slot], pn * 64, it.head, krow);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        ++item_no;
       }
-    } else if (warp == 1 && n_max > 0) {
-      // ===================== MMA issuer (whole warp waits, lane 0 issues) =====================
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuer of query tile t (whole warp waits, lane 0 issues) =====================
+      const int t = warp - 1;
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
       constexpr uint32_t idesc_pv = make_idesc(kBF16, BM, DP, false, true);
-      const uint32_t sQ = smem_u32(smem + C::offQ);
       const uint32_t sK = smem_u32(smem + C::offK);
       const uint32_t sV = smem_u32(smem + C::offV);
-      const uint32_t sP = smem_u32(smem + C::offP);
+      const uint32_t sP = smem_u32(smem + C::offP) + t * C::kPTileBytes;
+      const uint32_t tS = tmem_base + C::colS + t * BN;
+      const uint32_t tO = tmem_base + C::colO + t * DP;
+      uint32_t item_no = 0, blk = 0;  // same running counters as the producer
+      uint32_t s_cnt = 0;             // S tiles issued by this warp (s_free / s_full phases)
+      uint32_t pv_cnt = 0;            // PV products issued by this warp (p_ready / pv_done phases)
 
-      // S_t(j) = Q_t K_j^T ; optionally hands the K slot back to the producer
-      auto issue_s = [&](int t, int j, bool release_k) {
-        if (lane == 0) {
-          const uint32_t a_base = sQ + t * C::kQTileBytes;
-          const uint32_t b_base = sK + (j & 1) * C::kKVTileBytes;
-#pragma unroll
-          for (int kk = 0; kk < DP / 16; ++kk) {
-            const uint32_t a = a_base + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-            const uint32_t b = b_base + (kk >> 2) * C::kKVPanelBytes + (kk & 3) * 32;
-            umma_ss(tmem_base + C::colS + t * BN, make_smem_desc_sw128(a, 16, 1024),
-                    make_smem_desc_sw128(b, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-          }
-          if (release_k) umma_commit(&bars.k_empty[j & 1]);
-          umma_commit(&bars.s_full[t]);
-        }
-        __syncwarp();
-      };
-      // O_t (+)= P_t V_j ; V is the MN-major B operand
-      auto issue_pv = [&](int t, int j, bool release_v) {
-        if (lane == 0) {
-          const uint32_t a_base = sP + t * C::kPTileBytes;
-          const uint32_t b_base = sV + (j & 1) * C::kKVTileBytes;
-#pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            const uint32_t a = a_base + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-            const uint32_t b = b_base + kk * 2048;  // 16 key rows x 128 B
-            umma_ss(tmem_base + C::colO + t * DP, make_smem_desc_sw128(a, 16, 1024),
-                    make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-          }
-          if (release_v) umma_commit(&bars.v_empty[j & 1]);
-          umma_commit(&bars.pv_done[t]);
-        }
-        __syncwarp();
-      };
-      // tile 1 visits a superset of tile 0's key blocks, so it is the last reader whenever it exists
-      auto last_user = [&](int j) { return j < n_blk[1] ? 1 : 0; };
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+        const Item it = decode_item<BN>(p, w);
+        if (!it.valid) continue;
+        const uint32_t qb = item_no & 1;
+        const uint32_t sQ = smem_u32(smem + C::offQ) + (qb * 2 + t) * C::kQTileBytes;
+        const int n = it.n_of(t);
+        mbar_wait(&bars.q_full[qb], (item_no >> 1) & 1);
 
-      mbar_wait(&bars.q_full, 0);
-      mbar_wait(&bars.k_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < 2; ++t)
-        if (n_blk[t] > 0) issue_s(t, 0, t == last_user(0));
-      for (int j = 0; j < n_max; ++j) {
-        for (int t = 0; t < 2; ++t) {
-          if (j >= n_blk[t]) continue;
-          mbar_wait(&bars.p_ready[t], j & 1);
-          tc_fence_after();
-          if (j + 1 < n_blk[t]) {
-            mbar_wait(&bars.k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        // S(j) = Q K_j^T into this tile's S buffer, then hand the K slot back (both tiles must do so)
+        auto step_s = [&](int j, uint32_t kblk) {
+          const uint32_t slot = kblk & 1;
+          if (j < n) {
+            if (s_cnt >= 1) mbar_wait(&bars.s_free[t], (s_cnt - 1) & 1);   // softmax has read the previous S
+            mbar_wait(&bars.k_full[slot], (kblk >> 1) & 1);
             tc_fence_after();
-            issue_s(t, j + 1, t == last_user(j + 1));
+            if (lane == 0) {
+#pragma unroll
+              for (int kk = 0; kk < DP / 16; ++kk) {
+                const uint32_t a = sQ + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+                const uint32_t b = sK + slot * C::kKVTileBytes + (kk >> 2) * C::kKVPanelBytes + (kk & 3) * 32;
+                umma_ss(tS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_s,
+                        kk > 0 ? 1u : 0u);
+              }
+              umma_commit(&bars.k_empty[slot]);
+              if (j == n - 1) umma_commit(&bars.q_empty[qb]);   // last read of this item's Q tile
+              umma_commit(&bars.s_full[t]);
+            }
+            ++s_cnt;
+          } else if (lane == 0) {
+            umma_commit(&bars.k_empty[slot]);  // block not visited by this tile: release in MMA order
           }
-          mbar_wait(&bars.v_full[j & 1], (j >> 1) & 1);
-          tc_fence_after();
-          issue_pv(t, j, t == last_user(j));
+          __syncwarp();
+        };
+
+        if (n == 0 && lane == 0) umma_commit(&bars.q_empty[qb]);
+        step_s(0, blk);
+        for (int j = 0; j < it.n_max; ++j, ++blk) {
+          if (j + 1 < it.n_max) step_s(j + 1, blk + 1);
+          const uint32_t slot = blk & 1;
+          if (j < n) {
+            mbar_wait(&bars.p_ready[t], pv_cnt & 1);
+            mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+              for (int kk = 0; kk < BN / 16; ++kk) {
+                const uint32_t a = sP + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+                const uint32_t b = sV + slot * C::kKVTileBytes + kk * 2048;  // 16 key rows x 128 B
+                umma_ss(tO, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, C::kKVPanelBytes, 1024),
+                        idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+              }
+              umma_commit(&bars.v_empty[slot]);
+              umma_commit(&bars.pv_done[t]);
+            }
+            ++pv_cnt;
+          } else if (lane == 0) {
+            umma_commit(&bars.v_empty[slot]);
+          }
+          __syncwarp();
         }
+        ++item_no;
       }
     }
   } else {
@@ -240,19 +275,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     reg_alloc<224>();
     const int t = (warp >> 2) - 1;                 // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
-    const int n = n_blk[t];
-    if (n > 0) {
-      const int qrow = row0 + t * BM + r;          // query index within the sequence
-      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN;
-      const uint32_t tO = tmem_base + lane_addr + C::colO + t * DP;
-      uint8_t* sP = smem + C::offP + t * C::kPTileBytes;
-      const float scale_log2 = p.scale_log2;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN;
+    const uint32_t tO = tmem_base + lane_addr + C::colO + t * DP;
+    uint8_t* sP = smem + C::offP + t * C::kPTileBytes;
+    const float scale_log2 = p.scale_log2;
+    uint32_t cnt = 0;  // key blocks processed by this warpgroup (phases of s_full / pv_done)
+
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+      const Item it = decode_item<BN>(p, w);
+      const int n = it.n_of(t);
+      if (!it.valid || n == 0) continue;
+      const int qrow = it.row0 + t * BM + r;       // query index within the sequence
       float m_used = 0.f;  // running max (raw score units) the exponentials are taken against
       float l = 0.f;
 
-      for (int j = 0; j < n; ++j) {
-        mbar_wait(&bars.s_full[t], j & 1);
+      for (int j = 0; j < n; ++j, ++cnt) {
+        mbar_wait(&bars.s_full[t], cnt & 1);
         tc_fence_after();
         float s[BN];
 #pragma unroll
@@ -263,18 +302,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(u[i]);
         }
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.s_free[t]);   // S(j+1) may now overwrite the buffer while we work on registers
 
         const int col0 = j * BN;
-        const bool partial = (col0 + BN > len_k) || (p.is_causal && (col0 + BN - 1 > row0 + t * BM));
+        const bool partial = (col0 + BN > it.len_k) || (p.is_causal && (col0 + BN - 1 > it.row0 + t * BM));
         if (partial) {
-          const int limit = p.is_causal ? min(len_k, qrow + 1) : len_k;  // visible keys: col < limit
+          const int limit = p.is_causal ? min(it.len_k, qrow + 1) : it.len_k;  // visible keys: col < limit
 #pragma unroll
           for (int c = 0; c < BN; ++c)
             if (col0 + c >= limit) s[c] = -INFINITY;
         }
-        float mx = s[0];
+        // row max: four independent chains
+        float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int c = 1; c < BN; ++c) mx = fmaxf(mx, s[c]);
+        for (int c = 4; c < BN; c += 4) {
+          mx4[0] = fmaxf(mx4[0], s[c]);
+          mx4[1] = fmaxf(mx4[1], s[c + 1]);
+          mx4[2] = fmaxf(mx4[2], s[c + 2]);
+          mx4[3] = fmaxf(mx4[3], s[c + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
         if (j == 0) {
           m_used = (mx == -INFINITY) ? 0.f : mx;
@@ -286,7 +334,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             m_used = mx;
           }
           // P tile and O accumulator are free once the previous PV MMA has completed
-          mbar_wait(&bars.pv_done[t], (j - 1) & 1);
+          mbar_wait(&bars.pv_done[t], (cnt - 1) & 1);
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
@@ -304,35 +352,36 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
 
         const float neg_m = -m_used * scale_log2;
-        float sum = 0.f;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c8 = 0; c8 < BN / 8; ++c8) {
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = fast_exp2(fmaf(s[c8 * 8 + i], scale_log2, neg_m));
-            sum += e[i];
-          }
-          uint4 w;
-          w.x = pack2<kBF16>(e[0], e[1]);
-          w.y = pack2<kBF16>(e[2], e[3]);
-          w.z = pack2<kBF16>(e[4], e[5]);
-          w.w = pack2<kBF16>(e[6], e[7]);
-          *reinterpret_cast<uint4*>(sP + (c8 >> 3) * (BM * 128) + sw128_offset(r, c8 & 7)) = w;
+          for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(s[c8 * 8 + i], scale_log2, neg_m));
+          sum4[0] += e[0] + e[4];
+          sum4[1] += e[1] + e[5];
+          sum4[2] += e[2] + e[6];
+          sum4[3] += e[3] + e[7];
+          uint4 v;
+          v.x = pack2<kBF16>(e[0], e[1]);
+          v.y = pack2<kBF16>(e[2], e[3]);
+          v.z = pack2<kBF16>(e[4], e[5]);
+          v.w = pack2<kBF16>(e[6], e[7]);
+          *reinterpret_cast<uint4*>(sP + (c8 >> 3) * (BM * 128) + sw128_offset(r, c8 & 7)) = v;
         }
-        l += sum;
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bars.p_ready[t]);
       }
 
       // ---- epilogue: O / l -> global, LSE ----
-      mbar_wait(&bars.pv_done[t], (n - 1) & 1);
+      mbar_wait(&bars.pv_done[t], (cnt - 1) & 1);
       tc_fence_after();
-      const bool valid = qrow < len_q;
+      const bool valid = qrow < it.len_q;
       const float inv_l = 1.f / l;
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
-                      2 * (static_cast<int64_t>(q_begin + qrow) * p.o_row_stride + head * p.o_head_stride);
+                      2 * (static_cast<int64_t>(it.q_begin + qrow) * p.o_row_stride + it.head * p.o_head_stride);
 #pragma unroll
       for (int c = 0; c < DP / 32; ++c) {
         uint32_t o[32];
@@ -342,29 +391,33 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (c * 32 + g * 8 < p.headdim) {
-              uint4 w;
-              w.x = pack2<kBF16>(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
-              w.y = pack2<kBF16>(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
-              w.z = pack2<kBF16>(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
-              w.w = pack2<kBF16>(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + (c * 32 + g * 8) * 2) = w;
+              uint4 v;
+              v.x = pack2<kBF16>(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+              v.y = pack2<kBF16>(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+              v.z = pack2<kBF16>(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+              v.w = pack2<kBF16>(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + (c * 32 + g * 8) * 2) = v;
             }
           }
         }
       }
       if (valid)
-        p.lse[(static_cast<int64_t>(batch) * p.nheads + head) * p.lse_stride + qrow] = m_used * p.scale + logf(l);
+        p.lse[(static_cast<int64_t>(it.batch) * p.nheads + it.head) * p.lse_stride + qrow] =
+            m_used * p.scale + logf(l);
+      // the O reads above are complete (wait::ld); the next item's first PV (accumulate = 0) is only issued
+      // after this warpgroup's next p_ready, i.e. after this point in program order.
+      tc_fence_before();
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 3) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 template <int DP, bool kBF16>
-int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Params& p, int batch,
+int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Params& p,
            cudaStream_t stream) {
   using C = Cfg<DP>;
   auto kern = fmha_fwd_kernel<DP, kBF16>;
@@ -374,7 +427,10 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
     return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaFuncSetAttribute(%u B smem): %s", C::kSmemBytes,
                 cudaGetErrorString(e));
   }
-  dim3 grid(p.num_pairs, p.nheads, batch);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_items < sms ? p.num_items : sms;
   kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   return check_launch("bp_fmha_fwd launch");
 }
@@ -435,14 +491,18 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
   p.o_row_stride = o_row_stride;
   p.o_head_stride = o_head_stride;
   p.lse_stride = lse_stride;
+  p.batch = batch;
   p.nheads = nheads;
   p.headdim = headdim;
   p.num_pairs = (max_seqlen_q + 2 * fmha::BM - 1) / (2 * fmha::BM);
+  if ((int64_t)p.num_pairs * batch * nheads > 0x7fffffff)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: too many work items");
+  p.num_items = p.num_pairs * batch * nheads;
   p.is_causal = is_causal ? 1 : 0;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * fmha::kLog2e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
-  if (DP == 64) return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, p, batch, st) : fmha::launch<64, false>(tmQ, tmK, tmV, p, batch, st);
-  return bf16 ? fmha::launch<128, true>(tmQ, tmK, tmV, p, batch, st) : fmha::launch<128, false>(tmQ, tmK, tmV, p, batch, st);
+  if (DP == 64) return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, p, st) : fmha::launch<64, false>(tmQ, tmK, tmV, p, st);
+  return bf16 ? fmha::launch<128, true>(tmQ, tmK, tmV, p, st) : fmha::launch<128, false>(tmQ, tmK, tmV, p, st);
 }
