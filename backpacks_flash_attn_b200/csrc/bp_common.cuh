@@ -77,8 +77,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Blocking wait.  A pipeline bug would otherwise hang the GPU until the watchdog fires; after ~16M failed
+// polls (orders of magnitude beyond any legitimate wait in these kernels) the kernel traps instead, which
+// surfaces as a CUDA launch failure on the host.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++polls > (1u << 24)) __trap();
   }
 }
 

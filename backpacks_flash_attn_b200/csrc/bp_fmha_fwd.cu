@@ -235,8 +235,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               umma_commit(&bars.s_full[t]);
             }
             ++s_cnt;
-          } else if (lane == 0) {
-            umma_commit(&bars.k_empty[slot]);  // block not visited by this tile: release in MMA order
+          } else {
+            // Block not visited by this tile.  The slot still needs this warp's release, but only once the
+            // producer has (re)filled it for THIS block: arriving earlier could complete the previous
+            // phase of k_empty while the other tile still reads the previous occupant.
+            mbar_wait(&bars.k_full[slot], (kblk >> 1) & 1);
+            if (lane == 0) umma_commit(&bars.k_empty[slot]);
           }
           __syncwarp();
         };
@@ -262,8 +266,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               umma_commit(&bars.pv_done[t]);
             }
             ++pv_cnt;
-          } else if (lane == 0) {
-            umma_commit(&bars.v_empty[slot]);
+          } else {
+            mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);   // same pacing rule as for K
+            if (lane == 0) umma_commit(&bars.v_empty[slot]);
           }
           __syncwarp();
         }
