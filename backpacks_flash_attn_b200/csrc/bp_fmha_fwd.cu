@@ -9,10 +9,13 @@
 //   * persistent: one CTA per SM walks the work items (heaviest causal tiles first, round-robin), barrier
 //     phases run on across items, Q is double-buffered per item and the K/V rings never drain, so the loads
 //     and the first S = Q K^T of the next item overlap the epilogue of the current one.
-//   * warp-specialised, 384 threads:  warp 0 = TMA producer, warps 1 / 2 = tcgen05.mma issuers for query
-//     tile 0 / 1 (two independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator,
-//     warpgroups 1 / 2 = softmax for query tile 0 / 1 (one thread per query row; TMEM lane == row, so
-//     row max / row sum need no shuffles).
+//   * warp-specialised:  warp 0 = TMA producer, warps 1 / 2 = tcgen05.mma issuers for query tile 0 / 1 (two
+//     independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator, then 2 x NH softmax
+//     warpgroups (one thread per query row; TMEM lane == row, so row max / row sum need no shuffles).
+//     The kernel is bound by the MUFU ex2 pipe, not by the tensor pipe, so for head dim <= 64 each key
+//     block is split into NH = 2 halves that run as independent online-softmax streams (own running max,
+//     own row sum, own O accumulator in TMEM; merged once in the epilogue): four softmax warps per SM
+//     sub-partition keep the MUFU pipe fed while their siblings wait on TMEM loads and barriers.
 //   * S (M=128, N=BN) lands in TMEM; the softmax threads tcgen05.ld their row and hand the S buffer back at
 //     once (s_free), so S of the next key block is computed while this block's exponentials run; running
 //     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8), P = exp2(...) as
@@ -29,32 +32,39 @@ namespace bp {
 namespace fmha {
 
 constexpr int BM = 128;           // query rows per tile (= TMEM lanes)
-constexpr int kThreads = 384;     // 3 warpgroups
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int DP>
 struct Cfg {
   static constexpr int BN = (DP == 64) ? 128 : 64;  // keys per block
+  static constexpr int NH = (DP == 64) ? 2 : 1;      // independent softmax streams (key halves) per block
+  static constexpr int HB = BN / NH;                 // keys per stream and block (= 64)
+  static constexpr int kThreads = 128 + 256 * NH;    // warps 0-3 + 2*NH softmax warpgroups
+  static constexpr int kRegsLow = NH == 2 ? 32 : 56;
+  static constexpr int kRegsHigh = NH == 2 ? 112 : 224;
   static constexpr int kStages = 2;                  // K and V rings
-  static constexpr int kQBufs = 2;                   // Q double-buffered across work items
+  static constexpr int kQBufs = (DP == 64) ? 2 : 1;  // Q buffers across work items (smem-limited at DP = 128)
   static constexpr int kPanelsD = DP / 64;           // 64-column (128 B) panels along head dim
   static constexpr uint32_t kQTileBytes = BM * DP * 2;
   static constexpr uint32_t kKVTileBytes = BN * DP * 2;
   static constexpr uint32_t kPTileBytes = BM * BN * 2;
   static constexpr uint32_t kKVPanelBytes = BN * 128;  // one 64-column panel of a K/V tile
   // shared memory map (all tile bases 1024-aligned)
-  static constexpr uint32_t offQ = 0;
+  static constexpr uint32_t offQ = 0;                                  // [kQBufs item buffers][2 tiles]
   static constexpr uint32_t offK = offQ + kQBufs * 2 * kQTileBytes;
   static constexpr uint32_t offV = offK + kStages * kKVTileBytes;
   static constexpr uint32_t offP = offV + kStages * kKVTileBytes;
-  static constexpr uint32_t offBar = offP + 2 * kPTileBytes;
+  static constexpr uint32_t offX = offP + 2 * kPTileBytes;            // (m, l) exchange [2][NH][128] float2
+  static constexpr uint32_t offBar = offX + 2 * NH * 128 * 8;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;  // + barriers + alignment slack
   static_assert(kSmemBytes <= 232448, "shared memory budget");
+  static_assert(HB == 64, "one 64-key P panel per softmax stream");
   // TMEM columns
   static constexpr uint32_t colS = 0;            // S_t at colS + t*BN
-  static constexpr uint32_t colO = 2 * BN;       // O_t at colO + t*DP
+  static constexpr uint32_t colO = 2 * BN;       // O_{t,h} at colO + (t*NH + h)*DP
   static constexpr uint32_t kTmemCols = 512;
+  static_assert(colO + 2 * NH * DP <= 512, "TMEM budget");
 };
 
 struct Params {
@@ -75,7 +85,8 @@ struct Params {
 struct Barriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2];
+  uint64_t s_full[2], s_free[2];
+  uint64_t p_ready[2][2], pv_done[2][2];   // [tile][stream]
   uint32_t tmem_base;
 };
 
@@ -113,12 +124,29 @@ __device__ __forceinline__ Item decode_item(const Params& p, int w) {
   return it;
 }
 
+// packed fp32x2 math (FFMA2 / FADD2): halves the issue slots of the exponent arguments and row sums
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  uint64_t a, bb, cc, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a1) {
+  uint64_t a, c, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc0), "f"(acc1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc0), "=f"(acc1) : "l"(d));
+}
+
 template <int DP, bool kBF16>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<DP>::kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const Params p) {
   using C = Cfg<DP>;
-  constexpr int BN = C::BN;
+  constexpr int BN = C::BN, NH = C::NH, HB = C::HB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers& bars = *reinterpret_cast<Barriers*>(smem + C::offBar);
@@ -139,9 +167,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&bars.v_full[i], 1);
       mbar_init(&bars.v_empty[i], 2);
       mbar_init(&bars.s_full[i], 1);
-      mbar_init(&bars.s_free[i], 128);
-      mbar_init(&bars.p_ready[i], 128);
-      mbar_init(&bars.pv_done[i], 1);
+      mbar_init(&bars.s_free[i], 128 * NH);
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(&bars.p_ready[i][h], 128);
+        mbar_init(&bars.pv_done[i][h], 1);
+      }
     }
     fence_barrier_init();
   }
@@ -155,15 +185,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = bars.tmem_base;
 
   if (warp < 4) {
-    reg_dealloc<56>();
+    reg_dealloc<C::kRegsLow>();
     if (warp == 0) {
       // ===================== TMA producer (whole warp walks the loop, lane 0 issues) =====================
-      uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no & 1, K/V slot = blk & 1
+      uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no % kQBufs, K/V slot = blk & 1
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
         const Item it = decode_item<BN>(p, w);
         if (!it.valid) continue;
-        const uint32_t qb = item_no & 1;
-        if (item_no >= 2) mbar_wait(&bars.q_empty[qb], ((item_no >> 1) - 1) & 1);
+        const uint32_t qb = item_no % C::kQBufs;
+        if (item_no >= C::kQBufs) mbar_wait(&bars.q_empty[qb], ((item_no / C::kQBufs) - 1) & 1);
         if (lane == 0) {
           const int n_q_tiles = (it.row0 + BM < it.len_q) ? 2 : 1;
           mbar_arrive_expect_tx(&bars.q_full[qb], n_q_tiles * C::kQTileBytes);
@@ -202,18 +232,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t sV = smem_u32(smem + C::offV);
       const uint32_t sP = smem_u32(smem + C::offP) + t * C::kPTileBytes;
       const uint32_t tS = tmem_base + C::colS + t * BN;
-      const uint32_t tO = tmem_base + C::colO + t * DP;
+      const uint32_t tO = tmem_base + C::colO + t * NH * DP;
       uint32_t item_no = 0, blk = 0;  // same running counters as the producer
       uint32_t s_cnt = 0;             // S tiles issued by this warp (s_free / s_full phases)
-      uint32_t pv_cnt = 0;            // PV products issued by this warp (p_ready / pv_done phases)
+      uint32_t pv_cnt = 0;            // key blocks whose PV products were issued (p_ready / pv_done phases)
 
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
         const Item it = decode_item<BN>(p, w);
         if (!it.valid) continue;
-        const uint32_t qb = item_no & 1;
+        const uint32_t qb = item_no % C::kQBufs;
         const uint32_t sQ = smem_u32(smem + C::offQ) + (qb * 2 + t) * C::kQTileBytes;
         const int n = it.n_of(t);
-        mbar_wait(&bars.q_full[qb], (item_no >> 1) & 1);
+        mbar_wait(&bars.q_full[qb], (item_no / C::kQBufs) & 1);
 
         // S(j) = Q K_j^T into this tile's S buffer, then hand the K slot back (both tiles must do so)
         auto step_s = [&](int j, uint32_t kblk) {
@@ -251,39 +281,48 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (j + 1 < it.n_max) step_s(j + 1, blk + 1);
           const uint32_t slot = blk & 1;
           if (j < n) {
-            mbar_wait(&bars.p_ready[t], pv_cnt & 1);
             mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);
-            tc_fence_after();
-            if (lane == 0) {
 #pragma unroll
-              for (int kk = 0; kk < BN / 16; ++kk) {
-                const uint32_t a = sP + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-                const uint32_t b = sV + slot * C::kKVTileBytes + kk * 2048;  // 16 key rows x 128 B
-                umma_ss(tO, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, C::kKVPanelBytes, 1024),
-                        idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            for (int h = 0; h < NH; ++h) {
+              // O_{t,h} (+)= P_{t,h} V_j[h*64 : h*64+64, :]   (V rows are the K dimension: MN-major B)
+              mbar_wait(&bars.p_ready[t][h], pv_cnt & 1);
+              tc_fence_after();
+              if (lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < HB / 16; ++kk) {
+                  const uint32_t a = sP + h * (BM * 128) + kk * 32;
+                  const uint32_t b = sV + slot * C::kKVTileBytes + (h * HB + kk * 16) * 128;
+                  umma_ss(tO + h * DP, make_smem_desc_sw128(a, 16, 1024),
+                          make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                if (h == NH - 1) umma_commit(&bars.v_empty[slot]);
+                umma_commit(&bars.pv_done[t][h]);
               }
-              umma_commit(&bars.v_empty[slot]);
-              umma_commit(&bars.pv_done[t]);
+              __syncwarp();
             }
             ++pv_cnt;
           } else {
             mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);   // same pacing rule as for K
             if (lane == 0) umma_commit(&bars.v_empty[slot]);
+            __syncwarp();
           }
-          __syncwarp();
         }
         ++item_no;
       }
     }
   } else {
     // ===================== softmax warpgroups =====================
-    reg_alloc<224>();
-    const int t = (warp >> 2) - 1;                 // query tile of this warpgroup
+    reg_alloc<C::kRegsHigh>();
+    const int g = (warp >> 2) - 1;
+    const int t = g / NH;                          // query tile of this warpgroup
+    const int h = g % NH;                          // key half (stream) of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN;
-    const uint32_t tO = tmem_base + lane_addr + C::colO + t * DP;
-    uint8_t* sP = smem + C::offP + t * C::kPTileBytes;
+    const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN + h * HB;
+    const uint32_t tO_tile = tmem_base + lane_addr + C::colO + t * NH * DP;
+    const uint32_t tO = tO_tile + h * DP;
+    uint8_t* sP = smem + C::offP + t * C::kPTileBytes + h * (BM * 128);
+    float2* xchg = reinterpret_cast<float2*>(smem + C::offX) + t * NH * 128;
     const float scale_log2 = p.scale_log2;
     uint32_t cnt = 0;  // key blocks processed by this warpgroup (phases of s_full / pv_done)
 
@@ -298,9 +337,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n; ++j, ++cnt) {
         mbar_wait(&bars.s_full[t], cnt & 1);
         tc_fence_after();
-        float s[BN];
+        float s[HB];
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < HB / 32; ++c) {
           uint32_t u[32];
           tmem_ld32(tS + c * 32, u);
 #pragma unroll
@@ -310,18 +349,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         mbar_arrive(&bars.s_free[t]);   // S(j+1) may now overwrite the buffer while we work on registers
 
-        const int col0 = j * BN;
-        const bool partial = (col0 + BN > it.len_k) || (p.is_causal && (col0 + BN - 1 > it.row0 + t * BM));
+        const int col0 = j * BN + h * HB;
+        const bool partial = (col0 + HB > it.len_k) || (p.is_causal && (col0 + HB - 1 > it.row0 + t * BM));
         if (partial) {
-          const int limit = p.is_causal ? min(it.len_k, qrow + 1) : it.len_k;  // visible keys: col < limit
+          // visible keys of this row inside the half-block: local column c < lim
+          const int lim = (p.is_causal ? min(it.len_k, qrow + 1) : it.len_k) - col0;
 #pragma unroll
-          for (int c = 0; c < BN; ++c)
-            if (col0 + c >= limit) s[c] = -INFINITY;
+          for (int c = 0; c < HB; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
         }
         // row max: four independent chains
         float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int c = 4; c < BN; c += 4) {
+        for (int c = 4; c < HB; c += 4) {
           mx4[0] = fmaxf(mx4[0], s[c]);
           mx4[1] = fmaxf(mx4[1], s[c + 1]);
           mx4[2] = fmaxf(mx4[2], s[c + 2]);
@@ -329,27 +368,32 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
-        if (j == 0) {
+        float alpha = 1.f;
+        bool grow = false;
+        if (l == 0.f) {
+          // nothing accumulated yet for this row (first block, or only fully masked keys so far)
           m_used = (mx == -INFINITY) ? 0.f : mx;
         } else {
-          float alpha = 1.f;
-          const bool grow = (mx - m_used) * scale_log2 > kRescaleThreshold;
+          grow = (mx - m_used) * scale_log2 > kRescaleThreshold;
           if (grow) {
             alpha = fast_exp2((m_used - mx) * scale_log2);
             m_used = mx;
           }
-          // P tile and O accumulator are free once the previous PV MMA has completed
-          mbar_wait(&bars.pv_done[t], (cnt - 1) & 1);
+        }
+        if (j > 0) {
+          // P tile and O accumulator are free once the previous PV MMA of this stream has completed
+          mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-            for (int c = 0; c < DP / 32; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tO + c * 32, o);
+            // rare path: 16 columns at a time keeps the register footprint next to the live S row small
+#pragma unroll 1
+            for (int c = 0; c < DP / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + c * 32, o);
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
             }
             tmem_st_wait();
           }
@@ -359,59 +403,90 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float neg_m = -m_used * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c8 = 0; c8 < BN / 8; ++c8) {
+        for (int c8 = 0; c8 < HB / 8; ++c8) {
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(s[c8 * 8 + i], scale_log2, neg_m));
-          sum4[0] += e[0] + e[4];
-          sum4[1] += e[1] + e[5];
-          sum4[2] += e[2] + e[6];
-          sum4[3] += e[3] + e[7];
+          for (int i = 0; i < 8; i += 2) {
+            fma2(e[i], e[i + 1], s[c8 * 8 + i], s[c8 * 8 + i + 1], scale_log2, neg_m);
+            e[i] = fast_exp2(e[i]);
+            e[i + 1] = fast_exp2(e[i + 1]);
+          }
+          add2(sum4[0], sum4[1], e[0], e[1]);
+          add2(sum4[2], sum4[3], e[2], e[3]);
+          add2(sum4[0], sum4[1], e[4], e[5]);
+          add2(sum4[2], sum4[3], e[6], e[7]);
           uint4 v;
           v.x = pack2<kBF16>(e[0], e[1]);
           v.y = pack2<kBF16>(e[2], e[3]);
           v.z = pack2<kBF16>(e[4], e[5]);
           v.w = pack2<kBF16>(e[6], e[7]);
-          *reinterpret_cast<uint4*>(sP + (c8 >> 3) * (BM * 128) + sw128_offset(r, c8 & 7)) = v;
+          *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&bars.p_ready[t]);
+        mbar_arrive(&bars.p_ready[t][h]);
       }
 
-      // ---- epilogue: O / l -> global, LSE ----
-      mbar_wait(&bars.pv_done[t], (cnt - 1) & 1);
+      // ---- epilogue: merge the NH streams, O / l -> global, LSE ----
+      mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
       tc_fence_after();
       const bool valid = qrow < it.len_q;
-      const float inv_l = 1.f / l;
+      float w_self = 1.f, w_other = 0.f, m_all = m_used, l_all = l;
+      if constexpr (NH == 2) {
+        xchg[h * 128 + r] = make_float2(m_used, l);
+        if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
+        const float2 o = xchg[(h ^ 1) * 128 + r];
+        const bool has_self = l > 0.f, has_other = o.y > 0.f;
+        m_all = has_self ? (has_other ? fmaxf(m_used, o.x) : m_used) : o.x;
+        w_self = has_self ? fast_exp2((m_used - m_all) * scale_log2) : 0.f;
+        w_other = has_other ? fast_exp2((o.x - m_all) * scale_log2) : 0.f;
+        l_all = w_self * l + w_other * o.y;
+      }
+      const float inv_l = 1.f / l_all;
+      w_self *= inv_l;
+      w_other *= inv_l;
+      constexpr int kColsPerWG = DP / NH;   // output columns written by this warpgroup
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
-                      2 * (static_cast<int64_t>(it.q_begin + qrow) * p.o_row_stride + it.head * p.o_head_stride);
+                      2 * (static_cast<int64_t>(it.q_begin + qrow) * p.o_row_stride + it.head * p.o_head_stride +
+                           h * kColsPerWG);
 #pragma unroll
-      for (int c = 0; c < DP / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tO + c * 32, o);
+      for (int c = 0; c < kColsPerWG / 16; ++c) {
+        uint32_t o[16];
+        float f[16];
+        tmem_ld16(tO + h * kColsPerWG + c * 16, o);   // own accumulator, this warpgroup's columns
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * w_self;
+        if constexpr (NH == 2) {
+          tmem_ld16(tO_tile + (h ^ 1) * DP + h * kColsPerWG + c * 16, o);   // sibling stream, same columns
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(o[i]), w_other, f[i]);
+        }
         if (valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (c * 32 + g * 8 < p.headdim) {
+          for (int q = 0; q < 2; ++q) {
+            if (h * kColsPerWG + c * 16 + q * 8 < p.headdim) {
               uint4 v;
-              v.x = pack2<kBF16>(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
-              v.y = pack2<kBF16>(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
-              v.z = pack2<kBF16>(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
-              v.w = pack2<kBF16>(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + (c * 32 + g * 8) * 2) = v;
+              v.x = pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]);
+              v.y = pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]);
+              v.z = pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]);
+              v.w = pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(orow + (c * 16 + q * 8) * 2) = v;
             }
           }
         }
       }
-      if (valid)
+      if (valid && h == 0)
         p.lse[(static_cast<int64_t>(it.batch) * p.nheads + it.head) * p.lse_stride + qrow] =
-            m_used * p.scale + logf(l);
-      // the O reads above are complete (wait::ld); the next item's first PV (accumulate = 0) is only issued
-      // after this warpgroup's next p_ready, i.e. after this point in program order.
+            m_all * p.scale + logf(l_all);
+      // Both accumulators of this tile have been read (wait::ld) by this warpgroup; the sibling must be done
+      // too before either stream's next PV (accumulate = 0) may overwrite them, and before xchg is reused.
       tc_fence_before();
+      if constexpr (NH == 2) {
+        if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
+      }
     }
   }
 
@@ -436,7 +511,7 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_items < sms ? p.num_items : sms;
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   return check_launch("bp_fmha_fwd launch");
 }
 
