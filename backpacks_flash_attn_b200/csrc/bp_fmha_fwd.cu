@@ -80,7 +80,31 @@ struct Params {
   int32_t is_causal;
   float scale;        // softmax scale
   float scale_log2;   // scale * log2(e)
+  uint64_t* trace;    // debug: per-role event timestamps of CTA 0 (null in production)
 };
+
+// Debug timeline (compiled in only with -DBP_FMHA_TRACE): role-major buffer of (tag, clock) records written
+// by one thread per role of CTA 0; read by benchmarks/trace_fmha.py.
+constexpr int kTraceRecs = 512;
+#ifdef BP_FMHA_TRACE
+struct Tracer {
+  uint64_t* base;
+  int n;
+  __device__ __forceinline__ Tracer(uint64_t* buf, int role, bool on) : base(on && buf ? buf + role * kTraceRecs * 2 : nullptr), n(0) {}
+  __device__ __forceinline__ void rec(uint32_t ev, uint32_t j) {
+    if (base != nullptr && n < kTraceRecs) {
+      base[2 * n] = (static_cast<uint64_t>(ev) << 32) | j;
+      base[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+#else
+struct Tracer {
+  __device__ __forceinline__ Tracer(uint64_t*, int, bool) {}
+  __device__ __forceinline__ void rec(uint32_t, uint32_t) {}
+};
+#endif
 
 struct Barriers {
   uint64_t q_full[2], q_empty[2];
@@ -102,15 +126,17 @@ template <int BN>
 __device__ __forceinline__ Item decode_item(const Params& p, int w) {
   Item it;
   const int bh = p.batch * p.nheads;
-  const int pair = p.num_pairs - 1 - w / bh;  // heaviest (most key blocks) first
-  const int rem = w % bh;
+  const int pq = w / bh;                      // heaviest (most key blocks) pair first
+  const int rem = w - pq * bh;
   it.batch = rem / p.nheads;
-  it.head = rem % p.nheads;
-  it.q_begin = p.cu_q[it.batch];
-  it.len_q = p.cu_q[it.batch + 1] - it.q_begin;
-  it.k_begin = p.cu_k[it.batch];
-  it.len_k = p.cu_k[it.batch + 1] - it.k_begin;
-  it.row0 = pair * 2 * BM;
+  it.head = rem - it.batch * p.nheads;
+  const int2 cq = make_int2(__ldg(p.cu_q + it.batch), __ldg(p.cu_q + it.batch + 1));
+  const int2 ck = make_int2(__ldg(p.cu_k + it.batch), __ldg(p.cu_k + it.batch + 1));
+  it.q_begin = cq.x;
+  it.len_q = cq.y - cq.x;
+  it.k_begin = ck.x;
+  it.len_k = ck.y - ck.x;
+  it.row0 = (p.num_pairs - 1 - pq) * 2 * BM;
   auto blocks = [&](int r0) {
     if (r0 >= it.len_q) return 0;
     int kmax = it.len_k;
@@ -189,6 +215,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (warp == 0) {
       // ===================== TMA producer (whole warp walks the loop, lane 0 issues) =====================
       uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no % kQBufs, K/V slot = blk & 1
+      Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
         const Item it = decode_item<BN>(p, w);
         if (!it.valid) continue;
@@ -206,6 +233,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t slot = blk & 1;
           const int krow = it.k_begin + j * BN;
           if (blk >= 2) mbar_wait(&bars.k_empty[slot], ((blk >> 1) - 1) & 1);
+          tr.rec(1, blk);
           if (lane == 0) {
             mbar_arrive_expect_tx(&bars.k_full[slot], C::kKVTileBytes);
             for (int pn = 0; pn < C::kPanelsD; ++pn)
@@ -213,6 +241,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                           &bars.k_full[slot], pn * 64, it.head, krow);
           }
           if (blk >= 2) mbar_wait(&bars.v_empty[slot], ((blk >> 1) - 1) & 1);
+          tr.rec(2, blk);
           if (lane == 0) {
             mbar_arrive_expect_tx(&bars.v_full[slot], C::kKVTileBytes);
             for (int pn = 0; pn < C::kPanelsD; ++pn)
@@ -236,6 +265,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t item_no = 0, blk = 0;  // same running counters as the producer
       uint32_t s_cnt = 0;             // S tiles issued by this warp (s_free / s_full phases)
       uint32_t pv_cnt = 0;            // key blocks whose PV products were issued (p_ready / pv_done phases)
+      Tracer tr(p.trace, 1 + t, blockIdx.x == 0 && lane == 0);
 
       for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
         const Item it = decode_item<BN>(p, w);
@@ -250,8 +280,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t slot = kblk & 1;
           if (j < n) {
             if (s_cnt >= 1) mbar_wait(&bars.s_free[t], (s_cnt - 1) & 1);   // softmax has read the previous S
+            tr.rec(1, kblk);
             mbar_wait(&bars.k_full[slot], (kblk >> 1) & 1);
             tc_fence_after();
+            tr.rec(2, kblk);
             if (lane == 0) {
 #pragma unroll
               for (int kk = 0; kk < DP / 16; ++kk) {
@@ -287,6 +319,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               // O_{t,h} (+)= P_{t,h} V_j[h*64 : h*64+64, :]   (V rows are the K dimension: MN-major B)
               mbar_wait(&bars.p_ready[t][h], pv_cnt & 1);
               tc_fence_after();
+              tr.rec(3 + h, blk);
               if (lane == 0) {
 #pragma unroll
                 for (int kk = 0; kk < HB / 16; ++kk) {
@@ -325,7 +358,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float2* xchg = reinterpret_cast<float2*>(smem + C::offX) + t * NH * 128;
     const float scale_log2 = p.scale_log2;
     uint32_t cnt = 0;  // key blocks processed by this warpgroup (phases of s_full / pv_done)
-
+    Tracer tr(p.trace, 3 + g, blockIdx.x == 0 && r == 0);
     for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
       const Item it = decode_item<BN>(p, w);
       const int n = it.n_of(t);
@@ -335,8 +368,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float l = 0.f;
 
       for (int j = 0; j < n; ++j, ++cnt) {
+        tr.rec(0, cnt);
         mbar_wait(&bars.s_full[t], cnt & 1);
         tc_fence_after();
+        tr.rec(1, cnt);
         float s[HB];
 #pragma unroll
         for (int c = 0; c < HB / 32; ++c) {
@@ -348,6 +383,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bars.s_free[t]);   // S(j+1) may now overwrite the buffer while we work on registers
+        tr.rec(2, cnt);
 
         const int col0 = j * BN + h * HB;
         const bool partial = (col0 + HB > it.len_k) || (p.is_causal && (col0 + HB - 1 > it.row0 + t * BM));
@@ -380,10 +416,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             m_used = mx;
           }
         }
+        tr.rec(3, cnt);
         if (j > 0) {
           // P tile and O accumulator are free once the previous PV MMA of this stream has completed
           mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
           tc_fence_after();
+          tr.rec(4, cnt);
           if (__any_sync(0xffffffffu, grow)) {
             // rare path: 16 columns at a time keeps the register footprint next to the live S row small
 #pragma unroll 1
@@ -423,14 +461,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        tr.rec(5, cnt);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bars.p_ready[t][h]);
+        tr.rec(6, cnt);
       }
 
       // ---- epilogue: merge the NH streams, O / l -> global, LSE ----
+      tr.rec(7, cnt);
       mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
       tc_fence_after();
+      tr.rec(8, cnt);
       const bool valid = qrow < it.len_q;
       float w_self = 1.f, w_other = 0.f, m_all = m_used, l_all = l;
       if constexpr (NH == 2) {
@@ -480,13 +522,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (valid && h == 0)
         p.lse[(static_cast<int64_t>(it.batch) * p.nheads + it.head) * p.lse_stride + qrow] =
-            m_all * p.scale + logf(l_all);
+            m_all * p.scale + __logf(l_all);
       // Both accumulators of this tile have been read (wait::ld) by this warpgroup; the sibling must be done
       // too before either stream's next PV (accumulate = 0) may overwrite them, and before xchg is reused.
       tc_fence_before();
       if constexpr (NH == 2) {
         if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
       }
+      tr.rec(9, cnt);
     }
   }
 
@@ -517,6 +560,11 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
 
 }  // namespace fmha
 }  // namespace bp
+
+// Debug hook (not part of the public ABI): when set, CTA 0 of the next launches writes its timeline here
+// (7 roles x kTraceRecs x 2 uint64).  Used by benchmarks/trace_fmha.py only.
+static uint64_t* g_fmha_trace = nullptr;
+extern "C" void bp_debug_set_fmha_trace(void* buf) { g_fmha_trace = static_cast<uint64_t*>(buf); }
 
 extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
                            const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
@@ -581,6 +629,7 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
   p.is_causal = is_causal ? 1 : 0;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * fmha::kLog2e;
+  p.trace = g_fmha_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
   if (DP == 64) return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, p, st) : fmha::launch<64, false>(tmQ, tmK, tmV, p, st);

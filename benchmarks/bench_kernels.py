@@ -26,19 +26,24 @@ def peaks():
         return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def time_fn(fn, variants, iters, warmup=5):
-    """fn(i) runs variant i; variants rotate so that consecutive launches never see a warm L2."""
+def time_fn(fn, variants, iters, warmup=5, inner=8):
+    """fn(i) runs variant i; variants rotate so that consecutive launches never see a warm L2.  Each timed
+    sample brackets `inner` back-to-back launches with one pair of CUDA events (so the host-side launch
+    preparation is hidden behind the previous kernel and does not leak into the measurement)."""
     for i in range(warmup):
         fn(i % variants)
     torch.cuda.synchronize()
     times = []
-    for i in range(iters):
+    k = 0
+    for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(k % variants); k += 1          # keeps the GPU busy while the timed launches are being queued
         a.record()
-        fn(i % variants)
+        for _ in range(inner):
+            fn(k % variants); k += 1
         b.record()
         b.synchronize()
-        times.append(a.elapsed_time(b) * 1e-3)
+        times.append(a.elapsed_time(b) * 1e-3 / inner)
     return statistics.median(times), min(times)
 
 
