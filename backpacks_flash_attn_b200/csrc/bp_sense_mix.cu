@@ -211,15 +211,18 @@ struct MixCfg {
   static constexpr uint32_t kKTileBytes = BN * 128 * PK;
   static constexpr uint32_t kCPanelBytes = BN * 128;           // 64 keys x 64 columns
   static constexpr uint32_t kCTileBytes = (DC / 64) * kCPanelBytes;
-  static constexpr uint32_t kPTileBytes = BM * BN * 2;
   static constexpr uint32_t offQ = 0;
   static constexpr uint32_t offK = offQ + QS * kQTileBytes;
   static constexpr uint32_t offC = offK + KS * kKTileBytes;
-  static constexpr uint32_t offP = offC + CS * kCTileBytes;
-  static constexpr uint32_t offBar = offP + 2 * kPTileBytes;
+  static constexpr uint32_t offBar = offC + CS * kCTileBytes;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
-  static constexpr uint32_t colO = 0, colS = DC;
+  // TMEM: O accumulator, one S buffer (handed back as soon as the softmax warps hold it in registers) and
+  // two P buffers: P (bf16/f16, two values per 32-bit column) is the A operand of the PV product and is
+  // read by the tensor core straight from TMEM -- it never touches shared memory, whose bandwidth is
+  // what bounds this kernel (every K-step already streams a 64 x 384 slice of C through it).
+  static constexpr uint32_t colO = 0, colS = DC, colP = DC + BN;
   static constexpr uint32_t kTmemCols = 512;
+  static_assert(colP + 2 * (BN / 2) <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
@@ -227,7 +230,7 @@ struct MixBarriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[2], k_empty[2];
   uint64_t c_full[3], c_empty[3];
-  uint64_t s_full[2], p_ready[2], p_free[2];
+  uint64_t s_full, s_free, p_ready[2], p_free[2];
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -268,8 +271,9 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
       mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
-      mbar_init(&bars.s_full[i], 1), mbar_init(&bars.p_ready[i], 128), mbar_init(&bars.p_free[i], 1);
+      mbar_init(&bars.p_ready[i], 128), mbar_init(&bars.p_free[i], 1);
     }
+    mbar_init(&bars.s_full, 1), mbar_init(&bars.s_free, 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars.c_full[i], 1), mbar_init(&bars.c_empty[i], 1);
     mbar_init(&bars.o_full, 1);
     fence_barrier_init();
@@ -334,47 +338,47 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
       const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
       const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
-      const uint32_t sC = smem_u32(smem + C::offC), sP = smem_u32(smem + C::offP);
+      const uint32_t sC = smem_u32(smem + C::offC);
 
+      // S(n) = Q_l K_l[j]^T into the single S buffer (free once the warpgroup of step n-1 has loaded S(n-1))
       auto issue_s = [&](int n) {
         const int sense = n / nj, j = n - sense * nj;
         const int qs = sense % C::QS, ks = n % C::KS;
         if (j == 0) mbar_wait(&bars.q_full[qs], (sense / C::QS) & 1);
         mbar_wait(&bars.k_full[ks], (n / C::KS) & 1);
+        if (n >= 1) mbar_wait(&bars.s_free, (n - 1) & 1);
         tc_fence_after();
         if (lane == 0) {
           for (int kk = 0; kk < p.ksteps; ++kk) {
             const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
             const uint32_t b = sK + ks * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
-            umma_ss(tmem_base + C::colS + (n & 1) * BN, make_smem_desc_sw128(a, 16, 1024),
-                    make_smem_desc_sw128(b, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+            umma_ss(tmem_base + C::colS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024),
+                    idesc_s, kk > 0 ? 1u : 0u);
           }
           umma_commit(&bars.k_empty[ks]);
           if (j == nj - 1) umma_commit(&bars.q_empty[qs]);
-          umma_commit(&bars.s_full[n & 1]);
+          umma_commit(&bars.s_full);
         }
         __syncwarp();
       };
 
       issue_s(0);
-      if (n_steps > 1) issue_s(1);
       for (int n = 0; n < n_steps; ++n) {
-        mbar_wait(&bars.p_ready[n & 1], (n >> 1) & 1);
-        tc_fence_after();
-        if (n + 2 < n_steps) issue_s(n + 2);
+        if (n + 1 < n_steps) issue_s(n + 1);
         const int cs = n % C::CS;
+        mbar_wait(&bars.p_ready[n & 1], (n >> 1) & 1);
         mbar_wait(&bars.c_full[cs], (n / C::CS) & 1);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_base = sP + (n & 1) * C::kPTileBytes;
+          const uint32_t a_tmem = tmem_base + C::colP + (n & 1) * (BN / 2);   // P(n): 8 columns per K-step of 16
           const uint32_t b_base = sC + cs * C::kCTileBytes;
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
-            const uint64_t a = make_smem_desc_sw128(a_base + kk * 32, 16, 1024);
-            umma_ss(tmem_base + C::colO, a, make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024),
-                    idesc_pv1, (n > 0 || kk > 0) ? 1u : 0u);
+            umma_ts(tmem_base + C::colO, a_tmem + kk * 8,
+                    make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024), idesc_pv1,
+                    (n > 0 || kk > 0) ? 1u : 0u);
             if (n2 > 0)
-              umma_ss(tmem_base + C::colO + 256, a,
+              umma_ts(tmem_base + C::colO + 256, a_tmem + kk * 8,
                       make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024), idesc_pv2,
                       (n > 0 || kk > 0) ? 1u : 0u);
           }
@@ -393,8 +397,8 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int qrow = row0 + r;
     const bool valid = qrow < S;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + C::colS + w * BN;
-    uint8_t* sP = smem + C::offP + w * C::kPTileBytes;
+    const uint32_t tS = tmem_base + lane_addr + C::colS;
+    const uint32_t tP = tmem_base + lane_addr + C::colP + w * (BN / 2);
     const float c2 = p.scale_log2;
     const float* lse_row = p.lse + static_cast<int64_t>(batch) * p.nv * S + (valid ? qrow : S - 1);
     int cur_sense = -1;
@@ -406,7 +410,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         cur_sense = sense;
         neg_lse2 = -__ldg(lse_row + static_cast<int64_t>(sense) * S) * kLog2e;
       }
-      mbar_wait(&bars.s_full[w], i & 1);
+      mbar_wait(&bars.s_full, n & 1);
       tc_fence_after();
       float s[BN];
 #pragma unroll
@@ -417,26 +421,24 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int k = 0; k < 32; ++k) s[c * 32 + k] = __uint_as_float(u[k]);
       }
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars.s_free);   // S(n+1) may be computed while this step's exponentials run
       const int col0 = j * BN;
       if (col0 + BN - 1 > row0) {
 #pragma unroll
         for (int c = 0; c < BN; ++c)
           if (col0 + c > qrow) s[c] = -INFINITY;
       }
-      if (i >= 1) mbar_wait(&bars.p_free[w], (i - 1) & 1);  // PV of step n-2 has drained this P tile
+      uint32_t pk[BN / 2];
 #pragma unroll
-      for (int c8 = 0; c8 < BN / 8; ++c8) {
-        float e[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = fast_exp2(fmaf(s[c8 * 8 + k], c2, neg_lse2));
-        uint4 v;
-        v.x = pack2<kBF16>(e[0], e[1]);
-        v.y = pack2<kBF16>(e[2], e[3]);
-        v.z = pack2<kBF16>(e[4], e[5]);
-        v.w = pack2<kBF16>(e[6], e[7]);
-        *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
+      for (int c = 0; c < BN / 2; ++c)
+        pk[c] = pack2<kBF16>(fast_exp2(fmaf(s[2 * c], c2, neg_lse2)), fast_exp2(fmaf(s[2 * c + 1], c2, neg_lse2)));
+      if (i >= 1) {
+        mbar_wait(&bars.p_free[w], (i - 1) & 1);   // the PV product of step n-2 has consumed this P buffer
+        tc_fence_after();
       }
-      fence_proxy_async_smem();
+      tmem_st32(tP, pk);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars.p_ready[w]);
     }

@@ -148,6 +148,41 @@ class BackpackModel(GPTPreTrainedModel):
         self.contextualization_attn = ContextSelfAttn(self.num_content_vectors, config.n_embd, **factory_kwargs)
         # fused sense-mix follows use_flash_attn unless the config says otherwise
         self.fused_sense_mix = getattr(config, "fused_sense_mix", getattr(config, "use_flash_attn", False))
+        # optional inference-time table of sense vectors, see build_sense_table()
+        self.sense_table = None
+
+    @torch.no_grad()
+    def build_sense_table(self, chunk: int = 8192):
+        """Precompute C(x) for every vocabulary item.
+
+        The content model is context-free: it sees the word embedding only (no positions, identity mixer;
+        training/src/models/backpack.py:258, :125-143), so for inference `content_model(ids)` is a row gather
+        from a (vocab, nv, d) table computed once with the very same kernels.  The analysis scripts of the
+        reference rely on the same fact (training/src/run_simlex.py:179-184).  The table must be rebuilt
+        (or dropped with `drop_sense_table()`) whenever the content-model weights change."""
+        emb = self.embeddings.word_embeddings
+        vocab, d, nv = emb.num_embeddings, self.config.n_embd, self.num_content_vectors
+        table = torch.empty((vocab, nv, d), dtype=emb.weight.dtype, device=emb.weight.device)
+        was_training = self.content_model.training
+        self.content_model.eval()
+        for start in range(0, vocab, chunk):
+            ids = torch.arange(start, min(vocab, start + chunk), device=emb.weight.device).unsqueeze(0)
+            table[start:start + ids.shape[1]] = self.content_model(ids)[0].transpose(0, 1)
+        self.content_model.train(was_training)
+        self.sense_table = table
+        return table
+
+    def drop_sense_table(self):
+        self.sense_table = None
+
+    def content(self, input_ids, position_ids=None, inference_params=None):
+        """Sense vectors (b, nv, s, d): the content model, or a gather from the precomputed table."""
+        if self.sense_table is None or self.training:
+            return self.content_model(input_ids, position_ids, inference_params)
+        b, s = input_ids.shape
+        flat = self.sense_table.view(self.sense_table.shape[0], -1)
+        rows = torch.nn.functional.embedding(input_ids, flat)                      # (b, s, nv*d)
+        return rows.view(b, s, self.num_content_vectors, self.config.n_embd).transpose(1, 2)
 
     def sense_mix(self, contextl_hidden_states, content):
         """sum_l alpha_l(contextl_hidden_states) @ content_l without materialising alpha; `content` may be any
@@ -158,7 +193,7 @@ class BackpackModel(GPTPreTrainedModel):
     def forward(self, input_ids, position_ids=None, inference_params=None):
         contextl_hidden_states = self.gpt2_model(input_ids, position_ids=position_ids,
                                                  inference_params=inference_params)
-        content = self.content_model(input_ids, position_ids, inference_params)  # (b, nv, s, d)
+        content = self.content(input_ids, position_ids, inference_params)  # (b, nv, s, d)
         if self.fused_sense_mix:
             return self.sense_mix(contextl_hidden_states, content)
         contextualization = self.contextualization_attn(contextl_hidden_states)  # (b, nv, s, s)

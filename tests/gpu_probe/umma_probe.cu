@@ -4,6 +4,9 @@
 //   case B: D[128x64]  = P[128x128] * V[128x64]        P written by threads with sw128_offset(),
 //                                                      V TMA-loaded [key rows x 64] consumed MN-major
 //   case C: like B with N = 128 (two 64-column V panels, LBO = panel stride)
+//   case D: D[128x64]  = P[128x128] * V[128x64]        P packed bf16x2 into TMEM by tcgen05.st (32x32b: register c
+//                                                      of lane r = elements (r, 2c) | (r, 2c+1) << 16), A operand read
+//                                                      from TMEM (tcgen05.mma [d], [a_tmem], b_desc)
 // Prints "caseX max_err <e>" lines and exits non-zero on mismatch.
 #include <math.h>
 #include <stdio.h>
@@ -41,7 +44,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* sB = smem + 32768;    // 32 KB reserved
   Smem& sm = *reinterpret_cast<Smem*>(smem + 65536);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
-  constexpr int N = MODE == 0 ? 128 : (MODE == 1 ? 64 : 128);
+  constexpr int N = MODE == 0 ? 128 : (MODE == 2 ? 128 : 64);
   if (threadIdx.x == 0) {
     mbar_init(&sm.full, 1);
     mbar_init(&sm.done, 1);
@@ -56,7 +59,18 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem = sm.tmem;
 
-  if (MODE != 0) {
+  if (MODE == 3) {
+    // P row r -> 64 packed words -> TMEM columns [64, 128) of lane r
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(Pg + r * 128);
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + 64;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      for (int i = 0; i < 32; ++i) v[i] = src[c * 32 + i];
+      tmem_st32(taddr + c * 32, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  } else if (MODE != 0) {
     // P tile: thread r owns row r, 128 bf16 = 16 chunks of 16 B, two 64-column panels
     const uint4* src = reinterpret_cast<const uint4*>(Pg + r * 128);
     for (int c = 0; c < 16; ++c)
@@ -81,6 +95,10 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int kk = 0; kk < 4; ++kk)
         umma_ss(tmem, make_smem_desc_sw128(smem_u32(sA) + kk * 32, 16, 1024),
                 make_smem_desc_sw128(smem_u32(sB) + kk * 32, 16, 1024), idesc, kk > 0);
+    } else if (MODE == 3) {
+      constexpr uint32_t idesc = make_idesc(true, 128, N, false, true);
+      for (int kk = 0; kk < 8; ++kk)
+        umma_ts(tmem, tmem + 64 + kk * 8, make_smem_desc_sw128(smem_u32(sB) + kk * 2048, 16384, 1024), idesc, kk > 0);
     } else {
       constexpr uint32_t idesc = make_idesc(true, 128, N, false, true);
       for (int kk = 0; kk < 8; ++kk)
@@ -155,8 +173,8 @@ int main() {
     if (!(err < 1e-3)) bad |= 1;
   }
   // ---------------- case B / C ----------------
-  for (int mode = 1; mode <= 2; ++mode) {
-    const int N = mode == 1 ? 64 : 128;
+  for (int mode = 1; mode <= 3; ++mode) {
+    const int N = mode == 2 ? 128 : 64;
     std::vector<float> P(128 * 128), V(128 * N);
     for (auto& x : P) x = rnd();
     for (auto& x : V) x = rnd();
@@ -180,9 +198,12 @@ int main() {
     if (mode == 1) {
       CK(cudaFuncSetAttribute(probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       probe_kernel<1><<<1, 128, smem_bytes>>>(tV, tV, dP, dD);
-    } else {
+    } else if (mode == 2) {
       CK(cudaFuncSetAttribute(probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       probe_kernel<2><<<1, 128, smem_bytes>>>(tV, tV, dP, dD);
+    } else {
+      CK(cudaFuncSetAttribute(probe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      probe_kernel<3><<<1, 128, smem_bytes>>>(tV, tV, dP, dD);
     }
     CK(cudaDeviceSynchronize());
     std::vector<float> D(128 * N);
@@ -194,7 +215,7 @@ int main() {
         for (int k = 0; k < 128; ++k) ref += (double)P[i * 128 + k] * V[k * N + j];
         err = fmax(err, fabs(ref - D[i * N + j]));
       }
-    printf("case%c max_err %.3e\n", mode == 1 ? 'B' : 'C', err);
+    printf("case%c max_err %.3e\n", "ABCD"[mode], err);
     if (!(err < 2e-3)) bad |= (1 << mode);
   }
   printf(bad ? "PROBE FAILED mask=%d\n" : "PROBE OK %d\n", bad);

@@ -86,6 +86,29 @@ def test_fused_and_eager_sense_mix_agree_inside_the_model():
         assert (got2.float() - got.float()).abs().max() > 1e-3
 
 
+def test_sense_table_is_equivalent_to_the_content_model():
+    """C(x) depends on the token id only, so a (vocab, nv, d) table gathered by id must
+    reproduce content_model(ids) and leave the logits unchanged."""
+    fused, _ = _pair(dict(n_embd=384, n_head=6, n_layer=2, n_positions=512))
+    ids = torch.randint(0, 50257, (3, 200), device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+    with torch.inference_mode():
+        base_content = fused.transformer.content_model(ids)
+        base_logits = fused(ids).logits
+        table = fused.transformer.build_sense_table(chunk=4096)
+        assert table.shape == (50264, 16, 384)
+        got_content = fused.transformer.content(ids)
+        got_logits = fused(ids).logits
+        fused.transformer.drop_sense_table()
+        again = fused(ids).logits
+    assert got_content.shape == base_content.shape and got_content.stride() == base_content.stride()
+    # identical kernels on identical rows; a library GEMM may pick another tile shape for another batch size,
+    # so allow one bf16 ulp of the O(1) values
+    assert (got_content.float() - base_content.float()).abs().max() <= 2 ** -6
+    assert (got_logits.float() - base_logits.float()).abs().max() <= 0.06
+    assert (got_logits.argmax(-1) == base_logits.argmax(-1)).float().mean() > 0.995
+    assert torch.equal(again, base_logits)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_non_default_device():
     """Launches follow the tensors' device (the reference guards with CUDAGuard, fmha_api.cpp:267)."""
