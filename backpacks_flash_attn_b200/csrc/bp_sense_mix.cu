@@ -230,7 +230,7 @@ struct MixBarriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[2], k_empty[2];
   uint64_t c_full[3], c_empty[3];
-  uint64_t s_full, s_free, p_ready[2], p_free[2];
+  uint64_t s_full[2], s_free, p_ready[2], p_free[2];   // s_full[n & 1]: each warpgroup must see every phase
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -273,7 +273,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
       mbar_init(&bars.p_ready[i], 128), mbar_init(&bars.p_free[i], 1);
     }
-    mbar_init(&bars.s_full, 1), mbar_init(&bars.s_free, 128);
+    mbar_init(&bars.s_full[0], 1), mbar_init(&bars.s_full[1], 1), mbar_init(&bars.s_free, 128);
     for (int i = 0; i < 3; ++i) mbar_init(&bars.c_full[i], 1), mbar_init(&bars.c_empty[i], 1);
     mbar_init(&bars.o_full, 1);
     fence_barrier_init();
@@ -357,7 +357,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
           umma_commit(&bars.k_empty[ks]);
           if (j == nj - 1) umma_commit(&bars.q_empty[qs]);
-          umma_commit(&bars.s_full);
+          umma_commit(&bars.s_full[n & 1]);
         }
         __syncwarp();
       };
@@ -410,7 +410,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         cur_sense = sense;
         neg_lse2 = -__ldg(lse_row + static_cast<int64_t>(sense) * S) * kLog2e;
       }
-      mbar_wait(&bars.s_full, n & 1);
+      mbar_wait(&bars.s_full[w], i & 1);
       tc_fence_after();
       float s[BN];
 #pragma unroll
