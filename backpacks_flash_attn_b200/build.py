@@ -50,7 +50,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def _compile(src: str, obj: str) -> str:
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+    extra = os.environ.get("BP_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DBP_TRACE for timeline debugging
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

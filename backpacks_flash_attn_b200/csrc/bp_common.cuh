@@ -271,6 +271,31 @@ __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// Debug timeline (compiled in only with -DBP_TRACE): role-major buffer of (tag, clock) records written by one
+// thread per warp role of CTA 0; dumped by benchmarks/trace_kernel.py.  A no-op otherwise.
+constexpr int kTraceRecs = 512;
+#ifdef BP_TRACE
+struct Tracer {
+  uint64_t* base;
+  int n;
+  __device__ __forceinline__ Tracer(uint64_t* buf, int role, bool on)
+      : base(on && buf ? buf + role * kTraceRecs * 2 : nullptr), n(0) {}
+  __device__ __forceinline__ void rec(uint32_t ev, uint32_t j) {
+    if (base != nullptr && n < kTraceRecs) {
+      base[2 * n] = (static_cast<uint64_t>(ev) << 32) | j;
+      base[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+#else
+struct Tracer {
+  __device__ __forceinline__ Tracer(uint64_t*, int, bool) {}
+  __device__ __forceinline__ void rec(uint32_t, uint32_t) {}
+};
+#endif
+extern uint64_t* g_trace;   // host-side pointer handed to the kernels' Params (bp_debug_set_trace)
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows x 128 B] SWIZZLE_128B panel
 // whose base is 1024-byte aligned (the layout TMA writes and UMMA reads).
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {

@@ -83,29 +83,6 @@ struct Params {
   uint64_t* trace;    // debug: per-role event timestamps of CTA 0 (null in production)
 };
 
-// Debug timeline (compiled in only with -DBP_FMHA_TRACE): role-major buffer of (tag, clock) records written
-// by one thread per role of CTA 0; read by benchmarks/trace_fmha.py.
-constexpr int kTraceRecs = 512;
-#ifdef BP_FMHA_TRACE
-struct Tracer {
-  uint64_t* base;
-  int n;
-  __device__ __forceinline__ Tracer(uint64_t* buf, int role, bool on) : base(on && buf ? buf + role * kTraceRecs * 2 : nullptr), n(0) {}
-  __device__ __forceinline__ void rec(uint32_t ev, uint32_t j) {
-    if (base != nullptr && n < kTraceRecs) {
-      base[2 * n] = (static_cast<uint64_t>(ev) << 32) | j;
-      base[2 * n + 1] = clock64();
-      ++n;
-    }
-  }
-};
-#else
-struct Tracer {
-  __device__ __forceinline__ Tracer(uint64_t*, int, bool) {}
-  __device__ __forceinline__ void rec(uint32_t, uint32_t) {}
-};
-#endif
-
 struct Barriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
@@ -563,8 +540,8 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
 
 // Debug hook (not part of the public ABI): when set, CTA 0 of the next launches writes its timeline here
 // (7 roles x kTraceRecs x 2 uint64).  Used by benchmarks/trace_fmha.py only.
-static uint64_t* g_fmha_trace = nullptr;
-extern "C" void bp_debug_set_fmha_trace(void* buf) { g_fmha_trace = static_cast<uint64_t*>(buf); }
+namespace bp { uint64_t* g_trace = nullptr; }
+extern "C" void bp_debug_set_trace(void* buf) { bp::g_trace = static_cast<uint64_t*>(buf); }
 
 extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
                            const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
@@ -629,7 +606,7 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
   p.is_causal = is_causal ? 1 : 0;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * fmha::kLog2e;
-  p.trace = g_fmha_trace;
+  p.trace = g_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
   if (DP == 64) return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, p, st) : fmha::launch<64, false>(tmQ, tmK, tmV, p, st);

@@ -14,8 +14,12 @@
 // Normalising per sense needs the row statistics before the first P.C product, hence two passes; pass 1
 // costs 1/17 of the MMA work.  The accumulator of a 128-row tile at d=768 is 384 KB fp32 -- more than
 // the 256 KB of TMEM -- so one CTA owns a 384-column chunk of the output (O: 384 TMEM columns, S: 2 x 64).
-// Layout per CTA (384 threads): warp 0 = TMA producer for C, warp 3 = TMA producer for Q_l / K_l,
-// warp 1 = MMA issuer, warp 2 = TMEM allocator, warpgroups 1/2 = softmax for even/odd steps + epilogue.
+// Layout per CTA (384 threads): warp 0 = TMA producer for C, warp 3 = TMA producer for Q_l / K_l (+ TMEM
+// allocator), warp 1 = issuer of the P.C products, warp 2 = issuer of the S = Q K^T products, warpgroups 1/2 =
+// softmax for even/odd steps + epilogue.  A satisfied mbarrier wait still costs ~200 cycles of latency on
+// the single issuing thread, so each MMA issuer waits on exactly ONE barrier per step: the barrier that the
+// TMA producer arms for the operand tile also counts the 128 softmax threads that hand over S / P
+// ("s_go" = K tile landed + S buffer drained, "pv_go" = C tile landed + P stored).
 // C_l(x_j) tiles are consumed as MN-major B operands exactly as TMA wrote them (no transpose).
 #include "bp_common.cuh"
 #include "bp_host.h"
@@ -228,9 +232,9 @@ struct MixCfg {
 
 struct MixBarriers {
   uint64_t q_full[2], q_empty[2];
-  uint64_t k_full[2], k_empty[2];
-  uint64_t c_full[3], c_empty[3];
-  uint64_t s_full[2], s_free, p_ready[2], p_free[2];   // s_full[n & 1]: each warpgroup must see every phase
+  uint64_t s_go[2], k_empty[2];    // s_go[n & 1]: K(n) landed (tx) + S(n-1) drained by its 128 softmax threads
+  uint64_t pv_go[3], c_empty[3];   // pv_go[n % CS]: C(n) landed (tx) + P(n) stored by its 128 softmax threads
+  uint64_t s_full[2], p_free[2];   // s_full[n & 1]: each warpgroup must see every phase
   uint64_t o_full;
   uint32_t tmem_base;
 };
@@ -241,6 +245,7 @@ struct MixParams {
   int32_t seqlen, nv, dk, ksteps, d, num_qtiles, num_chunks;
   int32_t c_sense_inner;  // content tensor-map dims are (d, nv, s, b) instead of (d, s, nv, b)
   float scale_log2;
+  uint64_t* trace;        // debug timeline (BP_TRACE builds), else null
 };
 
 template <int PK, bool kBF16>
@@ -270,15 +275,14 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmC);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
-      mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
-      mbar_init(&bars.p_ready[i], 128), mbar_init(&bars.p_free[i], 1);
+      mbar_init(&bars.s_go[i], 129), mbar_init(&bars.k_empty[i], 1);
+      mbar_init(&bars.s_full[i], 1), mbar_init(&bars.p_free[i], 1);
     }
-    mbar_init(&bars.s_full[0], 1), mbar_init(&bars.s_full[1], 1), mbar_init(&bars.s_free, 128);
-    for (int i = 0; i < 3; ++i) mbar_init(&bars.c_full[i], 1), mbar_init(&bars.c_empty[i], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&bars.pv_go[i], 129), mbar_init(&bars.c_empty[i], 1);
     mbar_init(&bars.o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 3) {
     tmem_alloc(&bars.tmem_base, C::kTmemCols);
     tmem_relinquish();
   }
@@ -292,18 +296,21 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     reg_dealloc<56>();
     if (warp == 0) {
       // ---- producer A: content tiles C_l[j] : (ncols/64) panels of [64 keys x 64 columns] ----
+      Tracer tr(p.trace, 0, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
       for (int n = 0; n < n_steps; ++n) {
         const int slot = n % C::CS;
+        tr.rec(0, n);
         if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
+        tr.rec(1, n);
         if (lane == 0) {
           const int sense = n / nj, j = n - sense * nj;
-          mbar_arrive_expect_tx(&bars.c_full[slot], (ncols / 64) * C::kCPanelBytes);
+          mbar_arrive_expect_tx(&bars.pv_go[slot], (ncols / 64) * C::kCPanelBytes);
           for (int pn = 0; pn < ncols / 64; ++pn) {
             uint8_t* dst = smem + C::offC + slot * C::kCTileBytes + pn * C::kCPanelBytes;
             if (p.c_sense_inner)
-              tma_load_4d(dst, &tmC, &bars.c_full[slot], col_base + pn * 64, sense, j * BN, batch);
+              tma_load_4d(dst, &tmC, &bars.pv_go[slot], col_base + pn * 64, sense, j * BN, batch);
             else
-              tma_load_4d(dst, &tmC, &bars.c_full[slot], col_base + pn * 64, j * BN, sense, batch);
+              tma_load_4d(dst, &tmC, &bars.pv_go[slot], col_base + pn * 64, j * BN, sense, batch);
           }
         }
         __syncwarp();
@@ -325,29 +332,26 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int slot = n % C::KS;
         if (n >= C::KS) mbar_wait(&bars.k_empty[slot], ((n / C::KS) - 1) & 1);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKTileBytes);
+          mbar_arrive_expect_tx(&bars.s_go[slot], C::kKTileBytes);
           for (int pn = 0; pn < PK; ++pn)
-            tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmK, &bars.k_full[slot], pn * 64,
+            tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmK, &bars.s_go[slot], pn * 64,
                         p.nv + sense, tok0 + j * BN);
         }
         __syncwarp();
       }
-    } else if (warp == 1) {
-      // ---- MMA issuer ----
+    } else if (warp == 2) {
+      // ---- issuer of S(n) = Q_l K_l[j]^T into the single S buffer ----
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
-      const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
-      const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
       const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
-      const uint32_t sC = smem_u32(smem + C::offC);
-
-      // S(n) = Q_l K_l[j]^T into the single S buffer (free once the warpgroup of step n-1 has loaded S(n-1))
-      auto issue_s = [&](int n) {
+      Tracer tr(p.trace, 4, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
+      for (int n = 0; n < n_steps; ++n) {
         const int sense = n / nj, j = n - sense * nj;
-        const int qs = sense % C::QS, ks = n % C::KS;
+        const int qs = sense % C::QS, ks = n & 1;
+        tr.rec(0, n);
         if (j == 0) mbar_wait(&bars.q_full[qs], (sense / C::QS) & 1);
-        mbar_wait(&bars.k_full[ks], (n / C::KS) & 1);
-        if (n >= 1) mbar_wait(&bars.s_free, (n - 1) & 1);
+        mbar_wait(&bars.s_go[ks], (n >> 1) & 1);
         tc_fence_after();
+        tr.rec(1, n);
         if (lane == 0) {
           for (int kk = 0; kk < p.ksteps; ++kk) {
             const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
@@ -360,15 +364,19 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_commit(&bars.s_full[n & 1]);
         }
         __syncwarp();
-      };
-
-      issue_s(0);
+      }
+    } else if (warp == 1) {
+      // ---- issuer of O += P(n) C_l[j]: P from TMEM (A operand), C tile MN-major from shared memory ----
+      const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
+      const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
+      const uint32_t sC = smem_u32(smem + C::offC);
+      Tracer tr(p.trace, 1, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
       for (int n = 0; n < n_steps; ++n) {
-        if (n + 1 < n_steps) issue_s(n + 1);
         const int cs = n % C::CS;
-        mbar_wait(&bars.p_ready[n & 1], (n >> 1) & 1);
-        mbar_wait(&bars.c_full[cs], (n / C::CS) & 1);
+        tr.rec(3, n);
+        mbar_wait(&bars.pv_go[cs], (n / C::CS) & 1);
         tc_fence_after();
+        tr.rec(5, n);
         if (lane == 0) {
           const uint32_t a_tmem = tmem_base + C::colP + (n & 1) * (BN / 2);   // P(n): 8 columns per K-step of 16
           const uint32_t b_base = sC + cs * C::kCTileBytes;
@@ -387,6 +395,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (n == n_steps - 1) umma_commit(&bars.o_full);
         }
         __syncwarp();
+        tr.rec(6, n);
       }
     }
   } else {
@@ -404,14 +413,18 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int cur_sense = -1;
     float neg_lse2 = 0.f;
     int i = 0;
+    Tracer tr(p.trace, 2 + w, blockIdx.x == 0 && blockIdx.y == 0 && r == 0);
+    if (w == 1) mbar_arrive(&bars.s_go[0]);   // "S(-1) drained": lets S(0) go as soon as K(0) has landed
     for (int n = w; n < n_steps; n += 2, ++i) {
       const int sense = n / nj, j = n - sense * nj;
       if (sense != cur_sense) {
         cur_sense = sense;
         neg_lse2 = -__ldg(lse_row + static_cast<int64_t>(sense) * S) * kLog2e;
       }
+      tr.rec(0, n);
       mbar_wait(&bars.s_full[w], i & 1);
       tc_fence_after();
+      tr.rec(1, n);
       float s[BN];
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
@@ -422,7 +435,8 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars.s_free);   // S(n+1) may be computed while this step's exponentials run
+      mbar_arrive(&bars.s_go[(n + 1) & 1]);   // S(n+1) may be computed while this step's exponentials run
+      tr.rec(2, n);
       const int col0 = j * BN;
       if (col0 + BN - 1 > row0) {
 #pragma unroll
@@ -433,14 +447,17 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < BN / 2; ++c)
         pk[c] = pack2<kBF16>(fast_exp2(fmaf(s[2 * c], c2, neg_lse2)), fast_exp2(fmaf(s[2 * c + 1], c2, neg_lse2)));
+      tr.rec(3, n);
       if (i >= 1) {
         mbar_wait(&bars.p_free[w], (i - 1) & 1);   // the PV product of step n-2 has consumed this P buffer
         tc_fence_after();
       }
+      tr.rec(4, n);
       tmem_st32(tP, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bars.p_ready[w]);
+      mbar_arrive(&bars.pv_go[n % C::CS]);
+      tr.rec(5, n);
     }
     // ---- epilogue: warpgroup w stores columns [w*ncols/2, (w+1)*ncols/2) of its row ----
     mbar_wait(&bars.o_full, 0);
@@ -468,7 +485,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 3) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -578,6 +595,7 @@ extern "C" int bp_sense_mix_fwd(const void* qk, const void* content, const float
   }
   sense::MixParams p;
   p.c_sense_inner = sense_inner ? 1 : 0;
+  p.trace = g_trace;
   p.lse = lse;
   p.out = out;
   p.seqlen = seqlen, p.nv = nv, p.dk = dk, p.ksteps = (dk + 15) / 16, p.d = d;

@@ -1,0 +1,53 @@
+"""Debug: dump the per-warp-role timeline of CTA 0 of a kernel (library built with BP_EXTRA_NVCC_FLAGS=-DBP_TRACE).
+
+    python benchmarks/trace_kernel.py fmha|sense [max_lines]
+"""
+import ctypes, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from backpacks_flash_attn_b200 import _lib
+
+which = sys.argv[1] if len(sys.argv) > 1 else "fmha"
+limit = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+R, N = 8, 512
+buf = torch.zeros(R * N * 2, dtype=torch.int64, device="cuda")
+lib = _lib.load()
+lib.bp_debug_set_trace.argtypes = [ctypes.c_void_p]
+lib.bp_debug_set_trace.restype = None
+
+if which == "fmha":
+    from backpacks_flash_attn_b200.flash_attn_interface import flash_attn_unpadded_qkvpacked_func
+    b, s, h, d = 32, 1024, 12, 64
+    qkv = torch.randn(b * s, 3, h, d, device="cuda").bfloat16()
+    cu = torch.arange(0, (b + 1) * s, s, dtype=torch.int32, device="cuda")
+    run = lambda: flash_attn_unpadded_qkvpacked_func(qkv, cu, s, 0.0, causal=True)
+    names = ["prod", "mma0", "mma1", "sm00", "sm01", "sm10", "sm11", "-"]
+else:
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    b, s, nv, d = 64, 1024, 16, 768
+    qk = torch.randn(b, s, 2, nv, d // nv, device="cuda").bfloat16()
+    content = torch.randn(b, s, nv, d, device="cuda").bfloat16().transpose(1, 2)
+    run = lambda: sense_mix(qk, content)
+    names = ["prodC", "mma", "sm0", "sm1", "-", "-", "-", "-"]
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+lib.bp_debug_set_trace(buf.data_ptr())
+run()
+torch.cuda.synchronize()
+lib.bp_debug_set_trace(None)
+t = buf.cpu().view(R, N, 2)
+starts = [int(t[r, 0, 1]) for r in range(R) if int(t[r, 0, 1]) > 0]
+t0 = min(starts)
+events = []
+for r in range(R):
+    for i in range(N):
+        tag, clk = int(t[r, i, 0]), int(t[r, i, 1])
+        if clk == 0:
+            break
+        events.append((clk - t0, names[r], tag >> 32, tag & 0xffffffff))
+events.sort()
+for e in events[:limit]:
+    print(f"{e[0]:8d} {e[1]:5s} ev{e[2]} #{e[3]}")
+print("total events", len(events))
