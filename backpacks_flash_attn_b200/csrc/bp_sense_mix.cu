@@ -412,6 +412,10 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float* lse_row = p.lse + static_cast<int64_t>(batch) * p.nv * S + (valid ? qrow : S - 1);
     int cur_sense = -1;
     float neg_lse2 = 0.f;
+    // the row statistic of the NEXT sense is fetched one sense ahead so its global-load latency never sits
+    // on the softmax path (light query tiles change sense every couple of steps)
+    float lse_next = __ldg(lse_row);
+    int next_id = 0;   // sense whose statistic lse_next holds
     int i = 0;
     Tracer tr(p.trace, 2 + w, blockIdx.x == 0 && blockIdx.y == 0 && r == 0);
     if (w == 1) mbar_arrive(&bars.s_go[0]);   // "S(-1) drained": lets S(0) go as soon as K(0) has landed
@@ -419,7 +423,10 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int sense = n / nj, j = n - sense * nj;
       if (sense != cur_sense) {
         cur_sense = sense;
-        neg_lse2 = -__ldg(lse_row + static_cast<int64_t>(sense) * S) * kLog2e;
+        if (next_id != sense) lse_next = __ldg(lse_row + static_cast<int64_t>(sense) * S);   // skipped a sense
+        neg_lse2 = -lse_next * kLog2e;
+        next_id = min(sense + 1, p.nv - 1);
+        lse_next = __ldg(lse_row + static_cast<int64_t>(next_id) * S);
       }
       tr.rec(0, n);
       mbar_wait(&bars.s_full[w], i & 1);
