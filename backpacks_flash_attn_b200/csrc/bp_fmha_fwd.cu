@@ -25,8 +25,6 @@
 // Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
 // are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill
 // to a padded width DP of 64 or 128.
-#include <type_traits>
-
 #include "bp_common.cuh"
 #include "bp_host.h"
 
@@ -89,7 +87,7 @@ struct Barriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
   uint64_t s_full[2], s_free[2];
-  uint64_t p_ready[2], pv_done[2];   // per tile: all NH streams hand over P / see the PV products together
+  uint64_t p_ready[2][2], pv_done[2][2];   // [tile][stream]
   uint32_t tmem_base;
 };
 
@@ -173,8 +171,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&bars.v_empty[i], 2);
       mbar_init(&bars.s_full[i], 1);
       mbar_init(&bars.s_free[i], 128 * NH);
-      mbar_init(&bars.p_ready[i], 128 * NH);
-      mbar_init(&bars.pv_done[i], 1);
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(&bars.p_ready[i][h], 128);
+        mbar_init(&bars.pv_done[i][h], 1);
+      }
     }
     fence_barrier_init();
   }
@@ -290,16 +290,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (j + 1 < it.n_max) step_s(j + 1, blk + 1);
           const uint32_t slot = blk & 1;
           if (j < n) {
-            // one wait per block on the issuing thread (a satisfied mbarrier wait still costs ~200 cycles):
-            // v_full was completed long ago by the time the softmax streams hand over P
             mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);
-            mbar_wait(&bars.p_ready[t], pv_cnt & 1);
-            tc_fence_after();
-            tr.rec(3, blk);
-            if (lane == 0) {
 #pragma unroll
-              for (int h = 0; h < NH; ++h) {
-                // O_{t,h} (+)= P_{t,h} V_j[h*64 : h*64+64, :]   (V rows are the K dimension: MN-major B)
+            for (int h = 0; h < NH; ++h) {
+              // O_{t,h} (+)= P_{t,h} V_j[h*64 : h*64+64, :]   (V rows are the K dimension: MN-major B)
+              mbar_wait(&bars.p_ready[t][h], pv_cnt & 1);
+              tc_fence_after();
+              tr.rec(3 + h, blk);
+              if (lane == 0) {
 #pragma unroll
                 for (int kk = 0; kk < HB / 16; ++kk) {
                   const uint32_t a = sP + h * (BM * 128) + kk * 32;
@@ -307,11 +305,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   umma_ss(tO + h * DP, make_smem_desc_sw128(a, 16, 1024),
                           make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
                 }
+                if (h == NH - 1) umma_commit(&bars.v_empty[slot]);
+                umma_commit(&bars.pv_done[t][h]);
               }
-              umma_commit(&bars.v_empty[slot]);
-              umma_commit(&bars.pv_done[t]);
+              __syncwarp();
             }
-            __syncwarp();
             ++pv_cnt;
           } else {
             mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);   // same pacing rule as for K
@@ -372,117 +370,84 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int c = 0; c < HB; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
         }
+        // row max: four independent chains
+        float mx4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+        for (int c = 4; c < HB; c += 4) {
+          mx4[0] = fmaxf(mx4[0], s[c]);
+          mx4[1] = fmaxf(mx4[1], s[c + 1]);
+          mx4[2] = fmaxf(mx4[2], s[c + 2]);
+          mx4[3] = fmaxf(mx4[3], s[c + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
-        // P = exp2(s * c - m * c) -> bf16 -> swizzled smem; returns the row sum.  With kWithMax the row maximum
-        // is accumulated in the same pass (independent instructions that fill the MUFU-bound schedule).
-        float mx = -INFINITY;
-        auto exp_pass = [&](float neg_m, auto with_max) -> float {
-          float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c8 = 0; c8 < HB / 8; ++c8) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              fma2(e[i], e[i + 1], s[c8 * 8 + i], s[c8 * 8 + i + 1], scale_log2, neg_m);
-              e[i] = fast_exp2(e[i]);
-              e[i + 1] = fast_exp2(e[i + 1]);
-            }
-            if constexpr (decltype(with_max)::value) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[c8 * 8 + i]);
-            }
-            add2(sum4[0], sum4[1], e[0], e[1]);
-            add2(sum4[2], sum4[3], e[2], e[3]);
-            add2(sum4[0], sum4[1], e[4], e[5]);
-            add2(sum4[2], sum4[3], e[6], e[7]);
-            uint4 v;
-            v.x = pack2<kBF16>(e[0], e[1]);
-            v.y = pack2<kBF16>(e[2], e[3]);
-            v.z = pack2<kBF16>(e[4], e[5]);
-            v.w = pack2<kBF16>(e[6], e[7]);
-            *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
+        float alpha = 1.f;
+        bool grow = false;
+        if (l == 0.f) {
+          // nothing accumulated yet for this row (first block, or only fully masked keys so far)
+          m_used = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          grow = (mx - m_used) * scale_log2 > kRescaleThreshold;
+          if (grow) {
+            alpha = fast_exp2((m_used - mx) * scale_log2);
+            m_used = mx;
           }
-          if constexpr (decltype(with_max)::value)
-            mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-          return (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-        };
-        auto row_max = [&]() {
-          float mx4[4] = {s[0], s[1], s[2], s[3]};
-#pragma unroll
-          for (int c = 4; c < HB; c += 4) {
-            mx4[0] = fmaxf(mx4[0], s[c]);
-            mx4[1] = fmaxf(mx4[1], s[c + 1]);
-            mx4[2] = fmaxf(mx4[2], s[c + 2]);
-            mx4[3] = fmaxf(mx4[3], s[c + 3]);
-          }
-          return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        };
-        // O_{t,h} *= alpha (rare): 16 columns at a time keeps the register footprint next to the live S row small
-        auto rescale_o = [&](float alpha) {
-#pragma unroll 1
-          for (int c = 0; c < DP / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld16(tO + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + c * 16, o);
-          }
-          tmem_st_wait();
-        };
-
+        }
+        tr.rec(3, cnt);
         if (j > 0) {
-          // P tile and O accumulator are free once the previous PV products of this tile have completed
-          tr.rec(3, cnt);
-          mbar_wait(&bars.pv_done[t], (cnt - 1) & 1);
+          // P tile and O accumulator are free once the previous PV MMA of this stream has completed
+          mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
           tc_fence_after();
           tr.rec(4, cnt);
-        }
-        if (j > 0 && __all_sync(0xffffffffu, l > 0.f)) {
-          // Steady state: take the exponentials against the running max of the previous blocks right away and
-          // find this block's max in the same pass.  Only if a row's max grew by more than 2^8 (rare after the
-          // first blocks) is the pass redone against the new max, after rescaling O.
-          const float sum = exp_pass(-m_used * scale_log2, std::true_type{});
-          const bool grow = (mx - m_used) * scale_log2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
-            float alpha = 1.f;
-            if (grow) {
-              alpha = fast_exp2((m_used - mx) * scale_log2);
-              m_used = mx;
+            // rare path: 16 columns at a time keeps the register footprint next to the live S row small
+#pragma unroll 1
+            for (int c = 0; c < DP / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
             }
-            rescale_o(alpha);
-            l = l * alpha + exp_pass(-m_used * scale_log2, std::false_type{});
-          } else {
-            l += sum;
+            tmem_st_wait();
           }
-        } else {
-          // First block of the item, or rows that have only seen masked keys so far: exact max first.
-          mx = row_max();
-          float alpha = 1.f;
-          bool grow = false;
-          if (l == 0.f) {
-            m_used = (mx == -INFINITY) ? 0.f : mx;
-          } else {
-            grow = (mx - m_used) * scale_log2 > kRescaleThreshold;
-            if (grow) {
-              alpha = fast_exp2((m_used - mx) * scale_log2);
-              m_used = mx;
-            }
-          }
-          if (j > 0 && __any_sync(0xffffffffu, grow)) rescale_o(alpha);
-          l = l * alpha + exp_pass(-m_used * scale_log2, std::false_type{});
+          l *= alpha;
         }
+
+        const float neg_m = -m_used * scale_log2;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c8 = 0; c8 < HB / 8; ++c8) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            fma2(e[i], e[i + 1], s[c8 * 8 + i], s[c8 * 8 + i + 1], scale_log2, neg_m);
+            e[i] = fast_exp2(e[i]);
+            e[i + 1] = fast_exp2(e[i + 1]);
+          }
+          add2(sum4[0], sum4[1], e[0], e[1]);
+          add2(sum4[2], sum4[3], e[2], e[3]);
+          add2(sum4[0], sum4[1], e[4], e[5]);
+          add2(sum4[2], sum4[3], e[6], e[7]);
+          uint4 v;
+          v.x = pack2<kBF16>(e[0], e[1]);
+          v.y = pack2<kBF16>(e[2], e[3]);
+          v.z = pack2<kBF16>(e[4], e[5]);
+          v.w = pack2<kBF16>(e[6], e[7]);
+          *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
+        }
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         tr.rec(5, cnt);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&bars.p_ready[t]);
+        mbar_arrive(&bars.p_ready[t][h]);
         tr.rec(6, cnt);
       }
 
       // ---- epilogue: merge the NH streams, O / l -> global, LSE ----
       tr.rec(7, cnt);
-      mbar_wait(&bars.pv_done[t], (cnt - 1) & 1);
+      mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
       tc_fence_after();
       tr.rec(8, cnt);
       const bool valid = qrow < it.len_q;
