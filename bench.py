@@ -98,6 +98,16 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def physical_gpu_index(local_rank: int) -> int:
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -267,13 +277,15 @@ def run_ours(args):
     roofline.update({"kernel": "fmha_fwd_kernel<64,bf16> (bp_fmha_fwd), 12 launches per step",
                      "ms_per_launch": fmha_t * 1e3, "algorithmic_gflop_per_launch": fmha_flops / 1e9,
                      "algorithmic_mb_per_launch": fmha_bytes / 1e6, "hbm_gbs": fmha_bytes / fmha_t / 1e9,
-                     "hbm_frac": fmha_bytes / fmha_t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                     "hbm_frac": fmha_bytes / fmha_t / 1e9 / peaks["hbm_gbs"],
+                     "traffic": ncu_traffic("fmha_fwd_kernel") if (B, S) == (64, 1024) else None,
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})"})
     mix = roof(mix_flops, mix_t)
     mix.update({"kernel": "sense_lse_kernel + sense_mix_kernel (1 launch each per step)", "ms_per_launch": mix_t * 1e3,
                 "ms_lse": per_kernel["bp_sense_lse_fwd"], "ms_mix": per_kernel["bp_sense_mix_fwd"],
                 "algorithmic_gflop_per_launch": mix_flops / 1e9, "algorithmic_mb_per_launch": mix_bytes / 1e6,
-                "traffic": None})
+                "traffic": ncu_traffic("sense_mix_kernel") if (B, S) == (64, 1024) else None})
     model_flops_per_token = 371.3e6   # SURVEY.md §8d, s = 1024
     cpu_base, _ = cpu_reference_run(S, steps=3, warmup=1)
     value = tokens / dt
@@ -290,8 +302,10 @@ def run_ours(args):
         "e2e": {"value": tokens / dt_e2e, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * 8 * world,
                 "d2h_bytes_per_step": last_host.numel() * 2 * world, "ms_per_step": dt_e2e / args.steps * 1e3,
                 "result": "last-position logits (batch, vocab) bf16 copied to pinned host memory every step"},
-        "gpu_launches": launches,
-        "gpu_launches_per_step": launches / args.steps,
+        "gpu_launches": launches * world,
+        "gpu_launches_per_step_per_gpu": launches / args.steps,
+        "gpu_launches_note": "kernels of libbackpack_b200.so inside the timed region, all ranks (per GPU and step: 28 "
+                             "LayerNorm, 12 attention, 14 GEMM+GELU, 2 sense-mix); library GEMMs / gathers not counted",
         "roofline": roofline,
         "kernels": {"sense_mix": mix},
         "model_mfu": {"achieved_tflops": value / world * model_flops_per_token / 1e12,
