@@ -102,11 +102,15 @@ struct Item {
 template <int BN>
 __device__ __forceinline__ Item decode_item(const Params& p, int w) {
   Item it;
-  const int bh = p.batch * p.nheads;
-  const int pq = w / bh;                      // heaviest (most key blocks) pair first
-  const int rem = w - pq * bh;
-  it.batch = rem / p.nheads;
-  it.head = rem - it.batch * p.nheads;
+  // Items are ordered (batch*head)-major with the query-tile pair fastest, so the CTAs that run together
+  // sweep the SAME K/V (L2 hits instead of DRAM re-reads: every K/V block is needed by all pairs below it);
+  // the pair index is rotated by the (batch, head) index so that the round-robin walk hands every CTA a
+  // balanced mix of light and heavy causal pairs.
+  const int bhi = w / p.num_pairs;
+  const int slot = w - bhi * p.num_pairs;
+  const int pq = (slot + bhi) % p.num_pairs;  // 0 = heaviest pair (most key blocks)
+  it.batch = bhi / p.nheads;
+  it.head = bhi - it.batch * p.nheads;
   const int2 cq = make_int2(__ldg(p.cu_q + it.batch), __ldg(p.cu_q + it.batch + 1));
   const int2 ck = make_int2(__ldg(p.cu_k + it.batch), __ldg(p.cu_k + it.batch + 1));
   it.q_begin = cq.x;
