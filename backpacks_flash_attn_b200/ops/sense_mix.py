@@ -30,6 +30,13 @@ def sense_mix(qk: torch.Tensor, content: torch.Tensor, softmax_scale: float | No
     if torch.is_grad_enabled() and (qk.requires_grad or content.requires_grad):
         raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
     d = content.shape[3]
+    if dk % 8 != 0:
+        # TMA needs 16-byte row strides.  Zero-padding the sense key width (e.g. d/nv = 12 at k = 64 senses of a
+        # 768-wide model) leaves every q.k dot product unchanged; the softmax scale keeps using the true width.
+        if softmax_scale is None:
+            softmax_scale = dk ** -0.5
+        qk = torch.nn.functional.pad(qk, (0, (-dk) % 8))
+        dk = qk.shape[-1]
     if not qk.is_contiguous():
         qk = qk.contiguous()
     if content.stride(3) != 1 or any(st % 8 for st in content.stride()[:3]) or content.data_ptr() % 16:

@@ -103,6 +103,14 @@ def test_sense_mix_rejects_bad_arguments():
         sense_mix(qk, content.half())
     with pytest.raises(RuntimeError, match="content must be"):
         sense_mix(qk, content[:, :8])
-    with pytest.raises(RuntimeError, match="multiple of 8"):
-        sense_mix(torch.zeros(1, 64, 2, 64, 12, device="cuda", dtype=torch.bfloat16),
-                  torch.zeros(1, 64, 64, 768, device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        sense_mix(torch.zeros(1, 64, 2, 4, 8, device="cuda", dtype=torch.bfloat16),
+                  torch.zeros(1, 4, 64, 32, device="cuda", dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("s", [128, 512])
+def test_sense_mix_k64_odd_key_width(s):
+    """BASELINE config 5: k = 64 senses of a 768-wide model => sense key width 12 (zero-padded to 16 for TMA)."""
+    qk, content = _inputs(2, s, 64, 768, torch.bfloat16, seed=s)
+    assert qk.shape[-1] == 12
+    _check(qk, content)
