@@ -203,7 +203,8 @@ def run_ours(args):
         launches0 = _lib.total_launches()
         per_kernel = {}
         with ClockSampler(physical_gpu_index(local_rank)) as clocks:
-            timers = [_lib.KernelTimer(n) for n in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd")]
+            timers = [_lib.KernelTimer(n) for n in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd",
+                                                    "bp_linear_bias_act_fwd", "bp_ln_residual_fwd")]
             for t in timers:
                 t.__enter__()
             parallel.barrier()
@@ -219,6 +220,7 @@ def run_ours(args):
                 t.__exit__(None, None, None)
             for t in timers:
                 per_kernel[t.name] = t.mean_ms()
+                per_kernel[t.name + ":n"] = len(t.events) / args.steps
         launches = _lib.total_launches() - launches0
         dt = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
         tokens = parallel.sum_over_ranks(float(B * S * args.steps), dev)
@@ -267,25 +269,54 @@ def run_ours(args):
     mix_bytes = (2 * B * S * d + nv * B * S * d + B * S * d) * 2
     fmha_t = per_kernel["bp_fmha_fwd"] * 1e-3
     mix_t = (per_kernel["bp_sense_lse_fwd"] + per_kernel["bp_sense_mix_fwd"]) * 1e-3
+    gemm_t = per_kernel["bp_linear_bias_act_fwd"] * 1e-3
+    ln_t = per_kernel["bp_ln_residual_fwd"] * 1e-3
     peak_tf = peaks["tf_sustained"]
+    inner = cfg.n_inner or 4 * d
+    gemm_flops = 2.0 * B * S * inner * d                     # every fused GEMM+GELU launch is (B*S, 4d, d)
+    gemm_bytes = (B * S * d + inner * d + B * S * inner) * 2
+    ln_bytes = B * S * d * (2 + 4) * 2                        # x0 bf16 + residual fp32 in, z bf16 + residual fp32 out
 
-    def roof(flops, t):
+    def roof_tensor(flops, t):
         a = flops / t / 1e12
         return {"bound": "tensor", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf}
 
-    roofline = roof(fmha_flops, fmha_t)
-    roofline.update({"kernel": "fmha_fwd_kernel<64,bf16> (bp_fmha_fwd), 12 launches per step",
-                     "ms_per_launch": fmha_t * 1e3, "algorithmic_gflop_per_launch": fmha_flops / 1e9,
-                     "algorithmic_mb_per_launch": fmha_bytes / 1e6, "hbm_gbs": fmha_bytes / fmha_t / 1e9,
-                     "hbm_frac": fmha_bytes / fmha_t / 1e9 / peaks["hbm_gbs"],
-                     "traffic": ncu_traffic("fmha_fwd_kernel") if (B, S) == (64, 1024) else None,
-                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})"})
-    mix = roof(mix_flops, mix_t)
-    mix.update({"kernel": "sense_lse_kernel + sense_mix_kernel (1 launch each per step)", "ms_per_launch": mix_t * 1e3,
-                "ms_lse": per_kernel["bp_sense_lse_fwd"], "ms_mix": per_kernel["bp_sense_mix_fwd"],
-                "algorithmic_gflop_per_launch": mix_flops / 1e9, "algorithmic_mb_per_launch": mix_bytes / 1e6,
-                "traffic": ncu_traffic("sense_mix_kernel") if (B, S) == (64, 1024) else None})
+    kernels = {}
+    k = roof_tensor(fmha_flops, fmha_t)
+    k.update({"kernel": "fmha_fwd_kernel<64,bf16> (bp_fmha_fwd)", "launches_per_step": per_kernel["bp_fmha_fwd:n"],
+              "ms_per_launch": fmha_t * 1e3, "algorithmic_gflop_per_launch": fmha_flops / 1e9,
+              "algorithmic_mb_per_launch": fmha_bytes / 1e6, "hbm_gbs": fmha_bytes / fmha_t / 1e9,
+              "hbm_frac": fmha_bytes / fmha_t / 1e9 / peaks["hbm_gbs"],
+              "traffic": ncu_traffic("fmha_fwd_kernel") if (B, S) == (64, 1024) else None})
+    kernels["fmha"] = k
+    k = roof_tensor(mix_flops, mix_t)
+    k.update({"kernel": "sense_lse_kernel + sense_mix_kernel (bp_sense_lse_fwd, bp_sense_mix_fwd)",
+              "launches_per_step": 1, "ms_per_launch": mix_t * 1e3, "ms_lse": per_kernel["bp_sense_lse_fwd"],
+              "ms_mix": per_kernel["bp_sense_mix_fwd"], "algorithmic_gflop_per_launch": mix_flops / 1e9,
+              "algorithmic_mb_per_launch": mix_bytes / 1e6,
+              "traffic": ncu_traffic("sense_mix_kernel") if (B, S) == (64, 1024) else None})
+    kernels["sense_mix"] = k
+    k = roof_tensor(gemm_flops, gemm_t)
+    k.update({"kernel": "gemm_bias_act_kernel<bf16> (bp_linear_bias_act_fwd), fc1 + bias + tanh-GELU",
+              "launches_per_step": per_kernel["bp_linear_bias_act_fwd:n"], "ms_per_launch": gemm_t * 1e3,
+              "algorithmic_gflop_per_launch": gemm_flops / 1e9, "algorithmic_mb_per_launch": gemm_bytes / 1e6,
+              "traffic": ncu_traffic("gemm_bias_act_kernel") if (B, S) == (64, 1024) else None})
+    kernels["gemm_bias_gelu"] = k
+    a = ln_bytes / ln_t / 1e9
+    kernels["ln_residual"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": a / peaks["hbm_gbs"], "kernel": "ln_residual_fwd_kernel (bp_ln_residual_fwd)",
+                              "launches_per_step": per_kernel["bp_ln_residual_fwd:n"], "ms_per_launch": ln_t * 1e3,
+                              "algorithmic_mb_per_launch": ln_bytes / 1e6,
+                              "traffic": ncu_traffic("ln_residual_fwd_kernel") if (B, S) == (64, 1024) else None}
+    for v in kernels.values():
+        v["ms_per_step"] = v["ms_per_launch"] * v["launches_per_step"]
+        v["traffic_unit"] = "DRAM bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)"
+    # `roofline` = the kernel of this library with the largest share of the step
+    dominant = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
+    roofline = dict(kernels[dominant])
+    roofline["dominant_of"] = {n: round(v["ms_per_step"], 3) for n, v in kernels.items()}
+    roofline["peak_source"] = (f"MEASURED_PEAKS.json ({peaks['source']}): bf16_tflops_sustained for tensor-bound kernels "
+                               "(timed inside a long step), hbm_gbs for HBM-bound ones")
     model_flops_per_token = 371.3e6   # SURVEY.md §8d, s = 1024
     cpu_base, _ = cpu_reference_run(S, steps=3, warmup=1)
     value = tokens / dt
@@ -307,7 +338,7 @@ def run_ours(args):
         "gpu_launches_note": "kernels of libbackpack_b200.so inside the timed region, all ranks (per GPU and step: 28 "
                              "LayerNorm, 12 attention, 14 GEMM+GELU, 2 sense-mix); library GEMMs / gathers not counted",
         "roofline": roofline,
-        "kernels": {"sense_mix": mix},
+        "kernels": kernels,
         "model_mfu": {"achieved_tflops": value / world * model_flops_per_token / 1e12,
                       "frac_of_sustained_peak": value / world * model_flops_per_token / 1e12 / peak_tf},
         "cpu_baseline": cpu_base,
