@@ -200,6 +200,193 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// =============================================================================================
+// CTA-pair variant (cta_group::2): the default for m >= 256.
+//
+// The 1-CTA kernel above is bound by shared-memory bandwidth, not by the tensor pipe: per 64-wide K block
+// (512 MMA cycles) TMA writes 48 KB of operands into shared memory and the four MMAs read 48 KB back out,
+// 190 B/clk against the 128 B/clk an SM has -- a hard 2/3 ceiling, which is what it measures (1.12 of 1.65
+// PFLOP/s).  With a CTA pair the MMA is 256 x 256 x 16 across two SMs: each CTA keeps its own 128 rows of A and
+// of the accumulator but only HALF of the W tile, so fill + operand reads drop to 64 KB per 512 cycles.
+// Roles per CTA as above; only the leader CTA (cluster rank 0) issues MMAs, both CTAs load (their TMA
+// transaction bytes are credited to the leader's `full` barrier), `tcgen05.commit ... multicast::cluster`
+// releases the stage / publishes the accumulator in both CTAs, and the epilogue threads of both CTAs hand the
+// TMEM buffer back on the leader's `acc_empty` barrier.
+// =============================================================================================
+namespace pair {
+constexpr int kStages = 6;
+constexpr uint32_t kABytes = 128 * BK * 2;         // this CTA's 128 rows of A          (16 KB)
+constexpr uint32_t kBBytes = 128 * BK * 2;         // this CTA's half (128 rows) of W   (16 KB)
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t offOut = kStages * kStageBytes;
+constexpr uint32_t offBar = offOut + 2 * kOutChunkBytes;
+constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+struct Barriers {
+  uint64_t full[kStages], empty[kStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+}  // namespace pair
+
+template <bool kBF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmO, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pair::Barriers& bars = *reinterpret_cast<pair::Barriers*>(smem + pair::offBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t num_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;   // 256 x 256 tiles
+  const int64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < pair::kStages; ++i) mbar_init(&bars.full[i], 1), mbar_init(&bars.empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 256);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(&bars.tmem_base, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of BOTH CTAs are initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    uint32_t it = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t slot = it % pair::kStages;
+        if (it >= pair::kStages) mbar_wait(&bars.empty[slot], ((it / pair::kStages) - 1) & 1);
+        if (lane == 0) {
+          uint8_t* a = smem + slot * pair::kStageBytes;
+          if (leader) mbar_arrive_expect_tx(&bars.full[slot], 2 * pair::kStageBytes);   // both CTAs' bytes
+          tma_load_2d_pair(a, &tmA, &bars.full[slot], kb * BK, m0);
+          tma_load_2d_pair(a + pair::kABytes, &tmB, &bars.full[slot], kb * BK, n0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = make_idesc(kBF16, 256, 256, false, false);
+    uint32_t it = 0, local = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      const uint32_t buf = local & 1;
+      if (local >= 2) mbar_wait(&bars.acc_empty[buf], ((local >> 1) - 1) & 1);
+      tc_fence_after();
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+        const uint32_t slot = it % pair::kStages;
+        mbar_wait(&bars.full[slot], (it / pair::kStages) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a = smem_u32(smem + slot * pair::kStageBytes);
+          const uint32_t b = a + pair::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_ss_pair(tmem_base + buf * BN, make_smem_desc_sw128(a + kk * 32, 16, 1024),
+                         make_smem_desc_sw128(b + kk * 32, 16, 1024), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_pair(&bars.empty[slot]);
+          if (kb == p.k_blocks - 1) umma_commit_pair(&bars.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const bool store_leader = threadIdx.x == 128;
+    uint32_t local = 0, chunk_it = 0;
+    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * 256;
+      const uint32_t buf = local & 1;
+      mbar_wait(&bars.acc_full[buf], (local >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_it) {
+        const bool outside = n0 + c64 * 64 >= p.n;   // uniform: whole 64-column chunk beyond the matrix
+        uint8_t* stage = smem + pair::offOut + (chunk_it & 1) * kOutChunkBytes;
+        if (!outside) {
+          if (store_leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_addr + buf * BN + c64 * 64 + h * 32, v);
+            tmem_ld_wait();
+            const int col = n0 + c64 * 64 + h * 32;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+              const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                if (col + i < p.n) {
+                  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + i));
+                  if constexpr (kBF16) {
+                    f[i] += __uint_as_float(w << 16);
+                    f[i + 1] += __uint_as_float(w & 0xFFFF0000u);
+                  } else {
+                    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                    f[i] += t.x;
+                    f[i + 1] += t.y;
+                  }
+                }
+              }
+            }
+            if (p.act == BP_ACT_GELU_TANH) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 w;
+              w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
+              w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
+              w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
+              w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(stage + sw128_offset(r, h * 4 + g)) = w;
+            }
+          }
+        }
+        if (c64 == BN / 64 - 1) {
+          // all columns of this accumulator buffer have been read: hand it back to the leader's MMA warp
+          tc_fence_before();
+          mbar_arrive_leader(&bars.acc_empty[buf]);
+        }
+        if (!outside) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (store_leader) {
+            tma_store_2d(&tmO, stage, n0 + c64 * 64, m0);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (store_leader) tma_store_wait_read<0>();
+  }
+  // no CTA of the pair may exit (or free TMEM) while its peer can still read its shared memory / signal it
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, kTmemCols);
+}
+
 }  // namespace gemm
 }  // namespace bp
 
@@ -232,17 +419,38 @@ extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* 
   gemm::Params p;
   p.bias = bias;
   p.m = m, p.n = n, p.k = k;
-  p.m_tiles = static_cast<int32_t>((m + gemm::BM - 1) / gemm::BM);
-  p.n_tiles = (n + gemm::BN - 1) / gemm::BN;
   p.k_blocks = (k + gemm::BK - 1) / gemm::BK;
   p.act = activation;
+  p.n_tiles = (n + gemm::BN - 1) / gemm::BN;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf = dtype == BP_DTYPE_BF16;
+
+  if (m >= 256 && sms >= 2) {
+    // CTA-pair kernel: 256 x 256 tiles, one cluster of two CTAs per tile
+    p.m_tiles = static_cast<int32_t>((m + 255) / 256);
+    const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+    const int clusters = static_cast<int>(tiles < sms / 2 ? tiles : sms / 2);
+    // the W tile map of this variant has a 128-row box (each CTA loads half of the 256-wide tile)
+    const uint64_t db[2] = {(uint64_t)k, (uint64_t)n}, sb[1] = {(uint64_t)k * 2};
+    const uint32_t bb[2] = {gemm::BK, 128};
+    if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;
+    auto kern = bf ? gemm::gemm_bias_act_pair_kernel<true> : gemm::gemm_bias_act_pair_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::pair::kSmemBytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BP_ERR_CUDA, "bp_linear_bias_act_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<2 * clusters, gemm::kThreads, gemm::pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
+    return check_launch("bp_linear_bias_act_fwd (pair) launch");
+  }
+
+  p.m_tiles = static_cast<int32_t>((m + gemm::BM - 1) / gemm::BM);
   const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto kern = dtype == BP_DTYPE_BF16 ? gemm::gemm_bias_act_kernel<true> : gemm::gemm_bias_act_kernel<false>;
+  auto kern = bf ? gemm::gemm_bias_act_kernel<true> : gemm::gemm_bias_act_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::kSmemBytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
