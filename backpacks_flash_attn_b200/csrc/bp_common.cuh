@@ -77,6 +77,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe.  A satisfied wait still costs ~100-200 cycles of latency on the issuing thread; MMA issuers
+// probe the NEXT stage's barrier before issuing the current stage's MMAs so that latency overlaps the issue.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Blocking wait.  A pipeline bug would otherwise hang the GPU until the watchdog fires; after ~16M failed
 // polls (orders of magnitude beyond any legitimate wait in these kernels) the kernel traps instead, which
 // surfaces as a CUDA launch failure on the host.

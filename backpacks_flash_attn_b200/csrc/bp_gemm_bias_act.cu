@@ -51,6 +51,26 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.f + t);
 }
 
+// two GELUs at once with packed fp32x2 FMA-pipe instructions (5 packed ops + 2 MUFU.TANH per pair)
+__device__ __forceinline__ void gelu_tanh_pair(float& x0, float& x1) {
+  uint64_t x, xx, in, u, hx, t, c1, c2, half;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.7978845608f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.0356774081f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(half) : "f"(0.5f));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(xx) : "l"(x));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(in) : "l"(xx), "l"(c2), "l"(c1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(x), "l"(in));
+  float u0, u1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(u0), "=f"(u1) : "l"(u));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx) : "l"(x), "l"(half));
+  asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(x) : "l"(hx), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
+
 template <bool kBF16>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -100,14 +120,16 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(kBF16, BM, BN, false, false);
     uint32_t it = 0, local = 0;
+    bool ready = false;   // result of the early probe of full[it]
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const uint32_t buf = local & 1;
       if (local >= 2) mbar_wait(&bars.acc_empty[buf], ((local >> 1) - 1) & 1);
       tc_fence_after();
       for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
         const uint32_t slot = it % kStages;
-        mbar_wait(&bars.full[slot], (it / kStages) & 1);
+        if (!ready) mbar_wait(&bars.full[slot], (it / kStages) & 1);
         tc_fence_after();
+        ready = mbar_test(&bars.full[(it + 1) % kStages], ((it + 1) / kStages) & 1);   // overlaps the MMA issue below
         if (lane == 0) {
           const uint32_t a = smem_u32(smem + slot * kStageBytes);
           const uint32_t b = a + kABytes;
@@ -215,6 +237,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // TMEM buffer back on the leader's `acc_empty` barrier.
 // =============================================================================================
 namespace pair {
+constexpr int kThreads = 384;   // warps 0-3 as in the 1-CTA kernel + EIGHT epilogue warps (two per TMEM lane quadrant)
 constexpr int kStages = 6;
 constexpr uint32_t kABytes = 128 * BK * 2;         // this CTA's 128 rows of A          (16 KB)
 constexpr uint32_t kBBytes = 128 * BK * 2;         // this CTA's half (128 rows) of W   (16 KB)
@@ -232,7 +255,7 @@ struct Barriers {
 }  // namespace pair
 
 template <bool kBF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::kThreads, 1)
 gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -249,7 +272,7 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < pair::kStages; ++i) mbar_init(&bars.full[i], 1), mbar_init(&bars.empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 256);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 512);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -283,14 +306,16 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // ===================== MMA issuer (leader CTA only) =====================
     constexpr uint32_t idesc = make_idesc(kBF16, 256, 256, false, false);
     uint32_t it = 0, local = 0;
+    bool ready = false;   // result of the early probe of full[it]
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
       const uint32_t buf = local & 1;
       if (local >= 2) mbar_wait(&bars.acc_empty[buf], ((local >> 1) - 1) & 1);
       tc_fence_after();
       for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
         const uint32_t slot = it % pair::kStages;
-        mbar_wait(&bars.full[slot], (it / pair::kStages) & 1);
+        if (!ready) mbar_wait(&bars.full[slot], (it / pair::kStages) & 1);
         tc_fence_after();
+        ready = mbar_test(&bars.full[(it + 1) % pair::kStages], ((it + 1) / pair::kStages) & 1);
         if (lane == 0) {
           const uint32_t a = smem_u32(smem + slot * pair::kStageBytes);
           const uint32_t b = a + pair::kABytes;
@@ -306,7 +331,10 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
+    // Eight warps: warp w and w+4 share a TMEM lane quadrant and split every 64-column chunk in two, so the
+    // bias + GELU + convert work per tile (which, with four warps, took longer than the tile's MMAs) halves.
     const int r = (warp & 3) * 32 + lane;
+    const int hsel = (warp - 4) >> 2;                 // which 32-column half of each 64-column chunk
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const bool store_leader = threadIdx.x == 128;
     uint32_t local = 0, chunk_it = 0;
@@ -322,46 +350,43 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         uint8_t* stage = smem + pair::offOut + (chunk_it & 1) * kOutChunkBytes;
         if (!outside) {
           if (store_leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_addr + buf * BN + c64 * 64 + hsel * 32, v);
+          tmem_ld_wait();
+          const int col = n0 + c64 * 64 + hsel * 32;
+          float f[32];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + lane_addr + buf * BN + c64 * 64 + h * 32, v);
-            tmem_ld_wait();
-            const int col = n0 + c64 * 64 + h * 32;
-            float f[32];
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+            const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            if (p.bias != nullptr) {
-              const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                if (col + i < p.n) {
-                  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + i));
-                  if constexpr (kBF16) {
-                    f[i] += __uint_as_float(w << 16);
-                    f[i + 1] += __uint_as_float(w & 0xFFFF0000u);
-                  } else {
-                    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                    f[i] += t.x;
-                    f[i + 1] += t.y;
-                  }
+            for (int i = 0; i < 32; i += 2) {
+              if (col + i < p.n) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + i));
+                if constexpr (kBF16) {
+                  f[i] += __uint_as_float(w << 16);
+                  f[i + 1] += __uint_as_float(w & 0xFFFF0000u);
+                } else {
+                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                  f[i] += t.x;
+                  f[i + 1] += t.y;
                 }
               }
             }
-            if (p.act == BP_ACT_GELU_TANH) {
+          }
+          if (p.act == BP_ACT_GELU_TANH) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
-            }
+            for (int i = 0; i < 32; i += 2) gelu_tanh_pair(f[i], f[i + 1]);
+          }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 w;
-              w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
-              w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
-              w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
-              w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
-              *reinterpret_cast<uint4*>(stage + sw128_offset(r, h * 4 + g)) = w;
-            }
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
+            w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
+            w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
+            w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(stage + sw128_offset(r, hsel * 4 + g)) = w;
           }
         }
         if (c64 == BN / 64 - 1) {
@@ -371,7 +396,7 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         if (!outside) {
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
           if (store_leader) {
             tma_store_2d(&tmO, stage, n0 + c64 * 64, m0);
             tma_store_commit();
@@ -443,7 +468,7 @@ extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* 
       cudaGetLastError();
       return fail(BP_ERR_CUDA, "bp_linear_bias_act_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<2 * clusters, gemm::kThreads, gemm::pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
+    kern<<<2 * clusters, gemm::pair::kThreads, gemm::pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
     return check_launch("bp_linear_bias_act_fwd (pair) launch");
   }
 

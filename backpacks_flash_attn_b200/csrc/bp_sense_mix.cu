@@ -371,11 +371,13 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
       const uint32_t sC = smem_u32(smem + C::offC);
       Tracer tr(p.trace, 1, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
+      bool ready = false;   // result of the early probe of pv_go for this step
       for (int n = 0; n < n_steps; ++n) {
         const int cs = n % C::CS;
         tr.rec(3, n);
-        mbar_wait(&bars.pv_go[cs], (n / C::CS) & 1);
+        if (!ready) mbar_wait(&bars.pv_go[cs], (n / C::CS) & 1);
         tc_fence_after();
+        ready = mbar_test(&bars.pv_go[(n + 1) % C::CS], ((n + 1) / C::CS) & 1);   // latency hidden by the issue below
         tr.rec(5, n);
         if (lane == 0) {
           const uint32_t a_tmem = tmem_base + C::colP + (n & 1) * (BN / 2);   // P(n): 8 columns per K-step of 16
