@@ -12,7 +12,8 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbackpack_b200.so")
+_TAG = os.environ.get("BP_LIB_TAG", "")   # debug builds only (see build.py: BP_BUILD_TAG)
+LIB_PATH = os.path.join(_PKG, "libbackpack_b200" + (f"_{_TAG}" if _TAG else "") + ".so")
 
 BP_DTYPE_F16, BP_DTYPE_BF16, BP_DTYPE_F32 = 0, 1, 2
 BP_ACT_NONE, BP_ACT_GELU_TANH = 0, 1

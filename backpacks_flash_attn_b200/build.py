@@ -16,8 +16,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-BUILD_DIR = os.path.join(PKG_DIR, "build")
-LIB_PATH = os.path.join(PKG_DIR, "libbackpack_b200.so")
+# BP_BUILD_TAG=trace builds a side-by-side debug variant (build_trace/, libbackpack_b200_trace.so) that the
+# binding loads when BP_LIB_TAG=trace; the production library is never overwritten by a debug build.
+_TAG = os.environ.get("BP_BUILD_TAG", "")
+BUILD_DIR = os.path.join(PKG_DIR, "build" + (f"_{_TAG}" if _TAG else ""))
+LIB_PATH = os.path.join(PKG_DIR, "libbackpack_b200" + (f"_{_TAG}" if _TAG else "") + ".so")
 ROOT = os.path.dirname(PKG_DIR)
 
 NVCC_FLAGS = [

@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace bp {
 
@@ -100,6 +101,68 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same operations on 32-bit shared-window addresses.  Kernels whose inner loops are issue-bound keep one
+// 32-bit base and add compile-time offsets: a generic pointer costs a handful of ALU instructions per use
+// (the generic -> shared conversion is re-materialised under register pressure).
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#ifdef BP_DEBUG_WAIT
+__device__ int g_debug_abort = 0;
+#endif
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+#ifdef BP_DEBUG_WAIT
+    // debug builds: report the stuck barrier (with its raw state word) and carry on (results are garbage)
+    if (++polls > (1u << 16) || (polls > 64 && *(volatile int*)&g_debug_abort)) {
+      if ((threadIdx.x & 31) == 0) {
+        unsigned long long w;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(bar));
+        printf("stuck: block %d warp %d barrier offset 0x%x parity %u state %016llx polls %u\n", blockIdx.x,
+               threadIdx.x >> 5, bar & 0xfff, parity, w, polls);
+      }
+      g_debug_abort = 1;
+      return;
+    }
+#else
+    if (++polls > (1u << 24)) __trap();
+#endif
+  }
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                              int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------
 // proxies / fences
 // ------------------------------------------------------------------------------------------
@@ -149,6 +212,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

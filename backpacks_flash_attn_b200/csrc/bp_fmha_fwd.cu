@@ -6,9 +6,12 @@
 //
 //   * Q-outer / KV-inner: a work item is 2 x 128 query rows of one (batch, head); O stays in TMEM for the
 //     whole KV sweep, so Q, K, V are read once and O written once (the algorithmic traffic).
-//   * persistent: one CTA per SM walks the work items (heaviest causal tiles first, round-robin), barrier
-//     phases run on across items, Q is double-buffered per item and the K/V rings never drain, so the loads
-//     and the first S = Q K^T of the next item overlap the epilogue of the current one.
+//   * persistent with a dynamic scheduler: one CTA per SM; the producer warp draws work items from a global
+//     ticket counter (heaviest causal tiles first inside chunks of 148 (batch, head) pairs, so that the K/V of
+//     a chunk stay in L2 and the last tickets are the lightest ones) and publishes the decoded item through a
+//     small shared-memory ring to the other roles; barrier phases run on across items, Q is double-buffered
+//     per item and the K/V rings never drain, so the loads and the first S = Q K^T of the next item overlap
+//     the epilogue of the current one.
 //   * warp-specialised:  warp 0 = TMA producer, warps 1 / 2 = tcgen05.mma issuers for query tile 0 / 1 (two
 //     independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator, then 2 x NH softmax
 //     warpgroups (one thread per query row; TMEM lane == row, so row max / row sum need no shuffles).
@@ -25,6 +28,9 @@
 // Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
 // are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill
 // to a padded width DP of 64 or 128.
+#include <atomic>
+#include <cstddef>
+
 #include "bp_common.cuh"
 #include "bp_host.h"
 
@@ -34,6 +40,14 @@ namespace fmha {
 constexpr int BM = 128;           // query rows per tile (= TMEM lanes)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr int kItemSlots = 4;     // shared-memory ring of decoded work items (producer -> all other roles)
+constexpr int kChunkBH = 148;     // (batch, head) pairs per scheduling chunk
+constexpr int kSchedSlots = 64;   // ticket counters, one per in-flight launch (rotating)
+#ifndef BP_FMHA_STAGGER
+#define BP_FMHA_STAGGER 1
+#endif
+constexpr bool kStagger = BP_FMHA_STAGGER != 0;   // anti-phase hint between the two query tiles' softmax warps
+constexpr int kStaggerMaxSpins = 256;   // x ~25 cycles per probe: a few exponential phases at most
 constexpr int kPolyPairs = 0;   // of every 4 score pairs, how many take the polynomial exp2 (FMA pipe) instead of MUFU; measured: 1 -> 139 us vs 0 -> 134 us at config 2 (the lockstep softmax warps are issue-limited, not MUFU-limited)
 
 template <int DP>
@@ -42,10 +56,15 @@ struct Cfg {
   static constexpr int NH = (DP == 64) ? 2 : 1;      // independent softmax streams (key halves) per block
   static constexpr int HB = BN / NH;                 // keys per stream and block (= 64)
   static constexpr int kThreads = 128 + 256 * NH;    // warps 0-3 + 2*NH softmax warpgroups
+  // setmaxnreg only redistributes the registers the CTA was launched with (kThreads x the compiled per-thread
+  // count): 128 * kRegsLow + (kThreads - 128) * kRegsHigh must not exceed it, or the last warps to grow block forever
   static constexpr int kRegsLow = NH == 2 ? 32 : 56;
   static constexpr int kRegsHigh = NH == 2 ? 112 : 224;
   static constexpr int kStages = 2;                  // K and V rings
   static constexpr int kQBufs = (DP == 64) ? 2 : 1;  // Q buffers across work items (smem-limited at DP = 128)
+  // O leaves through shared memory + one TMA store per query tile (staged in the idle P panel of stream 0); at
+  // DP = 128 the P panel is too small for the O tile and rows are stored directly
+  static constexpr bool kStageO = (DP == 64);
   static constexpr int kPanelsD = DP / 64;           // 64-column (128 B) panels along head dim
   static constexpr uint32_t kQTileBytes = BM * DP * 2;
   static constexpr uint32_t kKVTileBytes = BN * DP * 2;
@@ -57,8 +76,9 @@ struct Cfg {
   static constexpr uint32_t offV = offK + kStages * kKVTileBytes;
   static constexpr uint32_t offP = offV + kStages * kKVTileBytes;
   static constexpr uint32_t offX = offP + 2 * kPTileBytes;            // (m, l) exchange [2][NH][128] float2
-  static constexpr uint32_t offBar = offX + 2 * NH * 128 * 8;
-  static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;  // + barriers + alignment slack
+  static constexpr uint32_t offItems = offX + 2 * NH * 128 * 8;       // ring of decoded work items
+  static constexpr uint32_t offBar = offItems + kItemSlots * 64;
+  static constexpr uint32_t kSmemBytes = offBar + 512 + 1024;  // + barriers + alignment slack
   static_assert(kSmemBytes <= 232448, "shared memory budget");
   static_assert(HB == 64, "one 64-key P panel per softmax stream");
   // TMEM columns
@@ -78,6 +98,7 @@ struct Params {
   int32_t batch, nheads, headdim;
   int32_t num_pairs;  // ceil(max_seqlen_q / 256)
   int32_t num_items;  // num_pairs * batch * nheads
+  unsigned int* sched;  // [0] ticket counter, [1] finished CTAs; both zero between launches
   int32_t is_causal;
   float scale;        // softmax scale
   float scale_log2;   // scale * log2(e)
@@ -89,36 +110,59 @@ struct Barriers {
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
   uint64_t s_full[2], s_free[2];
   uint64_t p_ready[2][2], pv_done[2][2];   // [tile][stream]
+  uint64_t item_full[kItemSlots], item_empty[kItemSlots];
   uint32_t tmem_base;
+  uint32_t busy[2][2];                     // [tile][stream]: softmax warpgroup is in its exponential phase
 };
+#define BAR(field) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)))
+#define BAR_I(field, i) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)) + 8u * static_cast<uint32_t>(i))
 
-// One work item = (pair of query tiles, head, batch).  Every role decodes the same sequence of items.
+// One work item = (pair of query tiles, head, batch).  The producer warp decodes it once and publishes it
+// through the shared-memory ring; every other role reads the same sequence of items from there.
 struct Item {
   int head, batch, q_begin, k_begin, len_q, len_k, row0;
-  int n0, n1, n_max;   // key blocks visited by query tile 0 / 1
-  bool valid;
+  int n0, n1;   // key blocks visited by query tile 0 / 1
+  int end;      // sentinel: no more work for this CTA
   __device__ __forceinline__ int n_of(int t) const { return t == 0 ? n0 : n1; }
+  __device__ __forceinline__ int n_max() const { return max(n0, n1); }
 };
 
+// Decoding is split so that the producer can issue the cu_seqlens loads of the NEXT item, go on issuing TMA
+// loads of the current one, and only then consume them.
+struct ItemPre {
+  int head, batch, pq;
+  int2 cq, ck;
+};
+__device__ __forceinline__ ItemPre decode_prefetch(const Params& p, int w) {
+  // Ticket order: chunks of kChunkBH (batch, head) pairs; inside a chunk all heaviest query-tile pairs first,
+  // then the next lighter class, ...  The CTAs that run together sweep the K/V of one chunk (L2 hits instead
+  // of DRAM re-reads: every K/V block is needed by all pairs below it), heavy items are handed out before
+  // light ones, and the last tickets of the launch are the lightest (short tail).
+  ItemPre pre;
+  const int total_bh = p.batch * p.nheads;
+  const int per_chunk = kChunkBH * p.num_pairs;
+  const int c = w / per_chunk;
+  const int r = w - c * per_chunk;
+  const int bh0 = c * kChunkBH;
+  const int gc = min(kChunkBH, total_bh - bh0);
+  pre.pq = r / gc;  // 0 = heaviest pair (most key blocks)
+  const int bhi = bh0 + (r - pre.pq * gc);
+  pre.batch = bhi / p.nheads;
+  pre.head = bhi - pre.batch * p.nheads;
+  pre.cq = make_int2(__ldg(p.cu_q + pre.batch), __ldg(p.cu_q + pre.batch + 1));
+  pre.ck = make_int2(__ldg(p.cu_k + pre.batch), __ldg(p.cu_k + pre.batch + 1));
+  return pre;
+}
 template <int BN>
-__device__ __forceinline__ Item decode_item(const Params& p, int w) {
+__device__ __forceinline__ Item decode_finish(const Params& p, const ItemPre& pre) {
   Item it;
-  // Items are ordered (batch*head)-major with the query-tile pair fastest, so the CTAs that run together
-  // sweep the SAME K/V (L2 hits instead of DRAM re-reads: every K/V block is needed by all pairs below it);
-  // the pair index is rotated by the (batch, head) index so that the round-robin walk hands every CTA a
-  // balanced mix of light and heavy causal pairs.
-  const int bhi = w / p.num_pairs;
-  const int slot = w - bhi * p.num_pairs;
-  const int pq = (slot + bhi) % p.num_pairs;  // 0 = heaviest pair (most key blocks)
-  it.batch = bhi / p.nheads;
-  it.head = bhi - it.batch * p.nheads;
-  const int2 cq = make_int2(__ldg(p.cu_q + it.batch), __ldg(p.cu_q + it.batch + 1));
-  const int2 ck = make_int2(__ldg(p.cu_k + it.batch), __ldg(p.cu_k + it.batch + 1));
-  it.q_begin = cq.x;
-  it.len_q = cq.y - cq.x;
-  it.k_begin = ck.x;
-  it.len_k = ck.y - ck.x;
-  it.row0 = (p.num_pairs - 1 - pq) * 2 * BM;
+  it.batch = pre.batch;
+  it.head = pre.head;
+  it.q_begin = pre.cq.x;
+  it.len_q = pre.cq.y - pre.cq.x;
+  it.k_begin = pre.ck.x;
+  it.len_k = pre.ck.y - pre.ck.x;
+  it.row0 = (p.num_pairs - 1 - pre.pq) * 2 * BM;
   auto blocks = [&](int r0) {
     if (r0 >= it.len_q) return 0;
     int kmax = it.len_k;
@@ -127,8 +171,27 @@ __device__ __forceinline__ Item decode_item(const Params& p, int w) {
   };
   it.n0 = blocks(it.row0);
   it.n1 = blocks(it.row0 + BM);
-  it.n_max = max(it.n0, it.n1);
-  it.valid = it.n_max > 0;
+  it.end = 0;
+  return it;
+}
+__device__ __forceinline__ Item end_item() {
+  Item fin;
+  fin.head = fin.batch = fin.q_begin = fin.k_begin = fin.len_q = fin.len_k = fin.row0 = fin.n0 = fin.n1 = 0;
+  fin.end = 1;
+  return fin;
+}
+
+__device__ __forceinline__ void put_item(uint32_t a, const Item& it) {
+  sts128(a, it.head, it.batch, it.q_begin, it.k_begin);
+  sts128(a + 16, it.len_q, it.len_k, it.row0, it.n0);
+  sts128(a + 32, it.n1, it.end, 0, 0);
+}
+__device__ __forceinline__ Item get_item(uint32_t a) {
+  const uint4 x = lds128(a), y = lds128(a + 16), z = lds128(a + 32);
+  Item it;
+  it.head = x.x; it.batch = x.y; it.q_begin = x.z; it.k_begin = x.w;
+  it.len_q = y.x; it.len_k = y.y; it.row0 = y.z; it.n0 = y.w;
+  it.n1 = z.x; it.end = z.y;
   return it;
 }
 
@@ -177,14 +240,27 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
   x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
+__device__ __forceinline__ uint32_t ld_volatile_shared_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_shared_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 template <int DP, bool kBF16>
 __global__ void __launch_bounds__(Cfg<DP>::kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const Params p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   using C = Cfg<DP>;
   constexpr int BN = C::BN, NH = C::NH, HB = C::HB;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // everything below works on 32-bit shared-window addresses (see bp_common.cuh)
+  const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars_a = smem_a + C::offBar;
+  const uint32_t items_a = smem_a + C::offItems;
+  uint8_t* smem = smem_raw + (smem_a - smem_u32(smem_raw));
   Barriers& bars = *reinterpret_cast<Barriers*>(smem + C::offBar);
 
   const int warp = threadIdx.x >> 5;
@@ -195,6 +271,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.q_full[i], 1);
       mbar_init(&bars.q_empty[i], 2);   // both MMA warps release a Q buffer
@@ -207,7 +284,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int h = 0; h < 2; ++h) {
         mbar_init(&bars.p_ready[i][h], 128);
         mbar_init(&bars.pv_done[i][h], 1);
+        bars.busy[i][h] = 0;
       }
+    }
+    for (int i = 0; i < kItemSlots; ++i) {
+      mbar_init(&bars.item_full[i], 1);
+      mbar_init(&bars.item_empty[i], 2 + 8 * NH);   // one lane of every MMA and softmax warp
     }
     fence_barrier_init();
   }
@@ -220,56 +302,117 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
+  // every consumer role walks the item ring with its own sequence number
+  uint32_t item_seq = 0;
+  auto next_item = [&]() {
+    const uint32_t slot = item_seq % kItemSlots;
+    mbar_wait_a(BAR_I(item_full, slot), (item_seq / kItemSlots) & 1);
+    const Item it = get_item(items_a + slot * 64);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(BAR_I(item_empty, slot));
+    ++item_seq;
+    return it;
+  };
+
   if (warp < 4) {
     reg_dealloc<C::kRegsLow>();
     if (warp == 0) {
-      // ===================== TMA producer (whole warp walks the loop, lane 0 issues) =====================
+      // ===================== scheduler + TMA producer (whole warp walks the loop, lane 0 issues) =====================
       uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no % kQBufs, K/V slot = blk & 1
+      uint32_t seq = 0;               // items published (valid items + the end marker)
       Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
-      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
-        const Item it = decode_item<BN>(p, w);
-        if (!it.valid) continue;
+      auto publish = [&](const Item& it) {
+        const uint32_t slot = seq % kItemSlots;
+        if (seq >= kItemSlots) mbar_wait_a(BAR_I(item_empty, slot), ((seq / kItemSlots) - 1) & 1);
+        if (lane == 0) {
+          put_item(items_a + slot * 64, it);
+          mbar_arrive_a(BAR_I(item_full, slot));
+        }
+        ++seq;
+      };
+      // lane 0 draws the next ticket; the result is only consumed (shuffled to the warp) much later
+      auto draw = [&]() {
+        unsigned int d = 0;
+        if (lane == 0) d = gridDim.x + atomicAdd(p.sched, 1u);
+        return d;
+      };
+      // slow path: first item, and tickets that decode to empty items (rows beyond a short sequence)
+      auto fetch_valid = [&](int& w) {
+        while (w < p.num_items) {
+          const Item c = decode_finish<BN>(p, decode_prefetch(p, w));
+          w = static_cast<int>(__shfl_sync(0xffffffffu, draw(), 0));
+          if (c.n_max() > 0) return c;
+        }
+        return end_item();
+      };
+      int w = blockIdx.x;   // first ticket is static; the following ones come from the global counter
+      Item cur = fetch_valid(w);
+      publish(cur);
+      while (!cur.end) {
+        // Next item: ticket w is already known.  Start its cu_seqlens loads and the draw after it now, publish it
+        // after the first loads of the current item are out, so that the other roles never wait for an item.
+        const bool have_next = w < p.num_items;
+        ItemPre pre;
+        unsigned int drawn = 0;
+        if (have_next) {
+          pre = decode_prefetch(p, w);
+          drawn = draw();
+        }
+        const Item it = cur;
+        const int n_max = it.n_max();
         const uint32_t qb = item_no % C::kQBufs;
-        if (item_no >= C::kQBufs) mbar_wait(&bars.q_empty[qb], ((item_no / C::kQBufs) - 1) & 1);
+        if (item_no >= C::kQBufs) mbar_wait_a(BAR_I(q_empty, qb), ((item_no / C::kQBufs) - 1) & 1);
         if (lane == 0) {
           const int n_q_tiles = (it.row0 + BM < it.len_q) ? 2 : 1;
-          mbar_arrive_expect_tx(&bars.q_full[qb], n_q_tiles * C::kQTileBytes);
+          mbar_arrive_expect_tx_a(BAR_I(q_full, qb), n_q_tiles * C::kQTileBytes);
           for (int t = 0; t < n_q_tiles; ++t)
             for (int pn = 0; pn < C::kPanelsD; ++pn)
-              tma_load_3d(smem + C::offQ + (qb * 2 + t) * C::kQTileBytes + pn * (BM * 128), &tmQ, &bars.q_full[qb],
-                          pn * 64, it.head, it.q_begin + it.row0 + t * BM);
+              tma_load_3d_a(smem_a + C::offQ + (qb * 2 + t) * C::kQTileBytes + pn * (BM * 128), &tmQ,
+                            BAR_I(q_full, qb), pn * 64, it.head, it.q_begin + it.row0 + t * BM);
         }
-        for (int j = 0; j < it.n_max; ++j, ++blk) {
+        auto issue_kv = [&](int j) {
           const uint32_t slot = blk & 1;
           const int krow = it.k_begin + j * BN;
-          if (blk >= 2) mbar_wait(&bars.k_empty[slot], ((blk >> 1) - 1) & 1);
+          if (blk >= 2) mbar_wait_a(BAR_I(k_empty, slot), ((blk >> 1) - 1) & 1);
           tr.rec(1, blk);
           if (lane == 0) {
-            mbar_arrive_expect_tx(&bars.k_full[slot], C::kKVTileBytes);
+            mbar_arrive_expect_tx_a(BAR_I(k_full, slot), C::kKVTileBytes);
             for (int pn = 0; pn < C::kPanelsD; ++pn)
-              tma_load_3d(smem + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK,
-                          &bars.k_full[slot], pn * 64, it.head, krow);
+              tma_load_3d_a(smem_a + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK,
+                            BAR_I(k_full, slot), pn * 64, it.head, krow);
           }
-          if (blk >= 2) mbar_wait(&bars.v_empty[slot], ((blk >> 1) - 1) & 1);
+          if (blk >= 2) mbar_wait_a(BAR_I(v_empty, slot), ((blk >> 1) - 1) & 1);
           tr.rec(2, blk);
           if (lane == 0) {
-            mbar_arrive_expect_tx(&bars.v_full[slot], C::kKVTileBytes);
+            mbar_arrive_expect_tx_a(BAR_I(v_full, slot), C::kKVTileBytes);
             for (int pn = 0; pn < C::kPanelsD; ++pn)
-              tma_load_3d(smem + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV,
-                          &bars.v_full[slot], pn * 64, it.head, krow);
+              tma_load_3d_a(smem_a + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV,
+                            BAR_I(v_full, slot), pn * 64, it.head, krow);
           }
           __syncwarp();
+          ++blk;
+        };
+        const int n_first = min(n_max, 2);
+        for (int j = 0; j < n_first; ++j) issue_kv(j);
+        Item nxt = end_item();
+        if (have_next) {
+          nxt = decode_finish<BN>(p, pre);
+          w = static_cast<int>(__shfl_sync(0xffffffffu, drawn, 0));
+          if (nxt.n_max() == 0) nxt = fetch_valid(w);
         }
+        publish(nxt);
+        for (int j = n_first; j < n_max; ++j) issue_kv(j);
         ++item_no;
+        cur = nxt;
       }
     } else if (warp == 1 || warp == 2) {
       // ===================== MMA issuer of query tile t (whole warp waits, lane 0 issues) =====================
       const int t = warp - 1;
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
       constexpr uint32_t idesc_pv = make_idesc(kBF16, BM, DP, false, true);
-      const uint32_t sK = smem_u32(smem + C::offK);
-      const uint32_t sV = smem_u32(smem + C::offV);
-      const uint32_t sP = smem_u32(smem + C::offP) + t * C::kPTileBytes;
+      const uint32_t sK = smem_a + C::offK;
+      const uint32_t sV = smem_a + C::offV;
+      const uint32_t sP = smem_a + C::offP + t * C::kPTileBytes;
       const uint32_t tS = tmem_base + C::colS + t * BN;
       const uint32_t tO = tmem_base + C::colO + t * NH * DP;
       uint32_t item_no = 0, blk = 0;  // same running counters as the producer
@@ -277,21 +420,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pv_cnt = 0;            // key blocks whose PV products were issued (p_ready / pv_done phases)
       Tracer tr(p.trace, 1 + t, blockIdx.x == 0 && lane == 0);
 
-      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
-        const Item it = decode_item<BN>(p, w);
-        if (!it.valid) continue;
+      while (true) {
+        const Item it = next_item();
+        if (it.end) break;
         const uint32_t qb = item_no % C::kQBufs;
-        const uint32_t sQ = smem_u32(smem + C::offQ) + (qb * 2 + t) * C::kQTileBytes;
+        const uint32_t sQ = smem_a + C::offQ + (qb * 2 + t) * C::kQTileBytes;
         const int n = it.n_of(t);
-        mbar_wait(&bars.q_full[qb], (item_no / C::kQBufs) & 1);
+        const int n_max = it.n_max();
+        mbar_wait_a(BAR_I(q_full, qb), (item_no / C::kQBufs) & 1);
 
         // S(j) = Q K_j^T into this tile's S buffer, then hand the K slot back (both tiles must do so)
         auto step_s = [&](int j, uint32_t kblk) {
           const uint32_t slot = kblk & 1;
           if (j < n) {
-            if (s_cnt >= 1) mbar_wait(&bars.s_free[t], (s_cnt - 1) & 1);   // softmax has read the previous S
+            if (s_cnt >= 1) mbar_wait_a(BAR_I(s_free, t), (s_cnt - 1) & 1);   // softmax has read the previous S
             tr.rec(1, kblk);
-            mbar_wait(&bars.k_full[slot], (kblk >> 1) & 1);
+            mbar_wait_a(BAR_I(k_full, slot), (kblk >> 1) & 1);
             tc_fence_after();
             tr.rec(2, kblk);
             if (lane == 0) {
@@ -302,32 +446,32 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 umma_ss(tS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_s,
                         kk > 0 ? 1u : 0u);
               }
-              umma_commit(&bars.k_empty[slot]);
-              if (j == n - 1) umma_commit(&bars.q_empty[qb]);   // last read of this item's Q tile
-              umma_commit(&bars.s_full[t]);
+              umma_commit_a(BAR_I(k_empty, slot));
+              if (j == n - 1) umma_commit_a(BAR_I(q_empty, qb));   // last read of this item's Q tile
+              umma_commit_a(BAR_I(s_full, t));
             }
             ++s_cnt;
           } else {
             // Block not visited by this tile.  The slot still needs this warp's release, but only once the
             // producer has (re)filled it for THIS block: arriving earlier could complete the previous
             // phase of k_empty while the other tile still reads the previous occupant.
-            mbar_wait(&bars.k_full[slot], (kblk >> 1) & 1);
-            if (lane == 0) umma_commit(&bars.k_empty[slot]);
+            mbar_wait_a(BAR_I(k_full, slot), (kblk >> 1) & 1);
+            if (lane == 0) umma_commit_a(BAR_I(k_empty, slot));
           }
           __syncwarp();
         };
 
-        if (n == 0 && lane == 0) umma_commit(&bars.q_empty[qb]);
+        if (n == 0 && lane == 0) umma_commit_a(BAR_I(q_empty, qb));
         step_s(0, blk);
-        for (int j = 0; j < it.n_max; ++j, ++blk) {
-          if (j + 1 < it.n_max) step_s(j + 1, blk + 1);
+        for (int j = 0; j < n_max; ++j, ++blk) {
+          if (j + 1 < n_max) step_s(j + 1, blk + 1);
           const uint32_t slot = blk & 1;
           if (j < n) {
-            mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);
+            mbar_wait_a(BAR_I(v_full, slot), (blk >> 1) & 1);
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
               // O_{t,h} (+)= P_{t,h} V_j[h*64 : h*64+64, :]   (V rows are the K dimension: MN-major B)
-              mbar_wait(&bars.p_ready[t][h], pv_cnt & 1);
+              mbar_wait_a(BAR_I(p_ready, t * 2 + h), pv_cnt & 1);
               tc_fence_after();
               tr.rec(3 + h, blk);
               if (lane == 0) {
@@ -338,15 +482,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   umma_ss(tO + h * DP, make_smem_desc_sw128(a, 16, 1024),
                           make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
                 }
-                if (h == NH - 1) umma_commit(&bars.v_empty[slot]);
-                umma_commit(&bars.pv_done[t][h]);
+                if (h == NH - 1) umma_commit_a(BAR_I(v_empty, slot));
+                umma_commit_a(BAR_I(pv_done, t * 2 + h));
               }
               __syncwarp();
             }
             ++pv_cnt;
           } else {
-            mbar_wait(&bars.v_full[slot], (blk >> 1) & 1);   // same pacing rule as for K
-            if (lane == 0) umma_commit(&bars.v_empty[slot]);
+            mbar_wait_a(BAR_I(v_full, slot), (blk >> 1) & 1);   // same pacing rule as for K
+            if (lane == 0) umma_commit_a(BAR_I(v_empty, slot));
             __syncwarp();
           }
         }
@@ -364,22 +508,31 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN + h * HB;
     const uint32_t tO_tile = tmem_base + lane_addr + C::colO + t * NH * DP;
     const uint32_t tO = tO_tile + h * DP;
-    uint8_t* sP = smem + C::offP + t * C::kPTileBytes + h * (BM * 128);
-    float2* xchg = reinterpret_cast<float2*>(smem + C::offX) + t * NH * 128;
+    // this thread's row of the P panel: chunk c8 lives at row_base + ((c8 ^ (r & 7)) << 4)
+    const uint32_t sP_row = smem_a + C::offP + t * C::kPTileBytes + h * (BM * 128) + r * 128;
+    const uint32_t sw = (r & 7) << 4;
+    const uint32_t sO_tile = smem_a + C::offP + t * C::kPTileBytes;   // O staging = P panel of stream 0
+    const uint32_t sO_row = sO_tile + r * 128;
+    bool store_pending = false;
+    const uint32_t xchg_a = smem_a + C::offX + t * NH * 128 * 8;
+    const uint32_t bar_s_full = BAR_I(s_full, t), bar_s_free = BAR_I(s_free, t);
+    const uint32_t bar_p_ready = BAR_I(p_ready, t * 2 + h), bar_pv_done = BAR_I(pv_done, t * 2 + h);
+    const uint32_t busy_mine = BAR(busy) + 4u * (t * 2 + h), busy_other = BAR(busy) + 8u * (t ^ 1);
     const float scale_log2 = p.scale_log2;
     uint32_t cnt = 0;  // key blocks processed by this warpgroup (phases of s_full / pv_done)
     Tracer tr(p.trace, 3 + g, blockIdx.x == 0 && r == 0);
-    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
-      const Item it = decode_item<BN>(p, w);
+    while (true) {
+      const Item it = next_item();
+      if (it.end) break;
       const int n = it.n_of(t);
-      if (!it.valid || n == 0) continue;
+      if (n == 0) continue;
       const int qrow = it.row0 + t * BM + r;       // query index within the sequence
       float m_used = 0.f;  // running max (raw score units) the exponentials are taken against
       float l = 0.f;
 
       for (int j = 0; j < n; ++j, ++cnt) {
         tr.rec(0, cnt);
-        mbar_wait(&bars.s_full[t], cnt & 1);
+        mbar_wait_a(bar_s_full, cnt & 1);
         tc_fence_after();
         tr.rec(1, cnt);
         float s[HB];
@@ -392,7 +545,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&bars.s_free[t]);   // S(j+1) may now overwrite the buffer while we work on registers
+        mbar_arrive_a(bar_s_free);   // S(j+1) may now overwrite the buffer while we work on registers
         tr.rec(2, cnt);
 
         const int col0 = j * BN + h * HB;
@@ -427,9 +580,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tr.rec(3, cnt);
-        if (j > 0) {
+        if (j == 0) {
+          if constexpr (C::kStageO) {
+            // The previous item's O tile was staged in this stream's P panel: the TMA store must have read it
+            if (h == 0 && store_pending) {
+              if (r == 0) tma_store_wait_read<0>();
+              if (t == 0) named_bar_sync(3, 128); else named_bar_sync(4, 128);
+              store_pending = false;
+            }
+          }
+        } else {
           // P tile and O accumulator are free once the previous PV MMA of this stream has completed
-          mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
+          mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
           tc_fence_after();
           tr.rec(4, cnt);
           if (__any_sync(0xffffffffu, grow)) {
@@ -446,6 +608,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st_wait();
           }
           l *= alpha;
+        }
+        if constexpr (kStagger && NH == 2) {
+          // Advisory anti-phase scheduling of the two query tiles: the exponentials of one tile should run
+          // while the other tile's warps wait on barriers / TMEM loads / take their row max, instead of all
+          // sixteen softmax warps hitting the MUFU pipe together and then idling together.  A tile defers its
+          // exponential phase while the other tile is inside its own (bounded: this is a hint, never a
+          // dependency, so unequal block counts and epilogues cannot deadlock).
+          int spins = 0;
+          while (ld_volatile_shared_u32(busy_other) + ld_volatile_shared_u32(busy_other + 4) != 0 &&
+                 spins < kStaggerMaxSpins)
+            ++spins;
+          if (r == 0) st_volatile_shared_u32(busy_mine, 1);
         }
 
         const float neg_m = -m_used * scale_log2;
@@ -467,32 +641,33 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           add2(sum4[2], sum4[3], e[2], e[3]);
           add2(sum4[0], sum4[1], e[4], e[5]);
           add2(sum4[2], sum4[3], e[6], e[7]);
-          uint4 v;
-          v.x = pack2<kBF16>(e[0], e[1]);
-          v.y = pack2<kBF16>(e[2], e[3]);
-          v.z = pack2<kBF16>(e[4], e[5]);
-          v.w = pack2<kBF16>(e[6], e[7]);
-          *reinterpret_cast<uint4*>(sP + sw128_offset(r, c8)) = v;
+          sts128(sP_row + ((c8 << 4) ^ sw), pack2<kBF16>(e[0], e[1]), pack2<kBF16>(e[2], e[3]),
+                 pack2<kBF16>(e[4], e[5]), pack2<kBF16>(e[6], e[7]));
+          if constexpr (kStagger && NH == 2) {
+            // hand the MUFU pipe over a little early: the other tile needs ~100 cycles to notice
+            if (c8 == HB / 8 - 2 && r == 0) st_volatile_shared_u32(busy_mine, 0);
+          }
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         tr.rec(5, cnt);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&bars.p_ready[t][h]);
+        mbar_arrive_a(bar_p_ready);
         tr.rec(6, cnt);
       }
 
       // ---- epilogue: merge the NH streams, O / l -> global, LSE ----
       tr.rec(7, cnt);
-      mbar_wait(&bars.pv_done[t][h], (cnt - 1) & 1);
+      mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
       tc_fence_after();
       tr.rec(8, cnt);
       const bool valid = qrow < it.len_q;
       float w_self = 1.f, w_other = 0.f, m_all = m_used, l_all = l;
       if constexpr (NH == 2) {
-        xchg[h * 128 + r] = make_float2(m_used, l);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xchg_a + (h * 128 + r) * 8), "f"(m_used), "f"(l) : "memory");
         if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
-        const float2 o = xchg[(h ^ 1) * 128 + r];
+        float2 o;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(xchg_a + ((h ^ 1) * 128 + r) * 8) : "memory");
         const bool has_self = l > 0.f, has_other = o.y > 0.f;
         m_all = has_self ? (has_other ? fmaxf(m_used, o.x) : m_used) : o.x;
         w_self = has_self ? fast_exp2((m_used - m_all) * scale_log2) : 0.f;
@@ -503,33 +678,44 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       w_self *= inv_l;
       w_other *= inv_l;
       constexpr int kColsPerWG = DP / NH;   // output columns written by this warpgroup
+      // Full tiles are staged in shared memory (128B-swizzled rows, the layout the TMA store expects) and leave
+      // as ONE bulk store; a thread-per-row store would touch 32 different lines per instruction.  Tiles that
+      // end inside the sequence keep the guarded per-row stores (the next sequence's rows follow in memory).
+      const bool stage = C::kStageO && (it.row0 + t * BM + BM <= it.len_q);
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
                       2 * (static_cast<int64_t>(it.q_begin + qrow) * p.o_row_stride + it.head * p.o_head_stride +
                            h * kColsPerWG);
 #pragma unroll
-      for (int c = 0; c < kColsPerWG / 16; ++c) {
-        uint32_t o[16];
-        float f[16];
-        tmem_ld16(tO + h * kColsPerWG + c * 16, o);   // own accumulator, this warpgroup's columns
+      for (int c = 0; c < kColsPerWG / 32; ++c) {
+        // both accumulators' columns are fetched with one TMEM round trip
+        uint32_t o[32], o2[32];
+        float f[32];
+        tmem_ld32(tO + h * kColsPerWG + c * 32, o);   // own accumulator, this warpgroup's columns
+        if constexpr (NH == 2) tmem_ld32(tO_tile + (h ^ 1) * DP + h * kColsPerWG + c * 32, o2);   // sibling stream
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * w_self;
-        if constexpr (NH == 2) {
-          tmem_ld16(tO_tile + (h ^ 1) * DP + h * kColsPerWG + c * 16, o);   // sibling stream, same columns
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(o[i]), w_other, f[i]);
+        for (int i = 0; i < 32; ++i) {
+          f[i] = __uint_as_float(o[i]) * w_self;
+          if constexpr (NH == 2) f[i] = fmaf(__uint_as_float(o2[i]), w_other, f[i]);
         }
-        if (valid) {
+        if (stage) {
+          if constexpr (C::kStageO) {
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (h * kColsPerWG + c * 16 + q * 8 < p.headdim) {
+            for (int q = 0; q < 4; ++q)
+              sts128(sO_row + ((static_cast<uint32_t>(h * 4 + q) << 4) ^ sw), pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]),
+                     pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]), pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]),
+                     pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]));
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (h * kColsPerWG + c * 32 + q * 8 < p.headdim) {
               uint4 v;
               v.x = pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]);
               v.y = pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]);
               v.z = pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]);
               v.w = pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(orow + (c * 16 + q * 8) * 2) = v;
+              *reinterpret_cast<uint4*>(orow + (c * 32 + q * 8) * 2) = v;
             }
           }
         }
@@ -540,10 +726,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // Both accumulators of this tile have been read (wait::ld) by this warpgroup; the sibling must be done
       // too before either stream's next PV (accumulate = 0) may overwrite them, and before xchg is reused.
       tc_fence_before();
+      if (stage) fence_proxy_async_smem();   // staged O rows -> visible to the TMA store
       if constexpr (NH == 2) {
         if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
       }
+      if constexpr (C::kStageO) {
+        if (stage && h == 0) {
+          if (r == 0) {
+            tma_store_3d(&tmO, sO_tile, 0, it.head, it.q_begin + it.row0 + t * BM);
+            tma_store_commit();
+          }
+          store_pending = true;   // checked before this stream's next write to its P panel
+        }
+      }
       tr.rec(9, cnt);
+    }
+    if constexpr (C::kStageO) {
+      if (h == 0 && r == 0) tma_store_wait_all();   // shared memory must outlive the last O store
     }
   }
 
@@ -551,11 +750,36 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 3) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (threadIdx.x == 0) {
+    // The last CTA to finish re-arms the ticket counter for the next launch that uses this slot (every CTA
+    // has drawn its last ticket before it gets here).
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// Ticket counters of the dynamic scheduler: {tickets drawn, CTAs finished} per slot, zero between launches (the
+// last CTA of a launch re-arms its slot).  Launches rotate over the slots so that kernels in flight on different
+// streams never share one.
+__device__ unsigned int g_sched[kSchedSlots * 2];
+
+static unsigned int* next_sched_slot() {
+  static std::atomic<unsigned int> launch_no{0};
+  void* base = nullptr;
+  if (cudaGetSymbolAddress(&base, g_sched) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return static_cast<unsigned int*>(base) + 2 * (launch_no.fetch_add(1) % kSchedSlots);
 }
 
 template <int DP, bool kBF16>
-int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Params& p,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+           const Params& p, cudaStream_t stream) {
   using C = Cfg<DP>;
   auto kern = fmha_fwd_kernel<DP, kBF16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -568,7 +792,10 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_items < sms ? p.num_items : sms;
-  kern<<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  Params pp = p;
+  pp.sched = next_sched_slot();
+  if (!pp.sched) return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaGetSymbolAddress(g_sched) failed");
+  kern<<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, pp);
   return check_launch("bp_fmha_fwd launch");
 }
 
@@ -612,7 +839,7 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
 
   const int DP = headdim <= 64 ? 64 : 128;
   const int BN = DP == 64 ? 128 : 64;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   {
     const uint64_t dq[3] = {(uint64_t)headdim, (uint64_t)nheads, (uint64_t)total_q};
     const uint64_t sq[2] = {(uint64_t)q_head_stride * 2, (uint64_t)q_row_stride * 2};
@@ -624,6 +851,8 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
     if (int rc = encode_tensor_map(&tmK, dtype, 3, k, dk, sk, bk, true)) return rc;
     const uint64_t sv[2] = {(uint64_t)v_head_stride * 2, (uint64_t)v_row_stride * 2};
     if (int rc = encode_tensor_map(&tmV, dtype, 3, v, dk, sv, bk, true)) return rc;
+    const uint64_t so[2] = {(uint64_t)o_head_stride * 2, (uint64_t)o_row_stride * 2};
+    if (int rc = encode_tensor_map(&tmO, dtype, 3, out, dq, so, bq, true)) return rc;
   }
   fmha::Params p;
   p.out = out;
@@ -646,6 +875,7 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
   p.trace = g_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
-  if (DP == 64) return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, p, st) : fmha::launch<64, false>(tmQ, tmK, tmV, p, st);
-  return bf16 ? fmha::launch<128, true>(tmQ, tmK, tmV, p, st) : fmha::launch<128, false>(tmQ, tmK, tmV, p, st);
+  if (DP == 64)
+    return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, tmO, p, st) : fmha::launch<64, false>(tmQ, tmK, tmV, tmO, p, st);
+  return bf16 ? fmha::launch<128, true>(tmQ, tmK, tmV, tmO, p, st) : fmha::launch<128, false>(tmQ, tmK, tmV, tmO, p, st);
 }
