@@ -44,11 +44,14 @@ constexpr int kItemSlots = 4;     // shared-memory ring of decoded work items (p
 constexpr int kChunkBH = 148;     // (batch, head) pairs per scheduling chunk
 constexpr int kSchedSlots = 64;   // ticket counters, one per in-flight launch (rotating)
 #ifndef BP_FMHA_STAGGER
-#define BP_FMHA_STAGGER 1
+#define BP_FMHA_STAGGER 0
 #endif
 constexpr bool kStagger = BP_FMHA_STAGGER != 0;   // anti-phase hint between the two query tiles' softmax warps
 constexpr int kStaggerMaxSpins = 256;   // x ~25 cycles per probe: a few exponential phases at most
-constexpr int kPolyPairs = 0;   // of every 4 score pairs, how many take the polynomial exp2 (FMA pipe) instead of MUFU; measured: 1 -> 139 us vs 0 -> 134 us at config 2 (the lockstep softmax warps are issue-limited, not MUFU-limited)
+#ifndef BP_FMHA_POLY_PAIRS
+#define BP_FMHA_POLY_PAIRS 0
+#endif
+constexpr int kPolyPairs = BP_FMHA_POLY_PAIRS;   // of every 4 score pairs, how many take the polynomial exp2 (FMA pipe) instead of MUFU; measured: 1 -> 139 us vs 0 -> 134 us at config 2 (the lockstep softmax warps are issue-limited, not MUFU-limited)
 
 template <int DP>
 struct Cfg {
@@ -111,6 +114,7 @@ struct Barriers {
   uint64_t s_full[2], s_free[2];
   uint64_t p_ready[2][2], pv_done[2][2];   // [tile][stream]
   uint64_t item_full[kItemSlots], item_empty[kItemSlots];
+  uint64_t o_staged[2], o_free[2];         // [tile]: O tile staged in smem / read out by the TMA store
   uint32_t tmem_base;
   uint32_t busy[2][2];                     // [tile][stream]: softmax warpgroup is in its exponential phase
 };
@@ -265,6 +269,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef BP_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    uint64_t ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.trace[8 * kTraceRecs * 2 + 2 * blockIdx.x] = ns;
+  }
+#endif
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -287,9 +298,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bars.busy[i][h] = 0;
       }
     }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.o_staged[i], 256);
+      mbar_init(&bars.o_free[i], 1);
+    }
     for (int i = 0; i < kItemSlots; ++i) {
       mbar_init(&bars.item_full[i], 1);
-      mbar_init(&bars.item_empty[i], 2 + 8 * NH);   // one lane of every MMA and softmax warp
+      mbar_init(&bars.item_empty[i], 2 + 8 * NH + (C::kStageO ? 1 : 0));   // one lane of every consumer warp
     }
     fence_barrier_init();
   }
@@ -496,6 +511,29 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         ++item_no;
       }
+    } else if (C::kStageO) {
+      // ===================== warp 3: O tile stores =====================
+      // The softmax warpgroups stage a finished O tile in shared memory; this otherwise idle warp issues the
+      // TMA store, waits until the tile has been read out and hands the buffer (stream 0's P panel) back.
+      uint32_t st_cnt[2] = {0, 0};
+      while (true) {
+        const Item it = next_item();
+        if (it.end) break;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (it.n_of(t) == 0 || it.row0 + t * BM + BM > it.len_q) continue;   // tile absent or stored row by row
+          mbar_wait_a(BAR_I(o_staged, t), st_cnt[t] & 1);
+          if (lane == 0) {
+            tma_store_3d(&tmO, smem_a + C::offP + t * C::kPTileBytes, 0, it.head, it.q_begin + it.row0 + t * BM);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive_a(BAR_I(o_free, t));
+          }
+          __syncwarp();
+          ++st_cnt[t];
+        }
+      }
+      if (lane == 0) tma_store_wait_all();   // shared memory must outlive the last store
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -511,9 +549,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // this thread's row of the P panel: chunk c8 lives at row_base + ((c8 ^ (r & 7)) << 4)
     const uint32_t sP_row = smem_a + C::offP + t * C::kPTileBytes + h * (BM * 128) + r * 128;
     const uint32_t sw = (r & 7) << 4;
-    const uint32_t sO_tile = smem_a + C::offP + t * C::kPTileBytes;   // O staging = P panel of stream 0
-    const uint32_t sO_row = sO_tile + r * 128;
+    const uint32_t sO_row = smem_a + C::offP + t * C::kPTileBytes + r * 128;   // O staging = P panel of stream 0
     bool store_pending = false;
+    uint32_t st_cnt = 0;   // O tiles of this query tile handed to warp 3
     const uint32_t xchg_a = smem_a + C::offX + t * NH * 128 * 8;
     const uint32_t bar_s_full = BAR_I(s_full, t), bar_s_free = BAR_I(s_free, t);
     const uint32_t bar_p_ready = BAR_I(p_ready, t * 2 + h), bar_pv_done = BAR_I(pv_done, t * 2 + h);
@@ -550,9 +588,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
         const int col0 = j * BN + h * HB;
         const bool partial = (col0 + HB > it.len_k) || (p.is_causal && (col0 + HB - 1 > it.row0 + t * BM));
+        bool dead = false;   // every key of this half-block is masked for every row of this warp
         if (partial) {
           // visible keys of this row inside the half-block: local column c < lim
           const int lim = (p.is_causal ? min(it.len_k, qrow + 1) : it.len_k) - col0;
+          dead = __all_sync(0xffffffffu, lim <= 0);
 #pragma unroll
           for (int c = 0; c < HB; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
         }
@@ -584,8 +624,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if constexpr (C::kStageO) {
             // The previous item's O tile was staged in this stream's P panel: the TMA store must have read it
             if (h == 0 && store_pending) {
-              if (r == 0) tma_store_wait_read<0>();
-              if (t == 0) named_bar_sync(3, 128); else named_bar_sync(4, 128);
+              mbar_wait_a(BAR_I(o_free, t), (st_cnt - 1) & 1);
               store_pending = false;
             }
           }
@@ -615,15 +654,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // sixteen softmax warps hitting the MUFU pipe together and then idling together.  A tile defers its
           // exponential phase while the other tile is inside its own (bounded: this is a hint, never a
           // dependency, so unequal block counts and epilogues cannot deadlock).
-          int spins = 0;
-          while (ld_volatile_shared_u32(busy_other) + ld_volatile_shared_u32(busy_other + 4) != 0 &&
-                 spins < kStaggerMaxSpins)
-            ++spins;
-          if (r == 0) st_volatile_shared_u32(busy_mine, 1);
+          if (!dead) {
+            int spins = 0;
+            while (ld_volatile_shared_u32(busy_other) + ld_volatile_shared_u32(busy_other + 4) != 0 &&
+                   spins < kStaggerMaxSpins)
+              ++spins;
+            if (r == 0) st_volatile_shared_u32(busy_mine, 1);
+          }
         }
 
         const float neg_m = -m_used * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (dead) {
+          // above the causal diagonal: P = 0 without a single exponential
+#pragma unroll
+          for (int c8 = 0; c8 < HB / 8; ++c8) sts128(sP_row + ((c8 << 4) ^ sw), 0u, 0u, 0u, 0u);
+        } else
 #pragma unroll
         for (int c8 = 0; c8 < HB / 8; ++c8) {
           float e[8];
@@ -666,6 +712,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (NH == 2) {
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xchg_a + (h * 128 + r) * 8), "f"(m_used), "f"(l) : "memory");
         if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
+        tr.rec(10, cnt);
         float2 o;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(xchg_a + ((h ^ 1) * 128 + r) * 8) : "memory");
         const bool has_self = l > 0.f, has_other = o.y > 0.f;
@@ -693,6 +740,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tO + h * kColsPerWG + c * 32, o);   // own accumulator, this warpgroup's columns
         if constexpr (NH == 2) tmem_ld32(tO_tile + (h ^ 1) * DP + h * kColsPerWG + c * 32, o2);   // sibling stream
         tmem_ld_wait();
+        tr.rec(11, cnt);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           f[i] = __uint_as_float(o[i]) * w_self;
@@ -725,24 +773,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             m_all * p.scale + __logf(l_all);
       // Both accumulators of this tile have been read (wait::ld) by this warpgroup; the sibling must be done
       // too before either stream's next PV (accumulate = 0) may overwrite them, and before xchg is reused.
+      tr.rec(12, cnt);
       tc_fence_before();
       if (stage) fence_proxy_async_smem();   // staged O rows -> visible to the TMA store
       if constexpr (NH == 2) {
         if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
       }
       if constexpr (C::kStageO) {
-        if (stage && h == 0) {
-          if (r == 0) {
-            tma_store_3d(&tmO, sO_tile, 0, it.head, it.q_begin + it.row0 + t * BM);
-            tma_store_commit();
-          }
-          store_pending = true;   // checked before this stream's next write to its P panel
+        if (stage) {
+          mbar_arrive_a(BAR_I(o_staged, t));   // warp 3 stores the tile
+          ++st_cnt;
+          store_pending = true;   // stream 0 checks o_free before its next write to the P panel
         }
       }
       tr.rec(9, cnt);
-    }
-    if constexpr (C::kStageO) {
-      if (h == 0 && r == 0) tma_store_wait_all();   // shared memory must outlive the last O store
     }
   }
 
@@ -750,6 +794,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 3) tmem_dealloc(tmem_base, C::kTmemCols);
+#ifdef BP_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    uint64_t ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.trace[8 * kTraceRecs * 2 + 2 * blockIdx.x + 1] = ns;
+  }
+#endif
   if (threadIdx.x == 0) {
     // The last CTA to finish re-arms the ticket counter for the next launch that uses this slot (every CTA
     // has drawn its last ticket before it gets here).

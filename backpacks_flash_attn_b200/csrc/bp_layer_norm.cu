@@ -86,54 +86,62 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // NV = 8-element vectors per lane; a row has cols/8 vectors, vector index = i*32 + lane.
+// gamma / beta live in shared memory in their storage type (read back 16 bytes at a time, conflict-free), not
+// in registers: with the row itself (NV x 8 floats) that keeps the kernel under 85 registers, so 24 warps per
+// SM keep enough loads in flight to cover the HBM latency.
 template <typename X, typename R, typename W, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const W* __restrict__ gamma,
                        const W* __restrict__ beta, X* __restrict__ z, R* __restrict__ x_out,
                        float* __restrict__ mu_out, float* __restrict__ rs_out, int64_t rows, int cols, float eps) {
+  extern __shared__ uint4 ln_smem[];   // [cols] gamma then [cols] beta, in W
+  W* s_gamma = reinterpret_cast<W*>(ln_smem);
+  W* s_beta = s_gamma + cols;
   const int lane = threadIdx.x & 31;
   const int nvec = cols >> 3;
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kWarpsPerCta;
   const float inv_cols = 1.f / static_cast<float>(cols);
 
-  // gamma / beta are reused by every row this warp handles
-  float g[NV][8], b[NV][8];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int v = i * 32 + lane;
-    if (v < nvec) {
-      Vec8<W> t;
-      t.load(gamma + v * 8);
-      t.to(g[i]);
-      t.load(beta + v * 8);
-      t.to(b[i]);
-    }
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    Vec8<W> t;
+    t.load(gamma + v * 8);
+    t.store(s_gamma + v * 8);
+    t.load(beta + v * 8);
+    t.store(s_beta + v * 8);
   }
+  __syncthreads();
 
   for (int64_t row = warp_global; row < rows; row += warp_stride) {
     const int64_t base = row * cols;
     float x[NV][8];
+    // all loads of the row are issued before the first use
+    Vec8<X> a[NV];
+    Vec8<R> r[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = i * 32 + lane;
+      if (v < nvec) {
+        a[i].load(x0 + base + v * 8);
+        if (x1 != nullptr) r[i].load(x1 + base + v * 8);
+      }
+    }
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = i * 32 + lane;
       if (v < nvec) {
-        Vec8<X> t;
-        t.load(x0 + base + v * 8);
-        t.to(x[i]);
+        a[i].to(x[i]);
         if (x1 != nullptr) {
-          Vec8<R> r;
           float rf[8];
-          r.load(x1 + base + v * 8);
-          r.to(rf);
+          r[i].to(rf);
 #pragma unroll
           for (int k = 0; k < 8; ++k) x[i][k] += rf[k];
         }
         if (x_out != nullptr) {
-          Vec8<R> r;
-          r.from(x[i]);
-          r.store(x_out + base + v * 8);
+          Vec8<R> o;
+          o.from(x[i]);
+          o.store(x_out + base + v * 8);
           // the reference normalises the value it stored (ln_fwd_kernels.cuh keeps x in compute type;
           // with a 16-bit residual stream the stored value is the rounded one) -- keep fp32 here.
         }
@@ -162,12 +170,17 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
     for (int i = 0; i < NV; ++i) {
       const int v = i * 32 + lane;
       if (v < nvec) {
-        float y[8];
+        float g[8], b[8], y[8];
+        Vec8<W> t;
+        t.load(s_gamma + v * 8);
+        t.to(g);
+        t.load(s_beta + v * 8);
+        t.to(b);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = g[i][k] * ((x[i][k] - mu) * rs) + b[i][k];
-        Vec8<X> t;
-        t.from(y);
-        t.store(z + base + v * 8);
+        for (int k = 0; k < 8; ++k) y[k] = g[k] * ((x[i][k] - mu) * rs) + b[k];
+        Vec8<X> o;
+        o.from(y);
+        o.store(z + base + v * 8);
       }
     }
   }
@@ -180,9 +193,18 @@ int launch_nv(const void* x0, const void* x1, const void* gamma, const void* bet
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ctas_needed = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-  const int64_t cap = static_cast<int64_t>(sms) * 8;  // 8 resident CTAs of 256 threads per SM
+  const int64_t cap = static_cast<int64_t>(sms) * 3;  // 3 resident CTAs of 256 threads per SM (register-limited)
   const int grid = static_cast<int>(ctas_needed < cap ? ctas_needed : cap);
-  ln_residual_fwd_kernel<X, R, W, NV><<<grid, kWarpsPerCta * 32, 0, st>>>(
+  const size_t smem = 2 * static_cast<size_t>(cols) * sizeof(W);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ln_residual_fwd_kernel<X, R, W, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BP_ERR_CUDA, "bp_ln_residual_fwd: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
+    }
+  }
+  ln_residual_fwd_kernel<X, R, W, NV><<<grid, kWarpsPerCta * 32, smem, st>>>(
       static_cast<const X*>(x0), static_cast<const R*>(x1), static_cast<const W*>(gamma),
       static_cast<const W*>(beta), static_cast<X*>(z), static_cast<R*>(x_out), mu, rs, rows, cols, eps);
   return check_launch("bp_ln_residual_fwd launch");

@@ -11,7 +11,7 @@ from backpacks_flash_attn_b200 import _lib
 which = sys.argv[1] if len(sys.argv) > 1 else "fmha"
 limit = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
 R, N = 8, 512
-buf = torch.zeros(R * N * 2, dtype=torch.int64, device="cuda")
+buf = torch.zeros(R * N * 2 + 2 * 148, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 lib.bp_debug_set_trace.argtypes = [ctypes.c_void_p]
 lib.bp_debug_set_trace.restype = None
@@ -37,7 +37,8 @@ lib.bp_debug_set_trace(buf.data_ptr())
 run()
 torch.cuda.synchronize()
 lib.bp_debug_set_trace(None)
-t = buf.cpu().view(R, N, 2)
+cta = buf.cpu()[R * N * 2:].view(148, 2)
+t = buf.cpu()[:R * N * 2].view(R, N, 2)
 starts = [int(t[r, 0, 1]) for r in range(R) if int(t[r, 0, 1]) > 0]
 t0 = min(starts)
 events = []
@@ -50,4 +51,10 @@ for r in range(R):
 events.sort()
 for e in events[:limit]:
     print(f"{e[0]:8d} {e[1]:5s} ev{e[2]} #{e[3]}")
+if int(cta[:, 0].max()) > 0:
+    t0 = int(cta[:, 0][cta[:, 0] > 0].min())
+    ends = sorted(int(e) - t0 for e in cta[:, 1] if int(e) > 0)
+    starts = sorted(int(b) - t0 for b in cta[:, 0] if int(b) > 0)
+    print("CTA start ns: min %d max %d; end ns: min %d p25 %d median %d p75 %d max %d" % (
+        starts[0], starts[-1], ends[0], ends[len(ends) // 4], ends[len(ends) // 2], ends[3 * len(ends) // 4], ends[-1]))
 print("total events", len(events))
