@@ -22,7 +22,7 @@ if which == "fmha":
     qkv = torch.randn(b * s, 3, h, d, device="cuda").bfloat16()
     cu = torch.arange(0, (b + 1) * s, s, dtype=torch.int32, device="cuda")
     run = lambda: flash_attn_unpadded_qkvpacked_func(qkv, cu, s, 0.0, causal=True)
-    names = ["prod", "mma0", "mma1", "sm00", "sm01", "sm10", "sm11", "-"]
+    names = ["prod0", "mma0", "mma1", "sm00", "sm01", "sm10", "sm11", "prod1"]
 else:
     from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
     b, s, nv, d = 64, 1024, 16, 768
