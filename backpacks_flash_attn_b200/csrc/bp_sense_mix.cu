@@ -230,6 +230,35 @@ struct MixCfg {
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
+// Step order of pass 2.  A step is one (sense l, 64-key block j) pair; the n_steps = nv * nj steps of a query tile
+// are walked key-GROUP outermost (kGroup blocks = 256 keys), then sense, then block within the group:
+//     for g: for l: for j in group g: step(l, j)
+// With the sense outermost (the first version) the query tiles of a batch element drift apart -- a tile with 2
+// key blocks is done with sense l after 2 steps, the tile with 16 blocks after 16 -- so the CTAs that run together
+// touch all 25 MB of that batch element's sense vectors and every C tile is re-read from DRAM by most of the 8
+// query tiles that need it (measured: 4.2 GB per launch against 1.9 GB algorithmic).  Group-outermost, all query
+// tiles of a batch element need the same 256-key slab (6 MB) at the same time, which stays in L2; Q_l is
+// reloaded once per (group, sense) instead of once per sense (4 KB per step on average).
+constexpr int kGroup = 4;
+struct StepIter {
+  int nj, nv, g0, gsz, l, jj;
+  __device__ __forceinline__ StepIter(int nj_, int nv_) : nj(nj_), nv(nv_), g0(0), gsz(min(kGroup, nj_)), l(0), jj(0) {}
+  __device__ __forceinline__ int sense() const { return l; }
+  __device__ __forceinline__ int j() const { return g0 + jj; }
+  __device__ __forceinline__ bool first_of_visit() const { return jj == 0; }        // first block of this (group, sense)
+  __device__ __forceinline__ bool last_of_visit() const { return jj == gsz - 1; }
+  __device__ __forceinline__ void next() {
+    if (++jj == gsz) {
+      jj = 0;
+      if (++l == nv) {
+        l = 0;
+        g0 += gsz;
+        gsz = min(kGroup, nj - g0);
+      }
+    }
+  }
+};
+
 struct MixBarriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t s_go[2], k_empty[2];    // s_go[n & 1]: K(n) landed (tx) + S(n-1) drained by its 128 softmax threads
@@ -264,7 +293,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int S = p.seqlen;
   const int row0 = qtile * BM;
   const int nj = (min(S, row0 + BM) + BN - 1) / BN;  // causal key blocks of this query tile
-  const int n_steps = p.nv * nj;                      // step n = sense * nj + j
+  const int n_steps = p.nv * nj;                      // walked in StepIter order
   const int col_base = chunk * C::DC;
   const int ncols = min(C::DC, p.d - col_base);       // multiple of 64
   const int n1 = min(ncols, 256), n2 = ncols - n1;    // the two MMA N extents per k-step
@@ -297,13 +326,14 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 0) {
       // ---- producer A: content tiles C_l[j] : (ncols/64) panels of [64 keys x 64 columns] ----
       Tracer tr(p.trace, 0, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
-      for (int n = 0; n < n_steps; ++n) {
+      StepIter it(nj, p.nv);
+      for (int n = 0; n < n_steps; ++n, it.next()) {
         const int slot = n % C::CS;
         tr.rec(0, n);
         if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
         tr.rec(1, n);
         if (lane == 0) {
-          const int sense = n / nj, j = n - sense * nj;
+          const int sense = it.sense(), j = it.j();
           mbar_arrive_expect_tx(&bars.pv_go[slot], (ncols / 64) * C::kCPanelBytes);
           for (int pn = 0; pn < ncols / 64; ++pn) {
             uint8_t* dst = smem + C::offC + slot * C::kCTileBytes + pn * C::kCPanelBytes;
@@ -317,11 +347,14 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     } else if (warp == 3) {
       // ---- producer B: Q_l (once per sense) and K_l[j] ----
-      for (int n = 0; n < n_steps; ++n) {
-        const int sense = n / nj, j = n - sense * nj;
-        if (j == 0) {
-          const int qs = sense % C::QS;
-          if (sense >= C::QS) mbar_wait(&bars.q_empty[qs], ((sense / C::QS) - 1) & 1);
+      StepIter it(nj, p.nv);
+      int qv = 0;   // (group, sense) visits so far: Q buffer = qv % QS
+      for (int n = 0; n < n_steps; ++n, it.next()) {
+        const int sense = it.sense(), j = it.j();
+        if (it.first_of_visit()) {
+          const int qs = qv % C::QS;
+          if (qv >= C::QS) mbar_wait(&bars.q_empty[qs], ((qv / C::QS) - 1) & 1);
+          ++qv;
           if (lane == 0) {
             mbar_arrive_expect_tx(&bars.q_full[qs], C::kQTileBytes);
             for (int pn = 0; pn < PK; ++pn)
@@ -344,11 +377,12 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
       const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
       Tracer tr(p.trace, 4, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
-      for (int n = 0; n < n_steps; ++n) {
-        const int sense = n / nj, j = n - sense * nj;
-        const int qs = sense % C::QS, ks = n & 1;
+      StepIter it(nj, p.nv);
+      int qv = 0;
+      for (int n = 0; n < n_steps; ++n, it.next()) {
+        const int qs = qv % C::QS, ks = n & 1;
         tr.rec(0, n);
-        if (j == 0) mbar_wait(&bars.q_full[qs], (sense / C::QS) & 1);
+        if (it.first_of_visit()) mbar_wait(&bars.q_full[qs], (qv / C::QS) & 1);
         mbar_wait(&bars.s_go[ks], (n >> 1) & 1);
         tc_fence_after();
         tr.rec(1, n);
@@ -360,9 +394,10 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     idesc_s, kk > 0 ? 1u : 0u);
           }
           umma_commit(&bars.k_empty[ks]);
-          if (j == nj - 1) umma_commit(&bars.q_empty[qs]);
+          if (it.last_of_visit()) umma_commit(&bars.q_empty[qs]);
           umma_commit(&bars.s_full[n & 1]);
         }
+        if (it.last_of_visit()) ++qv;
         __syncwarp();
       }
     } else if (warp == 1) {
@@ -421,13 +456,16 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int i = 0;
     Tracer tr(p.trace, 2 + w, blockIdx.x == 0 && blockIdx.y == 0 && r == 0);
     if (w == 1) mbar_arrive(&bars.s_go[0]);   // "S(-1) drained": lets S(0) go as soon as K(0) has landed
+    StepIter it(nj, p.nv);
+    if (w == 1 && n_steps > 1) it.next();
     for (int n = w; n < n_steps; n += 2, ++i) {
-      const int sense = n / nj, j = n - sense * nj;
+      const int sense = it.sense(), j = it.j();
+      if (n + 2 < n_steps) { it.next(); it.next(); }
       if (sense != cur_sense) {
         cur_sense = sense;
         if (next_id != sense) lse_next = __ldg(lse_row + static_cast<int64_t>(sense) * S);   // skipped a sense
         neg_lse2 = -lse_next * kLog2e;
-        next_id = min(sense + 1, p.nv - 1);
+        next_id = sense + 1 == p.nv ? 0 : sense + 1;   // senses wrap around at the end of a key group
         lse_next = __ldg(lse_row + static_cast<int64_t>(next_id) * S);
       }
       tr.rec(0, n);
