@@ -238,12 +238,15 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // =============================================================================================
 namespace pair {
 constexpr int kThreads = 384;   // warps 0-3 as in the 1-CTA kernel + EIGHT epilogue warps (two per TMEM lane quadrant)
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr uint32_t kABytes = 128 * BK * 2;         // this CTA's 128 rows of A          (16 KB)
 constexpr uint32_t kBBytes = 128 * BK * 2;         // this CTA's half (128 rows) of W   (16 KB)
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
+// Every epilogue warp owns 32 rows x 128 columns of the CTA's 128 x 256 tile and two private staging buffers of
+// 32 rows x 64 columns (4 KB): it converts, stages and TMA-stores its part without any CTA-wide barrier.
+constexpr uint32_t kWarpChunkBytes = 32 * 128;
 constexpr uint32_t offOut = kStages * kStageBytes;
-constexpr uint32_t offBar = offOut + 2 * kOutChunkBytes;
+constexpr uint32_t offBar = offOut + 8 * 2 * kWarpChunkBytes;
 constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -331,80 +334,83 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
-    // Eight warps: warp w and w+4 share a TMEM lane quadrant and split every 64-column chunk in two, so the
-    // bias + GELU + convert work per tile (which, with four warps, took longer than the tile's MMAs) halves.
-    const int r = (warp & 3) * 32 + lane;
-    const int hsel = (warp - 4) >> 2;                 // which 32-column half of each 64-column chunk
-    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const bool store_leader = threadIdx.x == 128;
+    // Eight independent warps: warp w owns TMEM lane quadrant (w & 3) (32 rows) and the 128 columns [hsel*128, +128)
+    // of the tile, as two chunks of 64 columns (one 128-byte swizzled row each).  Per chunk: tcgen05.ld -> bias ->
+    // tanh-GELU -> bf16 -> the warp's own staging buffer -> its own TMA store (box 64 x 32).  No CTA-wide barrier:
+    // the bulk-store bookkeeping (wait_group.read) is private to the warp's lane 0.  (The first version staged
+    // 128-row chunks behind two 256-thread barriers per chunk; its ~5000-cycle critical path per tile was longer
+    // than the 6144-cycle main loop of a K = 768 tile once GELU was added.)
+    const int quad = warp & 3;
+    const int hsel = (warp - 4) >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    uint8_t* my_stage = smem + pair::offOut + (warp - 4) * 2 * pair::kWarpChunkBytes;
     uint32_t local = 0, chunk_it = 0;
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-      const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
-      const int n0 = static_cast<int>(tile % p.n_tiles) * 256;
+      const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128 + quad * 32;
+      const int n0 = static_cast<int>(tile % p.n_tiles) * 256 + hsel * 128;
       const uint32_t buf = local & 1;
       mbar_wait(&bars.acc_full[buf], (local >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c64 = 0; c64 < BN / 64; ++c64, ++chunk_it) {
-        const bool outside = n0 + c64 * 64 >= p.n;   // uniform: whole 64-column chunk beyond the matrix
-        uint8_t* stage = smem + pair::offOut + (chunk_it & 1) * kOutChunkBytes;
-        if (!outside) {
-          if (store_leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 256);
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_addr + buf * BN + c64 * 64 + hsel * 32, v);
-          tmem_ld_wait();
-          const int col = n0 + c64 * 64 + hsel * 32;
-          float f[32];
+      // both chunks of this warp leave TMEM first, so the accumulator goes back to the MMA warp early
+      uint32_t v[2][64];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias != nullptr) {
-            const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tmem_base + lane_addr + buf * BN + hsel * 128 + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[c][0]));
+        tmem_ld32(tmem_base + lane_addr + buf * BN + hsel * 128 + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c][32]));
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_leader(&bars.acc_empty[buf]);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              if (col + i < p.n) {
-                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + i));
-                if constexpr (kBF16) {
-                  f[i] += __uint_as_float(w << 16);
-                  f[i + 1] += __uint_as_float(w & 0xFFFF0000u);
-                } else {
-                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                  f[i] += t.x;
-                  f[i + 1] += t.y;
-                }
+      for (int c = 0; c < 2; ++c, ++chunk_it) {
+        const int col = n0 + c * 64;
+        if (col >= p.n) continue;   // uniform: whole 64-column chunk beyond the matrix
+        uint8_t* stage = my_stage + (chunk_it & 1) * pair::kWarpChunkBytes;
+        // the store that last read this staging buffer (two chunks ago) must have finished reading
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        float f[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(v[c][i]);
+        if (p.bias != nullptr) {
+          const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            if (col + i < p.n) {   // n % 8 == 0, so pairs are all-or-nothing
+              const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + i));
+              if constexpr (kBF16) {
+                f[i] += __uint_as_float(w << 16);
+                f[i + 1] += __uint_as_float(w & 0xFFFF0000u);
+              } else {
+                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                f[i] += t.x;
+                f[i + 1] += t.y;
               }
             }
           }
-          if (p.act == BP_ACT_GELU_TANH) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) gelu_tanh_pair(f[i], f[i + 1]);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 w;
-            w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
-            w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
-            w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
-            w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(stage + sw128_offset(r, hsel * 4 + g)) = w;
-          }
         }
-        if (c64 == BN / 64 - 1) {
-          // all columns of this accumulator buffer have been read: hand it back to the leader's MMA warp
-          tc_fence_before();
-          mbar_arrive_leader(&bars.acc_empty[buf]);
+        if (p.act == BP_ACT_GELU_TANH) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) gelu_tanh_pair(f[i], f[i + 1]);
         }
-        if (!outside) {
-          fence_proxy_async_smem();
-          named_bar_sync(1, 256);
-          if (store_leader) {
-            tma_store_2d(&tmO, stage, n0 + c64 * 64, m0);
-            tma_store_commit();
-          }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 w;
+          w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
+          w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
+          w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
+          w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(stage + sw128_offset(lane, g)) = w;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, stage, col, m0);
+          tma_store_commit();
         }
       }
     }
-    if (store_leader) tma_store_wait_read<0>();
+    if (lane == 0) tma_store_wait_read<0>();
   }
   // no CTA of the pair may exit (or free TMEM) while its peer can still read its shared memory / signal it
   tc_fence_before();
@@ -462,6 +468,10 @@ extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* 
     const uint64_t db[2] = {(uint64_t)k, (uint64_t)n}, sb[1] = {(uint64_t)k * 2};
     const uint32_t bb[2] = {gemm::BK, 128};
     if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;
+    // ... and every epilogue warp stores its own 32-row x 64-column chunks
+    const uint64_t dout[2] = {(uint64_t)n, (uint64_t)m}, so[1] = {(uint64_t)n * 2};
+    const uint32_t bo[2] = {64, 32};
+    if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
     auto kern = bf ? gemm::gemm_bias_act_pair_kernel<true> : gemm::gemm_bias_act_pair_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::pair::kSmemBytes);
     if (e != cudaSuccess) {
