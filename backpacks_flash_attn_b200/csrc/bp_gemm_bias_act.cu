@@ -41,6 +41,7 @@ struct Params {
   int32_t n, k;
   int32_t m_tiles, n_tiles, k_blocks;
   int32_t act;
+  int32_t residual_mode;   // pair kernel: the output map is the fp32 residual stream, updated in place (+=)
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -253,6 +254,7 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 struct Barriers {
   uint64_t full[kStages], empty[kStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t res_full[8][2];   // residual mode: [epilogue warp][staging buffer] residual box landed
   uint32_t tmem_base;
 };
 }  // namespace pair
@@ -276,6 +278,7 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < pair::kStages; ++i) mbar_init(&bars.full[i], 1), mbar_init(&bars.empty[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 512);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars.res_full[i][0], 1), mbar_init(&bars.res_full[i][1], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -345,10 +348,25 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* my_stage = smem + pair::offOut + (warp - 4) * 2 * pair::kWarpChunkBytes;
     uint32_t local = 0, chunk_it = 0;
+    uint32_t res_phase[2] = {0, 0};
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
       const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128 + quad * 32;
       const int n0 = static_cast<int>(tile % p.n_tiles) * 256 + hsel * 128;
       const uint32_t buf = local & 1;
+      if (p.residual_mode) {
+        // the first two residual boxes (32 fp32 columns each) travel while the tile's main loop still runs
+        if (lane == 0) {
+          tma_store_wait_read<0>();   // the previous tile's stores have been read out of both staging buffers
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (n0 + b * 32 < p.n) {
+              mbar_arrive_expect_tx(&bars.res_full[warp - 4][b], pair::kWarpChunkBytes);
+              tma_load_2d(my_stage + b * pair::kWarpChunkBytes, &tmO, &bars.res_full[warp - 4][b], n0 + b * 32, m0);
+            }
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(&bars.acc_full[buf], (local >> 1) & 1);
       tc_fence_after();
       // both chunks of this warp leave TMEM first, so the accumulator goes back to the MMA warp early
@@ -361,6 +379,59 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive_leader(&bars.acc_empty[buf]);
+      if (p.residual_mode) {
+        // residual[m0.., col..] += acc + bias, one 32 x 32 fp32 box at a time through the two staging buffers
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = n0 + i * 32;
+          if (col < p.n) {   // uniform
+            const int b = i & 1;
+            uint8_t* stage = my_stage + b * pair::kWarpChunkBytes;
+            mbar_wait(&bars.res_full[warp - 4][b], res_phase[b]);
+            res_phase[b] ^= 1;
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[i >> 1][(i & 1) * 32 + e]);
+            if (p.bias != nullptr) {
+              const uint16_t* bptr = static_cast<const uint16_t*>(p.bias) + col;
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                if (col + e < p.n) {
+                  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(bptr + e));
+                  if constexpr (kBF16) {
+                    f[e] += __uint_as_float(w << 16);
+                    f[e + 1] += __uint_as_float(w & 0xFFFF0000u);
+                  } else {
+                    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                    f[e] += t.x;
+                    f[e + 1] += t.y;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4* cell = reinterpret_cast<float4*>(stage + sw128_offset(lane, g));
+              float4 r = *cell;
+              r.x += f[g * 4 + 0], r.y += f[g * 4 + 1], r.z += f[g * 4 + 2], r.w += f[g * 4 + 3];
+              *cell = r;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO, stage, col, m0);
+              tma_store_commit();
+              if (i + 2 < 4 && col + 64 < p.n) {
+                tma_store_wait_read<0>();   // this buffer is about to be refilled
+                mbar_arrive_expect_tx(&bars.res_full[warp - 4][b], pair::kWarpChunkBytes);
+                tma_load_2d(stage, &tmO, &bars.res_full[warp - 4][b], col + 64, m0);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c, ++chunk_it) {
         const int col = n0 + c * 64;
@@ -421,76 +492,106 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 }  // namespace gemm
 }  // namespace bp
 
-extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void* out, int64_t m,
-                                      int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream) {
-  using namespace bp;
-  if (!x || !w || !out) return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: null pointer argument");
+namespace bp {
+namespace gemm {
+
+// shared by both entry points; out == nullptr selects the residual mode (residual updated in place)
+static int launch_linear(const char* fn, const void* x, const void* w, const void* bias, void* out, float* residual,
+                         int64_t m, int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream) {
+  if (!x || !w || (!out && !residual)) return fail(BP_ERR_INVALID_ARGUMENT, "%s: null pointer argument", fn);
   if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
-    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: only fp16 and bf16 are supported");
-  if (m <= 0 || n <= 0 || k <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: empty input");
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: only fp16 and bf16 are supported", fn);
+  if (m <= 0 || n <= 0 || k <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "%s: empty input", fn);
   if (n % 8 != 0 || k % 8 != 0)
-    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: n and k must be multiples of 8 (got n=%d k=%d)", n, k);
-  if (m > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: m too large");
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: n and k must be multiples of 8 (got n=%d k=%d)", fn, n, k);
+  if (m > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "%s: m too large", fn);
   if (activation != BP_ACT_NONE && activation != BP_ACT_GELU_TANH)
-    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: unknown activation %d", activation);
-  if ((uintptr_t)x % 16 || (uintptr_t)w % 16 || (uintptr_t)out % 16 || (uintptr_t)bias % 4)
-    return fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: pointers must be 16-byte aligned");
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: unknown activation %d", fn, activation);
+  if ((uintptr_t)x % 16 || (uintptr_t)w % 16 || (uintptr_t)out % 16 || (uintptr_t)residual % 16 || (uintptr_t)bias % 4)
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: pointers must be 16-byte aligned", fn);
   CUtensorMap tmA, tmB, tmO;
   {
     const uint64_t da[2] = {(uint64_t)k, (uint64_t)m}, sa[1] = {(uint64_t)k * 2};
-    const uint32_t ba[2] = {gemm::BK, gemm::BM};
+    const uint32_t ba[2] = {BK, BM};
     if (int rc = encode_tensor_map(&tmA, dtype, 2, x, da, sa, ba, true)) return rc;
-    const uint64_t db[2] = {(uint64_t)k, (uint64_t)n};
-    const uint32_t bb[2] = {gemm::BK, gemm::BN};
-    if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sa, bb, true)) return rc;
-    const uint64_t dout[2] = {(uint64_t)n, (uint64_t)m}, so[1] = {(uint64_t)n * 2};
-    const uint32_t bo[2] = {64, gemm::BM};
-    if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
   }
-  gemm::Params p;
+  Params p;
   p.bias = bias;
   p.m = m, p.n = n, p.k = k;
-  p.k_blocks = (k + gemm::BK - 1) / gemm::BK;
+  p.k_blocks = (k + BK - 1) / BK;
   p.act = activation;
-  p.n_tiles = (n + gemm::BN - 1) / gemm::BN;
+  p.residual_mode = residual != nullptr ? 1 : 0;
+  p.n_tiles = (n + BN - 1) / BN;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf = dtype == BP_DTYPE_BF16;
+  const uint64_t db[2] = {(uint64_t)k, (uint64_t)n}, sb[1] = {(uint64_t)k * 2};
+  const uint64_t dout[2] = {(uint64_t)n, (uint64_t)m};
 
   if (m >= 256 && sms >= 2) {
     // CTA-pair kernel: 256 x 256 tiles, one cluster of two CTAs per tile
     p.m_tiles = static_cast<int32_t>((m + 255) / 256);
     const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
     const int clusters = static_cast<int>(tiles < sms / 2 ? tiles : sms / 2);
-    // the W tile map of this variant has a 128-row box (each CTA loads half of the 256-wide tile)
-    const uint64_t db[2] = {(uint64_t)k, (uint64_t)n}, sb[1] = {(uint64_t)k * 2};
-    const uint32_t bb[2] = {gemm::BK, 128};
+    // the W tile map of this variant has a 128-row box (each CTA loads half of the 256-wide tile) ...
+    const uint32_t bb[2] = {BK, 128};
     if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;
-    // ... and every epilogue warp stores its own 32-row x 64-column chunks
-    const uint64_t dout[2] = {(uint64_t)n, (uint64_t)m}, so[1] = {(uint64_t)n * 2};
-    const uint32_t bo[2] = {64, 32};
-    if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
-    auto kern = bf ? gemm::gemm_bias_act_pair_kernel<true> : gemm::gemm_bias_act_pair_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::pair::kSmemBytes);
+    if (residual) {
+      // ... every epilogue warp reads and writes 32 x 32 boxes of the fp32 residual stream ...
+      const uint64_t so[1] = {(uint64_t)n * 4};
+      const uint32_t bo[2] = {32, 32};
+      if (int rc = encode_tensor_map(&tmO, BP_DTYPE_F32, 2, residual, dout, so, bo, true)) return rc;
+    } else {
+      // ... or stores its own 32-row x 64-column chunks of the 16-bit output
+      const uint64_t so[1] = {(uint64_t)n * 2};
+      const uint32_t bo[2] = {64, 32};
+      if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
+    }
+    auto kern = bf ? gemm_bias_act_pair_kernel<true> : gemm_bias_act_pair_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      return fail(BP_ERR_CUDA, "bp_linear_bias_act_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     }
-    kern<<<2 * clusters, gemm::pair::kThreads, gemm::pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
-    return check_launch("bp_linear_bias_act_fwd (pair) launch");
+    kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
+    return check_launch(fn);
   }
+  if (residual) return fail(BP_ERR_UNSUPPORTED, "%s: needs m >= 256 (got %lld)", fn, (long long)m);
 
-  p.m_tiles = static_cast<int32_t>((m + gemm::BM - 1) / gemm::BM);
+  {
+    const uint32_t bb[2] = {BK, BN};
+    if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;
+    const uint64_t so[1] = {(uint64_t)n * 2};
+    const uint32_t bo[2] = {64, BM};
+    if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
+  }
+  p.m_tiles = static_cast<int32_t>((m + BM - 1) / BM);
   const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  auto kern = bf ? gemm::gemm_bias_act_kernel<true> : gemm::gemm_bias_act_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::kSmemBytes);
+  auto kern = bf ? gemm_bias_act_kernel<true> : gemm_bias_act_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    return fail(BP_ERR_CUDA, "bp_linear_bias_act_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
   }
-  kern<<<grid, gemm::kThreads, gemm::kSmemBytes, st>>>(tmA, tmB, tmO, p);
-  return check_launch("bp_linear_bias_act_fwd launch");
+  kern<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, p);
+  return check_launch(fn);
+}
+
+}  // namespace gemm
+}  // namespace bp
+
+extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void* out, int64_t m,
+                                      int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream) {
+  if (!out) return bp::fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: null pointer argument");
+  return bp::gemm::launch_linear("bp_linear_bias_act_fwd", x, w, bias, out, nullptr, m, n, k, activation, dtype, stream);
+}
+
+extern "C" int bp_linear_bias_residual_fwd(const void* x, const void* w, const void* bias, float* residual, int64_t m,
+                                           int32_t n, int32_t k, int32_t dtype, void* stream) {
+  if (!residual) return bp::fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_residual_fwd: null pointer argument");
+  return bp::gemm::launch_linear("bp_linear_bias_residual_fwd", x, w, bias, nullptr, residual, m, n, k, BP_ACT_NONE,
+                                 dtype, stream);
 }

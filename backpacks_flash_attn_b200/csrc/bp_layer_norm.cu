@@ -89,10 +89,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // gamma / beta live in shared memory in their storage type (read back 16 bytes at a time, conflict-free), not
 // in registers: with the row itself (NV x 8 floats) that keeps the kernel under 85 registers, so 24 warps per
 // SM keep enough loads in flight to cover the HBM latency.
-template <typename X, typename R, typename W, int NV>
+template <typename X, typename R, typename W, int NV, typename Z = X>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const W* __restrict__ gamma,
-                       const W* __restrict__ beta, X* __restrict__ z, R* __restrict__ x_out,
+                       const W* __restrict__ beta, Z* __restrict__ z, R* __restrict__ x_out,
                        float* __restrict__ mu_out, float* __restrict__ rs_out, int64_t rows, int cols, float eps) {
   extern __shared__ uint4 ln_smem[];   // [cols] gamma then [cols] beta, in W
   W* s_gamma = reinterpret_cast<W*>(ln_smem);
@@ -178,7 +178,7 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
         t.to(b);
 #pragma unroll
         for (int k = 0; k < 8; ++k) y[k] = g[k] * ((x[i][k] - mu) * rs) + b[k];
-        Vec8<X> o;
+        Vec8<Z> o;
         o.from(y);
         o.store(z + base + v * 8);
       }
@@ -186,7 +186,7 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
   }
 }
 
-template <typename X, typename R, typename W, int NV>
+template <typename X, typename R, typename W, int NV, typename Z = X>
 int launch_nv(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
               float* rs, int64_t rows, int cols, float eps, cudaStream_t st) {
   int dev = 0, sms = 148;
@@ -197,25 +197,25 @@ int launch_nv(const void* x0, const void* x1, const void* gamma, const void* bet
   const int grid = static_cast<int>(ctas_needed < cap ? ctas_needed : cap);
   const size_t smem = 2 * static_cast<size_t>(cols) * sizeof(W);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ln_residual_fwd_kernel<X, R, W, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(ln_residual_fwd_kernel<X, R, W, NV, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       cudaGetLastError();
       return fail(BP_ERR_CUDA, "bp_ln_residual_fwd: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     }
   }
-  ln_residual_fwd_kernel<X, R, W, NV><<<grid, kWarpsPerCta * 32, smem, st>>>(
+  ln_residual_fwd_kernel<X, R, W, NV, Z><<<grid, kWarpsPerCta * 32, smem, st>>>(
       static_cast<const X*>(x0), static_cast<const R*>(x1), static_cast<const W*>(gamma),
-      static_cast<const W*>(beta), static_cast<X*>(z), static_cast<R*>(x_out), mu, rs, rows, cols, eps);
+      static_cast<const W*>(beta), static_cast<Z*>(z), static_cast<R*>(x_out), mu, rs, rows, cols, eps);
   return check_launch("bp_ln_residual_fwd launch");
 }
 
-template <typename X, typename R, typename W>
+template <typename X, typename R, typename W, typename Z = X>
 int launch(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
            float* rs, int64_t rows, int cols, float eps, cudaStream_t st) {
   const int nv = (cols / 8 + 31) / 32;
 #define BP_LN_CASE(N) \
-  if (nv <= N) return launch_nv<X, R, W, N>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, st)
+  if (nv <= N) return launch_nv<X, R, W, N, Z>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, st)
   BP_LN_CASE(1);
   BP_LN_CASE(2);
   BP_LN_CASE(3);
@@ -259,4 +259,28 @@ extern "C" int bp_ln_residual_fwd(const void* x0, const void* x1, const void* ga
 #undef BP_LN_DISPATCH
   return fail(BP_ERR_UNSUPPORTED, "bp_ln_residual_fwd: dtype combination (x0=%d, residual=%d, weight=%d) not built",
               x0_dtype, residual_dtype, weight_dtype);
+}
+
+extern "C" int bp_ln_fwd(const void* x, const void* gamma, const void* beta, void* z, float* mu, float* rsigma,
+                         int64_t rows, int32_t cols, float epsilon, int32_t x_dtype, int32_t z_dtype,
+                         int32_t weight_dtype, void* stream) {
+  using namespace bp;
+  if (!x || !gamma || !beta || !z) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_fwd: null pointer argument");
+  if (rows <= 0 || cols <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_fwd: empty input");
+  if (cols % 8 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_fwd: hidden size must be a multiple of 8 (got %d)", cols);
+  const uintptr_t ptrs[] = {(uintptr_t)x, (uintptr_t)gamma, (uintptr_t)beta, (uintptr_t)z};
+  for (uintptr_t a : ptrs)
+    if (a % 16 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == z_dtype)   // same-type LayerNorm: the residual-add kernel without a residual
+    return bp_ln_residual_fwd(x, nullptr, gamma, beta, z, nullptr, mu, rsigma, rows, cols, epsilon, x_dtype,
+                              x_dtype == BP_DTYPE_F32 ? BP_DTYPE_F32 : x_dtype, weight_dtype, stream);
+  using bf = __nv_bfloat16;
+  using hf = __half;
+  if (x_dtype == BP_DTYPE_F32 && z_dtype == BP_DTYPE_BF16 && weight_dtype == BP_DTYPE_BF16)
+    return ln::launch<float, float, bf, bf>(x, nullptr, gamma, beta, z, nullptr, mu, rsigma, rows, cols, epsilon, st);
+  if (x_dtype == BP_DTYPE_F32 && z_dtype == BP_DTYPE_F16 && weight_dtype == BP_DTYPE_F16)
+    return ln::launch<float, float, hf, hf>(x, nullptr, gamma, beta, z, nullptr, mu, rsigma, rows, cols, epsilon, st);
+  return fail(BP_ERR_UNSUPPORTED, "bp_ln_fwd: dtype combination (x=%d, z=%d, weight=%d) not built", x_dtype, z_dtype,
+              weight_dtype);
 }

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from ..flash_attn_interface import flash_attn_unpadded_qkvpacked_func
 from ..layers.rotary import RotaryEmbedding
-from ..ops.fused_dense import FusedDense
+from ..ops.fused_dense import FusedDense, linear_bias_residual_
 
 
 class FlashSelfAttention(nn.Module):
@@ -111,7 +111,7 @@ class MHA(nn.Module):
         self.out_proj = linear_cls(embed_dim, embed_dim, **factory_kwargs)
 
     def forward(self, x, x_kv=None, key_padding_mask=None, cu_seqlens=None, max_seqlen=None,
-                inference_params=None, **kwargs):
+                inference_params=None, residual_out=None, **kwargs):
         """x: (batch, seqlen, hidden) or, with cu_seqlens / max_seqlen, (total, hidden)."""
         if x_kv is not None or inference_params is not None:
             raise RuntimeError("cross-attention / KV-cache decoding are out of scope for this path")
@@ -129,4 +129,8 @@ class MHA(nn.Module):
         if self.rotary_emb_dim > 0:
             qkv = self.rotary_emb(qkv)
         context = self.inner_attn(qkv, **kw)
-        return self.out_proj(context.reshape(*context.shape[:-2], self.embed_dim))
+        context = context.reshape(*context.shape[:-2], self.embed_dim)
+        if residual_out is not None:
+            # out_proj with the residual add in its epilogue (Block's fused path); returns the residual stream
+            return linear_bias_residual_(context, self.out_proj.weight, self.out_proj.bias, residual_out)
+        return self.out_proj(context)

@@ -43,6 +43,42 @@ def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
     return out.reshape(*x.shape[:-1], n)
 
 
+def linear_bias_residual_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
+                          residual: torch.Tensor) -> torch.Tensor:
+    """residual += x @ weight.T + bias, in place, on the fp32 residual stream (bp_linear_bias_residual_fwd): the
+    out_proj / fc2 GEMM of a pre-norm block with the "add" of dropout_add_layer_norm (block.py:84-88,101-105)
+    in its epilogue.  Returns `residual`."""
+    _lib.require_cuda(x, weight, bias, residual)
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
+        raise RuntimeError("linear_bias_residual_ needs fp16/bf16 activations and weights of the same dtype")
+    if bias is not None and bias.dtype != x.dtype:
+        raise RuntimeError("bias must have the activation dtype")
+    n, k = weight.shape
+    if x.shape[-1] != k or residual.shape[-1] != n or residual.numel() // n != x.numel() // k:
+        raise RuntimeError("shape mismatch between x, weight and residual")
+    if residual.dtype != torch.float32 or not residual.is_contiguous():
+        raise RuntimeError("the residual stream must be a contiguous fp32 tensor")
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or residual.requires_grad):
+        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+    x2 = x.reshape(-1, k)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    weight = weight.contiguous()
+    with torch.cuda.device(x.device):
+        st = _lib.load().bp_linear_bias_residual_fwd(x2.data_ptr(), weight.data_ptr(), _lib.ptr(bias),
+                                                     residual.data_ptr(), x2.shape[0], n, k,
+                                                     _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device))
+    _lib.check(st, "bp_linear_bias_residual_fwd")
+    return residual
+
+
+def can_fuse_residual(x: torch.Tensor, weight: torch.Tensor, residual: torch.Tensor | None) -> bool:
+    """The epilogue-add GEMM needs a CUDA fp32 residual, 16-bit operands and at least one 256-row tile."""
+    return (residual is not None and residual.is_cuda and residual.dtype == torch.float32 and residual.is_contiguous()
+            and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype
+            and x.numel() // x.shape[-1] >= 256 and not torch.is_grad_enabled())
+
+
 def fused_dense_func(x, weight, bias=None, return_residual=False, process_group=None):
     if process_group is not None:
         raise RuntimeError("tensor parallelism is out of scope for this path (batch sharding only)")
@@ -88,6 +124,11 @@ class FusedDenseGeluDense(nn.Module):
         self.heuristic = heuristic
         self.fc1 = nn.Linear(in_features, hidden_features, bias=bias1, **factory_kwargs)
         self.fc2 = nn.Linear(hidden_features, out_features, bias=bias2, **factory_kwargs)
+
+    def forward_into_residual(self, x, residual):
+        """residual += fc2(gelu_tanh(fc1(x))) with the add in the fc2 epilogue; returns residual."""
+        hidden = linear_bias_act(x, self.fc1.weight, self.fc1.bias, "gelu_tanh")
+        return linear_bias_residual_(hidden, self.fc2.weight, self.fc2.bias, residual)
 
     def forward(self, x, process_group=None):
         return fused_dense_gelu_dense_func(x, self.fc1.weight, self.fc2.weight, self.fc1.bias, self.fc2.bias,

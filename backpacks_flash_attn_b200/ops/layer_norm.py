@@ -44,6 +44,27 @@ def _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, want_re
     return z, (x_out.reshape(x0.shape) if need_x else x0)
 
 
+def layer_norm_from_residual(x, weight, bias, epsilon):
+    """z = LayerNorm(x) for an already-summed residual stream x (fp32 in, weight dtype out): bp_ln_fwd.  Used by
+    Block when the branch GEMM has added its output into the residual in its epilogue."""
+    _lib.require_cuda(x, weight, bias)
+    cols = x.shape[-1]
+    if not x.is_contiguous():
+        x = x.contiguous()
+    weight, bias = weight.contiguous(), bias.contiguous()
+    if weight.dtype != bias.dtype or weight.shape != (cols,) or bias.shape != (cols,):
+        raise RuntimeError("gamma and beta must both be (hidden,) with the same dtype")
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (x, weight, bias)):
+        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+    z = torch.empty(x.shape, dtype=weight.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.load().bp_ln_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), z.data_ptr(), None, None,
+                                   x.numel() // cols, cols, float(epsilon), _lib.dtype_code(x.dtype),
+                                   _lib.dtype_code(z.dtype), _lib.dtype_code(weight.dtype), _lib.stream_ptr(x.device))
+    _lib.check(st, "bp_ln_fwd")
+    return z
+
+
 def dropout_add_layer_norm(x0, x1, weight, bias, dropout_p, epsilon, rowscale=None, layerscale=None,
                            prenorm=False, residual_in_fp32=False, return_dropout_mask=False):
     """z = LayerNorm(x0 + x1) (and the fp32/16-bit residual x0 + x1 when prenorm=True).

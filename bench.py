@@ -227,7 +227,8 @@ def run_ours(args):
         per_kernel = {}
         with ClockSampler(physical_gpu_index(local_rank)) as clocks:
             timers = [_lib.KernelTimer(n) for n in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd",
-                                                    "bp_linear_bias_act_fwd", "bp_ln_residual_fwd")]
+                                                    "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd",
+                                                    "bp_ln_residual_fwd", "bp_ln_fwd")]
             for t in timers:
                 t.__enter__()
             parallel.barrier()
@@ -294,9 +295,20 @@ def run_ours(args):
     ln_t = per_kernel["bp_ln_residual_fwd"] * 1e-3
     peak_tf = peaks["tf_sustained"]
     inner = cfg.n_inner or 4 * d
-    gemm_flops = 2.0 * B * S * inner * d                     # every fused GEMM+GELU launch is (B*S, 4d, d)
-    gemm_bytes = (B * S * d + inner * d + B * S * inner) * 2
-    ln_bytes = B * S * d * (2 + 4) * 2                        # x0 bf16 + residual fp32 in, z bf16 + residual fp32 out
+    M = B * S
+    gemm_flops = 2.0 * M * inner * d                          # every fused GEMM+GELU launch is (B*S, 4d, d)
+    gemm_bytes = (M * d + inner * d + M * inner) * 2
+    ln_bytes = M * d * (2 + 4) * 2                            # x0 bf16 + residual fp32 in, z bf16 + residual fp32 out
+    # GEMMs with the residual add in the epilogue: per layer out_proj (d x d) and fc2 (d x 4d), + the content
+    # block's fc2; the mean over the launches of a step is what the live timer measures
+    n_res = per_kernel["bp_linear_bias_residual_fwd:n"]
+    n_fc2 = (n_res + 1) // 2 if n_res else 0
+    n_out = n_res - n_fc2
+    res_flops = (n_out * 2.0 * M * d * d + n_fc2 * 2.0 * M * d * inner) / max(n_res, 1)
+    res_bytes = (n_out * (M * d * 2 + d * d * 2) + n_fc2 * (M * inner * 2 + inner * d * 2)) / max(n_res, 1) + M * d * 8
+    res_t = per_kernel["bp_linear_bias_residual_fwd"] * 1e-3
+    lnf_t = per_kernel["bp_ln_fwd"] * 1e-3
+    lnf_bytes = M * d * (4 + 2)                               # fp32 residual in, bf16 z out
 
     def roof_tensor(flops, t):
         a = flops / t / 1e12
@@ -329,6 +341,20 @@ def run_ours(args):
                               "launches_per_step": per_kernel["bp_ln_residual_fwd:n"], "ms_per_launch": ln_t * 1e3,
                               "algorithmic_mb_per_launch": ln_bytes / 1e6,
                               "traffic": ncu_traffic("ln_residual_fwd_kernel") if (B, S) == (64, 1024) else None}
+    if n_res:
+        k = roof_tensor(res_flops, res_t)
+        k.update({"kernel": "gemm_bias_act_pair_kernel<bf16>, residual epilogue (bp_linear_bias_residual_fwd): out_proj "
+                            "and fc2 with the fp32 residual add in the epilogue",
+                  "launches_per_step": n_res, "ms_per_launch": res_t * 1e3,
+                  "algorithmic_gflop_per_launch": res_flops / 1e9, "algorithmic_mb_per_launch": res_bytes / 1e6,
+                  "hbm_frac": res_bytes / res_t / 1e9 / peaks["hbm_gbs"], "traffic": None})
+        kernels["gemm_bias_residual"] = k
+    if per_kernel["bp_ln_fwd:n"]:
+        a = lnf_bytes / lnf_t / 1e9
+        kernels["ln_from_residual"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": a / peaks["hbm_gbs"], "kernel": "ln_residual_fwd_kernel<float -> bf16> (bp_ln_fwd)",
+                                       "launches_per_step": per_kernel["bp_ln_fwd:n"], "ms_per_launch": lnf_t * 1e3,
+                                       "algorithmic_mb_per_launch": lnf_bytes / 1e6, "traffic": None}
     for v in kernels.values():
         v["ms_per_step"] = v["ms_per_launch"] * v["launches_per_step"]
         v["traffic_unit"] = "DRAM bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)"
@@ -356,8 +382,11 @@ def run_ours(args):
                 "result": "last-position logits (batch, vocab) bf16 copied to pinned host memory every step; the host reads step i while step i+1 runs (two pinned result buffers)"},
         "gpu_launches": launches * world,
         "gpu_launches_per_step_per_gpu": launches / args.steps,
-        "gpu_launches_note": "kernels of libbackpack_b200.so inside the timed region, all ranks (per GPU and step: 28 "
-                             "LayerNorm, 12 attention, 14 GEMM+GELU, 2 sense-mix); library GEMMs / gathers not counted",
+        "gpu_launches_note": "kernels of libbackpack_b200.so inside the timed region, all ranks (per GPU and step: "
+                             + ", ".join(f"{per_kernel[n + ':n']:g} {n}" for n in (
+                                 "bp_fmha_fwd", "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd", "bp_ln_fwd",
+                                 "bp_ln_residual_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd"))
+                             + "); library GEMMs / gathers not counted",
         "roofline": roofline,
         "kernels": kernels,
         "model_mfu": {"achieved_tflops": value / world * model_flops_per_token / 1e12,

@@ -109,6 +109,25 @@ int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void*
                            int64_t m, int32_t n, int32_t k, int32_t activation /* bp_activation_t */,
                            int32_t dtype, void* stream);
 
+/* residual += x W^T + bias, fp32 residual stream updated in place: the out_proj / fc2 GEMM of a pre-norm block
+ * with the "dropout(0) + add" half of dropout_add_ln_fwd (flash_attn/modules/block.py:84-88, 101-105;
+ * csrc/layer_norm/ln_fwd_kernels.cuh:98-131) moved into its epilogue, so the branch output is never written
+ * to HBM in 16 bits and read back.  The fp32 accumulator is added un-rounded (the reference rounds the branch
+ * to bf16/fp16 first), i.e. this is at least as close to exact arithmetic as the reference.
+ *   x (m, k) row-major 16-bit, W (n, k) row-major, bias (n) or NULL, residual (m, n) row-major f32.
+ *   k % 8 == 0, n % 8 == 0, m >= 256.
+ */
+int bp_linear_bias_residual_fwd(const void* x, const void* w, const void* bias, float* residual,
+                                int64_t m, int32_t n, int32_t k, int32_t dtype, void* stream);
+
+/* z = LayerNorm(x): the "LayerNorm" half of dropout_add_ln_fwd on an already-summed residual stream
+ * (x (rows, cols) in x_dtype, typically f32; z in z_dtype, typically the 16-bit activation dtype; gamma / beta
+ * in weight_dtype; mu / rsigma (rows) f32 or NULL).
+ */
+int bp_ln_fwd(const void* x, const void* gamma, const void* beta, void* z, float* mu, float* rsigma,
+              int64_t rows, int32_t cols, float epsilon, int32_t x_dtype, int32_t z_dtype, int32_t weight_dtype,
+              void* stream);
+
 /* In-place rotary embedding on q and k of a packed qkv tensor (replaces apply_rotary as driven by
  * ApplyRotaryEmbQKV_.forward, flash_attn/layers/rotary.py:81-105; csrc/rotary/rotary_cuda.cu:5-41).
  *   qkv (batch, seqlen, 3, nheads, headdim) contiguous; cos/sin (seqlen, rotary_dim/2) in qkv's dtype;

@@ -59,3 +59,64 @@ def test_linear_bias_act_3d_input_and_errors():
     lin = FusedDense(64, 128, device="cuda", dtype=torch.bfloat16)
     with torch.no_grad():
         assert lin(x).shape == (4, 33, 128)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("has_bias", [True, False])
+@pytest.mark.parametrize("m,n,k", [(1024, 768, 768), (4096, 768, 3072), (517, 1024, 256), (256, 40, 64),
+                                    (300, 776, 200), (2048, 1536, 768)])
+def test_linear_bias_residual_inplace(m, n, k, has_bias, dtype):
+    """residual += x W^T + b in the GEMM epilogue (the add of block.py:84-88 moved into out_proj / fc2): compared
+    with fp32 math on the same 16-bit inputs; the fp32 accumulator is added un-rounded, so the error must not
+    exceed that of the reference sequence (round the branch to 16 bits, then add)."""
+    from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_residual_
+    torch.manual_seed(m + n + k)
+    x = torch.randn(m, k, device="cuda").to(dtype)
+    w = (torch.randn(n, k, device="cuda") * k ** -0.5).to(dtype)
+    b = (torch.randn(n, device="cuda") * 0.5).to(dtype) if has_bias else None
+    res0 = torch.randn(m, n, device="cuda") * 3
+    ref = res0 + F.linear(x.float(), w.float(), b.float() if has_bias else None)
+    two_step = res0 + F.linear(x, w, b).float()          # what the reference's un-fused sequence computes
+    res = res0.clone()
+    out = linear_bias_residual_(x, w, b, res)
+    assert out.data_ptr() == res.data_ptr() and out.dtype == torch.float32
+    assert O.max_abs(out, ref) <= O.max_abs(two_step, ref) + 1e-4
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=2e-3)
+
+
+def test_linear_bias_residual_rejects_small_m_and_wrong_types():
+    from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_residual_, can_fuse_residual
+    x = torch.randn(64, 64, device="cuda").bfloat16()
+    w = torch.randn(128, 64, device="cuda").bfloat16()
+    res = torch.zeros(64, 128, device="cuda")
+    assert not can_fuse_residual(x, w, res)               # fewer than 256 rows: Block keeps the two-kernel path
+    with pytest.raises(RuntimeError, match="m >= 256"):
+        with torch.no_grad():
+            linear_bias_residual_(x, w, None, res)
+    with pytest.raises(RuntimeError, match="fp32"):
+        with torch.no_grad():
+            linear_bias_residual_(x, w, None, res.bfloat16())
+
+
+def test_block_fused_residual_path_matches_two_kernel_path():
+    """Block with the add in the GEMM epilogues (default) against the same block with dropout_add_layer_norm."""
+    from functools import partial
+    from backpacks_flash_attn_b200.modules.block import Block
+    from backpacks_flash_attn_b200.modules.mha import MHA
+    from backpacks_flash_attn_b200.ops.fused_dense import FusedDenseGeluDense
+    torch.manual_seed(0)
+    d = 256
+    blk = Block(d, mixer_cls=partial(MHA, num_heads=4, causal=True, fused_bias_fc=True, use_flash_attn=True),
+                mlp_cls=partial(FusedDenseGeluDense, hidden_features=4 * d), fused_dropout_add_ln=True)
+    blk = blk.to("cuda", torch.bfloat16).eval()
+    h = torch.randn(2, 256, d, device="cuda").bfloat16()
+    res = torch.randn(2, 256, d, device="cuda")
+    with torch.inference_mode():
+        blk.fuse_residual_add = "none"
+        h_ref, r_ref = blk(h, res.clone())
+        blk.fuse_residual_add = "all"
+        r_in = res.clone()
+        h_new, r_new = blk(h, r_in)
+    assert r_new.data_ptr() == r_in.data_ptr()           # updated in place
+    assert O.max_abs(r_new, r_ref) < 3e-2 and O.max_abs(h_new, h_ref) < 6e-2
+    assert O.mean_abs(r_new, r_ref) < 2e-3

@@ -80,3 +80,20 @@ def test_rotary_xpos_scale():
     k_ref = O.apply_rotary_ref(orig[:, :, 1].float(), rot._cos_k_cached.float(), rot._sin_k_cached.float())
     assert (out[:, :, 0].float() - q_ref).abs().max() < 2e-2
     assert (out[:, :, 1].float() - k_ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cols", [768, 384, 1024, 8192, 40])
+def test_layer_norm_from_fp32_residual(cols, dtype):
+    """bp_ln_fwd: LayerNorm of the already-summed fp32 residual stream, 16-bit output (Block's fused path)."""
+    from backpacks_flash_attn_b200.ops.layer_norm import layer_norm_from_residual
+    torch.manual_seed(cols)
+    x = torch.randn(777, cols, device="cuda") * 2 + 0.3
+    g = (1 + 0.1 * torch.randn(cols, device="cuda")).to(dtype)
+    b = (0.1 * torch.randn(cols, device="cuda")).to(dtype)
+    with torch.no_grad():
+        z = layer_norm_from_residual(x, g, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x, (cols,), g.float(), b.float(), 1e-5)
+    pt = torch.nn.functional.layer_norm(x.to(dtype), (cols,), g, b, 1e-5)
+    assert z.dtype == dtype and z.shape == x.shape
+    assert (z.float() - ref).abs().max() <= 4 * (pt.float() - ref).abs().max() + 1e-4   # the reference's LN rule
