@@ -8,12 +8,14 @@ name-seeded random weights.
 N > 1 is launched by torchrun (one process per GPU); the batch is sharded with no data-path collective
 (weak scaling: every rank runs B sequences).  Rank 0 prints ONE JSON line:
   value    whole-job tokens/s with the ids resident in HBM (CUDA events, barrier + synchronize on both sides,
-           max over ranks);
+           max over ranks).  The step is replayed as one CUDA graph (utils/graph.py; `--no-graph` launches every
+           kernel from Python instead) -- the same kernels on the same buffers, without the gaps between launches;
   e2e      the same forward through the public API with HOST inputs: per step a pinned-host -> device copy of
            the ids and a device -> host read of the last-position logits (what the reference's generation loop
-           consumes, training/src/utils/generation.py:34-44);
-  roofline the dominant kernel of this library inside the step (the fused attention, 12 launches per step),
-           timed live with CUDA events on the launching stream; `kernels` adds the sense-mix passes;
+           consumes, training/src/utils/generation.py:34-44); the host reads step i while step i+1 runs;
+  roofline the kernel of this library with the largest share of the step, `kernels` all of them: average launch
+           durations from CUDA events recorded on the launching stream around every C-ABI call during an eager
+           pass of the same K steps (events cannot be recorded inside a graph replay), against the measured peaks;
   cpu_baseline  the oracle port of the reference's pure-PyTorch path on the host cores (bounded sample).
 `--impl reference` times that CPU path alone (the reference's CUDA attention cannot run on sm_100, and its
 Python cannot travel to the GPU box).
@@ -185,8 +187,10 @@ def run_ours(args):
     ids_dev = ids_host.to(dev)
     last_host = torch.empty((2, B, cfg.vocab_size), dtype=torch.bfloat16).pin_memory()   # double-buffered results
 
+    graphed = None   # set after warm-up (capture needs inference_mode)
+
     def step_resident():
-        return model(ids_dev).logits
+        return graphed() if graphed is not None else model(ids_dev).logits
 
     copy_stream = torch.cuda.Stream(device=dev)
 
@@ -198,8 +202,10 @@ def run_ours(args):
         checksum = 0.0
         main = torch.cuda.current_stream()
         for i in range(steps):
-            x = ids_host.to(dev, non_blocking=True)
-            logits = model(x).logits
+            if graphed is not None:
+                logits = graphed(ids_host)               # pinned host -> static device input, graph replay
+            else:
+                logits = model(ids_host.to(dev, non_blocking=True)).logits
             last_dev = logits[:, -1].contiguous()
             del logits
             ready = torch.cuda.Event()
@@ -222,15 +228,13 @@ def run_ours(args):
         for _ in range(args.warmup):
             step_resident()
         torch.cuda.synchronize()
+        if args.graph:
+            from backpacks_flash_attn_b200.utils.graph import GraphedForward
+            graphed = GraphedForward(model, ids_dev)
+            for _ in range(args.warmup):
+                step_resident()
         # ---- timed region 1: inputs resident in HBM ----
-        launches0 = _lib.total_launches()
-        per_kernel = {}
         with ClockSampler(physical_gpu_index(local_rank)) as clocks:
-            timers = [_lib.KernelTimer(n) for n in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd",
-                                                    "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd",
-                                                    "bp_ln_residual_fwd", "bp_ln_fwd")]
-            for t in timers:
-                t.__enter__()
             parallel.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -240,14 +244,34 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             parallel.barrier()
-            for t in reversed(timers):
-                t.__exit__(None, None, None)
-            for t in timers:
-                per_kernel[t.name] = t.mean_ms()
-                per_kernel[t.name + ":n"] = len(t.events) / args.steps
-        launches = _lib.total_launches() - launches0
         dt = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
         tokens = parallel.sum_over_ranks(float(B * S * args.steps), dev)
+        # ---- kernel region: the same K steps launched from Python, every kernel of this library bracketed by CUDA
+        #      events on its stream (the per-kernel durations behind `roofline` / `kernels`) ----
+        graph_on, graphed = graphed, None                      # this region launches from Python
+        launches0 = _lib.total_launches()
+        per_kernel = {}
+        timers = [_lib.KernelTimer(n) for n in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd",
+                                                "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd",
+                                                "bp_ln_residual_fwd", "bp_ln_fwd")]
+        for t in timers:
+            t.__enter__()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            step_resident()
+        k1.record()
+        torch.cuda.synchronize()
+        for t in reversed(timers):
+            t.__exit__(None, None, None)
+        for t in timers:
+            per_kernel[t.name] = t.mean_ms()
+            per_kernel[t.name + ":n"] = len(t.events) / args.steps
+        launches = _lib.total_launches() - launches0          # per K steps; a graph replay launches the same kernels
+        dt_eager = parallel.max_over_ranks(k0.elapsed_time(k1) * 1e-3, dev)
+        graphed = graph_on
         # ---- timed region 2: end to end through the public API with host buffers ----
         run_e2e(2)
         parallel.barrier()
@@ -265,6 +289,7 @@ def run_ours(args):
         # ---- secondary variant: sense vectors gathered from a precomputed (vocab, nv, d) table ----
         table_ms = None
         if args.sense_table:
+            graphed = None                                    # the variant runs the eager launch sequence
             model.transformer.build_sense_table()
             for _ in range(2):
                 step_resident()
@@ -375,6 +400,10 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": B * world, "seq_len": S, "d_model": d, "n_layer": cfg.n_layer,
                    "n_head": h, "num_content_vectors": nv, "vocab": cfg.vocab_size, "parallelism": f"dp{world}",
                    "weights": "name-seeded random (SURVEY.md §8c recipe), bf16",
+                   "execution": ("one CUDA graph per step (utils/graph.py); the eager launch sequence of the same "
+                                 f"kernels takes {dt_eager / args.steps * 1e3:.3f} ms per step" if args.graph
+                                 else "eager launches from Python"),
+                   "kernel_timings": "per-kernel CUDA events around an eager pass of the same K steps on the same inputs",
                    "l2": "no flush: each step streams > 10 GB of activations (6.6 GB logits, 1.6 GB sense vectors) "
                          "through a 126 MB L2"},
         "e2e": {"value": tokens / dt_e2e, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * 8 * world,
@@ -410,6 +439,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU")
     ap.add_argument("--seqlen", type=int, default=1024)
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--no-sense-table", dest="sense_table", action="store_false",
                     help="skip the secondary sense-vector-table variant")
     args = ap.parse_args()

@@ -118,3 +118,22 @@ def test_non_default_device():
         a = fused(ids.cuda(0)).logits
         b = fused.to("cuda:1")(ids.to("cuda:1")).logits
     assert torch.equal(a.cpu(), b.cpu())
+
+
+def test_graphed_forward_replays_the_same_kernels():
+    """utils/graph.GraphedForward: the captured CUDA graph reproduces the eager forward bit for bit, for new ids."""
+    from backpacks_flash_attn_b200.models.backpack import BackpackLMHeadModel, flash_config
+    from backpacks_flash_attn_b200.utils.graph import GraphedForward
+    from backpacks_flash_attn_b200.utils.weights import name_seeded_
+    cfg = flash_config(n_embd=128, n_head=2, n_layer=2, n_positions=512)
+    model = name_seeded_(BackpackLMHeadModel(cfg).eval()).to("cuda", torch.bfloat16)
+    g = torch.Generator().manual_seed(7)
+    ids_a = torch.randint(0, 50257, (2, 384), generator=g).cuda()
+    ids_b = torch.randint(0, 50257, (2, 384), generator=g).cuda()
+    with torch.inference_mode():
+        fwd = GraphedForward(model, ids_a)
+        for ids in (ids_a, ids_b, ids_a):
+            out = fwd(ids).clone()
+            assert torch.equal(out, model(ids).logits)
+        with pytest.raises(RuntimeError, match="captured for ids of shape"):
+            fwd(ids_a[:, :128])
