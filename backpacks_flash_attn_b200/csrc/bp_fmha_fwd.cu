@@ -28,8 +28,9 @@
 // Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
 // are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill
 // to a padded width DP of 64 or 128.
-#include <atomic>
 #include <cstddef>
+#include <mutex>
+#include <unordered_map>
 
 #include "bp_common.cuh"
 #include "bp_host.h"
@@ -42,7 +43,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kItemSlots = 4;     // shared-memory ring of decoded work items (producer -> all other roles)
 constexpr int kChunkBH = 148;     // (batch, head) pairs per scheduling chunk
-constexpr int kSchedSlots = 64;   // ticket counters, one per in-flight launch (rotating)
+constexpr int kSchedSlots = 64;   // ticket counter slots, one per CUDA stream
 #ifndef BP_FMHA_STAGGER
 #define BP_FMHA_STAGGER 0
 #endif
@@ -814,18 +815,30 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // Ticket counters of the dynamic scheduler: {tickets drawn, CTAs finished} per slot, zero between launches (the
-// last CTA of a launch re-arms its slot).  Launches rotate over the slots so that kernels in flight on different
-// streams never share one.
+// last CTA of a launch re-arms its slot).  Launches on one stream are serialised, so every stream gets ONE slot
+// (assigned on first use): kernels that may run concurrently -- different streams, or a graph replay next to
+// eager launches -- never share counters.  More than kSchedSlots distinct streams share the last slot.
 __device__ unsigned int g_sched[kSchedSlots * 2];
 
-static unsigned int* next_sched_slot() {
-  static std::atomic<unsigned int> launch_no{0};
+static unsigned int* sched_slot_of(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::unordered_map<cudaStream_t, int> slots;
   void* base = nullptr;
   if (cudaGetSymbolAddress(&base, g_sched) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
-  return static_cast<unsigned int*>(base) + 2 * (launch_no.fetch_add(1) % kSchedSlots);
+  int slot;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = slots.find(stream);
+    if (it == slots.end()) {
+      const int next = static_cast<int>(slots.size());
+      it = slots.emplace(stream, next < kSchedSlots ? next : kSchedSlots - 1).first;
+    }
+    slot = it->second;
+  }
+  return static_cast<unsigned int*>(base) + 2 * slot;
 }
 
 template <int DP, bool kBF16>
@@ -844,7 +857,7 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_items < sms ? p.num_items : sms;
   Params pp = p;
-  pp.sched = next_sched_slot();
+  pp.sched = sched_slot_of(stream);
   if (!pp.sched) return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaGetSymbolAddress(g_sched) failed");
   kern<<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, pp);
   return check_launch("bp_fmha_fwd launch");

@@ -16,6 +16,25 @@ namespace ln {
 
 constexpr int kWarpsPerCta = 8;
 
+#ifndef BP_LN_STREAMING
+#define BP_LN_STREAMING 0
+#endif
+// streaming (evict-first) variants of the 16-byte accesses: the residual stream is touched once per kernel
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+#if BP_LN_STREAMING
+  return __ldcs(reinterpret_cast<const uint4*>(p));
+#else
+  return *reinterpret_cast<const uint4*>(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(void* p, uint4 v) {
+#if BP_LN_STREAMING
+  __stcs(reinterpret_cast<uint4*>(p), v);
+#else
+  *reinterpret_cast<uint4*>(p) = v;
+#endif
+}
+
 template <typename T>
 struct Vec8;  // 8 consecutive elements
 template <>
@@ -28,6 +47,15 @@ struct Vec8<float> {
   __device__ void store(float* p) const {
     *reinterpret_cast<float4*>(p) = a;
     *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ void load_stream(const float* p) {   // global memory only
+    const uint4 u = ld_stream(p), w = ld_stream(p + 4);
+    a = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+    b = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+  }
+  __device__ void store_stream(float* p) const {
+    st_stream(p, make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w)));
+    st_stream(p + 4, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
   }
   __device__ void to(float (&f)[8]) const {
     f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
@@ -42,6 +70,8 @@ struct Vec8<__nv_bfloat16> {
   uint4 u;
   __device__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
   __device__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ void load_stream(const __nv_bfloat16* p) { u = ld_stream(p); }
+  __device__ void store_stream(__nv_bfloat16* p) const { st_stream(p, u); }
   __device__ void to(float (&f)[8]) const {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -62,6 +92,8 @@ struct Vec8<__half> {
   uint4 u;
   __device__ void load(const __half* p) { u = *reinterpret_cast<const uint4*>(p); }
   __device__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ void load_stream(const __half* p) { u = ld_stream(p); }
+  __device__ void store_stream(__half* p) const { st_stream(p, u); }
   __device__ void to(float (&f)[8]) const {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -122,8 +154,8 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
     for (int i = 0; i < NV; ++i) {
       const int v = i * 32 + lane;
       if (v < nvec) {
-        a[i].load(x0 + base + v * 8);
-        if (x1 != nullptr) r[i].load(x1 + base + v * 8);
+        a[i].load_stream(x0 + base + v * 8);
+        if (x1 != nullptr) r[i].load_stream(x1 + base + v * 8);
       }
     }
     float sum = 0.f;
@@ -141,7 +173,7 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
         if (x_out != nullptr) {
           Vec8<R> o;
           o.from(x[i]);
-          o.store(x_out + base + v * 8);
+          o.store_stream(x_out + base + v * 8);
           // the reference normalises the value it stored (ln_fwd_kernels.cuh keeps x in compute type;
           // with a 16-bit residual stream the stored value is the rounded one) -- keep fp32 here.
         }

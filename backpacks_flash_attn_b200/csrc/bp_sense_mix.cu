@@ -34,14 +34,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 // =============================================================================================
 // pass 1: row statistics
 // =============================================================================================
+constexpr int kLseSenses = 4;   // senses per CTA of pass 1 (a CTA per sense spent more time starting up than working)
+
 template <int PK>  // 64-column panels covering dk
 struct LseCfg {
   static constexpr int BN = 128;
   static constexpr int kStages = PK == 3 ? 2 : 4;
+  static constexpr int QB = PK == 1 ? 2 : 1;     // Q buffers across senses
   static constexpr uint32_t kQTileBytes = BM * 128 * PK;
   static constexpr uint32_t kKTileBytes = BN * 128 * PK;
-  static constexpr uint32_t offQ = 0;
-  static constexpr uint32_t offK = offQ + 2 * kQTileBytes;
+  static constexpr uint32_t offQ = 0;                                  // [QB][2 tiles]
+  static constexpr uint32_t offK = offQ + QB * 2 * kQTileBytes;
   static constexpr uint32_t offBar = offK + kStages * kKTileBytes;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
   static constexpr uint32_t kTmemCols = 512;  // S_t[buf] at (t*2+buf)*128
@@ -49,7 +52,7 @@ struct LseCfg {
 };
 
 struct LseBarriers {
-  uint64_t q_full;
+  uint64_t q_full[2], q_empty[2];
   uint64_t k_full[4], k_empty[4];
   uint64_t s_full[2][2], s_free[2][2];
   uint32_t tmem_base;
@@ -61,6 +64,9 @@ struct LseParams {
   float scale, scale_log2;
 };
 
+// One CTA = two 128-row query tiles of one batch element x kLseSenses consecutive senses.  Barrier phases, the K
+// ring and the S buffers run on across senses (cumulative counters), Q is double-buffered when it fits, so the
+// next sense's loads and first S overlap the tail of the current one.
 template <int PK, bool kBF16>
 __global__ void __launch_bounds__(kThreads, 1)
 sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
@@ -71,7 +77,8 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
   LseBarriers& bars = *reinterpret_cast<LseBarriers*>(smem + C::offBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = p.num_pairs - 1 - static_cast<int>(blockIdx.x);
-  const int sense = blockIdx.y, batch = blockIdx.z;
+  const int sense0 = blockIdx.y * kLseSenses, batch = blockIdx.z;
+  const int n_senses = min(kLseSenses, p.nv - sense0);
   const int S = p.seqlen;
   const int row0 = pair * 2 * BM;
   int n_blk[2];
@@ -84,7 +91,7 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQK);
-    mbar_init(&bars.q_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
     for (int t = 0; t < 2; ++t)
       for (int i = 0; i < 2; ++i) mbar_init(&bars.s_full[t][i], 1), mbar_init(&bars.s_free[t][i], 128);
@@ -103,50 +110,63 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
   if (warp < 4) {
     reg_dealloc<56>();
     if (warp == 0) {
-      // ---- producer: Q tiles of both query tiles (coordinate 1 = which*nv + sense), K ring ----
+      // ---- producer: per sense the Q tiles of both query tiles (coordinate 1 = which*nv + sense), K ring ----
       const int n_q_tiles = (row0 + BM < S) ? 2 : 1;
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&bars.q_full, n_q_tiles * C::kQTileBytes);
-        for (int t = 0; t < n_q_tiles; ++t)
-          for (int pn = 0; pn < PK; ++pn)
-            tma_load_3d(smem + C::offQ + t * C::kQTileBytes + pn * (BM * 128), &tmQK, &bars.q_full, pn * 64, sense,
-                        tok0 + row0 + t * BM);
-      }
-      for (int j = 0; j < n_max; ++j) {
-        const int slot = j % C::kStages;
-        if (j >= C::kStages) mbar_wait(&bars.k_empty[slot], ((j / C::kStages) - 1) & 1);
+      int kb = 0;   // K tiles loaded so far (all senses)
+      for (int si = 0; si < n_senses; ++si) {
+        const int sense = sense0 + si;
+        const int qb = si % C::QB;
+        if (si >= C::QB) mbar_wait(&bars.q_empty[qb], ((si / C::QB) - 1) & 1);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKTileBytes);
-          for (int pn = 0; pn < PK; ++pn)
-            tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmQK, &bars.k_full[slot], pn * 64,
-                        p.nv + sense, tok0 + j * BN);
+          mbar_arrive_expect_tx(&bars.q_full[qb], n_q_tiles * C::kQTileBytes);
+          for (int t = 0; t < n_q_tiles; ++t)
+            for (int pn = 0; pn < PK; ++pn)
+              tma_load_3d(smem + C::offQ + (qb * 2 + t) * C::kQTileBytes + pn * (BM * 128), &tmQK, &bars.q_full[qb],
+                          pn * 64, sense, tok0 + row0 + t * BM);
         }
-        __syncwarp();
-      }
-    } else if (warp == 1) {
-      // ---- MMA issuer: S_t(j) into buffer j&1 of tile t ----
-      constexpr uint32_t idesc = make_idesc(kBF16, BM, BN, false, false);
-      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
-      auto last_user = [&](int j) { return j < n_blk[1] ? 1 : 0; };
-      mbar_wait(&bars.q_full, 0);
-      for (int j = 0; j < n_max; ++j) {
-        const int slot = j % C::kStages;
-        mbar_wait(&bars.k_full[slot], (j / C::kStages) & 1);
-        for (int t = 0; t < 2; ++t) {
-          if (j >= n_blk[t]) continue;
-          if (j >= 2) mbar_wait(&bars.s_free[t][j & 1], ((j >> 1) - 1) & 1);
-          tc_fence_after();
+        for (int j = 0; j < n_max; ++j, ++kb) {
+          const int slot = kb % C::kStages;
+          if (kb >= C::kStages) mbar_wait(&bars.k_empty[slot], ((kb / C::kStages) - 1) & 1);
           if (lane == 0) {
-            for (int kk = 0; kk < p.ksteps; ++kk) {
-              const uint32_t a = sQ + t * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-              const uint32_t b = sK + slot * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
-              umma_ss(tmem_base + (t * 2 + (j & 1)) * BN, make_smem_desc_sw128(a, 16, 1024),
-                      make_smem_desc_sw128(b, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-            }
-            if (t == last_user(j)) umma_commit(&bars.k_empty[slot]);
-            umma_commit(&bars.s_full[t][j & 1]);
+            mbar_arrive_expect_tx(&bars.k_full[slot], C::kKTileBytes);
+            for (int pn = 0; pn < PK; ++pn)
+              tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmQK, &bars.k_full[slot], pn * 64,
+                          p.nv + sense, tok0 + j * BN);
           }
           __syncwarp();
+        }
+      }
+    } else if (warp == 1) {
+      // ---- MMA issuer: S_t(j) into buffer (count of S tiles of tile t so far) & 1 ----
+      constexpr uint32_t idesc = make_idesc(kBF16, BM, BN, false, false);
+      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
+      int kb = 0;
+      int sc[2] = {0, 0};   // S tiles issued per query tile (all senses)
+      for (int si = 0; si < n_senses; ++si) {
+        const int qb = si % C::QB;
+        mbar_wait(&bars.q_full[qb], (si / C::QB) & 1);
+        for (int j = 0; j < n_max; ++j, ++kb) {
+          const int slot = kb % C::kStages;
+          mbar_wait(&bars.k_full[slot], (kb / C::kStages) & 1);
+          const int last_user = j < n_blk[1] ? 1 : 0;
+          for (int t = 0; t < 2; ++t) {
+            if (j >= n_blk[t]) continue;
+            const int c = sc[t]++;
+            if (c >= 2) mbar_wait(&bars.s_free[t][c & 1], ((c >> 1) - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              for (int kk = 0; kk < p.ksteps; ++kk) {
+                const uint32_t a = sQ + (qb * 2 + t) * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+                const uint32_t b = sK + slot * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
+                umma_ss(tmem_base + (t * 2 + (c & 1)) * BN, make_smem_desc_sw128(a, 16, 1024),
+                        make_smem_desc_sw128(b, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+              }
+              if (t == last_user) umma_commit(&bars.k_empty[slot]);
+              if (j == n_max - 1 && t == last_user) umma_commit(&bars.q_empty[qb]);   // last S of this sense
+              umma_commit(&bars.s_full[t][c & 1]);
+            }
+            __syncwarp();
+          }
         }
       }
     }
@@ -159,41 +179,44 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
       const int qrow = row0 + t * BM + r;
       const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
       const float c2 = p.scale_log2;
-      float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < n; ++j) {
-        mbar_wait(&bars.s_full[t][j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        float s[BN];
-        const uint32_t tS = tmem_base + lane_addr + (t * 2 + (j & 1)) * BN;
+      int c = 0;   // S tiles consumed (all senses)
+      for (int si = 0; si < n_senses; ++si) {
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < n; ++j, ++c) {
+          mbar_wait(&bars.s_full[t][c & 1], (c >> 1) & 1);
+          tc_fence_after();
+          float s[BN];
+          const uint32_t tS = tmem_base + lane_addr + (t * 2 + (c & 1)) * BN;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t u[32];
-          tmem_ld32(tS + c * 32, u);
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t u[32];
+            tmem_ld32(tS + cc * 32, u);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(u[i]);
+            for (int i = 0; i < 32; ++i) s[cc * 32 + i] = __uint_as_float(u[i]);
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&bars.s_free[t][c & 1]);
+          const int col0 = j * BN;
+          if (col0 + BN - 1 > row0 + t * BM) {  // block touches the diagonal (also covers cols >= seqlen)
+#pragma unroll
+            for (int cc = 0; cc < BN; ++cc)
+              if (col0 + cc > qrow) s[cc] = -INFINITY;
+          }
+          float mx = s[0];
+#pragma unroll
+          for (int cc = 1; cc < BN; ++cc) mx = fmaxf(mx, s[cc]);
+          const float m_new = fmaxf(m, mx);  // column 0 is always visible, so m_new is finite
+          const float neg = -m_new * c2;
+          float sum = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < BN; ++cc) sum += fast_exp2(fmaf(s[cc], c2, neg));
+          l = l * fast_exp2((m - m_new) * c2) + sum;
+          m = m_new;
         }
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&bars.s_free[t][j & 1]);
-        const int col0 = j * BN;
-        if (col0 + BN - 1 > row0 + t * BM) {  // block touches the diagonal (also covers cols >= seqlen)
-#pragma unroll
-          for (int c = 0; c < BN; ++c)
-            if (col0 + c > qrow) s[c] = -INFINITY;
-        }
-        float mx = s[0];
-#pragma unroll
-        for (int c = 1; c < BN; ++c) mx = fmaxf(mx, s[c]);
-        const float m_new = fmaxf(m, mx);  // column 0 is always visible, so m_new is finite
-        const float neg = -m_new * c2;
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < BN; ++c) sum += fast_exp2(fmaf(s[c], c2, neg));
-        l = l * fast_exp2((m - m_new) * c2) + sum;
-        m = m_new;
+        if (qrow < S)
+          p.lse[(static_cast<int64_t>(batch) * p.nv + sense0 + si) * S + qrow] = m * p.scale + logf(l);
       }
-      if (qrow < S)
-        p.lse[(static_cast<int64_t>(batch) * p.nv + sense) * S + qrow] = m * p.scale + logf(l);
     }
   }
   tc_fence_before();
@@ -567,7 +590,7 @@ static int launch_lse(const CUtensorMap& tm, const LseParams& p, int batch, cuda
     cudaGetLastError();
     return fail(BP_ERR_CUDA, "bp_sense_lse_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  kern<<<dim3(p.num_pairs, p.nv, batch), kThreads, C::kSmemBytes, st>>>(tm, p);
+  kern<<<dim3(p.num_pairs, (p.nv + kLseSenses - 1) / kLseSenses, batch), kThreads, C::kSmemBytes, st>>>(tm, p);
   return check_launch("bp_sense_lse_fwd launch");
 }
 

@@ -151,3 +151,28 @@ def test_fmha_rejects_bad_arguments():
     bad = torch.zeros(64, 3, 2, 36, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="multiple of 8"):
         F.flash_attn_unpadded_qkvpacked_func(bad, cu, 64, 0.0)
+
+
+@pytest.mark.parametrize("b,h,s", [(149, 1, 256), (37, 8, 384), (3, 99, 130)])
+def test_fmha_scheduler_chunk_boundaries(b, h, s):
+    """More (batch, head) pairs than one scheduling chunk (148), a ragged last chunk, odd tile counts: every work
+    item must be handed out exactly once by the ticket scheduler."""
+    qkv = _make_qkv(b, s, h, 64, torch.bfloat16, seed=b * 7 + h)
+    _check(qkv, True)
+
+
+def test_fmha_concurrent_streams_do_not_share_scheduler_state():
+    F = _ops()
+    qkv = _make_qkv(8, 1024, 12, 64, torch.bfloat16, seed=11)
+    cu = torch.arange(0, 9 * 1024, 1024, dtype=torch.int32, device="cuda")
+    ref = F.flash_attn_unpadded_qkvpacked_func(qkv.reshape(-1, 3, 12, 64), cu, 1024, 0.0, causal=True)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(4):
+        for st in streams:
+            with torch.cuda.stream(st):
+                outs.append(F.flash_attn_unpadded_qkvpacked_func(qkv.reshape(-1, 3, 12, 64), cu, 1024, 0.0, causal=True))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, ref)
