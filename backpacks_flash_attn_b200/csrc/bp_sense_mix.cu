@@ -61,6 +61,7 @@ struct LseBarriers {
 struct LseParams {
   float* lse;  // (b, nv, s)
   int32_t seqlen, nv, dk, ksteps, num_pairs;
+  int32_t senses_per_cta;   // <= kLseSenses; fewer when the grid would not fill the GPU
   float scale, scale_log2;
 };
 
@@ -77,8 +78,8 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
   LseBarriers& bars = *reinterpret_cast<LseBarriers*>(smem + C::offBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = p.num_pairs - 1 - static_cast<int>(blockIdx.x);
-  const int sense0 = blockIdx.y * kLseSenses, batch = blockIdx.z;
-  const int n_senses = min(kLseSenses, p.nv - sense0);
+  const int sense0 = blockIdx.y * p.senses_per_cta, batch = blockIdx.z;
+  const int n_senses = min(p.senses_per_cta, p.nv - sense0);
   const int S = p.seqlen;
   const int row0 = pair * 2 * BM;
   int n_blk[2];
@@ -262,10 +263,14 @@ struct MixCfg {
 // query tiles that need it (measured: 4.2 GB per launch against 1.9 GB algorithmic).  Group-outermost, all query
 // tiles of a batch element need the same 256-key slab (6 MB) at the same time, which stays in L2; Q_l is
 // reloaded once per (group, sense) instead of once per sense (4 KB per step on average).
+// Wide sense keys (dk > 64: few senses, single-buffered Q) keep the sense outermost (group = all blocks): their
+// per-batch-element footprint is small and a Q reload every few steps would stall the pipeline (measured at k = 4:
+// 165 -> 229 us with groups of 4).
 constexpr int kGroup = 4;
 struct StepIter {
-  int nj, nv, g0, gsz, l, jj;
-  __device__ __forceinline__ StepIter(int nj_, int nv_) : nj(nj_), nv(nv_), g0(0), gsz(min(kGroup, nj_)), l(0), jj(0) {}
+  int nj, nv, grp, g0, gsz, l, jj;
+  __device__ __forceinline__ StepIter(int nj_, int nv_, int grp_)
+      : nj(nj_), nv(nv_), grp(grp_), g0(0), gsz(min(grp_, nj_)), l(0), jj(0) {}
   __device__ __forceinline__ int sense() const { return l; }
   __device__ __forceinline__ int j() const { return g0 + jj; }
   __device__ __forceinline__ bool first_of_visit() const { return jj == 0; }        // first block of this (group, sense)
@@ -276,7 +281,7 @@ struct StepIter {
       if (++l == nv) {
         l = 0;
         g0 += gsz;
-        gsz = min(kGroup, nj - g0);
+        gsz = min(grp, nj - g0);
       }
     }
   }
@@ -296,6 +301,7 @@ struct MixParams {
   void* out;         // (b, s, d)
   int32_t seqlen, nv, dk, ksteps, d, num_qtiles, num_chunks;
   int32_t c_sense_inner;  // content tensor-map dims are (d, nv, s, b) instead of (d, s, nv, b)
+  int32_t group;          // key blocks per group of the step order (StepIter)
   float scale_log2;
   uint64_t* trace;        // debug timeline (BP_TRACE builds), else null
 };
@@ -349,7 +355,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (warp == 0) {
       // ---- producer A: content tiles C_l[j] : (ncols/64) panels of [64 keys x 64 columns] ----
       Tracer tr(p.trace, 0, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
-      StepIter it(nj, p.nv);
+      StepIter it(nj, p.nv, p.group);
       for (int n = 0; n < n_steps; ++n, it.next()) {
         const int slot = n % C::CS;
         tr.rec(0, n);
@@ -370,7 +376,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     } else if (warp == 3) {
       // ---- producer B: Q_l (once per sense) and K_l[j] ----
-      StepIter it(nj, p.nv);
+      StepIter it(nj, p.nv, p.group);
       int qv = 0;   // (group, sense) visits so far: Q buffer = qv % QS
       for (int n = 0; n < n_steps; ++n, it.next()) {
         const int sense = it.sense(), j = it.j();
@@ -400,7 +406,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
       const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
       Tracer tr(p.trace, 4, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
-      StepIter it(nj, p.nv);
+      StepIter it(nj, p.nv, p.group);
       int qv = 0;
       for (int n = 0; n < n_steps; ++n, it.next()) {
         const int qs = qv % C::QS, ks = n & 1;
@@ -479,7 +485,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int i = 0;
     Tracer tr(p.trace, 2 + w, blockIdx.x == 0 && blockIdx.y == 0 && r == 0);
     if (w == 1) mbar_arrive(&bars.s_go[0]);   // "S(-1) drained": lets S(0) go as soon as K(0) has landed
-    StepIter it(nj, p.nv);
+    StepIter it(nj, p.nv, p.group);
     if (w == 1 && n_steps > 1) it.next();
     for (int n = w; n < n_steps; n += 2, ++i) {
       const int sense = it.sense(), j = it.j();
@@ -590,7 +596,16 @@ static int launch_lse(const CUtensorMap& tm, const LseParams& p, int batch, cuda
     cudaGetLastError();
     return fail(BP_ERR_CUDA, "bp_sense_lse_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  kern<<<dim3(p.num_pairs, (p.nv + kLseSenses - 1) / kLseSenses, batch), kThreads, C::kSmemBytes, st>>>(tm, p);
+  // several senses per CTA amortise the start-up cost, as long as the grid still covers the GPU a few times over
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  LseParams pp = p;
+  pp.senses_per_cta = kLseSenses;
+  while (pp.senses_per_cta > 1 &&
+         static_cast<int64_t>(p.num_pairs) * ((p.nv + pp.senses_per_cta - 1) / pp.senses_per_cta) * batch < 4 * sms)
+    pp.senses_per_cta >>= 1;
+  kern<<<dim3(p.num_pairs, (p.nv + pp.senses_per_cta - 1) / pp.senses_per_cta, batch), kThreads, C::kSmemBytes, st>>>(tm, pp);
   return check_launch("bp_sense_lse_fwd launch");
 }
 
@@ -674,6 +689,7 @@ extern "C" int bp_sense_mix_fwd(const void* qk, const void* content, const float
   p.scale_log2 = softmax_scale * sense::kLog2e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int pk = (dk + 63) / 64;
+  p.group = pk == 1 ? sense::kGroup : 1 << 20;
   const bool bf = dtype == BP_DTYPE_BF16;
   switch (pk) {
     case 1: return bf ? sense::launch_mix<1, true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix<1, false>(tmQ, tmK, tmC, p, batch, st);

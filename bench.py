@@ -358,7 +358,7 @@ def run_ours(args):
     k.update({"kernel": "gemm_bias_act_kernel<bf16> (bp_linear_bias_act_fwd), fc1 + bias + tanh-GELU",
               "launches_per_step": per_kernel["bp_linear_bias_act_fwd:n"], "ms_per_launch": gemm_t * 1e3,
               "algorithmic_gflop_per_launch": gemm_flops / 1e9, "algorithmic_mb_per_launch": gemm_bytes / 1e6,
-              "traffic": ncu_traffic("gemm_bias_act_kernel") if (B, S) == (64, 1024) else None})
+              "traffic": ncu_traffic("gemm_bias_act_pair_kernel") if (B, S) == (64, 1024) else None})
     kernels["gemm_bias_gelu"] = k
     a = ln_bytes / ln_t / 1e9
     kernels["ln_residual"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -401,7 +401,7 @@ def run_ours(args):
                    "n_head": h, "num_content_vectors": nv, "vocab": cfg.vocab_size, "parallelism": f"dp{world}",
                    "weights": "name-seeded random (SURVEY.md §8c recipe), bf16",
                    "execution": ("one CUDA graph per step (utils/graph.py); the eager launch sequence of the same "
-                                 f"kernels takes {dt_eager / args.steps * 1e3:.3f} ms per step" if args.graph
+                                 f"kernels, with an event pair recorded around each of them, takes {dt_eager / args.steps * 1e3:.3f} ms per step" if args.graph
                                  else "eager launches from Python"),
                    "kernel_timings": "per-kernel CUDA events around an eager pass of the same K steps on the same inputs",
                    "l2": "no flush: each step streams > 10 GB of activations (6.6 GB logits, 1.6 GB sense vectors) "

@@ -29,8 +29,11 @@ def main(path, steps):
         tot[k] += v
         cnt[k] += 1
     total = sum(tot.values())
+    fm = [k for k in cnt if "fmha_fwd_kernel" in k]
+    if fm:   # 12 attention launches per forward pass: count the passes instead of trusting the argument
+        steps = max(1, round(sum(cnt[k] for k in fm) / 12))
     print(f"ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-sense-table` "
-          f"({steps} forward passes captured; per-launch times are cold-cache and serialised: compare SHARES)")
+          f"({steps} forward passes captured, eager and graph-replayed; per-launch times are cold-cache and serialised: compare SHARES)")
     ours = 0.0
     for k in sorted(tot, key=lambda k: -tot[k])[:14]:
         mark = "*" if any(o in k for o in OURS) else " "
