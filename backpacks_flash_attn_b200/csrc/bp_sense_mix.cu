@@ -21,12 +21,17 @@
 // TMA producer arms for the operand tile also counts the 128 softmax threads that hand over S / P
 // ("s_go" = K tile landed + S buffer drained, "pv_go" = C tile landed + P stored).
 // C_l(x_j) tiles are consumed as MN-major B operands exactly as TMA wrote them (no transpose).
+#include <stdlib.h>
+
 #include "bp_common.cuh"
 #include "bp_host.h"
 
 namespace bp {
 namespace sense {
 
+#ifndef BP_SENSE_DC
+#define BP_SENSE_DC 384
+#endif
 constexpr int BM = 128;
 constexpr int kThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -231,10 +236,17 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
 template <int PK>
 struct MixCfg {
   static constexpr int BN = 64;    // keys per step
-  static constexpr int DC = 384;   // output columns per CTA (TMEM: 384 for O + 2 x 64 for S)
+  // Output columns per CTA.  The fp32 accumulator of a 128-row tile at d = 768 (384 KB) exceeds TMEM, so a CTA owns
+  // a column chunk and recomputes S (and the exponentials) for it.  384 columns (2 chunks) leave room for ONE S
+  // buffer only; ncu shows the tensor pipe 60 % active: S(n+1) queues behind the 768-cycle PV(n-1) in the in-order
+  // pipe and the softmax of a step (~1000 cycles of latency) is longer than one PV.  256 columns (-DBP_SENSE_DC=256:
+  // 3 chunks, TWO S buffers, S two steps ahead of PV) was measured SLOWER (1.21 vs 0.99 ms): every chunk repeats
+  // the exponentials, and with a 512-cycle PV per step the MUFU pipe becomes the bound.
+  static constexpr int DC = BP_SENSE_DC;
+  static constexpr int SB = (DC + 2 * BN + 2 * (BN / 2) <= 512) ? 2 : 1;   // S buffers
   static constexpr int QS = PK == 1 ? 2 : 1;
   static constexpr int KS = 2;
-  static constexpr int CS = PK == 1 ? 3 : 2;
+  static constexpr int CS = PK == 1 ? (DC <= 256 ? 4 : 3) : 2;
   static constexpr uint32_t kQTileBytes = BM * 128 * PK;
   static constexpr uint32_t kKTileBytes = BN * 128 * PK;
   static constexpr uint32_t kCPanelBytes = BN * 128;           // 64 keys x 64 columns
@@ -248,7 +260,7 @@ struct MixCfg {
   // two P buffers: P (bf16/f16, two values per 32-bit column) is the A operand of the PV product and is
   // read by the tensor core straight from TMEM -- it never touches shared memory, whose bandwidth is
   // what bounds this kernel (every K-step already streams a 64 x 384 slice of C through it).
-  static constexpr uint32_t colO = 0, colS = DC, colP = DC + BN;
+  static constexpr uint32_t colO = 0, colS = DC, colP = DC + SB * BN;
   static constexpr uint32_t kTmemCols = 512;
   static_assert(colP + 2 * (BN / 2) <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -266,7 +278,10 @@ struct MixCfg {
 // Wide sense keys (dk > 64: few senses, single-buffered Q) keep the sense outermost (group = all blocks): their
 // per-batch-element footprint is small and a Q reload every few steps would stall the pipeline (measured at k = 4:
 // 165 -> 229 us with groups of 4).
-constexpr int kGroup = 4;
+#ifndef BP_SENSE_GROUP
+#define BP_SENSE_GROUP 4
+#endif
+constexpr int kGroup = BP_SENSE_GROUP;
 struct StepIter {
   int nj, nv, grp, g0, gsz, l, jj;
   __device__ __forceinline__ StepIter(int nj_, int nv_, int grp_)
@@ -290,7 +305,7 @@ struct StepIter {
 struct MixBarriers {
   uint64_t q_full[2], q_empty[2];
   uint64_t s_go[2], k_empty[2];    // s_go[n & 1]: K(n) landed (tx) + S(n-1) drained by its 128 softmax threads
-  uint64_t pv_go[3], c_empty[3];   // pv_go[n % CS]: C(n) landed (tx) + P(n) stored by its 128 softmax threads
+  uint64_t pv_go[4], c_empty[4];   // pv_go[n % CS]: C(n) landed (tx) + P(n) stored by its 128 softmax threads
   uint64_t s_full[2], p_free[2];   // s_full[n & 1]: each warpgroup must see every phase
   uint64_t o_full;
   uint32_t tmem_base;
@@ -336,7 +351,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&bars.s_go[i], 129), mbar_init(&bars.k_empty[i], 1);
       mbar_init(&bars.s_full[i], 1), mbar_init(&bars.p_free[i], 1);
     }
-    for (int i = 0; i < 3; ++i) mbar_init(&bars.pv_go[i], 129), mbar_init(&bars.c_empty[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars.pv_go[i], 129), mbar_init(&bars.c_empty[i], 1);
     mbar_init(&bars.o_full, 1);
     fence_barrier_init();
   }
@@ -419,8 +434,8 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int kk = 0; kk < p.ksteps; ++kk) {
             const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
             const uint32_t b = sK + ks * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
-            umma_ss(tmem_base + C::colS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024),
-                    idesc_s, kk > 0 ? 1u : 0u);
+            umma_ss(tmem_base + C::colS + (C::SB == 2 ? (n & 1) * BN : 0), make_smem_desc_sw128(a, 16, 1024),
+                    make_smem_desc_sw128(b, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
           }
           umma_commit(&bars.k_empty[ks]);
           if (it.last_of_visit()) umma_commit(&bars.q_empty[qs]);
@@ -472,7 +487,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int qrow = row0 + r;
     const bool valid = qrow < S;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + C::colS;
+    const uint32_t tS = tmem_base + lane_addr + C::colS + (C::SB == 2 ? w * BN : 0);
     const uint32_t tP = tmem_base + lane_addr + C::colP + w * (BN / 2);
     const float c2 = p.scale_log2;
     const float* lse_row = p.lse + static_cast<int64_t>(batch) * p.nv * S + (valid ? qrow : S - 1);
@@ -484,7 +499,9 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int next_id = 0;   // sense whose statistic lse_next holds
     int i = 0;
     Tracer tr(p.trace, 2 + w, blockIdx.x == 0 && blockIdx.y == 0 && r == 0);
-    if (w == 1) mbar_arrive(&bars.s_go[0]);   // "S(-1) drained": lets S(0) go as soon as K(0) has landed
+    // "S buffer free": with two S buffers each warpgroup owns one (S(n) needs S(n-2) drained); with one buffer
+    // S(0) only needs "S(-1) drained" from the warpgroup of the odd steps
+    if (C::SB == 2 || w == 1) mbar_arrive(&bars.s_go[C::SB == 2 ? w : 0]);
     StepIter it(nj, p.nv, p.group);
     if (w == 1 && n_steps > 1) it.next();
     for (int n = w; n < n_steps; n += 2, ++i) {
@@ -511,7 +528,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bars.s_go[(n + 1) & 1]);   // S(n+1) may be computed while this step's exponentials run
+      mbar_arrive(&bars.s_go[C::SB == 2 ? (n & 1) : ((n + 1) & 1)]);   // the S buffer is free again
       tr.rec(2, n);
       const int col0 = j * BN;
       if (col0 + BN - 1 > row0) {
@@ -562,6 +579,290 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 3) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// =============================================================================================
+// pass 2 on CTA pairs (cta_group::2): the default when dk <= 64 and d is a multiple of 384.
+//
+// The 1-CTA kernel above is bound by shared-memory bandwidth: every 64-key step streams a 48 KB C tile into shared
+// memory and out again into the tensor core (~148 KB of traffic per 864 MMA cycles against 128 B/clk).  Here two
+// CTAs of a cluster take two consecutive query tiles of the same (batch, column chunk) and every MMA is 256 rows
+// across the two SMs: each CTA keeps its own Q tile, S, P and O (128 rows) but only HALF of the K tile (32 keys)
+// and half of the C tile (192 of the 384 columns), so fill + operand reads drop to ~76 KB per step.  Only the
+// leader CTA (cluster rank 0) issues MMAs; both CTAs' TMA loads credit the leader's barriers, both CTAs' softmax
+// threads arrive on them, and `tcgen05.commit ... multicast::cluster` releases buffers in both CTAs.  The lighter
+// query tile of a pair computes (fully masked, P = 0) the two key blocks only its sibling needs: 11 % more MMA
+// work at seq 1024.
+// =============================================================================================
+struct PairCfg {
+  static constexpr int BN = 64;
+  static constexpr int DC = 384;
+  static constexpr int QS = 2, KS = 2, CS = 4;
+  static constexpr uint32_t kQTileBytes = BM * 128;            // own 128 rows x 64 (padded dk)
+  static constexpr uint32_t kKHalfBytes = (BN / 2) * 128;      // 32 keys
+  static constexpr uint32_t kCPanelBytes = BN * 128;           // 64 keys x 64 columns
+  static constexpr uint32_t kCHalfBytes = 3 * kCPanelBytes;    // this CTA's 192 columns
+  static constexpr uint32_t offQ = 0;
+  static constexpr uint32_t offK = offQ + QS * kQTileBytes;
+  static constexpr uint32_t offC = offK + KS * 8192;           // (slots kept 1024-aligned)
+  static constexpr uint32_t offBar = offC + CS * kCHalfBytes;
+  static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+  static constexpr uint32_t colO = 0, colS = DC, colP = DC + BN;
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct PairBarriers {
+  uint64_t q_full[2], q_empty[2];
+  uint64_t s_go[2], k_empty[2];
+  uint64_t pv_go[4], c_empty[4];
+  uint64_t s_full[2], p_free[2];
+  uint64_t o_full;
+  uint32_t tmem_base;
+};
+
+template <bool kBF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+sense_mix_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmC, const MixParams p) {
+  using C = PairCfg;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PairBarriers& bars = *reinterpret_cast<PairBarriers*>(smem + C::offBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = rank == 0;
+  const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
+  const int num_qpairs = (p.num_qtiles + 1) / 2;
+  const int qpair = num_qpairs - 1 - cluster_id / p.num_chunks;  // heaviest first
+  const int chunk = cluster_id % p.num_chunks;
+  const int batch = blockIdx.y;
+  const int S = p.seqlen;
+  const int row0 = (qpair * 2 + rank) * BM;                      // this CTA's query tile
+  const int nj = (min(S, qpair * 2 * BM + 2 * BM) + BN - 1) / BN;  // causal key blocks of the PAIR
+  const int n_steps = p.nv * nj;
+  const int col_base = chunk * C::DC;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
+      mbar_init(&bars.s_go[i], 9), mbar_init(&bars.k_empty[i], 1);       // producer + one lane of 4 softmax warps x 2 CTAs
+      mbar_init(&bars.s_full[i], 1), mbar_init(&bars.p_free[i], 1);
+    }
+    for (int i = 0; i < C::CS; ++i) mbar_init(&bars.pv_go[i], 9), mbar_init(&bars.c_empty[i], 1);
+    mbar_init(&bars.o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 3) {
+    tmem_alloc_2cta(&bars.tmem_base, C::kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of BOTH CTAs are initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+  const int tok0 = batch * S;
+
+  if (warp < 4) {
+    reg_dealloc<56>();
+    if (warp == 0) {
+      // ---- producer A (both CTAs): this CTA's three 64-column panels of C_l[j]; bytes credited to the leader ----
+      StepIter it(nj, p.nv, p.group);
+      for (int n = 0; n < n_steps; ++n, it.next()) {
+        const int slot = n % C::CS;
+        if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
+        if (lane == 0) {
+          const int sense = it.sense(), j = it.j();
+          if (leader) mbar_arrive_expect_tx(&bars.pv_go[slot], 2 * C::kCHalfBytes);
+          for (int pn = 0; pn < 3; ++pn) {
+            // panels 0,1 = this CTA's half of columns [0,256); panel 2 = its half of columns [256,384)
+            const int col = col_base + (pn < 2 ? rank * 128 + pn * 64 : 256 + rank * 64);
+            uint8_t* dst = smem + C::offC + slot * C::kCHalfBytes + pn * C::kCPanelBytes;
+            if (p.c_sense_inner)
+              tma_load_4d_pair(dst, &tmC, &bars.pv_go[slot], col, sense, j * BN, batch);
+            else
+              tma_load_4d_pair(dst, &tmC, &bars.pv_go[slot], col, j * BN, sense, batch);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 3) {
+      // ---- producer B (both CTAs): own Q_l tile (once per visit) and own half (32 keys) of K_l[j] ----
+      StepIter it(nj, p.nv, p.group);
+      int qv = 0;
+      for (int n = 0; n < n_steps; ++n, it.next()) {
+        const int sense = it.sense(), j = it.j();
+        if (it.first_of_visit()) {
+          const int qs = qv % C::QS;
+          if (qv >= C::QS) mbar_wait(&bars.q_empty[qs], ((qv / C::QS) - 1) & 1);
+          ++qv;
+          if (lane == 0) {
+            if (leader) mbar_arrive_expect_tx(&bars.q_full[qs], 2 * C::kQTileBytes);
+            tma_load_3d_pair(smem + C::offQ + qs * C::kQTileBytes, &tmQ, &bars.q_full[qs], 0, sense, tok0 + row0);
+          }
+        }
+        const int slot = n % C::KS;
+        if (n >= C::KS) mbar_wait(&bars.k_empty[slot], ((n / C::KS) - 1) & 1);
+        if (lane == 0) {
+          if (leader) mbar_arrive_expect_tx(&bars.s_go[slot], 2 * C::kKHalfBytes);
+          tma_load_3d_pair(smem + C::offK + slot * 8192, &tmK, &bars.s_go[slot], 0, p.nv + sense,
+                           tok0 + j * BN + rank * (BN / 2));
+        }
+        __syncwarp();
+      }
+    } else if (warp == 2 && leader) {
+      // ---- issuer of S(n) = Q_l K_l[j]^T for both CTAs (M = 256, N = 64) ----
+      constexpr uint32_t idesc_s = make_idesc(kBF16, 256, BN, false, false);
+      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
+      StepIter it(nj, p.nv, p.group);
+      int qv = 0;
+      for (int n = 0; n < n_steps; ++n, it.next()) {
+        const int qs = qv % C::QS, ks = n & 1;
+        if (it.first_of_visit()) mbar_wait(&bars.q_full[qs], (qv / C::QS) & 1);
+        mbar_wait(&bars.s_go[ks], (n >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int kk = 0; kk < p.ksteps; ++kk) {
+            const uint32_t a = sQ + qs * C::kQTileBytes + kk * 32;
+            const uint32_t b = sK + ks * 8192 + kk * 32;
+            umma_ss_pair(tmem_base + C::colS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024),
+                         idesc_s, kk > 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&bars.k_empty[ks]);
+          if (it.last_of_visit()) umma_commit_pair(&bars.q_empty[qs]);
+          umma_commit_pair(&bars.s_full[n & 1]);
+        }
+        if (it.last_of_visit()) ++qv;
+        __syncwarp();
+      }
+    } else if (warp == 1 && leader) {
+      // ---- issuer of O += P(n) C_l[j] for both CTAs: P from TMEM, C half-tiles MN-major from shared memory ----
+      constexpr uint32_t idesc_pv1 = make_idesc(kBF16, 256, 256, false, true);
+      constexpr uint32_t idesc_pv2 = make_idesc(kBF16, 256, 128, false, true);
+      const uint32_t sC = smem_u32(smem + C::offC);
+      bool ready = false;
+      for (int n = 0; n < n_steps; ++n) {
+        const int cs = n % C::CS;
+        if (!ready) mbar_wait(&bars.pv_go[cs], (n / C::CS) & 1);
+        tc_fence_after();
+        ready = mbar_test(&bars.pv_go[(n + 1) % C::CS], ((n + 1) / C::CS) & 1);
+        if (lane == 0) {
+          const uint32_t a_tmem = tmem_base + C::colP + (n & 1) * (BN / 2);
+          const uint32_t b_base = sC + cs * C::kCHalfBytes;
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            umma_ts_pair(tmem_base + C::colO, a_tmem + kk * 8,
+                         make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024), idesc_pv1,
+                         (n > 0 || kk > 0) ? 1u : 0u);
+            umma_ts_pair(tmem_base + C::colO + 256, a_tmem + kk * 8,
+                         make_smem_desc_sw128(b_base + 2 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024),
+                         idesc_pv2, (n > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&bars.c_empty[cs]);
+          umma_commit_pair(&bars.p_free[n & 1]);
+          if (n == n_steps - 1) umma_commit_pair(&bars.o_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- softmax warpgroups (both CTAs, own 128 rows): w handles steps n = 2i + w ----
+    reg_alloc<224>();
+    const int w = (warp >> 2) - 1;
+    const int r = (warp & 3) * 32 + lane;
+    const int qrow = row0 + r;
+    const bool valid = qrow < S;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + C::colS;
+    const uint32_t tP = tmem_base + lane_addr + C::colP + w * (BN / 2);
+    const float c2 = p.scale_log2;
+    const float* lse_row = p.lse + static_cast<int64_t>(batch) * p.nv * S + (valid ? qrow : S - 1);
+    int cur_sense = -1;
+    float neg_lse2 = 0.f;
+    float lse_next = __ldg(lse_row);
+    int next_id = 0;
+    int i = 0;
+    // Hand-overs to the leader's barriers are ONE remote arrive per warp (after a warp sync), not one per thread:
+    // 256 remote arrives per barrier and step made this kernel twice as slow as the 1-CTA one.
+    if (w == 1 && lane == 0) mbar_arrive_leader(&bars.s_go[0]);   // "S(-1) drained"
+    StepIter it(nj, p.nv, p.group);
+    if (w == 1 && n_steps > 1) it.next();
+    for (int n = w; n < n_steps; n += 2, ++i) {
+      const int sense = it.sense(), j = it.j();
+      if (n + 2 < n_steps) { it.next(); it.next(); }
+      if (sense != cur_sense) {
+        cur_sense = sense;
+        if (next_id != sense) lse_next = __ldg(lse_row + static_cast<int64_t>(sense) * S);
+        neg_lse2 = -lse_next * kLog2e;
+        next_id = sense + 1 == p.nv ? 0 : sense + 1;
+        lse_next = __ldg(lse_row + static_cast<int64_t>(next_id) * S);
+      }
+      mbar_wait(&bars.s_full[w], i & 1);
+      tc_fence_after();
+      float s[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t u[32];
+        tmem_ld32(tS + c * 32, u);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[c * 32 + k] = __uint_as_float(u[k]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&bars.s_go[(n + 1) & 1]);   // S(n+1) may be computed while the exponentials run
+      const int col0 = j * BN;
+      if (col0 + BN - 1 > row0) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c)
+          if (col0 + c > qrow) s[c] = -INFINITY;
+      }
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int c = 0; c < BN / 2; ++c)
+        pk[c] = pack2<kBF16>(fast_exp2(fmaf(s[2 * c], c2, neg_lse2)), fast_exp2(fmaf(s[2 * c + 1], c2, neg_lse2)));
+      if (i >= 1) {
+        mbar_wait(&bars.p_free[w], (i - 1) & 1);   // the PV product of step n-2 has consumed this P buffer
+        tc_fence_after();
+      }
+      tmem_st32(tP, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&bars.pv_go[n % C::CS]);
+    }
+    // ---- epilogue: warpgroup w stores columns [w*192, (w+1)*192) of its rows ----
+    mbar_wait(&bars.o_full, 0);
+    tc_fence_after();
+    constexpr int half_cols = C::DC / 2;
+    const uint32_t tO = tmem_base + lane_addr + C::colO + w * half_cols;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
+                    2 * ((static_cast<int64_t>(tok0) + qrow) * p.d + col_base + w * half_cols);
+    for (int c = 0; c < half_cols / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack2<kBF16>(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+          v.y = pack2<kBF16>(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+          v.z = pack2<kBF16>(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+          v.w = pack2<kBF16>(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(orow + (c * 32 + g * 8) * 2) = v;
+        }
+      }
+    }
+  }
+  // no CTA of the pair may exit (or free TMEM) while its peer can still read its shared memory / signal it
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 3) tmem_dealloc_2cta(tmem_base, C::kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -621,6 +922,28 @@ static int launch_mix(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   }
   kern<<<dim3(p.num_qtiles * p.num_chunks, batch), kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmC, p);
   return check_launch("bp_sense_mix_fwd launch");
+}
+
+static bool use_pair_kernel() {   // BP_SENSE_PAIR=1 selects the CTA-pair kernel (A/B measurements)
+  static const bool on = [] {
+    const char* e = getenv("BP_SENSE_PAIR");   // measured: level with the 1-CTA kernel at 384 columns, slower than it at 256
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+template <bool kBF16>
+static int launch_mix_pair(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmC, const MixParams& p,
+                           int batch, cudaStream_t st) {
+  auto kern = sense_mix_pair_kernel<kBF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_sense_mix_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  const int num_qpairs = (p.num_qtiles + 1) / 2;
+  kern<<<dim3(num_qpairs * p.num_chunks * 2, batch), kThreads, PairCfg::kSmemBytes, st>>>(tmQ, tmK, tmC, p);
+  return check_launch("bp_sense_mix_fwd (pair) launch");
 }
 
 }  // namespace sense
@@ -685,12 +1008,18 @@ extern "C" int bp_sense_mix_fwd(const void* qk, const void* content, const float
   p.out = out;
   p.seqlen = seqlen, p.nv = nv, p.dk = dk, p.ksteps = (dk + 15) / 16, p.d = d;
   p.num_qtiles = (seqlen + sense::BM - 1) / sense::BM;
-  p.num_chunks = (d + 383) / 384;
+  p.num_chunks = (d + BP_SENSE_DC - 1) / BP_SENSE_DC;
   p.scale_log2 = softmax_scale * sense::kLog2e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int pk = (dk + 63) / 64;
   p.group = pk == 1 ? sense::kGroup : 1 << 20;
   const bool bf = dtype == BP_DTYPE_BF16;
+  if (pk == 1 && d % 384 == 0 && p.num_qtiles >= 2 && sense::use_pair_kernel()) {
+    // CTA-pair kernel: every CTA loads 32-key halves of the K tiles
+    if (int rc = sense::make_qk_map(&tmK, qk, batch, seqlen, nv, dk, dtype, 32)) return rc;
+    p.num_chunks = d / 384;
+    return bf ? sense::launch_mix_pair<true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix_pair<false>(tmQ, tmK, tmC, p, batch, st);
+  }
   switch (pk) {
     case 1: return bf ? sense::launch_mix<1, true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix<1, false>(tmQ, tmK, tmC, p, batch, st);
     case 2: return bf ? sense::launch_mix<2, true>(tmQ, tmK, tmC, p, batch, st) : sense::launch_mix<2, false>(tmQ, tmK, tmC, p, batch, st);
