@@ -67,10 +67,12 @@ def last_error() -> str:
 launch_counts: dict[str, int] = {}
 
 
-def check(status: int, what: str) -> None:
+def check(status: int, what: str, launched: bool = True) -> None:
+    """Raise on a non-zero status; count the call as one kernel launch unless `launched` is False (queries)."""
     if status != 0:
         raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
-    launch_counts[what] = launch_counts.get(what, 0) + 1
+    if launched:
+        launch_counts[what] = launch_counts.get(what, 0) + 1
 
 
 def total_launches() -> int:

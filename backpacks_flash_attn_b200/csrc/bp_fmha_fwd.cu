@@ -12,9 +12,9 @@
 //     small shared-memory ring to the other roles; barrier phases run on across items, Q is double-buffered
 //     per item and the K/V rings never drain, so the loads and the first S = Q K^T of the next item overlap
 //     the epilogue of the current one.
-//   * warp-specialised:  warp 0 = TMA producer, warps 1 / 2 = tcgen05.mma issuers for query tile 0 / 1 (two
-//     independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator, then 2 x NH softmax
-//     warpgroups (one thread per query row; TMEM lane == row, so row max / row sum need no shuffles).
+//   * warp-specialised:  warp 0 = scheduler + TMA producer, warps 1 / 2 = tcgen05.mma issuers for query tile 0 / 1
+//     (two independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator + O-tile store issuer, then
+//     2 x NH softmax warpgroups (one thread per query row; TMEM lane == row, so row max / row sum need no shuffles).
 //     The kernel is bound by the MUFU ex2 pipe, not by the tensor pipe, so for head dim <= 64 each key
 //     block is split into NH = 2 halves that run as independent online-softmax streams (own running max,
 //     own row sum, own O accumulator in TMEM; merged once in the epilogue): four softmax warps per SM
@@ -24,6 +24,7 @@
 //     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8), P = exp2(...) as
 //     bf16/f16 into a 128B-swizzled smem tile; O += P V is a second tcgen05.mma with V consumed as an
 //     MN-major B operand straight from the TMA tile (no transpose).
+//   * a finished full O tile is staged in shared memory (the idle P panel) and leaves as ONE TMA store.
 //
 // Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
 // are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill

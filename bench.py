@@ -177,7 +177,7 @@ def run_ours(args):
         print(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    _lib.check(_lib.load().bp_check_device(), "bp_check_device")
+    _lib.check(_lib.load().bp_check_device(), "bp_check_device", launched=False)
 
     B, S = args.batch, args.seqlen
     cfg = flash_config(**{**SMALL, "n_positions": max(1024, S)})
