@@ -45,11 +45,6 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kItemSlots = 4;     // shared-memory ring of decoded work items (producer -> all other roles)
 constexpr int kChunkBH = 148;     // (batch, head) pairs per scheduling chunk
 constexpr int kSchedSlots = 64;   // ticket counter slots, one per CUDA stream
-#ifndef BP_FMHA_STAGGER
-#define BP_FMHA_STAGGER 0
-#endif
-constexpr bool kStagger = BP_FMHA_STAGGER != 0;   // anti-phase hint between the two query tiles' softmax warps
-constexpr int kStaggerMaxSpins = 256;   // x ~25 cycles per probe: a few exponential phases at most
 #ifndef BP_FMHA_POLY_PAIRS
 #define BP_FMHA_POLY_PAIRS 0
 #endif
@@ -118,9 +113,7 @@ struct Barriers {
   uint64_t item_full[kItemSlots], item_empty[kItemSlots];
   uint64_t o_staged[2], o_free[2];         // [tile]: O tile staged in smem / read out by the TMA store
   uint32_t tmem_base;
-  uint32_t busy[2][2];                     // [tile][stream]: softmax warpgroup is in its exponential phase
 };
-#define BAR(field) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)))
 #define BAR_I(field, i) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)) + 8u * static_cast<uint32_t>(i))
 
 // One work item = (pair of query tiles, head, batch).  The producer warp decodes it once and publishes it
@@ -246,15 +239,6 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
   x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-__device__ __forceinline__ uint32_t ld_volatile_shared_u32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_volatile_shared_u32(uint32_t a, uint32_t v) {
-  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-
 template <int DP, bool kBF16>
 __global__ void __launch_bounds__(Cfg<DP>::kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -297,7 +281,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int h = 0; h < 2; ++h) {
         mbar_init(&bars.p_ready[i][h], 128);
         mbar_init(&bars.pv_done[i][h], 1);
-        bars.busy[i][h] = 0;
       }
     }
     for (int i = 0; i < 2; ++i) {
@@ -557,7 +540,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t xchg_a = smem_a + C::offX + t * NH * 128 * 8;
     const uint32_t bar_s_full = BAR_I(s_full, t), bar_s_free = BAR_I(s_free, t);
     const uint32_t bar_p_ready = BAR_I(p_ready, t * 2 + h), bar_pv_done = BAR_I(pv_done, t * 2 + h);
-    const uint32_t busy_mine = BAR(busy) + 4u * (t * 2 + h), busy_other = BAR(busy) + 8u * (t ^ 1);
     const float scale_log2 = p.scale_log2;
     uint32_t cnt = 0;  // key blocks processed by this warpgroup (phases of s_full / pv_done)
     Tracer tr(p.trace, 3 + g, blockIdx.x == 0 && r == 0);
@@ -650,20 +632,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           l *= alpha;
         }
-        if constexpr (kStagger && NH == 2) {
-          // Advisory anti-phase scheduling of the two query tiles: the exponentials of one tile should run
-          // while the other tile's warps wait on barriers / TMEM loads / take their row max, instead of all
-          // sixteen softmax warps hitting the MUFU pipe together and then idling together.  A tile defers its
-          // exponential phase while the other tile is inside its own (bounded: this is a hint, never a
-          // dependency, so unequal block counts and epilogues cannot deadlock).
-          if (!dead) {
-            int spins = 0;
-            while (ld_volatile_shared_u32(busy_other) + ld_volatile_shared_u32(busy_other + 4) != 0 &&
-                   spins < kStaggerMaxSpins)
-              ++spins;
-            if (r == 0) st_volatile_shared_u32(busy_mine, 1);
-          }
-        }
 
         const float neg_m = -m_used * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -691,10 +659,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           add2(sum4[2], sum4[3], e[6], e[7]);
           sts128(sP_row + ((c8 << 4) ^ sw), pack2<kBF16>(e[0], e[1]), pack2<kBF16>(e[2], e[3]),
                  pack2<kBF16>(e[4], e[5]), pack2<kBF16>(e[6], e[7]));
-          if constexpr (kStagger && NH == 2) {
-            // hand the MUFU pipe over a little early: the other tile needs ~100 cycles to notice
-            if (c8 == HB / 8 - 2 && r == 0) st_volatile_shared_u32(busy_mine, 0);
-          }
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         tr.rec(5, cnt);

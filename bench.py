@@ -355,7 +355,7 @@ def run_ours(args):
               "traffic": ncu_traffic("sense_mix_kernel") if (B, S) == (64, 1024) else None})
     kernels["sense_mix"] = k
     k = roof_tensor(gemm_flops, gemm_t)
-    k.update({"kernel": "gemm_bias_act_kernel<bf16> (bp_linear_bias_act_fwd), fc1 + bias + tanh-GELU",
+    k.update({"kernel": "gemm_bias_act_pair_kernel<bf16> (bp_linear_bias_act_fwd), fc1 + bias + tanh-GELU",
               "launches_per_step": per_kernel["bp_linear_bias_act_fwd:n"], "ms_per_launch": gemm_t * 1e3,
               "algorithmic_gflop_per_launch": gemm_flops / 1e9, "algorithmic_mb_per_launch": gemm_bytes / 1e6,
               "traffic": ncu_traffic("gemm_bias_act_pair_kernel") if (B, S) == (64, 1024) else None})
