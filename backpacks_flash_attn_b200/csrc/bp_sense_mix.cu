@@ -32,6 +32,9 @@ namespace sense {
 #ifndef BP_SENSE_DC
 #define BP_SENSE_DC 384
 #endif
+#ifndef BP_SENSE_P_SMEM
+#define BP_SENSE_P_SMEM 0
+#endif
 constexpr int BM = 128;
 constexpr int kThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -242,8 +245,12 @@ struct MixCfg {
   // pipe and the softmax of a step (~1000 cycles of latency) is longer than one PV.  256 columns (-DBP_SENSE_DC=256:
   // 3 chunks, TWO S buffers, S two steps ahead of PV) was measured SLOWER (1.21 vs 0.99 ms): every chunk repeats
   // the exponentials, and with a 512-cycle PV per step the MUFU pipe becomes the bound.
+  // -DBP_SENSE_P_SMEM=1 keeps P in shared memory instead (two 16 KB swizzled tiles, SS product as in the attention
+  // kernel): that frees the 64 TMEM columns of the P buffers for a SECOND S buffer at 384 columns, so S runs two
+  // steps ahead of PV without a third chunk.  Measured: 1.11 ms vs 1.02 ms with P in TMEM -- off by default.
   static constexpr int DC = BP_SENSE_DC;
-  static constexpr int SB = (DC + 2 * BN + 2 * (BN / 2) <= 512) ? 2 : 1;   // S buffers
+  static constexpr bool kPSmem = BP_SENSE_P_SMEM != 0 && PK == 1;
+  static constexpr int SB = (kPSmem ? DC + 2 * BN <= 512 : DC + 2 * BN + 2 * (BN / 2) <= 512) ? 2 : 1;   // S buffers
   static constexpr int QS = PK == 1 ? 2 : 1;
   static constexpr int KS = 2;
   static constexpr int CS = PK == 1 ? (DC <= 256 ? 4 : 3) : 2;
@@ -254,7 +261,9 @@ struct MixCfg {
   static constexpr uint32_t offQ = 0;
   static constexpr uint32_t offK = offQ + QS * kQTileBytes;
   static constexpr uint32_t offC = offK + KS * kKTileBytes;
-  static constexpr uint32_t offBar = offC + CS * kCTileBytes;
+  static constexpr uint32_t offP = offC + CS * kCTileBytes;            // [2] P tiles (128 rows x 64 keys), kPSmem only
+  static constexpr uint32_t kPTileBytes = BM * 128;
+  static constexpr uint32_t offBar = offP + (kPSmem ? 2 * kPTileBytes : 0);
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
   // TMEM: O accumulator, one S buffer (handed back as soon as the softmax warps hold it in registers) and
   // two P buffers: P (bf16/f16, two values per 32-bit column) is the A operand of the PV product and is
@@ -262,7 +271,7 @@ struct MixCfg {
   // what bounds this kernel (every K-step already streams a 64 x 384 slice of C through it).
   static constexpr uint32_t colO = 0, colS = DC, colP = DC + SB * BN;
   static constexpr uint32_t kTmemCols = 512;
-  static_assert(colP + 2 * (BN / 2) <= 512, "TMEM budget");
+  static_assert(kPSmem ? colP <= 512 : colP + 2 * (BN / 2) <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
@@ -449,6 +458,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
       const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
       const uint32_t sC = smem_u32(smem + C::offC);
+      const uint32_t sP = smem_u32(smem + C::offP);
       Tracer tr(p.trace, 1, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
       bool ready = false;   // result of the early probe of pv_go for this step
       for (int n = 0; n < n_steps; ++n) {
@@ -463,13 +473,23 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t b_base = sC + cs * C::kCTileBytes;
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
-            umma_ts(tmem_base + C::colO, a_tmem + kk * 8,
-                    make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024), idesc_pv1,
-                    (n > 0 || kk > 0) ? 1u : 0u);
-            if (n2 > 0)
-              umma_ts(tmem_base + C::colO + 256, a_tmem + kk * 8,
-                      make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024), idesc_pv2,
+            if constexpr (C::kPSmem) {
+              const uint64_t a_desc = make_smem_desc_sw128(sP + (n & 1) * C::kPTileBytes + kk * 32, 16, 1024);
+              umma_ss(tmem_base + C::colO, a_desc, make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024),
+                      idesc_pv1, (n > 0 || kk > 0) ? 1u : 0u);
+              if (n2 > 0)
+                umma_ss(tmem_base + C::colO + 256, a_desc,
+                        make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024),
+                        idesc_pv2, (n > 0 || kk > 0) ? 1u : 0u);
+            } else {
+              umma_ts(tmem_base + C::colO, a_tmem + kk * 8,
+                      make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024), idesc_pv1,
                       (n > 0 || kk > 0) ? 1u : 0u);
+              if (n2 > 0)
+                umma_ts(tmem_base + C::colO + 256, a_tmem + kk * 8,
+                        make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024),
+                        idesc_pv2, (n > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&bars.c_empty[cs]);
           umma_commit(&bars.p_free[n & 1]);
@@ -546,8 +566,17 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
       }
       tr.rec(4, n);
-      tmem_st32(tP, pk);
-      tmem_st_wait();
+      if constexpr (C::kPSmem) {
+        uint8_t* prow = smem + C::offP + w * C::kPTileBytes;   // this warpgroup's P tile, 128B-swizzled rows
+#pragma unroll
+        for (int c8 = 0; c8 < BN / 8; ++c8)
+          *reinterpret_cast<uint4*>(prow + sw128_offset(r, c8)) =
+              make_uint4(pk[c8 * 4 + 0], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+        fence_proxy_async_smem();
+      } else {
+        tmem_st32(tP, pk);
+        tmem_st_wait();
+      }
       tc_fence_before();
       mbar_arrive(&bars.pv_go[n % C::CS]);
       tr.rec(5, n);
