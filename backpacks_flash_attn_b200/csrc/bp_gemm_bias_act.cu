@@ -509,6 +509,7 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
     return fail(BP_ERR_INVALID_ARGUMENT, "%s: unknown activation %d", fn, activation);
   if ((uintptr_t)x % 16 || (uintptr_t)w % 16 || (uintptr_t)out % 16 || (uintptr_t)residual % 16 || (uintptr_t)bias % 4)
     return fail(BP_ERR_INVALID_ARGUMENT, "%s: pointers must be 16-byte aligned", fn);
+  if (residual && m < 256) return fail(BP_ERR_UNSUPPORTED, "%s: needs m >= 256 (got %lld)", fn, (long long)m);
   CUtensorMap tmA, tmB, tmO;
   {
     const uint64_t da[2] = {(uint64_t)k, (uint64_t)m}, sa[1] = {(uint64_t)k * 2};
@@ -558,8 +559,6 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
     kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
     return check_launch(fn);
   }
-  if (residual) return fail(BP_ERR_UNSUPPORTED, "%s: needs m >= 256 (got %lld)", fn, (long long)m);
-
   {
     const uint32_t bb[2] = {BK, BN};
     if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;

@@ -64,6 +64,18 @@ def test_invalid_arguments_are_rejected_without_a_gpu(lib_path):
     assert st == -1 and "multiple of 8" in _lib.last_error()
     st = lib.bp_rotary_qk_inplace(a, a, a, None, None, 1, 4, 1, 64, 65, 1, None)
     assert st == -1
+    # residual-epilogue GEMM: fewer rows than one CTA-pair tile, odd n, null residual
+    st = lib.bp_linear_bias_residual_fwd(a, a, None, a, 64, 64, 64, 1, None)
+    assert st != 0 and "m >= 256" in _lib.last_error()
+    st = lib.bp_linear_bias_residual_fwd(a, a, None, a, 512, 60, 64, 1, None)
+    assert st == -1 and "multiples of 8" in _lib.last_error()
+    st = lib.bp_linear_bias_residual_fwd(a, a, None, None, 512, 64, 64, 1, None)
+    assert st == -1
+    # LayerNorm of the fp32 residual: unsupported dtype combination, bad width
+    st = lib.bp_ln_fwd(a, a, a, a, None, None, 4, 64, 1e-5, 2, 1, 0, None)      # f32 -> bf16 with f16 weights
+    assert st != 0 and "not built" in _lib.last_error()
+    st = lib.bp_ln_fwd(a, a, a, a, None, None, 4, 60, 1e-5, 2, 1, 1, None)
+    assert st == -1 and "multiple of 8" in _lib.last_error()
 
 
 def test_operators_refuse_cpu_tensors(lib_path):
@@ -73,6 +85,13 @@ def test_operators_refuse_cpu_tensors(lib_path):
     cu = torch.tensor([0, 16], dtype=torch.int32)
     with pytest.raises(RuntimeError, match="CUDA"):
         flash_attn_unpadded_qkvpacked_func(qkv, cu, 16, 0.0, causal=True)
+
+
+def test_graphed_forward_refuses_cpu_inputs():
+    from backpacks_flash_attn_b200.utils.graph import GraphedForward
+    with torch.inference_mode():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            GraphedForward(torch.nn.Identity(), torch.zeros(1, 8, dtype=torch.long))
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
