@@ -496,6 +496,10 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (n == n_steps - 1) umma_commit(&bars.o_full);
         }
         __syncwarp();
+        // Issuing blocks while the tensor pipe's queue is full (a timeline trace shows ~850 cycles for the eight
+        // MMAs of a step), so P(n+1) has usually been stored by now: probe again rather than pay the ~240-cycle
+        // round trip of a blocking wait on an already completed phase with the pipe draining.
+        if (!ready) ready = mbar_test(&bars.pv_go[(n + 1) % C::CS], ((n + 1) / C::CS) & 1);
         tr.rec(6, n);
       }
     }
