@@ -52,6 +52,75 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------
+// softmax arithmetic shared by the attention and sense-mix kernels
+// ------------------------------------------------------------------------------------------
+// packed fp32x2 math (FFMA2 / FADD2): halves the issue slots of the exponent arguments and row sums
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  uint64_t a, bb, cc, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a1) {
+  uint64_t a, c, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc0), "f"(acc1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc0), "=f"(acc1) : "l"(d));
+}
+// three-input maximum (FMNMX3): the row max of a 128-key block costs 64 ALU instructions instead of 128
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// exp2 of a packed pair on the FMA pipe instead of the MUFU pipe (which bounds this kernel): round-to-nearest
+// range reduction through the 1.5*2^23 magic constant, degree-3 minimax polynomial for 2^f on [-0.5, 0.5]
+// (max relative error 7.5e-5, far below the bf16 rounding of P), exponent re-inserted with an integer add.
+__device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
+  x0 = fmaxf(x0, -126.f);   // masked (-inf) scores and underflow: 2^-126 ~ 0
+  x1 = fmaxf(x1, -126.f);
+  uint64_t x, t, nf, f, pz, magic, nmagic, neg1, c0, c1, c2, c3;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(magic) : "f"(12582912.f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(nmagic) : "f"(-12582912.f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(neg1) : "f"(-1.f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.9999280572f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.6932609677f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.2426111251f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.0551716462f));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic));        // low mantissa bits of t = rn(x)
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(nf) : "l"(t), "l"(nmagic));      // rn(x) as a float
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(nf), "l"(neg1), "l"(x));   // f = x - rn(x)
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(c3), "l"(f), "l"(c2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(pz), "l"(f), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(pz), "l"(f), "l"(c0));
+  float p0, p1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(pz));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// e[i] = exp2(s[i] * c + neg) for eight scores; kPolyOf8 (0, 2 or 4) of them take the FMA-pipe polynomial
+template <int kPolyOf8>
+__device__ __forceinline__ void exp2_scaled8(float (&e)[8], const float* s, float c, float neg) {
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    fma2(e[q], e[q + 1], s[q], s[q + 1], c, neg);
+    if (q < 8 - kPolyOf8) {
+      e[q] = fast_exp2(e[q]);
+      e[q + 1] = fast_exp2(e[q + 1]);
+    } else {
+      exp2_poly_pair(e[q], e[q + 1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -204,6 +273,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
       "r"(c2), "r"(c3)
+      : "memory");
+}
+// Row gather: four rows (r0..r3, arbitrary) x one box width of columns starting at c0 of a 2-D tensor land as four
+// consecutive rows at smem_dst (tensor map encoded with box {columns, 1}; swizzling as in tile mode).
+__device__ __forceinline__ void tma_gather4_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int r0,
+                                               int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {

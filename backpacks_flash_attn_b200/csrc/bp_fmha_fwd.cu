@@ -11,27 +11,31 @@
 //     a chunk stay in L2 and the last tickets are the lightest ones) and publishes the decoded item through a
 //     small shared-memory ring to the other roles; barrier phases run on across items, Q is double-buffered
 //     per item and the K/V rings never drain, so the loads and the first S = Q K^T of the next item overlap
-//     the epilogue of the current one.
-//   * warp-specialised:  warp 0 = scheduler + TMA producer, warps 1 / 2 = tcgen05.mma issuers for query tile 0 / 1
-//     (two independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator + O-tile store issuer, then
-//     2 x NH softmax warpgroups (one thread per query row; TMEM lane == row, so row max / row sum need no shuffles).
-//     The kernel is bound by the MUFU ex2 pipe, not by the tensor pipe, so for head dim <= 64 each key
-//     block is split into NH = 2 halves that run as independent online-softmax streams (own running max,
-//     own row sum, own O accumulator in TMEM; merged once in the epilogue): four softmax warps per SM
-//     sub-partition keep the MUFU pipe fed while their siblings wait on TMEM loads and barriers.
+//     the epilogue of the current one.  The counter is per LAUNCH: a slot of a device-side ring, zeroed by a
+//     memset node in front of the kernel, so concurrent launches (streams, graph replays) never share tickets
+//     and an aborted launch cannot poison a later one.
+//   * warp-specialised (384 threads): warp 0 = scheduler + TMA producer, warps 1 / 2 = tcgen05.mma issuers for
+//     query tile 0 / 1 (two independent pipelines sharing the K/V tiles), warp 3 = TMEM allocator + O-tile store
+//     issuer, then ONE softmax warpgroup per query tile: one thread per query row (TMEM lane == row, so row
+//     max / row sum need no shuffles) holding the whole score row of a key block in registers.
+//   * the kernel is bound by the MUFU ex2 pipe (16 exponentials per clock and SM against 128 x 128 scores per
+//     512 tensor-pipe cycles at head dim 64), so everything is arranged to keep that pipe busy: each SM
+//     sub-partition hosts exactly two softmax warps (one per query tile) whose exponential phases are long
+//     (a full 128-key row per thread) and whose other phases (TMEM load, 3-input row max, hand-overs) overlap the
+//     sibling tile's exponentials; the causal asymmetry of the two tiles keeps them out of phase.
 //   * S (M=128, N=BN) lands in TMEM; the softmax threads tcgen05.ld their row and hand the S buffer back at
 //     once (s_free), so S of the next key block is computed while this block's exponentials run; running
-//     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8), P = exp2(...) as
-//     bf16/f16 into a 128B-swizzled smem tile; O += P V is a second tcgen05.mma with V consumed as an
-//     MN-major B operand straight from the TMA tile (no transpose).
-//   * a finished full O tile is staged in shared memory (the idle P panel) and leaves as ONE TMA store.
+//     max with *lazy* rescaling (O is only touched when the max grew by more than 2^8); P = exp2(...) is packed to
+//     bf16/f16 and written back to TMEM (tcgen05.st), and O += P V is a TS tcgen05.mma (A = P from TMEM, B = V
+//     consumed MN-major straight from the TMA tile, no transpose): P never touches shared memory.
+//   * chunks of 32 keys that lie above the causal diagonal for a whole warp cost no exponentials at all.
+//   * a finished full O tile is staged in shared memory and leaves as ONE TMA store per 64-column panel.
 //
 // Varlen: sequences are addressed through cu_seqlens (rows of other sequences that fall inside a tile
 // are masked / never stored), head dims that are a multiple of 8 up to 128 are handled by TMA zero-fill
 // to a padded width DP of 64 or 128.
+#include <atomic>
 #include <cstddef>
-#include <mutex>
-#include <unordered_map>
 
 #include "bp_common.cuh"
 #include "bp_host.h"
@@ -44,48 +48,46 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kItemSlots = 4;     // shared-memory ring of decoded work items (producer -> all other roles)
 constexpr int kChunkBH = 148;     // (batch, head) pairs per scheduling chunk
-constexpr int kSchedSlots = 64;   // ticket counter slots, one per CUDA stream
-#ifndef BP_FMHA_POLY_PAIRS
-#define BP_FMHA_POLY_PAIRS 0
+#ifndef BP_FMHA_POLY
+#define BP_FMHA_POLY 0
 #endif
-constexpr int kPolyPairs = BP_FMHA_POLY_PAIRS;   // of every 4 score pairs, how many take the polynomial exp2 (FMA pipe) instead of MUFU; measured: 1 -> 139 us vs 0 -> 134 us at config 2 (the lockstep softmax warps are issue-limited, not MUFU-limited)
+// of every 8 scores, how many take the polynomial exp2 (FMA pipe) instead of MUFU (0, 2 or 4)
+constexpr int kPoly = BP_FMHA_POLY;
+#ifndef BP_FMHA_STAGGER
+#define BP_FMHA_STAGGER 0
+#endif
+constexpr int kStagger = BP_FMHA_STAGGER;   // cycles query tile 1 holds back its very first block (debug knob)
 
 template <int DP>
 struct Cfg {
-  static constexpr int BN = (DP == 64) ? 128 : 64;  // keys per block
-  static constexpr int NH = (DP == 64) ? 2 : 1;      // independent softmax streams (key halves) per block
-  static constexpr int HB = BN / NH;                 // keys per stream and block (= 64)
-  static constexpr int kThreads = 128 + 256 * NH;    // warps 0-3 + 2*NH softmax warpgroups
+  static constexpr int BN = (DP == 64) ? 128 : 64;   // keys per block
+  static constexpr int kThreads = 384;               // warps 0-3 + one softmax warpgroup per query tile
   // setmaxnreg only redistributes the registers the CTA was launched with (kThreads x the compiled per-thread
-  // count): 128 * kRegsLow + (kThreads - 128) * kRegsHigh must not exceed it, or the last warps to grow block forever
-  static constexpr int kRegsLow = NH == 2 ? 32 : 56;
-  static constexpr int kRegsHigh = NH == 2 ? 112 : 224;
-  static constexpr int kStages = 2;                  // K and V rings
+  // count, 168): 128 * kRegsLow + 256 * kRegsHigh must not exceed it, or the last warps to grow block forever
+  static constexpr int kRegsLow = 56;
+  static constexpr int kRegsHigh = 224;
+  static constexpr int kStages = 3;                  // K and V rings
   static constexpr int kQBufs = (DP == 64) ? 2 : 1;  // Q buffers across work items (smem-limited at DP = 128)
-  // O leaves through shared memory + one TMA store per query tile (staged in the idle P panel of stream 0); at
-  // DP = 128 the P panel is too small for the O tile and rows are stored directly
-  static constexpr bool kStageO = (DP == 64);
   static constexpr int kPanelsD = DP / 64;           // 64-column (128 B) panels along head dim
   static constexpr uint32_t kQTileBytes = BM * DP * 2;
   static constexpr uint32_t kKVTileBytes = BN * DP * 2;
-  static constexpr uint32_t kPTileBytes = BM * BN * 2;
   static constexpr uint32_t kKVPanelBytes = BN * 128;  // one 64-column panel of a K/V tile
+  static constexpr uint32_t kOTileBytes = BM * DP * 2; // staging of a finished O tile (kPanelsD panels of 128 rows x 128 B)
   // shared memory map (all tile bases 1024-aligned)
   static constexpr uint32_t offQ = 0;                                  // [kQBufs item buffers][2 tiles]
   static constexpr uint32_t offK = offQ + kQBufs * 2 * kQTileBytes;
   static constexpr uint32_t offV = offK + kStages * kKVTileBytes;
-  static constexpr uint32_t offP = offV + kStages * kKVTileBytes;
-  static constexpr uint32_t offX = offP + 2 * kPTileBytes;            // (m, l) exchange [2][NH][128] float2
-  static constexpr uint32_t offItems = offX + 2 * NH * 128 * 8;       // ring of decoded work items
+  static constexpr uint32_t offO = offV + kStages * kKVTileBytes;     // [2 tiles]
+  static constexpr uint32_t offItems = offO + 2 * kOTileBytes;        // ring of decoded work items
   static constexpr uint32_t offBar = offItems + kItemSlots * 64;
   static constexpr uint32_t kSmemBytes = offBar + 512 + 1024;  // + barriers + alignment slack
   static_assert(kSmemBytes <= 232448, "shared memory budget");
-  static_assert(HB == 64, "one 64-key P panel per softmax stream");
-  // TMEM columns
-  static constexpr uint32_t colS = 0;            // S_t at colS + t*BN
-  static constexpr uint32_t colO = 2 * BN;       // O_{t,h} at colO + (t*NH + h)*DP
+  // TMEM columns: S_t (fp32, BN columns), O_t (fp32, DP columns), P_t (16-bit pairs, BN / 2 columns)
+  static constexpr uint32_t colS = 0;                 // S_t at colS + t*BN
+  static constexpr uint32_t colO = 2 * BN;            // O_t at colO + t*DP
+  static constexpr uint32_t colP = 2 * BN + 2 * DP;   // P_t at colP + t*BN/2
   static constexpr uint32_t kTmemCols = 512;
-  static_assert(colO + 2 * NH * DP <= 512, "TMEM budget");
+  static_assert(colP + BN <= 512, "TMEM budget");
 };
 
 struct Params {
@@ -98,8 +100,9 @@ struct Params {
   int32_t batch, nheads, headdim;
   int32_t num_pairs;  // ceil(max_seqlen_q / 256)
   int32_t num_items;  // num_pairs * batch * nheads
-  unsigned int* sched;  // [0] ticket counter, [1] finished CTAs; both zero between launches
+  unsigned int* sched;  // this launch's ticket counter (zeroed by a memset in front of the kernel)
   int32_t is_causal;
+  int32_t out_f32;    // debug / test mode: `out` is fp32 (same element strides), written before the 16-bit rounding
   float scale;        // softmax scale
   float scale_log2;   // scale * log2(e)
   uint64_t* trace;    // debug: per-role event timestamps of CTA 0 (null in production)
@@ -107,13 +110,14 @@ struct Params {
 
 struct Barriers {
   uint64_t q_full[2], q_empty[2];
-  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t s_full[2], s_free[2];
-  uint64_t p_ready[2][2], pv_done[2][2];   // [tile][stream]
+  uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
+  uint64_t s_full[2], s_free[2];           // [tile]
+  uint64_t p_ready[2], pv_done[2];         // [tile]
   uint64_t item_full[kItemSlots], item_empty[kItemSlots];
   uint64_t o_staged[2], o_free[2];         // [tile]: O tile staged in smem / read out by the TMA store
   uint32_t tmem_base;
 };
+static_assert(sizeof(Barriers) <= 512, "barrier block");
 #define BAR_I(field, i) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)) + 8u * static_cast<uint32_t>(i))
 
 // One work item = (pair of query tiles, head, batch).  The producer warp decodes it once and publishes it
@@ -194,57 +198,13 @@ __device__ __forceinline__ Item get_item(uint32_t a) {
   return it;
 }
 
-// packed fp32x2 math (FFMA2 / FADD2): halves the issue slots of the exponent arguments and row sums
-__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
-  uint64_t a, bb, cc, d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
-}
-__device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a1) {
-  uint64_t a, c, d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc0), "f"(acc1));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(c));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc0), "=f"(acc1) : "l"(d));
-}
-
-// exp2 of a packed pair on the FMA pipe instead of the MUFU pipe (which bounds this kernel): round-to-nearest
-// range reduction through the 1.5*2^23 magic constant, degree-3 minimax polynomial for 2^f on [-0.5, 0.5]
-// (max relative error 7.5e-5, far below the bf16 rounding of P), exponent re-inserted with an integer add.
-__device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
-  x0 = fmaxf(x0, -126.f);   // masked (-inf) scores and underflow: 2^-126 ~ 0
-  x1 = fmaxf(x1, -126.f);
-  uint64_t x, t, nf, f, pz, magic, nmagic, neg1, c0, c1, c2, c3;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(magic) : "f"(12582912.f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(nmagic) : "f"(-12582912.f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(neg1) : "f"(-1.f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.9999280572f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.6932609677f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.2426111251f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.0551716462f));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic));        // low mantissa bits of t = rn(x)
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(nf) : "l"(t), "l"(nmagic));      // rn(x) as a float
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(nf), "l"(neg1), "l"(x));   // f = x - rn(x)
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(c3), "l"(f), "l"(c2));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(pz), "l"(f), "l"(c1));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(pz), "l"(f), "l"(c0));
-  float p0, p1, t0, t1;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(pz));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
-  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
-
 template <int DP, bool kBF16>
 __global__ void __launch_bounds__(Cfg<DP>::kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   using C = Cfg<DP>;
-  constexpr int BN = C::BN, NH = C::NH, HB = C::HB;
+  constexpr int BN = C::BN;
+  constexpr int NC = BN / 32;   // 32-key chunks of a block
   extern __shared__ uint8_t smem_raw[];
   // everything below works on 32-bit shared-window addresses (see bp_common.cuh)
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -272,24 +232,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.q_full[i], 1);
       mbar_init(&bars.q_empty[i], 2);   // both MMA warps release a Q buffer
+      mbar_init(&bars.s_full[i], 1);
+      mbar_init(&bars.s_free[i], 128);
+      mbar_init(&bars.p_ready[i], 128);
+      mbar_init(&bars.pv_done[i], 1);
+      mbar_init(&bars.o_staged[i], 128);
+      mbar_init(&bars.o_free[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&bars.k_full[i], 1);
       mbar_init(&bars.k_empty[i], 2);   // both MMA warps release a K / V slot
       mbar_init(&bars.v_full[i], 1);
       mbar_init(&bars.v_empty[i], 2);
-      mbar_init(&bars.s_full[i], 1);
-      mbar_init(&bars.s_free[i], 128 * NH);
-      for (int h = 0; h < 2; ++h) {
-        mbar_init(&bars.p_ready[i][h], 128);
-        mbar_init(&bars.pv_done[i][h], 1);
-      }
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars.o_staged[i], 256);
-      mbar_init(&bars.o_free[i], 1);
     }
     for (int i = 0; i < kItemSlots; ++i) {
       mbar_init(&bars.item_full[i], 1);
-      mbar_init(&bars.item_empty[i], 2 + 8 * NH + (C::kStageO ? 1 : 0));   // one lane of every consumer warp
+      mbar_init(&bars.item_empty[i], 2 + 8 + 1);   // one lane of every consumer warp (2 MMA, 8 softmax, warp 3)
     }
     fence_barrier_init();
   }
@@ -318,7 +276,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     reg_dealloc<C::kRegsLow>();
     if (warp == 0) {
       // ===================== scheduler + TMA producer (whole warp walks the loop, lane 0 issues) =====================
-      uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no % kQBufs, K/V slot = blk & 1
+      uint32_t item_no = 0, blk = 0;  // running counters: Q buffer = item_no % kQBufs, K/V slot = blk % kStages
       uint32_t seq = 0;               // items published (valid items + the end marker)
       Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
       auto publish = [&](const Item& it) {
@@ -371,9 +329,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             BAR_I(q_full, qb), pn * 64, it.head, it.q_begin + it.row0 + t * BM);
         }
         auto issue_kv = [&](int j) {
-          const uint32_t slot = blk & 1;
+          const uint32_t slot = blk % C::kStages;
+          const uint32_t ph = ((blk / C::kStages) - 1) & 1;
           const int krow = it.k_begin + j * BN;
-          if (blk >= 2) mbar_wait_a(BAR_I(k_empty, slot), ((blk >> 1) - 1) & 1);
+          if (blk >= C::kStages) mbar_wait_a(BAR_I(k_empty, slot), ph);
           tr.rec(1, blk);
           if (lane == 0) {
             mbar_arrive_expect_tx_a(BAR_I(k_full, slot), C::kKVTileBytes);
@@ -381,7 +340,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               tma_load_3d_a(smem_a + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK,
                             BAR_I(k_full, slot), pn * 64, it.head, krow);
           }
-          if (blk >= 2) mbar_wait_a(BAR_I(v_empty, slot), ((blk >> 1) - 1) & 1);
+          if (blk >= C::kStages) mbar_wait_a(BAR_I(v_empty, slot), ph);
           tr.rec(2, blk);
           if (lane == 0) {
             mbar_arrive_expect_tx_a(BAR_I(v_full, slot), C::kKVTileBytes);
@@ -412,9 +371,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_pv = make_idesc(kBF16, BM, DP, false, true);
       const uint32_t sK = smem_a + C::offK;
       const uint32_t sV = smem_a + C::offV;
-      const uint32_t sP = smem_a + C::offP + t * C::kPTileBytes;
       const uint32_t tS = tmem_base + C::colS + t * BN;
-      const uint32_t tO = tmem_base + C::colO + t * NH * DP;
+      const uint32_t tO = tmem_base + C::colO + t * DP;
+      const uint32_t tP = tmem_base + C::colP + t * (BN / 2);
       uint32_t item_no = 0, blk = 0;  // same running counters as the producer
       uint32_t s_cnt = 0;             // S tiles issued by this warp (s_free / s_full phases)
       uint32_t pv_cnt = 0;            // key blocks whose PV products were issued (p_ready / pv_done phases)
@@ -431,11 +390,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
         // S(j) = Q K_j^T into this tile's S buffer, then hand the K slot back (both tiles must do so)
         auto step_s = [&](int j, uint32_t kblk) {
-          const uint32_t slot = kblk & 1;
+          const uint32_t slot = kblk % C::kStages;
+          const uint32_t ph = (kblk / C::kStages) & 1;
           if (j < n) {
             if (s_cnt >= 1) mbar_wait_a(BAR_I(s_free, t), (s_cnt - 1) & 1);   // softmax has read the previous S
             tr.rec(1, kblk);
-            mbar_wait_a(BAR_I(k_full, slot), (kblk >> 1) & 1);
+            mbar_wait_a(BAR_I(k_full, slot), ph);
             tc_fence_after();
             tr.rec(2, kblk);
             if (lane == 0) {
@@ -455,7 +415,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // Block not visited by this tile.  The slot still needs this warp's release, but only once the
             // producer has (re)filled it for THIS block: arriving earlier could complete the previous
             // phase of k_empty while the other tile still reads the previous occupant.
-            mbar_wait_a(BAR_I(k_full, slot), (kblk >> 1) & 1);
+            mbar_wait_a(BAR_I(k_full, slot), ph);
             if (lane == 0) umma_commit_a(BAR_I(k_empty, slot));
           }
           __syncwarp();
@@ -465,51 +425,50 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         step_s(0, blk);
         for (int j = 0; j < n_max; ++j, ++blk) {
           if (j + 1 < n_max) step_s(j + 1, blk + 1);
-          const uint32_t slot = blk & 1;
+          const uint32_t slot = blk % C::kStages;
+          const uint32_t ph = (blk / C::kStages) & 1;
+          mbar_wait_a(BAR_I(v_full, slot), ph);
           if (j < n) {
-            mbar_wait_a(BAR_I(v_full, slot), (blk >> 1) & 1);
+            // O_t (+)= P_t V_j : A = P from TMEM (8 columns per K-step of 16 keys), V rows are the K dimension
+            // (MN-major B operand, the TMA tile as it landed)
+            mbar_wait_a(BAR_I(p_ready, t), pv_cnt & 1);
+            tc_fence_after();
+            tr.rec(3, blk);
+            if (lane == 0) {
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-              // O_{t,h} (+)= P_{t,h} V_j[h*64 : h*64+64, :]   (V rows are the K dimension: MN-major B)
-              mbar_wait_a(BAR_I(p_ready, t * 2 + h), pv_cnt & 1);
-              tc_fence_after();
-              tr.rec(3 + h, blk);
-              if (lane == 0) {
-#pragma unroll
-                for (int kk = 0; kk < HB / 16; ++kk) {
-                  const uint32_t a = sP + h * (BM * 128) + kk * 32;
-                  const uint32_t b = sV + slot * C::kKVTileBytes + (h * HB + kk * 16) * 128;
-                  umma_ss(tO + h * DP, make_smem_desc_sw128(a, 16, 1024),
-                          make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                }
-                if (h == NH - 1) umma_commit_a(BAR_I(v_empty, slot));
-                umma_commit_a(BAR_I(pv_done, t * 2 + h));
+              for (int kk = 0; kk < BN / 16; ++kk) {
+                const uint32_t b = sV + slot * C::kKVTileBytes + kk * 16 * 128;
+                umma_ts(tO, tP + kk * 8, make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv,
+                        (j > 0 || kk > 0) ? 1u : 0u);
               }
-              __syncwarp();
+              umma_commit_a(BAR_I(v_empty, slot));
+              umma_commit_a(BAR_I(pv_done, t));
             }
             ++pv_cnt;
           } else {
-            mbar_wait_a(BAR_I(v_full, slot), (blk >> 1) & 1);   // same pacing rule as for K
-            if (lane == 0) umma_commit_a(BAR_I(v_empty, slot));
-            __syncwarp();
+            if (lane == 0) umma_commit_a(BAR_I(v_empty, slot));   // same pacing rule as for K
           }
+          __syncwarp();
         }
         ++item_no;
       }
-    } else if (C::kStageO) {
+    } else {
       // ===================== warp 3: O tile stores =====================
       // The softmax warpgroups stage a finished O tile in shared memory; this otherwise idle warp issues the
-      // TMA store, waits until the tile has been read out and hands the buffer (stream 0's P panel) back.
+      // TMA store, waits until the tile has been read out and hands the staging buffer back.
       uint32_t st_cnt[2] = {0, 0};
       while (true) {
         const Item it = next_item();
         if (it.end) break;
+        if (p.out_f32) continue;   // test mode: rows are stored directly
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (it.n_of(t) == 0 || it.row0 + t * BM + BM > it.len_q) continue;   // tile absent or stored row by row
           mbar_wait_a(BAR_I(o_staged, t), st_cnt[t] & 1);
           if (lane == 0) {
-            tma_store_3d(&tmO, smem_a + C::offP + t * C::kPTileBytes, 0, it.head, it.q_begin + it.row0 + t * BM);
+            for (int pn = 0; pn < C::kPanelsD; ++pn)
+              tma_store_3d(&tmO, smem_a + C::offO + t * C::kOTileBytes + pn * (BM * 128), pn * 64, it.head,
+                           it.q_begin + it.row0 + t * BM);
             tma_store_commit();
             tma_store_wait_read<0>();
             mbar_arrive_a(BAR_I(o_free, t));
@@ -521,34 +480,37 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) tma_store_wait_all();   // shared memory must outlive the last store
     }
   } else {
-    // ===================== softmax warpgroups =====================
+    // ===================== softmax warpgroups: one per query tile =====================
     reg_alloc<C::kRegsHigh>();
-    const int g = (warp >> 2) - 1;
-    const int t = g / NH;                          // query tile of this warpgroup
-    const int h = g % NH;                          // key half (stream) of this warpgroup
+    const int t = (warp >> 2) - 1;                 // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN + h * HB;
-    const uint32_t tO_tile = tmem_base + lane_addr + C::colO + t * NH * DP;
-    const uint32_t tO = tO_tile + h * DP;
-    // this thread's row of the P panel: chunk c8 lives at row_base + ((c8 ^ (r & 7)) << 4)
-    const uint32_t sP_row = smem_a + C::offP + t * C::kPTileBytes + h * (BM * 128) + r * 128;
+    const uint32_t tS = tmem_base + lane_addr + C::colS + t * BN;
+    const uint32_t tO = tmem_base + lane_addr + C::colO + t * DP;
+    const uint32_t tP = tmem_base + lane_addr + C::colP + t * (BN / 2);
+    // this thread's row of the O staging tile: 16-byte chunk q of panel pn lives at + pn*BM*128 + ((q << 4) ^ sw)
+    const uint32_t sO_row = smem_a + C::offO + t * C::kOTileBytes + r * 128;
     const uint32_t sw = (r & 7) << 4;
-    const uint32_t sO_row = smem_a + C::offP + t * C::kPTileBytes + r * 128;   // O staging = P panel of stream 0
     bool store_pending = false;
     uint32_t st_cnt = 0;   // O tiles of this query tile handed to warp 3
-    const uint32_t xchg_a = smem_a + C::offX + t * NH * 128 * 8;
     const uint32_t bar_s_full = BAR_I(s_full, t), bar_s_free = BAR_I(s_free, t);
-    const uint32_t bar_p_ready = BAR_I(p_ready, t * 2 + h), bar_pv_done = BAR_I(pv_done, t * 2 + h);
+    const uint32_t bar_p_ready = BAR_I(p_ready, t), bar_pv_done = BAR_I(pv_done, t);
     const float scale_log2 = p.scale_log2;
     uint32_t cnt = 0;  // key blocks processed by this warpgroup (phases of s_full / pv_done)
-    Tracer tr(p.trace, 3 + g, blockIdx.x == 0 && r == 0);
+    Tracer tr(p.trace, 3 + t, blockIdx.x == 0 && r == 0);
+    if constexpr (kStagger > 0) {
+      if (t == 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < kStagger) {}
+      }
+    }
     while (true) {
       const Item it = next_item();
       if (it.end) break;
       const int n = it.n_of(t);
       if (n == 0) continue;
-      const int qrow = it.row0 + t * BM + r;       // query index within the sequence
+      const int row0_t = it.row0 + t * BM;
+      const int qrow = row0_t + r;                 // query index within the sequence
       float m_used = 0.f;  // running max (raw score units) the exponentials are taken against
       float l = 0.f;
 
@@ -557,9 +519,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait_a(bar_s_full, cnt & 1);
         tc_fence_after();
         tr.rec(1, cnt);
-        float s[HB];
+        float s[BN];
 #pragma unroll
-        for (int c = 0; c < HB / 32; ++c) {
+        for (int c = 0; c < NC; ++c) {
           uint32_t u[32];
           tmem_ld32(tS + c * 32, u);
 #pragma unroll
@@ -570,26 +532,37 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive_a(bar_s_free);   // S(j+1) may now overwrite the buffer while we work on registers
         tr.rec(2, cnt);
 
-        const int col0 = j * BN + h * HB;
-        const bool partial = (col0 + HB > it.len_k) || (p.is_causal && (col0 + HB - 1 > it.row0 + t * BM));
-        bool dead = false;   // every key of this half-block is masked for every row of this warp
+        const int col0 = j * BN;
+        const bool partial = (col0 + BN > it.len_k) || (p.is_causal && (col0 + BN - 1 > row0_t));
+        uint32_t dead = 0;   // bit c: every key of chunk c is masked for every row of this warp
         if (partial) {
-          // visible keys of this row inside the half-block: local column c < lim
+          // visible keys of this row inside the block: local column < lim
           const int lim = (p.is_causal ? min(it.len_k, qrow + 1) : it.len_k) - col0;
-          dead = __all_sync(0xffffffffu, lim <= 0);
 #pragma unroll
-          for (int c = 0; c < HB; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
-        }
-        // row max: four independent chains
-        float mx4[4] = {s[0], s[1], s[2], s[3]};
+          for (int c = 0; c < NC; ++c) {
+            if (!__all_sync(0xffffffffu, lim >= (c + 1) * 32)) {
+              if (__all_sync(0xffffffffu, lim <= c * 32)) {
+                dead |= 1u << c;
+              } else {
 #pragma unroll
-        for (int c = 4; c < HB; c += 4) {
-          mx4[0] = fmaxf(mx4[0], s[c]);
-          mx4[1] = fmaxf(mx4[1], s[c + 1]);
-          mx4[2] = fmaxf(mx4[2], s[c + 2]);
-          mx4[3] = fmaxf(mx4[3], s[c + 3]);
+                for (int i = 0; i < 32; ++i) s[c * 32 + i] = (c * 32 + i < lim) ? s[c * 32 + i] : -INFINITY;
+              }
+            }
+          }
         }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // row max over the live chunks: two independent 3-input chains per chunk
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (!((dead >> c) & 1u)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mxa = max3(mxa, s[c * 32 + i], s[c * 32 + i + 1]);
+              mxb = max3(mxb, s[c * 32 + i + 2], s[c * 32 + i + 3]);
+            }
+          }
+        }
+        const float mx = fmaxf(mxa, mxb);
 
         float alpha = 1.f;
         bool grow = false;
@@ -604,16 +577,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tr.rec(3, cnt);
-        if (j == 0) {
-          if constexpr (C::kStageO) {
-            // The previous item's O tile was staged in this stream's P panel: the TMA store must have read it
-            if (h == 0 && store_pending) {
-              mbar_wait_a(BAR_I(o_free, t), (st_cnt - 1) & 1);
-              store_pending = false;
-            }
-          }
-        } else {
-          // P tile and O accumulator are free once the previous PV MMA of this stream has completed
+        if (j > 0) {
+          // the P buffer and the O accumulator are free once the previous PV product of this tile has completed
           mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
           tc_fence_after();
           tr.rec(4, cnt);
@@ -635,122 +600,113 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
         const float neg_m = -m_used * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (dead) {
-          // above the causal diagonal: P = 0 without a single exponential
 #pragma unroll
-          for (int c8 = 0; c8 < HB / 8; ++c8) sts128(sP_row + ((c8 << 4) ^ sw), 0u, 0u, 0u, 0u);
-        } else
+        for (int c = 0; c < NC; ++c) {
+          uint32_t pk[16];
+          if ((dead >> c) & 1u) {
+            // above the causal diagonal: P = 0 without a single exponential
 #pragma unroll
-        for (int c8 = 0; c8 < HB / 8; ++c8) {
-          float e[8];
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            fma2(e[i], e[i + 1], s[c8 * 8 + i], s[c8 * 8 + i + 1], scale_log2, neg_m);
-            if (i < 8 - 2 * kPolyPairs) {
-              e[i] = fast_exp2(e[i]);
-              e[i + 1] = fast_exp2(e[i + 1]);
-            } else {
-              exp2_poly_pair(e[i], e[i + 1]);   // this share of the exponentials runs on the FMA pipe
+            for (int i = 0; i < 32; i += 8) {
+              float e[8];
+#pragma unroll
+              for (int q = 0; q < 8; q += 2) {
+                fma2(e[q], e[q + 1], s[c * 32 + i + q], s[c * 32 + i + q + 1], scale_log2, neg_m);
+                if (q < 8 - kPoly) {
+                  e[q] = fast_exp2(e[q]);
+                  e[q + 1] = fast_exp2(e[q + 1]);
+                } else {
+                  exp2_poly_pair(e[q], e[q + 1]);   // this share of the exponentials runs on the FMA pipe
+                }
+              }
+              add2(sum4[0], sum4[1], e[0], e[1]);
+              add2(sum4[2], sum4[3], e[2], e[3]);
+              add2(sum4[0], sum4[1], e[4], e[5]);
+              add2(sum4[2], sum4[3], e[6], e[7]);
+              pk[i / 2 + 0] = pack2<kBF16>(e[0], e[1]);
+              pk[i / 2 + 1] = pack2<kBF16>(e[2], e[3]);
+              pk[i / 2 + 2] = pack2<kBF16>(e[4], e[5]);
+              pk[i / 2 + 3] = pack2<kBF16>(e[6], e[7]);
             }
           }
-          add2(sum4[0], sum4[1], e[0], e[1]);
-          add2(sum4[2], sum4[3], e[2], e[3]);
-          add2(sum4[0], sum4[1], e[4], e[5]);
-          add2(sum4[2], sum4[3], e[6], e[7]);
-          sts128(sP_row + ((c8 << 4) ^ sw), pack2<kBF16>(e[0], e[1]), pack2<kBF16>(e[2], e[3]),
-                 pack2<kBF16>(e[4], e[5]), pack2<kBF16>(e[6], e[7]));
+          tmem_st16(tP + c * 16, pk);
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        tmem_st_wait();
         tr.rec(5, cnt);
-        fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive_a(bar_p_ready);
         tr.rec(6, cnt);
       }
 
-      // ---- epilogue: merge the NH streams, O / l -> global, LSE ----
+      // ---- epilogue: O / l -> global, LSE ----
       tr.rec(7, cnt);
       mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
       tc_fence_after();
       tr.rec(8, cnt);
       const bool valid = qrow < it.len_q;
-      float w_self = 1.f, w_other = 0.f, m_all = m_used, l_all = l;
-      if constexpr (NH == 2) {
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xchg_a + (h * 128 + r) * 8), "f"(m_used), "f"(l) : "memory");
-        if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
-        tr.rec(10, cnt);
-        float2 o;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o.x), "=f"(o.y) : "r"(xchg_a + ((h ^ 1) * 128 + r) * 8) : "memory");
-        const bool has_self = l > 0.f, has_other = o.y > 0.f;
-        m_all = has_self ? (has_other ? fmaxf(m_used, o.x) : m_used) : o.x;
-        w_self = has_self ? fast_exp2((m_used - m_all) * scale_log2) : 0.f;
-        w_other = has_other ? fast_exp2((o.x - m_all) * scale_log2) : 0.f;
-        l_all = w_self * l + w_other * o.y;
-      }
-      const float inv_l = 1.f / l_all;
-      w_self *= inv_l;
-      w_other *= inv_l;
-      constexpr int kColsPerWG = DP / NH;   // output columns written by this warpgroup
+      const float inv_l = 1.f / l;
       // Full tiles are staged in shared memory (128B-swizzled rows, the layout the TMA store expects) and leave
-      // as ONE bulk store; a thread-per-row store would touch 32 different lines per instruction.  Tiles that
-      // end inside the sequence keep the guarded per-row stores (the next sequence's rows follow in memory).
-      const bool stage = C::kStageO && (it.row0 + t * BM + BM <= it.len_q);
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) +
-                      2 * (static_cast<int64_t>(it.q_begin + qrow) * p.o_row_stride + it.head * p.o_head_stride +
-                           h * kColsPerWG);
+      // as one bulk store per panel; a thread-per-row store would touch 32 different lines per instruction.  Tiles
+      // that end inside the sequence keep the guarded per-row stores (the next sequence's rows follow in memory).
+      const bool stage = !p.out_f32 && (row0_t + BM <= it.len_q);
+      if (stage && store_pending) {
+        mbar_wait_a(BAR_I(o_free, t), (st_cnt - 1) & 1);   // the previous tile's TMA store has read the staging buffer
+        store_pending = false;
+      }
+      const int64_t o_elem = static_cast<int64_t>(it.q_begin + qrow) * p.o_row_stride + it.head * p.o_head_stride;
 #pragma unroll
-      for (int c = 0; c < kColsPerWG / 32; ++c) {
-        // both accumulators' columns are fetched with one TMEM round trip
-        uint32_t o[32], o2[32];
+      for (int c = 0; c < DP / 32; ++c) {
+        uint32_t o[32];
         float f[32];
-        tmem_ld32(tO + h * kColsPerWG + c * 32, o);   // own accumulator, this warpgroup's columns
-        if constexpr (NH == 2) tmem_ld32(tO_tile + (h ^ 1) * DP + h * kColsPerWG + c * 32, o2);   // sibling stream
+        tmem_ld32(tO + c * 32, o);
         tmem_ld_wait();
-        tr.rec(11, cnt);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          f[i] = __uint_as_float(o[i]) * w_self;
-          if constexpr (NH == 2) f[i] = fmaf(__uint_as_float(o2[i]), w_other, f[i]);
-        }
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
         if (stage) {
-          if constexpr (C::kStageO) {
+          const uint32_t base = sO_row + (c >> 1) * (BM * 128);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              sts128(sO_row + ((static_cast<uint32_t>(h * 4 + q) << 4) ^ sw), pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]),
-                     pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]), pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]),
-                     pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]));
-          }
+          for (int q = 0; q < 4; ++q)
+            sts128(base + ((static_cast<uint32_t>((c & 1) * 4 + q) << 4) ^ sw), pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]),
+                   pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]), pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]),
+                   pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]));
         } else if (valid) {
+          if (p.out_f32) {
+            float* orow = reinterpret_cast<float*>(p.out) + o_elem + c * 32;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (h * kColsPerWG + c * 32 + q * 8 < p.headdim) {
-              uint4 v;
-              v.x = pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]);
-              v.y = pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]);
-              v.z = pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]);
-              v.w = pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(orow + (c * 32 + q * 8) * 2) = v;
+            for (int q = 0; q < 8; ++q)
+              if (c * 32 + q * 4 < p.headdim)
+                *reinterpret_cast<float4*>(orow + q * 4) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          } else {
+            uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + 2 * (o_elem + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (c * 32 + q * 8 < p.headdim) {
+                uint4 v;
+                v.x = pack2<kBF16>(f[q * 8 + 0], f[q * 8 + 1]);
+                v.y = pack2<kBF16>(f[q * 8 + 2], f[q * 8 + 3]);
+                v.z = pack2<kBF16>(f[q * 8 + 4], f[q * 8 + 5]);
+                v.w = pack2<kBF16>(f[q * 8 + 6], f[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(orow + q * 16) = v;
+              }
             }
           }
         }
       }
-      if (valid && h == 0)
+      if (valid)
         p.lse[(static_cast<int64_t>(it.batch) * p.nheads + it.head) * p.lse_stride + qrow] =
-            m_all * p.scale + __logf(l_all);
-      // Both accumulators of this tile have been read (wait::ld) by this warpgroup; the sibling must be done
-      // too before either stream's next PV (accumulate = 0) may overwrite them, and before xchg is reused.
+            m_used * p.scale + __logf(l);
+      // The accumulator has been read (wait::ld); the next item's first PV (accumulate = 0) is ordered behind the
+      // p_ready arrive of its first block, which these same threads perform.
       tr.rec(12, cnt);
       tc_fence_before();
-      if (stage) fence_proxy_async_smem();   // staged O rows -> visible to the TMA store
-      if constexpr (NH == 2) {
-        if (t == 0) named_bar_sync(1, 256); else named_bar_sync(2, 256);
-      }
-      if constexpr (C::kStageO) {
-        if (stage) {
-          mbar_arrive_a(BAR_I(o_staged, t));   // warp 3 stores the tile
-          ++st_cnt;
-          store_pending = true;   // stream 0 checks o_free before its next write to the P panel
-        }
+      if (stage) {
+        fence_proxy_async_smem();   // staged O rows -> visible to the TMA store
+        mbar_arrive_a(BAR_I(o_staged, t));   // warp 3 stores the tile
+        ++st_cnt;
+        store_pending = true;
       }
       tr.rec(9, cnt);
     }
@@ -767,43 +723,49 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     p.trace[8 * kTraceRecs * 2 + 2 * blockIdx.x + 1] = ns;
   }
 #endif
-  if (threadIdx.x == 0) {
-    // The last CTA to finish re-arms the ticket counter for the next launch that uses this slot (every CTA
-    // has drawn its last ticket before it gets here).
-    __threadfence();
-    if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
-      p.sched[0] = 0;
-      p.sched[1] = 0;
-      __threadfence();
-    }
-  }
 }
 
-// Ticket counters of the dynamic scheduler: {tickets drawn, CTAs finished} per slot, zero between launches (the
-// last CTA of a launch re-arms its slot).  Launches on one stream are serialised, so every stream gets ONE slot
-// (assigned on first use): kernels that may run concurrently -- different streams, or a graph replay next to
-// eager launches -- never share counters.  More than kSchedSlots distinct streams share the last slot.
-__device__ unsigned int g_sched[kSchedSlots * 2];
+// Ticket counters of the dynamic scheduler, one per LAUNCH.  Every launch takes the next slot of a ring and zeroes
+// it with a memset enqueued in front of the kernel on the same stream (a memset node when the stream is being
+// captured: every replay of the graph re-arms its own counter).  Launches that may run concurrently therefore never
+// share a counter, and a launch that aborted mid-way cannot leave state behind.  Eager launches recycle a ring of
+// kSchedEager slots (two live launches would have to be kSchedEager launches apart to collide); launches recorded
+// into CUDA graphs take slots of a second pool that is never recycled, because a graph may be replayed at any later
+// time next to anything else -- when that pool is exhausted the call fails instead of aliasing.
+constexpr unsigned kSchedEager = 4096, kSchedCapture = 12288;
+__device__ unsigned int g_sched[kSchedEager + kSchedCapture];
+static std::atomic<unsigned> g_next_eager{0}, g_next_capture{0};
 
-static unsigned int* sched_slot_of(cudaStream_t stream) {
-  static std::mutex mu;
-  static std::unordered_map<cudaStream_t, int> slots;
+static int sched_slot(cudaStream_t stream, unsigned int** out) {
   void* base = nullptr;
   if (cudaGetSymbolAddress(&base, g_sched) != cudaSuccess) {
     cudaGetLastError();
-    return nullptr;
+    return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaGetSymbolAddress(g_sched) failed");
   }
-  int slot;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = slots.find(stream);
-    if (it == slots.end()) {
-      const int next = static_cast<int>(slots.size());
-      it = slots.emplace(stream, next < kSchedSlots ? next : kSchedSlots - 1).first;
-    }
-    slot = it->second;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) {
+    cudaGetLastError();
+    cap = cudaStreamCaptureStatusNone;
   }
-  return static_cast<unsigned int*>(base) + 2 * slot;
+  unsigned idx;
+  if (cap == cudaStreamCaptureStatusActive) {
+    const unsigned n = g_next_capture.fetch_add(1);
+    if (n >= kSchedCapture)
+      return fail(BP_ERR_UNSUPPORTED,
+                  "bp_fmha_fwd: more than %u attention launches have been recorded into CUDA graphs by this process; "
+                  "the scheduler's per-launch counters for captured launches are exhausted", kSchedCapture);
+    idx = kSchedEager + n;
+  } else {
+    idx = g_next_eager.fetch_add(1) % kSchedEager;
+  }
+  unsigned int* slot = static_cast<unsigned int*>(base) + idx;
+  cudaError_t e = cudaMemsetAsync(slot, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaMemsetAsync(scheduler counter): %s", cudaGetErrorString(e));
+  }
+  *out = slot;
+  return BP_OK;
 }
 
 template <int DP, bool kBF16>
@@ -822,19 +784,40 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_items < sms ? p.num_items : sms;
   Params pp = p;
-  pp.sched = sched_slot_of(stream);
-  if (!pp.sched) return fail(BP_ERR_CUDA, "bp_fmha_fwd: cudaGetSymbolAddress(g_sched) failed");
+  if (int rc = sched_slot(stream, &pp.sched)) return rc;
   kern<<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, pp);
   return check_launch("bp_fmha_fwd launch");
 }
 
+static int g_out_f32 = 0;   // bp_debug_set_fmha_out_f32
+
 }  // namespace fmha
 }  // namespace bp
 
-// Debug hook (not part of the public ABI): when set, CTA 0 of the next launches writes its timeline here
-// (7 roles x kTraceRecs x 2 uint64).  Used by benchmarks/trace_fmha.py only.
+// Debug hooks (not part of the public ABI).
+//   bp_debug_set_trace: when set, CTA 0 of the next launches writes its timeline here (8 roles x kTraceRecs x 2
+//     uint64; -DBP_TRACE builds only).  Used by benchmarks/trace_kernel.py.
+//   bp_debug_set_fmha_out_f32: test mode of SURVEY.md §8c (T2): the next bp_fmha_fwd calls treat `out` as an fp32
+//     tensor with the same element strides and store O before the final 16-bit rounding.
+//   bp_debug_poison_fmha_sched: overwrite every scheduler counter with garbage (what an aborted launch could leave
+//     behind under the old per-stream scheme); tests check that later launches are unaffected.
 namespace bp { uint64_t* g_trace = nullptr; }
 extern "C" void bp_debug_set_trace(void* buf) { bp::g_trace = static_cast<uint64_t*>(buf); }
+extern "C" void bp_debug_set_fmha_out_f32(int on) { bp::fmha::g_out_f32 = on ? 1 : 0; }
+extern "C" int bp_debug_poison_fmha_sched(void* stream) {
+  void* base = nullptr;
+  if (cudaGetSymbolAddress(&base, bp::fmha::g_sched) != cudaSuccess) {
+    cudaGetLastError();
+    return bp::fail(BP_ERR_CUDA, "bp_debug_poison_fmha_sched: cudaGetSymbolAddress failed");
+  }
+  cudaError_t e = cudaMemsetAsync(base, 0x5a, sizeof(unsigned int) * (bp::fmha::kSchedEager + bp::fmha::kSchedCapture),
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return bp::fail(BP_ERR_CUDA, "bp_debug_poison_fmha_sched: %s", cudaGetErrorString(e));
+  }
+  return BP_OK;
+}
 
 extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
                            const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
@@ -899,6 +882,8 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: too many work items");
   p.num_items = p.num_pairs * batch * nheads;
   p.is_causal = is_causal ? 1 : 0;
+  p.out_f32 = fmha::g_out_f32;
+  p.sched = nullptr;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * fmha::kLog2e;
   p.trace = g_trace;

@@ -21,13 +21,15 @@ def _check_common(dropout_p, return_attn_probs, *tensors):
 
 
 def _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
-                        softmax_scale, causal):
+                        softmax_scale, causal, out_fp32=False):
     """q, k, v: (total, nheads, headdim) views with unit last stride (fmha_api.cpp:72-80).
-    Returns (out, softmax_lse (batch, nheads, max_seqlen_q rounded up to 16) fp32)."""
+    Returns (out, softmax_lse (batch, nheads, max_seqlen_q rounded up to 16) fp32).
+    `out_fp32` is the test mode of SURVEY.md §8c (T2): `out` is an fp32 tensor of q's shape and receives O before
+    the final 16-bit rounding (a debug switch of the library, not part of the C ABI)."""
     _lib.require_cuda(q, k, v, out, cu_seqlens_q, cu_seqlens_k)
     if q.dtype not in (torch.float16, torch.bfloat16):
         raise RuntimeError("FlashAttention only support fp16 and bf16 data type")      # fmha_api.cpp:215-217
-    if k.dtype != q.dtype or v.dtype != q.dtype or out.dtype != q.dtype:
+    if k.dtype != q.dtype or v.dtype != q.dtype or out.dtype != (torch.float32 if out_fp32 else q.dtype):
         raise RuntimeError("query, key, value and out must have the same dtype")       # fmha_api.cpp:218-221
     if cu_seqlens_q.dtype != torch.int32 or cu_seqlens_k.dtype != torch.int32:
         raise RuntimeError("cu_seqlens must have dtype int32")                         # fmha_api.cpp:222-223
@@ -47,14 +49,21 @@ def _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, 
         raise RuntimeError("head dimension must be a multiple of 8 and at most 128")   # fmha_api.cpp:245
     lse_stride = (max_seqlen_q + 15) // 16 * 16                                        # fmha_api.cpp:254,276
     lse = torch.empty((batch, nheads, lse_stride), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
     with torch.cuda.device(q.device):
-        st = _lib.load().bp_fmha_fwd(
-            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
-            cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr(),
-            batch, nheads, d, total_q, total_k, max_seqlen_q, max_seqlen_k,
-            q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
-            out.stride(0), out.stride(1), lse_stride, float(softmax_scale), int(bool(causal)),
-            _lib.dtype_code(q.dtype), _lib.stream_ptr(q.device))
+        if out_fp32:
+            lib.bp_debug_set_fmha_out_f32(1)
+        try:
+            st = lib.bp_fmha_fwd(
+                q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr(),
+                batch, nheads, d, total_q, total_k, max_seqlen_q, max_seqlen_k,
+                q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                out.stride(0), out.stride(1), lse_stride, float(softmax_scale), int(bool(causal)),
+                _lib.dtype_code(q.dtype), _lib.stream_ptr(q.device))
+        finally:
+            if out_fp32:
+                lib.bp_debug_set_fmha_out_f32(0)
     _lib.check(st, "bp_fmha_fwd")
     return out, lse
 
@@ -97,15 +106,15 @@ def flash_attn_unpadded_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, 
 
 
 def flash_attn_unpadded_with_lse(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
-                                 softmax_scale=None, causal=False):
+                                 softmax_scale=None, causal=False, out_fp32=False):
     """Like flash_attn_unpadded_func but also returns softmax_lse, as _flash_attn_forward does in the
     reference (flash_attn_interface.py:13-28)."""
     _check_common(0.0, False, q, k, v)
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** (-0.5)
-    out = torch.empty_like(q)
+    out = torch.empty(q.shape, dtype=torch.float32 if out_fp32 else q.dtype, device=q.device)
     return _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
-                               softmax_scale, causal)
+                               softmax_scale, causal, out_fp32=out_fp32)
 
 
 def flash_attn_func(qkv, cu_seqlens, dropout_p, max_s, softmax_scale=None, causal=False,

@@ -23,7 +23,7 @@ from transformers import GPT2Config
 
 from ..modules.block import Block
 from ..ops.fused_dense import FusedDense
-from ..ops.sense_mix import sense_mix
+from ..ops.sense_mix import sense_mix, sense_mix_table
 from .gpt import (CausalLMOutput, GPTModel, GPTPreTrainedModel, _init_weights, _no_tp, create_mlp_cls,
                   first_layer_norm, pad_vocab)
 
@@ -85,7 +85,8 @@ def create_nomix_block(config, expand_out=False, layer_idx=None, process_group=N
     mlp_cls = create_content_mlp_cls(config, layer_idx, expand_out, **factory_kwargs)
     norm_cls = partial(nn.LayerNorm, eps=config.layer_norm_epsilon, **factory_kwargs)
     block = Block(config.hidden_size, Identity, mlp_cls, norm_cls=norm_cls, prenorm=True,
-                  resid_dropout=config.resid_pdrop, fused_dropout_add_ln=getattr(config, "fused_dropout_add_ln", False))
+                  resid_dropout=config.resid_pdrop, fused_dropout_add_ln=getattr(config, "fused_dropout_add_ln", False),
+                  fuse_residual_add=getattr(config, "fuse_residual_add", "none"))
     block.layer_idx = layer_idx
     return block
 
@@ -148,8 +149,22 @@ class BackpackModel(GPTPreTrainedModel):
         self.contextualization_attn = ContextSelfAttn(self.num_content_vectors, config.n_embd, **factory_kwargs)
         # fused sense-mix follows use_flash_attn unless the config says otherwise
         self.fused_sense_mix = getattr(config, "fused_sense_mix", getattr(config, "use_flash_attn", False))
-        # optional inference-time table of sense vectors, see build_sense_table()
-        self.sense_table = None
+        # `config.use_sense_table`: in eval mode serve the sense vectors from a precomputed (vocab, nv, d) table and
+        # let the sense-mix kernel gather them by token id; see build_sense_table()
+        self.use_sense_table = bool(getattr(config, "use_sense_table", False))
+        self.register_buffer("sense_table", None, persistent=False)   # follows .to(); never in the state dict
+        self._sense_table_key = None
+
+    # ---- sense-vector table -------------------------------------------------------------------------------------
+    def _content_params_key(self):
+        """Identity + in-place version of every tensor the content model reads.  load_state_dict, optimizer steps and
+        the intervention scripts' weight edits all bump `_version`; .to() replaces the tensors."""
+        def version(p):
+            try:
+                return p._version
+            except RuntimeError:      # inference tensors do not track versions
+                return -1
+        return tuple((p.data_ptr(), version(p), p.dtype, p.device) for p in self.content_model.parameters())
 
     @torch.no_grad()
     def build_sense_table(self, chunk: int = 8192):
@@ -158,8 +173,9 @@ class BackpackModel(GPTPreTrainedModel):
         The content model is context-free: it sees the word embedding only (no positions, identity mixer;
         training/src/models/backpack.py:258, :125-143), so for inference `content_model(ids)` is a row gather
         from a (vocab, nv, d) table computed once with the very same kernels.  The analysis scripts of the
-        reference rely on the same fact (training/src/run_simlex.py:179-184).  The table must be rebuilt
-        (or dropped with `drop_sense_table()`) whenever the content-model weights change."""
+        reference rely on the same fact (training/src/run_simlex.py:179-184).  The table is a non-persistent
+        buffer (it follows `.to()` and is not part of the state dict) and is rebuilt automatically when a
+        content-model parameter has changed since it was built (`load_state_dict`, in-place edits)."""
         emb = self.embeddings.word_embeddings
         vocab, d, nv = emb.num_embeddings, self.config.n_embd, self.num_content_vectors
         table = torch.empty((vocab, nv, d), dtype=emb.weight.dtype, device=emb.weight.device)
@@ -170,18 +186,35 @@ class BackpackModel(GPTPreTrainedModel):
             table[start:start + ids.shape[1]] = self.content_model(ids)[0].transpose(0, 1)
         self.content_model.train(was_training)
         self.sense_table = table
+        self._sense_table_key = self._content_params_key()
         return table
 
     def drop_sense_table(self):
         self.sense_table = None
+        self._sense_table_key = None
+
+    def current_sense_table(self):
+        """The table if it is enabled and usable now (eval mode), (re)built when missing or stale; else None."""
+        if self.training or not (self.use_sense_table or self.sense_table is not None):
+            return None
+        emb = self.embeddings.word_embeddings.weight
+        if (self.sense_table is None or self._sense_table_key != self._content_params_key()
+                or self.sense_table.device != emb.device or self.sense_table.dtype != emb.dtype):
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the sense-vector table is missing or stale: call build_sense_table() before "
+                                   "capturing a CUDA graph")
+            self.build_sense_table()
+        return self.sense_table
 
     def content(self, input_ids, position_ids=None, inference_params=None):
-        """Sense vectors (b, nv, s, d): the content model, or a gather from the precomputed table."""
-        if self.sense_table is None or self.training:
+        """Sense vectors (b, nv, s, d): the content model, or (eval mode, table enabled) a gather from the table.
+        `forward` does not call this in table mode -- the kernel gathers by itself; this is for callers that want
+        the tensor (analysis scripts)."""
+        table = self.current_sense_table()
+        if table is None:
             return self.content_model(input_ids, position_ids, inference_params)
         b, s = input_ids.shape
-        flat = self.sense_table.view(self.sense_table.shape[0], -1)
-        rows = torch.nn.functional.embedding(input_ids, flat)                      # (b, s, nv*d)
+        rows = torch.nn.functional.embedding(input_ids, table.view(table.shape[0], -1))   # (b, s, nv*d)
         return rows.view(b, s, self.num_content_vectors, self.config.n_embd).transpose(1, 2)
 
     def sense_mix(self, contextl_hidden_states, content):
@@ -193,9 +226,15 @@ class BackpackModel(GPTPreTrainedModel):
     def forward(self, input_ids, position_ids=None, inference_params=None):
         contextl_hidden_states = self.gpt2_model(input_ids, position_ids=position_ids,
                                                  inference_params=inference_params)
-        content = self.content(input_ids, position_ids, inference_params)  # (b, nv, s, d)
         if self.fused_sense_mix:
+            table = self.current_sense_table()
+            if table is not None:
+                # C_l(x_j) rows are gathered from the table inside the kernel: no (b, s, nv, d) tensor in HBM
+                qk = self.contextualization_attn.project_qk(contextl_hidden_states)
+                return sense_mix_table(qk, table, input_ids, softmax_scale=self.contextualization_attn.softmax_scale)
+            content = self.content_model(input_ids, position_ids, inference_params)  # (b, nv, s, d)
             return self.sense_mix(contextl_hidden_states, content)
+        content = self.content(input_ids, position_ids, inference_params)  # (b, nv, s, d)
         contextualization = self.contextualization_attn(contextl_hidden_states)  # (b, nv, s, s)
         return torch.sum(contextualization @ content, dim=1)
 
@@ -233,4 +272,12 @@ def flash_config(**kwargs) -> BackpackConfig:
     cfg.fused_dense_gelu_dense = True
     cfg.fused_dropout_add_ln = True
     cfg.pad_vocab_size_multiple = 8
+    return cfg
+
+
+def serving_config(**kwargs) -> BackpackConfig:
+    """`flash_config` plus the inference-only sense-vector table (`use_sense_table`): in eval mode the content model
+    runs once per vocabulary item (at the first forward, or `build_sense_table()`) instead of once per token."""
+    cfg = flash_config(**kwargs)
+    cfg.use_sense_table = True
     return cfg

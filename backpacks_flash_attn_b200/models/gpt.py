@@ -86,7 +86,8 @@ def create_block(config, layer_idx=None, process_group=None, device=None, dtype=
     norm_cls = partial(nn.LayerNorm, eps=config.layer_norm_epsilon, **factory_kwargs)
     block = Block(config.hidden_size, mixer_cls, mlp_cls, norm_cls=norm_cls, prenorm=True,
                   resid_dropout=config.resid_pdrop,
-                  fused_dropout_add_ln=getattr(config, "fused_dropout_add_ln", False))
+                  fused_dropout_add_ln=getattr(config, "fused_dropout_add_ln", False),
+                  fuse_residual_add=getattr(config, "fuse_residual_add", "none"))
     block.layer_idx = layer_idx
     return block
 

@@ -15,7 +15,6 @@ Dropout and stochastic depth are identities in eval mode and not modelled; post-
 """
 from __future__ import annotations
 
-import os
 from functools import partial
 from typing import Optional
 
@@ -32,7 +31,7 @@ class Block(nn.Module):
 
     def __init__(self, dim, mixer_cls=None, mlp_cls=None, norm_cls=nn.LayerNorm, dropout_cls=nn.Dropout,
                  prenorm=True, resid_dropout=0., drop_path=0., fused_dropout_add_ln=False, return_residual=False,
-                 sequence_parallel=False):
+                 sequence_parallel=False, fuse_residual_add="none"):
         super().__init__()
         if not prenorm:
             raise RuntimeError("post-norm blocks are out of scope (GPT/Backpack use prenorm=True)")
@@ -46,7 +45,9 @@ class Block(nn.Module):
         # Measured in the Backpack-Small step (A/B in one run, profiles/): 24.9 ms with and without; the GEMM takes
         # over exactly the traffic the LayerNorm sheds (out_proj becomes HBM-bound at 105 us), so the default stays
         # the two-kernel path of the reference.
-        self.fuse_residual_add = os.environ.get("BP_FUSE_RESIDUAL", "none")   # "all" | "mixer" | "mlp" | "none"
+        if fuse_residual_add not in ("all", "mixer", "mlp", "none"):
+            raise ValueError('fuse_residual_add must be "all", "mixer", "mlp" or "none"')
+        self.fuse_residual_add = fuse_residual_add   # model factories pass `config.fuse_residual_add`
         if mixer_cls is None:
             mixer_cls = partial(MHA, num_heads=dim // 64)
         if mlp_cls is None:
@@ -74,8 +75,8 @@ class Block(nn.Module):
             raise RuntimeError("prenorm Block needs the residual stream")
         mixer_kwargs = mixer_kwargs if mixer_kwargs is not None else {}
         fuse = self.fused_dropout_add_ln and not self.training
-        fuse_mixer = fuse and self.fuse_residual_add in (True, "all", "mixer")
-        fuse_mlp = fuse and self.fuse_residual_add in (True, "all", "mlp")
+        fuse_mixer = fuse and self.fuse_residual_add in ("all", "mixer")
+        fuse_mlp = fuse and self.fuse_residual_add in ("all", "mlp")
         if (fuse_mixer and isinstance(self.mixer, MHA) and isinstance(self.mixer.out_proj, FusedDense)
                 and can_fuse_residual(hidden_states, self.mixer.out_proj.weight, residual)):
             residual = self.mixer(hidden_states, residual_out=residual, **mixer_kwargs)

@@ -16,6 +16,16 @@ import torch.nn.functional as F
 from .. import _lib
 
 
+def _dense_bias(bias: torch.Tensor | None, n: int) -> torch.Tensor | None:
+    """The C side reads `bias` as n dense elements: reject a wrongly sized bias, densify a strided one (e.g. a slice
+    of a fused parameter)."""
+    if bias is None:
+        return None
+    if bias.shape != (n,):
+        raise RuntimeError(f"bias must have shape ({n},), got {tuple(bias.shape)}")
+    return bias if bias.is_contiguous() else bias.contiguous()
+
+
 def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
                     activation: str = "gelu_tanh") -> torch.Tensor:
     """act(x @ weight.T + bias) through the hand-written tcgen05 GEMM (weight in nn.Linear layout)."""
@@ -27,6 +37,7 @@ def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
     n, k = weight.shape
     if x.shape[-1] != k:
         raise RuntimeError("shape mismatch between x and weight")
+    bias = _dense_bias(bias, n)
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
         raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
     x2 = x.reshape(-1, k)
@@ -54,6 +65,7 @@ def linear_bias_residual_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Ten
     if bias is not None and bias.dtype != x.dtype:
         raise RuntimeError("bias must have the activation dtype")
     n, k = weight.shape
+    bias = _dense_bias(bias, n)
     if x.shape[-1] != k or residual.shape[-1] != n or residual.numel() // n != x.numel() // k:
         raise RuntimeError("shape mismatch between x, weight and residual")
     if residual.dtype != torch.float32 or not residual.is_contiguous():

@@ -7,6 +7,9 @@ replaces `torch.sum(contextualization @ content, dim=1)` together with the softm
 materialised.  `content` may be ANY (b, nv, s, d) tensor with unit last stride -- in particular the
 transposed view the reference's content model returns (backpack.py:276) and the edited sense tensors
 the intervention wrappers build (training/src/models/intervened_models.py:78-101).
+
+`sense_mix_table` is the inference form: the sense vectors are gathered inside the kernel from a precomputed
+(vocab, nv, d) table by token id (C_l(x) is context-free, backpack.py:258), so no (b, s, nv, d) tensor exists.
 """
 from __future__ import annotations
 
@@ -15,42 +18,102 @@ import torch
 from .. import _lib
 
 
+def _prepare_qk(qk: torch.Tensor, softmax_scale):
+    if qk.dim() != 5 or qk.shape[2] != 2:
+        raise RuntimeError("qk must be (batch, seqlen, 2, nv, dk)")
+    if qk.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("sense_mix needs fp16/bf16 qk and content of the same dtype")
+    if torch.is_grad_enabled() and qk.requires_grad:
+        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+    dk = qk.shape[-1]
+    if softmax_scale is None:
+        softmax_scale = dk ** -0.5
+    if dk % 8 != 0:
+        # TMA needs 16-byte row strides.  Zero-padding the sense key width (e.g. d/nv = 12 at k = 64 senses of a
+        # 768-wide model) leaves every q.k dot product unchanged; the softmax scale keeps using the true width.
+        qk = torch.nn.functional.pad(qk, (0, (-dk) % 8))
+    if not qk.is_contiguous():
+        qk = qk.contiguous()
+    return qk, float(softmax_scale)
+
+
+def _out_buffer(b, s, d, dtype, device, out_fp32: bool):
+    """`out_fp32` is the test mode of SURVEY.md §8c (T2): the accumulator is stored before the 16-bit rounding."""
+    return torch.empty((b, s, d), dtype=torch.float32 if out_fp32 else dtype, device=device)
+
+
+class _F32Out:
+    """Context manager around the library's debug switch (not part of the C ABI)."""
+
+    def __init__(self, hook: str, on: bool):
+        self.fn = getattr(_lib.load(), hook) if on else None
+
+    def __enter__(self):
+        if self.fn is not None:
+            self.fn(1)
+
+    def __exit__(self, *exc):
+        if self.fn is not None:
+            self.fn(0)
+        return False
+
+
 def sense_mix(qk: torch.Tensor, content: torch.Tensor, softmax_scale: float | None = None,
-              return_lse: bool = False):
+              return_lse: bool = False, out_fp32: bool = False):
     """qk: (batch, seqlen, 2, nv, dk) -- ContextSelfAttn.Wqkv output viewed as at backpack.py:112-116;
     content: (batch, nv, seqlen, d).  Returns (batch, seqlen, d) [and lse (batch, nv, seqlen) fp32]."""
     _lib.require_cuda(qk, content)
-    if qk.dim() != 5 or qk.shape[2] != 2:
-        raise RuntimeError("qk must be (batch, seqlen, 2, nv, dk)")
-    if qk.dtype not in (torch.float16, torch.bfloat16) or content.dtype != qk.dtype:
+    qk, scale = _prepare_qk(qk, softmax_scale)
+    if content.dtype != qk.dtype:
         raise RuntimeError("sense_mix needs fp16/bf16 qk and content of the same dtype")
     b, s, _, nv, dk = qk.shape
     if content.dim() != 4 or content.shape[:3] != (b, nv, s):
         raise RuntimeError(f"content must be (batch, nv, seqlen, d) = ({b}, {nv}, {s}, d), got {tuple(content.shape)}")
-    if torch.is_grad_enabled() and (qk.requires_grad or content.requires_grad):
+    if torch.is_grad_enabled() and content.requires_grad:
         raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
     d = content.shape[3]
-    if dk % 8 != 0:
-        # TMA needs 16-byte row strides.  Zero-padding the sense key width (e.g. d/nv = 12 at k = 64 senses of a
-        # 768-wide model) leaves every q.k dot product unchanged; the softmax scale keeps using the true width.
-        if softmax_scale is None:
-            softmax_scale = dk ** -0.5
-        qk = torch.nn.functional.pad(qk, (0, (-dk) % 8))
-        dk = qk.shape[-1]
-    if not qk.is_contiguous():
-        qk = qk.contiguous()
     if content.stride(3) != 1 or any(st % 8 for st in content.stride()[:3]) or content.data_ptr() % 16:
         content = content.contiguous()
-    scale = float(softmax_scale) if softmax_scale is not None else dk ** -0.5
     lse = torch.empty((b, nv, s), dtype=torch.float32, device=qk.device)
-    out = torch.empty((b, s, d), dtype=qk.dtype, device=qk.device)
+    out = _out_buffer(b, s, d, qk.dtype, qk.device, out_fp32)
     lib = _lib.load()
     dt = _lib.dtype_code(qk.dtype)
-    with torch.cuda.device(qk.device):
+    with torch.cuda.device(qk.device), _F32Out("bp_debug_set_sense_out_f32", out_fp32):
         stream = _lib.stream_ptr(qk.device)
         _lib.check(lib.bp_sense_lse_fwd(qk.data_ptr(), lse.data_ptr(), b, s, nv, dk, scale, dt, stream),
                    "bp_sense_lse_fwd")
         _lib.check(lib.bp_sense_mix_fwd(qk.data_ptr(), content.data_ptr(), lse.data_ptr(), out.data_ptr(),
                                         b, s, nv, dk, d, content.stride(0), content.stride(1), content.stride(2),
                                         scale, dt, stream), "bp_sense_mix_fwd")
+    return (out, lse) if return_lse else out
+
+
+def sense_mix_table(qk: torch.Tensor, table: torch.Tensor, input_ids: torch.Tensor,
+                    softmax_scale: float | None = None, return_lse: bool = False, out_fp32: bool = False):
+    """qk: (batch, seqlen, 2, nv, dk); table: (vocab, nv, d) sense vectors of every vocabulary item
+    (`BackpackModel.build_sense_table()`); input_ids: (batch, seqlen) int64.  Equivalent to
+    `sense_mix(qk, table[input_ids].transpose(1, 2))` without ever forming that tensor."""
+    _lib.require_cuda(qk, table, input_ids)
+    qk, scale = _prepare_qk(qk, softmax_scale)
+    b, s, _, nv, dk = qk.shape
+    if table.dtype != qk.dtype:
+        raise RuntimeError("sense_mix_table needs fp16/bf16 qk and table of the same dtype")
+    if table.dim() != 3 or table.shape[1] != nv or not table.is_contiguous():
+        raise RuntimeError(f"table must be a contiguous (vocab, nv, d) = (vocab, {nv}, d) tensor, got {tuple(table.shape)}")
+    if input_ids.shape != (b, s) or input_ids.dtype != torch.int64:
+        raise RuntimeError(f"input_ids must be int64 of shape ({b}, {s})")
+    if not input_ids.is_contiguous():
+        input_ids = input_ids.contiguous()
+    vocab, _, d = table.shape
+    lse = torch.empty((b, nv, s), dtype=torch.float32, device=qk.device)
+    out = _out_buffer(b, s, d, qk.dtype, qk.device, out_fp32)
+    lib = _lib.load()
+    dt = _lib.dtype_code(qk.dtype)
+    with torch.cuda.device(qk.device), _F32Out("bp_debug_set_sense_out_f32", out_fp32):
+        stream = _lib.stream_ptr(qk.device)
+        _lib.check(lib.bp_sense_lse_fwd(qk.data_ptr(), lse.data_ptr(), b, s, nv, dk, scale, dt, stream),
+                   "bp_sense_lse_fwd")
+        _lib.check(lib.bp_sense_mix_table_fwd(qk.data_ptr(), table.data_ptr(), input_ids.data_ptr(), lse.data_ptr(),
+                                              out.data_ptr(), b, s, nv, dk, d, vocab, scale, dt, stream),
+                   "bp_sense_mix_table_fwd")
     return (out, lse) if return_lse else out

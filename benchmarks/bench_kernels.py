@@ -59,7 +59,7 @@ def report(name, t_med, t_min, flops, nbytes, extra=None):
     return rec
 
 
-def bench_fmha(iters, b=32, s=1024, h=12, d=64):
+def bench_fmha(iters, b=32, s=1024, h=12, d=64, comparators=True):
     from backpacks_flash_attn_b200.flash_attn_interface import flash_attn_unpadded_qkvpacked_func
     nvar = 3  # 3 x 75 MB of qkv + outputs > 126 MB L2
     qkvs = [torch.randn(b * s, 3, h, d, device="cuda").bfloat16() for _ in range(nvar)]
@@ -68,7 +68,40 @@ def bench_fmha(iters, b=32, s=1024, h=12, d=64):
     t_med, t_min = time_fn(fn, nvar, iters)
     flops = 4 * b * h * s * s * d / 2
     nbytes = 4 * b * s * h * d * 2 + 4 * b * h * s
-    return report(f"fmha_fwd b{b} h{h} s{s} d{d} causal bf16", t_med, t_min, flops, nbytes)
+    rec = report(f"fmha_fwd b{b} h{h} s{s} d{d} causal bf16", t_med, t_min, flops, nbytes)
+    if comparators:
+        fmha_comparators(iters, qkvs, b, s, h, d, flops, nbytes)
+    return rec
+
+
+def fmha_comparators(iters, qkvs, b, s, h, d, flops, nbytes):
+    """On-box yard-sticks SURVEY.md §8c allows as INFORMATIVE speed comparators (they are other projects' kernels,
+    not the reference fork): torch SDPA with the cuDNN / flash backends, and the site-packages flash_attn 2.8 (FA-2,
+    mma.sync).  Same inputs, same timing loop."""
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    views = [q.view(b, s, 3, h, d).permute(2, 0, 3, 1, 4) for q in qkvs]     # (3, b, h, s, d) strided views
+    for name, backend in (("torch SDPA, cuDNN backend", SDPBackend.CUDNN_ATTENTION),
+                          ("torch SDPA, flash backend", SDPBackend.FLASH_ATTENTION)):
+        try:
+            def fn(i, backend=backend):
+                with sdpa_kernel(backend):
+                    return F.scaled_dot_product_attention(views[i][0], views[i][1], views[i][2], is_causal=True)
+            t, tm = time_fn(fn, len(qkvs), iters)
+            report(f"  (comparator, informative) {name}", t, tm, flops, nbytes)
+        except Exception as e:  # backend not available for this shape / build
+            print(json.dumps({"kernel": f"(comparator) {name}", "unavailable": str(e)[:200]}))
+    try:
+        import importlib
+        sys_path = list(sys.path)
+        sys.path = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]   # the site-packages flash_attn, not a local dir
+        fa = importlib.import_module("flash_attn")
+        sys.path = sys_path
+        packed = [q.view(b, s, 3, h, d) for q in qkvs]
+        t, tm = time_fn(lambda i: fa.flash_attn_qkvpacked_func(packed[i], causal=True), len(qkvs), iters)
+        report(f"  (comparator, informative) site-packages flash_attn {getattr(fa, '__version__', '?')} (FA-2)", t, tm, flops, nbytes)
+    except Exception as e:
+        print(json.dumps({"kernel": "(comparator) site-packages flash_attn", "unavailable": str(e)[:200]}))
 
 
 def bench_sense(iters, b=64, s=1024, nv=16, d=768):
@@ -94,6 +127,17 @@ def bench_sense(iters, b=64, s=1024, nv=16, d=768):
     t2, _ = time_fn(f2, 1, iters)
     report("  sense_lse pass", t1, t1, b * nv * s * s * (d // nv), 2 * b * s * d * 2)
     report("  sense_mix pass", t2, t2, b * s * s * d * (1 + nv), nbytes)
+    # table mode: the sense vectors are gathered inside the kernel from a (vocab, nv, d) table (1.23 GB at Small size)
+    vocab = 50264
+    table = torch.randn(vocab, nv, d, device="cuda").bfloat16()
+    ids = torch.randint(0, 50257, (b, s), device="cuda")
+    f3 = lambda i: lib.bp_sense_mix_table_fwd(qk.data_ptr(), table.data_ptr(), ids.data_ptr(), lse.data_ptr(),
+                                              out.data_ptr(), b, s, nv, d // nv, d, vocab, scale, 1, st)
+    t3, _ = time_fn(f3, 1, iters)
+    report("  sense_mix pass, table mode (gather inside the kernel)", t3, t3, b * s * s * d * (1 + nv), nbytes)
+    f4 = lambda i: torch.nn.functional.embedding(ids, table.view(vocab, -1))
+    t4, _ = time_fn(f4, 1, iters)
+    report("  (for comparison: ATen gather that materialises (b, s, nv, d))", t4, t4, 0, 2 * nv * b * s * d * 2)
     return rec
 
 

@@ -22,14 +22,14 @@ if which == "fmha":
     qkv = torch.randn(b * s, 3, h, d, device="cuda").bfloat16()
     cu = torch.arange(0, (b + 1) * s, s, dtype=torch.int32, device="cuda")
     run = lambda: flash_attn_unpadded_qkvpacked_func(qkv, cu, s, 0.0, causal=True)
-    names = ["prod0", "mma0", "mma1", "sm00", "sm01", "sm10", "sm11", "prod1"]
+    names = ["prod", "mma0", "mma1", "sm0", "sm1", "-", "-", "-"]
 else:
     from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
     b, s, nv, d = 64, 1024, 16, 768
     qk = torch.randn(b, s, 2, nv, d // nv, device="cuda").bfloat16()
     content = torch.randn(b, s, nv, d, device="cuda").bfloat16().transpose(1, 2)
     run = lambda: sense_mix(qk, content)
-    names = ["prodC", "mma", "sm0", "sm1", "-", "-", "-", "-"]
+    names = ["prodC", "issue", "sm0", "sm1", "-", "-", "-", "-"]
 for _ in range(3):
     run()
 torch.cuda.synchronize()

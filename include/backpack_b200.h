@@ -9,7 +9,8 @@
  *   fused_dense_lib.linear_gelu_forward       csrc/fused_dense_lib/fused_dense.cpp:88-142 -> bp_linear_bias_act_fwd
  *   rotary_emb.apply_rotary                   csrc/rotary/rotary.cpp:12-33              -> bp_rotary_qk_inplace
  *   (no reference kernel; eager PyTorch at    training/src/models/backpack.py:111-122,313) -> bp_sense_lse_fwd,
- *                                                                                            bp_sense_mix_fwd
+ *                                                                                            bp_sense_mix_fwd,
+ *                                                                                            bp_sense_mix_table_fwd
  *
  * Conventions
  *   - plain C types only: device pointers, sizes, strides (in ELEMENTS), a cudaStream_t passed as void*.
@@ -88,6 +89,21 @@ int bp_sense_mix_fwd(const void* qk, const void* content, const float* lse, void
                      int32_t batch, int32_t seqlen, int32_t nv, int32_t dk, int32_t d,
                      int64_t c_batch_stride, int64_t c_sense_stride, int64_t c_row_stride,
                      float softmax_scale, int32_t dtype, void* stream);
+
+/* Backpack sense-mix, pass 2, with the sense vectors gathered from a precomputed table inside the kernel:
+ *   out[b,i,:] = sum_l sum_{j<=i} softmax_j(scale q_li.k_lj) * table[input_ids[b,j], l, :]
+ * C_l(x) depends on the token id only (BackpackContentModule sees the word embedding without positions and has
+ * an identity mixer: training/src/models/backpack.py:258, 125-143; the reference's analysis scripts rely on the
+ * same fact, training/src/run_simlex.py:179-184), so for inference content_model(input_ids) is a row gather from a
+ * (vocab, nv, d) table computed once with the same kernels.  The gather is done by TMA (tile::gather4) straight into
+ * the operand tiles: no (batch, seqlen, nv, d) tensor is ever written to or read from HBM.
+ *   table     : (vocab, nv, d) contiguous, same dtype as qk.   input_ids : (batch, seqlen) int64 contiguous;
+ *               rows of ids outside [0, vocab) read as zero vectors (TMA out-of-bounds fill).
+ *   lse       : from bp_sense_lse_fwd.   out : (batch, seqlen, d) contiguous.
+ */
+int bp_sense_mix_table_fwd(const void* qk, const void* table, const int64_t* input_ids, const float* lse, void* out,
+                           int32_t batch, int32_t seqlen, int32_t nv, int32_t dk, int32_t d, int32_t vocab,
+                           float softmax_scale, int32_t dtype, void* stream);
 
 /* Residual add + LayerNorm forward, eval mode (replaces dropout_add_ln_fwd with dropout_p = 0, no
  * rowscale/colscale/subset; csrc/layer_norm/ln_api.cpp:83-251, ln_fwd_kernels.cuh:98-188).

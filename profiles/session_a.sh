@@ -1,0 +1,25 @@
+#!/bin/bash
+# GPU session A of a round (run through gpurun from the repo root):  bash profiles/session_a.sh <round>
+# sanity of every kernel in isolated processes -> GPU test suite -> stand-alone kernel timings of the production
+# library and of the tagged variant builds present -> config-5 sweep -> timeline traces -> the bench line.
+set -u
+R=${1:-r02}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $O/${R}_gpu.txt 2>&1
+echo "== sanity"; timeout 900 python benchmarks/sanity.py --tag dbg > $O/${R}_sanity.log 2>&1; tail -16 $O/${R}_sanity.log | cut -c1-230
+echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -rf --tb=short > $O/${R}_pytest.log 2>&1; tail -25 $O/${R}_pytest.log | cut -c1-200
+echo "== kernels"
+for tag in "" p2 p4 stag; do
+  [ -n "$tag" ] && [ ! -f backpacks_flash_attn_b200/libbackpack_b200_$tag.so ] && continue
+  which="fmha,sense"; [ -z "$tag" ] && which="fmha,sense,ln,gemm"
+  BP_LIB_TAG=$tag timeout 600 python benchmarks/bench_kernels.py --which $which > $O/${R}_kernels_${tag:-prod}.jsonl 2>&1
+  echo "-- ${tag:-prod}"; cut -c1-150 $O/${R}_kernels_${tag:-prod}.jsonl | grep -v "^Traceback" | head -16
+done
+echo "== sweep"; timeout 900 python benchmarks/sweep.py > $O/${R}_sweep.jsonl 2>&1; cut -c1-120 $O/${R}_sweep.jsonl | head -24
+if [ -f backpacks_flash_attn_b200/libbackpack_b200_trace.so ]; then
+  echo "== traces"
+  BP_LIB_TAG=trace timeout 300 python benchmarks/trace_kernel.py fmha > $O/${R}_trace_fmha.txt 2>&1; tail -2 $O/${R}_trace_fmha.txt
+  BP_LIB_TAG=trace timeout 300 python benchmarks/trace_kernel.py sense > $O/${R}_trace_sense.txt 2>&1; tail -2 $O/${R}_trace_sense.txt
+fi
+echo "== bench"; timeout 1200 python bench.py > $O/${R}_bench_n1.json 2> $O/${R}_bench.err; tail -3 $O/${R}_bench.err; cut -c1-400 $O/${R}_bench_n1.json

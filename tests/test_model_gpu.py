@@ -86,27 +86,92 @@ def test_fused_and_eager_sense_mix_agree_inside_the_model():
         assert (got2.float() - got.float()).abs().max() > 1e-3
 
 
-def test_sense_table_is_equivalent_to_the_content_model():
-    """C(x) depends on the token id only, so a (vocab, nv, d) table gathered by id must
-    reproduce content_model(ids) and leave the logits unchanged."""
-    fused, _ = _pair(dict(n_embd=384, n_head=6, n_layer=2, n_positions=512))
+def _oracle_weights(model, dims):
+    from oracle import backpack_oracle as O
+    ocfg = O.OracleConfig(**dims)
+    names = O.canonical_param_shapes(ocfg)
+    # the model's own (bf16-rounded) weights, fp32 math: the oracle on identical inputs
+    return ocfg, {k: v.detach().float() for k, v in model.state_dict().items() if k in names}
+
+
+def test_sense_table_matches_the_oracle_content_vectors():
+    """SURVEY.md §8f rank 1 against the ORACLE (not against this library): every row of the (vocab, nv, d) table must
+    be oracle.content_vectors of that token (restating BackpackContentModule.forward, backpack.py:251-276), under the
+    model-level rule (error < 3x the eager bf16 path's error, tests/models/test_gpt.py:60,70)."""
+    from oracle import backpack_oracle as O
+    dims = dict(n_embd=384, n_head=6, n_layer=2, n_positions=512)
+    fused, eager = _pair(dims)
+    ocfg, w = _oracle_weights(fused, dims)
     ids = torch.randint(0, 50257, (3, 200), device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+    ids[0, :3] = torch.tensor([0, 50256, 50263], device="cuda")    # first, last real, last padded vocabulary row
     with torch.inference_mode():
-        base_content = fused.transformer.content_model(ids)
-        base_logits = fused(ids).logits
         table = fused.transformer.build_sense_table(chunk=4096)
         assert table.shape == (50264, 16, 384)
-        got_content = fused.transformer.content(ids)
-        got_logits = fused(ids).logits
-        fused.transformer.drop_sense_table()
-        again = fused(ids).logits
-    assert got_content.shape == base_content.shape and got_content.stride() == base_content.stride()
-    # identical kernels on identical rows; a library GEMM may pick another tile shape for another batch size,
-    # so allow one bf16 ulp of the O(1) values
-    assert (got_content.float() - base_content.float()).abs().max() <= 2 ** -6
-    assert (got_logits.float() - base_logits.float()).abs().max() <= 0.06
-    assert (got_logits.argmax(-1) == base_logits.argmax(-1)).float().mean() > 0.995
-    assert torch.equal(again, base_logits)
+        ref = O.content_vectors(ids, w, ocfg, fused_ln=True)                 # (b, nv, s, d) fp32
+        content_e = eager.transformer.content_model(ids)
+        got = table[ids].transpose(1, 2)
+        _rule(got, content_e, ref, "sense table rows vs oracle.content_vectors")
+        got_content = fused.transformer.content(ids)                          # the analysis-script accessor
+        assert got_content.shape == ref.shape and torch.equal(got_content, got)
+        assert list(got_content.stride()) == list(fused.transformer.content_model(ids).stride())
+
+
+def test_sense_table_model_forward_matches_the_oracle():
+    """The table-mode forward (`config.use_sense_table`: gather inside the sense-mix kernel, content model skipped)
+    against the fp32 oracle of the whole model, next to the eager bf16 path; and against the non-table forward."""
+    from oracle import backpack_oracle as O
+    from backpacks_flash_attn_b200.models.backpack import serving_config
+    dims = dict(n_embd=384, n_head=6, n_layer=2, n_positions=512)
+    fused, eager = _pair(dims)
+    served = name_seeded_(BackpackLMHeadModel(serving_config(**dims)).eval()).to("cuda", torch.bfloat16)
+    assert served.transformer.use_sense_table and "transformer.sense_table" not in served.state_dict()
+    ocfg, w = _oracle_weights(fused, dims)
+    ids = torch.randint(0, 50257, (2, 300), device="cuda", generator=torch.Generator("cuda").manual_seed(8))
+    with torch.inference_mode():
+        before = dict(_lib.launch_counts)
+        hid_t = served.transformer(ids)                # builds the table on first use
+        assert _lib.launch_counts.get("bp_sense_mix_table_fwd", 0) == before.get("bp_sense_mix_table_fwd", 0) + 1
+        hid, hid_e = fused.transformer(ids), eager.transformer(ids)
+        ref = O.backpack_hidden(ids, w, ocfg, fused_ln=True)
+        _rule(hid_t, hid_e, ref, "table-mode hidden vs oracle")
+        _rule(served(ids).logits[:, -1], eager(ids).logits[:, -1], O.backpack_logits(ids, w, ocfg, fused_ln=True)[:, -1],
+              "table-mode last-position logits vs oracle")
+        # same kernels on the same rows: only a library GEMM picking another tile shape for another M can differ
+        assert (hid_t.float() - hid.float()).abs().max() <= 0.06
+        # training mode never uses the table
+        served.train()
+        assert served.transformer.current_sense_table() is None
+        served.eval()
+        assert served.transformer.current_sense_table() is not None
+
+
+def test_sense_table_follows_weight_edits_and_device_moves():
+    """the table must not serve stale vectors after load_state_dict / in-place weight edits (what the
+    intervention scripts do to the content weights) and must follow .to()."""
+    from backpacks_flash_attn_b200.models.backpack import serving_config
+    dims = dict(n_embd=128, n_head=2, n_layer=1, n_positions=128)
+    model = name_seeded_(BackpackLMHeadModel(serving_config(**dims)).eval()).to("cuda", torch.bfloat16)
+    ids = torch.randint(0, 50257, (2, 128), device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    with torch.inference_mode():
+        a = model.transformer(ids).clone()
+        t0 = model.transformer.sense_table
+        assert model.transformer(ids) is not None and model.transformer.sense_table is t0     # cached
+    with torch.no_grad():
+        model.transformer.content_model.final_mlp.fc2.weight.mul_(0.5)                       # in-place edit
+        model.transformer.content_model.final_mlp.fc2.bias.mul_(0.5)
+    with torch.inference_mode():
+        b = model.transformer(ids)
+        assert model.transformer.sense_table is not t0                                       # rebuilt
+        assert (b.float() - 0.5 * a.float()).abs().max() < 0.05 * a.float().abs().max()      # C halves => output halves
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["transformer.content_model.final_mlp.fc2.weight"] *= 2.0
+    sd["transformer.content_model.final_mlp.fc2.bias"] *= 2.0
+    model.load_state_dict(sd)
+    with torch.inference_mode():
+        c = model.transformer(ids)
+        assert (c.float() - a.float()).abs().max() < 0.03 * a.float().abs().max() + 0.05
+    model.transformer.drop_sense_table()
+    assert model.transformer.sense_table is None
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
@@ -137,3 +202,20 @@ def test_graphed_forward_replays_the_same_kernels():
             assert torch.equal(out, model(ids).logits)
         with pytest.raises(RuntimeError, match="captured for ids of shape"):
             fwd(ids_a[:, :128])
+
+
+def test_graphed_forward_with_sense_table():
+    """The serving configuration (table gathered inside the kernel) under a CUDA graph: build the table first,
+    capture, replay for new ids."""
+    from backpacks_flash_attn_b200.models.backpack import BackpackLMHeadModel, serving_config
+    from backpacks_flash_attn_b200.utils.graph import GraphedForward
+    cfg = serving_config(n_embd=128, n_head=2, n_layer=2, n_positions=512)
+    model = name_seeded_(BackpackLMHeadModel(cfg).eval()).to("cuda", torch.bfloat16)
+    g = torch.Generator().manual_seed(11)
+    ids_a = torch.randint(0, 50257, (2, 384), generator=g).cuda()
+    ids_b = torch.randint(0, 50257, (2, 384), generator=g).cuda()
+    with torch.inference_mode():
+        model.transformer.build_sense_table()
+        fwd = GraphedForward(model, ids_a)
+        for ids in (ids_a, ids_b):
+            assert torch.equal(fwd(ids).clone(), model(ids).logits)

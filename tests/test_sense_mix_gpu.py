@@ -108,9 +108,97 @@ def test_sense_mix_rejects_bad_arguments():
                   torch.zeros(1, 4, 64, 32, device="cuda", dtype=torch.bfloat16))
 
 
-@pytest.mark.parametrize("s", [128, 512])
+@pytest.mark.parametrize("s", [128, 512, 1024])
 def test_sense_mix_k64_odd_key_width(s):
     """BASELINE config 5: k = 64 senses of a 768-wide model => sense key width 12 (zero-padded to 16 for TMA)."""
     qk, content = _inputs(2, s, 64, 768, torch.bfloat16, seed=s)
     assert qk.shape[-1] == 12
     _check(qk, content)
+
+
+def _per_batch_check(qk, content):
+    """2x rule + LSE bound with the oracle evaluated one batch element at a time (alpha is (nv, s, s) fp32 per
+    element: 4.3 GB at k = 64, s = 4096)."""
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    out, lse = sense_mix(qk, content, return_lse=True)
+    for i in range(qk.shape[0]):
+        ref, lse_ref = O.sense_mix_fp32_ref(qk[i:i + 1], content[i:i + 1])
+        eager = O.sense_mix_eager(qk[i:i + 1], content[i:i + 1])
+        err, err_eager = O.max_abs(out[i:i + 1], ref), O.max_abs(eager, ref)
+        assert O.max_abs(lse[i:i + 1], lse_ref) < 1e-3
+        assert err <= 2 * err_eager + 1e-5, f"batch {i}: max err {err:.3e} vs eager {err_eager:.3e}"
+        assert O.mean_abs(out[i:i + 1], ref) <= 2 * O.mean_abs(eager, ref) + 1e-6
+        del ref, lse_ref, eager
+
+
+@pytest.mark.parametrize("nv", [4, 16, 64])
+@pytest.mark.parametrize("s,b", [(2048, 8), (4096, 4), (1024, 16)])
+def test_sense_mix_config5_cells(s, b, nv):
+    """Every sense-mix cell of BASELINE config 5 that profiles/ reports a time for (seq x senses at 16384 tokens,
+    d = 768); the s <= 1024 cells at k in {4, 16} are also covered by test_sense_mix_matches_oracle."""
+    qk, content = _inputs(b, s, nv, 768, torch.bfloat16, seed=s + nv)
+    _per_batch_check(qk, content)
+
+
+@pytest.mark.parametrize("dtype,bound", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("s,nv,d", [(512, 16, 768), (257, 4, 768), (1024, 8, 128)])
+def test_sense_mix_fp32_output_mode(s, nv, d, dtype, bound):
+    """T2 of SURVEY.md §8c for the sense-mix: accumulator stored before the final 16-bit rounding, against the fp32
+    oracle on identical 16-bit inputs.  As in the attention kernel the remaining error is the rounding of P to the
+    16-bit MMA operand type (rel. 2^-12 for fp16, 2^-9 for bf16), here summed over nv senses whose outputs add up
+    (independent roundings: the bound grows like sqrt(nv)).  With fp16 operands and 16 senses that is ~1e-3, the
+    north-star bar; the mean error is far below it for both types.  The production output must be exactly the
+    rounding of the test-mode output."""
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    qk, content = _inputs(2, s, nv, d, dtype, seed=3 * s + nv)
+    out32, lse = sense_mix(qk, content, return_lse=True, out_fp32=True)
+    assert out32.dtype == torch.float32
+    ref, lse_ref = O.sense_mix_fp32_ref(qk, content)
+    err, mean = O.max_abs(out32, ref), O.mean_abs(out32, ref)
+    print(f"sense-mix fp32-output mode s{s} k{nv} d{d} {dtype}: max|err| {err:.2e} mean {mean:.2e}")
+    assert err < bound * (nv / 16) ** 0.5 + 1e-4, err
+    assert mean < 1e-3
+    assert O.max_abs(lse, lse_ref) < 1e-3
+    assert torch.equal(sense_mix(qk, content), out32.to(dtype))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("s,nv,d,vocab", [(1024, 16, 768, 3000), (200, 16, 768, 517), (257, 4, 768, 64), (512, 8, 128, 1000),
+                                          (128, 64, 768, 300)])
+def test_sense_mix_table_gathers_inside_the_kernel(s, nv, d, vocab, dtype):
+    """bp_sense_mix_table_fwd == bp_sense_mix_fwd on the gathered tensor, bit for bit, and within the 2x rule of the
+    fp32 oracle evaluated on table[ids]."""
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix, sense_mix_table
+    g = torch.Generator(device="cuda").manual_seed(s + vocab)
+    b = 3
+    qk = torch.randn(b, s, 2, nv, d // nv, device="cuda", generator=g).to(dtype)
+    table = torch.randn(vocab, nv, d, device="cuda", generator=g).to(dtype)
+    ids = torch.randint(0, vocab, (b, s), device="cuda", generator=g)
+    ids[0, :4] = torch.tensor([0, vocab - 1, 0, vocab - 1], device="cuda")     # first / last table rows
+    content = table[ids].transpose(1, 2)                                      # (b, nv, s, d) view, what the table replaces
+    out, lse = sense_mix_table(qk, table, ids, return_lse=True)
+    out_t, lse_t = sense_mix(qk, content, return_lse=True)
+    assert torch.equal(lse, lse_t)
+    assert torch.equal(out, out_t)
+    ref, lse_ref = O.sense_mix_fp32_ref(qk, content)
+    eager = O.sense_mix_eager(qk, content)
+    assert O.max_abs(out, ref) <= 2 * O.max_abs(eager, ref) + 1e-5
+    assert O.max_abs(lse, lse_ref) < 1e-3
+    first = sense_mix_table(qk, table, ids)
+    for _ in range(3):
+        assert torch.equal(first, sense_mix_table(qk, table, ids))
+
+
+def test_sense_mix_table_rejects_bad_arguments():
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix_table
+    qk = torch.zeros(1, 64, 2, 16, 48, device="cuda", dtype=torch.bfloat16)
+    table = torch.zeros(100, 16, 768, device="cuda", dtype=torch.bfloat16)
+    ids = torch.zeros(1, 64, device="cuda", dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="int64"):
+        sense_mix_table(qk, table, ids.int())
+    with pytest.raises(RuntimeError, match="table must be"):
+        sense_mix_table(qk, table[:, :8], ids)
+    with pytest.raises(RuntimeError, match="same dtype"):
+        sense_mix_table(qk, table.half(), ids)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sense_mix_table(qk, table, ids.cpu())
