@@ -57,6 +57,10 @@ constexpr int kPoly = BP_FMHA_POLY;
 #define BP_FMHA_STAGGER 0
 #endif
 constexpr int kStagger = BP_FMHA_STAGGER;   // cycles query tile 1 holds back its very first block (debug knob)
+#ifndef BP_FMHA_MUFU_LOCK
+#define BP_FMHA_MUFU_LOCK 1
+#endif
+constexpr bool kMufuLock = BP_FMHA_MUFU_LOCK != 0;   // serialise the exponential phases of the two warps of a sub-partition
 
 template <int DP>
 struct Cfg {
@@ -115,6 +119,7 @@ struct Barriers {
   uint64_t p_ready[2], pv_done[2];         // [tile]
   uint64_t item_full[kItemSlots], item_empty[kItemSlots];
   uint64_t o_staged[2], o_free[2];         // [tile]: O tile staged in smem / read out by the TMA store
+  uint32_t mufu_busy[2][4];                // [tile][warp & 3]: that warp is inside its exponential phase
   uint32_t tmem_base;
 };
 static_assert(sizeof(Barriers) <= 512, "barrier block");
@@ -249,6 +254,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&bars.item_full[i], 1);
       mbar_init(&bars.item_empty[i], 2 + 8 + 1);   // one lane of every consumer warp (2 MMA, 8 softmax, warp 3)
     }
+    for (int i = 0; i < 8; ++i) (&bars.mufu_busy[0][0])[i] = 0;
     fence_barrier_init();
   }
   if (warp == 3) {
@@ -388,67 +394,71 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int n_max = it.n_max();
         mbar_wait_a(BAR_I(q_full, qb), (item_no / C::kQBufs) & 1);
 
+        // The whole warp walks these loops with warp-uniform values; every tcgen05 instruction is predicated on an
+        // elected lane inside its asm block (umma_*_w), so there is no divergent region and no ELECT/R2UR waterfall
+        // around each MMA (which costs more than a narrow N = 64 MMA takes to execute).  Barriers that complete
+        // early (K/V tile landed, S buffer drained) are probed together ahead of their use; only p_ready -- the one
+        // hand-over this warp really waits for -- is a blocking wait.
         // S(j) = Q K_j^T into this tile's S buffer, then hand the K slot back (both tiles must do so)
-        auto step_s = [&](int j, uint32_t kblk) {
+        auto step_s = [&](int j, uint32_t kblk, bool sfree_ready, bool k_ready) {
           const uint32_t slot = kblk % C::kStages;
           const uint32_t ph = (kblk / C::kStages) & 1;
           if (j < n) {
-            if (s_cnt >= 1) mbar_wait_a(BAR_I(s_free, t), (s_cnt - 1) & 1);   // softmax has read the previous S
+            if (s_cnt >= 1 && !sfree_ready) mbar_wait_a(BAR_I(s_free, t), (s_cnt - 1) & 1);   // softmax has read the previous S
             tr.rec(1, kblk);
-            mbar_wait_a(BAR_I(k_full, slot), ph);
+            if (!k_ready) mbar_wait_a(BAR_I(k_full, slot), ph);
             tc_fence_after();
             tr.rec(2, kblk);
-            if (lane == 0) {
 #pragma unroll
-              for (int kk = 0; kk < DP / 16; ++kk) {
-                const uint32_t a = sQ + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-                const uint32_t b = sK + slot * C::kKVTileBytes + (kk >> 2) * C::kKVPanelBytes + (kk & 3) * 32;
-                umma_ss(tS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_s,
+            for (int kk = 0; kk < DP / 16; ++kk) {
+              const uint32_t a = sQ + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+              const uint32_t b = sK + slot * C::kKVTileBytes + (kk >> 2) * C::kKVPanelBytes + (kk & 3) * 32;
+              umma_ss_w(tS, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_s,
                         kk > 0 ? 1u : 0u);
-              }
-              umma_commit_a(BAR_I(k_empty, slot));
-              if (j == n - 1) umma_commit_a(BAR_I(q_empty, qb));   // last read of this item's Q tile
-              umma_commit_a(BAR_I(s_full, t));
             }
+            umma_commit_w(BAR_I(k_empty, slot));
+            if (j == n - 1) umma_commit_w(BAR_I(q_empty, qb));   // last read of this item's Q tile
+            umma_commit_w(BAR_I(s_full, t));
             ++s_cnt;
           } else {
             // Block not visited by this tile.  The slot still needs this warp's release, but only once the
             // producer has (re)filled it for THIS block: arriving earlier could complete the previous
             // phase of k_empty while the other tile still reads the previous occupant.
-            mbar_wait_a(BAR_I(k_full, slot), ph);
-            if (lane == 0) umma_commit_a(BAR_I(k_empty, slot));
+            if (!k_ready) mbar_wait_a(BAR_I(k_full, slot), ph);
+            umma_commit_w(BAR_I(k_empty, slot));
           }
-          __syncwarp();
         };
 
-        if (n == 0 && lane == 0) umma_commit_a(BAR_I(q_empty, qb));
-        step_s(0, blk);
+        if (n == 0) umma_commit_w(BAR_I(q_empty, qb));
+        step_s(0, blk, false, false);
         for (int j = 0; j < n_max; ++j, ++blk) {
-          if (j + 1 < n_max) step_s(j + 1, blk + 1);
           const uint32_t slot = blk % C::kStages;
           const uint32_t ph = (blk / C::kStages) & 1;
-          mbar_wait_a(BAR_I(v_full, slot), ph);
+          const bool has_s = j + 1 < n_max;
+          // probes issued back to back: their latencies overlap each other and the S issue below
+          const bool k_ready = has_s ? mbar_test_a(BAR_I(k_full, (blk + 1) % C::kStages), ((blk + 1) / C::kStages) & 1) : true;
+          const bool sfree_ready = (has_s && j + 1 < n && s_cnt >= 1) ? mbar_test_a(BAR_I(s_free, t), (s_cnt - 1) & 1) : false;
+          const bool v_ready = mbar_test_a(BAR_I(v_full, slot), ph);
+          if (has_s) step_s(j + 1, blk + 1, sfree_ready, k_ready);
+          if (!v_ready) mbar_wait_a(BAR_I(v_full, slot), ph);
           if (j < n) {
             // O_t (+)= P_t V_j : A = P from TMEM (8 columns per K-step of 16 keys), V rows are the K dimension
             // (MN-major B operand, the TMA tile as it landed)
             mbar_wait_a(BAR_I(p_ready, t), pv_cnt & 1);
             tc_fence_after();
             tr.rec(3, blk);
-            if (lane == 0) {
 #pragma unroll
-              for (int kk = 0; kk < BN / 16; ++kk) {
-                const uint32_t b = sV + slot * C::kKVTileBytes + kk * 16 * 128;
-                umma_ts(tO, tP + kk * 8, make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv,
+            for (int kk = 0; kk < BN / 16; ++kk) {
+              const uint32_t b = sV + slot * C::kKVTileBytes + kk * 16 * 128;
+              umma_ts_w(tO, tP + kk * 8, make_smem_desc_sw128(b, C::kKVPanelBytes, 1024), idesc_pv,
                         (j > 0 || kk > 0) ? 1u : 0u);
-              }
-              umma_commit_a(BAR_I(v_empty, slot));
-              umma_commit_a(BAR_I(pv_done, t));
             }
+            umma_commit_w(BAR_I(v_empty, slot));
+            umma_commit_w(BAR_I(pv_done, t));
             ++pv_cnt;
           } else {
-            if (lane == 0) umma_commit_a(BAR_I(v_empty, slot));   // same pacing rule as for K
+            umma_commit_w(BAR_I(v_empty, slot));   // same pacing rule as for K
           }
-          __syncwarp();
         }
         ++item_no;
       }
@@ -550,19 +560,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         }
-        // row max over the live chunks: two independent 3-input chains per chunk
-        float mxa = -INFINITY, mxb = -INFINITY;
+        // row max over the live chunks: EIGHT independent 3-input chains (with two chains the 32-deep dependent
+        // sequence of FMNMX3 cost ~650 cycles per block on a sub-partition that hosts only two softmax warps)
+        float mx8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx8[k] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           if (!((dead >> c) & 1u)) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mxa = max3(mxa, s[c * 32 + i], s[c * 32 + i + 1]);
-              mxb = max3(mxb, s[c * 32 + i + 2], s[c * 32 + i + 3]);
+            for (int i = 0; i < 32; i += 16) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) mx8[k] = max3(mx8[k], s[c * 32 + i + 2 * k], s[c * 32 + i + 2 * k + 1]);
             }
           }
         }
-        const float mx = fmaxf(mxa, mxb);
+        const float mx = max3(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]));
 
         float alpha = 1.f;
         bool grow = false;
@@ -600,6 +613,31 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
         const float neg_m = -m_used * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        // The exponentials are the bound of this kernel (MUFU: 4 lanes per clock and sub-partition, shared by this
+        // warp and its sibling of the other query tile).  Two warps that run their exponential phases at the same
+        // time each get half the pipe and then BOTH sit in their MUFU-free phases together (TMEM load, row max,
+        // hand-overs: ~40 % of a block), which is what a timeline trace of the lock-free version showed.  So the
+        // phase is a critical section per sub-partition: while one warp exponentiates at the full MUFU rate, the
+        // other does everything else.  Tile 0 wins ties; nothing inside the section can block.
+        if constexpr (kMufuLock) {
+          if (lane == 0) {
+            const uint32_t mine = bars_a + static_cast<uint32_t>(offsetof(Barriers, mufu_busy)) + 4u * (t * 4 + (warp & 3));
+            const uint32_t other = bars_a + static_cast<uint32_t>(offsetof(Barriers, mufu_busy)) + 4u * ((t ^ 1) * 4 + (warp & 3));
+            uint32_t busy;
+            for (;;) {
+              do {
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(busy) : "r"(other) : "memory");
+              } while (busy != 0);
+              asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(mine), "r"(1u) : "memory");
+              if (t == 0) break;
+              asm volatile("membar.cta;" ::: "memory");
+              asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(busy) : "r"(other) : "memory");
+              if (busy == 0) break;
+              asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(mine), "r"(0u) : "memory");   // lost the tie: back off
+            }
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           uint32_t pk[16];
@@ -632,6 +670,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           tmem_st16(tP + c * 16, pk);
+        }
+        if constexpr (kMufuLock) {
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(bars_a + static_cast<uint32_t>(offsetof(Barriers, mufu_busy)) +
+                                                                  4u * (t * 4 + (warp & 3))), "r"(0u) : "memory");
         }
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         tmem_st_wait();

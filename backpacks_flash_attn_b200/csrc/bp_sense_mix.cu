@@ -20,7 +20,7 @@
 //     content model's output, backpack.py:276, or an edited tensor of the intervention wrappers), or
 //   * a (vocab, nv, d) TABLE of sense vectors plus the token ids: C_l(x) is a pure function of the token
 //     (backpack.py:258 -- no positions, identity mixer), so for inference the content model collapses to a row
-//     gather, and the gather happens INSIDE the kernel (TMA tile::gather4 straight into the swizzled operand
+//     gather, and the gather happens INSIDE the kernel (16-byte cp.async copies straight into the swizzled operand
 //     tile); no (b, s, nv, d) tensor ever exists in HBM.
 #include <stdlib.h>
 
@@ -361,7 +361,8 @@ struct MixParams {
   const float* lse;  // (b, nv, s), natural log
   void* out;         // (b, s, d)
   const int64_t* ids;     // table mode: token ids (b, s); null in tensor mode
-  int32_t table_rows;     // table mode: vocab * nv rows of d columns
+  const void* table;      // table mode: (vocab, nv, d) sense vectors
+  int32_t vocab;          // table mode: rows of ids are clamped to [0, vocab)
   int32_t seqlen, nv, dk, ksteps, d, num_qtiles, num_chunks;
   int32_t c_sense_inner;  // tensor mode: content tensor-map dims are (d, nv, s, b) instead of (d, s, nv, b)
   int32_t group;          // key blocks per group of the step order (StepIter)
@@ -394,14 +395,15 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmC);
+    if (p.ids == nullptr) tma_prefetch_desc(&tmC);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
       mbar_init(&bars.s_full[i], 1), mbar_init(&bars.pb_go[i], 128);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
-      mbar_init(&bars.pa_go[i], 129), mbar_init(&bars.c_empty[i], 1);
+      // C(n) landed: one expect_tx arrival of the TMA producer, or one cp.async-completion arrival per gather thread
+      mbar_init(&bars.pa_go[i], p.ids != nullptr ? 128 + 64 : 128 + 1), mbar_init(&bars.c_empty[i], 1);
     }
     mbar_init(&bars.o_full, 1);
     fence_barrier_init();
@@ -418,68 +420,75 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp < 4) {
     reg_dealloc<104>();   // 128 x 104 + 256 x 200 = 384 x 168: the issuer keeps its iterators in registers
-    if (warp == 0) {
-      // ---- producer A: content tiles C_l[j] : (ncols/64) panels of [64 keys x 64 columns] ----
+    if (warp == 0 && p.ids == nullptr) {
+      // ---- producer A, tensor mode: content tiles C_l[j] : (ncols/64) panels of [64 keys x 64 columns] by TMA ----
       Tracer tr(p.trace, 0, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
       StepIter it(nj, p.nv, p.group);
       const uint32_t tile_bytes = (ncols / 64) * C::kCPanelBytes;
-      if (p.ids == nullptr) {
-        for (int n = 0; n < n_steps; ++n, it.next()) {
-          const int slot = n % C::CS;
-          tr.rec(0, n);
-          if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
-          tr.rec(1, n);
-          if (lane == 0) {
-            const int sense = it.sense(), j = it.j();
-            mbar_arrive_expect_tx(&bars.pa_go[slot], tile_bytes);
-            for (int pn = 0; pn < ncols / 64; ++pn) {
-              uint8_t* dst = smem + C::offC + slot * C::kCTileBytes + pn * C::kCPanelBytes;
-              if (p.c_sense_inner)
-                tma_load_4d(dst, &tmC, &bars.pa_go[slot], col_base + pn * 64, sense, j * BN, batch);
-              else
-                tma_load_4d(dst, &tmC, &bars.pa_go[slot], col_base + pn * 64, j * BN, sense, batch);
-            }
+      for (int n = 0; n < n_steps; ++n, it.next()) {
+        const int slot = n % C::CS;
+        tr.rec(0, n);
+        if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
+        tr.rec(1, n);
+        if (lane == 0) {
+          const int sense = it.sense(), j = it.j();
+          mbar_arrive_expect_tx(&bars.pa_go[slot], tile_bytes);
+          for (int pn = 0; pn < ncols / 64; ++pn) {
+            uint8_t* dst = smem + C::offC + slot * C::kCTileBytes + pn * C::kCPanelBytes;
+            if (p.c_sense_inner)
+              tma_load_4d(dst, &tmC, &bars.pa_go[slot], col_base + pn * 64, sense, j * BN, batch);
+            else
+              tma_load_4d(dst, &tmC, &bars.pa_go[slot], col_base + pn * 64, j * BN, sense, batch);
           }
-          __syncwarp();
         }
-      } else {
-        // Table mode: row (x_j * nv + l) of the (vocab*nv, d) table for each of the 64 keys of the block.  One
-        // tile::gather4 moves 4 rows x 64 columns (512 B) into 4 consecutive 128-byte rows of a panel, so a tile is
-        // 16 row groups x (ncols/64) panels; lane L owns row group L & 15 and every second panel, i.e. the 32
-        // lanes issue the tile's copies in parallel.  The ids of the NEXT step are fetched before waiting for the
-        // ring slot of this one.
-        const int g = lane & 15, half = lane >> 4;
-        const int64_t* ids = p.ids + static_cast<int64_t>(batch) * S;
-        auto load_rows = [&](int j) {
-          int4 r;
-          const int k0 = j * BN + 4 * g;   // keys beyond the sequence are masked (P = 0): any valid row will do
-          r.x = static_cast<int>(__ldg(ids + min(k0 + 0, S - 1))) * p.nv;
-          r.y = static_cast<int>(__ldg(ids + min(k0 + 1, S - 1))) * p.nv;
-          r.z = static_cast<int>(__ldg(ids + min(k0 + 2, S - 1))) * p.nv;
-          r.w = static_cast<int>(__ldg(ids + min(k0 + 3, S - 1))) * p.nv;
-          return r;
-        };
-        int4 cur = load_rows(it.j());
-        for (int n = 0; n < n_steps; ++n) {
-          const int slot = n % C::CS;
-          const int sense = it.sense();
-          it.next();
-          int4 nxt = cur;
-          if (n + 1 < n_steps) nxt = load_rows(it.j());
-          tr.rec(0, n);
-          if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
-          tr.rec(1, n);
-          if (lane == 0) mbar_arrive_expect_tx(&bars.pa_go[slot], tile_bytes);
-          __syncwarp();
-          const uint32_t dst0 = smem_u32(smem + C::offC + slot * C::kCTileBytes) + g * 512;
-          const uint32_t bar = smem_u32(&bars.pa_go[slot]);
-          for (int pn = half; pn < ncols / 64; pn += 2)
-            tma_gather4_2d(dst0 + pn * C::kCPanelBytes, &tmC, bar, col_base + pn * 64, cur.x + sense, cur.y + sense,
-                           cur.z + sense, cur.w + sense);
-          __syncwarp();
-          cur = nxt;
-        }
+        __syncwarp();
       }
+    } else if ((warp == 0 || warp == 2) && p.ids != nullptr) {
+      // ---- producer A, table mode: warps 0 and 2 gather row (x_j * nv + l) of the (vocab * nv, d) table for each of
+      // the 64 keys of the block with 16-byte cp.async copies, writing the 128B-swizzled panel layout the MMA expects
+      // (TMA is the wrong tool here: tile::gather4 walks a descriptor per 128-byte row and measured 2.8x slower
+      // than the whole tiled kernel).  Lane l copies chunk (l & 7) of rows 4i + (l >> 3): one warp instruction moves
+      // four whole 128-byte lines.  Warp g takes every second 64-column panel.  Completion is signalled to the MMA
+      // issuer by the copies themselves (cp.async.mbarrier.arrive.noinc): the gather warps never wait for data.
+      const int gw = warp >> 1;
+      const int chunk = lane & 7, r4 = lane >> 3;
+      Tracer tr(p.trace, 0, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && warp == 0);
+      StepIter it(nj, p.nv, p.group);
+      const int64_t* ids = p.ids + static_cast<int64_t>(batch) * S;
+      const uint8_t* tbase = static_cast<const uint8_t*>(p.table) + (static_cast<int64_t>(col_base) + chunk * 8) * 2;
+      const int64_t row_bytes = static_cast<int64_t>(p.d) * 2;
+      const int npan = ncols / 64;
+      const uint32_t sC = smem_u32(smem + C::offC);
+      auto load_ids = [&](int j, int& lo, int& hi) {
+        // keys beyond the sequence are masked (P = 0): any valid row will do; ids are clamped to the table
+        const int k0 = j * BN + lane;
+        lo = min(max(static_cast<int>(__ldg(ids + min(k0, S - 1))), 0), p.vocab - 1) * p.nv;
+        hi = min(max(static_cast<int>(__ldg(ids + min(k0 + 32, S - 1))), 0), p.vocab - 1) * p.nv;
+      };
+      int lo, hi;
+      load_ids(it.j(), lo, hi);
+      for (int n = 0; n < n_steps; ++n) {
+        const int slot = n % C::CS;
+        const int sense = it.sense();
+        it.next();
+        int nlo = lo, nhi = hi;
+        if (n + 1 < n_steps) load_ids(it.j(), nlo, nhi);   // next step's ids travel while this step's copies are issued
+        tr.rec(0, n);
+        if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
+        tr.rec(1, n);
+        const uint32_t dst_slot = sC + slot * C::kCTileBytes;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = 4 * i + r4;
+          const int rid = __shfl_sync(0xffffffffu, i < 8 ? lo : hi, row & 31) + sense;
+          const uint8_t* src = tbase + rid * row_bytes;
+          const uint32_t dst = dst_slot + row * 128 + ((chunk ^ (row & 7)) << 4);
+          for (int pn = gw; pn < npan; pn += 2) cp_async16(dst + pn * C::kCPanelBytes, src + pn * 128);
+        }
+        cp_async_arrive_noinc(smem_u32(&bars.pa_go[slot]));
+        lo = nlo, hi = nhi;
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");   // nothing of this CTA may still be in flight at exit
     } else if (warp == 3) {
       // ---- producer B: Q_l (once per (group, sense) visit) and K_l[j] ----
       StepIter it(nj, p.nv, p.group);
@@ -509,67 +518,75 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     } else if (warp == 1) {
       // ---- the issuer: PV(n), S(n+2), PV(n+1), S(n+3), ... ----
+      // The WHOLE warp walks this loop with warp-uniform values and every tcgen05 instruction is predicated on an
+      // elected lane inside its asm block (umma_*_w): no divergent region, hence no ELECT/R2UR waterfall around each
+      // MMA.  This thread is the kernel's critical resource -- a timeline trace of the first version of this loop
+      // showed ~2000 cycles per step (four satisfied barrier waits at ~180 cycles each plus ~55 cycles per MMA)
+      // against 896 cycles of tensor-pipe work -- so barriers that are known to complete early (K tile landed, next
+      // step's P) are PROBED ahead of time with test_wait, whose latency overlaps the MMA issue, and only a failed
+      // probe falls back to the blocking wait.
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
       const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
       const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
       const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK), sC = smem_u32(smem + C::offC);
+      const uint32_t tO = tmem_base + C::colO, tB = tmem_base + C::colB;
+      const bool table = p.ids != nullptr;
       Tracer tr(p.trace, 1, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
       StepIter its(nj, p.nv, p.group);   // walks the S products (two steps ahead of the PV products)
       int qv = 0;                        // (group, sense) visits whose Q buffer has been waited for
-      auto issue_s = [&](int n) {
+      auto issue_s = [&](int n, bool k_ready) {
         const int qs = qv % C::QS, ks = n % C::KS;
         if (its.first_of_visit()) mbar_wait(&bars.q_full[qs], (qv / C::QS) & 1);
-        mbar_wait(&bars.k_full[ks], (n / C::KS) & 1);
+        if (!k_ready) mbar_wait(&bars.k_full[ks], (n / C::KS) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          for (int kk = 0; kk < p.ksteps; ++kk) {
-            const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-            const uint32_t b = sK + ks * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
-            umma_ss(tmem_base + C::colB + (n & 1) * BN, make_smem_desc_sw128(a, 16, 1024),
-                    make_smem_desc_sw128(b, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(&bars.k_empty[ks]);
-          if (its.last_of_visit()) umma_commit(&bars.q_empty[qs]);
-          umma_commit(&bars.s_full[n & 1]);
+        for (int kk = 0; kk < p.ksteps; ++kk) {
+          const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+          const uint32_t b = sK + ks * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
+          umma_ss_w(tB + (n & 1) * BN, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_s,
+                    kk > 0 ? 1u : 0u);
         }
-        if (its.last_of_visit()) ++qv;
+        umma_commit_w(smem_u32(&bars.k_empty[ks]));
+        if (its.last_of_visit()) {
+          umma_commit_w(smem_u32(&bars.q_empty[qs]));
+          ++qv;
+        }
+        umma_commit_w(smem_u32(&bars.s_full[n & 1]));
         its.next();
-        __syncwarp();
       };
-      issue_s(0);
-      if (n_steps > 1) issue_s(1);
+      issue_s(0, false);
+      if (n_steps > 1) issue_s(1, false);
+      bool pa_ready = false;   // probe of pa_go for the step at the top of the loop
       for (int n = 0; n < n_steps; ++n) {
         const int cs = n % C::CS;
-        const uint32_t a_tmem = tmem_base + C::colB + (n & 1) * BN;   // P(n): 8 columns per K-step of 16 keys
+        const uint32_t a_tmem = tB + (n & 1) * BN;   // P(n): 8 columns per K-step of 16 keys
         const uint32_t b_base = sC + cs * C::kCTileBytes;
         auto issue_pv = [&](int kk) {
-          umma_ts(tmem_base + C::colO, a_tmem + kk * 8, make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024),
-                  idesc_pv1, (n > 0 || kk > 0) ? 1u : 0u);
-          if (n2 > 0)
-            umma_ts(tmem_base + C::colO + 256, a_tmem + kk * 8,
-                    make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024), idesc_pv2,
+          umma_ts_w(tO, a_tmem + kk * 8, make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024), idesc_pv1,
                     (n > 0 || kk > 0) ? 1u : 0u);
+          if (n2 > 0)
+            umma_ts_w(tO + 256, a_tmem + kk * 8,
+                      make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024), idesc_pv2,
+                      (n > 0 || kk > 0) ? 1u : 0u);
         };
         tr.rec(3, n);
-        mbar_wait(&bars.pa_go[cs], (n / C::CS) & 1);      // C(n) landed, keys 0-31 of P(n) stored
+        if (!pa_ready) mbar_wait(&bars.pa_go[cs], (n / C::CS) & 1);      // C(n) landed, keys 0-31 of P(n) stored
+        if (table) fence_proxy_async_smem();   // the gathered C tile was written by cp.async (generic proxy)
         tc_fence_after();
         tr.rec(4, n);
-        if (lane == 0) {
-          issue_pv(0);
-          issue_pv(1);
-        }
-        __syncwarp();
-        mbar_wait(&bars.pb_go[n & 1], (n >> 1) & 1);      // keys 32-63 of P(n) stored
+        // K(n+2) landed long ago (the K ring runs three steps ahead): probe now, use after the PV products
+        const bool k_ready = n + 2 < n_steps ? mbar_test(&bars.k_full[(n + 2) % C::KS], ((n + 2) / C::KS) & 1) : true;
+        issue_pv(0);
+        issue_pv(1);
+        mbar_wait(&bars.pb_go[n & 1], (n >> 1) & 1);      // keys 32-63 of P(n) stored (the pipe has 2 K-steps queued)
         tc_fence_after();
         tr.rec(5, n);
-        if (lane == 0) {
-          issue_pv(2);
-          issue_pv(3);
-          umma_commit(&bars.c_empty[cs]);
-          if (n == n_steps - 1) umma_commit(&bars.o_full);
-        }
-        __syncwarp();
-        if (n + 2 < n_steps) issue_s(n + 2);   // into B_{n&1}: ordered behind PV(n) by the in-order tensor pipe
+        issue_pv(2);
+        issue_pv(3);
+        umma_commit_w(smem_u32(&bars.c_empty[cs]));
+        if (n == n_steps - 1) umma_commit_w(smem_u32(&bars.o_full));
+        // P(n+1): its first half is usually stored by now (its warpgroup started when S(n+1) completed, a step ago)
+        pa_ready = n + 1 < n_steps ? mbar_test(&bars.pa_go[(n + 1) % C::CS], ((n + 1) / C::CS) & 1) : false;
+        if (n + 2 < n_steps) issue_s(n + 2, k_ready);   // into B_{n&1}: ordered behind PV(n) by the in-order tensor pipe
         tr.rec(6, n);
       }
     }
@@ -827,7 +844,8 @@ extern "C" int bp_sense_mix_fwd(const void* qk, const void* content, const float
   }
   sense::MixParams p;
   p.ids = nullptr;
-  p.table_rows = 0;
+  p.table = nullptr;
+  p.vocab = 0;
   p.c_sense_inner = sense_inner ? 1 : 0;
   return sense::run_mix("bp_sense_mix_fwd", qk, tmC, p, lse, out, batch, seqlen, nv, dk, d, softmax_scale, dtype, stream);
 }
@@ -845,7 +863,8 @@ extern "C" int bp_sense_mix_table_fwd(const void* qk, const void* table, const i
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_mix_table_fwd: vocab * nv must fit 31 bits (vocab=%d nv=%d)", vocab, nv);
   if ((uintptr_t)table % 16 || (uintptr_t)qk % 16 || (uintptr_t)out % 16 || (uintptr_t)input_ids % 8)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_mix_table_fwd: pointers must be 16-byte aligned (ids: 8)");
-  // (vocab, nv, d) contiguous viewed as a 2-D tensor of vocab*nv rows; box = one row x 64 columns, four rows per gather4
+  // table mode reads the (vocab, nv, d) table with plain cp.async copies; the tensor map of the C operand is unused
+  // (a valid map of the table keeps the kernel signature uniform)
   CUtensorMap tmC;
   const uint64_t dims[2] = {(uint64_t)d, (uint64_t)vocab * nv};
   const uint64_t str[1] = {(uint64_t)d * 2};
@@ -853,7 +872,8 @@ extern "C" int bp_sense_mix_table_fwd(const void* qk, const void* table, const i
   if (int rc = encode_tensor_map(&tmC, dtype, 2, table, dims, str, box, true)) return rc;
   sense::MixParams p;
   p.ids = input_ids;
-  p.table_rows = vocab * nv;
+  p.table = table;
+  p.vocab = vocab;
   p.c_sense_inner = 0;
   return sense::run_mix("bp_sense_mix_table_fwd", qk, tmC, p, lse, out, batch, seqlen, nv, dk, d, softmax_scale, dtype,
                         stream);

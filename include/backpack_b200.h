@@ -95,10 +95,10 @@ int bp_sense_mix_fwd(const void* qk, const void* content, const float* lse, void
  * C_l(x) depends on the token id only (BackpackContentModule sees the word embedding without positions and has
  * an identity mixer: training/src/models/backpack.py:258, 125-143; the reference's analysis scripts rely on the
  * same fact, training/src/run_simlex.py:179-184), so for inference content_model(input_ids) is a row gather from a
- * (vocab, nv, d) table computed once with the same kernels.  The gather is done by TMA (tile::gather4) straight into
- * the operand tiles: no (batch, seqlen, nv, d) tensor is ever written to or read from HBM.
+ * (vocab, nv, d) table computed once with the same kernels.  The gather is done inside the kernel (16-byte cp.async
+ * copies straight into the swizzled operand tiles): no (batch, seqlen, nv, d) tensor is ever written to or read from HBM.
  *   table     : (vocab, nv, d) contiguous, same dtype as qk.   input_ids : (batch, seqlen) int64 contiguous;
- *               rows of ids outside [0, vocab) read as zero vectors (TMA out-of-bounds fill).
+ *               ids are clamped to [0, vocab) (the caller validates them; the kernel cannot raise).
  *   lse       : from bp_sense_lse_fwd.   out : (batch, seqlen, d) contiguous.
  */
 int bp_sense_mix_table_fwd(const void* qk, const void* table, const int64_t* input_ids, const float* lse, void* out,
