@@ -39,7 +39,9 @@ __device__ __forceinline__ bool elect_one() {
 #endif
 template <int kWarps>
 __device__ __forceinline__ int role_warp() {
-  const int w = threadIdx.x >> 5;
+  // the shuffle tells the compiler that the result is warp-uniform: role dispatch becomes uniform control flow and the
+  // code of a role is known to run with the whole warp converged (no divergence handling around tcgen05 / TMA issue)
+  const int w = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   return BP_SERVICE_WARPS_HIGH ? (w + 4) % kWarps : w;
 }
 
@@ -436,6 +438,39 @@ __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
       "{\n\t.reg .pred e;\n\t"
       "elect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
+}
+// Issue helpers for loops that the whole warp walks but in which ONE lane (leader != 0, normally lane 0) issues:
+// the predicate travels in a register, so a group of MMAs needs no elect / vote of its own, and the descriptors are
+// advanced with desc_add (a 64-bit add of an immediate) instead of being re-encoded for every MMA.  The single issuing
+// thread is the critical resource of the attention and sense-mix kernels: their first versions spent 25-40
+// instructions per MMA on descriptor encoding, ELECT / R2UR sequences and divergence checks.
+__device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+__device__ __forceinline__ void umma_ss_p(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_p(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar), "r"(leader)
       : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.

@@ -376,9 +376,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_pv = make_idesc(kBF16, BM, DP, false, true);
       const uint32_t sK = smem_a + C::offK;
       const uint32_t sV = smem_a + C::offV;
-      const uint32_t tS = tmem_base + C::colS + t * BN;
-      const uint32_t tO = tmem_base + C::colO + t * DP;
-      const uint32_t tP = tmem_base + C::colP + t * (BN / 2);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform: stays in uniform registers
+      const uint32_t tS = tm + C::colS + t * BN;
+      const uint32_t tO = tm + C::colO + t * DP;
+      const uint32_t tP = tm + C::colP + t * (BN / 2);
       uint32_t item_no = 0, blk = 0;  // same running counters as the producer
       uint32_t s_cnt = 0;             // S tiles issued by this warp (s_free / s_full phases)
       uint32_t pv_cnt = 0;            // key blocks whose PV products were issued (p_ready / pv_done phases)

@@ -152,8 +152,11 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
       }
     } else if (warp == 1) {
       // ---- MMA issuer: S_t(j) into buffer (count of S tiles of tile t so far) & 1 ----
+      // (whole warp, warp-uniform values, elected lane inside the asm: see the issuer of pass 2)
       constexpr uint32_t idesc = make_idesc(kBF16, BM, BN, false, false);
-      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t dQ0 = make_smem_desc_sw128(smem_u32(smem + C::offQ), 16, 1024);
+      const uint64_t dK0 = make_smem_desc_sw128(smem_u32(smem + C::offK), 16, 1024);
       int kb = 0;
       int sc[2] = {0, 0};   // S tiles issued per query tile (all senses)
       for (int si = 0; si < n_senses; ++si) {
@@ -168,18 +171,14 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
             const int c = sc[t]++;
             if (c >= 2) mbar_wait(&bars.s_free[t][c & 1], ((c >> 1) - 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-              for (int kk = 0; kk < p.ksteps; ++kk) {
-                const uint32_t a = sQ + (qb * 2 + t) * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-                const uint32_t b = sK + slot * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
-                umma_ss(tmem_base + (t * 2 + (c & 1)) * BN, make_smem_desc_sw128(a, 16, 1024),
-                        make_smem_desc_sw128(b, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-              }
-              if (t == last_user) umma_commit(&bars.k_empty[slot]);
-              if (j == n_max - 1 && t == last_user) umma_commit(&bars.q_empty[qb]);   // last S of this sense
-              umma_commit(&bars.s_full[t][c & 1]);
-            }
-            __syncwarp();
+            const uint64_t a0 = dQ0 + static_cast<uint32_t>(qb * 2 + t) * (C::kQTileBytes >> 4);
+            const uint64_t b0 = dK0 + static_cast<uint32_t>(slot) * (C::kKTileBytes >> 4);
+            for (int kk = 0; kk < p.ksteps; ++kk)
+              umma_ss_w(tm + (t * 2 + (c & 1)) * BN, a0 + (kk >> 2) * ((BM * 128) >> 4) + (kk & 3) * 2,
+                        b0 + (kk >> 2) * ((BN * 128) >> 4) + (kk & 3) * 2, idesc, kk > 0 ? 1u : 0u);
+            if (t == last_user) umma_commit_w(smem_u32(&bars.k_empty[slot]));
+            if (j == n_max - 1 && t == last_user) umma_commit_w(smem_u32(&bars.q_empty[qb]));   // last S of this sense
+            umma_commit_w(smem_u32(&bars.s_full[t][c & 1]));
           }
         }
       }
@@ -526,77 +525,95 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     } else if (warp == 1) {
       // ---- the issuer: PV(n), S(n+2), PV(n+1), S(n+3), ... ----
-      // The WHOLE warp walks this loop with warp-uniform values and every tcgen05 instruction is predicated on an
-      // elected lane inside its asm block (umma_*_w): no divergent region, hence no ELECT/R2UR waterfall around each
-      // MMA.  This thread is the kernel's critical resource -- a timeline trace of the first version of this loop
-      // showed ~2000 cycles per step (four satisfied barrier waits at ~180 cycles each plus ~55 cycles per MMA)
-      // against 896 cycles of tensor-pipe work -- so barriers that are known to complete early (K tile landed, next
-      // step's P) are PROBED ahead of time with test_wait, whose latency overlaps the MMA issue, and only a failed
-      // probe falls back to the blocking wait.
+      // This thread is the kernel's critical resource.  A timeline trace plus an ncu source profile of the first
+      // version of this loop showed ~1800 cycles per step against 896 cycles of tensor-pipe work, all of it the
+      // issuing warp's own instruction stream: ~400 dependent scalar instructions per step (shared-memory
+      // descriptors re-encoded for every MMA, % and / for the ring slots, an ELECT / vote / divergence check around
+      // every tcgen05 instruction) plus four satisfied barrier waits at ~180 cycles each.  Hence:
+      //   * the whole warp walks the loop with provably warp-uniform values (role index and TMEM base come out of
+      //     shuffles), every tcgen05 instruction is predicated on an elected lane inside its asm block (umma_*_w);
+      //   * descriptors are base descriptors plus immediates (desc_add), ring slots and phases are running counters;
+      //   * barriers that complete early (K tile landed, next step's P) are PROBED ahead of time with test_wait,
+      //     whose latency overlaps the MMA issue; only a failed probe falls back to the blocking wait.
       constexpr uint32_t idesc_s = make_idesc(kBF16, BM, BN, false, false);
       const uint32_t idesc_pv1 = make_idesc(kBF16, BM, n1, false, true);
       const uint32_t idesc_pv2 = make_idesc(kBF16, BM, n2 > 0 ? n2 : 64, false, true);
-      const uint32_t sQ = smem_u32(smem + C::offQ), sK = smem_u32(smem + C::offK), sC = smem_u32(smem + C::offC);
-      const uint32_t tO = tmem_base + C::colO, tB = tmem_base + C::colB;
+      const uint64_t dQ0 = make_smem_desc_sw128(smem_u32(smem + C::offQ), 16, 1024);
+      const uint64_t dK0 = make_smem_desc_sw128(smem_u32(smem + C::offK), 16, 1024);
+      const uint64_t dC0 = make_smem_desc_sw128(smem_u32(smem + C::offC), C::kCPanelBytes, 1024);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
+      const uint32_t tO = tm + C::colO, tB = tm + C::colB;
+      const uint32_t bars_a = smem_u32(&bars);
+#define MIX_BAR(field, i) (bars_a + static_cast<uint32_t>(offsetof(MixBarriers, field)) + 8u * static_cast<uint32_t>(i))
       const bool table = p.ids != nullptr;
+      const bool two = n2 > 0;
+      const int ksteps = p.ksteps;
       Tracer tr(p.trace, 1, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
       StepIter its(nj, p.nv, p.group);   // walks the S products (two steps ahead of the PV products)
-      int qv = 0;                        // (group, sense) visits whose Q buffer has been waited for
-      auto issue_s = [&](int n, bool k_ready) {
-        const int qs = qv % C::QS, ks = n % C::KS;
-        if (its.first_of_visit()) mbar_wait(&bars.q_full[qs], (qv / C::QS) & 1);
-        if (!k_ready) mbar_wait(&bars.k_full[ks], (n / C::KS) & 1);
+      // S side: step m, K ring slot / phase, Q buffer / phase
+      int m = 0, s_ks = 0, s_qs = 0;
+      uint32_t s_kph = 0, s_qph = 0;
+      auto issue_s = [&](bool k_ready) {
+        if (its.first_of_visit()) mbar_wait_a(MIX_BAR(q_full, s_qs), s_qph);
+        if (!k_ready) mbar_wait_a(MIX_BAR(k_full, s_ks), s_kph);
         tc_fence_after();
-        for (int kk = 0; kk < p.ksteps; ++kk) {
-          const uint32_t a = sQ + qs * C::kQTileBytes + (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-          const uint32_t b = sK + ks * C::kKTileBytes + (kk >> 2) * (BN * 128) + (kk & 3) * 32;
-          umma_ss_w(tB + (n & 1) * BN, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_s,
-                    kk > 0 ? 1u : 0u);
+        const uint64_t a0 = dQ0 + static_cast<uint32_t>(s_qs) * (C::kQTileBytes >> 4);
+        const uint64_t b0 = dK0 + static_cast<uint32_t>(s_ks) * (C::kKTileBytes >> 4);
+        const uint32_t d = tB + (m & 1) * BN;
+        if constexpr (PK == 1) {
+#pragma unroll 4
+          for (int kk = 0; kk < ksteps; ++kk) umma_ss_w(d, a0 + 2u * kk, b0 + 2u * kk, idesc_s, kk > 0 ? 1u : 0u);
+        } else {
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_ss_w(d, a0 + (kk >> 2) * ((BM * 128) >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * ((BN * 128) >> 4) + (kk & 3) * 2,
+                      idesc_s, kk > 0 ? 1u : 0u);
         }
-        umma_commit_w(smem_u32(&bars.k_empty[ks]));
+        umma_commit_w(MIX_BAR(k_empty, s_ks));
         if (its.last_of_visit()) {
-          umma_commit_w(smem_u32(&bars.q_empty[qs]));
-          ++qv;
+          umma_commit_w(MIX_BAR(q_empty, s_qs));
+          if (++s_qs == C::QS) s_qs = 0, s_qph ^= 1;
         }
-        umma_commit_w(smem_u32(&bars.s_full[n & 1]));
+        umma_commit_w(MIX_BAR(s_full, m & 1));
+        if (++s_ks == C::KS) s_ks = 0, s_kph ^= 1;
         its.next();
+        ++m;
       };
-      issue_s(0, false);
-      if (n_steps > 1) issue_s(1, false);
+      issue_s(false);
+      if (n_steps > 1) issue_s(false);
       bool pa_ready = false;   // probe of pa_go for the step at the top of the loop
+      int cs = 0;              // C ring slot of step n
+      uint32_t cph = 0;        // its phase
       for (int n = 0; n < n_steps; ++n) {
-        const int cs = n % C::CS;
         const uint32_t a_tmem = tB + (n & 1) * BN;   // P(n): 8 columns per K-step of 16 keys
-        const uint32_t b_base = sC + cs * C::kCTileBytes;
-        auto issue_pv = [&](int kk) {
-          umma_ts_w(tO, a_tmem + kk * 8, make_smem_desc_sw128(b_base + kk * 2048, C::kCPanelBytes, 1024), idesc_pv1,
-                    (n > 0 || kk > 0) ? 1u : 0u);
-          if (n2 > 0)
-            umma_ts_w(tO + 256, a_tmem + kk * 8,
-                      make_smem_desc_sw128(b_base + 4 * C::kCPanelBytes + kk * 2048, C::kCPanelBytes, 1024), idesc_pv2,
-                      (n > 0 || kk > 0) ? 1u : 0u);
-        };
+        const uint64_t b0 = dC0 + static_cast<uint32_t>(cs) * (C::kCTileBytes >> 4);
+        const uint32_t acc0 = n > 0 ? 1u : 0u;
         tr.rec(3, n);
-        if (!pa_ready) mbar_wait(&bars.pa_go[cs], (n / C::CS) & 1);      // C(n) landed, keys 0-31 of P(n) stored
+        if (!pa_ready) mbar_wait_a(MIX_BAR(pa_go, cs), cph);      // C(n) landed, keys 0-31 of P(n) stored
         if (table) fence_proxy_async_smem();   // the gathered C tile was written by cp.async (generic proxy)
         tc_fence_after();
         tr.rec(4, n);
         // K(n+2) landed long ago (the K ring runs three steps ahead): probe now, use after the PV products
-        const bool k_ready = n + 2 < n_steps ? mbar_test(&bars.k_full[(n + 2) % C::KS], ((n + 2) / C::KS) & 1) : true;
-        issue_pv(0);
-        issue_pv(1);
-        mbar_wait(&bars.pb_go[n & 1], (n >> 1) & 1);      // keys 32-63 of P(n) stored (the pipe has 2 K-steps queued)
+        const bool k_ready = m < n_steps ? mbar_test_a(MIX_BAR(k_full, s_ks), s_kph) : true;
+        umma_ts_w(tO, a_tmem, b0, idesc_pv1, acc0);
+        if (two) umma_ts_w(tO + 256, a_tmem, desc_add(b0, 4 * C::kCPanelBytes), idesc_pv2, acc0);
+        umma_ts_w(tO, a_tmem + 8, desc_add(b0, 2048), idesc_pv1, 1u);
+        if (two) umma_ts_w(tO + 256, a_tmem + 8, desc_add(b0, 4 * C::kCPanelBytes + 2048), idesc_pv2, 1u);
+        mbar_wait_a(MIX_BAR(pb_go, n & 1), (n >> 1) & 1);      // keys 32-63 of P(n) stored (the pipe has 2 K-steps queued)
         tc_fence_after();
         tr.rec(5, n);
-        issue_pv(2);
-        issue_pv(3);
-        umma_commit_w(smem_u32(&bars.c_empty[cs]));
-        if (n == n_steps - 1) umma_commit_w(smem_u32(&bars.o_full));
+        umma_ts_w(tO, a_tmem + 16, desc_add(b0, 4096), idesc_pv1, 1u);
+        if (two) umma_ts_w(tO + 256, a_tmem + 16, desc_add(b0, 4 * C::kCPanelBytes + 4096), idesc_pv2, 1u);
+        umma_ts_w(tO, a_tmem + 24, desc_add(b0, 6144), idesc_pv1, 1u);
+        if (two) umma_ts_w(tO + 256, a_tmem + 24, desc_add(b0, 4 * C::kCPanelBytes + 6144), idesc_pv2, 1u);
+        umma_commit_w(MIX_BAR(c_empty, cs));
+        if (n == n_steps - 1) umma_commit_w(MIX_BAR(o_full, 0));
+        if (++cs == C::CS) cs = 0, cph ^= 1;
         // P(n+1): its first half is usually stored by now (its warpgroup started when S(n+1) completed, a step ago)
-        pa_ready = n + 1 < n_steps ? mbar_test(&bars.pa_go[(n + 1) % C::CS], ((n + 1) / C::CS) & 1) : false;
-        if (n + 2 < n_steps) issue_s(n + 2, k_ready);   // into B_{n&1}: ordered behind PV(n) by the in-order tensor pipe
+        pa_ready = n + 1 < n_steps ? mbar_test_a(MIX_BAR(pa_go, cs), cph) : false;
+        if (m < n_steps) issue_s(k_ready);   // S(n+2) into B_{n&1}: ordered behind PV(n) by the in-order tensor pipe
         tr.rec(6, n);
       }
+#undef MIX_BAR
     }
   } else {
     // ---- softmax warpgroups: w handles steps n = 2i + w, buffer B_w ----

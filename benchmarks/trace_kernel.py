@@ -1,6 +1,6 @@
 """Debug: dump the per-warp-role timeline of CTA 0 of a kernel (library built with BP_EXTRA_NVCC_FLAGS=-DBP_TRACE).
 
-    python benchmarks/trace_kernel.py fmha|sense [max_lines]
+    python benchmarks/trace_kernel.py fmha|sense|sense_table [max_lines]
 """
 import ctypes, os, sys
 import torch
@@ -24,11 +24,16 @@ if which == "fmha":
     run = lambda: flash_attn_unpadded_qkvpacked_func(qkv, cu, s, 0.0, causal=True)
     names = ["prod", "mma0", "mma1", "sm0", "sm1", "-", "-", "-"]
 else:
-    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
+    from backpacks_flash_attn_b200.ops.sense_mix import sense_mix, sense_mix_table
     b, s, nv, d = 64, 1024, 16, 768
     qk = torch.randn(b, s, 2, nv, d // nv, device="cuda").bfloat16()
-    content = torch.randn(b, s, nv, d, device="cuda").bfloat16().transpose(1, 2)
-    run = lambda: sense_mix(qk, content)
+    if which == "sense_table":
+        table = torch.randn(50264, nv, d, device="cuda").bfloat16()
+        ids = torch.randint(0, 50257, (b, s), device="cuda")
+        run = lambda: sense_mix_table(qk, table, ids)
+    else:
+        content = torch.randn(b, s, nv, d, device="cuda").bfloat16().transpose(1, 2)
+        run = lambda: sense_mix(qk, content)
     names = ["prodC", "issue", "sm0", "sm1", "-", "-", "-", "-"]
 for _ in range(3):
     run()
