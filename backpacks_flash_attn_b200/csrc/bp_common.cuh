@@ -344,6 +344,53 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 
 // ------------------------------------------------------------------------------------------
+// "_w" forms of the single-thread operations, for loops that the WHOLE warp walks with warp-uniform operands: the
+// instruction is predicated on an elected lane inside the asm block.  Together with a provably warp-uniform role
+// index (role_warp) this lets the compiler keep descriptors, addresses and loop state in uniform registers and emit
+// UTMALDG / UTCHMMA / UTCBAR straight from them; inside a divergent `if (lane == 0)` region it wraps every such
+// instruction in an ELECT / R2UR waterfall loop instead.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_w(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // TMEM allocation (one full warp executes these)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -558,6 +605,33 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
                : "memory");
+}
+// "_w" forms (whole warp walks the loop, elected lane issues; see above)
+__device__ __forceinline__ void umma_ss_pair_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_w(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
 }
 // Arrive on the mbarrier at the same offset in the leader CTA (a plain local arrive when executed by the leader).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {

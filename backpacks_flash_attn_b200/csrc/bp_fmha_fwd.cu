@@ -325,12 +325,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int n_max = it.n_max();
         const uint32_t qb = item_no % C::kQBufs;
         if (item_no >= C::kQBufs) mbar_wait_a(BAR_I(q_empty, qb), ((item_no / C::kQBufs) - 1) & 1);
-        if (lane == 0) {
+        {
+          // ("_w" forms: the whole warp walks this code with warp-uniform values, an elected lane issues)
           const int n_q_tiles = (it.row0 + BM < it.len_q) ? 2 : 1;
-          mbar_arrive_expect_tx_a(BAR_I(q_full, qb), n_q_tiles * C::kQTileBytes);
+          mbar_arrive_expect_tx_w(BAR_I(q_full, qb), n_q_tiles * C::kQTileBytes);
           for (int t = 0; t < n_q_tiles; ++t)
+#pragma unroll
             for (int pn = 0; pn < C::kPanelsD; ++pn)
-              tma_load_3d_a(smem_a + C::offQ + (qb * 2 + t) * C::kQTileBytes + pn * (BM * 128), &tmQ,
+              tma_load_3d_w(smem_a + C::offQ + (qb * 2 + t) * C::kQTileBytes + pn * (BM * 128), &tmQ,
                             BAR_I(q_full, qb), pn * 64, it.head, it.q_begin + it.row0 + t * BM);
         }
         auto issue_kv = [&](int j) {
@@ -339,21 +341,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int krow = it.k_begin + j * BN;
           if (blk >= C::kStages) mbar_wait_a(BAR_I(k_empty, slot), ph);
           tr.rec(1, blk);
-          if (lane == 0) {
-            mbar_arrive_expect_tx_a(BAR_I(k_full, slot), C::kKVTileBytes);
-            for (int pn = 0; pn < C::kPanelsD; ++pn)
-              tma_load_3d_a(smem_a + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK,
-                            BAR_I(k_full, slot), pn * 64, it.head, krow);
-          }
+          mbar_arrive_expect_tx_w(BAR_I(k_full, slot), C::kKVTileBytes);
+#pragma unroll
+          for (int pn = 0; pn < C::kPanelsD; ++pn)
+            tma_load_3d_w(smem_a + C::offK + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmK,
+                          BAR_I(k_full, slot), pn * 64, it.head, krow);
           if (blk >= C::kStages) mbar_wait_a(BAR_I(v_empty, slot), ph);
           tr.rec(2, blk);
-          if (lane == 0) {
-            mbar_arrive_expect_tx_a(BAR_I(v_full, slot), C::kKVTileBytes);
-            for (int pn = 0; pn < C::kPanelsD; ++pn)
-              tma_load_3d_a(smem_a + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV,
-                            BAR_I(v_full, slot), pn * 64, it.head, krow);
-          }
-          __syncwarp();
+          mbar_arrive_expect_tx_w(BAR_I(v_full, slot), C::kKVTileBytes);
+#pragma unroll
+          for (int pn = 0; pn < C::kPanelsD; ++pn)
+            tma_load_3d_w(smem_a + C::offV + slot * C::kKVTileBytes + pn * C::kKVPanelBytes, &tmV,
+                          BAR_I(v_full, slot), pn * 64, it.head, krow);
           ++blk;
         };
         const int n_first = min(n_max, 2);

@@ -294,47 +294,54 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    uint32_t it = 0;
+    // (whole warp walks the loop with warp-uniform values, the elected lane issues: bp_common.cuh "_w" forms)
+    const uint32_t sbase = smem_u32(smem), bars_a = smem_u32(&bars);
+    uint32_t slot = 0, ph = 0;   // parity of `empty` to wait for once the ring has wrapped: ((it / kStages) - 1) & 1
+    bool wrapped = false;
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
       const int n0 = static_cast<int>(tile % p.n_tiles) * 256 + static_cast<int>(rank) * 128;
-      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-        const uint32_t slot = it % pair::kStages;
-        if (it >= pair::kStages) mbar_wait(&bars.empty[slot], ((it / pair::kStages) - 1) & 1);
-        if (lane == 0) {
-          uint8_t* a = smem + slot * pair::kStageBytes;
-          if (leader) mbar_arrive_expect_tx(&bars.full[slot], 2 * pair::kStageBytes);   // both CTAs' bytes
-          tma_load_2d_pair(a, &tmA, &bars.full[slot], kb * BK, m0);
-          tma_load_2d_pair(a + pair::kABytes, &tmB, &bars.full[slot], kb * BK, n0);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        if (wrapped) mbar_wait_a(bars_a + static_cast<uint32_t>(offsetof(pair::Barriers, empty)) + 8u * slot, ph);
+        const uint32_t a = sbase + slot * pair::kStageBytes;
+        const uint32_t full = bars_a + static_cast<uint32_t>(offsetof(pair::Barriers, full)) + 8u * slot;
+        if (leader) mbar_arrive_expect_tx_w(full, 2 * pair::kStageBytes);   // both CTAs' bytes
+        tma_load_2d_pair_w(a, &tmA, full, kb * BK, m0);
+        tma_load_2d_pair_w(a + pair::kABytes, &tmB, full, kb * BK, n0);
+        if (++slot == pair::kStages) {
+          slot = 0;
+          if (wrapped) ph ^= 1;
+          wrapped = true;
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1 && leader) {
     // ===================== MMA issuer (leader CTA only) =====================
     constexpr uint32_t idesc = make_idesc(kBF16, 256, 256, false, false);
-    uint32_t it = 0, local = 0;
-    bool ready = false;   // result of the early probe of full[it]
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t bars_a = smem_u32(&bars);
+    const uint64_t dA0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t dB0 = make_smem_desc_sw128(smem_u32(smem) + pair::kABytes, 16, 1024);
+    uint32_t slot = 0, ph = 0, local = 0;
+    bool ready = false;   // result of the early probe of the next stage's `full` barrier
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
       const uint32_t buf = local & 1;
       if (local >= 2) mbar_wait(&bars.acc_empty[buf], ((local >> 1) - 1) & 1);
       tc_fence_after();
-      for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-        const uint32_t slot = it % pair::kStages;
-        if (!ready) mbar_wait(&bars.full[slot], (it / pair::kStages) & 1);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const uint32_t full = bars_a + static_cast<uint32_t>(offsetof(pair::Barriers, full)) + 8u * slot;
+        if (!ready) mbar_wait_a(full, ph);
         tc_fence_after();
-        ready = mbar_test(&bars.full[(it + 1) % pair::kStages], ((it + 1) / pair::kStages) & 1);
-        if (lane == 0) {
-          const uint32_t a = smem_u32(smem + slot * pair::kStageBytes);
-          const uint32_t b = a + pair::kABytes;
+        const uint64_t a = dA0 + slot * (pair::kStageBytes >> 4), b = dB0 + slot * (pair::kStageBytes >> 4);
+        const uint32_t empty = bars_a + static_cast<uint32_t>(offsetof(pair::Barriers, empty)) + 8u * slot;
+        if (++slot == pair::kStages) slot = 0, ph ^= 1;
+        // probe the next stage now: its latency overlaps the MMA issue below
+        ready = mbar_test_a(bars_a + static_cast<uint32_t>(offsetof(pair::Barriers, full)) + 8u * slot, ph);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-            umma_ss_pair(tmem_base + buf * BN, make_smem_desc_sw128(a + kk * 32, 16, 1024),
-                         make_smem_desc_sw128(b + kk * 32, 16, 1024), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-          umma_commit_pair(&bars.empty[slot]);
-          if (kb == p.k_blocks - 1) umma_commit_pair(&bars.acc_full[buf]);
-        }
-        __syncwarp();
+        for (int kk = 0; kk < BK / 16; ++kk)
+          umma_ss_pair_w(tm + buf * BN, a + 2u * kk, b + 2u * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+        umma_commit_pair_w(empty);
+        if (kb == p.k_blocks - 1) umma_commit_pair_w(smem_u32(&bars.acc_full[buf]));
       }
     }
   } else if (warp >= 4) {

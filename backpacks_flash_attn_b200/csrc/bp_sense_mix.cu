@@ -437,18 +437,15 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tr.rec(0, n);
         if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
         tr.rec(1, n);
-        if (lane == 0) {
+        {
           const int sense = it.sense(), j = it.j();
-          mbar_arrive_expect_tx(&bars.pa_go[slot], tile_bytes);
-          for (int pn = 0; pn < ncols / 64; ++pn) {
-            uint8_t* dst = smem + C::offC + slot * C::kCTileBytes + pn * C::kCPanelBytes;
-            if (p.c_sense_inner)
-              tma_load_4d(dst, &tmC, &bars.pa_go[slot], col_base + pn * 64, sense, j * BN, batch);
-            else
-              tma_load_4d(dst, &tmC, &bars.pa_go[slot], col_base + pn * 64, j * BN, sense, batch);
-          }
+          const uint32_t bar = smem_u32(&bars.pa_go[slot]);
+          const uint32_t dst0 = smem_u32(smem + C::offC) + slot * C::kCTileBytes;
+          mbar_arrive_expect_tx_w(bar, tile_bytes);
+          const int c1 = p.c_sense_inner ? sense : j * BN, c2 = p.c_sense_inner ? j * BN : sense;
+          for (int pn = 0; pn < ncols / 64; ++pn)
+            tma_load_4d_w(dst0 + pn * C::kCPanelBytes, &tmC, bar, col_base + pn * 64, c1, c2, batch);
         }
-        __syncwarp();
       }
     } else if ((warp == 0 || warp == 2) && p.ids != nullptr) {
       // ---- producer A, table mode: warps 0 and 2 gather row (x_j * nv + l) of the (vocab * nv, d) table for each of
@@ -462,10 +459,13 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       Tracer tr(p.trace, 0, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && warp == 0);
       StepIter it(nj, p.nv, p.group);
       const int64_t* ids = p.ids + static_cast<int64_t>(batch) * S;
-      const uint8_t* tbase = static_cast<const uint8_t*>(p.table) + (static_cast<int64_t>(col_base) + chunk * 8) * 2;
-      const int64_t row_bytes = static_cast<int64_t>(p.d) * 2;
-      const int npan = ncols / 64;
-      const uint32_t sC = smem_u32(smem + C::offC);
+      const uint32_t row_bytes = static_cast<uint32_t>(p.d) * 2u;
+      // this lane's 16-byte chunk of the first panel of this warp, of table row 0
+      const uint8_t* tb = static_cast<const uint8_t*>(p.table) + (static_cast<int64_t>(col_base) + gw * 64 + chunk * 8) * 2;
+      const int npw = (ncols / 64 - gw + 1) / 2;            // panels of this warp: gw, gw + 2, ...
+      // destination of row 4i + r4: (row & 7) is r4 for even i and r4 + 4 for odd i, so the swizzle has two values
+      const uint32_t dst_lane = smem_u32(smem + C::offC) + gw * C::kCPanelBytes + r4 * 128;
+      const uint32_t swz0 = static_cast<uint32_t>(chunk ^ r4) << 4, swz1 = static_cast<uint32_t>(chunk ^ (r4 + 4)) << 4;
       auto load_ids = [&](int j, int& lo, int& hi) {
         // keys beyond the sequence are masked (P = 0): any valid row will do; ids are clamped to the table
         const int k0 = j * BN + lane;
@@ -474,26 +474,36 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       };
       int lo, hi;
       load_ids(it.j(), lo, hi);
+      int slot = 0;
+      uint32_t ph = 0;   // parity of c_empty to wait for once the ring has wrapped: ((n / CS) - 1) & 1
       for (int n = 0; n < n_steps; ++n) {
-        const int slot = n % C::CS;
         const int sense = it.sense();
         it.next();
         int nlo = lo, nhi = hi;
         if (n + 1 < n_steps) load_ids(it.j(), nlo, nhi);   // next step's ids travel while this step's copies are issued
         tr.rec(0, n);
-        if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ((n / C::CS) - 1) & 1);
+        if (n >= C::CS) mbar_wait(&bars.c_empty[slot], ph);
         tr.rec(1, n);
-        const uint32_t dst_slot = sC + slot * C::kCTileBytes;
+        const uint32_t dst_slot = dst_lane + slot * C::kCTileBytes;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int row = 4 * i + r4;
-          const int rid = __shfl_sync(0xffffffffu, i < 8 ? lo : hi, row & 31) + sense;
-          const uint8_t* src = tbase + rid * row_bytes;
-          const uint32_t dst = dst_slot + row * 128 + ((chunk ^ (row & 7)) << 4);
-          for (int pn = gw; pn < npan; pn += 2) cp_async16(dst + pn * C::kCPanelBytes, src + pn * 128);
+          const int rid = __shfl_sync(0xffffffffu, i < 8 ? lo : hi, ((4 * i) & 31) + r4) + sense;
+          const uint8_t* src = tb + static_cast<uint64_t>(static_cast<uint32_t>(rid)) * row_bytes;   // one IMAD.WIDE.U32
+          const uint32_t dst = dst_slot + i * 512 + ((i & 1) ? swz1 : swz0);
+          if (npw == 3) {   // the 384-column chunk of d = 768: three panels per warp, immediates only
+            cp_async16(dst, src);
+            cp_async16(dst + 2 * C::kCPanelBytes, src + 256);
+            cp_async16(dst + 4 * C::kCPanelBytes, src + 512);
+          } else {
+            for (int k = 0; k < npw; ++k) cp_async16(dst + 2 * k * C::kCPanelBytes, src + 256 * k);
+          }
         }
         cp_async_arrive_noinc(smem_u32(&bars.pa_go[slot]));
         lo = nlo, hi = nhi;
+        if (++slot == C::CS) {
+          slot = 0;
+          if (n >= C::CS) ph ^= 1;
+        }
       }
       asm volatile("cp.async.wait_all;" ::: "memory");   // nothing of this CTA may still be in flight at exit
     } else if (warp == 3) {
@@ -506,22 +516,19 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const int qs = qv % C::QS;
           if (qv >= C::QS) mbar_wait(&bars.q_empty[qs], ((qv / C::QS) - 1) & 1);
           ++qv;
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&bars.q_full[qs], C::kQTileBytes);
-            for (int pn = 0; pn < PK; ++pn)
-              tma_load_3d(smem + C::offQ + qs * C::kQTileBytes + pn * (BM * 128), &tmQ, &bars.q_full[qs], pn * 64,
-                          sense, tok0 + row0);
-          }
+          mbar_arrive_expect_tx_w(smem_u32(&bars.q_full[qs]), C::kQTileBytes);
+#pragma unroll
+          for (int pn = 0; pn < PK; ++pn)
+            tma_load_3d_w(smem_u32(smem + C::offQ) + qs * C::kQTileBytes + pn * (BM * 128), &tmQ, smem_u32(&bars.q_full[qs]),
+                          pn * 64, sense, tok0 + row0);
         }
         const int slot = n % C::KS;
         if (n >= C::KS) mbar_wait(&bars.k_empty[slot], ((n / C::KS) - 1) & 1);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&bars.k_full[slot], C::kKTileBytes);
-          for (int pn = 0; pn < PK; ++pn)
-            tma_load_3d(smem + C::offK + slot * C::kKTileBytes + pn * (BN * 128), &tmK, &bars.k_full[slot], pn * 64,
-                        p.nv + sense, tok0 + j * BN);
-        }
-        __syncwarp();
+        mbar_arrive_expect_tx_w(smem_u32(&bars.k_full[slot]), C::kKTileBytes);
+#pragma unroll
+        for (int pn = 0; pn < PK; ++pn)
+          tma_load_3d_w(smem_u32(smem + C::offK) + slot * C::kKTileBytes + pn * (BN * 128), &tmK, smem_u32(&bars.k_full[slot]),
+                        pn * 64, p.nv + sense, tok0 + j * BN);
       }
     } else if (warp == 1) {
       // ---- the issuer: PV(n), S(n+2), PV(n+1), S(n+3), ... ----
