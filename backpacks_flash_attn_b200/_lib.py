@@ -81,26 +81,28 @@ def total_launches() -> int:
 
 
 class KernelTimer:
-    """Optional CUDA-event bracket around one C-ABI entry point (used by bench.py to time the dominant
-    kernel live inside the timed region, on the launching stream).  Usage:
-        with KernelTimer("bp_fmha_fwd") as t: ...run steps...;  t.mean_ms()"""
+    """Optional CUDA-event bracket around one C-ABI entry point (used by bench.py to time every kernel of this library
+    live inside an eager pass, on the launching stream).  `key_fn(args)` groups the launches of one entry point
+    (e.g. the GEMM by its (n, k, activation)).  Usage:
+        with KernelTimer("bp_fmha_fwd") as t: ...run steps...;  t.mean_ms(), t.by_key()"""
 
-    def __init__(self, name: str):
+    def __init__(self, name: str, key_fn=None):
         self.name = name
+        self.key_fn = key_fn
         self.events: list = []
         self._orig = None
 
     def __enter__(self):
         lib = load()
         self._orig = getattr(lib, self.name)
-        orig, events = self._orig, self.events
+        orig, events, key_fn = self._orig, self.events, self.key_fn
 
         def timed(*args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             st = orig(*args)
             b.record()
-            events.append((a, b))
+            events.append((a, b, key_fn(args) if key_fn else None))
             return st
 
         setattr(lib, self.name, timed)
@@ -112,7 +114,16 @@ class KernelTimer:
 
     def mean_ms(self) -> float:
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in self.events) / max(1, len(self.events))
+        return sum(a.elapsed_time(b) for a, b, _ in self.events) / max(1, len(self.events))
+
+    def by_key(self) -> dict:
+        """{key: (launches, total ms)}"""
+        torch.cuda.synchronize()
+        out: dict = {}
+        for a, b, k in self.events:
+            n, t = out.get(k, (0, 0.0))
+            out[k] = (n + 1, t + a.elapsed_time(b))
+        return out
 
 
 def dtype_code(dtype: torch.dtype) -> int:

@@ -380,6 +380,16 @@ __device__ __forceinline__ void tma_load_3d_w(uint32_t smem_dst, const CUtensorM
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_w(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "@e cp.async.bulk.commit_group;\n\t}\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+      : "memory");
+}
+// wait until at most N of the bulk stores committed by the elected lane are still reading shared memory (executed by
+// every lane: lanes without outstanding groups return at once)
 __device__ __forceinline__ void tma_load_4d_w(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                               int c3) {
   asm volatile(

@@ -42,7 +42,22 @@ struct Params {
   int32_t m_tiles, n_tiles, k_blocks;
   int32_t act;
   int32_t residual_mode;   // pair kernel: the output map is the fp32 residual stream, updated in place (+=)
+  int32_t group_n;         // pair kernel: n-tiles per tile-order group (see tile_coords)
 };
+
+// Tile order of the pair kernel.  Tiles are walked in groups of `group_n` n-tiles: inside a group n-fastest, then m,
+// then the next group.  The clusters that run together therefore share one 256-row block of x, and the group's slice of
+// W (group_n x 256 rows) stays in L2 across all m-blocks.  group_n = min(n_tiles, #clusters): for every layer of the
+// model that is all of W (the order is then plain n-fastest); for the LM head (197 n-tiles, W = 77 MB next to a 6.6 GB
+// stream of logits through L2) W is read from HBM once instead of being re-fetched for every block of rows.
+__device__ __forceinline__ void tile_coords(const Params& p, int64_t tile, int& m_blk, int& n_blk) {
+  const int64_t per_group = static_cast<int64_t>(p.group_n) * p.m_tiles;
+  const int g = static_cast<int>(tile / per_group);
+  const int r = static_cast<int>(tile - g * per_group);
+  const int gn = min(p.group_n, p.n_tiles - g * p.group_n);   // the last group may be narrower
+  m_blk = r / gn;
+  n_blk = g * p.group_n + (r - m_blk * gn);
+}
 
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
@@ -299,8 +314,10 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint32_t slot = 0, ph = 0;   // parity of `empty` to wait for once the ring has wrapped: ((it / kStages) - 1) & 1
     bool wrapped = false;
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
-      const int n0 = static_cast<int>(tile % p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
+      const int n0 = n_blk * 256 + static_cast<int>(rank) * 128;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         if (wrapped) mbar_wait_a(bars_a + static_cast<uint32_t>(offsetof(pair::Barriers, empty)) + 8u * slot, ph);
         const uint32_t a = sbase + slot * pair::kStageBytes;
@@ -359,8 +376,10 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint32_t local = 0, chunk_it = 0;
     uint32_t res_phase[2] = {0, 0};
     for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
-      const int m0 = static_cast<int>(tile / p.n_tiles) * 256 + static_cast<int>(rank) * 128 + quad * 32;
-      const int n0 = static_cast<int>(tile % p.n_tiles) * 256 + hsel * 128;
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      const int m0 = m_blk * 256 + static_cast<int>(rank) * 128 + quad * 32;
+      const int n0 = n_blk * 256 + hsel * 128;
       const uint32_t buf = local & 1;
       if (p.residual_mode) {
         // the first two residual boxes (32 fp32 columns each) travel while the tile's main loop still runs
@@ -532,6 +551,7 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
   p.act = activation;
   p.residual_mode = residual != nullptr ? 1 : 0;
   p.n_tiles = (n + BN - 1) / BN;
+  p.group_n = p.n_tiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -545,6 +565,7 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
     p.m_tiles = static_cast<int32_t>((m + 255) / 256);
     const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
     const int clusters = static_cast<int>(tiles < sms / 2 ? tiles : sms / 2);
+    p.group_n = p.n_tiles < clusters ? p.n_tiles : clusters;
     // the W tile map of this variant has a 128-row box (each CTA loads half of the 256-wide tile) ...
     const uint32_t bb[2] = {BK, 128};
     if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;

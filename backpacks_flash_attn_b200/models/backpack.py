@@ -22,7 +22,7 @@ import torch.nn as nn
 from transformers import GPT2Config
 
 from ..modules.block import Block
-from ..ops.fused_dense import FusedDense
+from ..ops.fused_dense import FusedDense, linear
 from ..ops.sense_mix import sense_mix, sense_mix_table
 from .gpt import (CausalLMOutput, GPTModel, GPTPreTrainedModel, _init_weights, _no_tp, create_mlp_cls,
                   first_layer_norm, pad_vocab)
@@ -257,6 +257,9 @@ class BackpackLMHeadModel(BackpackPreTrainedModel):
 
     def forward(self, input_ids, position_ids=None, inference_params=None):
         hidden_states = self.transformer(input_ids, position_ids=position_ids, inference_params=inference_params)
+        if getattr(self.config, "fused_bias_fc", False):
+            # the tied LM head is a plain GEMM (backpack.py:339-340, 349): same kernel as every other linear
+            return CausalLMOutput(logits=linear(hidden_states, self.lm_head.weight, self.lm_head.bias))
         return CausalLMOutput(logits=self.lm_head(hidden_states))
 
 

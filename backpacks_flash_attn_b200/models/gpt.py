@@ -182,4 +182,7 @@ class GPTLMHeadModel(GPTPreTrainedModel):
 
     def forward(self, input_ids, position_ids=None, inference_params=None):
         hidden_states = self.transformer(input_ids, position_ids=position_ids, inference_params=inference_params)
+        if getattr(self.config, "fused_bias_fc", False):
+            from ..ops.fused_dense import linear
+            return CausalLMOutput(logits=linear(hidden_states, self.lm_head.weight, self.lm_head.bias))
         return CausalLMOutput(logits=self.lm_head(hidden_states))

@@ -1,11 +1,15 @@
 """`FusedDense` / `FusedDenseGeluDense` with the reference's interface (flash_attn/ops/fused_dense.py:116-129,
 357-402), forward only.
 
-* `FusedDense.forward` is a plain GEMM + bias in the reference too (F.linear, fused_dense.py:52,112): it
-  stays a library GEMM (cuBLASLt picks its own tcgen05 kernels on B200).
+* `FusedDense.forward` is a GEMM + bias (F.linear in the reference, fused_dense.py:52,112).  On the inference
+  path (CUDA, fp16/bf16, no autograd) it runs this library's tcgen05 GEMM, bp_linear_bias_act_fwd with
+  BP_ACT_NONE: measured on B200 against the cuBLAS call F.linear makes, at the model's shapes (m = 65536), it is
+  7 % faster for Wqkv, 2.5 % for out_proj, 14 % for the content model's (3072 -> 12288) projection and within
+  +-5 % for fc2 and the LM head (profiles/).  Under autograd, on the CPU or for shapes the kernel does not take
+  (n or k not a multiple of 8) it is F.linear, exactly as in the reference.
 * `FusedDenseGeluDense`: fc1 + bias + tanh-GELU is ONE kernel, bp_linear_bias_act_fwd -- the replacement of
   fused_dense_lib.linear_gelu_forward (csrc/fused_dense_lib/fused_dense.cpp:88-142) -- followed by the fc2
-  library GEMM (fused_dense.py:225).
+  GEMM (fused_dense.py:225).
 """
 from __future__ import annotations
 
@@ -91,10 +95,29 @@ def can_fuse_residual(x: torch.Tensor, weight: torch.Tensor, residual: torch.Ten
             and x.numel() // x.shape[-1] >= 256 and not torch.is_grad_enabled())
 
 
+def _own_gemm_ok(x, weight, bias) -> bool:
+    """Inference-path conditions of bp_linear_bias_act_fwd; anything else is the reference's F.linear."""
+    if not (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype):
+        return False
+    if bias is not None and (bias.dtype != x.dtype or bias.shape != (weight.shape[0],)):
+        return False
+    if weight.shape[0] % 8 or weight.shape[1] % 8 or x.numel() == 0:
+        return False
+    return not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
+                                             or (bias is not None and bias.requires_grad)))
+
+
+def linear(x, weight, bias=None):
+    """x @ weight.T + bias: this library's GEMM on the inference path, F.linear otherwise (see the module docstring)."""
+    if _own_gemm_ok(x, weight, bias):
+        return linear_bias_act(x, weight, bias, "none")
+    return F.linear(x, weight, bias)
+
+
 def fused_dense_func(x, weight, bias=None, return_residual=False, process_group=None):
     if process_group is not None:
         raise RuntimeError("tensor parallelism is out of scope for this path (batch sharding only)")
-    out = F.linear(x, weight, bias)
+    out = linear(x, weight, bias)
     return out if not return_residual else (out, x)
 
 
@@ -117,7 +140,7 @@ def fused_dense_gelu_dense_func(x, weight1, weight2, bias1=None, bias2=None, sav
     if process_group is not None:
         raise RuntimeError("tensor parallelism is out of scope for this path (batch sharding only)")
     hidden = linear_bias_act(x, weight1, bias1, "gelu_tanh")
-    out = F.linear(hidden, weight2, bias2)
+    out = linear(hidden, weight2, bias2)
     return out if not return_residual else (out, x)
 
 

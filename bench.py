@@ -7,17 +7,23 @@ name-seeded random weights.
 
 N > 1 is launched by torchrun (one process per GPU); the batch is sharded with no data-path collective
 (weak scaling: every rank runs B sequences).  Rank 0 prints ONE JSON line:
-  value    whole-job tokens/s with the ids resident in HBM (CUDA events, barrier + synchronize on both sides,
-           max over ranks).  The step is replayed as one CUDA graph (utils/graph.py; `--no-graph` launches every
-           kernel from Python instead) -- the same kernels on the same buffers, without the gaps between launches;
-  e2e      the same forward through the public API with HOST inputs: per step a pinned-host -> device copy of
-           the ids and a device -> host read of the last-position logits (what the reference's generation loop
-           consumes, training/src/utils/generation.py:34-44); the host reads step i while step i+1 runs;
-  roofline the kernel of this library with the largest share of the step, `kernels` all of them: average launch
-           durations from CUDA events recorded on the launching stream around every C-ABI call during an eager
-           pass of the same K steps (events cannot be recorded inside a graph replay), against the measured peaks;
+  value      whole-job tokens/s of the FULL forward (content model evaluated for every token, all 6.6 GB of logits
+             written) with the ids resident in HBM: CUDA events, barrier + synchronize on both sides, max over ranks.
+             The step is replayed as one CUDA graph (utils/graph.py; `--no-graph` launches from Python instead);
+  e2e        the same forward through the public API with HOST inputs: per step a pinned-host -> device copy of
+             the ids and a device -> host read of the last-position logits (what the reference's generation loop
+             consumes, training/src/utils/generation.py:34-44); the host reads step i while step i+1 runs;
+             `e2e_full_logits` is the same loop returning the API's WHOLE result (6.6 GB of logits per step over PCIe);
+  roofline   the kernel of this library with the largest share of the step (all launches of that kernel);
+  north_star the two kernels BASELINE.json's north_star names (fused attention, sense-mix) with both their tensor
+             and HBM fractions;  kernels: every kernel of the library, the GEMM split by shape;
+  own_kernel_share  time inside kernels of libbackpack_b200.so / step time;
+  variants.sense_table  the serving configuration (`serving_config()`: sense vectors gathered inside the sense-mix
+             kernel from a precomputed (vocab, nv, d) table instead of running the content model per token);
   cpu_baseline  the oracle port of the reference's pure-PyTorch path on the host cores (bounded sample).
-`--impl reference` times that CPU path alone (the reference's CUDA attention cannot run on sm_100, and its
+Per-kernel durations come from CUDA events recorded on the launching stream around every C-ABI call during an eager
+pass of the same K steps (events cannot be recorded inside a graph replay), against the measured peaks.
+`--impl reference` times the CPU path alone (the reference's CUDA attention cannot run on sm_100, and its
 Python cannot travel to the GPU box).
 """
 from __future__ import annotations
@@ -150,9 +156,10 @@ def cpu_reference_run(seqlen: int, steps: int, warmup: int, sample_batch: int = 
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
-    base, ms = cpu_reference_run(args.seqlen, args.steps, max(1, min(args.warmup, 2)))
+    steps = min(args.steps, 30)     # ~0.3 s per (1,1024) forward on 16 cores: a bounded sample of the workload
+    base, ms = cpu_reference_run(args.seqlen, steps, max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Backpack-Small forward, seq 1024, k=16, d=768; CPU arm runs a (1,1024) sample per step",
                        "seq_len": args.seqlen, "per_step_batch": 1},
@@ -167,9 +174,28 @@ def run_reference_arm(args, rank: int):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+OWN_ENTRY_POINTS = ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd", "bp_sense_mix_table_fwd",
+                    "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd", "bp_ln_residual_fwd", "bp_ln_fwd")
+
+
+def timed_steps(fn, steps, parallel, dev):
+    """K calls of fn bracketed by barrier + synchronize on both sides and one CUDA event pair; max over ranks (s)."""
+    parallel.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    return parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+
+
 def run_ours(args):
     from backpacks_flash_attn_b200 import _lib, parallel
     from backpacks_flash_attn_b200.models.backpack import BackpackLMHeadModel, flash_config
+    from backpacks_flash_attn_b200.utils.graph import GraphedForward
     from backpacks_flash_attn_b200.utils.weights import name_seeded_
 
     rank, local_rank, world = parallel.init_distributed()
@@ -179,33 +205,29 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     _lib.check(_lib.load().bp_check_device(), "bp_check_device", launched=False)
 
-    B, S = args.batch, args.seqlen
+    B, S, K = args.batch, args.seqlen, args.steps
     cfg = flash_config(**{**SMALL, "n_positions": max(1024, S)})
     model = name_seeded_(BackpackLMHeadModel(cfg).eval()).to(dev, torch.bfloat16)
     parallel.assert_replicas_match(model)
     ids_host = parallel.shard_batch(make_ids(B * world, S), rank, world).contiguous().pin_memory()
     ids_dev = ids_host.to(dev)
     last_host = torch.empty((2, B, cfg.vocab_size), dtype=torch.bfloat16).pin_memory()   # double-buffered results
-
-    graphed = None   # set after warm-up (capture needs inference_mode)
-
-    def step_resident():
-        return graphed() if graphed is not None else model(ids_dev).logits
-
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def run_e2e(steps):
+    def make_forward(use_graph):
+        """resident(): forward on the ids already in HBM;  from_host(): same with a pinned-host -> device copy first."""
+        if use_graph:
+            g = GraphedForward(model, ids_dev)
+            return (lambda: g()), (lambda: g(ids_host))
+        return (lambda: model(ids_dev).logits), (lambda: model(ids_host.to(dev, non_blocking=True)).logits)
+
+    def run_e2e(from_host, steps):
         """Serving loop through the public API with host buffers.  Every step copies its ids from pinned host
         memory and its last-position logits back to pinned host memory; the host waits for (consumes) the result
         of step i while step i+1 is already running, so the device never idles behind the host's launch loop."""
-        pending = None
-        checksum = 0.0
-        main = torch.cuda.current_stream()
+        pending, checksum, main = None, 0.0, torch.cuda.current_stream()
         for i in range(steps):
-            if graphed is not None:
-                logits = graphed(ids_host)               # pinned host -> static device input, graph replay
-            else:
-                logits = model(ids_host.to(dev, non_blocking=True)).logits
+            logits = from_host()
             last_dev = logits[:, -1].contiguous()
             del logits
             ready = torch.cuda.Event()
@@ -221,228 +243,231 @@ def run_ours(args):
                 checksum += float(last_host[pending[1], 0, 0])   # the host touches the result
             pending = (done, i % 2)
         pending[0].synchronize()
-        checksum += float(last_host[pending[1], 0, 0])
-        return checksum
+        return checksum + float(last_host[pending[1], 0, 0])
 
-    with torch.inference_mode():
-        for _ in range(args.warmup):
-            step_resident()
-        torch.cuda.synchronize()
-        if args.graph:
-            from backpacks_flash_attn_b200.utils.graph import GraphedForward
-            graphed = GraphedForward(model, ids_dev)
-            for _ in range(args.warmup):
-                step_resident()
-        # ---- timed region 1: inputs resident in HBM ----
-        with ClockSampler(physical_gpu_index(local_rank)) as clocks:
-            parallel.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                step_resident()
-            e1.record()
-            torch.cuda.synchronize()
-            parallel.barrier()
-        dt = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
-        tokens = parallel.sum_over_ranks(float(B * S * args.steps), dev)
-        # ---- kernel region: the same K steps launched from Python, every kernel of this library bracketed by CUDA
-        #      events on its stream (the per-kernel durations behind `roofline` / `kernels`) ----
-        graph_on, graphed = graphed, None                      # this region launches from Python
-        launches0 = _lib.total_launches()
-        per_kernel = {}
-        timers = [_lib.KernelTimer(n) for n in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd",
-                                                "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd",
-                                                "bp_ln_residual_fwd", "bp_ln_fwd")]
-        for t in timers:
-            t.__enter__()
-        parallel.barrier()
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(args.steps):
-            step_resident()
-        k1.record()
-        torch.cuda.synchronize()
-        for t in reversed(timers):
-            t.__exit__(None, None, None)
-        for t in timers:
-            per_kernel[t.name] = t.mean_ms()
-            per_kernel[t.name + ":n"] = len(t.events) / args.steps
-        launches = _lib.total_launches() - launches0          # per K steps; a graph replay launches the same kernels
-        dt_eager = parallel.max_over_ranks(k0.elapsed_time(k1) * 1e-3, dev)
-        graphed = graph_on
-        # ---- timed region 2: end to end through the public API with host buffers ----
-        run_e2e(2)
+    def time_e2e(from_host, steps):
+        run_e2e(from_host, 2)
         parallel.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        run_e2e(args.steps)
+        run_e2e(from_host, steps)
         g1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         parallel.barrier()
-        dt_e2e = parallel.max_over_ranks(max(g0.elapsed_time(g1) * 1e-3, wall), dev)
+        return parallel.max_over_ranks(max(g0.elapsed_time(g1) * 1e-3, wall), dev)
 
-        # ---- secondary variant: sense vectors gathered from a precomputed (vocab, nv, d) table ----
-        table_ms = None
+    with torch.inference_mode():
+        for _ in range(args.warmup):
+            model(ids_dev)
+        torch.cuda.synchronize()
+        resident, from_host = make_forward(args.graph)
+        for _ in range(args.warmup):
+            resident()
+        # ---- timed region 1: inputs resident in HBM ----
+        with ClockSampler(physical_gpu_index(local_rank)) as clocks:
+            dt = timed_steps(resident, K, parallel, dev)
+        tokens = parallel.sum_over_ranks(float(B * S * K), dev)
+
+        # ---- kernel region: the same K steps launched from Python, every kernel of this library bracketed by CUDA
+        #      events on its stream (the per-kernel durations behind `roofline` / `kernels` / `own_kernel_share`) ----
+        launches0 = _lib.total_launches()
+        gemm_key = lambda a: (int(a[5]), int(a[6]), int(a[7]))          # (n, k, activation) of bp_linear_bias_act_fwd
+        timers = {n: _lib.KernelTimer(n, gemm_key if n == "bp_linear_bias_act_fwd" else None) for n in OWN_ENTRY_POINTS}
+        for t in timers.values():
+            t.__enter__()
+        dt_eager = timed_steps(lambda: model(ids_dev), K, parallel, dev)
+        for t in reversed(list(timers.values())):
+            t.__exit__(None, None, None)
+        launches = _lib.total_launches() - launches0          # per K steps; a graph replay launches the same kernels
+        per_kernel = {n: (len(t.events) / K, t.mean_ms()) for n, t in timers.items()}      # (launches per step, ms)
+        gemm_by_shape = {k: (n / K, ms / max(n, 1)) for k, (n, ms) in timers["bp_linear_bias_act_fwd"].by_key().items()}
+
+        # ---- timed region 2: end to end through the public API with host buffers ----
+        dt_e2e = time_e2e(from_host, K)
+        # ---- the API's WHOLE result to the host (few steps: 6.6 GB over PCIe each) ----
+        full_ms = None
+        if args.full_logits_steps > 0 and world == 1:
+            full_host = torch.empty((B, S, cfg.vocab_size), dtype=torch.bfloat16).pin_memory()
+            for i in range(1 + args.full_logits_steps):
+                if i == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                full_host.copy_(from_host(), non_blocking=True)
+                torch.cuda.synchronize()
+            full_ms = (time.perf_counter() - t0) / args.full_logits_steps * 1e3
+            del full_host
+
+        # ---- variant: the serving configuration (sense vectors gathered inside the kernel from a table) ----
+        table = None
         if args.sense_table:
-            graphed = None                                    # the variant runs the eager launch sequence
+            model.transformer.use_sense_table = True
             model.transformer.build_sense_table()
             for _ in range(2):
-                step_resident()
-            parallel.barrier()
-            torch.cuda.synchronize()
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            h0.record()
-            for _ in range(args.steps):
-                step_resident()
-            h1.record()
-            torch.cuda.synchronize()
-            parallel.barrier()
-            table_ms = parallel.max_over_ranks(h0.elapsed_time(h1) * 1e-3, dev)
+                model(ids_dev)
+            t_resident, t_from_host = make_forward(args.graph)
+            for _ in range(2):
+                t_resident()
+            t_dt = timed_steps(t_resident, K, parallel, dev)
+            tt = {n: _lib.KernelTimer(n) for n in ("bp_sense_lse_fwd", "bp_sense_mix_table_fwd")}
+            for t in tt.values():
+                t.__enter__()
+            timed_steps(lambda: model(ids_dev), min(K, 20), parallel, dev)
+            for t in reversed(list(tt.values())):
+                t.__exit__(None, None, None)
+            t_e2e = time_e2e(t_from_host, K)
+            table = {"dt": t_dt, "e2e": t_e2e, "lse_ms": tt["bp_sense_lse_fwd"].mean_ms(),
+                     "mix_ms": tt["bp_sense_mix_table_fwd"].mean_ms()}
+            model.transformer.use_sense_table = False
             model.transformer.drop_sense_table()
 
     if rank != 0:
         return
     peaks = load_peaks()
+    peak_tf, peak_hbm = peaks["tf_sustained"], peaks["hbm_gbs"]
     h, dh, nv, d = cfg.n_head, cfg.n_embd // cfg.n_head, cfg.num_content_vectors, cfg.n_embd
-    # algorithmic work per launch (SURVEY.md §8d)
-    fmha_flops = 4 * B * h * S * S * dh / 2
-    fmha_bytes = 4 * B * S * h * dh * 2 + 4 * B * h * S
-    mix_flops = B * S * S * d * (1 + nv)
-    mix_bytes = (2 * B * S * d + nv * B * S * d + B * S * d) * 2
-    fmha_t = per_kernel["bp_fmha_fwd"] * 1e-3
-    mix_t = (per_kernel["bp_sense_lse_fwd"] + per_kernel["bp_sense_mix_fwd"]) * 1e-3
-    gemm_t = per_kernel["bp_linear_bias_act_fwd"] * 1e-3
-    ln_t = per_kernel["bp_ln_residual_fwd"] * 1e-3
-    peak_tf = peaks["tf_sustained"]
-    inner = cfg.n_inner or 4 * d
     M = B * S
-    gemm_flops = 2.0 * M * inner * d                          # every fused GEMM+GELU launch is (B*S, 4d, d)
-    gemm_bytes = (M * d + inner * d + M * inner) * 2
-    ln_bytes = M * d * (2 + 4) * 2                            # x0 bf16 + residual fp32 in, z bf16 + residual fp32 out
-    # GEMMs with the residual add in the epilogue: per layer out_proj (d x d) and fc2 (d x 4d), + the content
-    # block's fc2; the mean over the launches of a step is what the live timer measures
-    n_res = per_kernel["bp_linear_bias_residual_fwd:n"]
-    n_fc2 = (n_res + 1) // 2 if n_res else 0
-    n_out = n_res - n_fc2
-    res_flops = (n_out * 2.0 * M * d * d + n_fc2 * 2.0 * M * d * inner) / max(n_res, 1)
-    res_bytes = (n_out * (M * d * 2 + d * d * 2) + n_fc2 * (M * inner * 2 + inner * d * 2)) / max(n_res, 1) + M * d * 8
-    res_t = per_kernel["bp_linear_bias_residual_fwd"] * 1e-3
-    lnf_t = per_kernel["bp_ln_fwd"] * 1e-3
-    lnf_bytes = M * d * (4 + 2)                               # fp32 residual in, bf16 z out
+    step_ms = dt / K * 1e3
+    full_shape = (B, S) == (64, 1024)
 
-    def roof_tensor(flops, t):
+    def tensor_rec(name, flops, nbytes, n_per_step, ms, extra=None):
+        t = ms * 1e-3
         a = flops / t / 1e12
-        return {"bound": "tensor", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf}
+        rec = {"bound": "tensor", "achieved": a, "peak": peak_tf, "unit": "TFLOP/s", "frac": a / peak_tf, "kernel": name,
+               "launches_per_step": n_per_step, "ms_per_launch": ms, "ms_per_step": ms * n_per_step,
+               "algorithmic_gflop_per_launch": flops / 1e9, "algorithmic_mb_per_launch": nbytes / 1e6,
+               "hbm_gbs": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / peak_hbm}
+        rec.update(extra or {})
+        return rec
 
+    def hbm_rec(name, nbytes, n_per_step, ms):
+        a = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": peak_hbm, "unit": "GB/s", "frac": a / peak_hbm, "kernel": name,
+                "launches_per_step": n_per_step, "ms_per_launch": ms, "ms_per_step": ms * n_per_step,
+                "algorithmic_mb_per_launch": nbytes / 1e6}
+
+    # algorithmic work per launch (SURVEY.md §8d)
     kernels = {}
-    k = roof_tensor(fmha_flops, fmha_t)
-    k.update({"kernel": "fmha_fwd_kernel<64,bf16> (bp_fmha_fwd)", "launches_per_step": per_kernel["bp_fmha_fwd:n"],
-              "ms_per_launch": fmha_t * 1e3, "algorithmic_gflop_per_launch": fmha_flops / 1e9,
-              "algorithmic_mb_per_launch": fmha_bytes / 1e6, "hbm_gbs": fmha_bytes / fmha_t / 1e9,
-              "hbm_frac": fmha_bytes / fmha_t / 1e9 / peaks["hbm_gbs"],
-              "traffic": ncu_traffic("fmha_fwd_kernel") if (B, S) == (64, 1024) else None})
-    kernels["fmha"] = k
-    k = roof_tensor(mix_flops, mix_t)
-    k.update({"kernel": "sense_lse_kernel + sense_mix_kernel (bp_sense_lse_fwd, bp_sense_mix_fwd)",
-              "launches_per_step": 1, "ms_per_launch": mix_t * 1e3, "ms_lse": per_kernel["bp_sense_lse_fwd"],
-              "ms_mix": per_kernel["bp_sense_mix_fwd"], "algorithmic_gflop_per_launch": mix_flops / 1e9,
-              "algorithmic_mb_per_launch": mix_bytes / 1e6,
-              "traffic": ncu_traffic("sense_mix_kernel") if (B, S) == (64, 1024) else None})
-    kernels["sense_mix"] = k
-    k = roof_tensor(gemm_flops, gemm_t)
-    k.update({"kernel": "gemm_bias_act_pair_kernel<bf16> (bp_linear_bias_act_fwd), fc1 + bias + tanh-GELU",
-              "launches_per_step": per_kernel["bp_linear_bias_act_fwd:n"], "ms_per_launch": gemm_t * 1e3,
-              "algorithmic_gflop_per_launch": gemm_flops / 1e9, "algorithmic_mb_per_launch": gemm_bytes / 1e6,
-              "traffic": ncu_traffic("gemm_bias_act_pair_kernel") if (B, S) == (64, 1024) else None})
-    kernels["gemm_bias_gelu"] = k
-    a = ln_bytes / ln_t / 1e9
-    kernels["ln_residual"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                              "frac": a / peaks["hbm_gbs"], "kernel": "ln_residual_fwd_kernel (bp_ln_residual_fwd)",
-                              "launches_per_step": per_kernel["bp_ln_residual_fwd:n"], "ms_per_launch": ln_t * 1e3,
-                              "algorithmic_mb_per_launch": ln_bytes / 1e6,
-                              "traffic": ncu_traffic("ln_residual_fwd_kernel") if (B, S) == (64, 1024) else None}
-    if n_res:
-        k = roof_tensor(res_flops, res_t)
-        k.update({"kernel": "gemm_bias_act_pair_kernel<bf16>, residual epilogue (bp_linear_bias_residual_fwd): out_proj "
-                            "and fc2 with the fp32 residual add in the epilogue",
-                  "launches_per_step": n_res, "ms_per_launch": res_t * 1e3,
-                  "algorithmic_gflop_per_launch": res_flops / 1e9, "algorithmic_mb_per_launch": res_bytes / 1e6,
-                  "hbm_frac": res_bytes / res_t / 1e9 / peaks["hbm_gbs"], "traffic": None})
-        kernels["gemm_bias_residual"] = k
-    if per_kernel["bp_ln_fwd:n"]:
-        a = lnf_bytes / lnf_t / 1e9
-        kernels["ln_from_residual"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                       "frac": a / peaks["hbm_gbs"], "kernel": "ln_residual_fwd_kernel<float -> bf16> (bp_ln_fwd)",
-                                       "launches_per_step": per_kernel["bp_ln_fwd:n"], "ms_per_launch": lnf_t * 1e3,
-                                       "algorithmic_mb_per_launch": lnf_bytes / 1e6, "traffic": None}
+    n_f, ms_f = per_kernel["bp_fmha_fwd"]
+    kernels["fmha"] = tensor_rec("fmha_fwd_kernel<64,bf16> (bp_fmha_fwd)", 4 * B * h * S * S * dh / 2,
+                                 4 * B * S * h * dh * 2 + 4 * B * h * S, n_f, ms_f,
+                                 {"traffic": ncu_traffic("fmha_fwd_kernel") if full_shape else None})
+    ms_lse, ms_mix = per_kernel["bp_sense_lse_fwd"][1], per_kernel["bp_sense_mix_fwd"][1]
+    mix_flops, mix_bytes = B * S * S * d * (1 + nv), (2 * B * S * d + nv * B * S * d + B * S * d) * 2
+    kernels["sense_mix"] = tensor_rec("sense_lse_kernel + sense_mix_kernel (bp_sense_lse_fwd, bp_sense_mix_fwd)",
+                                      mix_flops, mix_bytes, 1, ms_lse + ms_mix,
+                                      {"ms_lse": ms_lse, "ms_mix": ms_mix,
+                                       "traffic": ncu_traffic("sense_mix_kernel") if full_shape else None})
+    gemm_names = {(3 * d, d, 0): "Wqkv", (d, d, 0): "out_proj", (d, 4 * d, 0): "fc2", (4 * d, d, 1): "fc1 + bias + tanh-GELU",
+                  (2 * d, d, 0): "ctx Wqkv", (nv * d, 4 * d, 0): "content final_mlp.fc2", (cfg.vocab_size, d, 0): "tied LM head"}
+    gemm_total_ms = gemm_total_flops = gemm_total_bytes = gemm_total_n = 0.0
+    for (n, k, act), (cnt, ms) in sorted(gemm_by_shape.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+        flops, nbytes = 2.0 * M * n * k, (M * k + n * k + M * n) * 2.0
+        name = gemm_names.get((n, k, act), f"n{n} k{k} act{act}")
+        kernels[f"gemm[{name}]"] = tensor_rec(f"gemm_bias_act_pair_kernel<bf16> (bp_linear_bias_act_fwd): {name}, "
+                                              f"(m, n, k) = ({M}, {n}, {k})", flops, nbytes, cnt, ms)
+        gemm_total_ms += cnt * ms
+        gemm_total_flops += cnt * flops
+        gemm_total_bytes += cnt * nbytes
+        gemm_total_n += cnt
+    n_ln, ms_ln = per_kernel["bp_ln_residual_fwd"]
+    kernels["ln_residual"] = hbm_rec("ln_residual_fwd_kernel (bp_ln_residual_fwd)", M * d * (2 + 4) * 2, n_ln, ms_ln)
+    kernels["ln_residual"]["traffic"] = ncu_traffic("ln_residual_fwd_kernel") if full_shape else None
+    for nm in ("bp_linear_bias_residual_fwd", "bp_ln_fwd"):
+        if per_kernel[nm][0]:
+            kernels[nm] = {"launches_per_step": per_kernel[nm][0], "ms_per_launch": per_kernel[nm][1],
+                           "ms_per_step": per_kernel[nm][0] * per_kernel[nm][1]}
+    # all launches of the GEMM kernel as one record (it is ONE kernel; the shapes above are its breakdown)
+    gemm_all = tensor_rec("gemm_bias_act_pair_kernel<bf16> (bp_linear_bias_act_fwd), all launches of a step: every linear "
+                          "of the model incl. fc1+GELU, the content model's 3072->12288 projection and the tied LM head",
+                          gemm_total_flops / max(gemm_total_n, 1), gemm_total_bytes / max(gemm_total_n, 1), gemm_total_n,
+                          gemm_total_ms / max(gemm_total_n, 1),
+                          {"traffic": None, "traffic_note": "per-shape ncu captures are summarised under profiles/"})
+    own_ms = sum(v["ms_per_step"] for kname, v in kernels.items())
     for v in kernels.values():
-        v["ms_per_step"] = v["ms_per_launch"] * v["launches_per_step"]
-        v["traffic_unit"] = "DRAM bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)"
-    # `roofline` = the kernel of this library with the largest share of the step
-    dominant = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
-    roofline = dict(kernels[dominant])
-    roofline["dominant_of"] = {n: round(v["ms_per_step"], 3) for n, v in kernels.items()}
+        v.setdefault("traffic_unit", "DRAM bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)")
+    candidates = {"gemm": gemm_all, "fmha": kernels["fmha"], "sense_mix": kernels["sense_mix"],
+                  "ln_residual": kernels["ln_residual"]}
+    dominant = max(candidates, key=lambda n: candidates[n]["ms_per_step"])
+    roofline = dict(candidates[dominant])
+    roofline["dominant_of"] = {n: round(v["ms_per_step"], 3) for n, v in candidates.items()}
     roofline["peak_source"] = (f"MEASURED_PEAKS.json ({peaks['source']}): bf16_tflops_sustained for tensor-bound kernels "
                                "(timed inside a long step), hbm_gbs for HBM-bound ones")
+    north_star = {k: {kk: kernels[k][kk] for kk in ("kernel", "frac", "achieved", "unit", "hbm_frac", "hbm_gbs",
+                                                    "ms_per_launch", "launches_per_step", "ms_per_step")}
+                  for k in ("fmha", "sense_mix")}
     model_flops_per_token = 371.3e6   # SURVEY.md §8d, s = 1024
     cpu_base, _ = cpu_reference_run(S, steps=3, warmup=1)
     value = tokens / dt
     line = {
-        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Backpack-Small forward (BASELINE configs[2]; configs[3] when n_gpus=8)",
+        "config": {"workload": "Backpack-Small forward (BASELINE configs[2]; configs[3] when n_gpus=8): full model, "
+                               "content model evaluated per token, all logits written",
                    "batch_per_gpu": B, "global_batch": B * world, "seq_len": S, "d_model": d, "n_layer": cfg.n_layer,
                    "n_head": h, "num_content_vectors": nv, "vocab": cfg.vocab_size, "parallelism": f"dp{world}",
                    "weights": "name-seeded random (SURVEY.md §8c recipe), bf16",
                    "execution": ("one CUDA graph per step (utils/graph.py); the eager launch sequence of the same "
-                                 f"kernels, with an event pair recorded around each of them, takes {dt_eager / args.steps * 1e3:.3f} ms per step" if args.graph
-                                 else "eager launches from Python"),
+                                 f"kernels, with an event pair recorded around each of them, takes {dt_eager / K * 1e3:.3f} ms per step"
+                                 if args.graph else "eager launches from Python"),
                    "kernel_timings": "per-kernel CUDA events around an eager pass of the same K steps on the same inputs",
                    "l2": "no flush: each step streams > 10 GB of activations (6.6 GB logits, 1.6 GB sense vectors) "
                          "through a 126 MB L2"},
         "e2e": {"value": tokens / dt_e2e, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * 8 * world,
-                "d2h_bytes_per_step": last_host[0].numel() * 2 * world, "ms_per_step": dt_e2e / args.steps * 1e3,
-                "result": "last-position logits (batch, vocab) bf16 copied to pinned host memory every step; the host reads step i while step i+1 runs (two pinned result buffers)"},
+                "d2h_bytes_per_step": last_host[0].numel() * 2 * world, "ms_per_step": dt_e2e / K * 1e3,
+                "result": "last-position logits (batch, vocab) bf16 copied to pinned host memory every step; the host reads "
+                          "step i while step i+1 runs (two pinned result buffers)"},
         "gpu_launches": launches * world,
-        "gpu_launches_per_step_per_gpu": launches / args.steps,
+        "gpu_launches_per_step_per_gpu": launches / K,
         "gpu_launches_note": "kernels of libbackpack_b200.so inside the timed region, all ranks (per GPU and step: "
-                             + ", ".join(f"{per_kernel[n + ':n']:g} {n}" for n in (
-                                 "bp_fmha_fwd", "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd", "bp_ln_fwd",
-                                 "bp_ln_residual_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd"))
-                             + "); library GEMMs / gathers not counted",
+                             + ", ".join(f"{per_kernel[n][0]:g} {n}" for n in OWN_ENTRY_POINTS if per_kernel[n][0])
+                             + "); embedding gathers / element-wise ATen kernels not counted",
+        "own_kernel_share": own_ms / step_ms,
+        "own_kernel_ms_per_step": own_ms,
         "roofline": roofline,
+        "north_star": north_star,
         "kernels": kernels,
         "model_mfu": {"achieved_tflops": value / world * model_flops_per_token / 1e12,
                       "frac_of_sustained_peak": value / world * model_flops_per_token / 1e12 / peak_tf},
         "cpu_baseline": cpu_base,
         "clocks": clocks.summary(),
     }
-    if table_ms is not None:
+    if full_ms is not None:
+        line["e2e_full_logits"] = {
+            "value": B * S / (full_ms * 1e-3), "unit": "tokens/s", "ms_per_step": full_ms,
+            "h2d_bytes_per_step": ids_host.numel() * 8, "d2h_bytes_per_step": B * S * cfg.vocab_size * 2,
+            "steps": args.full_logits_steps,
+            "note": "the API's whole result (batch, seq, vocab) bf16 copied to pinned host memory every step: bound by the "
+                    "host link (6.6 GB per step), not by the GPU; no caller of the reference consumes it on the host"}
+    if table is not None:
         line["variants"] = {"sense_table": {
-            "value": tokens / table_ms, "unit": "tokens/s", "ms_per_step": table_ms / args.steps * 1e3,
-            "note": "inference-only: content model replaced by a gather from a precomputed (vocab, nv, d) table of "
-                    "sense vectors (context-free by construction, backpack.py:258); NOT the headline value"}}
+            "value": tokens / table["dt"], "unit": "tokens/s", "ms_per_step": table["dt"] / K * 1e3,
+            "e2e": {"value": tokens / table["e2e"], "unit": "tokens/s", "ms_per_step": table["e2e"] / K * 1e3},
+            "sense_mix_ms": {"lse": table["lse_ms"], "mix_table": table["mix_ms"]},
+            "sense_mix_frac_of_tensor_peak": mix_flops / ((table["lse_ms"] + table["mix_ms"]) * 1e-3) / 1e12 / peak_tf,
+            "note": "serving_config(): identical logits; the content model (24 % of the model's FLOPs) runs once per "
+                    "vocabulary item instead of once per token and bp_sense_mix_table_fwd gathers the rows inside the "
+                    "kernel (no (b, s, nv, d) tensor in HBM).  Reported as a variant: `value` above is the full forward"}}
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU")
     ap.add_argument("--seqlen", type=int, default=1024)
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--no-sense-table", dest="sense_table", action="store_false",
-                    help="skip the secondary sense-vector-table variant")
+                    help="skip the serving-configuration variant")
+    ap.add_argument("--full-logits-steps", type=int, default=3,
+                    help="steps of the whole-logits-to-host loop (0 = skip; single GPU only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -170,10 +170,31 @@ def bench_gemm(iters, m=65536, n=3072, k=768):
     return rec
 
 
+def bench_gemms(iters):
+    """Every linear of the Backpack-Small forward at config 3 (m = 65536 rows): this library's tcgen05 GEMM (plain
+    epilogue: + bias) next to the cuBLAS call `F.linear` makes.  One JSON line per shape."""
+    from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_act
+    m = 65536
+    shapes = [("Wqkv", 2304, 768), ("out_proj", 768, 768), ("fc2", 768, 3072), ("fc1 (plain)", 3072, 768),
+              ("ctx Wqkv", 1536, 768), ("final_mlp.fc2", 12288, 3072), ("lm_head (no bias)", 50264, 768)]
+    for name, n, k in shapes:
+        x = torch.randn(m, k, device="cuda").bfloat16()
+        w = (torch.randn(n, k, device="cuda") * k ** -0.5).bfloat16()
+        bias = None if "no bias" in name else torch.randn(n, device="cuda").bfloat16()
+        it = max(4, iters // 4) if n > 8000 else iters
+        t_own, _ = time_fn(lambda i: linear_bias_act(x, w, bias, "none"), 1, it, inner=4)
+        t_lib, _ = time_fn(lambda i: torch.nn.functional.linear(x, w, bias), 1, it, inner=4)
+        flops = 2.0 * m * n * k
+        print(json.dumps({"gemm": name, "m": m, "n": n, "k": k, "own_us": t_own * 1e6, "cublas_us": t_lib * 1e6,
+                          "own_tflops": flops / t_own / 1e12, "cublas_tflops": flops / t_lib / 1e12,
+                          "own_over_cublas_time": t_own / t_lib}), flush=True)
+        del x, w
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="fmha,sense,ln,gemm")
     ap.add_argument("--iters", type=int, default=20)
     a = ap.parse_args()
     for w in a.which.split(","):
-        {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm}[w](a.iters)
+        {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms}[w](a.iters)

@@ -16,6 +16,7 @@ for tag in "" p2; do
   BP_LIB_TAG=$tag timeout 600 python benchmarks/bench_kernels.py --which $which > $O/${R}_kernels_${tag:-prod}.jsonl 2>&1
   echo "-- ${tag:-prod}"; cut -c1-150 $O/${R}_kernels_${tag:-prod}.jsonl | grep -v "^Traceback" | head -16
 done
+echo "== gemms"; timeout 600 python benchmarks/bench_kernels.py --which gemms > $O/${R}_gemms.jsonl 2>&1; cut -c1-200 $O/${R}_gemms.jsonl
 echo "== sweep"; timeout 900 python benchmarks/sweep.py > $O/${R}_sweep.jsonl 2>&1; cut -c1-120 $O/${R}_sweep.jsonl | head -24
 if [ -f backpacks_flash_attn_b200/libbackpack_b200_trace.so ]; then
   echo "== traces"
@@ -23,4 +24,9 @@ if [ -f backpacks_flash_attn_b200/libbackpack_b200_trace.so ]; then
   BP_LIB_TAG=trace timeout 300 python benchmarks/trace_kernel.py sense > $O/${R}_trace_sense.txt 2>&1; tail -2 $O/${R}_trace_sense.txt
   BP_LIB_TAG=trace timeout 300 python benchmarks/trace_kernel.py sense_table > $O/${R}_trace_sense_table.txt 2>&1; tail -2 $O/${R}_trace_sense_table.txt
 fi
-echo "== bench"; timeout 1200 python bench.py > $O/${R}_bench_n1.json 2> $O/${R}_bench.err; tail -3 $O/${R}_bench.err; cut -c1-400 $O/${R}_bench_n1.json
+echo "== bench"; timeout 1200 python bench.py > $O/${R}_bench_n1.json 2> $O/${R}_bench.err; tail -3 $O/${R}_bench.err; cut -c1-300 $O/${R}_bench_n1.json; python - <<PY
+import json
+d=json.load(open("$O/${R}_bench_n1.json"))
+print("ms/step", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "own share", d["own_kernel_share"], "table", d.get("variants",{}).get("sense_table",{}).get("ms_per_step"), "full", d.get("e2e_full_logits",{}).get("ms_per_step"))
+for k,v in d["kernels"].items(): print(f"  {k:40s} n={v['launches_per_step']:5.1f} ms={v['ms_per_launch']:.4f} step={v['ms_per_step']:.3f} frac={v.get('frac')}")
+PY
