@@ -107,10 +107,33 @@ def _own_gemm_ok(x, weight, bias) -> bool:
                                              or (bias is not None and bias.requires_grad)))
 
 
+# Which GEMM serves the plain linears on the inference path: "own" (bp_linear_bias_act_fwd), "library" (F.linear ->
+# cuBLAS, what the reference calls), or a per-shape choice {(n, k): "own" | "library"} with "own" as the default.
+# Model factories set it from `config.linear_backend`; tests and bench.py use set_linear_backend().
+_backend = "own"
+_timing_hook = None      # bench.py: callable(tag, n, k) -> context manager bracketing the library GEMM with CUDA events
+
+
+def set_linear_backend(backend) -> None:
+    global _backend
+    if not (backend in ("own", "library") or isinstance(backend, dict)):
+        raise ValueError('linear backend must be "own", "library" or a {(n, k): backend} dict')
+    _backend = backend
+
+
+def get_linear_backend():
+    return _backend
+
+
 def linear(x, weight, bias=None):
     """x @ weight.T + bias: this library's GEMM on the inference path, F.linear otherwise (see the module docstring)."""
-    if _own_gemm_ok(x, weight, bias):
+    n, k = weight.shape
+    choice = _backend.get((n, k), "own") if isinstance(_backend, dict) else _backend
+    if choice == "own" and _own_gemm_ok(x, weight, bias):
         return linear_bias_act(x, weight, bias, "none")
+    if _timing_hook is not None and x.is_cuda:
+        with _timing_hook("F.linear", n, k):
+            return F.linear(x, weight, bias)
     return F.linear(x, weight, bias)
 
 

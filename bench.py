@@ -287,6 +287,42 @@ def run_ours(args):
 
         # ---- timed region 2: end to end through the public API with host buffers ----
         dt_e2e = time_e2e(from_host, K)
+
+        # ---- variant: the plain linears on the library GEMM (F.linear -> cuBLAS, what the reference calls), with every
+        #      library GEMM of an eager pass bracketed by events like the own kernels above ----
+        lib_linear = None
+        if args.library_linears:
+            from backpacks_flash_attn_b200.ops import fused_dense as FD
+            lib_events = {}
+
+            class _Bracket:
+                def __init__(self, tag, n, k):
+                    self.key = (n, k)
+
+                def __enter__(self):
+                    self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    self.a.record()
+
+                def __exit__(self, *exc):
+                    self.b.record()
+                    lib_events.setdefault(self.key, []).append((self.a, self.b))
+                    return False
+
+            FD.set_linear_backend("library")
+            for _ in range(2):
+                model(ids_dev)
+            l_resident, _ = make_forward(args.graph)
+            for _ in range(2):
+                l_resident()
+            l_dt = timed_steps(l_resident, K, parallel, dev)
+            FD._timing_hook = _Bracket
+            kk = min(K, 20)
+            timed_steps(lambda: model(ids_dev), kk, parallel, dev)
+            FD._timing_hook = None
+            FD.set_linear_backend("own")
+            torch.cuda.synchronize()
+            lib_linear = {"dt": l_dt, "per_shape": {k: (len(v) / kk, sum(a.elapsed_time(b) for a, b in v) / len(v))
+                                                    for k, v in lib_events.items()}}
         # ---- the API's WHOLE result to the host (few steps: 6.6 GB over PCIe each) ----
         full_ms = None
         if args.full_logits_steps > 0 and world == 1:
@@ -442,15 +478,24 @@ def run_ours(args):
             "steps": args.full_logits_steps,
             "note": "the API's whole result (batch, seq, vocab) bf16 copied to pinned host memory every step: bound by the "
                     "host link (6.6 GB per step), not by the GPU; no caller of the reference consumes it on the host"}
+    line["variants"] = {}
+    if lib_linear is not None:
+        line["variants"]["library_linears"] = {
+            "value": tokens / lib_linear["dt"], "unit": "tokens/s", "ms_per_step": lib_linear["dt"] / K * 1e3,
+            "per_shape_ms": {f"n{n} k{k}": {"launches_per_step": c, "cublas_ms": ms,
+                                             "own_ms": gemm_by_shape.get((n, k, 0), (0, None))[1]}
+                             for (n, k), (c, ms) in lib_linear["per_shape"].items()},
+            "note": "same forward with Wqkv / out_proj / fc2 / content projection / LM head on F.linear (cuBLAS), as the "
+                    "reference's FusedDense.forward does (flash_attn/ops/fused_dense.py:52,112); fc1+GELU stays fused"}
     if table is not None:
-        line["variants"] = {"sense_table": {
+        line["variants"]["sense_table"] = {
             "value": tokens / table["dt"], "unit": "tokens/s", "ms_per_step": table["dt"] / K * 1e3,
             "e2e": {"value": tokens / table["e2e"], "unit": "tokens/s", "ms_per_step": table["e2e"] / K * 1e3},
             "sense_mix_ms": {"lse": table["lse_ms"], "mix_table": table["mix_ms"]},
             "sense_mix_frac_of_tensor_peak": mix_flops / ((table["lse_ms"] + table["mix_ms"]) * 1e-3) / 1e12 / peak_tf,
             "note": "serving_config(): identical logits; the content model (24 % of the model's FLOPs) runs once per "
                     "vocabulary item instead of once per token and bp_sense_mix_table_fwd gathers the rows inside the "
-                    "kernel (no (b, s, nv, d) tensor in HBM).  Reported as a variant: `value` above is the full forward"}}
+                    "kernel (no (b, s, nv, d) tensor in HBM).  Reported as a variant: `value` above is the full forward"}
     print(json.dumps(line), flush=True)
 
 
@@ -466,6 +511,8 @@ def main():
                     help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--no-sense-table", dest="sense_table", action="store_false",
                     help="skip the serving-configuration variant")
+    ap.add_argument("--no-library-linears", dest="library_linears", action="store_false",
+                    help="skip the variant that runs the plain linears on cuBLAS")
     ap.add_argument("--full-logits-steps", type=int, default=3,
                     help="steps of the whole-logits-to-host loop (0 = skip; single GPU only)")
     args = ap.parse_args()

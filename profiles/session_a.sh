@@ -27,6 +27,6 @@ fi
 echo "== bench"; timeout 1200 python bench.py > $O/${R}_bench_n1.json 2> $O/${R}_bench.err; tail -3 $O/${R}_bench.err; cut -c1-300 $O/${R}_bench_n1.json; python - <<PY
 import json
 d=json.load(open("$O/${R}_bench_n1.json"))
-print("ms/step", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "own share", d["own_kernel_share"], "table", d.get("variants",{}).get("sense_table",{}).get("ms_per_step"), "full", d.get("e2e_full_logits",{}).get("ms_per_step"))
+print("lib linears", {k:(round(v["cublas_ms"],4), v["own_ms"] and round(v["own_ms"],4)) for k,v in d["variants"].get("library_linears",{}).get("per_shape_ms",{}).items()}, d["variants"].get("library_linears",{}).get("ms_per_step")); print("ms/step", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "own share", d["own_kernel_share"], "table", d.get("variants",{}).get("sense_table",{}).get("ms_per_step"), "full", d.get("e2e_full_logits",{}).get("ms_per_step"))
 for k,v in d["kernels"].items(): print(f"  {k:40s} n={v['launches_per_step']:5.1f} ms={v['ms_per_launch']:.4f} step={v['ms_per_step']:.3f} frac={v.get('frac')}")
 PY
