@@ -156,7 +156,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, 0x4E20;\n\t"   // suspend-time hint (20 us): sleep in hardware instead of spinning; wakes when the phase completes
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -176,13 +176,24 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Blocking wait.  A pipeline bug would otherwise hang the GPU until the watchdog fires; after ~16M failed
-// polls (orders of magnitude beyond any legitimate wait in these kernels) the kernel traps instead, which
-// surfaces as a CUDA launch failure on the host.
+// Blocking wait.  A pipeline bug would otherwise hang the GPU until the watchdog fires; after 4 s of failed polls
+// (orders of magnitude beyond any legitimate wait in these kernels) the kernel traps instead, which surfaces as a
+// CUDA launch failure on the host.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kWaitTimeoutNs = 4000000000ull;   // 4 s: orders of magnitude beyond any legitimate wait
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 24)) __trap();
+    if ((++polls & 1023u) == 0) {   // a failed try_wait has slept for up to the suspend-time hint
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) __trap();
+    }
   }
 }
 
@@ -199,7 +210,7 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, 0x4E20;\n\t"   // suspend-time hint (20 us): sleep in hardware instead of spinning; wakes when the phase completes
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -222,6 +233,8 @@ __device__ int g_debug_abort = 0;
 #endif
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
+  uint64_t t0 = 0;
+  (void)t0;
   while (!mbar_try_wait_a(bar, parity)) {
 #ifdef BP_DEBUG_WAIT
     // debug builds: report the stuck barrier (with its raw state word) and carry on (results are garbage)
@@ -236,7 +249,11 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       return;
     }
 #else
-    if (++polls > (1u << 24)) __trap();
+    if ((++polls & 1023u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) __trap();
+    }
 #endif
   }
 }

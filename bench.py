@@ -291,6 +291,7 @@ def run_ours(args):
         # ---- variant: the plain linears on the library GEMM (F.linear -> cuBLAS, what the reference calls), with every
         #      library GEMM of an eager pass bracketed by events like the own kernels above ----
         lib_linear = None
+        policy_ms = {}
         if args.library_linears:
             from backpacks_flash_attn_b200.ops import fused_dense as FD
             lib_events = {}
@@ -308,21 +309,27 @@ def run_ours(args):
                     lib_events.setdefault(self.key, []).append((self.a, self.b))
                     return False
 
-            FD.set_linear_backend("library")
-            for _ in range(2):
-                model(ids_dev)
-            l_resident, _ = make_forward(args.graph)
-            for _ in range(2):
-                l_resident()
-            l_dt = timed_steps(l_resident, K, parallel, dev)
-            FD._timing_hook = _Bracket
-            kk = min(K, 20)
-            timed_steps(lambda: model(ids_dev), kk, parallel, dev)
-            FD._timing_hook = None
-            FD.set_linear_backend("own")
-            torch.cuda.synchronize()
-            lib_linear = {"dt": l_dt, "per_shape": {k: (len(v) / kk, sum(a.elapsed_time(b) for a, b in v) / len(v))
-                                                    for k, v in lib_events.items()}}
+            default_backend = FD.get_linear_backend()
+            mixed = {(cfg.n_embd, 4 * cfg.n_embd): "library", (cfg.vocab_size, cfg.n_embd): "library"}
+            for pname, policy in (("library", "library"), ("own", "own"), ("own_except_fc2_lmhead", mixed)):
+                FD.set_linear_backend(policy)
+                for _ in range(2):
+                    model(ids_dev)
+                l_resident, _ = make_forward(args.graph)
+                for _ in range(2):
+                    l_resident()
+                policy_ms[pname] = timed_steps(l_resident, K, parallel, dev) / K * 1e3
+                if pname == "library":
+                    FD._timing_hook = _Bracket
+                    kk = min(K, 20)
+                    timed_steps(lambda: model(ids_dev), kk, parallel, dev)
+                    FD._timing_hook = None
+                    torch.cuda.synchronize()
+                    lib_linear = {"per_shape": {k: (len(v) / kk, sum(a.elapsed_time(b) for a, b in v) / len(v))
+                                                for k, v in lib_events.items()}}
+                del l_resident
+            FD.set_linear_backend(default_backend)
+
         # ---- the API's WHOLE result to the host (few steps: 6.6 GB over PCIe each) ----
         full_ms = None
         if args.full_logits_steps > 0 and world == 1:
@@ -480,13 +487,15 @@ def run_ours(args):
                     "host link (6.6 GB per step), not by the GPU; no caller of the reference consumes it on the host"}
     line["variants"] = {}
     if lib_linear is not None:
-        line["variants"]["library_linears"] = {
-            "value": tokens / lib_linear["dt"], "unit": "tokens/s", "ms_per_step": lib_linear["dt"] / K * 1e3,
+        line["variants"]["linear_backends"] = {
+            "ms_per_step": policy_ms,
             "per_shape_ms": {f"n{n} k{k}": {"launches_per_step": c, "cublas_ms": ms,
                                              "own_ms": gemm_by_shape.get((n, k, 0), (0, None))[1]}
                              for (n, k), (c, ms) in lib_linear["per_shape"].items()},
-            "note": "same forward with Wqkv / out_proj / fc2 / content projection / LM head on F.linear (cuBLAS), as the "
-                    "reference's FusedDense.forward does (flash_attn/ops/fused_dense.py:52,112); fc1+GELU stays fused"}
+            "note": "the same forward (one CUDA graph per step) with the plain linears (Wqkv / out_proj / fc2 / content "
+                    "projection / LM head) on F.linear = cuBLAS, as the reference's FusedDense.forward does "
+                    "(flash_attn/ops/fused_dense.py:52,112), on this library's GEMM, or mixed; fc1+GELU is always fused. "
+                    "per_shape_ms: CUDA events around every GEMM of an eager pass"}
     if table is not None:
         line["variants"]["sense_table"] = {
             "value": tokens / table["dt"], "unit": "tokens/s", "ms_per_step": table["dt"] / K * 1e3,
