@@ -2,11 +2,10 @@
 357-402), forward only.
 
 * `FusedDense.forward` is a GEMM + bias (F.linear in the reference, fused_dense.py:52,112).  On the inference
-  path (CUDA, fp16/bf16, no autograd) it runs this library's tcgen05 GEMM, bp_linear_bias_act_fwd with
-  BP_ACT_NONE: measured on B200 against the cuBLAS call F.linear makes, at the model's shapes (m = 65536), it is
-  7 % faster for Wqkv, 2.5 % for out_proj, 14 % for the content model's (3072 -> 12288) projection and within
-  +-5 % for fc2 and the LM head (profiles/).  Under autograd, on the CPU or for shapes the kernel does not take
-  (n or k not a multiple of 8) it is F.linear, exactly as in the reference.
+  path (CUDA, fp16/bf16, no autograd) `linear()` picks between this library's tcgen05 GEMM
+  (bp_linear_bias_act_fwd with BP_ACT_NONE) and the cuBLAS call F.linear makes, per shape, by measurement -- see
+  `_backend` below.  Under autograd, on the CPU or for shapes the kernel does not take (n or k not a multiple of
+  8) it is F.linear, exactly as in the reference.
 * `FusedDenseGeluDense`: fc1 + bias + tanh-GELU is ONE kernel, bp_linear_bias_act_fwd -- the replacement of
   fused_dense_lib.linear_gelu_forward (csrc/fused_dense_lib/fused_dense.cpp:88-142) -- followed by the fc2
   GEMM (fused_dense.py:225).
@@ -108,16 +107,21 @@ def _own_gemm_ok(x, weight, bias) -> bool:
 
 
 # Which GEMM serves the plain linears on the inference path: "own" (bp_linear_bias_act_fwd), "library" (F.linear ->
-# cuBLAS, what the reference calls), or a per-shape choice {(n, k): "own" | "library"} with "own" as the default.
-# Model factories set it from `config.linear_backend`; tests and bench.py use set_linear_backend().
-_backend = "own"
+# cuBLAS, what the reference calls), a per-shape choice {(n, k): "own" | "library"}, or "auto" (default):
+#   "auto" = own GEMM for k <= 1024 and 1024 <= n <= 4096 (Wqkv, the contextualisation Wqkv), library otherwise.
+# Measured on B200 with the whole Backpack-Small forward replayed as one CUDA graph (benchmarks/linear_policy_ab.py,
+# profiles/): per-kernel CUDA events make the own GEMM faster than cuBLAS at every shape but fc2 and the LM head
+# (Wqkv -12 %, content projection -8 %), yet the step runs under the 1000 W power cap and what counts is the step:
+# all-library 24.99 ms, all-own 25.71 ms, own for Wqkv only 24.83 ms (the only shape whose own GEMM makes the STEP
+# faster), own for the content projection only 25.24 ms.  set_linear_backend() overrides (tests, bench.py).
+_backend = "auto"
 _timing_hook = None      # bench.py: callable(tag, n, k) -> context manager bracketing the library GEMM with CUDA events
 
 
 def set_linear_backend(backend) -> None:
     global _backend
-    if not (backend in ("own", "library") or isinstance(backend, dict)):
-        raise ValueError('linear backend must be "own", "library" or a {(n, k): backend} dict')
+    if not (backend in ("auto", "own", "library") or isinstance(backend, dict)):
+        raise ValueError('linear backend must be "auto", "own", "library" or a {(n, k): backend} dict')
     _backend = backend
 
 
@@ -125,11 +129,18 @@ def get_linear_backend():
     return _backend
 
 
+def _choice(n: int, k: int) -> str:
+    if isinstance(_backend, dict):
+        return _backend.get((n, k), "library")
+    if _backend == "auto":
+        return "own" if (k <= 1024 and 1024 <= n <= 4096) else "library"
+    return _backend
+
+
 def linear(x, weight, bias=None):
     """x @ weight.T + bias: this library's GEMM on the inference path, F.linear otherwise (see the module docstring)."""
     n, k = weight.shape
-    choice = _backend.get((n, k), "own") if isinstance(_backend, dict) else _backend
-    if choice == "own" and _own_gemm_ok(x, weight, bias):
+    if _choice(n, k) == "own" and _own_gemm_ok(x, weight, bias):
         return linear_bias_act(x, weight, bias, "none")
     if _timing_hook is not None and x.is_cuda:
         with _timing_hook("F.linear", n, k):

@@ -310,8 +310,7 @@ def run_ours(args):
                     return False
 
             default_backend = FD.get_linear_backend()
-            mixed = {(cfg.n_embd, 4 * cfg.n_embd): "library", (cfg.vocab_size, cfg.n_embd): "library"}
-            for pname, policy in (("library", "library"), ("own", "own"), ("own_except_fc2_lmhead", mixed)):
+            for pname, policy in (("library", "library"), ("own", "own"), ("auto", "auto")):
                 FD.set_linear_backend(policy)
                 for _ in range(2):
                     model(ids_dev)

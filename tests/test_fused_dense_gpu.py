@@ -128,7 +128,9 @@ def test_fused_dense_runs_the_own_gemm_at_every_model_shape(n, k):
     runs bp_linear_bias_act_fwd on the inference path -- checked through the launch counter -- and matches fp32 math
     on the same inputs at least as well as the cuBLAS call the reference makes (flash_attn/ops/fused_dense.py:52)."""
     from backpacks_flash_attn_b200 import _lib
+    from backpacks_flash_attn_b200.ops import fused_dense as FD
     from backpacks_flash_attn_b200.ops.fused_dense import FusedDense, linear
+    FD.set_linear_backend("own")
     torch.manual_seed(n + k)
     m = 1500                                              # crosses the 256-row tile boundary with a ragged tail
     lin = FusedDense(k, n, bias=n != 50264, device="cuda", dtype=torch.bfloat16).eval()
@@ -146,3 +148,12 @@ def test_fused_dense_runs_the_own_gemm_at_every_model_shape(n, k):
     xg = x.clone().requires_grad_(True)
     yg = lin(xg)
     assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2 and yg.requires_grad
+    # "library" and the measured default ("auto": own GEMM for Wqkv-like shapes only)
+    FD.set_linear_backend("library")
+    with torch.no_grad():
+        assert torch.equal(lin(x), lib)
+    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2
+    FD.set_linear_backend("auto")
+    with torch.no_grad():
+        lin(x)
+    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2 + (1 if (n, k) in ((2304, 768), (1536, 768)) else 0)
