@@ -33,11 +33,16 @@ namespace sense {
 constexpr int BM = 128;
 constexpr int kThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
-#ifndef BP_SENSE_POLY
-#define BP_SENSE_POLY 0
+// Of every 8 exponentials, how many run as a polynomial on the FMA pipe instead of MUFU (0, 2 or 4; rel. error 7.5e-5).
+// Pass 1 is MUFU-bound and gains 7 % from 2 of 8 (0.262 -> 0.235 ms at config 3); pass 2 is bound by the tensor pipe
+// and its single issuer and measured 2-3 % SLOWER with it, so it keeps every exponential on MUFU.
+#ifndef BP_SENSE_LSE_POLY
+#define BP_SENSE_LSE_POLY 2
 #endif
-// of every 8 exponentials, how many run as a polynomial on the FMA pipe instead of MUFU (0, 2 or 4)
-constexpr int kPoly = BP_SENSE_POLY;
+#ifndef BP_SENSE_MIX_POLY
+#define BP_SENSE_MIX_POLY 0
+#endif
+constexpr int kPolyLse = BP_SENSE_LSE_POLY, kPolyMix = BP_SENSE_MIX_POLY;
 
 // =============================================================================================
 // pass 1: row statistics
@@ -251,7 +256,7 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
                 float e[8];
-                exp2_scaled8<kPoly>(e, &s[cc * 32 + i], c2, neg);
+                exp2_scaled8<kPolyLse>(e, &s[cc * 32 + i], c2, neg);
                 add2(sum4[0], sum4[1], e[0], e[1]);
                 add2(sum4[2], sum4[3], e[2], e[3]);
                 add2(sum4[0], sum4[1], e[4], e[5]);
@@ -679,7 +684,7 @@ sense_mix_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
           float e[8];
-          exp2_scaled8<kPoly>(e, &s[hf * 32 + c], c2, neg_lse2);
+          exp2_scaled8<kPolyMix>(e, &s[hf * 32 + c], c2, neg_lse2);
           pk[c / 2 + 0] = pack2<kBF16>(e[0], e[1]);
           pk[c / 2 + 1] = pack2<kBF16>(e[2], e[3]);
           pk[c / 2 + 2] = pack2<kBF16>(e[4], e[5]);

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --for
 echo "== sanity"; timeout 900 python benchmarks/sanity.py --tag dbg > $O/${R}_sanity.log 2>&1; tail -16 $O/${R}_sanity.log | cut -c1-230
 echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -rf --tb=short > $O/${R}_pytest.log 2>&1; tail -25 $O/${R}_pytest.log | cut -c1-200
 echo "== kernels"
-for tag in "" p2; do
+for tag in ""; do
   [ -n "$tag" ] && [ ! -f backpacks_flash_attn_b200/libbackpack_b200_$tag.so ] && continue
   which="fmha,sense"; [ -z "$tag" ] && which="fmha,sense,ln,gemm"
   BP_LIB_TAG=$tag timeout 600 python benchmarks/bench_kernels.py --which $which > $O/${R}_kernels_${tag:-prod}.jsonl 2>&1
