@@ -31,6 +31,7 @@ SIGNATURES = {
     "bp_sense_mix_table_fwd": [c_void_p] * 5 + [c_int32] * 6 + [c_float, c_int32, c_void_p],
     "bp_ln_residual_fwd": [c_void_p] * 8 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_linear_bias_act_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    "bp_lm_head_stats_fwd": [c_void_p] * 7 + [c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "bp_linear_bias_residual_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_ln_fwd": [c_void_p] * 6 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_rotary_qk_inplace": [c_void_p] * 5 + [c_int32] * 6 + [c_void_p],

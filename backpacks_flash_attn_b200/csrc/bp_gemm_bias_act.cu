@@ -43,6 +43,15 @@ struct Params {
   int32_t act;
   int32_t residual_mode;   // pair kernel: the output map is the fp32 residual stream, updated in place (+=)
   int32_t group_n;         // pair kernel: n-tiles per tile-order group (see tile_coords)
+  // "stats" mode of the pair kernel (bp_lm_head_stats_fwd): the logits are never written; every epilogue thread keeps
+  // the running softmax statistics of its row across all n-tiles
+  int32_t stats_mode;
+  int32_t n_valid;             // columns >= n_valid (vocabulary padding) are ignored
+  const int64_t* targets;      // (m) or null
+  float* lse;                  // (m)
+  int32_t* argmax;             // (m)
+  float* max_logit;            // (m)
+  float* target_logit;         // (m) or null
 };
 
 // Tile order of the pair kernel.  Tiles are walked in groups of `group_n` n-tiles: inside a group n-fastest, then m,
@@ -57,6 +66,27 @@ __device__ __forceinline__ void tile_coords(const Params& p, int64_t tile, int& 
   const int gn = min(p.group_n, p.n_tiles - g * p.group_n);   // the last group may be narrower
   m_blk = r / gn;
   n_blk = g * p.group_n + (r - m_blk * gn);
+}
+// Tiles of one cluster, by local index i.  Normal mode: tile cluster_id + i * num_clusters of the grouped order above.
+// Stats mode: a cluster owns whole 256-row blocks (cluster_id, cluster_id + num_clusters, ...) and walks ALL n-tiles of
+// a block before the next one, so that the row statistics can live in registers.
+__device__ __forceinline__ uint32_t tiles_of_cluster(const Params& p, int64_t cluster_id, int64_t num_clusters) {
+  if (p.stats_mode) {
+    const int64_t blocks = cluster_id < p.m_tiles ? (p.m_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+    return static_cast<uint32_t>(blocks * p.n_tiles);
+  }
+  const int64_t num_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  return cluster_id < num_tiles ? static_cast<uint32_t>((num_tiles - cluster_id + num_clusters - 1) / num_clusters) : 0u;
+}
+__device__ __forceinline__ void tile_of_cluster(const Params& p, int64_t cluster_id, int64_t num_clusters, uint32_t i,
+                                                int& m_blk, int& n_blk) {
+  if (p.stats_mode) {
+    const uint32_t r = i / static_cast<uint32_t>(p.n_tiles);
+    m_blk = static_cast<int>(cluster_id + r * num_clusters);
+    n_blk = static_cast<int>(i - r * p.n_tiles);
+  } else {
+    tile_coords(p, cluster_id + static_cast<int64_t>(i) * num_clusters, m_blk, n_blk);
+  }
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -286,13 +316,13 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int warp = role_warp<12>(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int64_t num_tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;   // 256 x 256 tiles
   const int64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const uint32_t my_tiles = tiles_of_cluster(p, cluster_id, num_clusters);   // 256 x 256 tiles of this cluster
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO);
+    if (!p.stats_mode) tma_prefetch_desc(&tmO);
     for (int i = 0; i < pair::kStages; ++i) mbar_init(&bars.full[i], 1), mbar_init(&bars.empty[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 512);
     for (int i = 0; i < 8; ++i) mbar_init(&bars.res_full[i][0], 1), mbar_init(&bars.res_full[i][1], 1);
@@ -313,9 +343,9 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const uint32_t sbase = smem_u32(smem), bars_a = smem_u32(&bars);
     uint32_t slot = 0, ph = 0;   // parity of `empty` to wait for once the ring has wrapped: ((it / kStages) - 1) & 1
     bool wrapped = false;
-    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (uint32_t ti = 0; ti < my_tiles; ++ti) {
       int m_blk, n_blk;
-      tile_coords(p, tile, m_blk, n_blk);
+      tile_of_cluster(p, cluster_id, num_clusters, ti, m_blk, n_blk);
       const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
       const int n0 = n_blk * 256 + static_cast<int>(rank) * 128;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -341,7 +371,7 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const uint64_t dB0 = make_smem_desc_sw128(smem_u32(smem) + pair::kABytes, 16, 1024);
     uint32_t slot = 0, ph = 0, local = 0;
     bool ready = false;   // result of the early probe of the next stage's `full` barrier
-    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+    for (; local < my_tiles; ++local) {
       const uint32_t buf = local & 1;
       if (local >= 2) mbar_wait(&bars.acc_empty[buf], ((local >> 1) - 1) & 1);
       tc_fence_after();
@@ -375,9 +405,12 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint8_t* my_stage = smem + pair::offOut + (warp - 4) * 2 * pair::kWarpChunkBytes;
     uint32_t local = 0, chunk_it = 0;
     uint32_t res_phase[2] = {0, 0};
-    for (int64_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+    // stats mode: running softmax statistics of this thread's row (row = TMEM lane) over the n-tiles of a row block
+    float st_m = -INFINITY, st_l = 0.f, st_best = -INFINITY, st_tgt = 0.f;
+    int st_idx = 0;
+    for (; local < my_tiles; ++local) {
       int m_blk, n_blk;
-      tile_coords(p, tile, m_blk, n_blk);
+      tile_of_cluster(p, cluster_id, num_clusters, local, m_blk, n_blk);
       const int m0 = m_blk * 256 + static_cast<int>(rank) * 128 + quad * 32;
       const int n0 = n_blk * 256 + hsel * 128;
       const uint32_t buf = local & 1;
@@ -407,6 +440,84 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive_leader(&bars.acc_empty[buf]);
+      if (p.stats_mode) {
+        // ---- fused softmax statistics (bp_lm_head_stats_fwd): this thread holds 128 logits of its row ----
+        constexpr float kLog2e = 1.4426950408889634f;
+        const int row = m0 + lane;
+        const int lim = p.n_valid - n0;                 // columns of this half-tile inside the vocabulary
+        float f[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) f[i] = (i < lim) ? __uint_as_float(v[i >> 6][i & 63]) : -INFINITY;
+        float mx8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mx8[q] = f[q];
+#pragma unroll
+        for (int i = 8; i < 128; i += 8)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) mx8[q] = fmaxf(mx8[q], f[i + q]);
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        if (mx > st_best) {                             // first column attaining the new maximum (torch.argmax order)
+          st_best = mx;
+          int idx = 127;
+#pragma unroll
+          for (int i = 127; i >= 0; --i) idx = (f[i] == mx) ? i : idx;
+          st_idx = n0 + idx;
+        }
+        if (p.targets != nullptr) {
+          const int64_t t = row < p.m ? __ldg(p.targets + row) : -1;
+          const int off = static_cast<int>(t) - n0;
+          if (t >= 0 && off >= 0 && off < 128) {
+#pragma unroll
+            for (int i = 0; i < 128; ++i) st_tgt = (i == off) ? f[i] : st_tgt;
+          }
+        }
+        if (mx > -INFINITY) {
+          const float m_new = fmaxf(st_m, mx);
+          const float neg = -m_new * kLog2e;
+          float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 128; i += 8) {
+            float e[8];
+            exp2_scaled8<0>(e, &f[i], kLog2e, neg);
+            add2(sum4[0], sum4[1], e[0], e[1]);
+            add2(sum4[2], sum4[3], e[2], e[3]);
+            add2(sum4[0], sum4[1], e[4], e[5]);
+            add2(sum4[2], sum4[3], e[6], e[7]);
+          }
+          st_l = st_l * fast_exp2((st_m - m_new) * kLog2e) + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+          st_m = m_new;
+        }
+        if (n_blk == p.n_tiles - 1) {
+          // last n-tile of this row block: merge the two column halves (warps w and w + 4 share their rows) and write
+          float* xch = reinterpret_cast<float*>(smem + pair::offOut + (quad + 4) * 2 * pair::kWarpChunkBytes);   // the hsel = 1 partner's staging
+          if (hsel == 1) {
+            xch[lane * 8 + 0] = st_m, xch[lane * 8 + 1] = st_l, xch[lane * 8 + 2] = st_best, xch[lane * 8 + 3] = st_tgt;
+            xch[lane * 8 + 4] = __int_as_float(st_idx);
+          }
+          named_bar_sync(1 + quad, 64);
+          if (hsel == 0) {
+            const float m2 = xch[lane * 8 + 0], l2 = xch[lane * 8 + 1], b2 = xch[lane * 8 + 2], t2 = xch[lane * 8 + 3];
+            const int i2 = __float_as_int(xch[lane * 8 + 4]);
+            const float m_all = fmaxf(st_m, m2);
+            const float l_all = st_l * fast_exp2((st_m - m_all) * kLog2e) + l2 * fast_exp2((m2 - m_all) * kLog2e);
+            if (row < p.m) {
+              p.lse[row] = m_all + __logf(l_all);
+              const bool second = b2 > st_best;          // ties go to the lower column (the hsel = 0 half)
+              p.argmax[row] = second ? i2 : st_idx;
+              p.max_logit[row] = second ? b2 : st_best;
+              if (p.target_logit != nullptr) {
+                const int64_t t = p.targets != nullptr ? __ldg(p.targets + row) : -1;
+                // the half that saw the target column holds its logit; a target outside [0, n_valid) yields 0
+                const int nb = (t >= 0 && t < p.n_valid) ? static_cast<int>((t % 256) / 128) : -1;
+                p.target_logit[row] = nb == 0 ? st_tgt : (nb == 1 ? t2 : 0.f);
+              }
+            }
+          }
+          named_bar_sync(1 + quad, 64);
+          st_m = -INFINITY, st_l = 0.f, st_best = -INFINITY, st_tgt = 0.f, st_idx = 0;
+        }
+        continue;
+      }
       if (p.residual_mode) {
         // residual[m0.., col..] += acc + bias, one 32 x 32 fp32 box at a time through the two staging buffers
 #pragma unroll
@@ -552,6 +663,8 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
   p.residual_mode = residual != nullptr ? 1 : 0;
   p.n_tiles = (n + BN - 1) / BN;
   p.group_n = p.n_tiles;
+  p.stats_mode = 0, p.n_valid = n;
+  p.targets = nullptr, p.lse = nullptr, p.argmax = nullptr, p.max_logit = nullptr, p.target_logit = nullptr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -623,4 +736,56 @@ extern "C" int bp_linear_bias_residual_fwd(const void* x, const void* w, const v
   if (!residual) return bp::fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_residual_fwd: null pointer argument");
   return bp::gemm::launch_linear("bp_linear_bias_residual_fwd", x, w, bias, nullptr, residual, m, n, k, BP_ACT_NONE,
                                  dtype, stream);
+}
+
+// LM head with the softmax statistics fused into the GEMM epilogue: the (m, n) logits are never written.
+extern "C" int bp_lm_head_stats_fwd(const void* x, const void* w, const int64_t* targets, float* lse, int32_t* argmax,
+                                    float* max_logit, float* target_logit, int64_t m, int32_t n, int32_t k,
+                                    int32_t n_valid, int32_t dtype, void* stream) {
+  using namespace bp;
+  using namespace bp::gemm;
+  const char* fn = "bp_lm_head_stats_fwd";
+  if (!x || !w || !lse || !argmax || !max_logit) return fail(BP_ERR_INVALID_ARGUMENT, "%s: null pointer argument", fn);
+  if (target_logit && !targets) return fail(BP_ERR_INVALID_ARGUMENT, "%s: target_logit needs targets", fn);
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: only fp16 and bf16 are supported", fn);
+  if (m <= 0 || n <= 0 || k <= 0 || m > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "%s: empty or oversized input", fn);
+  if (k % 8 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "%s: k must be a multiple of 8 (got %d)", fn, k);
+  if (n_valid <= 0 || n_valid > n) return fail(BP_ERR_INVALID_ARGUMENT, "%s: n_valid must be in [1, n]", fn);
+  if ((uintptr_t)x % 16 || (uintptr_t)w % 16) return fail(BP_ERR_INVALID_ARGUMENT, "%s: x and w must be 16-byte aligned", fn);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms < 2) return fail(BP_ERR_UNSUPPORTED, "%s: needs at least two SMs (CTA pairs)", fn);
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const uint64_t da[2] = {(uint64_t)k, (uint64_t)m}, sa[1] = {(uint64_t)k * 2};
+    const uint32_t ba[2] = {BK, BM};
+    if (int rc = encode_tensor_map(&tmA, dtype, 2, x, da, sa, ba, true)) return rc;
+    const uint64_t db[2] = {(uint64_t)k, (uint64_t)n}, sb[1] = {(uint64_t)k * 2};
+    const uint32_t bb[2] = {BK, 128};
+    if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;
+    tmO = tmA;   // unused in stats mode
+  }
+  Params p;
+  p.bias = nullptr;
+  p.m = m, p.n = n, p.k = k;
+  p.k_blocks = (k + BK - 1) / BK;
+  p.act = BP_ACT_NONE;
+  p.residual_mode = 0;
+  p.m_tiles = static_cast<int32_t>((m + 255) / 256);
+  p.n_tiles = (n_valid + BN - 1) / BN;
+  p.group_n = p.n_tiles;
+  p.stats_mode = 1, p.n_valid = n_valid;
+  p.targets = targets, p.lse = lse, p.argmax = argmax, p.max_logit = max_logit, p.target_logit = target_logit;
+  const int clusters = p.m_tiles < sms / 2 ? p.m_tiles : sms / 2;
+  const bool bf = dtype == BP_DTYPE_BF16;
+  auto kern = bf ? gemm_bias_act_pair_kernel<true> : gemm_bias_act_pair_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+  }
+  kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmO, p);
+  return check_launch(fn);
 }

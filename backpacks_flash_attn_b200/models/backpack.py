@@ -255,12 +255,34 @@ class BackpackLMHeadModel(BackpackPreTrainedModel):
     def tie_weights(self):
         self.lm_head.weight = self.transformer.embeddings.word_embeddings.weight
 
-    def forward(self, input_ids, position_ids=None, inference_params=None):
+    def forward(self, input_ids, position_ids=None, inference_params=None, num_last_tokens=0):
+        """num_last_tokens > 0: project only the last positions to the vocabulary (the generation loop consumes
+        logits[:, -1] only, training/src/utils/generation.py:34-44); 0 (the reference's behaviour): all positions."""
         hidden_states = self.transformer(input_ids, position_ids=position_ids, inference_params=inference_params)
+        if num_last_tokens > 0:
+            hidden_states = hidden_states[:, -num_last_tokens:]
         if getattr(self.config, "fused_bias_fc", False):
-            # the tied LM head is a plain GEMM (backpack.py:339-340, 349): same kernel as every other linear
+            # the tied LM head is a plain GEMM (backpack.py:339-340, 349): same dispatch as every other linear
             return CausalLMOutput(logits=linear(hidden_states, self.lm_head.weight, self.lm_head.bias))
         return CausalLMOutput(logits=self.lm_head(hidden_states))
+
+    @torch.no_grad()
+    def token_stats(self, input_ids, targets=None, position_ids=None, num_last_tokens=0):
+        """Per-position log-sum-exp, arg-max, max logit (and the logit of `targets`) of the LM head WITHOUT writing
+        the logits (ops/lm_head.py): what perplexity evaluation and greedy decoding consume."""
+        from ..ops.lm_head import lm_head_stats
+        hidden_states = self.transformer(input_ids, position_ids=position_ids)
+        if num_last_tokens > 0:
+            hidden_states = hidden_states[:, -num_last_tokens:]
+            targets = targets[:, -num_last_tokens:] if targets is not None else None
+        return lm_head_stats(hidden_states, self.lm_head.weight, targets)
+
+    @torch.no_grad()
+    def loss(self, input_ids, labels, ignore_index=-100, reduction="mean"):
+        """Next-token cross-entropy (labels already shifted by the caller, as in training/src/tasks/seq.py) through the
+        fused LM head: no (batch, seq, vocab) tensor is formed."""
+        from ..ops.lm_head import lm_head_cross_entropy
+        return lm_head_cross_entropy(self.transformer(input_ids), self.lm_head.weight, labels, ignore_index, reduction)
 
 
 def flash_config(**kwargs) -> BackpackConfig:

@@ -25,6 +25,9 @@ CASES = {
     "sense_table_k16": "sense(2, 512, 16, 768, table=True)",
     "sense_table_k4": "sense(2, 300, 4, 768, table=True)",
     "sense_k16_b64": "sense(64, 1024, 16, 768, check=False)",
+    "lm_head_stats": "lmstats(2000, 50264, 768)",
+    "lm_head_stats_small": "lmstats(300, 1000, 64)",
+    "gemm_plain": "gemm(3000, 2304, 768)",
 }
 
 PRELUDE = r'''
@@ -49,6 +52,33 @@ def fmha(b, s, h, d, causal, dtype=torch.bfloat16, check=True):
     lerr = (lse[:, :, :s] - torch.logsumexp(sc, -1)).abs().max().item()
     print(f"max|err| {err:.3e} lse err {lerr:.3e}")
     assert err < 3e-2 and lerr < 1e-3
+def lmstats(m, n, k):
+    from backpacks_flash_attn_b200.ops.lm_head import lm_head_stats
+    torch.manual_seed(0)
+    x = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * k ** -0.5).bfloat16()
+    t = torch.randint(0, n, (m,), device="cuda")
+    out = lm_head_stats(x, w, t)
+    torch.cuda.synchronize()
+    logits = x.float() @ w.float().t()
+    e1 = (out["lse"] - torch.logsumexp(logits, -1)).abs().max().item()
+    e2 = (out["target_logit"] - logits.gather(-1, t[:, None])[:, 0]).abs().max().item()
+    agree = (out["argmax"].long() == logits.argmax(-1)).float().mean().item()
+    print(f"lse err {e1:.3e} target err {e2:.3e} argmax agreement {agree:.4f}")
+    assert e1 < 2e-3 and e2 < 2e-3 and agree > 0.98
+def gemm(m, n, k):
+    from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_act
+    torch.manual_seed(0)
+    x = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * k ** -0.5).bfloat16()
+    b = torch.randn(n, device="cuda").bfloat16()
+    for act in ("none", "gelu_tanh"):
+        out = linear_bias_act(x, w, b, act)
+        ref = x.float() @ w.float().t() + b.float()
+        if act == "gelu_tanh": ref = torch.nn.functional.gelu(ref, approximate="tanh")
+        err = (out.float() - ref).abs().max().item()
+        print(act, f"max|err| {err:.3e}")
+        assert err < 5e-2
 def sense(b, s, nv, d, table=False, check=True):
     from backpacks_flash_attn_b200.ops.sense_mix import sense_mix, sense_mix_table
     torch.manual_seed(0)

@@ -125,6 +125,22 @@ int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void*
                            int64_t m, int32_t n, int32_t k, int32_t activation /* bp_activation_t */,
                            int32_t dtype, void* stream);
 
+/* Tied LM head with the softmax statistics fused into the GEMM epilogue: logits = x W^T are never written to HBM
+ * (6.6 GB per forward at Backpack-Small / batch 64 / seq 1024).  What evaluation and greedy decoding consume:
+ *   lse[i]          = log sum_j exp(logits[i, j])          (the cross-entropy is lse[i] - target_logit[i])
+ *   argmax[i]       = first j attaining max_j logits[i, j]  (torch.argmax order), max_logit[i] its value
+ *   target_logit[i] = logits[i, targets[i]]                 (targets / target_logit may both be NULL)
+ * over the columns j < n_valid (n_valid = n keeps the reference's padded vocabulary, backpack.py:285-288).
+ * Replaces, for inference, lm_head (training/src/models/backpack.py:349) followed by the softmax cross-entropy of
+ * csrc/xentropy/xentropy_kernel.cu:430-760 / flash_attn/losses/cross_entropy.py:19-129, and the
+ * logits[:, -1].argmax of the generation loop (training/src/utils/generation.py:34-44).  The statistics are taken on
+ * the fp32 accumulators (the reference rounds the logits to 16 bits first).
+ *   x (m, k) row-major 16-bit, W (n, k) row-major (the embedding matrix), k % 8 == 0; targets (m) int64.
+ */
+int bp_lm_head_stats_fwd(const void* x, const void* w, const int64_t* targets, float* lse, int32_t* argmax,
+                         float* max_logit, float* target_logit, int64_t m, int32_t n, int32_t k, int32_t n_valid,
+                         int32_t dtype, void* stream);
+
 /* residual += x W^T + bias, fp32 residual stream updated in place: the out_proj / fc2 GEMM of a pre-norm block
  * with the "dropout(0) + add" half of dropout_add_ln_fwd (flash_attn/modules/block.py:84-88, 101-105;
  * csrc/layer_norm/ln_fwd_kernels.cuh:98-131) moved into its epilogue, so the branch output is never written
