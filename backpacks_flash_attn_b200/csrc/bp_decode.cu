@@ -1,0 +1,346 @@
+// Incremental decoding (one new token per sequence) for sm_100a: the two operators that change shape when the query
+// is a single position.  Both are HBM-bound row streams (every step re-reads the whole KV cache / all sense vectors of
+// the context), so they are plain CUDA-core kernels built for coalesced 16-byte loads and deterministic reductions --
+// there is no GEMM-shaped work to put on the tensor cores.
+//
+//   bp_decode_attn_fwd      softmax(scale * q K^T) V for ONE query per (batch, head) against a KV cache
+//                           (flash_attn/modules/mha.py:356-380, 432-440: _update_kv_cache + inner_cross_attn with
+//                           causal=False; the mask is top-left aligned, csrc/flash_attn/src/fmha/mask.h:70, so a
+//                           decode step attends to every cached key).
+//   bp_sense_mix_decode_fwd the Backpack sense-mix for the LAST position only:
+//                           out[b,:] = sum_l sum_{j<len} softmax_j(scale q_l . k_lj) * table[ids[b,j], l, :]
+//                           (training/src/models/backpack.py:116-122 + :313 restricted to row i = len - 1).  The
+//                           reference has no incremental path for Backpacks: its generation loop re-runs the full forward
+//                           for every token (training/src/utils/generation.py:34-44, 62-72).
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace decode {
+
+template <bool kBF16>
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (kBF16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention of one query per (batch, head) against the KV cache
+// ---------------------------------------------------------------------------------------------
+// One CTA of 128 threads per (batch, head).  A key row (DH 16-bit values) is read by 8 lanes with one or two 16-byte loads
+// each, so a warp streams 4 keys per instruction and a CTA 16; every 8-lane group runs its own online softmax over the
+// keys it sees (running max, sum and DH/8 accumulators per lane) and the 16 partial results are merged at the end in a
+// fixed order (shuffles inside the warp, then shared memory across warps): bitwise deterministic.
+struct AttnParams {
+  const void* q;        // (batch, nheads, DH)
+  const void* kv;       // cache: element (b, j, which, h, :) at b*batch_stride + j*row_stride + which*which_stride + h*DH
+  void* out;            // (batch, nheads, DH)
+  const int32_t* lens;  // (batch) keys to attend to per sequence, or null: `len` for all
+  int64_t batch_stride, row_stride, which_stride;
+  int32_t batch, nheads, len;
+  float scale_log2;
+};
+
+template <int DH, bool kBF16>
+__global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
+  constexpr int DPL = DH / 8;          // dims per lane (8 or 16)
+  const int b = blockIdx.x / p.nheads, h = blockIdx.x % p.nheads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp * 4 + (lane >> 3), slot = lane & 7;
+  const int len = p.lens != nullptr ? p.lens[b] : p.len;
+  float q[DPL];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.q) + (static_cast<int64_t>(b) * p.nheads + h) * DH + slot * DPL);
+#pragma unroll
+    for (int c = 0; c < DPL / 8; ++c) {
+      float t[8];
+      unpack8<kBF16>(__ldg(qp + c), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[c * 8 + i] = t[i] * p.scale_log2;     // scores in log2 units
+    }
+  }
+  const uint16_t* kbase = static_cast<const uint16_t*>(p.kv) + b * p.batch_stride + static_cast<int64_t>(h) * DH + slot * DPL;
+  const uint16_t* vbase = kbase + p.which_stride;
+  float m = -INFINITY, l = 0.f, acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+  for (int j0 = 0; j0 < len; j0 += 16) {   // uniform trip count: the shuffles below need the whole warp
+    const int j = j0 + grp;
+    const bool live = j < len;
+    const uint4* kp = reinterpret_cast<const uint4*>(kbase + (live ? j : 0) * p.row_stride);
+    const uint4* vp = reinterpret_cast<const uint4*>(vbase + (live ? j : 0) * p.row_stride);
+    uint4 kr[DPL / 8], vr[DPL / 8];
+#pragma unroll
+    for (int c = 0; c < DPL / 8; ++c) kr[c] = __ldg(kp + c), vr[c] = __ldg(vp + c);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < DPL / 8; ++c) {
+      float t[8];
+      unpack8<kBF16>(kr[c], t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(q[c * 8 + i], t[i], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (live) {
+      const float m_new = fmaxf(m, s);
+      const float alpha = fast_exp2(m - m_new), pj = fast_exp2(s - m_new);
+      l = l * alpha + pj;
+      m = m_new;
+#pragma unroll
+      for (int c = 0; c < DPL / 8; ++c) {
+        float t[8];
+        unpack8<kBF16>(vr[c], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c * 8 + i] = fmaf(pj, t[i], acc[c * 8 + i] * alpha);
+      }
+    }
+  }
+  // merge the four key groups of the warp (lanes with equal slot), then the four warps through shared memory
+  auto merge = [&](float m2, float l2, const float (&a2)[DPL]) {
+    const float m_new = fmaxf(m, m2);
+    const float w1 = m == -INFINITY ? 0.f : fast_exp2(m - m_new), w2 = m2 == -INFINITY ? 0.f : fast_exp2(m2 - m_new);
+    l = l * w1 + l2 * w2;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = acc[i] * w1 + a2[i] * w2;
+    m = m_new;
+  };
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off), l2 = __shfl_xor_sync(0xffffffffu, l, off);
+    float a2[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) a2[i] = __shfl_xor_sync(0xffffffffu, acc[i], off);
+    merge(m2, l2, a2);
+  }
+  __shared__ float sm[4][8][DPL + 2];
+  if (lane < 8) {
+    sm[warp][lane][0] = m, sm[warp][lane][1] = l;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) sm[warp][lane][2 + i] = acc[i];
+  }
+  __syncthreads();
+  if (warp == 0 && lane < 8) {
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+      float a2[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) a2[i] = sm[w][lane][2 + i];
+      merge(sm[w][lane][0], sm[w][lane][1], a2);
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    uint16_t* op = static_cast<uint16_t*>(p.out) + (static_cast<int64_t>(b) * p.nheads + h) * DH + lane * DPL;
+#pragma unroll
+    for (int c = 0; c < DPL / 8; ++c) {
+      uint4 o;
+      o.x = pack2<kBF16>(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
+      o.y = pack2<kBF16>(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
+      o.z = pack2<kBF16>(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
+      o.w = pack2<kBF16>(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
+      reinterpret_cast<uint4*>(op)[c] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sense-mix of the last position
+// ---------------------------------------------------------------------------------------------
+// One CTA of 256 threads per (batch element, 128-column chunk of the output).  Phase 1: the (nv x len) attention weights
+// of the last position -- scores by one thread per (sense, key) pair, row max / sum per sense by block reductions -- are
+// normalised and written to shared memory (recomputed by each of the d/128 CTAs of a batch element: 48 MACs per weight
+// against the 128 x 2 bytes of sense-vector traffic it scales).  Phase 2: the weighted sum over the len * nv table rows
+// table[ids[j], l, chunk]: 16 lanes read one 256-byte row segment with 16-byte loads, a CTA has 16 rows in flight per
+// step; the 16 partial sums per column are merged through shared memory in a fixed order (deterministic).
+constexpr int kDecThreads = 256;
+constexpr int kTileKeys = 256;   // keys per weight tile in shared memory (nv * kTileKeys floats)
+
+struct MixParams {
+  const void* q;          // (batch, nv, dk) query of the new position
+  const void* kcache;     // (batch, max_len, nv, dk)
+  const int64_t* ids;     // (batch, max_len) token ids of the context incl. the new position
+  const void* table;      // (vocab, nv, d)
+  void* out;              // (batch, d)
+  const int32_t* lens;    // (batch) or null
+  int64_t k_batch_stride, ids_batch_stride;
+  int32_t batch, nv, dk, d, vocab, len;
+  float scale_log2;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const MixParams p) {
+  extern __shared__ float smem_f[];
+  float* wts = smem_f;                               // [nv][kTileKeys] normalised weights of the current key tile
+  float* stat = wts + p.nv * kTileKeys;              // [nv][2] row max (log2 units) and 1 / row sum
+  float* red = stat + 2 * p.nv;                      // [kDecThreads] reduction scratch / [16][128] column partials
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = p.lens != nullptr ? p.lens[b] : p.len;
+  const int nv = p.nv, dk = p.dk;
+  const uint16_t* qb = static_cast<const uint16_t*>(p.q) + static_cast<int64_t>(b) * nv * dk;
+  const uint16_t* kb = static_cast<const uint16_t*>(p.kcache) + b * p.k_batch_stride;
+
+  // score of (sense l, key j) in log2 units; dk is a multiple of 8
+  auto score = [&](int l, int j) {
+    const uint4* qp = reinterpret_cast<const uint4*>(qb + l * dk);
+    const uint4* kp = reinterpret_cast<const uint4*>(kb + (static_cast<int64_t>(j) * nv + l) * dk);
+    float s = 0.f;
+    for (int c = 0; c < dk / 8; ++c) {
+      float a[8], k8[8];
+      unpack8<kBF16>(__ldg(qp + c), a);
+      unpack8<kBF16>(__ldg(kp + c), k8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(a[i], k8[i], s);
+    }
+    return s * p.scale_log2;
+  };
+
+  // ---- phase 1a: per-sense row max and row sum (warp w handles senses w, w + 8, ...) ----
+  for (int l = warp; l < nv; l += kDecThreads / 32) {
+    float m = -INFINITY, sum = 0.f;
+    for (int j = lane; j < len; j += 32) {
+      const float s = score(l, j);
+      const float m_new = fmaxf(m, s);
+      sum = sum * fast_exp2(m - m_new) + fast_exp2(s - m_new);
+      m = m_new;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, off), s2 = __shfl_xor_sync(0xffffffffu, sum, off);
+      const float m_new = fmaxf(m, m2);
+      sum = (m == -INFINITY ? 0.f : sum * fast_exp2(m - m_new)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2(m2 - m_new));
+      m = m_new;
+    }
+    if (lane == 0) stat[2 * l] = m, stat[2 * l + 1] = 1.f / sum;
+  }
+  __syncthreads();
+
+  // ---- phase 2 set-up: this thread's 8 output columns and its row slot ----
+  const int slot = tid & 15, rslot = tid >> 4;        // 16 lanes x 16 B = 128 columns; 16 rows in flight
+  const int col0 = chunk * 128 + slot * 8;
+  const bool col_ok = col0 < p.d;                     // d is a multiple of 8
+  const uint16_t* tb = static_cast<const uint16_t*>(p.table) + col0;
+  const int64_t* ids = p.ids + b * p.ids_batch_stride;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int j0 = 0; j0 < len; j0 += kTileKeys) {
+    const int nkeys = min(kTileKeys, len - j0);
+    // ---- phase 1b: normalised weights of this key tile ----
+    for (int idx = tid; idx < nv * nkeys; idx += kDecThreads) {
+      const int l = idx / nkeys, jj = idx - l * nkeys;
+      wts[l * kTileKeys + jj] = fast_exp2(score(l, j0 + jj) - stat[2 * l]) * stat[2 * l + 1];
+    }
+    __syncthreads();
+    // ---- phase 2: acc += w[l][j] * table[ids[j], l, cols]; pairs (j, l) are walked key-major: the nv rows of one token
+    //      are contiguous in the table ----
+    if (col_ok) {
+      const int npairs = nkeys * nv;
+#pragma unroll 4
+      for (int pr = rslot; pr < npairs; pr += 16) {
+        const int jj = pr / nv, l = pr - jj * nv;
+        const int id = min(max(static_cast<int>(__ldg(ids + j0 + jj)), 0), p.vocab - 1);
+        const uint4 row = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<int64_t>(id) * nv + l) * p.d));
+        const float w = wts[l * kTileKeys + jj];
+        float t[8];
+        unpack8<kBF16>(row, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, t[i], acc[i]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- merge the 16 row slots (fixed order) and store ----
+  float* part = red;   // [16][128]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[rslot * 128 + slot * 8 + i] = acc[i];
+  __syncthreads();
+  if (tid < 128 && chunk * 128 + tid < p.d) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s += part[r * 128 + tid];
+    uint16_t* op = static_cast<uint16_t*>(p.out) + static_cast<int64_t>(b) * p.d + chunk * 128 + tid;
+    if constexpr (kBF16) {
+      *reinterpret_cast<__nv_bfloat16*>(op) = __float2bfloat16_rn(s);
+    } else {
+      *reinterpret_cast<__half*>(op) = __float2half_rn(s);
+    }
+  }
+}
+
+}  // namespace decode
+}  // namespace bp
+
+extern "C" int bp_decode_attn_fwd(const void* q, const void* kv_cache, void* out, const int32_t* seqlens_k, int32_t batch,
+                                  int32_t nheads, int32_t headdim, int32_t seqlen_k, int64_t kv_batch_stride,
+                                  int64_t kv_row_stride, int64_t kv_which_stride, float softmax_scale, int32_t dtype,
+                                  void* stream) {
+  using namespace bp;
+  const char* fn = "bp_decode_attn_fwd";
+  if (!q || !kv_cache || !out) return fail(BP_ERR_INVALID_ARGUMENT, "%s: null pointer argument", fn);
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16) return fail(BP_ERR_INVALID_ARGUMENT, "%s: only fp16 and bf16 are supported", fn);
+  if (batch <= 0 || nheads <= 0 || (seqlen_k <= 0 && !seqlens_k)) return fail(BP_ERR_INVALID_ARGUMENT, "%s: empty input", fn);
+  if (headdim != 64 && headdim != 128)
+    return fail(BP_ERR_UNSUPPORTED, "%s: head dim must be 64 or 128 (got %d)", fn, headdim);
+  if (kv_batch_stride % 8 || kv_row_stride % 8 || kv_which_stride % 8 || (uintptr_t)q % 16 || (uintptr_t)kv_cache % 16 || (uintptr_t)out % 16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: pointers must be 16-byte aligned and strides multiples of 8 elements", fn);
+  if ((int64_t)batch * nheads > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "%s: batch * nheads too large", fn);
+  decode::AttnParams p;
+  p.q = q, p.kv = kv_cache, p.out = out, p.lens = seqlens_k;
+  p.batch_stride = kv_batch_stride, p.row_stride = kv_row_stride, p.which_stride = kv_which_stride;
+  p.batch = batch, p.nheads = nheads, p.len = seqlen_k;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf = dtype == BP_DTYPE_BF16;
+  const dim3 grid(batch * nheads);
+  if (headdim == 64) {
+    if (bf) decode::decode_attn_kernel<64, true><<<grid, 128, 0, st>>>(p); else decode::decode_attn_kernel<64, false><<<grid, 128, 0, st>>>(p);
+  } else {
+    if (bf) decode::decode_attn_kernel<128, true><<<grid, 128, 0, st>>>(p); else decode::decode_attn_kernel<128, false><<<grid, 128, 0, st>>>(p);
+  }
+  return check_launch(fn);
+}
+
+extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const int64_t* ids, const void* table, void* out,
+                                       const int32_t* seqlens, int32_t batch, int32_t seqlen, int32_t nv, int32_t dk,
+                                       int32_t d, int32_t vocab, int64_t k_batch_stride, int64_t ids_batch_stride,
+                                       float softmax_scale, int32_t dtype, void* stream) {
+  using namespace bp;
+  const char* fn = "bp_sense_mix_decode_fwd";
+  if (!q || !k_cache || !ids || !table || !out) return fail(BP_ERR_INVALID_ARGUMENT, "%s: null pointer argument", fn);
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16) return fail(BP_ERR_INVALID_ARGUMENT, "%s: only fp16 and bf16 are supported", fn);
+  if (batch <= 0 || batch > 65535 || nv <= 0 || (seqlen <= 0 && !seqlens) || vocab <= 0)
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: empty input or batch > 65535", fn);
+  if (dk % 8 || d % 8) return fail(BP_ERR_UNSUPPORTED, "%s: dk and d must be multiples of 8 (got %d, %d)", fn, dk, d);
+  if ((uintptr_t)q % 16 || (uintptr_t)k_cache % 16 || (uintptr_t)table % 16 || k_batch_stride % 8)
+    return fail(BP_ERR_INVALID_ARGUMENT, "%s: pointers must be 16-byte aligned", fn);
+  decode::MixParams p;
+  p.q = q, p.kcache = k_cache, p.ids = ids, p.table = table, p.out = out, p.lens = seqlens;
+  p.k_batch_stride = k_batch_stride, p.ids_batch_stride = ids_batch_stride;
+  p.batch = batch, p.nv = nv, p.dk = dk, p.d = d, p.vocab = vocab, p.len = seqlen;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(nv) * decode::kTileKeys + 2 * nv + 16 * 128);
+  if (smem > 200 * 1024) return fail(BP_ERR_UNSUPPORTED, "%s: too many senses (%d) for the weight tile", fn, nv);
+  const bool bf = dtype == BP_DTYPE_BF16;
+  auto kern = bf ? decode::sense_mix_decode_kernel<true> : decode::sense_mix_decode_kernel<false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+    }
+  }
+  kern<<<dim3((d + 127) / 128, batch), decode::kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch(fn);
+}

@@ -23,7 +23,9 @@ from transformers import GPT2Config
 
 from ..modules.block import Block
 from ..ops.fused_dense import FusedDense, linear
+from ..ops.decode import sense_mix_decode
 from ..ops.sense_mix import sense_mix, sense_mix_table
+from ..utils.generation import GenerationMixin
 from .gpt import (CausalLMOutput, GPTModel, GPTPreTrainedModel, _init_weights, _no_tp, create_mlp_cls,
                   first_layer_norm, pad_vocab)
 
@@ -193,9 +195,14 @@ class BackpackModel(GPTPreTrainedModel):
         self.sense_table = None
         self._sense_table_key = None
 
-    def current_sense_table(self):
-        """The table if it is enabled and usable now (eval mode), (re)built when missing or stale; else None."""
-        if self.training or not (self.use_sense_table or self.sense_table is not None):
+    def current_sense_table(self, force=False):
+        """The table if it is enabled and usable now (eval mode), (re)built when missing or stale; else None.
+        `force`: build it even if the config did not ask for it (decode steps need it)."""
+        if self.training:
+            if force:
+                raise RuntimeError("incremental decoding needs eval mode (the sense-vector table is inference-only)")
+            return None
+        if not (force or self.use_sense_table or self.sense_table is not None):
             return None
         emb = self.embeddings.word_embeddings.weight
         if (self.sense_table is None or self._sense_table_key != self._content_params_key()
@@ -226,6 +233,8 @@ class BackpackModel(GPTPreTrainedModel):
     def forward(self, input_ids, position_ids=None, inference_params=None):
         contextl_hidden_states = self.gpt2_model(input_ids, position_ids=position_ids,
                                                  inference_params=inference_params)
+        if inference_params is not None:
+            return self._forward_cached(contextl_hidden_states, input_ids, inference_params)
         if self.fused_sense_mix:
             table = self.current_sense_table()
             if table is not None:
@@ -238,8 +247,62 @@ class BackpackModel(GPTPreTrainedModel):
         contextualization = self.contextualization_attn(contextl_hidden_states)  # (b, nv, s, s)
         return torch.sum(contextualization @ content, dim=1)
 
+    # ---- incremental decoding (no counterpart in the reference) ----------------------------
+    def _decode_caches(self, qk, input_ids, inference_params):
+        """Write this call's contextualisation keys and token ids at `sequence_len_offset` into the caches kept in
+        `inference_params.key_value_memory_dict` and return the batch slice of both."""
+        kvd = inference_params.key_value_memory_dict
+        nv, dk = qk.shape[3], qk.shape[4]
+        if "backpack.ctx_k" not in kvd:
+            kvd["backpack.ctx_k"] = torch.empty(inference_params.max_batch_size, inference_params.max_sequence_len,
+                                                nv, dk, dtype=qk.dtype, device=qk.device)
+            kvd["backpack.ids"] = torch.zeros(inference_params.max_batch_size, inference_params.max_sequence_len,
+                                              dtype=torch.int64, device=qk.device)
+        k_cache, ids_cache = kvd["backpack.ctx_k"], kvd["backpack.ids"]
+        b0 = inference_params.batch_size_offset
+        b1 = b0 + qk.shape[0]
+        s0 = inference_params.sequence_len_offset
+        s1 = s0 + qk.shape[1]
+        if b1 > k_cache.shape[0] or s1 > k_cache.shape[1]:
+            raise RuntimeError(f"sense-mix cache of shape {tuple(k_cache.shape)} is too small for batch rows "
+                               f"{b0}:{b1}, positions {s0}:{s1}")
+        k_cache[b0:b1, s0:s1] = qk[:, :, 1]
+        ids_cache[b0:b1, s0:s1] = input_ids
+        return k_cache[b0:b1], ids_cache[b0:b1]
 
-class BackpackLMHeadModel(BackpackPreTrainedModel):
+    def _forward_cached(self, contextl_hidden_states, input_ids, inference_params):
+        """Prompt pass (offset 0): the ordinary forward, with the contextualisation keys and the token ids stored.
+        Decode step (one new position): o_n = sum_l sum_{j<=n} alpha_l[n, j] C_l(x_j) from the caches -- the sense
+        vectors of the context come from the table (fused) or the content model (eager)."""
+        offset = inference_params.sequence_len_offset
+        attn = self.contextualization_attn
+        qk = attn.project_qk(contextl_hidden_states)               # (b, s, 2, nv, dk)
+        dk = qk.shape[-1]
+        scale = attn.softmax_scale or 1.0 / math.sqrt(dk)
+        if self.fused_sense_mix and dk % 8 != 0:
+            qk = torch.nn.functional.pad(qk, (0, (-dk) % 8))        # zero columns leave q.k unchanged (ops/sense_mix.py)
+        k_cache, ids_cache = self._decode_caches(qk, input_ids, inference_params)
+        if offset > 0 and qk.shape[1] != 1:
+            raise RuntimeError("after the prompt pass, decoding advances one position per call")
+        if self.fused_sense_mix:
+            table = self.current_sense_table(force=offset > 0)
+            if offset == 0:
+                if table is not None:
+                    return sense_mix_table(qk, table, input_ids, softmax_scale=scale)
+                return sense_mix(qk, self.content_model(input_ids), softmax_scale=scale)
+            out = sense_mix_decode(qk[:, 0, 0], k_cache, ids_cache, table, offset + 1, softmax_scale=scale)
+            return out.unsqueeze(1)
+        if offset == 0:
+            content = self.content(input_ids)
+            return torch.sum(attn(contextl_hidden_states) @ content, dim=1)
+        n = offset + 1
+        content = self.content(ids_cache[:, :n])                                         # (b, nv, n, d)
+        scores = torch.einsum("bthd,bshd->bhts", qk[:, :, 0], k_cache[:, :n] * scale)   # (b, nv, 1, n)
+        alpha = torch.softmax(scores, dim=-1, dtype=qk.dtype)
+        return torch.sum(alpha @ content, dim=1)
+
+
+class BackpackLMHeadModel(BackpackPreTrainedModel, GenerationMixin):
 
     def __init__(self, config: BackpackConfig, process_group=None, device=None, dtype=None):
         super().__init__(config)

@@ -24,6 +24,7 @@ from ..modules.mha import MHA
 from ..modules.mlp import Mlp
 from ..ops.fused_dense import FusedDenseGeluDense
 from ..ops.layer_norm import dropout_add_layer_norm
+from ..utils.generation import GenerationMixin
 
 CausalLMOutput = namedtuple("CausalLMOutput", ["logits"])
 
@@ -155,17 +156,17 @@ class GPTModel(GPTPreTrainedModel):
                            initializer_range=config.initializer_range))
 
     def forward(self, input_ids, position_ids=None, inference_params=None):
-        if inference_params is not None:
-            raise RuntimeError("KV-cache decoding is out of scope; the Backpack generation loop re-runs the forward")
         hidden_states = self.embeddings(input_ids, position_ids=position_ids)
         hidden_states, residual = first_layer_norm(hidden_states, self.ln_0, self.emb_drop,
                                                    self.fused_dropout_add_ln, self.training)
+        # gpt.py:241-245: the KV caches travel to the mixers as a keyword argument
+        mixer_kwargs = {"inference_params": inference_params} if inference_params is not None else None
         for layer in self.layers:
-            hidden_states, residual = layer(hidden_states, residual)
+            hidden_states, residual = layer(hidden_states, residual, mixer_kwargs=mixer_kwargs)
         return hidden_states
 
 
-class GPTLMHeadModel(GPTPreTrainedModel):
+class GPTLMHeadModel(GPTPreTrainedModel, GenerationMixin):
 
     def __init__(self, config: GPT2Config, process_group=None, device=None, dtype=None):
         super().__init__(config)
@@ -180,8 +181,12 @@ class GPTLMHeadModel(GPTPreTrainedModel):
     def tie_weights(self):
         self.lm_head.weight = self.transformer.embeddings.word_embeddings.weight
 
-    def forward(self, input_ids, position_ids=None, inference_params=None):
+    def forward(self, input_ids, position_ids=None, inference_params=None, num_last_tokens=0):
+        """inference_params: KV caches for generation (gpt.py:273-281).  num_last_tokens > 0 projects only the last
+        positions to the vocabulary (the generation loop reads logits[:, -1] only)."""
         hidden_states = self.transformer(input_ids, position_ids=position_ids, inference_params=inference_params)
+        if num_last_tokens > 0:
+            hidden_states = hidden_states[:, -num_last_tokens:]
         if getattr(self.config, "fused_bias_fc", False):
             from ..ops.fused_dense import linear
             return CausalLMOutput(logits=linear(hidden_states, self.lm_head.weight, self.lm_head.bias))

@@ -2,9 +2,12 @@
 `FlashSelfAttention` (:34-100) on bp_fmha_fwd, the eager `SelfAttention` (:179-224) that
 `use_flash_attn=False` selects, and `MHA` (:287-467, self-attention branch).
 
-Out of scope here, as in SURVEY.md §2.1 #4: cross-attention, depth-wise conv, tensor-parallel ParallelMHA
-and the KV-cache decode path (the Backpack generation loop re-runs the full forward,
-training/src/utils/generation.py:34-44).
+`MHA.forward(..., inference_params)` is the KV-cache path of mha.py:356-380, 432-440: the prompt pass fills the cache,
+every further single-token step attends to the whole cache (bp_decode_attn_fwd with use_flash_attn, the eager
+non-causal cross-attention of mha.py:226-268 otherwise).
+
+Out of scope here, as in SURVEY.md §2.1 #4: cross-attention between different sequences, depth-wise conv and the
+tensor-parallel ParallelMHA.
 """
 from __future__ import annotations
 
@@ -15,6 +18,7 @@ import torch.nn as nn
 
 from ..flash_attn_interface import flash_attn_unpadded_qkvpacked_func
 from ..layers.rotary import RotaryEmbedding
+from ..ops.decode import decode_attention
 from ..ops.fused_dense import FusedDense, linear_bias_residual_
 
 
@@ -110,11 +114,57 @@ class MHA(nn.Module):
         self.inner_attn = inner_attn_cls(causal=causal, softmax_scale=softmax_scale, attention_dropout=dropout)
         self.out_proj = linear_cls(embed_dim, embed_dim, **factory_kwargs)
 
+    def _update_kv_cache(self, kv, inference_params):
+        """kv: (batch, seqlen, 2, nheads, head_dim) of the positions being processed.  Writes them at
+        `sequence_len_offset` into this layer's preallocated cache (mha.py:356-380) and returns the cache rows of
+        this batch slice (all max_sequence_len positions; the caller knows how many are valid)."""
+        if self.layer_idx is None:
+            raise RuntimeError("generation requires layer_idx in the constructor")
+        cache = inference_params.key_value_memory_dict.get(self.layer_idx)
+        if cache is None:
+            cache = torch.empty(inference_params.max_batch_size, inference_params.max_sequence_len, 2, self.num_heads,
+                                self.head_dim, dtype=kv.dtype, device=kv.device)
+            inference_params.key_value_memory_dict[self.layer_idx] = cache
+        batch_start = inference_params.batch_size_offset
+        batch_end = batch_start + kv.shape[0]
+        sequence_start = inference_params.sequence_len_offset
+        sequence_end = sequence_start + kv.shape[1]
+        if batch_end > cache.shape[0] or sequence_end > cache.shape[1]:
+            raise RuntimeError(f"KV cache of shape {tuple(cache.shape)} is too small for batch rows "
+                               f"{batch_start}:{batch_end}, positions {sequence_start}:{sequence_end}")
+        cache[batch_start:batch_end, sequence_start:sequence_end] = kv
+        return cache[batch_start:batch_end]
+
+    def _forward_cached(self, x, inference_params):
+        """Prompt pass (offset 0): self-attention as usual, K/V stored.  Decode step (one new position, offset > 0):
+        the new query against all offset + 1 cached keys, non-causal (mha.py:437-440)."""
+        if x.dim() != 3:
+            raise RuntimeError("generation needs (batch, seqlen, hidden) input")
+        offset = inference_params.sequence_len_offset
+        qkv = self.Wqkv(x)
+        qkv = qkv.reshape(*qkv.shape[:-1], 3, self.num_heads, self.head_dim)
+        if self.rotary_emb_dim > 0:
+            qkv = self.rotary_emb(qkv, seqlen_offset=offset)
+        cache = self._update_kv_cache(qkv[:, :, 1:], inference_params)
+        if offset == 0:
+            return self.inner_attn(qkv)
+        if qkv.shape[1] != 1:
+            # the reference would run these rows non-causally against the cache (mha.py:439), i.e. let each new
+            # position see the ones after it; refuse instead of reproducing that
+            raise RuntimeError("after the prompt pass, decoding advances one position per call")
+        scale = self.inner_attn.softmax_scale or 1.0 / math.sqrt(self.head_dim)
+        if self.use_flash_attn:
+            return decode_attention(qkv[:, :, 0], cache, offset + 1, softmax_scale=scale)
+        k, v = cache[:, :offset + 1].unbind(dim=2)
+        scores = torch.einsum("bthd,bshd->bhts", qkv[:, :, 0], k * scale)
+        attention = torch.softmax(scores, dim=-1, dtype=v.dtype)
+        return torch.einsum("bhts,bshd->bthd", attention, v)
+
     def forward(self, x, x_kv=None, key_padding_mask=None, cu_seqlens=None, max_seqlen=None,
                 inference_params=None, residual_out=None, **kwargs):
         """x: (batch, seqlen, hidden) or, with cu_seqlens / max_seqlen, (total, hidden)."""
-        if x_kv is not None or inference_params is not None:
-            raise RuntimeError("cross-attention / KV-cache decoding are out of scope for this path")
+        if x_kv is not None:
+            raise RuntimeError("cross-attention is out of scope for this path")
         if cu_seqlens is not None:
             if max_seqlen is None or key_padding_mask is not None or not self.use_flash_attn:
                 raise RuntimeError("cu_seqlens needs max_seqlen, use_flash_attn=True and no key_padding_mask")
@@ -122,13 +172,18 @@ class MHA(nn.Module):
                 raise RuntimeError("rotary embedding is not supported with unpadded input")
         if key_padding_mask is not None and self.use_flash_attn:
             raise RuntimeError("key_padding_mask is only supported by the eager SelfAttention")
-        kw = ({"cu_seqlens": cu_seqlens, "max_seqlen": max_seqlen, **kwargs} if self.use_flash_attn
-              else {"key_padding_mask": key_padding_mask, **kwargs})
-        qkv = self.Wqkv(x)
-        qkv = qkv.reshape(*qkv.shape[:-1], 3, self.num_heads, self.head_dim)
-        if self.rotary_emb_dim > 0:
-            qkv = self.rotary_emb(qkv)
-        context = self.inner_attn(qkv, **kw)
+        if inference_params is not None:
+            if key_padding_mask is not None or cu_seqlens is not None or max_seqlen is not None:
+                raise RuntimeError("generation takes dense, unmasked batches (mha.py:409-412)")
+            context = self._forward_cached(x, inference_params)
+        else:
+            kw = ({"cu_seqlens": cu_seqlens, "max_seqlen": max_seqlen, **kwargs} if self.use_flash_attn
+                  else {"key_padding_mask": key_padding_mask, **kwargs})
+            qkv = self.Wqkv(x)
+            qkv = qkv.reshape(*qkv.shape[:-1], 3, self.num_heads, self.head_dim)
+            if self.rotary_emb_dim > 0:
+                qkv = self.rotary_emb(qkv)
+            context = self.inner_attn(qkv, **kw)
         context = context.reshape(*context.shape[:-2], self.embed_dim)
         if residual_out is not None:
             # out_proj with the residual add in its epilogue (Block's fused path); returns the residual stream

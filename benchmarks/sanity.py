@@ -28,6 +28,10 @@ CASES = {
     "lm_head_stats": "lmstats(2000, 50264, 768)",
     "lm_head_stats_small": "lmstats(300, 1000, 64)",
     "gemm_plain": "gemm(3000, 2304, 768)",
+    "decode_attn_d64": "dec_attn(3, 300, 12, 64)",
+    "decode_attn_d128": "dec_attn(2, 1025, 4, 128)",
+    "decode_sense": "dec_sense(3, 300, 16, 768)",
+    "decode_sense_k64": "dec_sense(2, 100, 64, 768)",
 }
 
 PRELUDE = r'''
@@ -79,6 +83,34 @@ def gemm(m, n, k):
         err = (out.float() - ref).abs().max().item()
         print(act, f"max|err| {err:.3e}")
         assert err < 5e-2
+def dec_attn(b, s, h, d):
+    from backpacks_flash_attn_b200.ops.decode import decode_attention
+    torch.manual_seed(0)
+    cache = torch.randn(b, s + 5, 2, h, d, device="cuda").bfloat16()
+    q = torch.randn(b, 1, h, d, device="cuda").bfloat16()
+    out = decode_attention(q, cache, s)
+    torch.cuda.synchronize()
+    k, v = cache[:, :s, 0].float(), cache[:, :s, 1].float()
+    p = torch.softmax(torch.einsum("bthd,bshd->bhts", q.float(), k) * d ** -0.5, -1)
+    ref = torch.einsum("bhts,bshd->bthd", p, v)
+    err = (out.float() - ref).abs().max().item()
+    print(f"max|err| {err:.3e}")
+    assert err < 2e-2
+def dec_sense(b, s, nv, d):
+    from backpacks_flash_attn_b200.ops.decode import sense_mix_decode
+    torch.manual_seed(0)
+    dk = (d // nv + 7) // 8 * 8
+    kc = torch.randn(b, s + 5, nv, dk, device="cuda").bfloat16()
+    q = torch.randn(b, nv, dk, device="cuda").bfloat16()
+    tab = torch.randn(777, nv, d, device="cuda").bfloat16()
+    ids = torch.randint(0, 777, (b, s + 5), device="cuda")
+    out = sense_mix_decode(q, kc, ids, tab, s)
+    torch.cuda.synchronize()
+    sc = torch.einsum("bhd,bshd->bhs", q.float(), kc[:, :s].float()) * dk ** -0.5
+    ref = torch.einsum("bhs,bshd->bd", torch.softmax(sc, -1), tab[ids[:, :s]].float())
+    err = (out.float() - ref).abs().max().item()
+    print(f"max|err| {err:.3e} (max|ref| {ref.abs().max().item():.2f})")
+    assert err < 0.08
 def sense(b, s, nv, d, table=False, check=True):
     from backpacks_flash_attn_b200.ops.sense_mix import sense_mix, sense_mix_table
     torch.manual_seed(0)

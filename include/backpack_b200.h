@@ -141,6 +141,33 @@ int bp_lm_head_stats_fwd(const void* x, const void* w, const int64_t* targets, f
                          float* max_logit, float* target_logit, int64_t m, int32_t n, int32_t k, int32_t n_valid,
                          int32_t dtype, void* stream);
 
+/* Incremental decoding, attention of ONE new query per (batch, head) against the KV cache: the seqlen_q = 1 form of
+ * MHA.forward with inference_params (flash_attn/modules/mha.py:356-380 _update_kv_cache, :432-440 inner_cross_attn with
+ * causal=False -- the mask is top-left aligned, csrc/flash_attn/src/fmha/mask.h:70, so the new token sees every cached key).
+ *   q (batch, nheads, headdim), out (batch, nheads, headdim), 16-bit, contiguous;
+ *   kv_cache: the reference's (max_batch, max_seqlen, 2, nheads, headdim) cache, addressed as
+ *     kv_cache + b * kv_batch_stride + j * kv_row_stride + which * kv_which_stride + h * headdim   (elements; which 0 = K, 1 = V)
+ *   seqlen_k keys are attended to (the new token's K/V must already be in the cache), or seqlens_k[b] (device, int32)
+ *   per batch element when not NULL.  headdim 64 or 128.
+ */
+int bp_decode_attn_fwd(const void* q, const void* kv_cache, void* out, const int32_t* seqlens_k, int32_t batch,
+                       int32_t nheads, int32_t headdim, int32_t seqlen_k, int64_t kv_batch_stride, int64_t kv_row_stride,
+                       int64_t kv_which_stride, float softmax_scale, int32_t dtype, void* stream);
+
+/* Incremental decoding, Backpack sense-mix of the LAST position only:
+ *   out[b, :] = sum_l sum_{j < len} softmax_j(scale * q[b,l,:] . k_cache[b,j,l,:]) * table[ids[b,j], l, :]
+ * i.e. row i = len - 1 of training/src/models/backpack.py:116-122 + :313 with the sense vectors served from the
+ * (vocab, nv, d) table of bp_sense_mix_table_fwd.  The reference has no incremental path for Backpacks (its generation
+ * loop re-runs the whole forward per token, training/src/utils/generation.py:34-44, 62-72); SURVEY.md section 8 row F2.
+ *   q (batch, nv, dk) contiguous; k_cache (max_batch, max_seqlen, nv, dk) with batch stride k_batch_stride (elements);
+ *   ids (max_batch, max_seqlen) int64 with batch stride ids_batch_stride, clamped to [0, vocab); out (batch, d).
+ *   len = seqlen, or seqlens[b] (device, int32) when not NULL.  dk % 8 == 0, d % 8 == 0.
+ */
+int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const int64_t* ids, const void* table, void* out,
+                            const int32_t* seqlens, int32_t batch, int32_t seqlen, int32_t nv, int32_t dk, int32_t d,
+                            int32_t vocab, int64_t k_batch_stride, int64_t ids_batch_stride, float softmax_scale,
+                            int32_t dtype, void* stream);
+
 /* residual += x W^T + bias, fp32 residual stream updated in place: the out_proj / fc2 GEMM of a pre-norm block
  * with the "dropout(0) + add" half of dropout_add_ln_fwd (flash_attn/modules/block.py:84-88, 101-105;
  * csrc/layer_norm/ln_fwd_kernels.cuh:98-131) moved into its epilogue, so the branch output is never written

@@ -27,7 +27,8 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ("bp_fmha_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd", "bp_ln_residual_fwd",
               "bp_linear_bias_act_fwd", "bp_linear_bias_residual_fwd", "bp_ln_fwd", "bp_rotary_qk_inplace", "bp_last_error", "bp_abi_version",
-              "bp_check_device"):
+              "bp_check_device", "bp_sense_mix_table_fwd", "bp_lm_head_stats_fwd", "bp_decode_attn_fwd",
+              "bp_sense_mix_decode_fwd"):
         assert s in syms
 
 

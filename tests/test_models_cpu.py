@@ -104,3 +104,53 @@ def test_gpt_lm_head_model_unfused_runs():
     with torch.no_grad():
         out = m(torch.randint(0, 100, (2, 16))).logits
     assert out.shape == (2, 16, 100)
+
+
+# ---- generation (training/src/utils/generation.py, flash_attn/utils/generation.py): host logic on the eager path ----
+def test_eager_incremental_decode_equals_prefix_rerun():
+    """The KV-cache / sense-cache bookkeeping (offsets, cache writes, position ids) on the un-fused model in fp32:
+    every incremental step must give the logits the reference's re-run loop gives (generation.py:62-72)."""
+    from backpacks_flash_attn_b200.utils.generation import InferenceParams
+    torch.manual_seed(0)
+    cfg = BackpackConfig(num_content_vectors=4, n_embd=64, n_head=4, n_layer=2, vocab_size=101, n_positions=64,
+                         resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    m = BackpackLMHeadModel(cfg).eval()
+    ids = torch.randint(0, 101, (3, 7))
+    inc = m.generate(ids, 20, return_dict_in_generate=True, output_scores=True)
+    rerun = m.generate(ids, 20, return_dict_in_generate=True, output_scores=True, incremental=False)
+    assert inc.sequences.shape == (3, 20) and torch.equal(inc.sequences[:, :7], ids)
+    assert torch.equal(inc.sequences, rerun.sequences)
+    assert max((a - b).abs().max().item() for a, b in zip(inc.scores, rerun.scores)) < 1e-5
+    # the re-run loop is the reference's: token t is the arg-max of the full forward on the prefix
+    with torch.no_grad():
+        assert torch.equal(rerun.sequences[:, 9], m(rerun.sequences[:, :9]).logits[:, -1].argmax(-1))
+    assert m.generate(ids, 9).shape == (3, 9) and m.sample(ids, 9).shape == (3, 9)
+    # caches: one per layer + the Backpack's two, sized by InferenceParams; a batch slice at batch_size_offset
+    params = InferenceParams(max_sequence_len=12, max_batch_size=5, batch_size_offset=2)
+    with torch.no_grad():
+        first = m(ids, inference_params=params).logits
+        assert torch.allclose(first, m(ids).logits, atol=1e-6)
+    kv = params.key_value_memory_dict
+    assert set(kv) == {0, 1, "backpack.ctx_k", "backpack.ids"}
+    assert kv[0].shape == (5, 12, 2, 4, 16) and kv["backpack.ctx_k"].shape == (5, 12, 4, 16)
+    assert torch.equal(kv["backpack.ids"][2:5, :7], ids)
+    params.sequence_len_offset = 7
+    with torch.no_grad(), pytest.raises(RuntimeError, match="one position per call"):
+        m(ids[:, :2], inference_params=params)
+    params.sequence_len_offset = 12
+    with torch.no_grad(), pytest.raises(RuntimeError, match="too small"):
+        m(ids[:, :1], inference_params=params)
+
+
+def test_gpt_eager_incremental_decode_equals_prefix_rerun():
+    from transformers import GPT2Config
+    torch.manual_seed(1)
+    g = GPTLMHeadModel(GPT2Config(n_embd=64, n_head=4, n_layer=2, vocab_size=101, n_positions=64, resid_pdrop=0.0,
+                                  embd_pdrop=0.0, attn_pdrop=0.0)).eval()
+    ids = torch.randint(0, 101, (2, 5))
+    inc = g.generate(ids, 16, return_dict_in_generate=True, output_scores=True)
+    rerun = g.generate(ids, 16, return_dict_in_generate=True, output_scores=True, incremental=False)
+    assert torch.equal(inc.sequences, rerun.sequences)
+    assert max((a - b).abs().max().item() for a, b in zip(inc.scores, rerun.scores)) < 1e-5
+    with pytest.raises(ValueError):
+        g.generate(ids, 5)
