@@ -12,8 +12,14 @@
 //                           (training/src/models/backpack.py:116-122 + :313 restricted to row i = len - 1).  The
 //                           reference has no incremental path for Backpacks: its generation loop re-runs the full forward
 //                           for every token (training/src/utils/generation.py:34-44, 62-72).
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "bp_common.cuh"
 #include "bp_host.h"
+
+namespace cg = cooperative_groups;
 
 namespace bp {
 namespace decode {
@@ -37,32 +43,44 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 // ---------------------------------------------------------------------------------------------
 // attention of one query per (batch, head) against the KV cache
 // ---------------------------------------------------------------------------------------------
-// One CTA of 128 threads per (batch, head).  A key row (DH 16-bit values) is read by 8 lanes with one or two 16-byte loads
-// each, so a warp streams 4 keys per instruction and a CTA 16; every 8-lane group runs its own online softmax over the
-// keys it sees (running max, sum and DH/8 accumulators per lane) and the 16 partial results are merged at the end in a
-// fixed order (shuffles inside the warp, then shared memory across warps): bitwise deterministic.
+// A thread-block CLUSTER of `nsplit` CTAs (1..8, chosen by the host so that small batches still fill the 148 SMs) per
+// (batch, head); CTA r of the cluster takes the r-th contiguous slice of the keys.  Inside a CTA (128 threads) a key row
+// (DH 16-bit values) is read by 8 lanes with one or two 16-byte loads each, so a warp streams 4 keys per instruction and
+// a CTA 16; the loads of four such steps (64 keys, 16 KB for DH = 64) are issued before the first is consumed.  Every
+// 8-lane group runs its own online softmax over the keys it sees (running max, sum and DH/8 accumulators per lane); the
+// 16 partial results of a CTA are merged in a fixed order (shuffles inside the warp, then shared memory across warps),
+// and the CTAs of the cluster are merged by rank 0 reading its peers' shared memory (DSMEM) in rank order: bitwise
+// deterministic for a given nsplit, no workspace in global memory.
+constexpr int kAttnUnroll = 4;
+
 struct AttnParams {
   const void* q;        // (batch, nheads, DH)
   const void* kv;       // cache: element (b, j, which, h, :) at b*batch_stride + j*row_stride + which*which_stride + h*DH
   void* out;            // (batch, nheads, DH)
   const int32_t* lens;  // (batch) keys to attend to per sequence, or null: `len` for all
   int64_t batch_stride, row_stride, which_stride;
-  int32_t batch, nheads, len;
+  int32_t batch, nheads, len, nsplit;
   float scale_log2;
 };
 
 template <int DH, bool kBF16>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
   constexpr int DPL = DH / 8;          // dims per lane (8 or 16)
-  const int b = blockIdx.x / p.nheads, h = blockIdx.x % p.nheads;
+  constexpr int NV = DPL / 8;          // 16-byte loads per lane and row
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int bh = blockIdx.x / p.nsplit;
+  const int b = bh / p.nheads, h = bh - b * p.nheads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp * 4 + (lane >> 3), slot = lane & 7;
   const int len = p.lens != nullptr ? p.lens[b] : p.len;
+  const int per = ((len + p.nsplit - 1) / p.nsplit + 15) & ~15;          // keys per CTA, a multiple of 16
+  const int j_begin = min(len, rank * per), j_end = min(len, j_begin + per);
   float q[DPL];
   {
     const uint4* qp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.q) + (static_cast<int64_t>(b) * p.nheads + h) * DH + slot * DPL);
 #pragma unroll
-    for (int c = 0; c < DPL / 8; ++c) {
+    for (int c = 0; c < NV; ++c) {
       float t[8];
       unpack8<kBF16>(__ldg(qp + c), t);
 #pragma unroll
@@ -74,41 +92,49 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
   float m = -INFINITY, l = 0.f, acc[DPL];
 #pragma unroll
   for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-  for (int j0 = 0; j0 < len; j0 += 16) {   // uniform trip count: the shuffles below need the whole warp
-    const int j = j0 + grp;
-    const bool live = j < len;
-    const uint4* kp = reinterpret_cast<const uint4*>(kbase + (live ? j : 0) * p.row_stride);
-    const uint4* vp = reinterpret_cast<const uint4*>(vbase + (live ? j : 0) * p.row_stride);
-    uint4 kr[DPL / 8], vr[DPL / 8];
+  // uniform trip count: the shuffles below need the whole warp
+  for (int j0 = j_begin; j0 < j_end; j0 += 16 * kAttnUnroll) {
+    uint4 kr[kAttnUnroll][NV], vr[kAttnUnroll][NV];
 #pragma unroll
-    for (int c = 0; c < DPL / 8; ++c) kr[c] = __ldg(kp + c), vr[c] = __ldg(vp + c);
-    float s = 0.f;
+    for (int u = 0; u < kAttnUnroll; ++u) {
+      const int j = j0 + u * 16 + grp;
+      const int64_t row = (j < j_end ? j : j_begin) * p.row_stride;       // dead lanes re-read a live row
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + row);
+      const uint4* vp = reinterpret_cast<const uint4*>(vbase + row);
 #pragma unroll
-    for (int c = 0; c < DPL / 8; ++c) {
-      float t[8];
-      unpack8<kBF16>(kr[c], t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s = fmaf(q[c * 8 + i], t[i], s);
+      for (int c = 0; c < NV; ++c) kr[u][c] = __ldg(kp + c), vr[u][c] = __ldg(vp + c);
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (live) {
-      const float m_new = fmaxf(m, s);
-      const float alpha = fast_exp2(m - m_new), pj = fast_exp2(s - m_new);
-      l = l * alpha + pj;
-      m = m_new;
 #pragma unroll
-      for (int c = 0; c < DPL / 8; ++c) {
+    for (int u = 0; u < kAttnUnroll; ++u) {
+      const bool live = j0 + u * 16 + grp < j_end;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
         float t[8];
-        unpack8<kBF16>(vr[c], t);
+        unpack8<kBF16>(kr[u][c], t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[c * 8 + i] = fmaf(pj, t[i], acc[c * 8 + i] * alpha);
+        for (int i = 0; i < 8; ++i) s = fmaf(q[c * 8 + i], t[i], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (live) {
+        const float m_new = fmaxf(m, s);
+        const float alpha = fast_exp2(m - m_new), pj = fast_exp2(s - m_new);
+        l = l * alpha + pj;
+        m = m_new;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+          float t[8];
+          unpack8<kBF16>(vr[u][c], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[c * 8 + i] = fmaf(pj, t[i], acc[c * 8 + i] * alpha);
+        }
       }
     }
   }
   // merge the four key groups of the warp (lanes with equal slot), then the four warps through shared memory
-  auto merge = [&](float m2, float l2, const float (&a2)[DPL]) {
+  auto merge = [&](float m2, float l2, const float* a2) {
     const float m_new = fmaxf(m, m2);
     const float w1 = m == -INFINITY ? 0.f : fast_exp2(m - m_new), w2 = m2 == -INFINITY ? 0.f : fast_exp2(m2 - m_new);
     l = l * w1 + l2 * w2;
@@ -124,8 +150,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
     for (int i = 0; i < DPL; ++i) a2[i] = __shfl_xor_sync(0xffffffffu, acc[i], off);
     merge(m2, l2, a2);
   }
-  __shared__ float sm[4][8][DPL + 2];
-  if (lane < 8) {
+  __shared__ float sm[4][8][DPL + 2];      // [warp][slot][m, l, acc...]; row [0] doubles as the CTA's merged partial
+  if (lane < 8 && warp != 0) {
     sm[warp][lane][0] = m, sm[warp][lane][1] = l;
 #pragma unroll
     for (int i = 0; i < DPL; ++i) sm[warp][lane][2 + i] = acc[i];
@@ -133,16 +159,26 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
   __syncthreads();
   if (warp == 0 && lane < 8) {
 #pragma unroll
-    for (int w = 1; w < 4; ++w) {
-      float a2[DPL];
+    for (int w = 1; w < 4; ++w) merge(sm[w][lane][0], sm[w][lane][1], &sm[w][lane][2]);
+    if (rank != 0) {
+      sm[0][lane][0] = m, sm[0][lane][1] = l;
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) a2[i] = sm[w][lane][2 + i];
-      merge(sm[w][lane][0], sm[w][lane][1], a2);
+      for (int i = 0; i < DPL; ++i) sm[0][lane][2 + i] = acc[i];
+    }
+  }
+  if (p.nsplit > 1) cluster.sync();        // the partials of ranks 1.. are visible cluster-wide
+  if (rank == 0 && warp == 0 && lane < 8) {
+    for (int r = 1; r < p.nsplit; ++r) {
+      const float* peer = cluster.map_shared_rank(&sm[0][lane][0], r);
+      float t[DPL + 2];
+#pragma unroll
+      for (int i = 0; i < DPL + 2; ++i) t[i] = peer[i];
+      merge(t[0], t[1], t + 2);
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
     uint16_t* op = static_cast<uint16_t*>(p.out) + (static_cast<int64_t>(b) * p.nheads + h) * DH + lane * DPL;
 #pragma unroll
-    for (int c = 0; c < DPL / 8; ++c) {
+    for (int c = 0; c < NV; ++c) {
       uint4 o;
       o.x = pack2<kBF16>(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
       o.y = pack2<kBF16>(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
@@ -151,19 +187,26 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
       reinterpret_cast<uint4*>(op)[c] = o;
     }
   }
+  if (p.nsplit > 1) cluster.sync();        // peers keep their shared memory alive until rank 0 has read it
 }
 
 // ---------------------------------------------------------------------------------------------
 // sense-mix of the last position
 // ---------------------------------------------------------------------------------------------
-// One CTA of 256 threads per (batch element, 128-column chunk of the output).  Phase 1: the (nv x len) attention weights
-// of the last position -- scores by one thread per (sense, key) pair, row max / sum per sense by block reductions -- are
-// normalised and written to shared memory (recomputed by each of the d/128 CTAs of a batch element: 48 MACs per weight
-// against the 128 x 2 bytes of sense-vector traffic it scales).  Phase 2: the weighted sum over the len * nv table rows
-// table[ids[j], l, chunk]: 16 lanes read one 256-byte row segment with 16-byte loads, a CTA has 16 rows in flight per
-// step; the 16 partial sums per column are merged through shared memory in a fixed order (deterministic).
+// A cluster of `nsplit` CTAs (1..8) per (batch element, 64-column chunk of the output); CTA r takes the r-th slice of
+// the context.  Phase 1a: per-sense running max / sum of the scores of the CTA's keys (one warp per sense), exchanged
+// through DSMEM and merged in rank order into the exact row max and 1 / row sum of every sense.  Phase 1b: normalised
+// weights of a tile of 256 keys into shared memory.  Phase 2: the weighted sum over the tile's (key, sense) table rows
+// table[ids[j], l, chunk]: 8 lanes read one 128-byte row segment with 16-byte loads, a CTA (256 threads) has 32 rows
+// in flight per step and issues 8 steps of loads before consuming them (32 KB in flight per CTA).  The 32 partial sums
+// per column are merged through shared memory in a fixed order, then across the cluster by rank 0: deterministic.  The
+// scores are recomputed by each of the d/64 column-chunk clusters of a batch element (48 MACs per weight against the
+// 64 x 2 bytes of sense-vector traffic it scales; the K rows come from L2).
 constexpr int kDecThreads = 256;
 constexpr int kTileKeys = 256;   // keys per weight tile in shared memory (nv * kTileKeys floats)
+constexpr int kMixCols = 64;     // output columns per CTA
+constexpr int kMixRows = kDecThreads / 8;   // table rows in flight per step
+constexpr int kMixUnroll = 8;
 
 struct MixParams {
   const void* q;          // (batch, nv, dk) query of the new position
@@ -173,19 +216,25 @@ struct MixParams {
   void* out;              // (batch, d)
   const int32_t* lens;    // (batch) or null
   int64_t k_batch_stride, ids_batch_stride;
-  int32_t batch, nv, dk, d, vocab, len;
+  int32_t batch, nv, dk, d, vocab, len, nsplit;
   float scale_log2;
 };
 
 template <bool kBF16>
 __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const MixParams p) {
   extern __shared__ float smem_f[];
-  float* wts = smem_f;                               // [nv][kTileKeys] normalised weights of the current key tile
+  float* wts = smem_f;                               // [kTileKeys][nv] normalised weights of the current key tile
   float* stat = wts + p.nv * kTileKeys;              // [nv][2] row max (log2 units) and 1 / row sum
-  float* red = stat + 2 * p.nv;                      // [kDecThreads] reduction scratch / [16][128] column partials
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  float* lstat = stat + 2 * p.nv;                    // [nv][2] this CTA's running max and sum (read by the peers)
+  float* part = lstat + 2 * p.nv;                    // [kMixRows][kMixCols] column partials
+  float* colsum = part + kMixRows * kMixCols;        // [kMixCols] this CTA's column sums (read by rank 0)
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int b = blockIdx.y, chunk = blockIdx.x / p.nsplit;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int len = p.lens != nullptr ? p.lens[b] : p.len;
+  const int per = ((len + p.nsplit - 1) / p.nsplit + 15) & ~15;
+  const int j_begin = min(len, rank * per), j_end = min(len, j_begin + per);
   const int nv = p.nv, dk = p.dk;
   const uint16_t* qb = static_cast<const uint16_t*>(p.q) + static_cast<int64_t>(b) * nv * dk;
   const uint16_t* kb = static_cast<const uint16_t*>(p.kcache) + b * p.k_batch_stride;
@@ -205,10 +254,10 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
     return s * p.scale_log2;
   };
 
-  // ---- phase 1a: per-sense row max and row sum (warp w handles senses w, w + 8, ...) ----
+  // ---- phase 1a: per-sense max and sum over this CTA's keys (warp w handles senses w, w + 8, ...) ----
   for (int l = warp; l < nv; l += kDecThreads / 32) {
     float m = -INFINITY, sum = 0.f;
-    for (int j = lane; j < len; j += 32) {
+    for (int j = j_begin + lane; j < j_end; j += 32) {
       const float s = score(l, j);
       const float m_new = fmaxf(m, s);
       sum = sum * fast_exp2(m - m_new) + fast_exp2(s - m_new);
@@ -221,62 +270,105 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
       sum = (m == -INFINITY ? 0.f : sum * fast_exp2(m - m_new)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2(m2 - m_new));
       m = m_new;
     }
-    if (lane == 0) stat[2 * l] = m, stat[2 * l + 1] = 1.f / sum;
+    if (lane == 0) lstat[2 * l] = m, lstat[2 * l + 1] = sum;
+  }
+  if (p.nsplit > 1) cluster.sync(); else __syncthreads();
+  for (int l = tid; l < nv; l += kDecThreads) {      // merge the cluster's partial statistics in rank order
+    float m = -INFINITY, sum = 0.f;
+    for (int r = 0; r < p.nsplit; ++r) {
+      const float* peer = p.nsplit > 1 ? cluster.map_shared_rank(lstat, r) : lstat;
+      const float m2 = peer[2 * l], s2 = peer[2 * l + 1];
+      const float m_new = fmaxf(m, m2);
+      sum = (m == -INFINITY ? 0.f : sum * fast_exp2(m - m_new)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2(m2 - m_new));
+      m = m_new;
+    }
+    stat[2 * l] = m, stat[2 * l + 1] = sum > 0.f ? 1.f / sum : 0.f;
   }
   __syncthreads();
 
   // ---- phase 2 set-up: this thread's 8 output columns and its row slot ----
-  const int slot = tid & 15, rslot = tid >> 4;        // 16 lanes x 16 B = 128 columns; 16 rows in flight
-  const int col0 = chunk * 128 + slot * 8;
+  const int slot = tid & 7, rslot = tid >> 3;         // 8 lanes x 16 B = 64 columns; 32 rows in flight
+  const int col0 = chunk * kMixCols + slot * 8;
   const bool col_ok = col0 < p.d;                     // d is a multiple of 8
-  const uint16_t* tb = static_cast<const uint16_t*>(p.table) + col0;
+  const uint16_t* tb = static_cast<const uint16_t*>(p.table) + (col_ok ? col0 : 0);
   const int64_t* ids = p.ids + b * p.ids_batch_stride;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  for (int j0 = 0; j0 < len; j0 += kTileKeys) {
-    const int nkeys = min(kTileKeys, len - j0);
+  for (int j0 = j_begin; j0 < j_end; j0 += kTileKeys) {
+    const int nkeys = min(kTileKeys, j_end - j0);
     // ---- phase 1b: normalised weights of this key tile ----
     for (int idx = tid; idx < nv * nkeys; idx += kDecThreads) {
-      const int l = idx / nkeys, jj = idx - l * nkeys;
-      wts[l * kTileKeys + jj] = fast_exp2(score(l, j0 + jj) - stat[2 * l]) * stat[2 * l + 1];
+      const int jj = idx / nv, l = idx - jj * nv;     // consecutive threads walk the senses of one key: contiguous K
+      wts[idx] = fast_exp2(score(l, j0 + jj) - stat[2 * l]) * stat[2 * l + 1];
     }
     __syncthreads();
     // ---- phase 2: acc += w[l][j] * table[ids[j], l, cols]; pairs (j, l) are walked key-major: the nv rows of one token
     //      are contiguous in the table ----
-    if (col_ok) {
-      const int npairs = nkeys * nv;
-#pragma unroll 4
-      for (int pr = rslot; pr < npairs; pr += 16) {
-        const int jj = pr / nv, l = pr - jj * nv;
-        const int id = min(max(static_cast<int>(__ldg(ids + j0 + jj)), 0), p.vocab - 1);
-        const uint4 row = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<int64_t>(id) * nv + l) * p.d));
-        const float w = wts[l * kTileKeys + jj];
-        float t[8];
-        unpack8<kBF16>(row, t);
+    const int npairs = nkeys * nv;
+    for (int pr0 = 0; pr0 < npairs; pr0 += kMixRows * kMixUnroll) {
+      uint4 row[kMixUnroll];
+      float w[kMixUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, t[i], acc[i]);
+      for (int u = 0; u < kMixUnroll; ++u) {
+        const int pr = pr0 + u * kMixRows + rslot;
+        const bool live = pr < npairs;
+        const int jj = live ? pr / nv : 0, l = live ? pr - jj * nv : 0;
+        const int id = min(max(static_cast<int>(__ldg(ids + j0 + jj)), 0), p.vocab - 1);
+        row[u] = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<int64_t>(id) * nv + l) * p.d));
+        w[u] = live ? wts[pr] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kMixUnroll; ++u) {
+        float t[8];
+        unpack8<kBF16>(row[u], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[u], t[i], acc[i]);
       }
     }
     __syncthreads();
   }
-  // ---- merge the 16 row slots (fixed order) and store ----
-  float* part = red;   // [16][128]
+  // ---- merge the 32 row slots (fixed order), then the cluster (rank order), and store ----
 #pragma unroll
-  for (int i = 0; i < 8; ++i) part[rslot * 128 + slot * 8 + i] = acc[i];
+  for (int i = 0; i < 8; ++i) part[rslot * kMixCols + slot * 8 + i] = acc[i];
   __syncthreads();
-  if (tid < 128 && chunk * 128 + tid < p.d) {
+  if (tid < kMixCols) {
     float s = 0.f;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s += part[r * 128 + tid];
-    uint16_t* op = static_cast<uint16_t*>(p.out) + static_cast<int64_t>(b) * p.d + chunk * 128 + tid;
+    for (int r = 0; r < kMixRows; ++r) s += part[r * kMixCols + tid];
+    colsum[tid] = s;
+  }
+  if (p.nsplit > 1) cluster.sync(); else __syncthreads();
+  if (rank == 0 && tid < kMixCols && chunk * kMixCols + tid < p.d) {
+    float s = 0.f;
+    for (int r = 0; r < p.nsplit; ++r) s += (p.nsplit > 1 ? cluster.map_shared_rank(colsum, r) : colsum)[tid];
+    uint16_t* op = static_cast<uint16_t*>(p.out) + static_cast<int64_t>(b) * p.d + chunk * kMixCols + tid;
     if constexpr (kBF16) {
       *reinterpret_cast<__nv_bfloat16*>(op) = __float2bfloat16_rn(s);
     } else {
       *reinterpret_cast<__half*>(op) = __float2half_rn(s);
     }
   }
+  if (p.nsplit > 1) cluster.sync();        // peers keep lstat / colsum alive until everyone has read them
+}
+
+// number of key slices (cluster size) that brings the grid to about two CTAs per SM without slices under `min_keys`
+inline int pick_nsplit(int64_t ctas, int len, int min_keys) {
+  int n = static_cast<int>((2 * 148 + ctas - 1) / ctas);
+  n = std::min(n, std::max(1, len / min_keys));
+  return std::max(1, std::min(n, 8));
+}
+
+template <typename Kern, typename Params>
+cudaError_t launch_cluster(Kern kern, dim3 grid, int threads, size_t smem, int nsplit, cudaStream_t st, const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nsplit, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 }  // namespace decode
@@ -301,13 +393,17 @@ extern "C" int bp_decode_attn_fwd(const void* q, const void* kv_cache, void* out
   p.batch_stride = kv_batch_stride, p.row_stride = kv_row_stride, p.which_stride = kv_which_stride;
   p.batch = batch, p.nheads = nheads, p.len = seqlen_k;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  // with per-sequence lengths on the device the host only knows the batch: assume long contexts
+  p.nsplit = decode::pick_nsplit(static_cast<int64_t>(batch) * nheads, seqlens_k ? (1 << 20) : seqlen_k, 64);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf = dtype == BP_DTYPE_BF16;
-  const dim3 grid(batch * nheads);
-  if (headdim == 64) {
-    if (bf) decode::decode_attn_kernel<64, true><<<grid, 128, 0, st>>>(p); else decode::decode_attn_kernel<64, false><<<grid, 128, 0, st>>>(p);
-  } else {
-    if (bf) decode::decode_attn_kernel<128, true><<<grid, 128, 0, st>>>(p); else decode::decode_attn_kernel<128, false><<<grid, 128, 0, st>>>(p);
+  const dim3 grid(batch * nheads * p.nsplit);
+  auto kern = headdim == 64 ? (bf ? decode::decode_attn_kernel<64, true> : decode::decode_attn_kernel<64, false>)
+                            : (bf ? decode::decode_attn_kernel<128, true> : decode::decode_attn_kernel<128, false>);
+  const cudaError_t e = decode::launch_cluster(kern, grid, 128, 0, p.nsplit, st, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "%s: launch failed: %s", fn, cudaGetErrorString(e));
   }
   return check_launch(fn);
 }
@@ -330,7 +426,10 @@ extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const
   p.k_batch_stride = k_batch_stride, p.ids_batch_stride = ids_batch_stride;
   p.batch = batch, p.nv = nv, p.dk = dk, p.d = d, p.vocab = vocab, p.len = seqlen;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(nv) * decode::kTileKeys + 2 * nv + 16 * 128);
+  const int chunks = (d + decode::kMixCols - 1) / decode::kMixCols;
+  p.nsplit = decode::pick_nsplit(static_cast<int64_t>(batch) * chunks, seqlens ? (1 << 20) : seqlen, 32);
+  const size_t smem = sizeof(float) * (static_cast<size_t>(nv) * decode::kTileKeys + 4 * nv +
+                                       decode::kMixRows * decode::kMixCols + decode::kMixCols);
   if (smem > 200 * 1024) return fail(BP_ERR_UNSUPPORTED, "%s: too many senses (%d) for the weight tile", fn, nv);
   const bool bf = dtype == BP_DTYPE_BF16;
   auto kern = bf ? decode::sense_mix_decode_kernel<true> : decode::sense_mix_decode_kernel<false>;
@@ -341,6 +440,11 @@ extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const
       return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     }
   }
-  kern<<<dim3((d + 127) / 128, batch), decode::kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const cudaError_t e = decode::launch_cluster(kern, dim3(chunks * p.nsplit, batch), decode::kDecThreads, smem, p.nsplit,
+                                               static_cast<cudaStream_t>(stream), p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "%s: launch failed: %s", fn, cudaGetErrorString(e));
+  }
   return check_launch(fn);
 }
