@@ -193,19 +193,24 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
 // ---------------------------------------------------------------------------------------------
 // sense-mix of the last position
 // ---------------------------------------------------------------------------------------------
-// A cluster of `nsplit` CTAs (1..8) per (batch element, 64-column chunk of the output); CTA r takes the r-th slice of
-// the context.  Phase 1a: per-sense running max / sum of the scores of the CTA's keys (one warp per sense), exchanged
-// through DSMEM and merged in rank order into the exact row max and 1 / row sum of every sense.  Phase 1b: normalised
-// weights of a tile of 256 keys into shared memory.  Phase 2: the weighted sum over the tile's (key, sense) table rows
-// table[ids[j], l, chunk]: 8 lanes read one 128-byte row segment with 16-byte loads, a CTA (256 threads) has 32 rows
-// in flight per step and issues 8 steps of loads before consuming them (32 KB in flight per CTA).  The 32 partial sums
-// per column are merged through shared memory in a fixed order, then across the cluster by rank 0: deterministic.  The
-// scores are recomputed by each of the d/64 column-chunk clusters of a batch element (48 MACs per weight against the
-// 64 x 2 bytes of sense-vector traffic it scales; the K rows come from L2).
+// A cluster of `nsplit` CTAs (1..8) per (batch element, column chunk of the output); CTA r takes the r-th slice of the
+// context.  A chunk is 8 * kLanes columns: kLanes = 32 (256 columns, a whole warp per table row) when the batch alone
+// fills the GPU, kLanes = 8 (64 columns) for small batches.
+//   scores   The K rows of a tile of keys, (key, sense)-major and contiguous in the cache, are read as one flat stream
+//            of 16-byte words: a warp covers floor(32 / (dk/8)) whole rows per load instruction (480 contiguous bytes
+//            for dk = 48), the dk/8 partial dot products of a row are summed with shuffles, and the score goes to
+//            shared memory, sc[sense][key].  q is staged in shared memory as fp32, pre-multiplied by scale * log2(e).
+//   pass A   per tile: scores, then the running max / sum of every sense (one warp per sense).  The CTAs of the
+//            cluster exchange their (max, sum) through DSMEM and merge them in rank order: exact softmax statistics.
+//   pass B   per tile: (scores again, unless the slice is a single tile and they are still in shared memory,)
+//            normalise in place, then acc += w[l][j] * table[ids[j], l, cols]: kLanes lanes read one row segment with
+//            16-byte loads, 256 / kLanes rows per step, 8 steps of loads issued before the first is consumed (32 KB in
+//            flight per CTA).
+//   merge    the row slots through shared memory in a fixed order, the cluster by rank 0 in rank order: deterministic
+//            for a given launch configuration.
+// The scores are recomputed by each of the column-chunk clusters of a batch element (for kLanes = 32 and d = 768: 3x,
+// 96 bytes of K per 512 bytes of sense vector; the K rows come from L2).
 constexpr int kDecThreads = 256;
-constexpr int kTileKeys = 256;   // keys per weight tile in shared memory (nv * kTileKeys floats)
-constexpr int kMixCols = 64;     // output columns per CTA
-constexpr int kMixRows = kDecThreads / 8;   // table rows in flight per step
 constexpr int kMixUnroll = 8;
 
 struct MixParams {
@@ -216,18 +221,26 @@ struct MixParams {
   void* out;              // (batch, d)
   const int32_t* lens;    // (batch) or null
   int64_t k_batch_stride, ids_batch_stride;
-  int32_t batch, nv, dk, d, vocab, len, nsplit;
+  int32_t batch, nv, dk, d, vocab, len, nsplit, tile;   // tile: keys per score tile in shared memory (multiple of 16)
   float scale_log2;
 };
 
-template <bool kBF16>
+__host__ __device__ inline size_t mix_smem_floats(int nv, int dk, int tile, int lanes) {
+  return static_cast<size_t>(nv) * dk + static_cast<size_t>(nv) * tile + 4 * nv + (kDecThreads / lanes) * (8 * lanes) + 8 * lanes;
+}
+
+template <bool kBF16, int kLanes>
 __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const MixParams p) {
+  constexpr int kCols = 8 * kLanes;                  // output columns per CTA
+  constexpr int kRows = kDecThreads / kLanes;        // table rows in flight per step
   extern __shared__ float smem_f[];
-  float* wts = smem_f;                               // [kTileKeys][nv] normalised weights of the current key tile
-  float* stat = wts + p.nv * kTileKeys;              // [nv][2] row max (log2 units) and 1 / row sum
-  float* lstat = stat + 2 * p.nv;                    // [nv][2] this CTA's running max and sum (read by the peers)
-  float* part = lstat + 2 * p.nv;                    // [kMixRows][kMixCols] column partials
-  float* colsum = part + kMixRows * kMixCols;        // [kMixCols] this CTA's column sums (read by rank 0)
+  const int nv = p.nv, dk = p.dk, tile = p.tile;
+  float* qs = smem_f;                                // [nv][dk] q * scale * log2(e)
+  float* sc = qs + nv * dk;                          // [nv][tile] scores, then normalised weights, of the current tile
+  float* stat = sc + nv * tile;                      // [nv][2] row max (log2 units) and 1 / row sum
+  float* lstat = stat + 2 * nv;                      // [nv][2] this CTA's running max and sum (read by the peers)
+  float* part = lstat + 2 * nv;                      // [kRows][kCols] column partials
+  float* colsum = part + kRows * kCols;              // [kCols] this CTA's column sums (read by rank 0)
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int b = blockIdx.y, chunk = blockIdx.x / p.nsplit;
@@ -235,42 +248,75 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
   const int len = p.lens != nullptr ? p.lens[b] : p.len;
   const int per = ((len + p.nsplit - 1) / p.nsplit + 15) & ~15;
   const int j_begin = min(len, rank * per), j_end = min(len, j_begin + per);
-  const int nv = p.nv, dk = p.dk;
-  const uint16_t* qb = static_cast<const uint16_t*>(p.q) + static_cast<int64_t>(b) * nv * dk;
   const uint16_t* kb = static_cast<const uint16_t*>(p.kcache) + b * p.k_batch_stride;
 
-  // score of (sense l, key j) in log2 units; dk is a multiple of 8
-  auto score = [&](int l, int j) {
-    const uint4* qp = reinterpret_cast<const uint4*>(qb + l * dk);
-    const uint4* kp = reinterpret_cast<const uint4*>(kb + (static_cast<int64_t>(j) * nv + l) * dk);
-    float s = 0.f;
-    for (int c = 0; c < dk / 8; ++c) {
-      float a[8], k8[8];
-      unpack8<kBF16>(__ldg(qp + c), a);
-      unpack8<kBF16>(__ldg(kp + c), k8);
+  {
+    const uint16_t* qb = static_cast<const uint16_t*>(p.q) + static_cast<int64_t>(b) * nv * dk;
+    for (int i = tid; i < nv * dk / 8; i += kDecThreads) {
+      float t[8];
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(qb) + i), t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s = fmaf(a[i], k8[i], s);
+      for (int e = 0; e < 8; ++e) qs[i * 8 + e] = t[e] * p.scale_log2;
     }
-    return s * p.scale_log2;
+    for (int i = tid; i < 2 * nv; i += kDecThreads) lstat[i] = (i & 1) ? 0.f : -INFINITY;
+  }
+  __syncthreads();
+
+  // scores of the keys [j0, j0 + nkeys) into sc[l * tile + jj]
+  const int C = dk / 8;                              // 16-byte words per K row
+  const int rpw = 32 / C;                            // whole rows per warp-wide load (dk <= 256)
+  const int my_r = lane / C, my_c = lane - my_r * C;
+  const bool my_on = my_r < rpw;
+  auto compute_scores = [&](int j0, int nkeys) {
+    const int nrows = nkeys * nv;
+    const uint4* kt = reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j0) * nv * dk);
+    for (int row0 = warp * rpw; row0 < nrows; row0 += (kDecThreads / 32) * rpw) {
+      const int row = row0 + my_r;
+      const bool on = my_on && row < nrows;
+      float s = 0.f;
+      int jj = 0, l = 0;
+      if (on) {
+        jj = row / nv, l = row - jj * nv;
+        float k8[8];
+        unpack8<kBF16>(__ldg(kt + static_cast<int64_t>(row) * C + my_c), k8);
+        const float4 qa = *reinterpret_cast<const float4*>(qs + l * dk + my_c * 8);
+        const float4 qb4 = *reinterpret_cast<const float4*>(qs + l * dk + my_c * 8 + 4);
+        s = qa.x * k8[0] + qa.y * k8[1] + qa.z * k8[2] + qa.w * k8[3] + qb4.x * k8[4] + qb4.y * k8[5] + qb4.z * k8[6] + qb4.w * k8[7];
+      }
+      float tot = s;
+      for (int i = 1; i < C; ++i) tot += __shfl_down_sync(0xffffffffu, s, i);
+      if (on && my_c == 0) sc[l * tile + jj] = tot;
+    }
   };
 
-  // ---- phase 1a: per-sense max and sum over this CTA's keys (warp w handles senses w, w + 8, ...) ----
-  for (int l = warp; l < nv; l += kDecThreads / 32) {
-    float m = -INFINITY, sum = 0.f;
-    for (int j = j_begin + lane; j < j_end; j += 32) {
-      const float s = score(l, j);
-      const float m_new = fmaxf(m, s);
-      sum = sum * fast_exp2(m - m_new) + fast_exp2(s - m_new);
-      m = m_new;
-    }
+  // ---- pass A: running max / sum of every sense over this CTA's keys (warp w owns senses w, w + 8, ...) ----
+  const bool single_tile = j_end - j_begin <= tile;
+  for (int j0 = j_begin; j0 < j_end; j0 += tile) {
+    const int nkeys = min(tile, j_end - j0);
+    compute_scores(j0, nkeys);
+    __syncthreads();
+    for (int l = warp; l < nv; l += kDecThreads / 32) {
+      float m = -INFINITY, sum = 0.f;
+      for (int jj = lane; jj < nkeys; jj += 32) {
+        const float s = sc[l * tile + jj];
+        const float m_new = fmaxf(m, s);
+        sum = sum * fast_exp2(m - m_new) + fast_exp2(s - m_new);
+        m = m_new;
+      }
+      float m0 = lstat[2 * l], s0 = lstat[2 * l + 1];      // running value of the earlier tiles, merged first
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m, off), s2 = __shfl_xor_sync(0xffffffffu, sum, off);
-      const float m_new = fmaxf(m, m2);
-      sum = (m == -INFINITY ? 0.f : sum * fast_exp2(m - m_new)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2(m2 - m_new));
-      m = m_new;
+      for (int off = 16; off >= 1; off >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, off), s2 = __shfl_xor_sync(0xffffffffu, sum, off);
+        const float m_new = fmaxf(m, m2);
+        sum = (m == -INFINITY ? 0.f : sum * fast_exp2(m - m_new)) + (m2 == -INFINITY ? 0.f : s2 * fast_exp2(m2 - m_new));
+        m = m_new;
+      }
+      const float m_new = fmaxf(m, m0);
+      sum = (m == -INFINITY ? 0.f : sum * fast_exp2(m - m_new)) + (m0 == -INFINITY ? 0.f : s0 * fast_exp2(m0 - m_new));
+      __syncwarp();
+      if (lane == 0) lstat[2 * l] = m_new, lstat[2 * l + 1] = sum;
     }
-    if (lane == 0) lstat[2 * l] = m, lstat[2 * l + 1] = sum;
+    if (!single_tile) __syncthreads();               // sc is overwritten by the next tile
   }
   if (p.nsplit > 1) cluster.sync(); else __syncthreads();
   for (int l = tid; l < nv; l += kDecThreads) {      // merge the cluster's partial statistics in rank order
@@ -286,9 +332,9 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
   }
   __syncthreads();
 
-  // ---- phase 2 set-up: this thread's 8 output columns and its row slot ----
-  const int slot = tid & 7, rslot = tid >> 3;         // 8 lanes x 16 B = 64 columns; 32 rows in flight
-  const int col0 = chunk * kMixCols + slot * 8;
+  // ---- pass B set-up: this thread's 8 output columns and its row slot ----
+  const int slot = tid % kLanes, rslot = tid / kLanes;
+  const int col0 = chunk * kCols + slot * 8;
   const bool col_ok = col0 < p.d;                     // d is a multiple of 8
   const uint16_t* tb = static_cast<const uint16_t*>(p.table) + (col_ok ? col0 : 0);
   const int64_t* ids = p.ids + b * p.ids_batch_stride;
@@ -296,28 +342,30 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  for (int j0 = j_begin; j0 < j_end; j0 += kTileKeys) {
-    const int nkeys = min(kTileKeys, j_end - j0);
-    // ---- phase 1b: normalised weights of this key tile ----
-    for (int idx = tid; idx < nv * nkeys; idx += kDecThreads) {
-      const int jj = idx / nv, l = idx - jj * nv;     // consecutive threads walk the senses of one key: contiguous K
-      wts[idx] = fast_exp2(score(l, j0 + jj) - stat[2 * l]) * stat[2 * l + 1];
+  for (int j0 = j_begin; j0 < j_end; j0 += tile) {
+    const int nkeys = min(tile, j_end - j0);
+    if (!single_tile) {
+      compute_scores(j0, nkeys);
+      __syncthreads();
+    }
+    for (int l = warp; l < nv; l += kDecThreads / 32) {   // normalise in place
+      const float m = stat[2 * l], inv = stat[2 * l + 1];
+      for (int jj = lane; jj < nkeys; jj += 32) sc[l * tile + jj] = fast_exp2(sc[l * tile + jj] - m) * inv;
     }
     __syncthreads();
-    // ---- phase 2: acc += w[l][j] * table[ids[j], l, cols]; pairs (j, l) are walked key-major: the nv rows of one token
-    //      are contiguous in the table ----
+    // acc += w[l][j] * table[ids[j], l, cols]; pairs (j, l) are walked key-major: the nv rows of a token are contiguous
     const int npairs = nkeys * nv;
-    for (int pr0 = 0; pr0 < npairs; pr0 += kMixRows * kMixUnroll) {
+    for (int pr0 = 0; pr0 < npairs; pr0 += kRows * kMixUnroll) {
       uint4 row[kMixUnroll];
       float w[kMixUnroll];
 #pragma unroll
       for (int u = 0; u < kMixUnroll; ++u) {
-        const int pr = pr0 + u * kMixRows + rslot;
+        const int pr = pr0 + u * kRows + rslot;
         const bool live = pr < npairs;
         const int jj = live ? pr / nv : 0, l = live ? pr - jj * nv : 0;
         const int id = min(max(static_cast<int>(__ldg(ids + j0 + jj)), 0), p.vocab - 1);
         row[u] = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<int64_t>(id) * nv + l) * p.d));
-        w[u] = live ? wts[pr] : 0.f;
+        w[u] = live ? sc[l * tile + jj] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < kMixUnroll; ++u) {
@@ -329,25 +377,28 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
     }
     __syncthreads();
   }
-  // ---- merge the 32 row slots (fixed order), then the cluster (rank order), and store ----
+  // ---- merge the row slots (fixed order), then the cluster (rank order), and store ----
 #pragma unroll
-  for (int i = 0; i < 8; ++i) part[rslot * kMixCols + slot * 8 + i] = acc[i];
+  for (int i = 0; i < 8; ++i) part[rslot * kCols + slot * 8 + i] = acc[i];
   __syncthreads();
-  if (tid < kMixCols) {
+  for (int c = tid; c < kCols; c += kDecThreads) {
     float s = 0.f;
 #pragma unroll
-    for (int r = 0; r < kMixRows; ++r) s += part[r * kMixCols + tid];
-    colsum[tid] = s;
+    for (int r = 0; r < kRows; ++r) s += part[r * kCols + c];
+    colsum[c] = s;
   }
   if (p.nsplit > 1) cluster.sync(); else __syncthreads();
-  if (rank == 0 && tid < kMixCols && chunk * kMixCols + tid < p.d) {
-    float s = 0.f;
-    for (int r = 0; r < p.nsplit; ++r) s += (p.nsplit > 1 ? cluster.map_shared_rank(colsum, r) : colsum)[tid];
-    uint16_t* op = static_cast<uint16_t*>(p.out) + static_cast<int64_t>(b) * p.d + chunk * kMixCols + tid;
-    if constexpr (kBF16) {
-      *reinterpret_cast<__nv_bfloat16*>(op) = __float2bfloat16_rn(s);
-    } else {
-      *reinterpret_cast<__half*>(op) = __float2half_rn(s);
+  if (rank == 0) {
+    for (int c = tid; c < kCols; c += kDecThreads) {
+      if (chunk * kCols + c >= p.d) continue;
+      float s = 0.f;
+      for (int r = 0; r < p.nsplit; ++r) s += (p.nsplit > 1 ? cluster.map_shared_rank(colsum, r) : colsum)[c];
+      uint16_t* op = static_cast<uint16_t*>(p.out) + static_cast<int64_t>(b) * p.d + chunk * kCols + c;
+      if constexpr (kBF16) {
+        *reinterpret_cast<__nv_bfloat16*>(op) = __float2bfloat16_rn(s);
+      } else {
+        *reinterpret_cast<__half*>(op) = __float2half_rn(s);
+      }
     }
   }
   if (p.nsplit > 1) cluster.sync();        // peers keep lstat / colsum alive until everyone has read them
@@ -426,13 +477,20 @@ extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const
   p.k_batch_stride = k_batch_stride, p.ids_batch_stride = ids_batch_stride;
   p.batch = batch, p.nv = nv, p.dk = dk, p.d = d, p.vocab = vocab, p.len = seqlen;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  const int chunks = (d + decode::kMixCols - 1) / decode::kMixCols;
-  p.nsplit = decode::pick_nsplit(static_cast<int64_t>(batch) * chunks, seqlens ? (1 << 20) : seqlen, 32);
-  const size_t smem = sizeof(float) * (static_cast<size_t>(nv) * decode::kTileKeys + 4 * nv +
-                                       decode::kMixRows * decode::kMixCols + decode::kMixCols);
-  if (smem > 200 * 1024) return fail(BP_ERR_UNSUPPORTED, "%s: too many senses (%d) for the weight tile", fn, nv);
+  if (dk > 256) return fail(BP_ERR_UNSUPPORTED, "%s: dk must be at most 256 (got %d)", fn, dk);
+  // a whole warp per table row (256-column chunks) when the batch alone fills the SMs, 8 lanes (64 columns) otherwise
+  const int lanes = static_cast<int64_t>(batch) * ((d + 255) / 256) >= 148 ? 32 : 8;
+  const int cols = 8 * lanes, chunks = (d + cols - 1) / cols;
+  const int len_hint = seqlens ? (1 << 20) : seqlen;
+  p.nsplit = decode::pick_nsplit(static_cast<int64_t>(batch) * chunks, len_hint, 32);
+  const int per = ((len_hint + p.nsplit - 1) / p.nsplit + 15) & ~15;
+  const int tile_max = std::max(16, (64 * 1024 / (4 * nv)) & ~15);       // <= 64 KB of scores
+  p.tile = std::min(per, tile_max);
+  const size_t smem = sizeof(float) * decode::mix_smem_floats(nv, dk, p.tile, lanes);
+  if (smem > 200 * 1024) return fail(BP_ERR_UNSUPPORTED, "%s: too many senses (%d) for the score tile", fn, nv);
   const bool bf = dtype == BP_DTYPE_BF16;
-  auto kern = bf ? decode::sense_mix_decode_kernel<true> : decode::sense_mix_decode_kernel<false>;
+  auto kern = lanes == 32 ? (bf ? decode::sense_mix_decode_kernel<true, 32> : decode::sense_mix_decode_kernel<false, 32>)
+                          : (bf ? decode::sense_mix_decode_kernel<true, 8> : decode::sense_mix_decode_kernel<false, 8>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {

@@ -281,6 +281,22 @@ class BackpackModel(GPTPreTrainedModel):
         scale = attn.softmax_scale or 1.0 / math.sqrt(dk)
         if self.fused_sense_mix and dk % 8 != 0:
             qk = torch.nn.functional.pad(qk, (0, (-dk) % 8))        # zero columns leave q.k unchanged (ops/sense_mix.py)
+        if inference_params.cache_position is not None:
+            # write position / context lengths on the device (CUDA-graph decode step, utils/generation.py)
+            if not self.fused_sense_mix or qk.shape[1] != 1:
+                raise RuntimeError("a device-offset decode step needs the fused sense-mix and one position per call")
+            kvd = inference_params.key_value_memory_dict
+            if "backpack.ctx_k" not in kvd:
+                raise RuntimeError("device-offset decoding starts after the prompt pass has allocated the caches")
+            b0 = inference_params.batch_size_offset
+            b1 = b0 + qk.shape[0]
+            k_cache, ids_cache = kvd["backpack.ctx_k"][b0:b1], kvd["backpack.ids"][b0:b1]
+            k_cache.index_copy_(1, inference_params.cache_position, qk[:, :, 1])
+            ids_cache.index_copy_(1, inference_params.cache_position, input_ids)
+            table = self.current_sense_table(force=True)
+            out = sense_mix_decode(qk[:, 0, 0], k_cache, ids_cache, table, 0, softmax_scale=scale,
+                                   seqlens=inference_params.cache_lengths[b0:b1])
+            return out.unsqueeze(1)
         k_cache, ids_cache = self._decode_caches(qk, input_ids, inference_params)
         if offset > 0 and qk.shape[1] != 1:
             raise RuntimeError("after the prompt pass, decoding advances one position per call")
@@ -317,6 +333,13 @@ class BackpackLMHeadModel(BackpackPreTrainedModel, GenerationMixin):
 
     def tie_weights(self):
         self.lm_head.weight = self.transformer.embeddings.word_embeddings.weight
+
+    def graphed_decode_ok(self):
+        """Whether a decode step can run with device-side offsets (and so inside a CUDA graph): every operator of the
+        step must be one of this library's CUDA kernels or a stream-ordered torch op."""
+        cfg = self.config
+        return bool(getattr(cfg, "use_flash_attn", False) and self.transformer.fused_sense_mix and not self.training
+                    and getattr(cfg, "rotary_emb_fraction", 0.0) == 0.0 and cfg.n_embd // cfg.n_head in (64, 128))
 
     def forward(self, input_ids, position_ids=None, inference_params=None, num_last_tokens=0):
         """num_last_tokens > 0: project only the last positions to the vocabulary (the generation loop consumes

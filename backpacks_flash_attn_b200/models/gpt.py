@@ -181,6 +181,12 @@ class GPTLMHeadModel(GPTPreTrainedModel, GenerationMixin):
     def tie_weights(self):
         self.lm_head.weight = self.transformer.embeddings.word_embeddings.weight
 
+    def graphed_decode_ok(self):
+        """Whether a decode step can run with device-side offsets, i.e. inside a CUDA graph (utils/generation.py)."""
+        cfg = self.config
+        return bool(getattr(cfg, "use_flash_attn", False) and not self.training
+                    and getattr(cfg, "rotary_emb_fraction", 0.0) == 0.0 and cfg.n_embd // cfg.n_head in (64, 128))
+
     def forward(self, input_ids, position_ids=None, inference_params=None, num_last_tokens=0):
         """inference_params: KV caches for generation (gpt.py:273-281).  num_last_tokens > 0 projects only the last
         positions to the vocabulary (the generation loop reads logits[:, -1] only)."""

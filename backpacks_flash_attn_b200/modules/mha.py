@@ -135,6 +135,29 @@ class MHA(nn.Module):
         cache[batch_start:batch_end, sequence_start:sequence_end] = kv
         return cache[batch_start:batch_end]
 
+    def _forward_cached_device_offsets(self, x, inference_params):
+        """Decode step whose write position and context lengths are device tensors (`InferenceParams.cache_position`,
+        `cache_lengths`): nothing depends on host integers, so the step can be captured in a CUDA graph."""
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise RuntimeError("a device-offset decode step takes (batch, 1, hidden) input")
+        if not self.use_flash_attn or self.rotary_emb_dim > 0:
+            raise RuntimeError("device-offset decoding needs use_flash_attn=True and no rotary embedding "
+                               "(the rotary tables are sliced on the host)")
+        cache = inference_params.key_value_memory_dict.get(self.layer_idx)
+        if cache is None:
+            raise RuntimeError("device-offset decoding starts after the prompt pass has allocated the KV cache")
+        b0 = inference_params.batch_size_offset
+        b1 = b0 + x.shape[0]
+        if b1 > cache.shape[0]:
+            raise RuntimeError(f"KV cache of shape {tuple(cache.shape)} is too small for batch rows {b0}:{b1}")
+        qkv = self.Wqkv(x)
+        qkv = qkv.reshape(*qkv.shape[:-1], 3, self.num_heads, self.head_dim)
+        cache = cache[b0:b1]
+        cache.index_copy_(1, inference_params.cache_position, qkv[:, :, 1:])
+        scale = self.inner_attn.softmax_scale or 1.0 / math.sqrt(self.head_dim)
+        return decode_attention(qkv[:, :, 0], cache, 0, softmax_scale=scale,
+                                seqlens_k=inference_params.cache_lengths[b0:b1])
+
     def _forward_cached(self, x, inference_params):
         """Prompt pass (offset 0): self-attention as usual, K/V stored.  Decode step (one new position, offset > 0):
         the new query against all offset + 1 cached keys, non-causal (mha.py:437-440)."""
@@ -175,7 +198,10 @@ class MHA(nn.Module):
         if inference_params is not None:
             if key_padding_mask is not None or cu_seqlens is not None or max_seqlen is not None:
                 raise RuntimeError("generation takes dense, unmasked batches (mha.py:409-412)")
-            context = self._forward_cached(x, inference_params)
+            if inference_params.cache_position is not None:
+                context = self._forward_cached_device_offsets(x, inference_params)
+            else:
+                context = self._forward_cached(x, inference_params)
         else:
             kw = ({"cu_seqlens": cu_seqlens, "max_seqlen": max_seqlen, **kwargs} if self.use_flash_attn
                   else {"key_padding_mask": key_padding_mask, **kwargs})
