@@ -195,23 +195,25 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const AttnParams p) {
 // ---------------------------------------------------------------------------------------------
 // A cluster of `nsplit` CTAs (1..8) per (batch element, column chunk of the output); CTA r takes the r-th slice of the
 // context.  A chunk is 8 * kLanes columns: kLanes = 32 (256 columns, a whole warp per table row) when the batch alone
-// fills the GPU, kLanes = 8 (64 columns) for small batches.
-//   scores   The K rows of a tile of keys, (key, sense)-major and contiguous in the cache, are read as one flat stream
-//            of 16-byte words: a warp covers floor(32 / (dk/8)) whole rows per load instruction (480 contiguous bytes
-//            for dk = 48), the dk/8 partial dot products of a row are summed with shuffles, and the score goes to
-//            shared memory, sc[sense][key].  q is staged in shared memory as fp32, pre-multiplied by scale * log2(e).
+// fills the GPU, kLanes = 8 (64 columns) for small batches.  The kernel is HBM-bound only if the inner loop stays under
+// ~25 instructions per 512-byte row segment, so everything that is per key or per row is computed once, up front:
+//   scores   The K rows of a sub-tile of keys, (key, sense)-major and contiguous in the cache, are read as one flat,
+//            fully coalesced stream of 16-byte words; word g multiplies the q words (g mod nv*dk/8) staged in shared
+//            memory as fp32 (pre-multiplied by scale * log2(e)) and leaves a partial dot product in shared memory; one
+//            thread per row then sums the dk/8 partials into sc[sense][key].
 //   pass A   per tile: scores, then the running max / sum of every sense (one warp per sense).  The CTAs of the
 //            cluster exchange their (max, sum) through DSMEM and merge them in rank order: exact softmax statistics.
 //   pass B   per tile: (scores again, unless the slice is a single tile and they are still in shared memory,)
-//            normalise in place, then acc += w[l][j] * table[ids[j], l, cols]: kLanes lanes read one row segment with
-//            16-byte loads, 256 / kLanes rows per step, 8 steps of loads issued before the first is consumed (32 KB in
-//            flight per CTA).
+//            normalise in place, per-key table offsets into shared memory, then acc += w[l][j] * table[ids[j], l, cols]:
+//            kLanes lanes read one row segment with 16-byte loads, 256 / kLanes rows per step, 8 steps of loads issued
+//            before the first is consumed (32 KB in flight per CTA).
 //   merge    the row slots through shared memory in a fixed order, the cluster by rank 0 in rank order: deterministic
 //            for a given launch configuration.
 // The scores are recomputed by each of the column-chunk clusters of a batch element (for kLanes = 32 and d = 768: 3x,
 // 96 bytes of K per 512 bytes of sense vector; the K rows come from L2).
 constexpr int kDecThreads = 256;
 constexpr int kMixUnroll = 8;
+constexpr int kSubKeys = 64;     // keys per score sub-tile (partial dot products: kSubKeys * nv * dk/8 floats)
 
 struct MixParams {
   const void* q;          // (batch, nv, dk) query of the new position
@@ -222,24 +224,30 @@ struct MixParams {
   const int32_t* lens;    // (batch) or null
   int64_t k_batch_stride, ids_batch_stride;
   int32_t batch, nv, dk, d, vocab, len, nsplit, tile;   // tile: keys per score tile in shared memory (multiple of 16)
+  int32_t nv_shift;       // log2(nv) when nv is a power of two (kPow2 kernels)
   float scale_log2;
 };
 
 __host__ __device__ inline size_t mix_smem_floats(int nv, int dk, int tile, int lanes) {
-  return static_cast<size_t>(nv) * dk + static_cast<size_t>(nv) * tile + 4 * nv + (kDecThreads / lanes) * (8 * lanes) + 8 * lanes;
+  const size_t partial = static_cast<size_t>(kSubKeys) * nv * (dk / 8);
+  const size_t merge = static_cast<size_t>(kDecThreads / lanes) * (8 * lanes) + 8 * lanes;
+  return static_cast<size_t>(nv) * dk + static_cast<size_t>(nv) * tile + tile + 4 * nv + (partial > merge ? partial : merge);
 }
 
-template <bool kBF16, int kLanes>
+template <bool kBF16, int kLanes, bool kPow2>
 __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const MixParams p) {
   constexpr int kCols = 8 * kLanes;                  // output columns per CTA
   constexpr int kRows = kDecThreads / kLanes;        // table rows in flight per step
   extern __shared__ float smem_f[];
   const int nv = p.nv, dk = p.dk, tile = p.tile;
-  float* qs = smem_f;                                // [nv][dk] q * scale * log2(e)
+  const int C = dk / 8;                              // 16-byte words per K row
+  float* qs = smem_f;                                // q * scale * log2(e): word i of q (8 values) as two float4, [2][nv * dk/8][4]
   float* sc = qs + nv * dk;                          // [nv][tile] scores, then normalised weights, of the current tile
-  float* stat = sc + nv * tile;                      // [nv][2] row max (log2 units) and 1 / row sum
+  uint32_t* keyoff = reinterpret_cast<uint32_t*>(sc + nv * tile);   // [tile] table offset of the key's token, 16-byte units
+  float* stat = reinterpret_cast<float*>(keyoff + tile);            // [nv][2] row max (log2 units) and 1 / row sum
   float* lstat = stat + 2 * nv;                      // [nv][2] this CTA's running max and sum (read by the peers)
-  float* part = lstat + 2 * nv;                      // [kRows][kCols] column partials
+  float* scratch = lstat + 2 * nv;                   // partial dot products of a sub-tile | column partials + column sums
+  float* part = scratch;                             // [kRows][kCols]
   float* colsum = part + kRows * kCols;              // [kCols] this CTA's column sums (read by rank 0)
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
@@ -249,43 +257,53 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
   const int per = ((len + p.nsplit - 1) / p.nsplit + 15) & ~15;
   const int j_begin = min(len, rank * per), j_end = min(len, j_begin + per);
   const uint16_t* kb = static_cast<const uint16_t*>(p.kcache) + b * p.k_batch_stride;
+  auto split_row = [&](int row, int& jj, int& l) {   // row = jj * nv + l
+    if constexpr (kPow2) {
+      jj = row >> p.nv_shift, l = row & (nv - 1);
+    } else {
+      jj = row / nv, l = row - jj * nv;
+    }
+  };
 
   {
     const uint16_t* qb = static_cast<const uint16_t*>(p.q) + static_cast<int64_t>(b) * nv * dk;
-    for (int i = tid; i < nv * dk / 8; i += kDecThreads) {
+    for (int i = tid; i < nv * C; i += kDecThreads) {
       float t[8];
       unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(qb) + i), t);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) qs[i * 8 + e] = t[e] * p.scale_log2;
+      for (int e = 0; e < 8; ++e) qs[(e >> 2) * nv * C * 4 + i * 4 + (e & 3)] = t[e] * p.scale_log2;   // conflict-free LDS.128
     }
     for (int i = tid; i < 2 * nv; i += kDecThreads) lstat[i] = (i & 1) ? 0.f : -INFINITY;
   }
   __syncthreads();
 
-  // scores of the keys [j0, j0 + nkeys) into sc[l * tile + jj]
-  const int C = dk / 8;                              // 16-byte words per K row
-  const int rpw = 32 / C;                            // whole rows per warp-wide load (dk <= 256)
-  const int my_r = lane / C, my_c = lane - my_r * C;
-  const bool my_on = my_r < rpw;
+  // scores of the keys [j0, j0 + nkeys) into sc[l * tile + jj]; ends with the CTA in sync
+  const int qwords = nv * C;                         // 16-byte words of q = words of one key's K rows
   auto compute_scores = [&](int j0, int nkeys) {
-    const int nrows = nkeys * nv;
-    const uint4* kt = reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j0) * nv * dk);
-    for (int row0 = warp * rpw; row0 < nrows; row0 += (kDecThreads / 32) * rpw) {
-      const int row = row0 + my_r;
-      const bool on = my_on && row < nrows;
-      float s = 0.f;
-      int jj = 0, l = 0;
-      if (on) {
-        jj = row / nv, l = row - jj * nv;
+    for (int s0 = 0; s0 < nkeys; s0 += kSubKeys) {
+      const int sk = min(kSubKeys, nkeys - s0);
+      const int nwords = sk * qwords;
+      const uint4* kt = reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j0 + s0) * nv * dk);
+      int qi = tid % qwords;
+      const int qstep = kDecThreads % qwords;
+      for (int g = tid; g < nwords; g += kDecThreads) {
         float k8[8];
-        unpack8<kBF16>(__ldg(kt + static_cast<int64_t>(row) * C + my_c), k8);
-        const float4 qa = *reinterpret_cast<const float4*>(qs + l * dk + my_c * 8);
-        const float4 qb4 = *reinterpret_cast<const float4*>(qs + l * dk + my_c * 8 + 4);
-        s = qa.x * k8[0] + qa.y * k8[1] + qa.z * k8[2] + qa.w * k8[3] + qb4.x * k8[4] + qb4.y * k8[5] + qb4.z * k8[6] + qb4.w * k8[7];
+        unpack8<kBF16>(__ldg(kt + g), k8);
+        const float4 qa = *reinterpret_cast<const float4*>(qs + qi * 4);
+        const float4 qc = *reinterpret_cast<const float4*>(qs + qwords * 4 + qi * 4);
+        scratch[g] = qa.x * k8[0] + qa.y * k8[1] + qa.z * k8[2] + qa.w * k8[3] + qc.x * k8[4] + qc.y * k8[5] + qc.z * k8[6] + qc.w * k8[7];
+        qi += qstep;
+        if (qi >= qwords) qi -= qwords;
       }
-      float tot = s;
-      for (int i = 1; i < C; ++i) tot += __shfl_down_sync(0xffffffffu, s, i);
-      if (on && my_c == 0) sc[l * tile + jj] = tot;
+      __syncthreads();
+      for (int row = tid; row < sk * nv; row += kDecThreads) {
+        float tot = 0.f;
+        for (int c = 0; c < C; ++c) tot += scratch[row * C + c];
+        int jj, l;
+        split_row(row, jj, l);
+        sc[l * tile + s0 + jj] = tot;
+      }
+      __syncthreads();
     }
   };
 
@@ -294,7 +312,6 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
   for (int j0 = j_begin; j0 < j_end; j0 += tile) {
     const int nkeys = min(tile, j_end - j0);
     compute_scores(j0, nkeys);
-    __syncthreads();
     for (int l = warp; l < nv; l += kDecThreads / 32) {
       float m = -INFINITY, sum = 0.f;
       for (int jj = lane; jj < nkeys; jj += 32) {
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
         sum = sum * fast_exp2(m - m_new) + fast_exp2(s - m_new);
         m = m_new;
       }
-      float m0 = lstat[2 * l], s0 = lstat[2 * l + 1];      // running value of the earlier tiles, merged first
+      const float m0 = lstat[2 * l], s0 = lstat[2 * l + 1];      // running value of the earlier tiles, merged last
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) {
         const float m2 = __shfl_xor_sync(0xffffffffu, m, off), s2 = __shfl_xor_sync(0xffffffffu, sum, off);
@@ -336,22 +353,23 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
   const int slot = tid % kLanes, rslot = tid / kLanes;
   const int col0 = chunk * kCols + slot * 8;
   const bool col_ok = col0 < p.d;                     // d is a multiple of 8
-  const uint16_t* tb = static_cast<const uint16_t*>(p.table) + (col_ok ? col0 : 0);
+  const uint4* tb = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.table) + (col_ok ? col0 : 0));
   const int64_t* ids = p.ids + b * p.ids_batch_stride;
+  const uint32_t row_words = static_cast<uint32_t>(p.d / 8);          // 16-byte words per table row
+  const uint32_t tok_words = row_words * static_cast<uint32_t>(nv);   // ... per token (host checks vocab * tok_words < 2^32)
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
   for (int j0 = j_begin; j0 < j_end; j0 += tile) {
     const int nkeys = min(tile, j_end - j0);
-    if (!single_tile) {
-      compute_scores(j0, nkeys);
-      __syncthreads();
-    }
+    if (!single_tile) compute_scores(j0, nkeys);
     for (int l = warp; l < nv; l += kDecThreads / 32) {   // normalise in place
       const float m = stat[2 * l], inv = stat[2 * l + 1];
       for (int jj = lane; jj < nkeys; jj += 32) sc[l * tile + jj] = fast_exp2(sc[l * tile + jj] - m) * inv;
     }
+    for (int jj = tid; jj < nkeys; jj += kDecThreads)
+      keyoff[jj] = static_cast<uint32_t>(min(max(static_cast<int>(__ldg(ids + j0 + jj)), 0), p.vocab - 1)) * tok_words;
     __syncthreads();
     // acc += w[l][j] * table[ids[j], l, cols]; pairs (j, l) are walked key-major: the nv rows of a token are contiguous
     const int npairs = nkeys * nv;
@@ -362,9 +380,9 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
       for (int u = 0; u < kMixUnroll; ++u) {
         const int pr = pr0 + u * kRows + rslot;
         const bool live = pr < npairs;
-        const int jj = live ? pr / nv : 0, l = live ? pr - jj * nv : 0;
-        const int id = min(max(static_cast<int>(__ldg(ids + j0 + jj)), 0), p.vocab - 1);
-        row[u] = __ldg(reinterpret_cast<const uint4*>(tb + (static_cast<int64_t>(id) * nv + l) * p.d));
+        int jj, l;
+        split_row(live ? pr : 0, jj, l);
+        row[u] = __ldg(tb + (keyoff[jj] + static_cast<uint32_t>(l) * row_words));
         w[u] = live ? sc[l * tile + jj] : 0.f;
       }
 #pragma unroll
@@ -402,6 +420,11 @@ __global__ void __launch_bounds__(kDecThreads) sense_mix_decode_kernel(const Mix
     }
   }
   if (p.nsplit > 1) cluster.sync();        // peers keep lstat / colsum alive until everyone has read them
+}
+
+template <bool kBF16, int kLanes>
+auto mix_kernel_for(bool pow2) {
+  return pow2 ? sense_mix_decode_kernel<kBF16, kLanes, true> : sense_mix_decode_kernel<kBF16, kLanes, false>;
 }
 
 // number of key slices (cluster size) that brings the grid to about two CTAs per SM without slices under `min_keys`
@@ -477,7 +500,8 @@ extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const
   p.k_batch_stride = k_batch_stride, p.ids_batch_stride = ids_batch_stride;
   p.batch = batch, p.nv = nv, p.dk = dk, p.d = d, p.vocab = vocab, p.len = seqlen;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  if (dk > 256) return fail(BP_ERR_UNSUPPORTED, "%s: dk must be at most 256 (got %d)", fn, dk);
+  if (static_cast<int64_t>(vocab) * nv * (d / 8) >= (int64_t{1} << 32))
+    return fail(BP_ERR_UNSUPPORTED, "%s: the table must be smaller than 64 GB (32-bit offsets in 16-byte units)", fn);
   // a whole warp per table row (256-column chunks) when the batch alone fills the SMs, 8 lanes (64 columns) otherwise
   const int lanes = static_cast<int64_t>(batch) * ((d + 255) / 256) >= 148 ? 32 : 8;
   const int cols = 8 * lanes, chunks = (d + cols - 1) / cols;
@@ -489,8 +513,11 @@ extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const
   const size_t smem = sizeof(float) * decode::mix_smem_floats(nv, dk, p.tile, lanes);
   if (smem > 200 * 1024) return fail(BP_ERR_UNSUPPORTED, "%s: too many senses (%d) for the score tile", fn, nv);
   const bool bf = dtype == BP_DTYPE_BF16;
-  auto kern = lanes == 32 ? (bf ? decode::sense_mix_decode_kernel<true, 32> : decode::sense_mix_decode_kernel<false, 32>)
-                          : (bf ? decode::sense_mix_decode_kernel<true, 8> : decode::sense_mix_decode_kernel<false, 8>);
+  const bool pow2 = (nv & (nv - 1)) == 0;
+  p.nv_shift = 0;
+  while (pow2 && (1 << p.nv_shift) < nv) ++p.nv_shift;
+  auto kern = lanes == 32 ? (bf ? decode::mix_kernel_for<true, 32>(pow2) : decode::mix_kernel_for<false, 32>(pow2))
+                          : (bf ? decode::mix_kernel_for<true, 8>(pow2) : decode::mix_kernel_for<false, 8>(pow2));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {

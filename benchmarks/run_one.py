@@ -1,6 +1,6 @@
 """Run ONE kernel of the library a few times at its BASELINE shape (for `ncu -k regex:...` captures and quick A/B timing).
 
-    python benchmarks/run_one.py fmha|fmha128|sense|sense_table|lse|gemm|ln [reps]
+    python benchmarks/run_one.py fmha|fmha128|sense|sense_table|lse|gemm|ln|dec_attn|dec_sense [reps]
 """
 import os
 import sys
@@ -30,6 +30,20 @@ elif which in ("sense", "sense_table", "lse"):
     else:
         content = torch.randn(b, s, nv, d, device="cuda").bfloat16().transpose(1, 2)
         run = lambda: sense_mix(qk, content)
+elif which == "dec_attn":
+    from backpacks_flash_attn_b200.ops.decode import decode_attention
+    b, s, h, d = 64, 1024, 12, 64
+    cache = torch.randn(b, s, 2, h, d, device="cuda").bfloat16()
+    q = torch.randn(b, 1, h, d, device="cuda").bfloat16()
+    run = lambda: decode_attention(q, cache, s)
+elif which == "dec_sense":
+    from backpacks_flash_attn_b200.ops.decode import sense_mix_decode
+    b, s, nv, d = 64, 1024, 16, 768
+    table = torch.randn(50264, nv, d, device="cuda").bfloat16()
+    kc = torch.randn(b, s, nv, d // nv, device="cuda").bfloat16()
+    ids = torch.randint(0, 50257, (b, s), device="cuda")
+    q = torch.randn(b, nv, d // nv, device="cuda").bfloat16()
+    run = lambda: sense_mix_decode(q, kc, ids, table, s)
 elif which == "gemm":
     from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_act
     x = torch.randn(65536, 768, device="cuda").bfloat16()
