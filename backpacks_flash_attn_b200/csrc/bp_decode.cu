@@ -502,10 +502,11 @@ extern "C" int bp_sense_mix_decode_fwd(const void* q, const void* k_cache, const
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   if (static_cast<int64_t>(vocab) * nv * (d / 8) >= (int64_t{1} << 32))
     return fail(BP_ERR_UNSUPPORTED, "%s: the table must be smaller than 64 GB (32-bit offsets in 16-byte units)", fn);
-  // a whole warp per table row (256-column chunks) when the batch alone fills the SMs, 8 lanes (64 columns) otherwise
-  const int lanes = static_cast<int64_t>(batch) * ((d + 255) / 256) >= 148 ? 32 : 8;
-  const int cols = 8 * lanes, chunks = (d + cols - 1) / cols;
+  // a whole warp per table row (256-column chunks) when batch x column chunks x key slices fill the SMs
+  // (counting the key slices a long context allows), 8 lanes (64 columns) otherwise
   const int len_hint = seqlens ? (1 << 20) : seqlen;
+  const int lanes = static_cast<int64_t>(batch) * ((d + 255) / 256) * std::min(8, std::max(1, len_hint / 128)) >= 148 ? 32 : 8;
+  const int cols = 8 * lanes, chunks = (d + cols - 1) / cols;
   p.nsplit = decode::pick_nsplit(static_cast<int64_t>(batch) * chunks, len_hint, 32);
   const int per = ((len_hint + p.nsplit - 1) / p.nsplit + 15) & ~15;
   const int tile_max = std::max(16, (64 * 1024 / (4 * nv)) & ~15);       // <= 64 KB of scores
