@@ -11,6 +11,8 @@
 //   (tcgen05.ld -> + bias -> tanh-GELU -> bf16/f16 -> swizzled smem -> TMA store, 64 columns at a time).
 //   Persistent grid = #SMs; tiles are walked n-fastest so the CTAs running together share rows of x
 //   while W stays L2-resident.
+#include <algorithm>
+
 #include "bp_common.cuh"
 #include "bp_host.h"
 
@@ -56,9 +58,10 @@ struct Params {
 
 // Tile order of the pair kernel.  Tiles are walked in groups of `group_n` n-tiles: inside a group n-fastest, then m,
 // then the next group.  The clusters that run together therefore share one 256-row block of x, and the group's slice of
-// W (group_n x 256 rows) stays in L2 across all m-blocks.  group_n = min(n_tiles, #clusters): for every layer of the
-// model that is all of W (the order is then plain n-fastest); for the LM head (197 n-tiles, W = 77 MB next to a 6.6 GB
-// stream of logits through L2) W is read from HBM once instead of being re-fetched for every block of rows.
+// W (group_n x 256 rows) stays in L2 across all m-blocks.  group_n = min(n_tiles, #clusters, what keeps the W slice
+// under ~32 MB): for most layers of the model that is all of W (the order is then plain n-fastest); for the LM head
+// (197 n-tiles, W = 77 MB next to a 6.6 GB stream of logits through L2) and the content model's 3072 -> 12288
+// projection (W = 75 MB) W is read from HBM about once instead of being re-fetched for every block of rows.
 __device__ __forceinline__ void tile_coords(const Params& p, int64_t tile, int& m_blk, int& n_blk) {
   const int64_t per_group = static_cast<int64_t>(p.group_n) * p.m_tiles;
   const int g = static_cast<int>(tile / per_group);
@@ -678,7 +681,23 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
     p.m_tiles = static_cast<int32_t>((m + 255) / 256);
     const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
     const int clusters = static_cast<int>(tiles < sms / 2 ? tiles : sms / 2);
-    p.group_n = p.n_tiles < clusters ? p.n_tiles : clusters;
+    {
+      // n-tiles per tile-order group: no more than run concurrently, and a W slice (group_n x 256 rows x k) that stays
+      // L2-resident next to the x blocks in flight.  Each half of the 126 MB L2 ends up holding its own copy of data
+      // every SM reads, so the budget is ~32 MB.  Without the cap the 3072 -> 12288 projection (W = 75 MB, 48 n-tiles)
+      // re-read W for every block of rows: 6.2 GB of DRAM reads against 0.48 GB algorithmic (ncu, profiles/).
+      const int64_t slice_bytes = int64_t{256} * k * 2;
+      const int cap = static_cast<int>(std::max<int64_t>(1, (int64_t{32} << 20) / slice_bytes));
+      const int wave = std::min(p.n_tiles, clusters);
+      if (cap >= wave) {
+        // group = one wave of clusters: every cluster keeps its n-tile across the m-blocks and a wave shares one x block
+        // (LM head: 0.54 GB of DRAM reads; a group of 66 instead of 74 n-tiles quadruples them)
+        p.group_n = wave;
+      } else {
+        const int groups = (p.n_tiles + cap - 1) / cap;
+        p.group_n = (p.n_tiles + groups - 1) / groups;    // equal-width groups
+      }
+    }
     // the W tile map of this variant has a 128-row box (each CTA loads half of the 256-wide tile) ...
     const uint32_t bb[2] = {BK, 128};
     if (int rc = encode_tensor_map(&tmB, dtype, 2, w, db, sb, bb, true)) return rc;

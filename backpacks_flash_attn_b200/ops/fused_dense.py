@@ -108,12 +108,14 @@ def _own_gemm_ok(x, weight, bias) -> bool:
 
 # Which GEMM serves the plain linears on the inference path: "own" (bp_linear_bias_act_fwd), "library" (F.linear ->
 # cuBLAS, what the reference calls), a per-shape choice {(n, k): "own" | "library"}, or "auto" (default):
-#   "auto" = own GEMM for k <= 1024 and 1024 <= n <= 4096 (Wqkv, the contextualisation Wqkv), library otherwise.
-# Measured on B200 with the whole Backpack-Small forward replayed as one CUDA graph (benchmarks/linear_policy_ab.py,
-# profiles/): per-kernel CUDA events make the own GEMM faster than cuBLAS at every shape but fc2 and the LM head
-# (Wqkv -12 %, content projection -8 %), yet the step runs under the 1000 W power cap and what counts is the step:
-# all-library 24.99 ms, all-own 25.71 ms, own for Wqkv only 24.83 ms (the only shape whose own GEMM makes the STEP
-# faster), own for the content projection only 25.24 ms.  set_linear_backend() overrides (tests, bench.py).
+#   "auto" = own GEMM for every linear with at least 512 rows and n <= 16384 -- all of the model but the tied LM head
+#   -- and the library for the LM head and for the skinny GEMMs of incremental decoding (a handful of rows against the
+#   whole weight matrix is a bandwidth-bound GEMV-like problem cuBLAS has split-K kernels for).
+# Measured on B200 (profiles/): the step runs under the 1000 W power cap, so what counts is throughput at that
+# operating point (benchmarks/gemm_sustained.py: own >= cuBLAS at every shape but fc2, -3 %) and, in the end, the
+# whole forward replayed as one CUDA graph (benchmarks/linear_policy_ab.py): all-library 24.9 ms; own for one shape
+# only: Wqkv 24.8, out_proj 25.0, fc2 25.0, contextualisation Wqkv 24.9, content projection 24.9, LM head 25.5.
+# set_linear_backend() overrides (tests, bench.py).
 _backend = "auto"
 _timing_hook = None      # bench.py: callable(tag, n, k) -> context manager bracketing the library GEMM with CUDA events
 
@@ -129,18 +131,18 @@ def get_linear_backend():
     return _backend
 
 
-def _choice(n: int, k: int) -> str:
+def _choice(n: int, k: int, m: int) -> str:
     if isinstance(_backend, dict):
         return _backend.get((n, k), "library")
     if _backend == "auto":
-        return "own" if (k <= 1024 and 1024 <= n <= 4096) else "library"
+        return "own" if (m >= 512 and n <= 16384) else "library"
     return _backend
 
 
 def linear(x, weight, bias=None):
     """x @ weight.T + bias: this library's GEMM on the inference path, F.linear otherwise (see the module docstring)."""
     n, k = weight.shape
-    if _choice(n, k) == "own" and _own_gemm_ok(x, weight, bias):
+    if _choice(n, k, x.numel() // max(k, 1)) == "own" and _own_gemm_ok(x, weight, bias):
         return linear_bias_act(x, weight, bias, "none")
     if _timing_hook is not None and x.is_cuda:
         with _timing_hook("F.linear", n, k):

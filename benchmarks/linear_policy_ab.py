@@ -26,6 +26,7 @@ shapes = {"Wqkv": (3 * d, d), "out_proj": (d, d), "fc2": (d, 4 * d), "ctx_Wqkv":
 policies = {"library": "library", "own": "own"}
 for name, key in shapes.items():
     policies["own_only_" + name] = {k: ("own" if k == key else "library") for k in shapes.values()}
+policies["auto"] = "auto"
 policies["library_again"] = "library"
 results = {}
 with torch.inference_mode():
