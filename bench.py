@@ -276,11 +276,33 @@ def run_ours(args):
         launches0 = _lib.total_launches()
         gemm_key = lambda a: (int(a[5]), int(a[6]), int(a[7]))          # (n, k, activation) of bp_linear_bias_act_fwd
         timers = {n: _lib.KernelTimer(n, gemm_key if n == "bp_linear_bias_act_fwd" else None) for n in OWN_ENTRY_POINTS}
+        from backpacks_flash_attn_b200.ops import fused_dense as FD
+        lib_events = {}
+
+        class _Bracket:
+            """CUDA events around an F.linear call (a GEMM the default policy leaves to cuBLAS: the tied LM head)."""
+
+            def __init__(self, tag, n, k):
+                self.key = (n, k)
+
+            def __enter__(self):
+                self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+            def __exit__(self, *exc):
+                self.b.record()
+                lib_events.setdefault(self.key, []).append((self.a, self.b))
+                return False
+
         for t in timers.values():
             t.__enter__()
+        FD._timing_hook = _Bracket
         dt_eager = timed_steps(lambda: model(ids_dev), K, parallel, dev)
+        FD._timing_hook = None
         for t in reversed(list(timers.values())):
             t.__exit__(None, None, None)
+        torch.cuda.synchronize()
+        default_lib_gemms = {k: (len(v) / K, sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in lib_events.items()}
         launches = _lib.total_launches() - launches0          # per K steps; a graph replay launches the same kernels
         per_kernel = {n: (len(t.events) / K, t.mean_ms()) for n, t in timers.items()}      # (launches per step, ms)
         gemm_by_shape = {k: (n / K, ms / max(n, 1)) for k, (n, ms) in timers["bp_linear_bias_act_fwd"].by_key().items()}
@@ -293,22 +315,7 @@ def run_ours(args):
         lib_linear = None
         policy_ms = {}
         if args.library_linears:
-            from backpacks_flash_attn_b200.ops import fused_dense as FD
             lib_events = {}
-
-            class _Bracket:
-                def __init__(self, tag, n, k):
-                    self.key = (n, k)
-
-                def __enter__(self):
-                    self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    self.a.record()
-
-                def __exit__(self, *exc):
-                    self.b.record()
-                    lib_events.setdefault(self.key, []).append((self.a, self.b))
-                    return False
-
             default_backend = FD.get_linear_backend()
             for pname, policy in (("library", "library"), ("own", "own"), ("auto", "auto")):
                 FD.set_linear_backend(policy)
@@ -469,6 +476,11 @@ def run_ours(args):
                              + "); embedding gathers / element-wise ATen kernels not counted",
         "own_kernel_share": own_ms / step_ms,
         "own_kernel_ms_per_step": own_ms,
+        "library_gemms": {f"n{n} k{k}": {"kernel": "cuBLAS via F.linear (default linear policy, ops/fused_dense.py: the tied "
+                                                   "LM head stays on the library)",
+                                          "launches_per_step": c, "ms_per_launch": ms, "ms_per_step": c * ms,
+                                          "frac": 2.0 * M * n * k / (ms * 1e-3) / 1e12 / peak_tf}
+                          for (n, k), (c, ms) in default_lib_gemms.items()},
         "roofline": roofline,
         "north_star": north_star,
         "kernels": kernels,
