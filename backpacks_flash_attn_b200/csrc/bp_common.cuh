@@ -86,13 +86,6 @@ __device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(c));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(acc0), "=f"(acc1) : "l"(d));
 }
-// three-input maximum (FMNMX3): the row max of a 128-key block costs 64 ALU instructions instead of 128
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
 // exp2 of a packed pair on the FMA pipe instead of the MUFU pipe (which bounds this kernel): round-to-nearest
 // range reduction through the 1.5*2^23 magic constant, degree-3 minimax polynomial for 2^f on [-0.5, 0.5]
 // (max relative error 7.5e-5, far below the bf16 rounding of P), exponent re-inserted with an integer add.

@@ -21,7 +21,7 @@
 //   * the kernel is bound by the MUFU ex2 pipe (16 exponentials per clock and SM against 128 x 128 scores per
 //     512 tensor-pipe cycles at head dim 64), so everything is arranged to keep that pipe busy: each SM
 //     sub-partition hosts exactly two softmax warps (one per query tile) whose exponential phases are long
-//     (a full 128-key row per thread) and whose other phases (TMEM load, 3-input row max, hand-overs) overlap the
+//     (a full 128-key row per thread) and whose other phases (TMEM load, row max, hand-overs) overlap the
 //     sibling tile's exponentials; the causal asymmetry of the two tiles keeps them out of phase.
 //   * S (M=128, N=BN) lands in TMEM; the softmax threads tcgen05.ld their row and hand the S buffer back at
 //     once (s_free), so S of the next key block is computed while this block's exponentials run; running
