@@ -1,14 +1,14 @@
 """Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`) per kernel: launches per step, ms per
 step, share of the step.  Kernels of libbackpack_b200.so are marked with *.
 
-    python profiles/summarize_launches.py gpurun_out/launches_r01.csv STEPS > profiles/r01_launch_list_summary.txt
+    python profiles/summarize_launches.py gpurun_out/launches_r02.csv STEPS > profiles/r02_launch_list_summary.txt
 """
 import csv
 import re
 import sys
 from collections import defaultdict
 
-OURS = ("fmha::", "sense::", "gemm::", "ln::", "rotary::")
+OURS = ("fmha::", "sense::", "gemm::", "ln::", "rotary::", "decode::")
 
 
 def main(path, steps):
@@ -32,8 +32,8 @@ def main(path, steps):
     fm = [k for k in cnt if "fmha_fwd_kernel" in k]
     if fm:   # 12 attention launches per forward pass: count the passes instead of trusting the argument
         steps = max(1, round(sum(cnt[k] for k in fm) / 12))
-    print(f"ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-sense-table` "
-          f"({steps} forward passes captured, eager and graph-replayed; per-launch times are cold-cache and serialised: compare SHARES)")
+    print(f"ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-sense-table --no-graph --no-library-linears --full-logits-steps 0` (profiles/collect.sh) "
+          f"({steps} forward passes captured; per-launch times are cold-cache and serialised: compare SHARES)")
     ours = 0.0
     for k in sorted(tot, key=lambda k: -tot[k])[:14]:
         mark = "*" if any(o in k for o in OURS) else " "
