@@ -1,10 +1,13 @@
 """Replay the forward pass as ONE CUDA graph.
 
-A Backpack-Small forward is ~130 kernel launches (56 of this library, the rest library GEMMs and gathers); every
-shape is static for a fixed (batch, seqlen), the library never allocates and never synchronises, and its only
-launch-time state (the attention scheduler's ticket counters) re-arms itself on the device, so the whole launch
-sequence can be captured once and replayed.  That removes the gaps between dependent launches (measured on B200:
-25.5 -> 25.0 ms per step).  The reference has no counterpart (its generation loop re-launches everything,
+A Backpack-Small forward is ~110 kernel launches (95 of this library, the LM-head GEMM, gathers and a few element-wise
+ATen kernels); every shape is static for a fixed (batch, seqlen), the library never allocates and never synchronises,
+and its only launch-time state -- the attention scheduler's ticket counter -- is PER LAUNCH: a slot of a device-side
+ring zeroed by a memset node in front of the kernel (csrc/bp_fmha_fwd.cu), so the whole launch sequence can be captured
+once and replayed, several graphs can replay concurrently on different streams next to eager launches, and a capture
+that would exhaust the slot pool fails with an error instead of sharing a counter.  Replaying removes the gaps between
+dependent launches (measured on B200: 25.5 -> 25.0 ms per step).  The decode step of utils/generation.py is captured
+the same way.  The reference has no counterpart (its generation loop re-launches everything,
 training/src/utils/generation.py:34-44); this is an opt-in serving helper, not a different compute path -- the
 same kernels run on the same buffers.
 
