@@ -372,6 +372,19 @@ def run_ours(args):
             model.transformer.use_sense_table = False
             model.transformer.drop_sense_table()
 
+        # ---- variant: evaluation (per-token cross-entropy) through the LM head with the softmax statistics in its
+        #      epilogue: the forward without the 6.6 GB of logits (bp_lm_head_stats_fwd) ----
+        fused_loss = None
+        if args.fused_loss_steps > 0:
+            labels = torch.randint(0, cfg.vocab_size - 7, (B, S), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+            loss_timer = _lib.KernelTimer("bp_lm_head_stats_fwd")
+            for _ in range(3):
+                model.loss(ids_dev, labels)
+            kk = min(K, args.fused_loss_steps)
+            with loss_timer:
+                fl_dt = timed_steps(lambda: model.loss(ids_dev, labels), kk, parallel, dev)
+            fused_loss = {"dt": fl_dt, "steps": kk, "stats_ms": loss_timer.mean_ms()}
+
     if rank != 0:
         return
     peaks = load_peaks()
@@ -516,6 +529,16 @@ def run_ours(args):
             "note": "serving_config(): identical logits; the content model (24 % of the model's FLOPs) runs once per "
                     "vocabulary item instead of once per token and bp_sense_mix_table_fwd gathers the rows inside the "
                     "kernel (no (b, s, nv, d) tensor in HBM).  Reported as a variant: `value` above is the full forward"}
+    if fused_loss is not None:
+        fl_ms = fused_loss["dt"] / fused_loss["steps"] * 1e3
+        line["variants"]["fused_loss"] = {
+            "value": B * S * world / (fl_ms * 1e-3), "unit": "tokens/s", "ms_per_step": fl_ms, "steps": fused_loss["steps"],
+            "lm_head_stats_ms": fused_loss["stats_ms"],
+            "lm_head_stats_frac_of_tensor_peak": 2.0 * M * cfg.vocab_size * d / (fused_loss["stats_ms"] * 1e-3) / 1e12 / peak_tf,
+            "note": "BackpackLMHeadModel.loss(ids, labels): the same forward with the tied LM head run by "
+                    "bp_lm_head_stats_fwd (log-sum-exp, arg-max and target logit per row in the GEMM epilogue; no "
+                    "(b, s, vocab) tensor), eager launches.  What perplexity evaluation needs; a different result than "
+                    "`value` (per-token loss instead of logits), hence a variant"}
     print(json.dumps(line), flush=True)
 
 
@@ -533,6 +556,8 @@ def main():
                     help="skip the serving-configuration variant")
     ap.add_argument("--no-library-linears", dest="library_linears", action="store_false",
                     help="skip the variant that runs the plain linears on cuBLAS")
+    ap.add_argument("--fused-loss-steps", type=int, default=30,
+                    help="steps of the evaluation-loss variant (0 = skip)")
     ap.add_argument("--full-logits-steps", type=int, default=3,
                     help="steps of the whole-logits-to-host loop (0 = skip; single GPU only)")
     args = ap.parse_args()

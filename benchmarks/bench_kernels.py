@@ -188,6 +188,19 @@ def bench_gemms(iters):
         print(json.dumps({"gemm": name, "m": m, "n": n, "k": k, "own_us": t_own * 1e6, "cublas_us": t_lib * 1e6,
                           "own_tflops": flops / t_own / 1e12, "cublas_tflops": flops / t_lib / 1e12,
                           "own_over_cublas_time": t_own / t_lib}), flush=True)
+        if "lm_head" in name:
+            # the LM head with the softmax statistics in the epilogue (no logits in HBM) next to what it replaces in
+            # evaluation: the GEMM above followed by a cross-entropy over the logits
+            from backpacks_flash_attn_b200.ops.lm_head import lm_head_stats
+            tgt = torch.randint(0, 50257, (m,), device="cuda")
+            t_stats, _ = time_fn(lambda i: lm_head_stats(x, w, tgt, n_valid=50257), 1, it, inner=4)
+            logits = torch.nn.functional.linear(x, w, bias)
+            t_ce, _ = time_fn(lambda i: torch.nn.functional.cross_entropy(logits, tgt, reduction="none"), 1, 4, inner=1)
+            print(json.dumps({"gemm": "lm_head + softmax statistics (bp_lm_head_stats_fwd: lse, argmax, target logit; no logits written)",
+                              "m": m, "n": n, "k": k, "own_us": t_stats * 1e6, "own_tflops": flops / t_stats / 1e12,
+                              "replaces_us": {"cublas_gemm": t_lib * 1e6, "torch_cross_entropy_on_bf16_logits": t_ce * 1e6},
+                              "own_over_replaced_time": t_stats / (t_lib + t_ce)}), flush=True)
+            del logits
         del x, w
 
 

@@ -32,7 +32,7 @@ def main(path, steps):
     fm = [k for k in cnt if "fmha_fwd_kernel" in k]
     if fm:   # 12 attention launches per forward pass: count the passes instead of trusting the argument
         steps = max(1, round(sum(cnt[k] for k in fm) / 12))
-    print(f"ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-sense-table --no-graph --no-library-linears --full-logits-steps 0` (profiles/collect.sh) "
+    print(f"ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-sense-table --no-graph --no-library-linears --full-logits-steps 0 --fused-loss-steps 0` (profiles/collect.sh) "
           f"({steps} forward passes captured; per-launch times are cold-cache and serialised: compare SHARES)")
     ours = 0.0
     for k in sorted(tot, key=lambda k: -tot[k])[:14]:
