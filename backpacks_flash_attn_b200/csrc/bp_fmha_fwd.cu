@@ -560,9 +560,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         }
-        // row max over the live chunks: eight independent chains of plain 2-input FMNMX.  (3-input FMNMX3 halves the
-        // instruction count but measured ~10 cycles per warp instruction on B200 against 2 for FMNMX: 64 of them cost
-        // ~650 cycles per block in the timeline trace.)
+        // row max over the live chunks: eight independent chains.  ptxas fuses the links into three-input FMNMX3 (66 per
+        // row); forcing two-input FMNMX (alternating NaN modes) measured 6 % slower at config 2: twice the instructions.
         float mx8[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) mx8[k] = -INFINITY;
