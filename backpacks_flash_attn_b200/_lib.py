@@ -26,6 +26,9 @@ SIGNATURES = {
     "bp_last_error": [],
     "bp_check_device": [],
     "bp_fmha_fwd": [c_void_p] * 7 + [c_int32] * 7 + [c_int64] * 8 + [c_int32, c_float, c_int32, c_int32, c_void_p],
+    "bp_fmha_bwd_workspace_bytes": [c_int32, c_int32, c_int32],
+    "bp_fmha_bwd": [c_void_p] * 11 + [c_int32] * 7 + [c_void_p, c_int32, c_float, c_int32, c_int32, c_void_p, c_int64,
+                                                       c_void_p],
     "bp_sense_lse_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p],
     "bp_sense_mix_fwd": [c_void_p] * 4 + [c_int32] * 5 + [c_int64] * 3 + [c_float, c_int32, c_void_p],
     "bp_sense_mix_table_fwd": [c_void_p] * 5 + [c_int32] * 6 + [c_float, c_int32, c_void_p],
@@ -38,7 +41,7 @@ SIGNATURES = {
     "bp_ln_fwd": [c_void_p] * 6 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_rotary_qk_inplace": [c_void_p] * 5 + [c_int32] * 6 + [c_void_p],
 }
-_RESTYPES = {"bp_last_error": c_char_p}
+_RESTYPES = {"bp_last_error": c_char_p, "bp_fmha_bwd_workspace_bytes": c_int64}
 
 _lib = None
 

@@ -1,0 +1,576 @@
+// FlashAttention backward for sm_100a: dQ, dK, dV of softmax(scale * Q K^T [+ causal mask]) V.
+//
+// Replaces the reference's FlashAttention-1 backward (csrc/flash_attn/fmha_api.cpp:338-500 mha_bwd ->
+// src/fmha_dgrad_kernel_1xN_loop.h), whose single kernel walks K/V blocks in the outer loop and accumulates dQ
+// through an fp32 `dq_tmp` round trip in HBM.  Written for Blackwell from scratch:
+//
+//   * three launches, all deterministic (no atomics, fixed accumulation order):
+//       1. bwd_stats_kernel: per query row {lse * log2(e), delta = sum_d dO * O} into a padded workspace
+//          (rows beyond a sequence get lse = +inf, so their probabilities are exactly 0);
+//       2. fmha_bwd_kernel<kDQ = false>: a CTA owns 128 KEYS of one (batch, head) and streams the query blocks
+//          that see them; dV and dK stay in TMEM for the whole sweep;
+//       3. fmha_bwd_kernel<kDQ = true>:  a CTA owns 128 QUERIES and streams the key blocks they see; dQ stays in TMEM.
+//     S and dP are recomputed in both kernels (7 tile products instead of 5) in exchange for no dQ read-modify-write
+//     traffic, no conversion pass and bit-wise reproducible gradients.
+//   * one kernel body for both modes.  With "stationary" tiles A1, A2 (128 rows) and "streaming" tiles B1, B2
+//     (64 rows per step):   T1 = A1 B1^T,  T2 = A2 B2^T   (SS tcgen05.mma, all operands K-major as TMA lands them)
+//         keys own   (A1, A2, B1, B2) = (K, V, Q, dO):  T1 = S^T, T2 = dP^T;  X1 = P^T, X2 = dS^T;
+//                                                        dV += X1 B2,  dK += X2 B1
+//         queries own (A1, A2, B1, B2) = (Q, dO, K, V): T1 = S,   T2 = dP;    X2 = dS;   dQ += X2 B1
+//     X1 / X2 are written back to TMEM as 16-bit pairs OVER the columns of T1 / T2 they were computed from (TMEM lanes
+//     are private to one thread, and tcgen05.mma of one thread execute in issue order, so the next step's T products
+//     overwrite them only after this step's gradient products have read them) and feed TS tcgen05.mma whose B
+//     operand is the SAME streaming tile consumed MN-major -- no transposes, nothing staged in shared memory.
+//   * 256 TMEM columns and ~85 KB of shared memory per CTA at head dim 64, so TWO CTAs share an SM: one CTA's
+//     exponentials overlap the other's tensor work without any software pipelining inside a CTA.
+//   * the softmax scale is applied once to the fp32 dK / dQ accumulators, not per element.
+//
+// Varlen through cu_seqlens as in the forward; head dims that are a multiple of 8 up to 128 (TMA zero-fill to 64 / 128).
+#include <cstddef>
+
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace fmha_bwd {
+
+constexpr int BS = 128;   // stationary rows per CTA (= TMEM lanes)
+constexpr int BT = 64;    // streaming rows per step
+constexpr float kLog2e = 1.4426950408889634f;
+#ifndef BP_FMHA_BWD_POLY
+#define BP_FMHA_BWD_POLY 2
+#endif
+constexpr int kPoly = BP_FMHA_BWD_POLY;   // of every 8 exponentials, how many run on the FMA pipe (see bp_common.cuh)
+
+template <int DP, bool kDQ>
+struct Cfg {
+  static constexpr int kThreads = 192;   // warps 0-3: softmax + epilogue (TMEM lane quadrant = warp), 4: TMA, 5: MMA
+  static constexpr int kStages = (DP == 64) ? 3 : 2;
+  static constexpr int kPanels = DP / 64;
+  static constexpr uint32_t kStatPanelBytes = BS * 128;
+  static constexpr uint32_t kStrPanelBytes = BT * 128;
+  static constexpr uint32_t kStatTileBytes = kPanels * kStatPanelBytes;
+  static constexpr uint32_t kStrTileBytes = kPanels * kStrPanelBytes;
+  static constexpr uint32_t kStatsBytes = BT * 8;   // {lse * log2e, delta} of the streaming rows (keys-own mode)
+  static constexpr uint32_t kStageBytes = 2 * kStrTileBytes + 1024;
+  static constexpr uint32_t offStat1 = 0;
+  static constexpr uint32_t offStat2 = kStatTileBytes;
+  static constexpr uint32_t offStr = 2 * kStatTileBytes;
+  static constexpr uint32_t offBar = offStr + kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+  static constexpr uint32_t colT1 = 0, colT2 = BT;
+  static constexpr uint32_t colA1 = 2 * BT;
+  static constexpr uint32_t colA2 = kDQ ? 2 * BT : 2 * BT + DP;
+  static constexpr uint32_t kColsUsed = colA2 + DP;
+  static constexpr uint32_t kTmemCols = kColsUsed <= 256 ? 256 : 512;
+  static constexpr int kCtasPerSm = (kTmemCols == 256 && kSmemBytes <= 113 * 1024) ? 2 : 1;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct Params {
+  const float2* stats;       // (batch * nheads, s_pad): {lse * log2e, delta}
+  void* out1;                // keys-own: dV
+  void* out2;                // keys-own: dK, queries-own: dQ (both scaled by the softmax scale)
+  int64_t o1_row_stride, o1_head_stride, o2_row_stride, o2_head_stride;
+  const int32_t* cu_q;
+  const int32_t* cu_k;
+  int32_t s_pad;
+  int32_t batch, nheads, headdim;
+  int32_t num_tiles;         // stationary tiles per sequence
+  int32_t chunk_bh;          // (batch, head) pairs per scheduling chunk
+  int32_t is_causal;
+  float scale, scale_log2;
+};
+
+struct Barriers {
+  uint64_t stat_full, t_full, x_ready, acc_full;
+  uint64_t str_full[3], str_empty[3];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Barriers) <= 256, "barrier block");
+#define BBAR(field) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)))
+#define BBAR_I(field, i) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)) + 8u * static_cast<uint32_t>(i))
+
+__device__ __forceinline__ void bulk_load_1d_w(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n"
+      ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch 1: per-row statistics
+// ------------------------------------------------------------------------------------------------------------------
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, const float* __restrict__ lse,
+                 float2* __restrict__ stats, const int32_t* __restrict__ cu_q, int64_t do_row, int64_t do_head,
+                 int64_t o_row, int64_t o_head, int32_t lse_stride, int32_t s_pad, int32_t nheads, int32_t headdim) {
+  // 16 lanes per query row (8 elements = 16 bytes each), 2 rows per warp, 16 rows per block
+  const int bh = blockIdx.x;
+  const int b = bh / nheads, h = bh - b * nheads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.y * 16 + warp * 2 + (lane >> 4);
+  const int q = lane & 15;
+  const int q_begin = __ldg(cu_q + b);
+  const int len_q = __ldg(cu_q + b + 1) - q_begin;
+  const bool valid = i < len_q;
+  float acc = 0.f;
+  if (valid && q * 8 < headdim) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(
+        reinterpret_cast<const uint16_t*>(dout) + static_cast<int64_t>(q_begin + i) * do_row + h * do_head + q * 8));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(
+        reinterpret_cast<const uint16_t*>(out) + static_cast<int64_t>(q_begin + i) * o_row + h * o_head + q * 8));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 fa, fc;
+      if constexpr (kBF16) {
+        fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[k]));
+        fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cw[k]));
+      } else {
+        fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
+        fc = __half22float2(*reinterpret_cast<const __half2*>(&cw[k]));
+      }
+      acc = fmaf(fa.x, fc.x, acc);
+      acc = fmaf(fa.y, fc.y, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (q == 0 && i < s_pad) {
+    float2 st;
+    st.x = valid ? __ldg(lse + static_cast<int64_t>(bh) * lse_stride + i) * kLog2e : INFINITY;
+    st.y = valid ? acc : 0.f;
+    stats[static_cast<int64_t>(bh) * s_pad + i] = st;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launches 2 and 3
+// ------------------------------------------------------------------------------------------------------------------
+template <int DP, bool kDQ, bool kBF16>
+__global__ void __launch_bounds__(Cfg<DP, kDQ>::kThreads, Cfg<DP, kDQ>::kCtasPerSm)
+fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_constant__ CUtensorMap tmStat2,
+                const __grid_constant__ CUtensorMap tmStr1, const __grid_constant__ CUtensorMap tmStr2, const Params p) {
+  using C = Cfg<DP, kDQ>;
+  // ---- which tile ----
+  const int total_bh = p.batch * p.nheads;
+  const int per_chunk = p.chunk_bh * p.num_tiles;
+  const int ch = blockIdx.x / per_chunk;
+  const int rr = blockIdx.x - ch * per_chunk;
+  const int bh0 = ch * p.chunk_bh;
+  const int gc = min(p.chunk_bh, total_bh - bh0);
+  const int rank = rr / gc;   // heaviest tiles of a chunk first
+  if (rank >= p.num_tiles) return;
+  const int bh = bh0 + (rr - rank * gc);
+  const int batch = bh / p.nheads, head = bh - batch * p.nheads;
+  const int tile = (kDQ && p.is_causal) ? p.num_tiles - 1 - rank : rank;
+  const int row0 = tile * BS;
+  const int q_begin = __ldg(p.cu_q + batch), len_q = __ldg(p.cu_q + batch + 1) - q_begin;
+  const int k_begin = __ldg(p.cu_k + batch), len_k = __ldg(p.cu_k + batch + 1) - k_begin;
+  const int stat_begin = kDQ ? q_begin : k_begin, len_stat = kDQ ? len_q : len_k;
+  const int str_begin = kDQ ? k_begin : q_begin, len_str = kDQ ? len_k : len_q;
+  if (row0 >= len_stat) return;
+  const int nblk = (len_str + BT - 1) / BT;
+  int first = 0, last = nblk;
+  if (p.is_causal) {
+    if (kDQ) last = min(nblk, (row0 + BS) / BT);   // keys <= last query of the tile
+    else first = row0 / BT;                        // queries >= first key of the tile
+  }
+  const int n_steps = max(0, last - first);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars_a = smem_a + C::offBar;
+  uint8_t* smem = smem_raw + (smem_a - smem_u32(smem_raw));
+  Barriers& bars = *reinterpret_cast<Barriers*>(smem + C::offBar);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmStat1);
+    tma_prefetch_desc(&tmStat2);
+    tma_prefetch_desc(&tmStr1);
+    tma_prefetch_desc(&tmStr2);
+    mbar_init(&bars.stat_full, 1);
+    mbar_init(&bars.t_full, 1);
+    mbar_init(&bars.x_ready, 128);
+    mbar_init(&bars.acc_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars.str_full[i], 1);
+      mbar_init(&bars.str_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&bars.tmem_base, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars.tmem_base;
+
+  if (warp == 4) {
+    // ===================== TMA producer (whole warp walks the loop, an elected lane issues) =====================
+    if (n_steps > 0) {
+      mbar_arrive_expect_tx_w(BBAR(stat_full), 2 * C::kStatTileBytes);
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int pn = 0; pn < C::kPanels; ++pn) {
+          const uint32_t off = pn * C::kStatPanelBytes + half * (BT * 128);
+          tma_load_3d_w(smem_a + C::offStat1 + off, &tmStat1, BBAR(stat_full), pn * 64, head, stat_begin + row0 + half * BT);
+          tma_load_3d_w(smem_a + C::offStat2 + off, &tmStat2, BBAR(stat_full), pn * 64, head, stat_begin + row0 + half * BT);
+        }
+    }
+    uint32_t slot = 0, ph = 1;   // ph: parity of the str_empty phase to wait for (first pass: the slots are free)
+    for (int n = 0; n < n_steps; ++n) {
+      if (n >= C::kStages) mbar_wait_a(BBAR_I(str_empty, slot), ph);
+      const uint32_t st = smem_a + C::offStr + slot * C::kStageBytes;
+      const int srow = str_begin + (first + n) * BT;
+      mbar_arrive_expect_tx_w(BBAR_I(str_full, slot), 2 * C::kStrTileBytes + (kDQ ? 0u : C::kStatsBytes));
+#pragma unroll
+      for (int pn = 0; pn < C::kPanels; ++pn) {
+        tma_load_3d_w(st + pn * C::kStrPanelBytes, &tmStr1, BBAR_I(str_full, slot), pn * 64, head, srow);
+        tma_load_3d_w(st + C::kStrTileBytes + pn * C::kStrPanelBytes, &tmStr2, BBAR_I(str_full, slot), pn * 64, head, srow);
+      }
+      if constexpr (!kDQ)
+        bulk_load_1d_w(st + 2 * C::kStrTileBytes, p.stats + static_cast<int64_t>(bh) * p.s_pad + (first + n) * BT,
+                       C::kStatsBytes, BBAR_I(str_full, slot));
+      if (++slot == C::kStages) {
+        slot = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_t = make_idesc(kBF16, BS, BT, false, false);
+    constexpr uint32_t idesc_acc = make_idesc(kBF16, BS, DP, false, true);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tT1 = tm + C::colT1, tT2 = tm + C::colT2, tA1 = tm + C::colA1, tA2 = tm + C::colA2;
+    const uint32_t sA1 = smem_a + C::offStat1, sA2 = smem_a + C::offStat2;
+    if (n_steps > 0) mbar_wait_a(BBAR(stat_full), 0);
+    uint32_t slot = 0, ph = 0;
+    for (int n = 0; n < n_steps; ++n) {
+      const uint32_t sB1 = smem_a + C::offStr + slot * C::kStageBytes;
+      const uint32_t sB2 = sB1 + C::kStrTileBytes;
+      mbar_wait_a(BBAR_I(str_full, slot), ph);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < DP / 16; ++kk) {
+        const uint32_t a = sA1 + (kk >> 2) * C::kStatPanelBytes + (kk & 3) * 32;
+        const uint32_t b = sB1 + (kk >> 2) * C::kStrPanelBytes + (kk & 3) * 32;
+        umma_ss_w(tT1, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_t, kk > 0 ? 1u : 0u);
+      }
+#pragma unroll
+      for (int kk = 0; kk < DP / 16; ++kk) {
+        const uint32_t a = sA2 + (kk >> 2) * C::kStatPanelBytes + (kk & 3) * 32;
+        const uint32_t b = sB2 + (kk >> 2) * C::kStrPanelBytes + (kk & 3) * 32;
+        umma_ss_w(tT2, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_t, kk > 0 ? 1u : 0u);
+      }
+      umma_commit_w(BBAR(t_full));
+      mbar_wait_a(BBAR(x_ready), n & 1);
+      tc_fence_after();
+      // gradient products: A = X from TMEM (8 columns per K-step of 16 streaming rows), B = the streaming tile MN-major
+      if constexpr (!kDQ) {
+#pragma unroll
+        for (int kk = 0; kk < BT / 16; ++kk)
+          umma_ts_w(tA1, tT1 + kk * 8, make_smem_desc_sw128(sB2 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
+                    (n > 0 || kk > 0) ? 1u : 0u);
+      }
+#pragma unroll
+      for (int kk = 0; kk < BT / 16; ++kk)
+        umma_ts_w(tA2, tT2 + kk * 8, make_smem_desc_sw128(sB1 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
+                  (n > 0 || kk > 0) ? 1u : 0u);
+      umma_commit_w(BBAR_I(str_empty, slot));
+      if (++slot == C::kStages) {
+        slot = 0;
+        ph ^= 1;
+      }
+    }
+    if (n_steps > 0) umma_commit_w(BBAR(acc_full));
+  } else {
+    // ===================== softmax / gradient warps: one thread per stationary row =====================
+    const int r = warp * 32 + lane;
+    const int row = row0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t tT1 = tmem_base + lane_addr + C::colT1, tT2 = tmem_base + lane_addr + C::colT2;
+    const float c2 = p.scale_log2;
+    float rowL = 0.f, rowD = 0.f;
+    if constexpr (kDQ) {
+      const float2 st = __ldg(p.stats + static_cast<int64_t>(bh) * p.s_pad + row);
+      rowL = st.x;
+      rowD = st.y;
+    }
+    uint32_t slot = 0, ph = 0;
+    for (int n = 0; n < n_steps; ++n) {
+      const int col0 = (first + n) * BT;
+      const uint32_t sStats = smem_a + C::offStr + slot * C::kStageBytes + 2 * C::kStrTileBytes;
+      if constexpr (!kDQ) mbar_wait_a(BBAR_I(str_full, slot), ph);   // the statistics travel with the streaming tiles
+      mbar_wait_a(BBAR(t_full), n & 1);
+      tc_fence_after();
+      // valid columns of this row inside the block: lo <= c < hi
+      int lo = 0, hi = len_str - col0;
+      bool partial = col0 + BT > len_str;
+      if (p.is_causal) {
+        if (kDQ) {
+          hi = min(hi, row + 1 - col0);
+          partial = partial || (col0 + BT - 1 > row0);
+        } else {
+          lo = row - col0;
+          partial = partial || (col0 < row0 + BS - 1);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < BT / 32; ++c) {
+        uint32_t us[32], ud[32];
+        tmem_ld32(tT1 + c * 32, us);
+        tmem_ld32(tT2 + c * 32, ud);
+        tmem_ld_wait();
+        float e[32], g[32];
+        if constexpr (kDQ) {
+          const float negL = -rowL;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float t8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t8[k] = __uint_as_float(us[i + k]);
+            float e8[8];
+            exp2_scaled8<kPoly>(e8, t8, c2, negL);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              e[i + k] = e8[k];
+              g[i + k] = e8[k] * (__uint_as_float(ud[i + k]) - rowD);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint4 st = lds128(sStats + (c * 32 + i) * 8);   // {L, delta} of two query columns (broadcast)
+            float a0 = fmaf(__uint_as_float(us[i]), c2, -__uint_as_float(st.x));
+            float a1 = fmaf(__uint_as_float(us[i + 1]), c2, -__uint_as_float(st.z));
+            if ((i & 7) < 8 - kPoly) {
+              a0 = fast_exp2(a0);
+              a1 = fast_exp2(a1);
+            } else {
+              exp2_poly_pair(a0, a1);
+            }
+            e[i] = a0;
+            e[i + 1] = a1;
+            g[i] = a0 * (__uint_as_float(ud[i]) - __uint_as_float(st.y));
+            g[i + 1] = a1 * (__uint_as_float(ud[i + 1]) - __uint_as_float(st.w));
+          }
+        }
+        if (partial) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = (c * 32 + i >= lo) && (c * 32 + i < hi);
+            e[i] = ok ? e[i] : 0.f;
+            g[i] = ok ? g[i] : 0.f;
+          }
+        }
+        uint32_t pk[16];
+        if constexpr (!kDQ) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
+          tmem_st16(tT1 + c * 16, pk);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(g[2 * i], g[2 * i + 1]);
+        tmem_st16(tT2 + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_a(BBAR(x_ready));
+      if (++slot == C::kStages) {
+        slot = 0;
+        ph ^= 1;
+      }
+    }
+
+    // ---- epilogue: accumulators -> global (one thread per row, 16-byte stores) ----
+    if (n_steps > 0) {
+      mbar_wait_a(BBAR(acc_full), 0);
+      tc_fence_after();
+    }
+    const bool valid = row < len_stat;
+    auto store_acc = [&](uint32_t col, void* out, int64_t row_stride, int64_t head_stride, float mult) {
+      uint8_t* orow = reinterpret_cast<uint8_t*>(out) +
+                      2 * (static_cast<int64_t>(stat_begin + row) * row_stride + head * head_stride);
+#pragma unroll
+      for (int c = 0; c < DP / 32; ++c) {
+        uint32_t o[32];
+        if (n_steps > 0) {
+          tmem_ld32(tmem_base + lane_addr + col + c * 32, o);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c * 32 + q * 8 < p.headdim) {
+              uint4 v;
+              v.x = pack2<kBF16>(__uint_as_float(o[q * 8 + 0]) * mult, __uint_as_float(o[q * 8 + 1]) * mult);
+              v.y = pack2<kBF16>(__uint_as_float(o[q * 8 + 2]) * mult, __uint_as_float(o[q * 8 + 3]) * mult);
+              v.z = pack2<kBF16>(__uint_as_float(o[q * 8 + 4]) * mult, __uint_as_float(o[q * 8 + 5]) * mult);
+              v.w = pack2<kBF16>(__uint_as_float(o[q * 8 + 6]) * mult, __uint_as_float(o[q * 8 + 7]) * mult);
+              *reinterpret_cast<uint4*>(orow + (c * 32 + q * 8) * 2) = v;
+            }
+          }
+        }
+      }
+    };
+    if constexpr (!kDQ) store_acc(C::colA1, p.out1, p.o1_row_stride, p.o1_head_stride, 1.f);
+    store_acc(C::colA2, p.out2, p.o2_row_stride, p.o2_head_stride, p.scale);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int DP, bool kDQ, bool kBF16>
+int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, const CUtensorMap& b2, const Params& p,
+           cudaStream_t stream) {
+  using C = Cfg<DP, kDQ>;
+  auto kern = fmha_bwd_kernel<DP, kDQ, kBF16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_fmha_bwd: cudaFuncSetAttribute(%u B smem): %s", C::kSmemBytes, cudaGetErrorString(e));
+  }
+  const int total_bh = p.batch * p.nheads;
+  const int chunks = (total_bh + p.chunk_bh - 1) / p.chunk_bh;
+  const int64_t grid = static_cast<int64_t>(chunks) * p.chunk_bh * p.num_tiles;
+  if (grid > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: too many work items");
+  kern<<<static_cast<unsigned>(grid), C::kThreads, C::kSmemBytes, stream>>>(s1, s2, b1, b2, p);
+  return check_launch(kDQ ? "bp_fmha_bwd (dQ) launch" : "bp_fmha_bwd (dK, dV) launch");
+}
+
+}  // namespace fmha_bwd
+}  // namespace bp
+
+extern "C" int64_t bp_fmha_bwd_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q) {
+  if (batch <= 0 || nheads <= 0 || max_seqlen_q <= 0) return 0;
+  const int64_t s_pad = (static_cast<int64_t>(max_seqlen_q) + 127) / 128 * 128;
+  return static_cast<int64_t>(batch) * nheads * s_pad * 8;
+}
+
+extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out,
+                           const float* softmax_lse, void* dq, void* dk, void* dv, const int32_t* cu_seqlens_q,
+                           const int32_t* cu_seqlens_k, int32_t batch, int32_t nheads, int32_t headdim, int32_t total_q,
+                           int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k, const int64_t* strides,
+                           int32_t lse_stride, float softmax_scale, int32_t is_causal, int32_t dtype, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  using namespace bp;
+  if (!dout || !q || !k || !v || !out || !softmax_lse || !dq || !dk || !dv || !cu_seqlens_q || !cu_seqlens_k || !strides)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: null pointer argument");
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: only fp16 and bf16 are supported (dtype=%d)", dtype);
+  if (batch <= 0 || nheads <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: batch and nheads must be positive");
+  if (headdim <= 0 || headdim % 8 != 0 || headdim > 128)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: head dim must be a multiple of 8 and <= 128 (got %d)", headdim);
+  if (total_q <= 0 || total_k <= 0 || max_seqlen_q <= 0 || max_seqlen_k <= 0)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: empty input (total_q=%d total_k=%d)", total_q, total_k);
+  if (lse_stride < max_seqlen_q)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: lse_stride %d < max_seqlen_q %d", lse_stride, max_seqlen_q);
+  for (int i = 0; i < 16; ++i)
+    if (strides[i] <= 0 || strides[i] % 8 != 0)
+      return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: row/head strides must be positive multiples of 8 elements (got %lld)",
+                  (long long)strides[i]);
+  const uintptr_t ptrs[] = {(uintptr_t)dout, (uintptr_t)q, (uintptr_t)k, (uintptr_t)v, (uintptr_t)out,
+                            (uintptr_t)dq,   (uintptr_t)dk, (uintptr_t)dv, (uintptr_t)workspace};
+  for (uintptr_t a : ptrs)
+    if (a % 16 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: tensors and workspace must be 16-byte aligned");
+  const int64_t need = bp_fmha_bwd_workspace_bytes(batch, nheads, max_seqlen_q);
+  if (!workspace || workspace_bytes < need)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: workspace of %lld bytes needed (got %lld)", (long long)need,
+                (long long)workspace_bytes);
+  // strides: {row, head} of dout, q, k, v, out, dq, dk, dv
+  const int64_t *s_do = strides, *s_q = strides + 2, *s_k = strides + 4, *s_v = strides + 6, *s_o = strides + 8,
+                *s_dq = strides + 10, *s_dk = strides + 12, *s_dv = strides + 14;
+  const int DP = headdim <= 64 ? 64 : 128;
+  const int s_pad = (max_seqlen_q + 127) / 128 * 128;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf16 = dtype == BP_DTYPE_BF16;
+  float2* stats = static_cast<float2*>(workspace);
+
+  {
+    dim3 grid(batch * nheads, (s_pad + 15) / 16);
+    if (bf16)
+      fmha_bwd::bwd_stats_kernel<true><<<grid, 256, 0, st>>>(dout, out, softmax_lse, stats, cu_seqlens_q, s_do[0], s_do[1],
+                                                             s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim);
+    else
+      fmha_bwd::bwd_stats_kernel<false><<<grid, 256, 0, st>>>(dout, out, softmax_lse, stats, cu_seqlens_q, s_do[0], s_do[1],
+                                                              s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim);
+    if (int rc = check_launch("bp_fmha_bwd (row statistics) launch")) return rc;
+  }
+
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  {
+    const uint32_t box[3] = {64, 1, (uint32_t)fmha_bwd::BT};
+    const uint64_t dq_[3] = {(uint64_t)headdim, (uint64_t)nheads, (uint64_t)total_q};
+    const uint64_t dk_[3] = {(uint64_t)headdim, (uint64_t)nheads, (uint64_t)total_k};
+    const uint64_t sq[2] = {(uint64_t)s_q[1] * 2, (uint64_t)s_q[0] * 2};
+    const uint64_t sk[2] = {(uint64_t)s_k[1] * 2, (uint64_t)s_k[0] * 2};
+    const uint64_t sv[2] = {(uint64_t)s_v[1] * 2, (uint64_t)s_v[0] * 2};
+    const uint64_t sdo[2] = {(uint64_t)s_do[1] * 2, (uint64_t)s_do[0] * 2};
+    if (int rc = encode_tensor_map(&tmQ, dtype, 3, q, dq_, sq, box, true)) return rc;
+    if (int rc = encode_tensor_map(&tmK, dtype, 3, k, dk_, sk, box, true)) return rc;
+    if (int rc = encode_tensor_map(&tmV, dtype, 3, v, dk_, sv, box, true)) return rc;
+    if (int rc = encode_tensor_map(&tmDO, dtype, 3, dout, dq_, sdo, box, true)) return rc;
+  }
+  fmha_bwd::Params p;
+  p.stats = stats;
+  p.cu_q = cu_seqlens_q;
+  p.cu_k = cu_seqlens_k;
+  p.s_pad = s_pad;
+  p.batch = batch;
+  p.nheads = nheads;
+  p.headdim = headdim;
+  p.is_causal = is_causal ? 1 : 0;
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * fmha_bwd::kLog2e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  // keys own: dK, dV
+  p.num_tiles = (max_seqlen_k + fmha_bwd::BS - 1) / fmha_bwd::BS;
+  p.chunk_bh = (2 * sms) / p.num_tiles > 0 ? (2 * sms) / p.num_tiles : 1;
+  p.out1 = dv;
+  p.o1_row_stride = s_dv[0];
+  p.o1_head_stride = s_dv[1];
+  p.out2 = dk;
+  p.o2_row_stride = s_dk[0];
+  p.o2_head_stride = s_dk[1];
+  int rc;
+  if (DP == 64)
+    rc = bf16 ? fmha_bwd::launch<64, false, true>(tmK, tmV, tmQ, tmDO, p, st)
+              : fmha_bwd::launch<64, false, false>(tmK, tmV, tmQ, tmDO, p, st);
+  else
+    rc = bf16 ? fmha_bwd::launch<128, false, true>(tmK, tmV, tmQ, tmDO, p, st)
+              : fmha_bwd::launch<128, false, false>(tmK, tmV, tmQ, tmDO, p, st);
+  if (rc) return rc;
+
+  // queries own: dQ
+  p.num_tiles = (max_seqlen_q + fmha_bwd::BS - 1) / fmha_bwd::BS;
+  p.chunk_bh = (2 * sms) / p.num_tiles > 0 ? (2 * sms) / p.num_tiles : 1;
+  p.out1 = nullptr;
+  p.out2 = dq;
+  p.o2_row_stride = s_dq[0];
+  p.o2_head_stride = s_dq[1];
+  if (DP == 64)
+    rc = bf16 ? fmha_bwd::launch<64, true, true>(tmQ, tmDO, tmK, tmV, p, st)
+              : fmha_bwd::launch<64, true, false>(tmQ, tmDO, tmK, tmV, p, st);
+  else
+    rc = bf16 ? fmha_bwd::launch<128, true, true>(tmQ, tmDO, tmK, tmV, p, st)
+              : fmha_bwd::launch<128, true, false>(tmQ, tmDO, tmK, tmV, p, st);
+  return rc;
+}

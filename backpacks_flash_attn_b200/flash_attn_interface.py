@@ -1,8 +1,9 @@
-"""FlashAttention forward operators with the reference's Python signatures
-(flash_attn/flash_attn_interface.py:242-380), backed by bp_fmha_fwd instead of flash_attn_cuda.fwd.
+"""FlashAttention operators with the reference's Python signatures (flash_attn/flash_attn_interface.py:242-380),
+backed by bp_fmha_fwd / bp_fmha_bwd instead of flash_attn_cuda.fwd / .bwd.
 
-Forward / inference only: dropout must be 0 and tensors must not require grad (the reference's autograd
-backward, flash_attn_interface.py:31-47, is out of scope for this path).
+Differentiable like the reference's autograd functions (flash_attn_interface.py:50-240): when an input requires
+grad the call goes through `_AttnFn`, whose backward is bp_fmha_bwd (deterministic).  Dropout must be 0: the
+attention-probability dropout of the reference's training configs is not implemented.
 """
 from __future__ import annotations
 
@@ -16,8 +17,6 @@ def _check_common(dropout_p, return_attn_probs, *tensors):
         raise RuntimeError("bp_fmha_fwd is the inference path: dropout_p must be 0.0")
     if return_attn_probs:
         raise RuntimeError("return_attn_probs is not supported (the S matrix is never materialised)")
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
 
 
 def _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
@@ -68,6 +67,89 @@ def _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, 
     return out, lse
 
 
+def _flash_attn_backward(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens_q, cu_seqlens_k,
+                         max_seqlen_q, max_seqlen_k, softmax_scale, causal):
+    """Gradients of _flash_attn_forward into the caller-allocated dq, dk, dv (strided views of a packed gradient are
+    written in place, as flash_attn_interface.py:77-83 does).  Mirrors flash_attn_interface.py:31-47; returns
+    (dq, dk, dv)."""
+    _lib.require_cuda(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens_q, cu_seqlens_k)
+    if dout.stride(-1) != 1:
+        dout = dout.contiguous()
+    if q.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("FlashAttention only support fp16 and bf16 data type")
+    if any(t.dtype != q.dtype for t in (dout, k, v, out, dq, dk, dv)) or softmax_lse.dtype != torch.float32:
+        raise RuntimeError("dout, q, k, v, out, dq, dk, dv must share a 16-bit dtype and softmax_lse must be fp32")
+    for t in (dout, q, k, v, out, dq, dk, dv):
+        if t.dim() != 3 or t.stride(-1) != 1:
+            raise RuntimeError("tensors must be (total, nheads, headdim) with contiguous last dimension")
+    total_q, nheads, d = q.shape
+    total_k = k.shape[0]
+    if (dout.shape != q.shape or out.shape != q.shape or dq.shape != q.shape or k.shape != (total_k, nheads, d)
+            or v.shape != k.shape or dk.shape != k.shape or dv.shape != k.shape):
+        raise RuntimeError("shape mismatch between q/k/v/out/dout and their gradients")
+    batch = cu_seqlens_q.numel() - 1
+    if softmax_lse.dim() != 3 or softmax_lse.shape[:2] != (batch, nheads) or not softmax_lse.is_contiguous():
+        raise RuntimeError("softmax_lse must be the contiguous (batch, nheads, lse_stride) tensor of the forward")
+    lib = _lib.load()
+    ws_bytes = lib.bp_fmha_bwd_workspace_bytes(batch, nheads, max_seqlen_q)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    import ctypes
+    strides = (ctypes.c_int64 * 16)(*[x for t in (dout, q, k, v, out, dq, dk, dv) for x in (t.stride(0), t.stride(1))])
+    with torch.cuda.device(q.device):
+        st = lib.bp_fmha_bwd(
+            dout.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), softmax_lse.data_ptr(),
+            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr(),
+            batch, nheads, d, total_q, total_k, max_seqlen_q, max_seqlen_k, ctypes.addressof(strides),
+            softmax_lse.shape[2], float(softmax_scale), int(bool(causal)), _lib.dtype_code(q.dtype),
+            workspace.data_ptr(), ws_bytes, _lib.stream_ptr(q.device))
+    _lib.check(st, "bp_fmha_bwd")
+    return dq, dk, dv
+
+
+class _AttnFn(torch.autograd.Function):
+    """One autograd node for the three packings of the reference (FlashAttnQKVPackedFunc / FlashAttnKVPackedFunc /
+    FlashAttnFunc, flash_attn_interface.py:50-240).  `packing` = "qkv" (a = qkv), "kv" (a = q, b = kv) or "none"
+    (a, b, c = q, k, v); the gradient of a packed input is allocated once and filled through strided views."""
+
+    @staticmethod
+    def forward(ctx, packing, a, b, c, cu_q, cu_k, max_q, max_k, softmax_scale, causal):
+        if packing == "qkv":
+            q, k, v = a[:, 0], a[:, 1], a[:, 2]
+        elif packing == "kv":
+            q, k, v = a, b[:, 0], b[:, 1]
+        else:
+            q, k, v = a, b, c
+        out, lse = _flash_attn_forward(q, k, v, torch.empty_like(q), cu_q, cu_k, max_q, max_k, softmax_scale, causal)
+        saved = {"qkv": (a,), "kv": (a, b)}.get(packing, (a, b, c))
+        ctx.save_for_backward(*saved, out, lse, cu_q, cu_k)
+        ctx.packing, ctx.max_q, ctx.max_k, ctx.softmax_scale, ctx.causal = packing, max_q, max_k, softmax_scale, causal
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        *inputs, out, lse, cu_q, cu_k = ctx.saved_tensors
+        if ctx.packing == "qkv":
+            qkv, = inputs
+            dqkv = torch.empty_like(qkv)
+            q, k, v, grads = qkv[:, 0], qkv[:, 1], qkv[:, 2], (dqkv, None, None)
+            dq, dk, dv = dqkv[:, 0], dqkv[:, 1], dqkv[:, 2]
+        elif ctx.packing == "kv":
+            q, kv = inputs
+            dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+            k, v, dk, dv, grads = kv[:, 0], kv[:, 1], dkv[:, 0], dkv[:, 1], (dq, dkv, None)
+        else:
+            q, k, v = inputs
+            dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+            grads = (dq, dk, dv)
+        _flash_attn_backward(dout, q, k, v, out, lse, dq, dk, dv, cu_q, cu_k, ctx.max_q, ctx.max_k,
+                             ctx.softmax_scale, ctx.causal)
+        return (None, *grads, None, None, None, None, None, None)
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 def flash_attn_unpadded_qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p, softmax_scale=None,
                                        causal=False, return_attn_probs=False):
     """qkv: (total, 3, nheads, headdim); cu_seqlens: (batch+1,) int32.  Returns (total, nheads, headdim).
@@ -75,6 +157,9 @@ def flash_attn_unpadded_qkvpacked_func(qkv, cu_seqlens, max_seqlen, dropout_p, s
     _check_common(dropout_p, return_attn_probs, qkv)
     if softmax_scale is None:
         softmax_scale = qkv.shape[-1] ** (-0.5)
+    if _needs_grad(qkv):
+        return _AttnFn.apply("qkv", qkv, None, None, cu_seqlens, cu_seqlens, max_seqlen, max_seqlen, softmax_scale,
+                             causal)
     out = torch.empty_like(qkv[:, 0])
     _flash_attn_forward(qkv[:, 0], qkv[:, 1], qkv[:, 2], out, cu_seqlens, cu_seqlens, max_seqlen, max_seqlen,
                         softmax_scale, causal)
@@ -87,6 +172,9 @@ def flash_attn_unpadded_kvpacked_func(q, kv, cu_seqlens_q, cu_seqlens_k, max_seq
     _check_common(dropout_p, return_attn_probs, q, kv)
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** (-0.5)
+    if _needs_grad(q, kv):
+        return _AttnFn.apply("kv", q, kv, None, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale,
+                             causal)
     out = torch.empty_like(q)
     _flash_attn_forward(q, kv[:, 0], kv[:, 1], out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
                         softmax_scale, causal)
@@ -99,6 +187,9 @@ def flash_attn_unpadded_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, 
     _check_common(dropout_p, return_attn_probs, q, k, v)
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** (-0.5)
+    if _needs_grad(q, k, v):
+        return _AttnFn.apply("none", q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale,
+                             causal)
     out = torch.empty_like(q)
     _flash_attn_forward(q, k, v, out, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
                         softmax_scale, causal)

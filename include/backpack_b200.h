@@ -71,6 +71,26 @@ int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* s
                 int32_t lse_stride, float softmax_scale, int32_t is_causal,
                 int32_t dtype /* bp_dtype_t */, void* stream);
 
+/* FlashAttention backward (replaces mha_bwd, csrc/flash_attn/fmha_api.cpp:338-500, as driven by
+ * _flash_attn_backward, flash_attn/flash_attn_interface.py:31-47).  SURVEY.md section 8f rank 4.
+ *   dout, q, out, dq : (total_q, nheads, headdim);  k, v, dk, dv : (total_k, nheads, headdim); last-dim stride 1.
+ *   softmax_lse      : what bp_fmha_fwd returned.  No dropout.  dq / dk / dv are overwritten (not accumulated into);
+ *                      the result is bit-wise reproducible (no atomics; the reference's determinism contract,
+ *                      tests/test_flash_attn.py:727-793).
+ *   strides          : HOST array of 16 element strides: {row, head} of dout, q, k, v, out, dq, dk, dv.
+ *   workspace        : device scratch of at least bp_fmha_bwd_workspace_bytes(batch, nheads, max_seqlen_q) bytes,
+ *                      16-byte aligned (per-row {lse, sum_d dout*out}; the reference returns the latter as softmax_d).
+ * Three kernel launches on `stream`: row statistics, (dK, dV), dQ.
+ */
+int64_t bp_fmha_bwd_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q);
+int bp_fmha_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out,
+                const float* softmax_lse, void* dq, void* dk, void* dv,
+                const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                int32_t batch, int32_t nheads, int32_t headdim,
+                int32_t total_q, int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                const int64_t* strides, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                int32_t dtype /* bp_dtype_t */, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Backpack sense-mix, pass 1: per-sense causal softmax statistics.
  *   qk  : (batch, seqlen, 2, nv, dk) contiguous -- the output of ContextSelfAttn.Wqkv reshaped as
  *         training/src/models/backpack.py:111-116 (q = [:, :, 0], k = [:, :, 1]).
