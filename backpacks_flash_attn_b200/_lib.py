@@ -39,9 +39,14 @@ SIGNATURES = {
     "bp_sense_mix_decode_fwd": [c_void_p] * 6 + [c_int32] * 6 + [c_int64] * 2 + [c_float, c_int32, c_void_p],
     "bp_linear_bias_residual_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_ln_fwd": [c_void_p] * 6 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
+    "bp_ln_bwd_workspace_bytes": [c_int32],
+    "bp_ln_residual_bwd": [c_void_p] * 9 + [c_int64, c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
+    "bp_bias_act_bwd_workspace_bytes": [c_int32],
+    "bp_bias_act_bwd": [c_void_p] * 5 + [c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_rotary_qk_inplace": [c_void_p] * 5 + [c_int32] * 6 + [c_void_p],
 }
-_RESTYPES = {"bp_last_error": c_char_p, "bp_fmha_bwd_workspace_bytes": c_int64}
+_RESTYPES = {"bp_last_error": c_char_p, "bp_fmha_bwd_workspace_bytes": c_int64,
+             "bp_ln_bwd_workspace_bytes": c_int64, "bp_bias_act_bwd_workspace_bytes": c_int64}
 
 _lib = None
 

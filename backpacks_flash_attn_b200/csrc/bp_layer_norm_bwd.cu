@@ -83,22 +83,29 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // X: dtype of dz / dx0; R: dtype of the saved sum x, of dx_residual and of dx1; W: dtype of gamma.
 template <typename X, typename R, typename W, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, NV <= 3 ? 2 : 1)
 ln_residual_bwd_kernel(const X* __restrict__ dz, const R* __restrict__ dxres, const R* __restrict__ x,
                        const W* __restrict__ gamma, X* __restrict__ dx0, R* __restrict__ dx1,
                        float* __restrict__ part /* [gridDim.x][2][cols] */, int64_t rows, int cols, float eps) {
-  extern __shared__ float lnb_smem[];   // [kWarpsPerCta][cols] reduction buffer (reused for dgamma, then dbeta)
+  extern __shared__ float lnb_smem[];   // [kWarpsPerCta][cols] reduction buffer (dgamma, then dbeta), then [cols] gamma
+  float* s_gamma = lnb_smem + kWarpsPerCta * cols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + warp;
   const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kWarpsPerCta;
   const float inv_cols = 1.f / static_cast<float>(cols);
 
-  float g[NV][8], dg[NV][8], db[NV][8];
+  // gamma lives in shared memory as fp32 (keeping it in registers next to the row, dz and the two column
+  // accumulators spills at hidden size 768)
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float t[8];
+    V8<W>::load(gamma + v * 8, t);
+    V8<float>::store(s_gamma + v * 8, t);
+  }
+  __syncthreads();
+  float dg[NV][8], db[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int v = i * 32 + lane;
-    if (v < nvec) V8<W>::load(gamma + v * 8, g[i]);
 #pragma unroll
     for (int k = 0; k < 8; ++k) dg[i][k] = db[i][k] = 0.f;
   }
@@ -134,13 +141,15 @@ ln_residual_bwd_kernel(const X* __restrict__ dz, const R* __restrict__ dxres, co
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (i * 32 + lane < nvec) {
+        float g[8];
+        V8<float>::load(s_gamma + (i * 32 + lane) * 8, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float y = (xv[i][k] - mu) * rs;
           const float d = dzv[i][k];
           dg[i][k] += d * y;
           db[i][k] += d;
-          const float dy = d * g[i][k];
+          const float dy = d * g[k];
           xv[i][k] = y;
           dzv[i][k] = dy;
           s1 += dy;
@@ -227,7 +236,7 @@ int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamm
   int64_t cap = static_cast<int64_t>(sms) * 2;
   if (cap > kMaxCtas) cap = kMaxCtas;
   const int grid = static_cast<int>(ctas_needed < cap ? ctas_needed : cap);
-  const size_t smem = static_cast<size_t>(kWarpsPerCta) * cols * sizeof(float);
+  const size_t smem = static_cast<size_t>(kWarpsPerCta + 1) * cols * sizeof(float);
   auto kern = ln_residual_bwd_kernel<X, R, W, NV>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -1,5 +1,5 @@
 """`FusedDense` / `FusedDenseGeluDense` with the reference's interface (flash_attn/ops/fused_dense.py:116-129,
-357-402), forward only.
+357-402), differentiable like FusedDenseFunc / FusedDenseGeluDenseFunc (fused_dense.py:39-80, 179-300).
 
 * `FusedDense.forward` is a GEMM + bias (F.linear in the reference, fused_dense.py:52,112).  On the inference
   path (CUDA, fp16/bf16, no autograd) `linear()` picks between this library's tcgen05 GEMM
@@ -41,8 +41,9 @@ def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
     if x.shape[-1] != k:
         raise RuntimeError("shape mismatch between x and weight")
     bias = _dense_bias(bias, n)
-    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
-        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
+                                    or (bias is not None and bias.requires_grad)):
+        return _LinearBiasActFn.apply(x, weight, bias, activation)
     x2 = x.reshape(-1, k)
     if not x2.is_contiguous():
         x2 = x2.contiguous()
@@ -55,6 +56,76 @@ def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
                                                 _lib.stream_ptr(x.device))
     _lib.check(st, "bp_linear_bias_act_fwd")
     return out.reshape(*x.shape[:-1], n)
+
+
+def bias_act_backward(dact: torch.Tensor, pre: torch.Tensor | None, activation: str, want_dbias: bool):
+    """The epilogue half of the dense backward (bp_bias_act_bwd): returns (dpre, dbias) for "gelu_tanh"
+    (dpre = dact * gelu'(pre)) or (dact, dbias) for "none"; dbias = column sums, None unless wanted."""
+    _lib.require_cuda(dact, pre)
+    n = dact.shape[-1]
+    d2 = dact.reshape(-1, n)
+    if not d2.is_contiguous():
+        d2 = d2.contiguous()
+    gelu = activation == "gelu_tanh"
+    if not gelu and not want_dbias:
+        return dact, None
+    p2 = dpre = None
+    if gelu:
+        p2 = pre.reshape(-1, n)
+        if not p2.is_contiguous():
+            p2 = p2.contiguous()
+        dpre = torch.empty_like(d2)
+    dbias = torch.empty(n, dtype=dact.dtype, device=dact.device) if want_dbias else None
+    lib = _lib.load()
+    ws_bytes = lib.bp_bias_act_bwd_workspace_bytes(n) if want_dbias else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dact.device) if want_dbias else None
+    with torch.cuda.device(dact.device):
+        st = lib.bp_bias_act_bwd(d2.data_ptr(), _lib.ptr(p2), _lib.ptr(dpre), _lib.ptr(dbias), _lib.ptr(ws), ws_bytes,
+                                 d2.shape[0], n, _lib.BP_ACT_GELU_TANH if gelu else _lib.BP_ACT_NONE,
+                                 _lib.dtype_code(dact.dtype), _lib.stream_ptr(dact.device))
+    _lib.check(st, "bp_bias_act_bwd")
+    return (dpre.reshape(dact.shape) if gelu else dact), dbias
+
+
+def _dgrad(dy2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dX = dY W for W in nn.Linear layout (n, k): this library's GEMM on a transposed copy of the (small) weight when
+    the shape is one it takes, cuBLAS otherwise (the reference's backward GEMMs are all cuBLASLt)."""
+    n, k = weight.shape
+    if _choice(k, n, dy2.shape[0]) == "own" and n % 8 == 0 and k % 8 == 0 and dy2.shape[0] >= 512:
+        with torch.no_grad():
+            return linear_bias_act(dy2, weight.t().contiguous(), None, "none")
+    return dy2 @ weight
+
+
+class _LinearBiasActFn(torch.autograd.Function):
+    """act(x W^T + b) with this library's forward GEMM (FusedDenseFunc, fused_dense.py:39-80, and the fc1 half of
+    FusedDenseGeluDenseFunc, :179-300).  Backward: the pre-activation is recomputed by one more GEMM (the
+    reference's checkpoint_lvl = 2 behaviour, fused_dense.py:262-266) because the fused forward kernel never writes
+    it; dgelu + bias gradient are one pass of bp_bias_act_bwd; dgrad on this library's GEMM, wgrad on cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, activation):
+        with torch.no_grad():
+            out = linear_bias_act(x, weight, bias, activation)
+        ctx.save_for_backward(x, weight, bias)
+        ctx.activation = activation
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, bias = ctx.saved_tensors
+        n, k = weight.shape
+        x2 = x.reshape(-1, k)
+        d2 = dout.reshape(-1, n)
+        want_db = bias is not None and ctx.needs_input_grad[2]
+        pre = None
+        if ctx.activation == "gelu_tanh":
+            with torch.no_grad():
+                pre = linear_bias_act(x2, weight, bias, "none")
+        dpre, dbias = bias_act_backward(d2, pre, ctx.activation, want_db)
+        dx = _dgrad(dpre, weight).reshape(x.shape) if ctx.needs_input_grad[0] else None
+        dw = dpre.t() @ x2 if ctx.needs_input_grad[1] else None
+        return dx, dw, dbias, None
 
 
 def linear_bias_residual_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
@@ -95,15 +166,12 @@ def can_fuse_residual(x: torch.Tensor, weight: torch.Tensor, residual: torch.Ten
 
 
 def _own_gemm_ok(x, weight, bias) -> bool:
-    """Inference-path conditions of bp_linear_bias_act_fwd; anything else is the reference's F.linear."""
+    """Conditions of bp_linear_bias_act_fwd; anything else is the reference's F.linear."""
     if not (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype):
         return False
     if bias is not None and (bias.dtype != x.dtype or bias.shape != (weight.shape[0],)):
         return False
-    if weight.shape[0] % 8 or weight.shape[1] % 8 or x.numel() == 0:
-        return False
-    return not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
-                                             or (bias is not None and bias.requires_grad)))
+    return not (weight.shape[0] % 8 or weight.shape[1] % 8 or x.numel() == 0)
 
 
 # Which GEMM serves the plain linears on the inference path: "own" (bp_linear_bias_act_fwd), "library" (F.linear ->

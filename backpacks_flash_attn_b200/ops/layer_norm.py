@@ -1,5 +1,6 @@
-"""`dropout_add_layer_norm` with the reference's signature (flash_attn/ops/layer_norm.py:207-252),
-running bp_ln_residual_fwd.  Inference path: dropout_p must be 0 and rowscale / layerscale are rejected."""
+"""`dropout_add_layer_norm` with the reference's signature (flash_attn/ops/layer_norm.py:207-252), running
+bp_ln_residual_fwd, and differentiable through bp_ln_residual_bwd like the reference's DropoutAddLayerNormFn
+(layer_norm.py:104-160).  dropout_p must be 0 and rowscale / layerscale are rejected."""
 from __future__ import annotations
 
 import torch
@@ -65,16 +66,60 @@ def layer_norm_from_residual(x, weight, bias, epsilon):
     return z
 
 
+class _DropoutAddLayerNormFn(torch.autograd.Function):
+    """The autograd node of DropoutAddLayerNormFn (layer_norm.py:104-160) for dropout 0.  The forward keeps the
+    pre-norm sum x (the residual stream it writes anyway) and gamma; mu / rsigma are recomputed in the backward."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, gamma, beta, epsilon, residual_in_fp32, prenorm):
+        z, x = _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, True)
+        ctx.save_for_backward(x, gamma)
+        ctx.has_x1, ctx.prenorm, ctx.epsilon, ctx.x0_dtype = x1 is not None, prenorm, float(epsilon), x0.dtype
+        ctx.set_materialize_grads(False)
+        if not prenorm:
+            return z
+        # when no separate residual stream was written x is x0 itself; hand back a distinct tensor object
+        return z, (x if x is not x0 else x0.view_as(x0))
+
+    @staticmethod
+    def backward(ctx, dz, dx=None):
+        x, gamma = ctx.saved_tensors
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        if dz is None:
+            dz = torch.zeros(x.shape, dtype=ctx.x0_dtype, device=x.device)
+        dz = dz.contiguous()
+        if dx is not None:
+            dx = dx.contiguous()
+            if dx.dtype != x.dtype:
+                dx = dx.to(x.dtype)
+        dx0 = torch.empty(x.shape, dtype=ctx.x0_dtype, device=x.device)
+        dx1 = torch.empty_like(x) if ctx.has_x1 else None
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        lib = _lib.load()
+        ws_bytes = lib.bp_ln_bwd_workspace_bytes(cols)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            st = lib.bp_ln_residual_bwd(
+                dz.data_ptr(), _lib.ptr(dx), x.data_ptr(), gamma.data_ptr(), dx0.data_ptr(), _lib.ptr(dx1),
+                dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws_bytes, rows, cols, ctx.epsilon,
+                _lib.dtype_code(ctx.x0_dtype), _lib.dtype_code(x.dtype), _lib.dtype_code(gamma.dtype),
+                _lib.stream_ptr(x.device))
+        _lib.check(st, "bp_ln_residual_bwd")
+        return dx0, dx1, dgamma, dbeta, None, None, None
+
+
 def dropout_add_layer_norm(x0, x1, weight, bias, dropout_p, epsilon, rowscale=None, layerscale=None,
                            prenorm=False, residual_in_fp32=False, return_dropout_mask=False):
     """z = LayerNorm(x0 + x1) (and the fp32/16-bit residual x0 + x1 when prenorm=True).
     residual_in_fp32 only matters when x1 is None (layer_norm.py:209-212)."""
     if dropout_p != 0.0:
-        raise RuntimeError("inference path: dropout_p must be 0.0")
+        raise RuntimeError("dropout inside the fused LayerNorm is not implemented: dropout_p must be 0.0")
     if rowscale is not None or layerscale is not None or return_dropout_mask:
         raise RuntimeError("rowscale / layerscale / dropout mask are training-only features (out of scope)")
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x0, x1, weight, bias)):
-        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
+        return _DropoutAddLayerNormFn.apply(x0, x1, weight.contiguous(), bias.contiguous(), epsilon, residual_in_fp32,
+                                            prenorm)
     z, res = _ln_residual_forward(x0, x1, weight, bias, epsilon, residual_in_fp32, prenorm)
     return (z, res) if prenorm else z
 

@@ -8,6 +8,11 @@ materialised.  `content` may be ANY (b, nv, s, d) tensor with unit last stride -
 transposed view the reference's content model returns (backpack.py:276) and the edited sense tensors
 the intervention wrappers build (training/src/models/intervened_models.py:78-101).
 
+Training: `sense_mix` is differentiable.  The forward is the fused kernel (alpha is neither materialised nor kept for
+the backward -- 2.15 GB at Backpack-Small, batch 64); the backward recomputes alpha for a few batch elements at a time
+with the reference's own eager composition under autograd (the reference trains through exactly that composition,
+backpack.py:116-122, 313), so its tensor work runs on cuBLAS: a hand-written sense-mix backward kernel is not built.
+
 `sense_mix_table` is the inference form: the sense vectors are gathered inside the kernel from a precomputed
 (vocab, nv, d) table by token id (C_l(x) is context-free, backpack.py:258), so no (b, s, nv, d) tensor exists.
 """
@@ -23,8 +28,6 @@ def _prepare_qk(qk: torch.Tensor, softmax_scale):
         raise RuntimeError("qk must be (batch, seqlen, 2, nv, dk)")
     if qk.dtype not in (torch.float16, torch.bfloat16):
         raise RuntimeError("sense_mix needs fp16/bf16 qk and content of the same dtype")
-    if torch.is_grad_enabled() and qk.requires_grad:
-        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
     dk = qk.shape[-1]
     if softmax_scale is None:
         softmax_scale = dk ** -0.5
@@ -58,19 +61,64 @@ class _F32Out:
         return False
 
 
+def _sense_mix_eager(qk, content, scale):
+    """The reference's composition (backpack.py:116-122, 313) in the tensors' own dtype."""
+    s = qk.shape[1]
+    q, k = qk.unbind(dim=2)
+    scores = torch.einsum("bthd,bshd->bhts", q, k * scale)
+    mask = torch.triu(torch.full((s, s), -10000.0, device=scores.device), 1)
+    alpha = torch.softmax(scores + mask.to(scores.dtype), dim=-1, dtype=q.dtype)
+    return torch.sum(alpha @ content, dim=1)
+
+
+class _SenseMixFn(torch.autograd.Function):
+    """Fused forward; backward by recomputation of the eager composition, a few batch elements at a time."""
+    chunk_bytes = 1 << 30   # bound on the recomputed alpha (and its autograd copies) per chunk
+
+    @staticmethod
+    def forward(ctx, qk, content, scale):
+        ctx.save_for_backward(qk, content)
+        ctx.scale = scale
+        with torch.no_grad():
+            return sense_mix(qk, content, softmax_scale=scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        qk, content = ctx.saved_tensors
+        b, s, _, nv, _ = qk.shape
+        step = max(1, _SenseMixFn.chunk_bytes // (4 * nv * s * s * qk.element_size()))
+        dqk = torch.empty_like(qk) if ctx.needs_input_grad[0] else None
+        dcontent = torch.empty(content.shape, dtype=content.dtype, device=content.device) if ctx.needs_input_grad[1] else None
+        for i in range(0, b, step):
+            with torch.enable_grad():
+                q_ = qk[i:i + step].detach().requires_grad_(dqk is not None)
+                c_ = content[i:i + step].detach().requires_grad_(dcontent is not None)
+                o = _sense_mix_eager(q_, c_, ctx.scale)
+                wanted = [t for t, g in ((q_, dqk), (c_, dcontent)) if g is not None]
+                grads = list(torch.autograd.grad(o, wanted, dout[i:i + step]))
+            if dqk is not None:
+                dqk[i:i + step] = grads.pop(0)
+            if dcontent is not None:
+                dcontent[i:i + step] = grads.pop(0)
+        return dqk, dcontent, None
+
+
 def sense_mix(qk: torch.Tensor, content: torch.Tensor, softmax_scale: float | None = None,
               return_lse: bool = False, out_fp32: bool = False):
     """qk: (batch, seqlen, 2, nv, dk) -- ContextSelfAttn.Wqkv output viewed as at backpack.py:112-116;
     content: (batch, nv, seqlen, d).  Returns (batch, seqlen, d) [and lse (batch, nv, seqlen) fp32]."""
     _lib.require_cuda(qk, content)
+    if torch.is_grad_enabled() and (qk.requires_grad or content.requires_grad):
+        if return_lse or out_fp32:
+            raise RuntimeError("return_lse / out_fp32 are inference-only options")
+        scale = float(softmax_scale) if softmax_scale is not None else qk.shape[-1] ** -0.5
+        return _SenseMixFn.apply(qk, content, scale)
     qk, scale = _prepare_qk(qk, softmax_scale)
     if content.dtype != qk.dtype:
         raise RuntimeError("sense_mix needs fp16/bf16 qk and content of the same dtype")
     b, s, _, nv, dk = qk.shape
     if content.dim() != 4 or content.shape[:3] != (b, nv, s):
         raise RuntimeError(f"content must be (batch, nv, seqlen, d) = ({b}, {nv}, {s}, d), got {tuple(content.shape)}")
-    if torch.is_grad_enabled() and content.requires_grad:
-        raise RuntimeError("backward is not implemented; call under torch.no_grad()/inference_mode()")
     d = content.shape[3]
     if content.stride(3) != 1 or any(st % 8 for st in content.stride()[:3]) or content.data_ptr() % 16:
         content = content.contiguous()

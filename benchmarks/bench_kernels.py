@@ -104,6 +104,85 @@ def fmha_comparators(iters, qkvs, b, s, h, d, flops, nbytes):
         print(json.dumps({"kernel": "(comparator) site-packages flash_attn", "unavailable": str(e)[:200]}))
 
 
+def bench_fmha_bwd(iters, b=32, s=1024, h=12, d=64, comparators=True):
+    """bp_fmha_bwd (three launches) at BASELINE config 2.  FLOPs by the usual convention: 2.5 x the forward
+    (five tile products against two); bytes: q, k, v, o, dO read and dq, dk, dv written once."""
+    from backpacks_flash_attn_b200.flash_attn_interface import _flash_attn_backward, _flash_attn_forward
+    nvar = 3
+    cu = torch.arange(0, (b + 1) * s, s, dtype=torch.int32, device="cuda")
+    sets = []
+    for _ in range(nvar):
+        qkv = torch.randn(b * s, 3, h, d, device="cuda").bfloat16()
+        out, lse = _flash_attn_forward(qkv[:, 0], qkv[:, 1], qkv[:, 2], torch.empty_like(qkv[:, 0]), cu, cu, s, s,
+                                       d ** -0.5, True)
+        sets.append((qkv, out, lse, torch.randn_like(out), torch.empty_like(qkv)))
+
+    def fn(i):
+        qkv, out, lse, g, dqkv = sets[i]
+        _flash_attn_backward(g, qkv[:, 0], qkv[:, 1], qkv[:, 2], out, lse, dqkv[:, 0], dqkv[:, 1], dqkv[:, 2], cu, cu,
+                             s, s, d ** -0.5, True)
+    t_med, t_min = time_fn(fn, nvar, iters)
+    flops = 2.5 * 4 * b * h * s * s * d / 2
+    nbytes = 8 * b * s * h * d * 2 + 4 * b * h * s
+    rec = report(f"fmha_bwd (stats + dKdV + dQ) b{b} h{h} s{s} d{d} causal bf16", t_med, t_min, flops, nbytes)
+    if comparators:
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        for name, backend in (("torch SDPA backward, cuDNN backend", SDPBackend.CUDNN_ATTENTION),
+                              ("torch SDPA backward, flash backend", SDPBackend.FLASH_ATTENTION)):
+            try:
+                graphs = []
+                for qkv, _, _, g, _ in sets:
+                    v = qkv.view(b, s, 3, h, d).permute(2, 0, 3, 1, 4).detach().requires_grad_(True)
+                    with sdpa_kernel(backend):
+                        o = F.scaled_dot_product_attention(v[0], v[1], v[2], is_causal=True)
+                    graphs.append((o, v, g.view(b, s, h, d).transpose(1, 2)))
+                t, tm = time_fn(lambda i: torch.autograd.grad(graphs[i][0], graphs[i][1], graphs[i][2], retain_graph=True),
+                                nvar, iters)
+                report(f"  (comparator, informative) {name}", t, tm, flops, nbytes)
+            except Exception as e:
+                print(json.dumps({"kernel": f"(comparator) {name}", "unavailable": str(e)[:200]}))
+        try:
+            import importlib
+            sys_path = list(sys.path)
+            sys.path = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
+            fa = importlib.import_module("flash_attn")
+            sys.path = sys_path
+            graphs = []
+            for qkv, _, _, g, _ in sets:
+                v = qkv.view(b, s, 3, h, d).detach().requires_grad_(True)
+                graphs.append((fa.flash_attn_qkvpacked_func(v, causal=True), v, g.view(b, s, h, d)))
+            t, tm = time_fn(lambda i: torch.autograd.grad(graphs[i][0], graphs[i][1], graphs[i][2], retain_graph=True),
+                            nvar, iters)
+            report(f"  (comparator, informative) site-packages flash_attn {getattr(fa, '__version__', '?')} backward (FA-2)",
+                   t, tm, flops, nbytes)
+        except Exception as e:
+            print(json.dumps({"kernel": "(comparator) site-packages flash_attn backward", "unavailable": str(e)[:200]}))
+    return rec
+
+
+def bench_bwd_ops(iters, rows=65536, cols=768, inner=3072):
+    """The HBM-bound backward passes at config-3 size: bp_ln_residual_bwd and bp_bias_act_bwd."""
+    from backpacks_flash_attn_b200.ops.fused_dense import bias_act_backward
+    from backpacks_flash_attn_b200.ops.layer_norm import dropout_add_layer_norm
+    x0 = torch.randn(rows, cols, device="cuda").bfloat16().requires_grad_()
+    x1 = torch.randn(rows, cols, device="cuda").requires_grad_()
+    w = torch.ones(cols, device="cuda").bfloat16().requires_grad_()
+    bb = torch.zeros(cols, device="cuda").bfloat16().requires_grad_()
+    z, r = dropout_add_layer_norm(x0, x1, w, bb, 0.0, 1e-5, prenorm=True)
+    g, g2 = torch.randn_like(z), torch.randn_like(r)
+    t, tm = time_fn(lambda i: torch.autograd.grad((z, r), (x0, x1, w, bb), (g, g2), retain_graph=True), 1, iters)
+    # dz (2) + x (4) + dx_residual (4) in, dx0 (2) + dx1 (4) out
+    report(f"ln_residual_bwd {rows}x{cols} bf16 / fp32 residual", t, tm, 0, rows * cols * 16)
+    d = torch.randn(rows, inner, device="cuda").bfloat16()
+    pre = torch.randn(rows, inner, device="cuda").bfloat16()
+    t, tm = time_fn(lambda i: bias_act_backward(d, pre, "gelu_tanh", True), 1, iters)
+    report(f"bias_act_bwd (dgelu + bias grad) {rows}x{inner} bf16", t, tm, 0, rows * inner * 6)
+    d2 = torch.randn(rows, cols, device="cuda").bfloat16()
+    t, tm = time_fn(lambda i: bias_act_backward(d2, None, "none", True), 1, iters)
+    report(f"bias_act_bwd (bias grad only) {rows}x{cols} bf16", t, tm, 0, rows * cols * 2)
+
+
 def bench_sense(iters, b=64, s=1024, nv=16, d=768):
     from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
     from backpacks_flash_attn_b200 import _lib
@@ -210,4 +289,5 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=20)
     a = ap.parse_args()
     for w in a.which.split(","):
-        {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms}[w](a.iters)
+        {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms,
+         "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops}[w](a.iters)

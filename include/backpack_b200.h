@@ -207,6 +207,31 @@ int bp_ln_fwd(const void* x, const void* gamma, const void* beta, void* z, float
               int64_t rows, int32_t cols, float epsilon, int32_t x_dtype, int32_t z_dtype, int32_t weight_dtype,
               void* stream);
 
+/* Backward of bp_ln_residual_fwd (replaces dropout_add_ln_bwd, csrc/layer_norm/ln_api.cpp:255-440 as driven by
+ * _dropout_add_layer_norm_backward, flash_attn/ops/layer_norm.py:27-47; dropout 0, no rowscale / colscale).
+ *   dz (rows, cols) in x0_dtype; x (rows, cols) in residual_dtype: the pre-norm sum x0 + x1 the forward wrote to
+ *   x_out (x0 itself when the forward wrote none); dx_residual: gradient arriving through the residual output of a
+ *   pre-norm block (residual_dtype) or NULL; gamma in weight_dtype.
+ *   dx0 (x0_dtype), dx1 (residual_dtype, or NULL when the forward had no x1), dgamma / dbeta (weight_dtype).
+ *   mu / rsigma are recomputed from x.  workspace: bp_ln_bwd_workspace_bytes(cols) bytes, 16-byte aligned.
+ * Two launches (row pass + column-sum finalisation); deterministic.
+ */
+int64_t bp_ln_bwd_workspace_bytes(int32_t cols);
+int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma, void* dx0, void* dx1,
+                       void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes, int64_t rows, int32_t cols,
+                       float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype, void* stream);
+
+/* Backward of the bias + activation epilogue of bp_linear_bias_act_fwd: what the reference gets from cuBLASLt's
+ * BGRADB / DGELU_BGRAD epilogues (csrc/fused_dense_lib/fused_dense_cuda.cu:559-787; flash_attn/ops/fused_dense.py:
+ * 57-80, 239-300).  The backward GEMMs themselves stay plain GEMMs.
+ *   BP_ACT_GELU_TANH: dpre = dact * gelu_tanh'(pre) (all (m, n) row-major, 16-bit), dbias = sum_rows dpre (or NULL).
+ *   BP_ACT_NONE     : dbias = sum_rows dact; pre / dpre ignored.
+ *   workspace: bp_bias_act_bwd_workspace_bytes(n) bytes when dbias is requested.  n % 8 == 0.  Deterministic.
+ */
+int64_t bp_bias_act_bwd_workspace_bytes(int32_t n);
+int bp_bias_act_bwd(const void* dact, const void* pre, void* dpre, void* dbias, void* workspace,
+                    int64_t workspace_bytes, int64_t m, int32_t n, int32_t activation, int32_t dtype, void* stream);
+
 /* In-place rotary embedding on q and k of a packed qkv tensor (replaces apply_rotary as driven by
  * ApplyRotaryEmbQKV_.forward, flash_attn/layers/rotary.py:81-105; csrc/rotary/rotary_cuda.cu:5-41).
  *   qkv (batch, seqlen, 3, nheads, headdim) contiguous; cos/sin (seqlen, rotary_dim/2) in qkv's dtype;

@@ -144,19 +144,20 @@ def test_fused_dense_runs_the_own_gemm_at_every_model_shape(n, k):
     lib = F.linear(x, lin.weight, lin.bias)
     assert torch.equal(y, y2) and y.shape == (3, m // 3, n)
     assert O.max_abs(y, ref) <= 2 * O.max_abs(lib, ref) + 1e-3
-    # under autograd the reference's F.linear is used (no backward kernel in this library)
+    # under autograd the same forward kernel runs, inside the autograd node whose backward is bp_bias_act_bwd + GEMMs
     xg = x.clone().requires_grad_(True)
     yg = lin(xg)
-    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2 and yg.requires_grad
+    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 3 and yg.requires_grad
+    assert torch.equal(yg.detach(), y)
     # "library" and the measured default ("auto": own GEMM for everything but the LM head and skinny decode GEMMs)
     FD.set_linear_backend("library")
     with torch.no_grad():
         assert torch.equal(lin(x), lib)
-    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2
+    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 3
     FD.set_linear_backend("auto")
     with torch.no_grad():
         lin(x)
-    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2 + (0 if n == 50264 else 1)
+    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 3 + (0 if n == 50264 else 1)
     with torch.no_grad():
         lin(x[:1, :64])                                   # 64 rows: a decode-step GEMM goes to the library
-    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 2 + (0 if n == 50264 else 1)
+    assert _lib.launch_counts.get("bp_linear_bias_act_fwd", 0) == before + 3 + (0 if n == 50264 else 1)
