@@ -5,8 +5,9 @@
 // through an fp32 `dq_tmp` round trip in HBM.  Written for Blackwell from scratch:
 //
 //   * three launches, all deterministic (no atomics, fixed accumulation order):
-//       1. bwd_stats_kernel: per query row {lse * log2(e), delta = sum_d dO * O} into a padded workspace
-//          (rows beyond a sequence get lse = +inf, so their probabilities are exactly 0);
+//       1. bwd_stats_kernel: per query row -lse * log2(e) and -delta = -sum_d dO * O into a padded workspace, blocked by 64
+//          rows ([64 x lse][64 x delta] per block: one 512-byte bulk copy per step; rows beyond a sequence get
+//          -lse = -inf, so their probabilities are exactly 0);
 //       2. fmha_bwd_kernel<kDQ = false>: a CTA owns 128 KEYS of one (batch, head) and streams the query blocks
 //          that see them; dV and dK stay in TMEM for the whole sweep;
 //       3. fmha_bwd_kernel<kDQ = true>:  a CTA owns 128 QUERIES and streams the key blocks they see; dQ stays in TMEM.
@@ -21,12 +22,19 @@
 //     are private to one thread, and tcgen05.mma of one thread execute in issue order, so the next step's T products
 //     overwrite them only after this step's gradient products have read them) and feed TS tcgen05.mma whose B
 //     operand is the SAME streaming tile consumed MN-major -- no transposes, nothing staged in shared memory.
-//   * 256 TMEM columns and ~85 KB of shared memory per CTA at head dim 64, so TWO CTAs share an SM: one CTA's
-//     exponentials overlap the other's tensor work without any software pipelining inside a CTA.
+//   * a step runs as two half-phases so that the tensor pipe and the exponentials overlap inside a CTA:
+//         softmax threads:  [T1 -> P (exp2) -> X1]  x1_ready  [T2 -> dS -> X2]  x2_ready  [next T1 ...]
+//         MMA thread:        ... T2(n) | x1_ready: acc1 += X1 B2, T1(n+1) | x2_ready: acc2 += X2 B1, T2(n+1) | ...
+//     i.e. the next step's S is computed while this step's dS is formed, and this step's dP / dV product while its
+//     exponentials run.  (The first version ran T1,T2 -> softmax -> both products strictly in sequence: ncu showed the
+//     tensor pipe 23 % and MUFU 20 % active with every warp waiting on the chain's latency.)
+//   * 256 TMEM columns and ~85 KB of shared memory per CTA at head dim 64, so TWO CTAs share an SM and fill each
+//     other's remaining bubbles (CTA start-up, stationary loads, epilogue stores).
 //   * the softmax scale is applied once to the fp32 dK / dQ accumulators, not per element.
 //
 // Varlen through cu_seqlens as in the forward; head dims that are a multiple of 8 up to 128 (TMA zero-fill to 64 / 128).
 #include <cstddef>
+#include <cstdlib>
 
 #include "bp_common.cuh"
 #include "bp_host.h"
@@ -44,7 +52,8 @@ constexpr int kPoly = BP_FMHA_BWD_POLY;   // of every 8 exponentials, how many r
 
 template <int DP, bool kDQ>
 struct Cfg {
-  static constexpr int kThreads = 192;   // warps 0-3: softmax + epilogue (TMEM lane quadrant = warp), 4: TMA, 5: MMA
+  static constexpr int kThreads = 320;   // warps 0-7: two softmax / epilogue warpgroups (TMEM lane quadrant = warp & 3,
+                                         // column half = warp >> 2), warp 8: TMA producer, warp 9: MMA issuer
   static constexpr int kStages = (DP == 64) ? 3 : 2;
   static constexpr int kPanels = DP / 64;
   static constexpr uint32_t kStatPanelBytes = BS * 128;
@@ -68,7 +77,7 @@ struct Cfg {
 };
 
 struct Params {
-  const float2* stats;       // (batch * nheads, s_pad): {lse * log2e, delta}
+  const float* stats;        // (batch * nheads, s_pad / 64, 2, 64): -lse * log2e, then -delta, per block of 64 query rows
   void* out1;                // keys-own: dV
   void* out2;                // keys-own: dK, queries-own: dQ (both scaled by the softmax scale)
   int64_t o1_row_stride, o1_head_stride, o2_row_stride, o2_head_stride;
@@ -80,16 +89,54 @@ struct Params {
   int32_t chunk_bh;          // (batch, head) pairs per scheduling chunk
   int32_t is_causal;
   float scale, scale_log2;
+  uint64_t* trace;           // debug: per-role event timestamps of CTA 0 (null in production)
 };
 
 struct Barriers {
-  uint64_t stat_full, t_full, x_ready, acc_full;
+  uint64_t stat_full, t1_full, t2_full, x1_ready, x2_ready, acc_full;
   uint64_t str_full[3], str_empty[3];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Barriers) <= 256, "barrier block");
 #define BBAR(field) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)))
 #define BBAR_I(field, i) (bars_a + static_cast<uint32_t>(offsetof(Barriers, field)) + 8u * static_cast<uint32_t>(i))
+
+// packed fp32x2 arithmetic with distinct operands per half (the softmax warps are bound by instruction issue)
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmov.b64 c, {%5, %6};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}\n"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+// (d0, d1) = (e0, e1) * ((x0, x1) + (n0, n1))
+__device__ __forceinline__ void mul_add2v(float& d0, float& d1, float e0, float e1, float x0, float x1, float n0, float n1) {
+  asm("{\n\t.reg .b64 e, x, n, t, d;\n\t"
+      "mov.b64 e, {%2, %3};\n\tmov.b64 x, {%4, %5};\n\tmov.b64 n, {%6, %7};\n\t"
+      "add.rn.f32x2 t, x, n;\n\tmul.rn.f32x2 d, e, t;\n\tmov.b64 {%0, %1}, d;\n\t}\n"
+      : "=f"(d0), "=f"(d1) : "f"(e0), "f"(e1), "f"(x0), "f"(x1), "f"(n0), "f"(n1));
+}
+
+// Spinning wait on test_wait for the MMA issuer: the suspending try_wait of mbar_wait_a wakes up several hundred cycles
+// after the phase completes, and the issuer's two hand-over waits sit on the critical path of every step.  Bounded like
+// mbar_wait_a (traps after 4 s).
+#ifndef BP_FMHA_BWD_SPIN
+#define BP_FMHA_BWD_SPIN 1
+#endif
+__device__ __forceinline__ void mbar_spin_a(uint32_t bar, uint32_t parity) {
+  if (!BP_FMHA_BWD_SPIN) {
+    mbar_wait_a(bar, parity);
+    return;
+  }
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
+  while (!mbar_test_a(bar, parity)) {
+    if ((++polls & 0xFFFFu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ void bulk_load_1d_w(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -106,24 +153,36 @@ __device__ __forceinline__ void bulk_load_1d_w(uint32_t smem_dst, const void* gs
 template <bool kBF16>
 __global__ void __launch_bounds__(256)
 bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, const float* __restrict__ lse,
-                 float2* __restrict__ stats, const int32_t* __restrict__ cu_q, int64_t do_row, int64_t do_head,
+                 float* __restrict__ stats, const int32_t* __restrict__ cu_q, int64_t do_row, int64_t do_head,
                  int64_t o_row, int64_t o_head, int32_t lse_stride, int32_t s_pad, int32_t nheads, int32_t headdim) {
-  // 16 lanes per query row (8 elements = 16 bytes each), 2 rows per warp, 16 rows per block
+  // One CTA = one block of 64 query rows of one (batch, head).  16 lanes per row (8 elements = 16 bytes each), a warp
+  // covers 8 rows in 4 passes whose loads are all issued before the first use.
   const int bh = blockIdx.x;
   const int b = bh / nheads, h = bh - b * nheads;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.y * 16 + warp * 2 + (lane >> 4);
   const int q = lane & 15;
   const int q_begin = __ldg(cu_q + b);
   const int len_q = __ldg(cu_q + b + 1) - q_begin;
-  const bool valid = i < len_q;
-  float acc = 0.f;
-  if (valid && q * 8 < headdim) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(
-        reinterpret_cast<const uint16_t*>(dout) + static_cast<int64_t>(q_begin + i) * do_row + h * do_head + q * 8));
-    const uint4 c = __ldg(reinterpret_cast<const uint4*>(
-        reinterpret_cast<const uint16_t*>(out) + static_cast<int64_t>(q_begin + i) * o_row + h * o_head + q * 8));
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+  uint4 a[4], c[4];
+  int rows[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = warp * 8 + it * 2 + (lane >> 4);
+    const int i = blockIdx.y * 64 + r;
+    rows[it] = r;
+    a[it] = c[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < len_q && q * 8 < headdim) {
+      a[it] = __ldg(reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint16_t*>(dout) + static_cast<int64_t>(q_begin + i) * do_row + h * do_head + q * 8));
+      c[it] = __ldg(reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint16_t*>(out) + static_cast<int64_t>(q_begin + i) * o_row + h * o_head + q * 8));
+    }
+  }
+  float* blk = stats + (static_cast<int64_t>(bh) * (s_pad / 64) + blockIdx.y) * 128;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const uint32_t aw[4] = {a[it].x, a[it].y, a[it].z, a[it].w}, cw[4] = {c[it].x, c[it].y, c[it].z, c[it].w};
+    float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float2 fa, fc;
@@ -137,14 +196,14 @@ bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, co
       acc = fmaf(fa.x, fc.x, acc);
       acc = fmaf(fa.y, fc.y, acc);
     }
-  }
 #pragma unroll
-  for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (q == 0 && i < s_pad) {
-    float2 st;
-    st.x = valid ? __ldg(lse + static_cast<int64_t>(bh) * lse_stride + i) * kLog2e : INFINITY;
-    st.y = valid ? acc : 0.f;
-    stats[static_cast<int64_t>(bh) * s_pad + i] = st;
+    for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (q == 0) {
+      const int i = blockIdx.y * 64 + rows[it];
+      const bool valid = i < len_q;
+      blk[rows[it]] = valid ? -__ldg(lse + static_cast<int64_t>(bh) * lse_stride + i) * kLog2e : -INFINITY;
+      blk[64 + rows[it]] = valid ? -acc : 0.f;
+    }
   }
 }
 
@@ -156,6 +215,11 @@ __global__ void __launch_bounds__(Cfg<DP, kDQ>::kThreads, Cfg<DP, kDQ>::kCtasPer
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_constant__ CUtensorMap tmStat2,
                 const __grid_constant__ CUtensorMap tmStr1, const __grid_constant__ CUtensorMap tmStr2, const Params p) {
   using C = Cfg<DP, kDQ>;
+#ifdef BP_TRACE
+  // debug: (start ns, end ns, SM id) of every CTA behind the role timelines (benchmarks/trace_kernel.py bwd_*)
+  uint64_t cta_t0 = 0;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 4096) cta_t0 = global_timer_ns();
+#endif
   // ---- which tile ----
   const int total_bh = p.batch * p.nheads;
   const int per_chunk = p.chunk_bh * p.num_tiles;
@@ -190,14 +254,16 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmStat1);
     tma_prefetch_desc(&tmStat2);
     tma_prefetch_desc(&tmStr1);
     tma_prefetch_desc(&tmStr2);
     mbar_init(&bars.stat_full, 1);
-    mbar_init(&bars.t_full, 1);
-    mbar_init(&bars.x_ready, 128);
+    mbar_init(&bars.t1_full, 1);
+    mbar_init(&bars.t2_full, 1);
+    mbar_init(&bars.x1_ready, 256);
+    mbar_init(&bars.x2_ready, 256);
     mbar_init(&bars.acc_full, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bars.str_full[i], 1);
@@ -205,7 +271,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(&bars.tmem_base, C::kTmemCols);
     tmem_relinquish();
   }
@@ -214,7 +280,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer (whole warp walks the loop, an elected lane issues) =====================
     if (n_steps > 0) {
       mbar_arrive_expect_tx_w(BBAR(stat_full), 2 * C::kStatTileBytes);
@@ -228,8 +294,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         }
     }
     uint32_t slot = 0, ph = 1;   // ph: parity of the str_empty phase to wait for (first pass: the slots are free)
+    Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
     for (int n = 0; n < n_steps; ++n) {
       if (n >= C::kStages) mbar_wait_a(BBAR_I(str_empty, slot), ph);
+      tr.rec(1, n);
       const uint32_t st = smem_a + C::offStr + slot * C::kStageBytes;
       const int srow = str_begin + (first + n) * BT;
       mbar_arrive_expect_tx_w(BBAR_I(str_full, slot), 2 * C::kStrTileBytes + (kDQ ? 0u : C::kStatsBytes));
@@ -239,170 +307,263 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         tma_load_3d_w(st + C::kStrTileBytes + pn * C::kStrPanelBytes, &tmStr2, BBAR_I(str_full, slot), pn * 64, head, srow);
       }
       if constexpr (!kDQ)
-        bulk_load_1d_w(st + 2 * C::kStrTileBytes, p.stats + static_cast<int64_t>(bh) * p.s_pad + (first + n) * BT,
-                       C::kStatsBytes, BBAR_I(str_full, slot));
+        bulk_load_1d_w(st + 2 * C::kStrTileBytes,
+                       p.stats + (static_cast<int64_t>(bh) * (p.s_pad / 64) + (first + n)) * 128, C::kStatsBytes,
+                       BBAR_I(str_full, slot));
       if (++slot == C::kStages) {
         slot = 0;
         ph ^= 1;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_t = make_idesc(kBF16, BS, BT, false, false);
     constexpr uint32_t idesc_acc = make_idesc(kBF16, BS, DP, false, true);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t tT1 = tm + C::colT1, tT2 = tm + C::colT2, tA1 = tm + C::colA1, tA2 = tm + C::colA2;
     const uint32_t sA1 = smem_a + C::offStat1, sA2 = smem_a + C::offStat2;
-    if (n_steps > 0) mbar_wait_a(BBAR(stat_full), 0);
-    uint32_t slot = 0, ph = 0;
-    for (int n = 0; n < n_steps; ++n) {
-      const uint32_t sB1 = smem_a + C::offStr + slot * C::kStageBytes;
-      const uint32_t sB2 = sB1 + C::kStrTileBytes;
-      mbar_wait_a(BBAR_I(str_full, slot), ph);
-      tc_fence_after();
+    auto issue_t1 = [&](uint32_t sB1) {
 #pragma unroll
       for (int kk = 0; kk < DP / 16; ++kk) {
         const uint32_t a = sA1 + (kk >> 2) * C::kStatPanelBytes + (kk & 3) * 32;
         const uint32_t b = sB1 + (kk >> 2) * C::kStrPanelBytes + (kk & 3) * 32;
         umma_ss_w(tT1, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_t, kk > 0 ? 1u : 0u);
       }
+      umma_commit_w(BBAR(t1_full));
+    };
+    auto issue_t2 = [&](uint32_t sB2) {
 #pragma unroll
       for (int kk = 0; kk < DP / 16; ++kk) {
         const uint32_t a = sA2 + (kk >> 2) * C::kStatPanelBytes + (kk & 3) * 32;
         const uint32_t b = sB2 + (kk >> 2) * C::kStrPanelBytes + (kk & 3) * 32;
         umma_ss_w(tT2, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_t, kk > 0 ? 1u : 0u);
       }
-      umma_commit_w(BBAR(t_full));
-      mbar_wait_a(BBAR(x_ready), n & 1);
+      umma_commit_w(BBAR(t2_full));
+    };
+    uint32_t slot = 0, ph = 0;
+    Tracer tr(p.trace, 1, blockIdx.x == 0 && lane == 0);
+    tr.rec(0, 0);
+    if (n_steps > 0) {
+      mbar_wait_a(BBAR(stat_full), 0);
+      mbar_wait_a(BBAR_I(str_full, 0), 0);
       tc_fence_after();
-      // gradient products: A = X from TMEM (8 columns per K-step of 16 streaming rows), B = the streaming tile MN-major
+      tr.rec(9, 0);
+      issue_t1(smem_a + C::offStr);
+      issue_t2(smem_a + C::offStr + C::kStrTileBytes);
+    }
+    for (int n = 0; n < n_steps; ++n) {
+      const uint32_t sB1 = smem_a + C::offStr + slot * C::kStageBytes;
+      const uint32_t sB2 = sB1 + C::kStrTileBytes;
+      uint32_t nslot = slot + 1, nph = ph;
+      if (nslot == C::kStages) {
+        nslot = 0;
+        nph ^= 1;
+      }
+      const uint32_t nB1 = smem_a + C::offStr + nslot * C::kStageBytes;
+      const bool more = n + 1 < n_steps;
+      // the next streaming tiles have normally landed long ago: probe now, the latency overlaps the hand-over wait
+      const bool next_ready = more ? mbar_test_a(BBAR_I(str_full, nslot), nph) : true;
+      // first half: X1 is in TMEM (keys own) / T1 has been read out (queries own)
+      mbar_spin_a(BBAR(x1_ready), n & 1);
+      tc_fence_after();
+      tr.rec(1, n);
+      // gradient products: A = X from TMEM (8 columns per K-step of 16 streaming rows; the two column halves of X sit at
+      // the start of the two halves of T, where their warpgroups wrote them), B = the streaming tile MN-major
       if constexpr (!kDQ) {
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
-          umma_ts_w(tA1, tT1 + kk * 8, make_smem_desc_sw128(sB2 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
+          umma_ts_w(tA1, tT1 + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc_sw128(sB2 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
                     (n > 0 || kk > 0) ? 1u : 0u);
       }
+      if (more) {
+        if (!next_ready) {
+          mbar_wait_a(BBAR_I(str_full, nslot), nph);
+          tc_fence_after();
+        }
+        issue_t1(nB1);   // executes behind the product above, which is the last reader of X1 (same issuing thread)
+      }
+      tr.rec(2, n);
+      // second half: X2 is in TMEM
+      mbar_spin_a(BBAR(x2_ready), n & 1);
+      tc_fence_after();
+      tr.rec(3, n);
 #pragma unroll
       for (int kk = 0; kk < BT / 16; ++kk)
-        umma_ts_w(tA2, tT2 + kk * 8, make_smem_desc_sw128(sB1 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
+        umma_ts_w(tA2, tT2 + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc_sw128(sB1 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
                   (n > 0 || kk > 0) ? 1u : 0u);
-      umma_commit_w(BBAR_I(str_empty, slot));
-      if (++slot == C::kStages) {
-        slot = 0;
-        ph ^= 1;
-      }
+      umma_commit_w(BBAR_I(str_empty, slot));   // every product that reads this step's streaming tiles has been issued
+      if (more) issue_t2(nB1 + C::kStrTileBytes);
+      tr.rec(4, n);
+      slot = nslot;
+      ph = nph;
     }
     if (n_steps > 0) umma_commit_w(BBAR(acc_full));
   } else {
-    // ===================== softmax / gradient warps: one thread per stationary row =====================
-    const int r = warp * 32 + lane;
+    // ===================== softmax / gradient warps =====================
+    // Two warpgroups share the 128 rows: thread (quadrant, lane) of warpgroup g owns row r and the 32 streaming columns
+    // [32 g, 32 g + 32) of every step.  (One warpgroup with whole 64-column rows left 8 softmax warps per SM walking a
+    // serial chain of ~2100 cycles per step; halving the per-thread work halves the chain.)
+    constexpr int HC = BT / 2;
+    const int g = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
     const int row = row0 + r;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const uint32_t tT1 = tmem_base + lane_addr + C::colT1, tT2 = tmem_base + lane_addr + C::colT2;
+    const int cbase = g * HC;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tT1 = tmem_base + lane_addr + C::colT1 + cbase, tT2 = tmem_base + lane_addr + C::colT2 + cbase;
     const float c2 = p.scale_log2;
     float rowL = 0.f, rowD = 0.f;
     if constexpr (kDQ) {
-      const float2 st = __ldg(p.stats + static_cast<int64_t>(bh) * p.s_pad + row);
-      rowL = st.x;
-      rowD = st.y;
+      const float* blk = p.stats + (static_cast<int64_t>(bh) * (p.s_pad / 64) + (row >> 6)) * 128;
+      rowL = __ldg(blk + (row & 63));
+      rowD = __ldg(blk + 64 + (row & 63));
     }
     uint32_t slot = 0, ph = 0;
+    Tracer tr(p.trace, 2 + g, blockIdx.x == 0 && lane == 0 && (warp & 3) == 0);
     for (int n = 0; n < n_steps; ++n) {
-      const int col0 = (first + n) * BT;
-      const uint32_t sStats = smem_a + C::offStr + slot * C::kStageBytes + 2 * C::kStrTileBytes;
-      if constexpr (!kDQ) mbar_wait_a(BBAR_I(str_full, slot), ph);   // the statistics travel with the streaming tiles
-      mbar_wait_a(BBAR(t_full), n & 1);
-      tc_fence_after();
-      // valid columns of this row inside the block: lo <= c < hi
+      tr.rec(0, n);
+      const int col0 = (first + n) * BT + cbase;   // first streaming row of this thread's columns
+      const uint32_t sStats = smem_a + C::offStr + slot * C::kStageBytes + 2 * C::kStrTileBytes + cbase * 4;
+      // valid columns of this row inside the thread's half block: lo <= i < hi
       int lo = 0, hi = len_str - col0;
-      bool partial = col0 + BT > len_str;
+      bool partial = col0 + HC > len_str;
       if (p.is_causal) {
         if (kDQ) {
           hi = min(hi, row + 1 - col0);
-          partial = partial || (col0 + BT - 1 > row0);
+          partial = partial || (col0 + HC - 1 > row0);
         } else {
           lo = row - col0;
           partial = partial || (col0 < row0 + BS - 1);
         }
       }
-#pragma unroll
-      for (int c = 0; c < BT / 32; ++c) {
-        uint32_t us[32], ud[32];
-        tmem_ld32(tT1 + c * 32, us);
-        tmem_ld32(tT2 + c * 32, ud);
+      // the statistics travel with the streaming tiles, which have landed before T1 could be computed: a probe whose
+      // latency overlaps the wait for T1 (a satisfied blocking wait costs ~200 cycles on its own)
+      bool stats_ready = true;
+      if constexpr (!kDQ) stats_ready = mbar_test_a(BBAR_I(str_full, slot), ph);
+
+      // ---- first half: P = exp2(T1 * scale_log2 - L) ----
+      mbar_wait_a(BBAR(t1_full), n & 1);
+      const bool t2_ready = mbar_test_a(BBAR(t2_full), n & 1);   // consumed after the exponentials
+      if constexpr (!kDQ) {
+        if (!stats_ready) mbar_wait_a(BBAR_I(str_full, slot), ph);
+      }
+      tc_fence_after();
+      tr.rec(1, n);
+      float e[HC];
+      {
+        uint32_t us[HC];
+        tmem_ld32(tT1, us);
         tmem_ld_wait();
-        float e[32], g[32];
+        tr.rec(2, n);
         if constexpr (kDQ) {
-          const float negL = -rowL;
+          tc_fence_before();
+          mbar_arrive_a(BBAR(x1_ready));   // T1 is in registers: the next S may overwrite it
+          const float negL = rowL;   // the workspace holds -lse * log2e
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float t8[8];
+          for (int i = 0; i < HC; i += 8) {
+            float t8[8], e8[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) t8[k] = __uint_as_float(us[i + k]);
-            float e8[8];
             exp2_scaled8<kPoly>(e8, t8, c2, negL);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              e[i + k] = e8[k];
-              g[i + k] = e8[k] * (__uint_as_float(ud[i + k]) - rowD);
-            }
+            for (int k = 0; k < 8; ++k) e[i + k] = e8[k];
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint4 st = lds128(sStats + (c * 32 + i) * 8);   // {L, delta} of two query columns (broadcast)
-            float a0 = fmaf(__uint_as_float(us[i]), c2, -__uint_as_float(st.x));
-            float a1 = fmaf(__uint_as_float(us[i + 1]), c2, -__uint_as_float(st.z));
-            if ((i & 7) < 8 - kPoly) {
-              a0 = fast_exp2(a0);
-              a1 = fast_exp2(a1);
+          for (int i = 0; i < HC; i += 4) {
+            const uint4 L = lds128(sStats + i * 4);   // -lse * log2e of four query columns (broadcast)
+            float a0, a1, a2, a3;
+            ffma2v(a0, a1, __uint_as_float(us[i]), __uint_as_float(us[i + 1]), c2, __uint_as_float(L.x), __uint_as_float(L.y));
+            ffma2v(a2, a3, __uint_as_float(us[i + 2]), __uint_as_float(us[i + 3]), c2, __uint_as_float(L.z), __uint_as_float(L.w));
+            a0 = fast_exp2(a0);
+            a1 = fast_exp2(a1);
+            if (kPoly == 4 || (kPoly == 2 && (i & 4))) {
+              exp2_poly_pair(a2, a3);   // this share of the exponentials runs on the FMA pipe
             } else {
-              exp2_poly_pair(a0, a1);
+              a2 = fast_exp2(a2);
+              a3 = fast_exp2(a3);
             }
             e[i] = a0;
             e[i + 1] = a1;
-            g[i] = a0 * (__uint_as_float(ud[i]) - __uint_as_float(st.y));
-            g[i + 1] = a1 * (__uint_as_float(ud[i + 1]) - __uint_as_float(st.w));
+            e[i + 2] = a2;
+            e[i + 3] = a3;
           }
         }
+      }
+      if (partial) {
+#pragma unroll
+        for (int i = 0; i < HC; ++i) e[i] = (i >= lo && i < hi) ? e[i] : 0.f;
+      }
+      tr.rec(3, n);
+      if constexpr (!kDQ) {
+        uint32_t pk[HC / 2];
+#pragma unroll
+        for (int i = 0; i < HC / 2; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
+        tmem_st16(tT1, pk);   // over the first half of the columns this thread has just read
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_a(BBAR(x1_ready));
+      }
+      tr.rec(4, n);
+
+      // ---- second half: dS = P * (T2 - delta) ----
+      if (!t2_ready) mbar_wait_a(BBAR(t2_full), n & 1);
+      tc_fence_after();
+      tr.rec(5, n);
+      {
+        uint32_t ud[HC];
+        tmem_ld32(tT2, ud);
+        tmem_ld_wait();
         if (partial) {
+          // masked columns may hold products with rows of a neighbouring sequence: select, never multiply by zero
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool ok = (c * 32 + i >= lo) && (c * 32 + i < hi);
-            e[i] = ok ? e[i] : 0.f;
-            g[i] = ok ? g[i] : 0.f;
+          for (int i = 0; i < HC; ++i) ud[i] = (i >= lo && i < hi) ? ud[i] : 0u;
+        }
+        uint32_t pk[HC / 2];
+        if constexpr (kDQ) {
+#pragma unroll
+          for (int i = 0; i < HC / 2; ++i) {
+            float g0, g1;
+            mul_add2v(g0, g1, e[2 * i], e[2 * i + 1], __uint_as_float(ud[2 * i]), __uint_as_float(ud[2 * i + 1]), rowD, rowD);
+            pk[i] = pack2<kBF16>(g0, g1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < HC; i += 4) {
+            const uint4 D = lds128(sStats + 256 + i * 4);   // -delta of four query columns
+            float g0, g1, g2, g3;
+            mul_add2v(g0, g1, e[i], e[i + 1], __uint_as_float(ud[i]), __uint_as_float(ud[i + 1]), __uint_as_float(D.x),
+                      __uint_as_float(D.y));
+            mul_add2v(g2, g3, e[i + 2], e[i + 3], __uint_as_float(ud[i + 2]), __uint_as_float(ud[i + 3]),
+                      __uint_as_float(D.z), __uint_as_float(D.w));
+            pk[i / 2] = pack2<kBF16>(g0, g1);
+            pk[i / 2 + 1] = pack2<kBF16>(g2, g3);
           }
         }
-        uint32_t pk[16];
-        if constexpr (!kDQ) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
-          tmem_st16(tT1 + c * 16, pk);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(g[2 * i], g[2 * i + 1]);
-        tmem_st16(tT2 + c * 16, pk);
+        tmem_st16(tT2, pk);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive_a(BBAR(x_ready));
+      mbar_arrive_a(BBAR(x2_ready));
+      tr.rec(7, n);
       if (++slot == C::kStages) {
         slot = 0;
         ph ^= 1;
       }
     }
 
-    // ---- epilogue: accumulators -> global (one thread per row, 16-byte stores) ----
+    // ---- epilogue: accumulators -> global (a thread stores its warpgroup's half of the columns of its row) ----
     if (n_steps > 0) {
       mbar_wait_a(BBAR(acc_full), 0);
       tc_fence_after();
     }
+    tr.rec(8, 0);
     const bool valid = row < len_stat;
     auto store_acc = [&](uint32_t col, void* out, int64_t row_stride, int64_t head_stride, float mult) {
       uint8_t* orow = reinterpret_cast<uint8_t*>(out) +
                       2 * (static_cast<int64_t>(stat_begin + row) * row_stride + head * head_stride);
 #pragma unroll
-      for (int c = 0; c < DP / 32; ++c) {
+      for (int cc = 0; cc < DP / 64; ++cc) {
+        const int c = g * (DP / 64) + cc;
         uint32_t o[32];
         if (n_steps > 0) {
           tmem_ld32(tmem_base + lane_addr + col + c * 32, o);
@@ -428,11 +589,23 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     };
     if constexpr (!kDQ) store_acc(C::colA1, p.out1, p.o1_row_stride, p.o1_head_stride, 1.f);
     store_acc(C::colA2, p.out2, p.o2_row_stride, p.o2_head_stride, p.scale);
+    tr.rec(9, 0);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 9) tmem_dealloc(tmem_base, C::kTmemCols);
+#ifdef BP_TRACE
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 4096) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint64_t* rec = p.trace + 8 * kTraceRecs * 2 + 2 * 148 + 4 * blockIdx.x;
+    rec[0] = cta_t0;
+    rec[1] = global_timer_ns();
+    rec[2] = smid;
+    rec[3] = static_cast<uint64_t>(n_steps);
+  }
+#endif
 }
 
 template <int DP, bool kDQ, bool kBF16>
@@ -499,10 +672,10 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   const int s_pad = (max_seqlen_q + 127) / 128 * 128;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
-  float2* stats = static_cast<float2*>(workspace);
+  float* stats = static_cast<float*>(workspace);
 
   {
-    dim3 grid(batch * nheads, (s_pad + 15) / 16);
+    dim3 grid(batch * nheads, s_pad / 64);
     if (bf16)
       fmha_bwd::bwd_stats_kernel<true><<<grid, 256, 0, st>>>(dout, out, softmax_lse, stats, cu_seqlens_q, s_do[0], s_do[1],
                                                              s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim);
@@ -537,6 +710,10 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   p.is_causal = is_causal ? 1 : 0;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * fmha_bwd::kLog2e;
+  p.trace = nullptr;
+#ifdef BP_TRACE
+  const char* trace_mode = getenv("BP_TRACE_BWD");   // "dkdv" or "dq": which of the two launches writes the timeline
+#endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -550,6 +727,9 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   p.out2 = dk;
   p.o2_row_stride = s_dk[0];
   p.o2_head_stride = s_dk[1];
+#ifdef BP_TRACE
+  p.trace = (trace_mode && trace_mode[0] == 'd' && trace_mode[1] == 'k') ? g_trace : nullptr;
+#endif
   int rc;
   if (DP == 64)
     rc = bf16 ? fmha_bwd::launch<64, false, true>(tmK, tmV, tmQ, tmDO, p, st)
@@ -562,6 +742,9 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   // queries own: dQ
   p.num_tiles = (max_seqlen_q + fmha_bwd::BS - 1) / fmha_bwd::BS;
   p.chunk_bh = (2 * sms) / p.num_tiles > 0 ? (2 * sms) / p.num_tiles : 1;
+#ifdef BP_TRACE
+  p.trace = (trace_mode && trace_mode[0] == 'd' && trace_mode[1] == 'q') ? g_trace : nullptr;
+#endif
   p.out1 = nullptr;
   p.out2 = dq;
   p.o2_row_stride = s_dq[0];
