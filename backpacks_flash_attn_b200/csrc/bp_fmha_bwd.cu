@@ -65,7 +65,8 @@ struct Cfg {
   static constexpr uint32_t offStat1 = 0;
   static constexpr uint32_t offStat2 = kStatTileBytes;
   static constexpr uint32_t offStr = 2 * kStatTileBytes;
-  static constexpr uint32_t offBar = offStr + kStages * kStageBytes;
+  static constexpr uint32_t offStage = offStr + kStages * kStageBytes;   // [128 rows][DP * 2 B] epilogue staging tile
+  static constexpr uint32_t offBar = offStage + BS * DP * 2;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
   static constexpr uint32_t colT1 = 0, colT2 = BT;
   static constexpr uint32_t colA1 = 2 * BT;
@@ -93,7 +94,7 @@ struct Params {
 };
 
 struct Barriers {
-  uint64_t stat_full, t1_full, t2_full, x1_ready, x2_ready, acc_full;
+  uint64_t stat_full, t1_full, t2_full, x1_ready, x2_ready, acc_full, acc_free;
   uint64_t str_full[3], str_empty[3];
   uint32_t tmem_base;
 };
@@ -210,41 +211,66 @@ bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, co
 // ------------------------------------------------------------------------------------------------------------------
 // launches 2 and 3
 // ------------------------------------------------------------------------------------------------------------------
+// One work item = one stationary tile (128 rows of one (batch, head)).  The schedule is static: CTA c of G walks the
+// scheduling chunks (chunk_bh (batch, head) pairs x num_tiles tiles = G items, sized to one wave of 2 CTAs per SM, so
+// the CTAs that run together sweep the same K/V/Q/dO in L2) and takes position c of every chunk; under causal masking
+// the tile rank is mirrored in odd chunks, so every CTA alternates heavy and light tiles (rank r and T-1-r add up to a
+// constant number of steps).  Every warp role derives the same item sequence on its own.
+struct Item {
+  int valid;
+  int bh, batch, head, row0;
+  int stat_begin, len_stat, str_begin, len_str;
+  int first, n_steps;
+};
+
+template <bool kDQ>
+__device__ __forceinline__ Item decode_item(const Params& p, int chunk, int pos) {
+  Item it;
+  it.valid = 0;
+  const int total_bh = p.batch * p.nheads;
+  const int bh0 = chunk * p.chunk_bh;
+  const int gc = min(p.chunk_bh, total_bh - bh0);
+  int rank = pos / gc;
+  if (rank >= p.num_tiles) return it;
+  it.bh = bh0 + (pos - rank * gc);
+  it.batch = it.bh / p.nheads;
+  it.head = it.bh - it.batch * p.nheads;
+  if (p.is_causal && (chunk & 1)) rank = p.num_tiles - 1 - rank;
+  const int tile = (kDQ && p.is_causal) ? p.num_tiles - 1 - rank : rank;   // rank 0 = most steps
+  it.row0 = tile * BS;
+  const int q_begin = __ldg(p.cu_q + it.batch), len_q = __ldg(p.cu_q + it.batch + 1) - q_begin;
+  const int k_begin = __ldg(p.cu_k + it.batch), len_k = __ldg(p.cu_k + it.batch + 1) - k_begin;
+  it.stat_begin = kDQ ? q_begin : k_begin;
+  it.len_stat = kDQ ? len_q : len_k;
+  it.str_begin = kDQ ? k_begin : q_begin;
+  it.len_str = kDQ ? len_k : len_q;
+  if (it.row0 >= it.len_stat) return it;
+  const int nblk = (it.len_str + BT - 1) / BT;
+  int first = 0, last = nblk;
+  if (p.is_causal) {
+    if (kDQ) last = min(nblk, (it.row0 + BS) / BT);   // keys <= last query of the tile
+    else first = it.row0 / BT;                        // queries >= first key of the tile
+  }
+  it.first = first;
+  it.n_steps = max(0, last - first);
+  it.valid = 1;
+  return it;
+}
+
 template <int DP, bool kDQ, bool kBF16>
 __global__ void __launch_bounds__(Cfg<DP, kDQ>::kThreads, Cfg<DP, kDQ>::kCtasPerSm)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_constant__ CUtensorMap tmStat2,
-                const __grid_constant__ CUtensorMap tmStr1, const __grid_constant__ CUtensorMap tmStr2, const Params p) {
+                const __grid_constant__ CUtensorMap tmStr1, const __grid_constant__ CUtensorMap tmStr2,
+                const __grid_constant__ CUtensorMap tmOut1, const __grid_constant__ CUtensorMap tmOut2, const Params p) {
   using C = Cfg<DP, kDQ>;
 #ifdef BP_TRACE
   // debug: (start ns, end ns, SM id) of every CTA behind the role timelines (benchmarks/trace_kernel.py bwd_*)
   uint64_t cta_t0 = 0;
   if (p.trace && threadIdx.x == 0 && blockIdx.x < 4096) cta_t0 = global_timer_ns();
 #endif
-  // ---- which tile ----
   const int total_bh = p.batch * p.nheads;
-  const int per_chunk = p.chunk_bh * p.num_tiles;
-  const int ch = blockIdx.x / per_chunk;
-  const int rr = blockIdx.x - ch * per_chunk;
-  const int bh0 = ch * p.chunk_bh;
-  const int gc = min(p.chunk_bh, total_bh - bh0);
-  const int rank = rr / gc;   // heaviest tiles of a chunk first
-  if (rank >= p.num_tiles) return;
-  const int bh = bh0 + (rr - rank * gc);
-  const int batch = bh / p.nheads, head = bh - batch * p.nheads;
-  const int tile = (kDQ && p.is_causal) ? p.num_tiles - 1 - rank : rank;
-  const int row0 = tile * BS;
-  const int q_begin = __ldg(p.cu_q + batch), len_q = __ldg(p.cu_q + batch + 1) - q_begin;
-  const int k_begin = __ldg(p.cu_k + batch), len_k = __ldg(p.cu_k + batch + 1) - k_begin;
-  const int stat_begin = kDQ ? q_begin : k_begin, len_stat = kDQ ? len_q : len_k;
-  const int str_begin = kDQ ? k_begin : q_begin, len_str = kDQ ? len_k : len_q;
-  if (row0 >= len_stat) return;
-  const int nblk = (len_str + BT - 1) / BT;
-  int first = 0, last = nblk;
-  if (p.is_causal) {
-    if (kDQ) last = min(nblk, (row0 + BS) / BT);   // keys <= last query of the tile
-    else first = row0 / BT;                        // queries >= first key of the tile
-  }
-  const int n_steps = max(0, last - first);
+  const int chunks = (total_bh + p.chunk_bh - 1) / p.chunk_bh;
+  const int pos = blockIdx.x;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -259,12 +285,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     tma_prefetch_desc(&tmStat2);
     tma_prefetch_desc(&tmStr1);
     tma_prefetch_desc(&tmStr2);
+    if constexpr (!kDQ) tma_prefetch_desc(&tmOut1);
+    tma_prefetch_desc(&tmOut2);
     mbar_init(&bars.stat_full, 1);
     mbar_init(&bars.t1_full, 1);
     mbar_init(&bars.t2_full, 1);
     mbar_init(&bars.x1_ready, 256);
     mbar_init(&bars.x2_ready, 256);
     mbar_init(&bars.acc_full, 1);
+    mbar_init(&bars.acc_free, 256);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bars.str_full[i], 1);
       mbar_init(&bars.str_empty[i], 1);
@@ -280,40 +309,52 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
+  // Barrier phases run on across items: `ic` counts this CTA's items that have steps (stat_full, acc_full, acc_free
+  // complete once per such item), `sc` counts steps (t1_full, t2_full, x1_ready, x2_ready), slot / ph walk the ring.
   if (warp == 8) {
     // ===================== TMA producer (whole warp walks the loop, an elected lane issues) =====================
-    if (n_steps > 0) {
+    uint32_t slot = 0, ph = 1;   // ph: parity of the str_empty phase to wait for (first pass: the slots are free)
+    uint32_t blk = 0;            // streaming blocks loaded so far
+    uint32_t ic = 0;
+    Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
+    for (int ch = 0; ch < chunks; ++ch) {
+      const Item it = decode_item<kDQ>(p, ch, pos);
+      if (!it.valid || it.n_steps == 0) continue;
+      // the stationary tiles of the previous item are free once all of its products have completed
+      if (ic > 0) mbar_wait_a(BBAR(acc_full), (ic - 1) & 1);
       mbar_arrive_expect_tx_w(BBAR(stat_full), 2 * C::kStatTileBytes);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int pn = 0; pn < C::kPanels; ++pn) {
           const uint32_t off = pn * C::kStatPanelBytes + half * (BT * 128);
-          tma_load_3d_w(smem_a + C::offStat1 + off, &tmStat1, BBAR(stat_full), pn * 64, head, stat_begin + row0 + half * BT);
-          tma_load_3d_w(smem_a + C::offStat2 + off, &tmStat2, BBAR(stat_full), pn * 64, head, stat_begin + row0 + half * BT);
+          tma_load_3d_w(smem_a + C::offStat1 + off, &tmStat1, BBAR(stat_full), pn * 64, it.head,
+                        it.stat_begin + it.row0 + half * BT);
+          tma_load_3d_w(smem_a + C::offStat2 + off, &tmStat2, BBAR(stat_full), pn * 64, it.head,
+                        it.stat_begin + it.row0 + half * BT);
         }
-    }
-    uint32_t slot = 0, ph = 1;   // ph: parity of the str_empty phase to wait for (first pass: the slots are free)
-    Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
-    for (int n = 0; n < n_steps; ++n) {
-      if (n >= C::kStages) mbar_wait_a(BBAR_I(str_empty, slot), ph);
-      tr.rec(1, n);
-      const uint32_t st = smem_a + C::offStr + slot * C::kStageBytes;
-      const int srow = str_begin + (first + n) * BT;
-      mbar_arrive_expect_tx_w(BBAR_I(str_full, slot), 2 * C::kStrTileBytes + (kDQ ? 0u : C::kStatsBytes));
+      for (int n = 0; n < it.n_steps; ++n, ++blk) {
+        if (blk >= C::kStages) mbar_wait_a(BBAR_I(str_empty, slot), ph);
+        tr.rec(1, blk);
+        const uint32_t st = smem_a + C::offStr + slot * C::kStageBytes;
+        const int srow = it.str_begin + (it.first + n) * BT;
+        mbar_arrive_expect_tx_w(BBAR_I(str_full, slot), 2 * C::kStrTileBytes + (kDQ ? 0u : C::kStatsBytes));
 #pragma unroll
-      for (int pn = 0; pn < C::kPanels; ++pn) {
-        tma_load_3d_w(st + pn * C::kStrPanelBytes, &tmStr1, BBAR_I(str_full, slot), pn * 64, head, srow);
-        tma_load_3d_w(st + C::kStrTileBytes + pn * C::kStrPanelBytes, &tmStr2, BBAR_I(str_full, slot), pn * 64, head, srow);
+        for (int pn = 0; pn < C::kPanels; ++pn) {
+          tma_load_3d_w(st + pn * C::kStrPanelBytes, &tmStr1, BBAR_I(str_full, slot), pn * 64, it.head, srow);
+          tma_load_3d_w(st + C::kStrTileBytes + pn * C::kStrPanelBytes, &tmStr2, BBAR_I(str_full, slot), pn * 64,
+                        it.head, srow);
+        }
+        if constexpr (!kDQ)
+          bulk_load_1d_w(st + 2 * C::kStrTileBytes,
+                         p.stats + (static_cast<int64_t>(it.bh) * (p.s_pad / 64) + (it.first + n)) * 128,
+                         C::kStatsBytes, BBAR_I(str_full, slot));
+        if (++slot == C::kStages) {
+          slot = 0;
+          ph ^= 1;
+        }
       }
-      if constexpr (!kDQ)
-        bulk_load_1d_w(st + 2 * C::kStrTileBytes,
-                       p.stats + (static_cast<int64_t>(bh) * (p.s_pad / 64) + (first + n)) * 128, C::kStatsBytes,
-                       BBAR_I(str_full, slot));
-      if (++slot == C::kStages) {
-        slot = 0;
-        ph ^= 1;
-      }
+      ++ic;
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
@@ -341,63 +382,73 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
       umma_commit_w(BBAR(t2_full));
     };
     uint32_t slot = 0, ph = 0;
+    uint32_t sc = 0, ic = 0;
     Tracer tr(p.trace, 1, blockIdx.x == 0 && lane == 0);
-    tr.rec(0, 0);
-    if (n_steps > 0) {
-      mbar_wait_a(BBAR(stat_full), 0);
-      mbar_wait_a(BBAR_I(str_full, 0), 0);
+    for (int ch = 0; ch < chunks; ++ch) {
+      const Item it = decode_item<kDQ>(p, ch, pos);
+      if (!it.valid || it.n_steps == 0) continue;
+      const int n_steps = it.n_steps;
+      tr.rec(0, ic);
+      mbar_wait_a(BBAR(stat_full), ic & 1);
+      mbar_wait_a(BBAR_I(str_full, slot), ph);
       tc_fence_after();
-      tr.rec(9, 0);
-      issue_t1(smem_a + C::offStr);
-      issue_t2(smem_a + C::offStr + C::kStrTileBytes);
-    }
-    for (int n = 0; n < n_steps; ++n) {
-      const uint32_t sB1 = smem_a + C::offStr + slot * C::kStageBytes;
-      const uint32_t sB2 = sB1 + C::kStrTileBytes;
-      uint32_t nslot = slot + 1, nph = ph;
-      if (nslot == C::kStages) {
-        nslot = 0;
-        nph ^= 1;
-      }
-      const uint32_t nB1 = smem_a + C::offStr + nslot * C::kStageBytes;
-      const bool more = n + 1 < n_steps;
-      // the next streaming tiles have normally landed long ago: probe now, the latency overlaps the hand-over wait
-      const bool next_ready = more ? mbar_test_a(BBAR_I(str_full, nslot), nph) : true;
-      // first half: X1 is in TMEM (keys own) / T1 has been read out (queries own)
-      mbar_spin_a(BBAR(x1_ready), n & 1);
-      tc_fence_after();
-      tr.rec(1, n);
-      // gradient products: A = X from TMEM (8 columns per K-step of 16 streaming rows; the two column halves of X sit at
-      // the start of the two halves of T, where their warpgroups wrote them), B = the streaming tile MN-major
-      if constexpr (!kDQ) {
+      tr.rec(9, ic);
+      // (T1 / T2 are free: their last readers, the previous item's final products, were issued by this thread)
+      issue_t1(smem_a + C::offStr + slot * C::kStageBytes);
+      issue_t2(smem_a + C::offStr + slot * C::kStageBytes + C::kStrTileBytes);
+      for (int n = 0; n < n_steps; ++n, ++sc) {
+        const uint32_t sB1 = smem_a + C::offStr + slot * C::kStageBytes;
+        const uint32_t sB2 = sB1 + C::kStrTileBytes;
+        uint32_t nslot = slot + 1, nph = ph;
+        if (nslot == C::kStages) {
+          nslot = 0;
+          nph ^= 1;
+        }
+        const uint32_t nB1 = smem_a + C::offStr + nslot * C::kStageBytes;
+        const bool more = n + 1 < n_steps;
+        // the next streaming tiles have normally landed long ago: probe now, the latency overlaps the hand-over wait
+        const bool next_ready = more ? mbar_test_a(BBAR_I(str_full, nslot), nph) : true;
+        // first half: X1 is in TMEM (keys own) / T1 has been read out (queries own)
+        mbar_spin_a(BBAR(x1_ready), sc & 1);
+        // the accumulators of the previous item must have been read out before the first products overwrite them
+        if (n == 0 && ic > 0) mbar_wait_a(BBAR(acc_free), (ic - 1) & 1);
+        tc_fence_after();
+        tr.rec(1, sc);
+        // gradient products: A = X from TMEM (8 columns per K-step of 16 streaming rows; the two column halves of X sit
+        // at the start of the two halves of T, where their warpgroups wrote them), B = the streaming tile MN-major
+        if constexpr (!kDQ) {
+#pragma unroll
+          for (int kk = 0; kk < BT / 16; ++kk)
+            umma_ts_w(tA1, tT1 + (kk >> 1) * 32 + (kk & 1) * 8,
+                      make_smem_desc_sw128(sB2 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
+                      (n > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (more) {
+          if (!next_ready) {
+            mbar_wait_a(BBAR_I(str_full, nslot), nph);
+            tc_fence_after();
+          }
+          issue_t1(nB1);   // executes behind the product above, which is the last reader of X1 (same issuing thread)
+        }
+        tr.rec(2, sc);
+        // second half: X2 is in TMEM
+        mbar_spin_a(BBAR(x2_ready), sc & 1);
+        tc_fence_after();
+        tr.rec(3, sc);
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
-          umma_ts_w(tA1, tT1 + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc_sw128(sB2 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
+          umma_ts_w(tA2, tT2 + (kk >> 1) * 32 + (kk & 1) * 8,
+                    make_smem_desc_sw128(sB1 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
                     (n > 0 || kk > 0) ? 1u : 0u);
+        umma_commit_w(BBAR_I(str_empty, slot));   // every product that reads this step's streaming tiles has been issued
+        if (more) issue_t2(nB1 + C::kStrTileBytes);
+        tr.rec(4, sc);
+        slot = nslot;
+        ph = nph;
       }
-      if (more) {
-        if (!next_ready) {
-          mbar_wait_a(BBAR_I(str_full, nslot), nph);
-          tc_fence_after();
-        }
-        issue_t1(nB1);   // executes behind the product above, which is the last reader of X1 (same issuing thread)
-      }
-      tr.rec(2, n);
-      // second half: X2 is in TMEM
-      mbar_spin_a(BBAR(x2_ready), n & 1);
-      tc_fence_after();
-      tr.rec(3, n);
-#pragma unroll
-      for (int kk = 0; kk < BT / 16; ++kk)
-        umma_ts_w(tA2, tT2 + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc_sw128(sB1 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
-                  (n > 0 || kk > 0) ? 1u : 0u);
-      umma_commit_w(BBAR_I(str_empty, slot));   // every product that reads this step's streaming tiles has been issued
-      if (more) issue_t2(nB1 + C::kStrTileBytes);
-      tr.rec(4, n);
-      slot = nslot;
-      ph = nph;
+      umma_commit_w(BBAR(acc_full));
+      ++ic;
     }
-    if (n_steps > 0) umma_commit_w(BBAR(acc_full));
   } else {
     // ===================== softmax / gradient warps =====================
     // Two warpgroups share the 128 rows: thread (quadrant, lane) of warpgroup g owns row r and the 32 streaming columns
@@ -406,190 +457,251 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     constexpr int HC = BT / 2;
     const int g = warp >> 2;
     const int r = (warp & 3) * 32 + lane;
-    const int row = row0 + r;
+    const int t256 = warp * 32 + lane;
     const int cbase = g * HC;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tT1 = tmem_base + lane_addr + C::colT1 + cbase, tT2 = tmem_base + lane_addr + C::colT2 + cbase;
     const float c2 = p.scale_log2;
-    float rowL = 0.f, rowD = 0.f;
-    if constexpr (kDQ) {
-      const float* blk = p.stats + (static_cast<int64_t>(bh) * (p.s_pad / 64) + (row >> 6)) * 128;
-      rowL = __ldg(blk + (row & 63));
-      rowD = __ldg(blk + 64 + (row & 63));
-    }
     uint32_t slot = 0, ph = 0;
+    uint32_t sc = 0, ic = 0;
     Tracer tr(p.trace, 2 + g, blockIdx.x == 0 && lane == 0 && (warp & 3) == 0);
-    for (int n = 0; n < n_steps; ++n) {
-      tr.rec(0, n);
-      const int col0 = (first + n) * BT + cbase;   // first streaming row of this thread's columns
-      const uint32_t sStats = smem_a + C::offStr + slot * C::kStageBytes + 2 * C::kStrTileBytes + cbase * 4;
-      // valid columns of this row inside the thread's half block: lo <= i < hi
-      int lo = 0, hi = len_str - col0;
-      bool partial = col0 + HC > len_str;
-      if (p.is_causal) {
-        if (kDQ) {
-          hi = min(hi, row + 1 - col0);
-          partial = partial || (col0 + HC - 1 > row0);
-        } else {
-          lo = row - col0;
-          partial = partial || (col0 < row0 + BS - 1);
-        }
+    bool store_pending = false;   // (thread 0) a bulk store may still be reading the staging tile
+    Item nxt = decode_item<kDQ>(p, 0, pos);
+    for (int ch = 0; ch < chunks; ++ch) {
+      const Item it = nxt;
+      // the next item is decoded one item ahead: its cu_seqlens loads complete behind this item's work
+      if (ch + 1 < chunks) nxt = decode_item<kDQ>(p, ch + 1, pos);
+      if (!it.valid) continue;
+      const int row0 = it.row0;
+      const int row = row0 + r;
+      const int len_str = it.len_str;
+      const int n_steps = it.n_steps;
+      float rowL = 0.f, rowD = 0.f;
+      if constexpr (kDQ) {
+        const float* blk = p.stats + (static_cast<int64_t>(it.bh) * (p.s_pad / 64) + (row >> 6)) * 128;
+        rowL = __ldg(blk + (row & 63));
+        rowD = __ldg(blk + 64 + (row & 63));
       }
-      // the statistics travel with the streaming tiles, which have landed before T1 could be computed: a probe whose
-      // latency overlaps the wait for T1 (a satisfied blocking wait costs ~200 cycles on its own)
-      bool stats_ready = true;
-      if constexpr (!kDQ) stats_ready = mbar_test_a(BBAR_I(str_full, slot), ph);
+      for (int n = 0; n < n_steps; ++n, ++sc) {
+        tr.rec(0, sc);
+        const int col0 = (it.first + n) * BT + cbase;   // first streaming row of this thread's columns
+        const uint32_t sStats = smem_a + C::offStr + slot * C::kStageBytes + 2 * C::kStrTileBytes + cbase * 4;
+        // valid columns of this row inside the thread's half block: lo <= i < hi
+        int lo = 0, hi = len_str - col0;
+        bool partial = col0 + HC > len_str;
+        if (p.is_causal) {
+          if (kDQ) {
+            hi = min(hi, row + 1 - col0);
+            partial = partial || (col0 + HC - 1 > row0);
+          } else {
+            lo = row - col0;
+            partial = partial || (col0 < row0 + BS - 1);
+          }
+        }
+        // the statistics travel with the streaming tiles, which have landed before T1 could be computed: a probe whose
+        // latency overlaps the wait for T1 (a satisfied blocking wait costs ~200 cycles on its own)
+        bool stats_ready = true;
+        if constexpr (!kDQ) stats_ready = mbar_test_a(BBAR_I(str_full, slot), ph);
 
-      // ---- first half: P = exp2(T1 * scale_log2 - L) ----
-      mbar_wait_a(BBAR(t1_full), n & 1);
-      const bool t2_ready = mbar_test_a(BBAR(t2_full), n & 1);   // consumed after the exponentials
-      if constexpr (!kDQ) {
-        if (!stats_ready) mbar_wait_a(BBAR_I(str_full, slot), ph);
-      }
-      tc_fence_after();
-      tr.rec(1, n);
-      float e[HC];
-      {
-        uint32_t us[HC];
-        tmem_ld32(tT1, us);
-        tmem_ld_wait();
-        tr.rec(2, n);
-        if constexpr (kDQ) {
-          tc_fence_before();
-          mbar_arrive_a(BBAR(x1_ready));   // T1 is in registers: the next S may overwrite it
-          const float negL = rowL;   // the workspace holds -lse * log2e
+        // ---- first half: P = exp2(T1 * scale_log2 - L) ----
+        mbar_wait_a(BBAR(t1_full), sc & 1);
+        const bool t2_ready = mbar_test_a(BBAR(t2_full), sc & 1);   // consumed after the exponentials
+        if constexpr (!kDQ) {
+          if (!stats_ready) mbar_wait_a(BBAR_I(str_full, slot), ph);
+        }
+        tc_fence_after();
+        tr.rec(1, sc);
+        float e[HC];
+        {
+          uint32_t us[HC];
+          tmem_ld32(tT1, us);
+          tmem_ld_wait();
+          tr.rec(2, sc);
+          if constexpr (kDQ) {
+            tc_fence_before();
+            mbar_arrive_a(BBAR(x1_ready));   // T1 is in registers: the next S may overwrite it
+            const float negL = rowL;   // the workspace holds -lse * log2e
 #pragma unroll
-          for (int i = 0; i < HC; i += 8) {
-            float t8[8], e8[8];
+            for (int i = 0; i < HC; i += 8) {
+              float t8[8], e8[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) t8[k] = __uint_as_float(us[i + k]);
-            exp2_scaled8<kPoly>(e8, t8, c2, negL);
+              for (int k = 0; k < 8; ++k) t8[k] = __uint_as_float(us[i + k]);
+              exp2_scaled8<kPoly>(e8, t8, c2, negL);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) e[i + k] = e8[k];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < HC; i += 4) {
-            const uint4 L = lds128(sStats + i * 4);   // -lse * log2e of four query columns (broadcast)
-            float a0, a1, a2, a3;
-            ffma2v(a0, a1, __uint_as_float(us[i]), __uint_as_float(us[i + 1]), c2, __uint_as_float(L.x), __uint_as_float(L.y));
-            ffma2v(a2, a3, __uint_as_float(us[i + 2]), __uint_as_float(us[i + 3]), c2, __uint_as_float(L.z), __uint_as_float(L.w));
-            a0 = fast_exp2(a0);
-            a1 = fast_exp2(a1);
-            if (kPoly == 4 || (kPoly == 2 && (i & 4))) {
-              exp2_poly_pair(a2, a3);   // this share of the exponentials runs on the FMA pipe
-            } else {
-              a2 = fast_exp2(a2);
-              a3 = fast_exp2(a3);
+              for (int k = 0; k < 8; ++k) e[i + k] = e8[k];
             }
-            e[i] = a0;
-            e[i + 1] = a1;
-            e[i + 2] = a2;
-            e[i + 3] = a3;
+          } else {
+#pragma unroll
+            for (int i = 0; i < HC; i += 4) {
+              const uint4 L = lds128(sStats + i * 4);   // -lse * log2e of four query columns (broadcast)
+              float a0, a1, a2, a3;
+              ffma2v(a0, a1, __uint_as_float(us[i]), __uint_as_float(us[i + 1]), c2, __uint_as_float(L.x),
+                     __uint_as_float(L.y));
+              ffma2v(a2, a3, __uint_as_float(us[i + 2]), __uint_as_float(us[i + 3]), c2, __uint_as_float(L.z),
+                     __uint_as_float(L.w));
+              a0 = fast_exp2(a0);
+              a1 = fast_exp2(a1);
+              if (kPoly == 4 || (kPoly == 2 && (i & 4))) {
+                exp2_poly_pair(a2, a3);   // this share of the exponentials runs on the FMA pipe
+              } else {
+                a2 = fast_exp2(a2);
+                a3 = fast_exp2(a3);
+              }
+              e[i] = a0;
+              e[i + 1] = a1;
+              e[i + 2] = a2;
+              e[i + 3] = a3;
+            }
           }
         }
-      }
-      if (partial) {
+        if (partial) {
 #pragma unroll
-        for (int i = 0; i < HC; ++i) e[i] = (i >= lo && i < hi) ? e[i] : 0.f;
-      }
-      tr.rec(3, n);
-      if constexpr (!kDQ) {
-        uint32_t pk[HC / 2];
+          for (int i = 0; i < HC; ++i) e[i] = (i >= lo && i < hi) ? e[i] : 0.f;
+        }
+        tr.rec(3, sc);
+        if constexpr (!kDQ) {
+          uint32_t pk[HC / 2];
 #pragma unroll
-        for (int i = 0; i < HC / 2; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
-        tmem_st16(tT1, pk);   // over the first half of the columns this thread has just read
+          for (int i = 0; i < HC / 2; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
+          tmem_st16(tT1, pk);   // over the first half of the columns this thread has just read
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive_a(BBAR(x1_ready));
+        }
+        tr.rec(4, sc);
+
+        // ---- second half: dS = P * (T2 - delta) ----
+        if (!t2_ready) mbar_wait_a(BBAR(t2_full), sc & 1);
+        tc_fence_after();
+        tr.rec(5, sc);
+        {
+          uint32_t ud[HC];
+          tmem_ld32(tT2, ud);
+          tmem_ld_wait();
+          if (partial) {
+            // masked columns may hold products with rows of a neighbouring sequence: select, never multiply by zero
+#pragma unroll
+            for (int i = 0; i < HC; ++i) ud[i] = (i >= lo && i < hi) ? ud[i] : 0u;
+          }
+          uint32_t pk[HC / 2];
+          if constexpr (kDQ) {
+#pragma unroll
+            for (int i = 0; i < HC / 2; ++i) {
+              float g0, g1;
+              mul_add2v(g0, g1, e[2 * i], e[2 * i + 1], __uint_as_float(ud[2 * i]), __uint_as_float(ud[2 * i + 1]), rowD,
+                        rowD);
+              pk[i] = pack2<kBF16>(g0, g1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < HC; i += 4) {
+              const uint4 D = lds128(sStats + 256 + i * 4);   // -delta of four query columns
+              float g0, g1, g2, g3;
+              mul_add2v(g0, g1, e[i], e[i + 1], __uint_as_float(ud[i]), __uint_as_float(ud[i + 1]),
+                        __uint_as_float(D.x), __uint_as_float(D.y));
+              mul_add2v(g2, g3, e[i + 2], e[i + 3], __uint_as_float(ud[i + 2]), __uint_as_float(ud[i + 3]),
+                        __uint_as_float(D.z), __uint_as_float(D.w));
+              pk[i / 2] = pack2<kBF16>(g0, g1);
+              pk[i / 2 + 1] = pack2<kBF16>(g2, g3);
+            }
+          }
+          tmem_st16(tT2, pk);
+        }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive_a(BBAR(x1_ready));
-      }
-      tr.rec(4, n);
-
-      // ---- second half: dS = P * (T2 - delta) ----
-      if (!t2_ready) mbar_wait_a(BBAR(t2_full), n & 1);
-      tc_fence_after();
-      tr.rec(5, n);
-      {
-        uint32_t ud[HC];
-        tmem_ld32(tT2, ud);
-        tmem_ld_wait();
-        if (partial) {
-          // masked columns may hold products with rows of a neighbouring sequence: select, never multiply by zero
-#pragma unroll
-          for (int i = 0; i < HC; ++i) ud[i] = (i >= lo && i < hi) ? ud[i] : 0u;
+        mbar_arrive_a(BBAR(x2_ready));
+        tr.rec(7, sc);
+        if (++slot == C::kStages) {
+          slot = 0;
+          ph ^= 1;
         }
-        uint32_t pk[HC / 2];
-        if constexpr (kDQ) {
+      }
+
+      // ---- epilogue: accumulators -> staging tile in shared memory -> global ----
+      // Thread (row r, warpgroup g) owns columns [g DP/2, (g+1) DP/2) of its accumulator row; a thread-per-row store would
+      // touch 32 different lines per instruction (the first version spent ~3700 cycles per tile on it).  The tile is
+      // staged in the layout TMA expects ([64-column panel][128 rows][128 B], 16-byte chunks XOR-swizzled by the row) and
+      // leaves as one bulk tensor store per panel; a tile that ends inside its sequence (the next sequence's rows follow
+      // in memory) is written by all 256 threads with guarded 16-byte stores, every warp instruction covering whole rows.
+      if (n_steps > 0) {
+        mbar_wait_a(BBAR(acc_full), ic & 1);
+        tc_fence_after();
+      }
+      tr.rec(8, ic);
+      constexpr int kChunks = DP / 8;                 // 16-byte chunks per row
+      const uint32_t sStage = smem_a + C::offStage;
+      const bool full_tile = row0 + BS <= it.len_stat;
+      auto stage_addr = [&](int rr, uint32_t chunk) {
+        return sStage + (chunk >> 3) * (BS * 128) + rr * 128 + (((chunk ^ rr) & 7u) << 4);
+      };
+      auto store_acc = [&](uint32_t col, const CUtensorMap* tm, void* out, int64_t row_stride, int64_t head_stride,
+                           float mult, bool last) {
+        if (store_pending) {   // thread 0 only: the previous bulk store has read the staging tile
+          tma_store_wait_read<0>();
+          store_pending = false;
+        }
+        uint32_t o[DP / 64][32];
 #pragma unroll
-          for (int i = 0; i < HC / 2; ++i) {
-            float g0, g1;
-            mul_add2v(g0, g1, e[2 * i], e[2 * i + 1], __uint_as_float(ud[2 * i]), __uint_as_float(ud[2 * i + 1]), rowD, rowD);
-            pk[i] = pack2<kBF16>(g0, g1);
+        for (int cc = 0; cc < DP / 64; ++cc) {
+          if (n_steps > 0) {
+            tmem_ld32(tmem_base + lane_addr + col + (g * (DP / 64) + cc) * 32, o[cc]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[cc][i] = 0u;
+          }
+        }
+        if (n_steps > 0) tmem_ld_wait();
+        if (last && n_steps > 0) {
+          // both accumulators are in registers: the next item's products may overwrite them
+          tc_fence_before();
+          mbar_arrive_a(BBAR(acc_free));
+        }
+        named_bar_sync(1, 256);   // (thread 0 has waited for the previous store) the staging tile is free
+#pragma unroll
+        for (int cc = 0; cc < DP / 64; ++cc) {
+          const int c = g * (DP / 64) + cc;           // 32-column group of this thread
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(stage_addr(r, static_cast<uint32_t>(c * 4 + q)),
+                   pack2<kBF16>(__uint_as_float(o[cc][q * 8 + 0]) * mult, __uint_as_float(o[cc][q * 8 + 1]) * mult),
+                   pack2<kBF16>(__uint_as_float(o[cc][q * 8 + 2]) * mult, __uint_as_float(o[cc][q * 8 + 3]) * mult),
+                   pack2<kBF16>(__uint_as_float(o[cc][q * 8 + 4]) * mult, __uint_as_float(o[cc][q * 8 + 5]) * mult),
+                   pack2<kBF16>(__uint_as_float(o[cc][q * 8 + 6]) * mult, __uint_as_float(o[cc][q * 8 + 7]) * mult));
+        }
+        tr.rec(10, ic);
+        if (full_tile) {
+          fence_proxy_async_smem();   // staged rows -> visible to the bulk store
+          named_bar_sync(1, 256);
+          if (t256 == 0) {
+#pragma unroll
+            for (int pn = 0; pn < C::kPanels; ++pn)
+              tma_store_3d(tm, sStage + pn * (BS * 128), pn * 64, it.head, it.stat_begin + row0);
+            tma_store_commit();
+            store_pending = true;
           }
         } else {
+          named_bar_sync(1, 256);
+          uint8_t* obase = reinterpret_cast<uint8_t*>(out) +
+                           2 * (static_cast<int64_t>(it.stat_begin + row0) * row_stride + it.head * head_stride);
 #pragma unroll
-          for (int i = 0; i < HC; i += 4) {
-            const uint4 D = lds128(sStats + 256 + i * 4);   // -delta of four query columns
-            float g0, g1, g2, g3;
-            mul_add2v(g0, g1, e[i], e[i + 1], __uint_as_float(ud[i]), __uint_as_float(ud[i + 1]), __uint_as_float(D.x),
-                      __uint_as_float(D.y));
-            mul_add2v(g2, g3, e[i + 2], e[i + 3], __uint_as_float(ud[i + 2]), __uint_as_float(ud[i + 3]),
-                      __uint_as_float(D.z), __uint_as_float(D.w));
-            pk[i / 2] = pack2<kBF16>(g0, g1);
-            pk[i / 2 + 1] = pack2<kBF16>(g2, g3);
-          }
-        }
-        tmem_st16(tT2, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive_a(BBAR(x2_ready));
-      tr.rec(7, n);
-      if (++slot == C::kStages) {
-        slot = 0;
-        ph ^= 1;
-      }
-    }
-
-    // ---- epilogue: accumulators -> global (a thread stores its warpgroup's half of the columns of its row) ----
-    if (n_steps > 0) {
-      mbar_wait_a(BBAR(acc_full), 0);
-      tc_fence_after();
-    }
-    tr.rec(8, 0);
-    const bool valid = row < len_stat;
-    auto store_acc = [&](uint32_t col, void* out, int64_t row_stride, int64_t head_stride, float mult) {
-      uint8_t* orow = reinterpret_cast<uint8_t*>(out) +
-                      2 * (static_cast<int64_t>(stat_begin + row) * row_stride + head * head_stride);
-#pragma unroll
-      for (int cc = 0; cc < DP / 64; ++cc) {
-        const int c = g * (DP / 64) + cc;
-        uint32_t o[32];
-        if (n_steps > 0) {
-          tmem_ld32(tmem_base + lane_addr + col + c * 32, o);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0u;
-        }
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (c * 32 + q * 8 < p.headdim) {
-              uint4 v;
-              v.x = pack2<kBF16>(__uint_as_float(o[q * 8 + 0]) * mult, __uint_as_float(o[q * 8 + 1]) * mult);
-              v.y = pack2<kBF16>(__uint_as_float(o[q * 8 + 2]) * mult, __uint_as_float(o[q * 8 + 3]) * mult);
-              v.z = pack2<kBF16>(__uint_as_float(o[q * 8 + 4]) * mult, __uint_as_float(o[q * 8 + 5]) * mult);
-              v.w = pack2<kBF16>(__uint_as_float(o[q * 8 + 6]) * mult, __uint_as_float(o[q * 8 + 7]) * mult);
-              *reinterpret_cast<uint4*>(orow + (c * 32 + q * 8) * 2) = v;
+          for (int k = 0; k < BS * kChunks / 256; ++k) {
+            const int idx = k * 256 + t256;
+            const int rr = idx / kChunks;
+            const uint32_t chunk = static_cast<uint32_t>(idx % kChunks);
+            if (row0 + rr < it.len_stat && static_cast<int>(chunk) * 8 < p.headdim) {
+              const uint4 v = lds128(stage_addr(rr, chunk));
+              *reinterpret_cast<uint4*>(obase + 2 * (static_cast<int64_t>(rr) * row_stride + chunk * 8)) = v;
             }
           }
         }
-      }
-    };
-    if constexpr (!kDQ) store_acc(C::colA1, p.out1, p.o1_row_stride, p.o1_head_stride, 1.f);
-    store_acc(C::colA2, p.out2, p.o2_row_stride, p.o2_head_stride, p.scale);
-    tr.rec(9, 0);
+        tr.rec(11, ic);
+      };
+      if constexpr (!kDQ) store_acc(C::colA1, &tmOut1, p.out1, p.o1_row_stride, p.o1_head_stride, 1.f, false);
+      store_acc(C::colA2, &tmOut2, p.out2, p.o2_row_stride, p.o2_head_stride, p.scale, true);
+      tr.rec(9, ic);
+      if (n_steps > 0) ++ic;
+    }
+    if (store_pending) tma_store_wait_all();   // shared memory must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -603,14 +715,22 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     rec[0] = cta_t0;
     rec[1] = global_timer_ns();
     rec[2] = smid;
-    rec[3] = static_cast<uint64_t>(n_steps);
+    rec[3] = 0;
   }
 #endif
 }
 
+// (batch, head) pairs per scheduling chunk: chunk_bh * num_tiles CTAs = one resident wave
+inline int chunk_bh_for(int dp, int sms, int num_tiles, int total_bh) {
+  const int resident = (dp == 64 ? 2 : 1) * sms;
+  int c = resident / num_tiles;
+  if (c < 1) c = 1;
+  return c < total_bh ? c : total_bh;
+}
+
 template <int DP, bool kDQ, bool kBF16>
-int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, const CUtensorMap& b2, const Params& p,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, const CUtensorMap& b2,
+           const CUtensorMap& o1, const CUtensorMap& o2, const Params& p, cudaStream_t stream) {
   using C = Cfg<DP, kDQ>;
   auto kern = fmha_bwd_kernel<DP, kDQ, kBF16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -618,11 +738,10 @@ int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, 
     cudaGetLastError();
     return fail(BP_ERR_CUDA, "bp_fmha_bwd: cudaFuncSetAttribute(%u B smem): %s", C::kSmemBytes, cudaGetErrorString(e));
   }
+  // one CTA per position of a scheduling chunk (see decode_item): a single wave that walks all chunks
   const int total_bh = p.batch * p.nheads;
-  const int chunks = (total_bh + p.chunk_bh - 1) / p.chunk_bh;
-  const int64_t grid = static_cast<int64_t>(chunks) * p.chunk_bh * p.num_tiles;
-  if (grid > 0x7fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: too many work items");
-  kern<<<static_cast<unsigned>(grid), C::kThreads, C::kSmemBytes, stream>>>(s1, s2, b1, b2, p);
+  const int64_t grid = static_cast<int64_t>(p.chunk_bh < total_bh ? p.chunk_bh : total_bh) * p.num_tiles;
+  kern<<<static_cast<unsigned>(grid), C::kThreads, C::kSmemBytes, stream>>>(s1, s2, b1, b2, o1, o2, p);
   return check_launch(kDQ ? "bp_fmha_bwd (dQ) launch" : "bp_fmha_bwd (dK, dV) launch");
 }
 
@@ -685,7 +804,7 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
     if (int rc = check_launch("bp_fmha_bwd (row statistics) launch")) return rc;
   }
 
-  CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV;
   {
     const uint32_t box[3] = {64, 1, (uint32_t)fmha_bwd::BT};
     const uint64_t dq_[3] = {(uint64_t)headdim, (uint64_t)nheads, (uint64_t)total_q};
@@ -698,6 +817,14 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
     if (int rc = encode_tensor_map(&tmK, dtype, 3, k, dk_, sk, box, true)) return rc;
     if (int rc = encode_tensor_map(&tmV, dtype, 3, v, dk_, sv, box, true)) return rc;
     if (int rc = encode_tensor_map(&tmDO, dtype, 3, dout, dq_, sdo, box, true)) return rc;
+    // gradient tiles leave through bulk stores of whole stationary tiles (128 rows x one 64-column panel)
+    const uint32_t obox[3] = {64, 1, (uint32_t)fmha_bwd::BS};
+    const uint64_t sdq[2] = {(uint64_t)s_dq[1] * 2, (uint64_t)s_dq[0] * 2};
+    const uint64_t sdk[2] = {(uint64_t)s_dk[1] * 2, (uint64_t)s_dk[0] * 2};
+    const uint64_t sdv[2] = {(uint64_t)s_dv[1] * 2, (uint64_t)s_dv[0] * 2};
+    if (int rc = encode_tensor_map(&tmDQ, dtype, 3, dq, dq_, sdq, obox, true)) return rc;
+    if (int rc = encode_tensor_map(&tmDK, dtype, 3, dk, dk_, sdk, obox, true)) return rc;
+    if (int rc = encode_tensor_map(&tmDV, dtype, 3, dv, dk_, sdv, obox, true)) return rc;
   }
   fmha_bwd::Params p;
   p.stats = stats;
@@ -720,7 +847,7 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
 
   // keys own: dK, dV
   p.num_tiles = (max_seqlen_k + fmha_bwd::BS - 1) / fmha_bwd::BS;
-  p.chunk_bh = (2 * sms) / p.num_tiles > 0 ? (2 * sms) / p.num_tiles : 1;
+  p.chunk_bh = fmha_bwd::chunk_bh_for(DP, sms, p.num_tiles, batch * nheads);
   p.out1 = dv;
   p.o1_row_stride = s_dv[0];
   p.o1_head_stride = s_dv[1];
@@ -732,16 +859,16 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
 #endif
   int rc;
   if (DP == 64)
-    rc = bf16 ? fmha_bwd::launch<64, false, true>(tmK, tmV, tmQ, tmDO, p, st)
-              : fmha_bwd::launch<64, false, false>(tmK, tmV, tmQ, tmDO, p, st);
+    rc = bf16 ? fmha_bwd::launch<64, false, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st)
+              : fmha_bwd::launch<64, false, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st);
   else
-    rc = bf16 ? fmha_bwd::launch<128, false, true>(tmK, tmV, tmQ, tmDO, p, st)
-              : fmha_bwd::launch<128, false, false>(tmK, tmV, tmQ, tmDO, p, st);
+    rc = bf16 ? fmha_bwd::launch<128, false, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st)
+              : fmha_bwd::launch<128, false, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st);
   if (rc) return rc;
 
   // queries own: dQ
   p.num_tiles = (max_seqlen_q + fmha_bwd::BS - 1) / fmha_bwd::BS;
-  p.chunk_bh = (2 * sms) / p.num_tiles > 0 ? (2 * sms) / p.num_tiles : 1;
+  p.chunk_bh = fmha_bwd::chunk_bh_for(DP, sms, p.num_tiles, batch * nheads);
 #ifdef BP_TRACE
   p.trace = (trace_mode && trace_mode[0] == 'd' && trace_mode[1] == 'q') ? g_trace : nullptr;
 #endif
@@ -750,10 +877,10 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   p.o2_row_stride = s_dq[0];
   p.o2_head_stride = s_dq[1];
   if (DP == 64)
-    rc = bf16 ? fmha_bwd::launch<64, true, true>(tmQ, tmDO, tmK, tmV, p, st)
-              : fmha_bwd::launch<64, true, false>(tmQ, tmDO, tmK, tmV, p, st);
+    rc = bf16 ? fmha_bwd::launch<64, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st)
+              : fmha_bwd::launch<64, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st);
   else
-    rc = bf16 ? fmha_bwd::launch<128, true, true>(tmQ, tmDO, tmK, tmV, p, st)
-              : fmha_bwd::launch<128, true, false>(tmQ, tmDO, tmK, tmV, p, st);
+    rc = bf16 ? fmha_bwd::launch<128, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st)
+              : fmha_bwd::launch<128, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st);
   return rc;
 }
