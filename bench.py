@@ -20,6 +20,7 @@ N > 1 is launched by torchrun (one process per GPU); the batch is sharded with n
   own_kernel_share  time inside kernels of libbackpack_b200.so / step time;
   variants.sense_table  the serving configuration (`serving_config()`: sense vectors gathered inside the sense-mix
              kernel from a precomputed (vocab, nv, d) table instead of running the content model per token);
+  variants.training_step  forward + backward (SURVEY.md §8f rank 4) with the backward operators of this library timed;
   cpu_baseline  the oracle port of the reference's pure-PyTorch path on the host cores (bounded sample).
 Per-kernel durations come from CUDA events recorded on the launching stream around every C-ABI call during an eager
 pass of the same K steps (events cannot be recorded inside a graph replay), against the measured peaks.
@@ -385,6 +386,41 @@ def run_ours(args):
                 fl_dt = timed_steps(lambda: model.loss(ids_dev, labels), kk, parallel, dev)
             fused_loss = {"dt": fl_dt, "steps": kk, "stats_ms": loss_timer.mean_ms()}
 
+    # ---- variant: a training step (forward + backward with a next-token cross-entropy), SURVEY.md §8f rank 4.  Outside
+    #      inference mode, smaller batch (the activations of 12 layers are kept), dropouts 0 (not implemented) ----
+    training = None
+    if args.training_steps > 0:
+        tb = min(B, args.training_batch)
+        tcfg = flash_config(**{**SMALL, "n_positions": max(1024, S), "resid_pdrop": 0.0, "embd_pdrop": 0.0,
+                               "attn_pdrop": 0.0})
+        tmodel = BackpackLMHeadModel(tcfg).to(dev, torch.bfloat16).train()
+        tmodel.load_state_dict(model.state_dict())
+        del model
+        torch.cuda.empty_cache()
+        tids = ids_dev[:tb]
+
+        def train_step():
+            tmodel.zero_grad(set_to_none=True)
+            logits = tmodel(tids).logits
+            loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(),
+                                                     tids[:, 1:].reshape(-1))
+            loss.backward()
+            return loss
+
+        for _ in range(2):
+            train_step()
+        bwd_names = ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_fwd", "bp_ln_residual_bwd", "bp_bias_act_bwd",
+                     "bp_linear_bias_act_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd")
+        tt = {n: _lib.KernelTimer(n) for n in bwd_names}
+        for t in tt.values():
+            t.__enter__()
+        tr_dt = timed_steps(train_step, args.training_steps, parallel, dev)
+        for t in reversed(list(tt.values())):
+            t.__exit__(None, None, None)
+        training = {"dt": tr_dt, "steps": args.training_steps, "batch": tb,
+                    "kernels": {n: (len(t.events) / args.training_steps, t.mean_ms()) for n, t in tt.items() if t.events}}
+        del tmodel
+
     if rank != 0:
         return
     peaks = load_peaks()
@@ -539,6 +575,28 @@ def run_ours(args):
                     "bp_lm_head_stats_fwd (log-sum-exp, arg-max and target logit per row in the GEMM epilogue; no "
                     "(b, s, vocab) tensor), eager launches.  What perplexity evaluation needs; a different result than "
                     "`value` (per-token loss instead of logits), hence a variant"}
+    if training is not None:
+        tb, tms = training["batch"], training["dt"] / training["steps"] * 1e3
+        tk = training["kernels"]
+        fb_flops = 2.5 * 4 * tb * h * S * S * dh / 2
+        line["variants"]["training_step"] = {
+            "value": tb * S * world / (tms * 1e-3), "unit": "tokens/s", "ms_per_step": tms, "steps": training["steps"],
+            "batch_per_gpu": tb,
+            "kernels": {n: {"calls_per_step": c, "ms_per_call": ms, "ms_per_step": c * ms} for n, (c, ms) in tk.items()},
+            "fmha_bwd": {"kernel": "bp_fmha_bwd: bwd_stats_kernel + fmha_bwd_kernel<64, keys own> + fmha_bwd_kernel<64, "
+                                   "queries own> (three launches per call)",
+                         "ms_per_call": tk["bp_fmha_bwd"][1],
+                         "tflops": fb_flops / (tk["bp_fmha_bwd"][1] * 1e-3) / 1e12,
+                         "frac": fb_flops / (tk["bp_fmha_bwd"][1] * 1e-3) / 1e12 / peak_tf,
+                         "flops_convention": "2.5 x the forward (five tile products against two); the two kernels execute "
+                                             "seven (S and dP are recomputed in both)"},
+            "ln_residual_bwd": {"ms_per_call": tk["bp_ln_residual_bwd"][1],
+                                "hbm_frac": tb * S * d * 16 / (tk["bp_ln_residual_bwd"][1] * 1e-3) / 1e9 / peak_hbm},
+            "note": "forward + backward of the same model in train mode (dropouts 0), next-token cross-entropy on fp32 "
+                    "logits, eager launches, no optimizer step: attention backward = bp_fmha_bwd, LayerNorm backward = "
+                    "bp_ln_residual_bwd, dgelu + bias gradients = bp_bias_act_bwd, dgrad GEMMs = this library's GEMM, wgrad "
+                    "GEMMs and the recomputed sense-mix backward = cuBLAS through PyTorch.  A variant: the headline "
+                    "metric is the forward"}
     print(json.dumps(line), flush=True)
 
 
@@ -558,6 +616,8 @@ def main():
                     help="skip the variant that runs the plain linears on cuBLAS")
     ap.add_argument("--fused-loss-steps", type=int, default=30,
                     help="steps of the evaluation-loss variant (0 = skip)")
+    ap.add_argument("--training-steps", type=int, default=5, help="steps of the training-step variant (0 = skip)")
+    ap.add_argument("--training-batch", type=int, default=16, help="sequences per GPU in the training-step variant")
     ap.add_argument("--full-logits-steps", type=int, default=3,
                     help="steps of the whole-logits-to-host loop (0 = skip; single GPU only)")
     args = ap.parse_args()
