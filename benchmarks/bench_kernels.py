@@ -287,7 +287,14 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="fmha,sense,ln,gemm")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--shape", default="", help="b,s,h,d for the attention benchmarks (default: BASELINE config 2)")
+    ap.add_argument("--no-comparators", action="store_true")
     a = ap.parse_args()
     for w in a.which.split(","):
-        {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms,
-         "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops}[w](a.iters)
+        fn = {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms,
+              "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops}[w]
+        if w in ("fmha", "fmha_bwd") and (a.shape or a.no_comparators):
+            b, s_, h, d = (int(x) for x in a.shape.split(",")) if a.shape else (32, 1024, 12, 64)
+            fn(a.iters, b=b, s=s_, h=h, d=d, comparators=not a.no_comparators)
+        else:
+            fn(a.iters)

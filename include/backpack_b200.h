@@ -1,13 +1,15 @@
 /* backpack_b200.h -- C ABI of libbackpack_b200.so
  *
- * The drop-in boundary for the Backpack forward hot path on B200 (sm_100a).  These entry points
- * replace, for the forward pass, the four pybind11 extensions the reference's Python op wrappers
- * import (paths relative to the reference repository):
+ * The drop-in boundary for the Backpack hot path on B200 (sm_100a).  These entry points replace the four
+ * pybind11 extensions the reference's Python op wrappers import (paths relative to the reference repository):
  *
  *   flash_attn_cuda.fwd                       csrc/flash_attn/fmha_api.cpp:189-325      -> bp_fmha_fwd
  *   dropout_layer_norm.dropout_add_ln_fwd     csrc/layer_norm/ln_api.cpp:83-251         -> bp_ln_residual_fwd
  *   fused_dense_lib.linear_gelu_forward       csrc/fused_dense_lib/fused_dense.cpp:88-142 -> bp_linear_bias_act_fwd
  *   rotary_emb.apply_rotary                   csrc/rotary/rotary.cpp:12-33              -> bp_rotary_qk_inplace
+ *   flash_attn_cuda.bwd                       csrc/flash_attn/fmha_api.cpp:338-500      -> bp_fmha_bwd
+ *   dropout_layer_norm.dropout_add_ln_bwd     csrc/layer_norm/ln_api.cpp:255-440        -> bp_ln_residual_bwd
+ *   fused_dense_lib backward epilogues        csrc/fused_dense_lib/fused_dense_cuda.cu:559-787 -> bp_bias_act_bwd
  *   (no reference kernel; eager PyTorch at    training/src/models/backpack.py:111-122,313) -> bp_sense_lse_fwd,
  *                                                                                            bp_sense_mix_fwd,
  *                                                                                            bp_sense_mix_table_fwd
