@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -26,6 +26,12 @@ SIGNATURES = {
     "bp_last_error": [],
     "bp_check_device": [],
     "bp_fmha_fwd": [c_void_p] * 7 + [c_int32] * 7 + [c_int64] * 8 + [c_int32, c_float, c_int32, c_int32, c_void_p],
+    "bp_fmha_fwd_dropout_workspace_bytes": [c_int32, c_int32, c_int32],
+    "bp_fmha_fwd_dropout": [c_void_p] * 7 + [c_int32] * 7 + [c_int64] * 8 + [c_int32, c_float, c_int32, c_int32, c_float,
+                                                                            c_uint64, c_void_p, c_int64, c_void_p],
+    "bp_fmha_bwd_dropout_workspace_bytes": [c_int32, c_int32, c_int32, c_int32],
+    "bp_fmha_bwd_dropout": [c_void_p] * 11 + [c_int32] * 7 + [c_void_p, c_int32, c_float, c_int32, c_int32, c_float,
+                                                               c_uint64, c_void_p, c_int64, c_void_p],
     "bp_fmha_bwd_workspace_bytes": [c_int32, c_int32, c_int32],
     "bp_fmha_bwd": [c_void_p] * 11 + [c_int32] * 7 + [c_void_p, c_int32, c_float, c_int32, c_int32, c_void_p, c_int64,
                                                        c_void_p],
@@ -46,6 +52,7 @@ SIGNATURES = {
     "bp_rotary_qk_inplace": [c_void_p] * 5 + [c_int32] * 6 + [c_void_p],
 }
 _RESTYPES = {"bp_last_error": c_char_p, "bp_fmha_bwd_workspace_bytes": c_int64,
+             "bp_fmha_fwd_dropout_workspace_bytes": c_int64, "bp_fmha_bwd_dropout_workspace_bytes": c_int64,
              "bp_ln_bwd_workspace_bytes": c_int64, "bp_bias_act_bwd_workspace_bytes": c_int64}
 
 _lib = None

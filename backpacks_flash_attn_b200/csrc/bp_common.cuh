@@ -130,6 +130,32 @@ __device__ __forceinline__ void exp2_scaled8(float (&e)[8], const float* s, floa
 }
 
 // ------------------------------------------------------------------------------------------
+// attention dropout: a counter-based keep mask that every kernel (forward, both backward modes) can regenerate.
+//   base = mix32(seed_lo ^ mix32(seed_hi + bh));  R[q] = mix32(base + q * 0x9E3779B1);  C[k] = mix32(~base + k * 0x85EBCA77)
+//   keep(q, k) = ((R[q] ^ C[k]) * 0x2C1B3C6D) >= (thr << 24),  thr = round(256 p)  =>  P(drop) = thr / 256
+// One word per query row and one per key column, so a thread holds its row's (or key's) word in a register and pays
+// XOR + IMAD + compare per element whichever of the two its TMEM lane stands for.  (The reference draws Philox numbers
+// per thread of ITS tiling, fmha/softmax.h; only the distribution is part of the contract.)  The Python side
+// (flash_attn_interface.attention_dropout_mask) restates these lines for the tests.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_base(uint64_t seed, uint32_t bh) {
+  return mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(seed >> 32) + bh));
+}
+__host__ __device__ __forceinline__ uint32_t drop_row_word(uint32_t base, uint32_t q) { return mix32(base + q * 0x9E3779B1u); }
+__host__ __device__ __forceinline__ uint32_t drop_col_word(uint32_t base, uint32_t k) { return mix32(~base + k * 0x85EBCA77u); }
+__device__ __forceinline__ bool drop_keep(uint32_t rw, uint32_t cw, uint32_t thr24) {
+  return ((rw ^ cw) * 0x2C1B3C6Du) >= thr24;
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -44,6 +44,7 @@ namespace fmha_bwd {
 
 constexpr int BS = 128;   // stationary rows per CTA (= TMEM lanes)
 constexpr int BT = 64;    // streaming rows per step
+constexpr int kStatsWords = 3 * BT;   // words per 64-row block of the statistics workspace
 constexpr float kLog2e = 1.4426950408889634f;
 #ifndef BP_FMHA_BWD_POLY
 #define BP_FMHA_BWD_POLY 2
@@ -60,7 +61,7 @@ struct Cfg {
   static constexpr uint32_t kStrPanelBytes = BT * 128;
   static constexpr uint32_t kStatTileBytes = kPanels * kStatPanelBytes;
   static constexpr uint32_t kStrTileBytes = kPanels * kStrPanelBytes;
-  static constexpr uint32_t kStatsBytes = BT * 8;   // {lse * log2e, delta} of the streaming rows (keys-own mode)
+  static constexpr uint32_t kStatsBytes = BT * 12;  // -lse * log2e, -delta and the dropout row word of the streaming rows
   static constexpr uint32_t kStageBytes = 2 * kStrTileBytes + 1024;
   static constexpr uint32_t offStat1 = 0;
   static constexpr uint32_t offStat2 = kStatTileBytes;
@@ -78,7 +79,12 @@ struct Cfg {
 };
 
 struct Params {
-  const float* stats;        // (batch * nheads, s_pad / 64, 2, 64): -lse * log2e, then -delta, per block of 64 query rows
+  const float* stats;        // (batch * nheads, s_pad / 64, 3, 64): -lse * log2e, -delta, dropout row word per block of 64
+                             // query rows
+  const uint32_t* drop_c;    // (batch * nheads, s_pad_k) dropout column words (null without dropout)
+  int32_t s_pad_k;
+  uint32_t drop_thr24;       // round(256 p) << 24
+  float drop_scale;          // 1 / (1 - p)
   void* out1;                // keys-own: dV
   void* out2;                // keys-own: dK, queries-own: dQ (both scaled by the softmax scale)
   int64_t o1_row_stride, o1_head_stride, o2_row_stride, o2_head_stride;
@@ -117,11 +123,12 @@ __device__ __forceinline__ void mul_add2v(float& d0, float& d1, float e0, float 
       : "=f"(d0), "=f"(d1) : "f"(e0), "f"(e1), "f"(x0), "f"(x1), "f"(n0), "f"(n1));
 }
 
-// Spinning wait on test_wait for the MMA issuer: the suspending try_wait of mbar_wait_a wakes up several hundred cycles
-// after the phase completes, and the issuer's two hand-over waits sit on the critical path of every step.  Bounded like
-// mbar_wait_a (traps after 4 s).
+// Optional spinning wait on test_wait for the MMA issuer's two hand-over waits (-DBP_FMHA_BWD_SPIN=1).  The suspending
+// try_wait of mbar_wait_a wakes up a few hundred cycles after the phase completes; spinning shortens that but takes
+// issue slots from the softmax warps of the same sub-partition.  Measured at config 2: 309.5 us spinning, 306.7 us
+// suspending -- the suspending wait is the default.  Bounded like mbar_wait_a (traps after 4 s).
 #ifndef BP_FMHA_BWD_SPIN
-#define BP_FMHA_BWD_SPIN 1
+#define BP_FMHA_BWD_SPIN 0
 #endif
 __device__ __forceinline__ void mbar_spin_a(uint32_t bar, uint32_t parity) {
   if (!BP_FMHA_BWD_SPIN) {
@@ -155,7 +162,8 @@ template <bool kBF16>
 __global__ void __launch_bounds__(256)
 bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, const float* __restrict__ lse,
                  float* __restrict__ stats, const int32_t* __restrict__ cu_q, int64_t do_row, int64_t do_head,
-                 int64_t o_row, int64_t o_head, int32_t lse_stride, int32_t s_pad, int32_t nheads, int32_t headdim) {
+                 int64_t o_row, int64_t o_head, int32_t lse_stride, int32_t s_pad, int32_t nheads, int32_t headdim,
+                 uint64_t seed) {
   // One CTA = one block of 64 query rows of one (batch, head).  16 lanes per row (8 elements = 16 bytes each), a warp
   // covers 8 rows in 4 passes whose loads are all issued before the first use.
   const int bh = blockIdx.x;
@@ -179,7 +187,8 @@ bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, co
           reinterpret_cast<const uint16_t*>(out) + static_cast<int64_t>(q_begin + i) * o_row + h * o_head + q * 8));
     }
   }
-  float* blk = stats + (static_cast<int64_t>(bh) * (s_pad / 64) + blockIdx.y) * 128;
+  float* blk = stats + (static_cast<int64_t>(bh) * (s_pad / 64) + blockIdx.y) * kStatsWords;
+  const uint32_t dbase = drop_base(seed, static_cast<uint32_t>(bh));
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const uint32_t aw[4] = {a[it].x, a[it].y, a[it].z, a[it].w}, cw[4] = {c[it].x, c[it].y, c[it].z, c[it].w};
@@ -204,6 +213,7 @@ bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, co
       const bool valid = i < len_q;
       blk[rows[it]] = valid ? -__ldg(lse + static_cast<int64_t>(bh) * lse_stride + i) * kLog2e : -INFINITY;
       blk[64 + rows[it]] = valid ? -acc : 0.f;
+      blk[128 + rows[it]] = __uint_as_float(drop_row_word(dbase, static_cast<uint32_t>(i)));
     }
   }
 }
@@ -257,7 +267,7 @@ __device__ __forceinline__ Item decode_item(const Params& p, int chunk, int pos)
   return it;
 }
 
-template <int DP, bool kDQ, bool kBF16>
+template <int DP, bool kDQ, bool kBF16, bool kDrop>
 __global__ void __launch_bounds__(Cfg<DP, kDQ>::kThreads, Cfg<DP, kDQ>::kCtasPerSm)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_constant__ CUtensorMap tmStat2,
                 const __grid_constant__ CUtensorMap tmStr1, const __grid_constant__ CUtensorMap tmStr2,
@@ -347,7 +357,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         }
         if constexpr (!kDQ)
           bulk_load_1d_w(st + 2 * C::kStrTileBytes,
-                         p.stats + (static_cast<int64_t>(it.bh) * (p.s_pad / 64) + (it.first + n)) * 128,
+                         p.stats + (static_cast<int64_t>(it.bh) * (p.s_pad / 64) + (it.first + n)) * kStatsWords,
                          C::kStatsBytes, BBAR_I(str_full, slot));
         if (++slot == C::kStages) {
           slot = 0;
@@ -477,10 +487,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
       const int len_str = it.len_str;
       const int n_steps = it.n_steps;
       float rowL = 0.f, rowD = 0.f;
+      uint32_t my_word = 0;
+      (void)my_word;
       if constexpr (kDQ) {
-        const float* blk = p.stats + (static_cast<int64_t>(it.bh) * (p.s_pad / 64) + (row >> 6)) * 128;
+        const float* blk = p.stats + (static_cast<int64_t>(it.bh) * (p.s_pad / 64) + (row >> 6)) * kStatsWords;
         rowL = __ldg(blk + (row & 63));
         rowD = __ldg(blk + 64 + (row & 63));
+        if constexpr (kDrop) my_word = __float_as_uint(__ldg(blk + 128 + (row & 63)));   // this query row's word
+      } else if constexpr (kDrop) {
+        my_word = __ldg(p.drop_c + static_cast<int64_t>(it.bh) * p.s_pad_k + row);       // this key's word
       }
       for (int n = 0; n < n_steps; ++n, ++sc) {
         tr.rec(0, sc);
@@ -561,8 +576,20 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         tr.rec(3, sc);
         if constexpr (!kDQ) {
           uint32_t pk[HC / 2];
+          if constexpr (kDrop) {
+            // X1 = the DROPPED probabilities (dV = (D o P)^T dO / (1 - p)); e itself stays undropped for dS
 #pragma unroll
-          for (int i = 0; i < HC / 2; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
+            for (int i = 0; i < HC; i += 4) {
+              const uint4 R = lds128(sStats + 512 + i * 4);   // dropout words of four query columns
+              pk[i / 2] = pack2<kBF16>(drop_keep(R.x, my_word, p.drop_thr24) ? e[i] : 0.f,
+                                       drop_keep(R.y, my_word, p.drop_thr24) ? e[i + 1] : 0.f);
+              pk[i / 2 + 1] = pack2<kBF16>(drop_keep(R.z, my_word, p.drop_thr24) ? e[i + 2] : 0.f,
+                                           drop_keep(R.w, my_word, p.drop_thr24) ? e[i + 3] : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < HC / 2; ++i) pk[i] = pack2<kBF16>(e[2 * i], e[2 * i + 1]);
+          }
           tmem_st16(tT1, pk);   // over the first half of the columns this thread has just read
           tmem_st_wait();
           tc_fence_before();
@@ -582,6 +609,20 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
             // masked columns may hold products with rows of a neighbouring sequence: select, never multiply by zero
 #pragma unroll
             for (int i = 0; i < HC; ++i) ud[i] = (i >= lo && i < hi) ? ud[i] : 0u;
+          }
+          if constexpr (kDrop) {
+            // dP = D o (dO V^T) / (1 - p)
+#pragma unroll
+            for (int i = 0; i < HC; i += 4) {
+              uint4 W;
+              if constexpr (kDQ) W = __ldg(reinterpret_cast<const uint4*>(p.drop_c + static_cast<int64_t>(it.bh) * p.s_pad_k + col0 + i));
+              else W = lds128(sStats + 512 + i * 4);
+              const uint32_t w[4] = {W.x, W.y, W.z, W.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ud[i + k] = drop_keep(kDQ ? my_word : w[k], kDQ ? w[k] : my_word, p.drop_thr24)
+                                ? __float_as_uint(__uint_as_float(ud[i + k]) * p.drop_scale) : 0u;
+            }
           }
           uint32_t pk[HC / 2];
           if constexpr (kDQ) {
@@ -696,7 +737,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         }
         tr.rec(11, ic);
       };
-      if constexpr (!kDQ) store_acc(C::colA1, &tmOut1, p.out1, p.o1_row_stride, p.o1_head_stride, 1.f, false);
+      if constexpr (!kDQ)
+        store_acc(C::colA1, &tmOut1, p.out1, p.o1_row_stride, p.o1_head_stride, kDrop ? p.drop_scale : 1.f, false);
       store_acc(C::colA2, &tmOut2, p.out2, p.o2_row_stride, p.o2_head_stride, p.scale, true);
       tr.rec(9, ic);
       if (n_steps > 0) ++ic;
@@ -728,11 +770,11 @@ inline int chunk_bh_for(int dp, int sms, int num_tiles, int total_bh) {
   return c < total_bh ? c : total_bh;
 }
 
-template <int DP, bool kDQ, bool kBF16>
+template <int DP, bool kDQ, bool kBF16, bool kDrop>
 int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, const CUtensorMap& b2,
            const CUtensorMap& o1, const CUtensorMap& o2, const Params& p, cudaStream_t stream) {
   using C = Cfg<DP, kDQ>;
-  auto kern = fmha_bwd_kernel<DP, kDQ, kBF16>;
+  auto kern = fmha_bwd_kernel<DP, kDQ, kBF16, kDrop>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -748,19 +790,57 @@ int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, 
 }  // namespace fmha_bwd
 }  // namespace bp
 
-extern "C" int64_t bp_fmha_bwd_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q) {
-  if (batch <= 0 || nheads <= 0 || max_seqlen_q <= 0) return 0;
-  const int64_t s_pad = (static_cast<int64_t>(max_seqlen_q) + 127) / 128 * 128;
-  return static_cast<int64_t>(batch) * nheads * s_pad * 8;
+// Dropout column words C[bh][k] (bp_common.cuh) for every (batch, head) and key position below s_pad_k.
+namespace bp {
+__global__ void __launch_bounds__(256)
+drop_col_table_kernel(uint32_t* __restrict__ table, uint64_t seed, int32_t s_pad_k) {
+  const uint32_t bh = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k < s_pad_k) table[static_cast<int64_t>(bh) * s_pad_k + k] = drop_col_word(drop_base(seed, bh), static_cast<uint32_t>(k));
 }
 
-extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out,
-                           const float* softmax_lse, void* dq, void* dk, void* dv, const int32_t* cu_seqlens_q,
-                           const int32_t* cu_seqlens_k, int32_t batch, int32_t nheads, int32_t headdim, int32_t total_q,
-                           int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k, const int64_t* strides,
-                           int32_t lse_stride, float softmax_scale, int32_t is_causal, int32_t dtype, void* workspace,
-                           int64_t workspace_bytes, void* stream) {
+int launch_drop_col_table(uint32_t* table, uint64_t seed, int32_t bh, int32_t s_pad_k, cudaStream_t st) {
+  if (bh > 65535) return fail(BP_ERR_UNSUPPORTED, "attention dropout: batch * nheads = %d exceeds 65535", bh);
+  drop_col_table_kernel<<<dim3((s_pad_k + 255) / 256, bh), 256, 0, st>>>(table, seed, s_pad_k);
+  return check_launch("attention dropout (column words) launch");
+}
+
+// p -> threshold of the 8-bit comparison; the effective probability is thr / 256
+int drop_threshold(float p) {
+  if (!(p > 0.f)) return 0;
+  int thr = static_cast<int>(p * 256.f + 0.5f);
+  return thr < 1 ? 1 : (thr > 255 ? 255 : thr);
+}
+}  // namespace bp
+
+static int64_t stats_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q) {
+  const int64_t s_pad = (static_cast<int64_t>(max_seqlen_q) + 127) / 128 * 128;
+  return static_cast<int64_t>(batch) * nheads * (s_pad / 64) * bp::fmha_bwd::kStatsWords * 4;
+}
+
+extern "C" int64_t bp_fmha_bwd_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q) {
+  if (batch <= 0 || nheads <= 0 || max_seqlen_q <= 0) return 0;
+  return stats_bytes(batch, nheads, max_seqlen_q);
+}
+
+extern "C" int64_t bp_fmha_bwd_dropout_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q,
+                                                       int32_t max_seqlen_k) {
+  if (batch <= 0 || nheads <= 0 || max_seqlen_q <= 0 || max_seqlen_k <= 0) return 0;
+  const int64_t s_pad_k = (static_cast<int64_t>(max_seqlen_k) + 127) / 128 * 128;
+  return stats_bytes(batch, nheads, max_seqlen_q) + static_cast<int64_t>(batch) * nheads * s_pad_k * 4;
+}
+
+static int fmha_bwd_impl(const void* dout, const void* q, const void* k, const void* v, const void* out,
+                         const float* softmax_lse, void* dq, void* dk, void* dv, const int32_t* cu_seqlens_q,
+                         const int32_t* cu_seqlens_k, int32_t batch, int32_t nheads, int32_t headdim, int32_t total_q,
+                         int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k, const int64_t* strides,
+                         int32_t lse_stride, float softmax_scale, int32_t is_causal, int32_t dtype, float p_dropout,
+                         uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace bp;
+  if (!(p_dropout >= 0.f) || p_dropout >= 1.f)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: p_dropout must be in [0, 1) (got %f)", (double)p_dropout);
+  const int thr = drop_threshold(p_dropout);
+  const bool drop = thr > 0;
   if (!dout || !q || !k || !v || !out || !softmax_lse || !dq || !dk || !dv || !cu_seqlens_q || !cu_seqlens_k || !strides)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: null pointer argument");
   if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
@@ -780,7 +860,8 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
                             (uintptr_t)dq,   (uintptr_t)dk, (uintptr_t)dv, (uintptr_t)workspace};
   for (uintptr_t a : ptrs)
     if (a % 16 != 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: tensors and workspace must be 16-byte aligned");
-  const int64_t need = bp_fmha_bwd_workspace_bytes(batch, nheads, max_seqlen_q);
+  const int64_t need = drop ? bp_fmha_bwd_dropout_workspace_bytes(batch, nheads, max_seqlen_q, max_seqlen_k)
+                            : bp_fmha_bwd_workspace_bytes(batch, nheads, max_seqlen_q);
   if (!workspace || workspace_bytes < need)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: workspace of %lld bytes needed (got %lld)", (long long)need,
                 (long long)workspace_bytes);
@@ -797,11 +878,17 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
     dim3 grid(batch * nheads, s_pad / 64);
     if (bf16)
       fmha_bwd::bwd_stats_kernel<true><<<grid, 256, 0, st>>>(dout, out, softmax_lse, stats, cu_seqlens_q, s_do[0], s_do[1],
-                                                             s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim);
+                                                             s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim, seed);
     else
       fmha_bwd::bwd_stats_kernel<false><<<grid, 256, 0, st>>>(dout, out, softmax_lse, stats, cu_seqlens_q, s_do[0], s_do[1],
-                                                              s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim);
+                                                              s_o[0], s_o[1], lse_stride, s_pad, nheads, headdim, seed);
     if (int rc = check_launch("bp_fmha_bwd (row statistics) launch")) return rc;
+  }
+  const int s_pad_k = (max_seqlen_k + 127) / 128 * 128;
+  uint32_t* drop_c = nullptr;
+  if (drop) {
+    drop_c = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + stats_bytes(batch, nheads, max_seqlen_q));
+    if (int rc = launch_drop_col_table(drop_c, seed, batch * nheads, s_pad_k, st)) return rc;
   }
 
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV;
@@ -837,6 +924,10 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   p.is_causal = is_causal ? 1 : 0;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * fmha_bwd::kLog2e;
+  p.drop_c = drop_c;
+  p.s_pad_k = s_pad_k;
+  p.drop_thr24 = static_cast<uint32_t>(thr) << 24;
+  p.drop_scale = drop ? 256.f / static_cast<float>(256 - thr) : 1.f;
   p.trace = nullptr;
 #ifdef BP_TRACE
   const char* trace_mode = getenv("BP_TRACE_BWD");   // "dkdv" or "dq": which of the two launches writes the timeline
@@ -859,11 +950,11 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
 #endif
   int rc;
   if (DP == 64)
-    rc = bf16 ? fmha_bwd::launch<64, false, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st)
-              : fmha_bwd::launch<64, false, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st);
+    rc = bf16 ? (drop ? fmha_bwd::launch<64, false, true, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st) : fmha_bwd::launch<64, false, true, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st))
+              : (drop ? fmha_bwd::launch<64, false, false, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st) : fmha_bwd::launch<64, false, false, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st));
   else
-    rc = bf16 ? fmha_bwd::launch<128, false, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st)
-              : fmha_bwd::launch<128, false, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st);
+    rc = bf16 ? (drop ? fmha_bwd::launch<128, false, true, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st) : fmha_bwd::launch<128, false, true, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st))
+              : (drop ? fmha_bwd::launch<128, false, false, true>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st) : fmha_bwd::launch<128, false, false, false>(tmK, tmV, tmQ, tmDO, tmDV, tmDK, p, st));
   if (rc) return rc;
 
   // queries own: dQ
@@ -877,10 +968,33 @@ extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const
   p.o2_row_stride = s_dq[0];
   p.o2_head_stride = s_dq[1];
   if (DP == 64)
-    rc = bf16 ? fmha_bwd::launch<64, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st)
-              : fmha_bwd::launch<64, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st);
+    rc = bf16 ? (drop ? fmha_bwd::launch<64, true, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st) : fmha_bwd::launch<64, true, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st))
+              : (drop ? fmha_bwd::launch<64, true, false, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st) : fmha_bwd::launch<64, true, false, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st));
   else
-    rc = bf16 ? fmha_bwd::launch<128, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st)
-              : fmha_bwd::launch<128, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st);
+    rc = bf16 ? (drop ? fmha_bwd::launch<128, true, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st) : fmha_bwd::launch<128, true, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st))
+              : (drop ? fmha_bwd::launch<128, true, false, true>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st) : fmha_bwd::launch<128, true, false, false>(tmQ, tmDO, tmK, tmV, tmDQ, tmDQ, p, st));
   return rc;
+}
+
+extern "C" int bp_fmha_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out,
+                           const float* softmax_lse, void* dq, void* dk, void* dv, const int32_t* cu_seqlens_q,
+                           const int32_t* cu_seqlens_k, int32_t batch, int32_t nheads, int32_t headdim, int32_t total_q,
+                           int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k, const int64_t* strides,
+                           int32_t lse_stride, float softmax_scale, int32_t is_causal, int32_t dtype, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  return fmha_bwd_impl(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens_q, cu_seqlens_k, batch, nheads, headdim,
+                       total_q, total_k, max_seqlen_q, max_seqlen_k, strides, lse_stride, softmax_scale, is_causal, dtype,
+                       0.f, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int bp_fmha_bwd_dropout(const void* dout, const void* q, const void* k, const void* v, const void* out,
+                                   const float* softmax_lse, void* dq, void* dk, void* dv, const int32_t* cu_seqlens_q,
+                                   const int32_t* cu_seqlens_k, int32_t batch, int32_t nheads, int32_t headdim,
+                                   int32_t total_q, int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                                   const int64_t* strides, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                                   int32_t dtype, float p_dropout, uint64_t seed, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  return fmha_bwd_impl(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens_q, cu_seqlens_k, batch, nheads, headdim,
+                       total_q, total_k, max_seqlen_q, max_seqlen_k, strides, lse_stride, softmax_scale, is_causal, dtype,
+                       p_dropout, seed, workspace, workspace_bytes, stream);
 }

@@ -106,6 +106,12 @@ struct Params {
   int32_t out_f32;    // debug / test mode: `out` is fp32 (same element strides), written before the 16-bit rounding
   float scale;        // softmax scale
   float scale_log2;   // scale * log2(e)
+  // attention dropout (bp_common.cuh: counter-based keep mask; fmha_fwd_kernel<..., kDrop = true> only)
+  const uint32_t* drop_c;   // (batch * nheads, s_pad_k) column words
+  uint64_t drop_seed;
+  int32_t s_pad_k;
+  uint32_t drop_thr24;      // round(256 p) << 24
+  float drop_scale;         // 1 / (1 - p)
   uint64_t* trace;    // debug: per-role event timestamps of CTA 0 (null in production)
 };
 
@@ -199,7 +205,7 @@ __device__ __forceinline__ Item get_item(uint32_t a) {
   return it;
 }
 
-template <int DP, bool kBF16>
+template <int DP, bool kBF16, bool kDrop>
 __global__ void __launch_bounds__(Cfg<DP>::kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -523,6 +529,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int qrow = row0_t + r;                 // query index within the sequence
       float m_used = 0.f;  // running max (raw score units) the exponentials are taken against
       float l = 0.f;
+      // dropout: this query row's word in a register, the key columns' words from a small table (warp-uniform loads)
+      uint32_t rq = 0;
+      const uint32_t* crow = nullptr;
+      if constexpr (kDrop) {
+        const uint32_t bh = static_cast<uint32_t>(it.batch * p.nheads + it.head);
+        rq = drop_row_word(drop_base(p.drop_seed, bh), static_cast<uint32_t>(qrow));
+        crow = p.drop_c + static_cast<int64_t>(bh) * p.s_pad_k;
+      }
+      (void)rq;
+      (void)crow;
 
       for (int j = 0; j < n; ++j, ++cnt) {
         tr.rec(0, cnt);
@@ -638,8 +654,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 32; i += 4) {
             add2(sum4[0], sum4[1], e[i], e[i + 1]);
             add2(sum4[2], sum4[3], e[i + 2], e[i + 3]);
-            pk[i / 2] = pack2<kBF16>(e[i], e[i + 1]);
-            pk[i / 2 + 1] = pack2<kBF16>(e[i + 2], e[i + 3]);
+            if constexpr (kDrop) {
+              // the row sum (softmax normaliser) takes every probability, the P.V product only the kept ones; the
+              // 1 / (1 - p) factor is applied once, to O
+              const uint4 W = __ldg(reinterpret_cast<const uint4*>(crow + col0 + c * 32 + i));
+              pk[i / 2] = pack2<kBF16>(drop_keep(rq, W.x, p.drop_thr24) ? e[i] : 0.f,
+                                       drop_keep(rq, W.y, p.drop_thr24) ? e[i + 1] : 0.f);
+              pk[i / 2 + 1] = pack2<kBF16>(drop_keep(rq, W.z, p.drop_thr24) ? e[i + 2] : 0.f,
+                                           drop_keep(rq, W.w, p.drop_thr24) ? e[i + 3] : 0.f);
+            } else {
+              pk[i / 2] = pack2<kBF16>(e[i], e[i + 1]);
+              pk[i / 2 + 1] = pack2<kBF16>(e[i + 2], e[i + 3]);
+            }
           }
         };
         if (!partial) {
@@ -678,7 +704,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       tr.rec(8, cnt);
       const bool valid = qrow < it.len_q;
-      const float inv_l = 1.f / l;
+      const float inv_l = kDrop ? p.drop_scale / l : 1.f / l;
       // Full tiles are staged in shared memory (128B-swizzled rows, the layout the TMA store expects) and leave
       // as one bulk store per panel; a thread-per-row store would touch 32 different lines per instruction.  Tiles
       // that end inside the sequence keep the guarded per-row stores (the next sequence's rows follow in memory).
@@ -799,11 +825,11 @@ static int sched_slot(cudaStream_t stream, unsigned int** out) {
   return BP_OK;
 }
 
-template <int DP, bool kBF16>
+template <int DP, bool kBF16, bool kDrop>
 int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
            const Params& p, cudaStream_t stream) {
   using C = Cfg<DP>;
-  auto kern = fmha_fwd_kernel<DP, kBF16>;
+  auto kern = fmha_fwd_kernel<DP, kBF16, kDrop>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -850,15 +876,29 @@ extern "C" int bp_debug_poison_fmha_sched(void* stream) {
   return BP_OK;
 }
 
-extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
-                           const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
-                           int32_t nheads, int32_t headdim, int32_t total_q, int32_t total_k,
-                           int32_t max_seqlen_q, int32_t max_seqlen_k, int64_t q_row_stride,
-                           int64_t q_head_stride, int64_t k_row_stride, int64_t k_head_stride,
-                           int64_t v_row_stride, int64_t v_head_stride, int64_t o_row_stride,
-                           int64_t o_head_stride, int32_t lse_stride, float softmax_scale, int32_t is_causal,
-                           int32_t dtype, void* stream) {
+extern "C" int64_t bp_fmha_fwd_dropout_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_k);
+
+static int fmha_fwd_impl(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
+                         const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
+                         int32_t nheads, int32_t headdim, int32_t total_q, int32_t total_k,
+                         int32_t max_seqlen_q, int32_t max_seqlen_k, int64_t q_row_stride,
+                         int64_t q_head_stride, int64_t k_row_stride, int64_t k_head_stride,
+                         int64_t v_row_stride, int64_t v_head_stride, int64_t o_row_stride,
+                         int64_t o_head_stride, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                         int32_t dtype, float p_dropout, uint64_t seed, void* workspace, int64_t workspace_bytes,
+                         void* stream) {
   using namespace bp;
+  if (!(p_dropout >= 0.f) || p_dropout >= 1.f)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: p_dropout must be in [0, 1) (got %f)", (double)p_dropout);
+  const int thr = drop_threshold(p_dropout);
+  const bool drop = thr > 0;
+  const int s_pad_k = (max_seqlen_k > 0 ? max_seqlen_k + 127 : 127) / 128 * 128;
+  if (drop) {
+    const int64_t need = bp_fmha_fwd_dropout_workspace_bytes(batch, nheads, max_seqlen_k);
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) % 16) != 0 || workspace_bytes < need)
+      return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: dropout needs a 16-byte aligned workspace of %lld bytes (got %lld)",
+                  (long long)need, (long long)workspace_bytes);
+  }
   if (!q || !k || !v || !out || !softmax_lse || !cu_seqlens_q || !cu_seqlens_k)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_fwd: null pointer argument");
   if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
@@ -920,7 +960,56 @@ extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* ou
   p.trace = g_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
+  p.drop_c = static_cast<const uint32_t*>(workspace);
+  p.drop_seed = seed;
+  p.s_pad_k = s_pad_k;
+  p.drop_thr24 = static_cast<uint32_t>(thr) << 24;
+  p.drop_scale = drop ? 256.f / static_cast<float>(256 - thr) : 1.f;
+  if (drop) {
+    if (int rc = launch_drop_col_table(static_cast<uint32_t*>(workspace), seed, batch * nheads, s_pad_k, st)) return rc;
+    if (DP == 64)
+      return bf16 ? fmha::launch<64, true, true>(tmQ, tmK, tmV, tmO, p, st)
+                  : fmha::launch<64, false, true>(tmQ, tmK, tmV, tmO, p, st);
+    return bf16 ? fmha::launch<128, true, true>(tmQ, tmK, tmV, tmO, p, st)
+                : fmha::launch<128, false, true>(tmQ, tmK, tmV, tmO, p, st);
+  }
   if (DP == 64)
-    return bf16 ? fmha::launch<64, true>(tmQ, tmK, tmV, tmO, p, st) : fmha::launch<64, false>(tmQ, tmK, tmV, tmO, p, st);
-  return bf16 ? fmha::launch<128, true>(tmQ, tmK, tmV, tmO, p, st) : fmha::launch<128, false>(tmQ, tmK, tmV, tmO, p, st);
+    return bf16 ? fmha::launch<64, true, false>(tmQ, tmK, tmV, tmO, p, st)
+                : fmha::launch<64, false, false>(tmQ, tmK, tmV, tmO, p, st);
+  return bf16 ? fmha::launch<128, true, false>(tmQ, tmK, tmV, tmO, p, st)
+              : fmha::launch<128, false, false>(tmQ, tmK, tmV, tmO, p, st);
+}
+
+extern "C" int64_t bp_fmha_fwd_dropout_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_k) {
+  if (batch <= 0 || nheads <= 0 || max_seqlen_k <= 0) return 0;
+  return static_cast<int64_t>(batch) * nheads * ((static_cast<int64_t>(max_seqlen_k) + 127) / 128 * 128) * 4;
+}
+
+extern "C" int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
+                           const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
+                           int32_t nheads, int32_t headdim, int32_t total_q, int32_t total_k,
+                           int32_t max_seqlen_q, int32_t max_seqlen_k, int64_t q_row_stride,
+                           int64_t q_head_stride, int64_t k_row_stride, int64_t k_head_stride,
+                           int64_t v_row_stride, int64_t v_head_stride, int64_t o_row_stride,
+                           int64_t o_head_stride, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                           int32_t dtype, void* stream) {
+  return fmha_fwd_impl(q, k, v, out, softmax_lse, cu_seqlens_q, cu_seqlens_k, batch, nheads, headdim, total_q, total_k,
+                       max_seqlen_q, max_seqlen_k, q_row_stride, q_head_stride, k_row_stride, k_head_stride, v_row_stride,
+                       v_head_stride, o_row_stride, o_head_stride, lse_stride, softmax_scale, is_causal, dtype, 0.f, 0,
+                       nullptr, 0, stream);
+}
+
+extern "C" int bp_fmha_fwd_dropout(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
+                                   const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int32_t batch,
+                                   int32_t nheads, int32_t headdim, int32_t total_q, int32_t total_k,
+                                   int32_t max_seqlen_q, int32_t max_seqlen_k, int64_t q_row_stride,
+                                   int64_t q_head_stride, int64_t k_row_stride, int64_t k_head_stride,
+                                   int64_t v_row_stride, int64_t v_head_stride, int64_t o_row_stride,
+                                   int64_t o_head_stride, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                                   int32_t dtype, float p_dropout, uint64_t seed, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  return fmha_fwd_impl(q, k, v, out, softmax_lse, cu_seqlens_q, cu_seqlens_k, batch, nheads, headdim, total_q, total_k,
+                       max_seqlen_q, max_seqlen_k, q_row_stride, q_head_stride, k_row_stride, k_head_stride, v_row_stride,
+                       v_head_stride, o_row_stride, o_head_stride, lse_stride, softmax_scale, is_causal, dtype, p_dropout,
+                       seed, workspace, workspace_bytes, stream);
 }

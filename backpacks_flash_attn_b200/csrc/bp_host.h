@@ -21,6 +21,10 @@ int encode_tensor_map(CUtensorMap* out, int elem_bytes_log2_dtype /*bp_dtype_t*/
 
 int check_launch(const char* what);
 
+// attention dropout helpers (bp_fmha_bwd.cu): column-word table launch, 8-bit threshold of a probability
+int launch_drop_col_table(uint32_t* table, uint64_t seed, int32_t bh, int32_t s_pad_k, cudaStream_t st);
+int drop_threshold(float p);
+
 inline int dtype_size(int dtype) { return dtype == BP_DTYPE_F32 ? 4 : 2; }
 
 }  // namespace bp

@@ -1,6 +1,7 @@
 """`dropout_add_layer_norm` with the reference's signature (flash_attn/ops/layer_norm.py:207-252), running
 bp_ln_residual_fwd, and differentiable through bp_ln_residual_bwd like the reference's DropoutAddLayerNormFn
-(layer_norm.py:104-160).  dropout_p must be 0 and rowscale / layerscale are rejected."""
+(layer_norm.py:104-160).  dropout_p > 0 (training) is applied to x0 by a separate pass in front of the kernel;
+rowscale / layerscale are rejected."""
 from __future__ import annotations
 
 import torch
@@ -114,7 +115,9 @@ def dropout_add_layer_norm(x0, x1, weight, bias, dropout_p, epsilon, rowscale=No
     """z = LayerNorm(x0 + x1) (and the fp32/16-bit residual x0 + x1 when prenorm=True).
     residual_in_fp32 only matters when x1 is None (layer_norm.py:209-212)."""
     if dropout_p != 0.0:
-        raise RuntimeError("dropout inside the fused LayerNorm is not implemented: dropout_p must be 0.0")
+        # z = LayerNorm(dropout(x0) + x1): the mask is drawn by a separate element-wise pass over x0 (training only; the
+        # reference draws it inside its kernel, ln_fwd_kernels.cuh:98-131 -- same distribution, one more pass over x0)
+        x0 = torch.nn.functional.dropout(x0, dropout_p, training=True)
     if rowscale is not None or layerscale is not None or return_dropout_mask:
         raise RuntimeError("rowscale / layerscale / dropout mask are training-only features (out of scope)")
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x0, x1, weight, bias)):

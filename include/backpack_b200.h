@@ -60,7 +60,7 @@ int bp_check_device(void);
  *   cu_seqlens_* : (batch+1) int32 device arrays (fmha_api.cpp:230-233); sequence i occupies rows
  *                  [cu[i], cu[i+1]).  Causal masking is top-left aligned: key j visible to query i iff j<=i
  *                  (csrc/flash_attn/src/fmha/mask.h:70).
- *   headdim % 8 == 0 and headdim <= 128 (fmha_api.cpp:245).  No dropout (inference path).
+ *   headdim % 8 == 0 and headdim <= 128 (fmha_api.cpp:245).  No dropout (see bp_fmha_fwd_dropout).
  */
 int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
                 const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
@@ -76,7 +76,7 @@ int bp_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* s
 /* FlashAttention backward (replaces mha_bwd, csrc/flash_attn/fmha_api.cpp:338-500, as driven by
  * _flash_attn_backward, flash_attn/flash_attn_interface.py:31-47).  SURVEY.md section 8f rank 4.
  *   dout, q, out, dq : (total_q, nheads, headdim);  k, v, dk, dv : (total_k, nheads, headdim); last-dim stride 1.
- *   softmax_lse      : what bp_fmha_fwd returned.  No dropout.  dq / dk / dv are overwritten (not accumulated into);
+ *   softmax_lse      : what bp_fmha_fwd returned.  No dropout (see bp_fmha_bwd_dropout).  dq / dk / dv are overwritten (not accumulated into);
  *                      the result is bit-wise reproducible (no atomics; the reference's determinism contract,
  *                      tests/test_flash_attn.py:727-793).
  *   strides          : HOST array of 16 element strides: {row, head} of dout, q, k, v, out, dq, dk, dv.
@@ -92,6 +92,36 @@ int bp_fmha_bwd(const void* dout, const void* q, const void* k, const void* v, c
                 int32_t total_q, int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k,
                 const int64_t* strides, int32_t lse_stride, float softmax_scale, int32_t is_causal,
                 int32_t dtype /* bp_dtype_t */, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Attention dropout (training): the same two operators with a Bernoulli keep mask on the attention probabilities,
+ * out = ((D o P) / (1 - p)) V (csrc/flash_attn/src/fmha/softmax.h apply_dropout; fmha_api.cpp:189-204 p_dropout, gen).
+ * The mask is counter-based -- keep(b, h, q, k) is a pure function of (seed, b * nheads + h, q, k), spelled out in
+ * csrc/bp_common.cuh and restated in Python by flash_attn_interface.attention_dropout_mask -- so the backward
+ * regenerates it from `seed` alone (the reference replays its Philox stream instead).  p is quantised to
+ * round(256 p) / 256.  Workspaces: the forward needs bp_fmha_fwd_dropout_workspace_bytes, the backward
+ * bp_fmha_bwd_dropout_workspace_bytes (both 16-byte aligned).  p_dropout = 0 is the plain operator.
+ */
+int64_t bp_fmha_fwd_dropout_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_k);
+int bp_fmha_fwd_dropout(const void* q, const void* k, const void* v, void* out, float* softmax_lse,
+                        const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                        int32_t batch, int32_t nheads, int32_t headdim,
+                        int32_t total_q, int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                        int64_t q_row_stride, int64_t q_head_stride,
+                        int64_t k_row_stride, int64_t k_head_stride,
+                        int64_t v_row_stride, int64_t v_head_stride,
+                        int64_t o_row_stride, int64_t o_head_stride,
+                        int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                        int32_t dtype /* bp_dtype_t */, float p_dropout, uint64_t seed,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int64_t bp_fmha_bwd_dropout_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q, int32_t max_seqlen_k);
+int bp_fmha_bwd_dropout(const void* dout, const void* q, const void* k, const void* v, const void* out,
+                        const float* softmax_lse, void* dq, void* dk, void* dv,
+                        const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                        int32_t batch, int32_t nheads, int32_t headdim,
+                        int32_t total_q, int32_t total_k, int32_t max_seqlen_q, int32_t max_seqlen_k,
+                        const int64_t* strides, int32_t lse_stride, float softmax_scale, int32_t is_causal,
+                        int32_t dtype /* bp_dtype_t */, float p_dropout, uint64_t seed,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Backpack sense-mix, pass 1: per-sense causal softmax statistics.
  *   qk  : (batch, seqlen, 2, nv, dk) contiguous -- the output of ContextSelfAttn.Wqkv reshaped as

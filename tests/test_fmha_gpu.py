@@ -229,7 +229,7 @@ def test_fmha_rejects_bad_arguments():
     with pytest.raises(RuntimeError, match="fp16 and bf16"):
         F.flash_attn_unpadded_qkvpacked_func(qkv, cu, 64, 0.0)
     with pytest.raises(RuntimeError, match="dropout"):
-        F.flash_attn_unpadded_qkvpacked_func(qkv.bfloat16(), cu, 64, 0.1)
+        F.flash_attn_unpadded_qkvpacked_func(qkv.bfloat16(), cu, 64, 1.0)
     with pytest.raises(RuntimeError, match="int32"):
         F.flash_attn_unpadded_qkvpacked_func(qkv.bfloat16(), cu.long(), 64, 0.0)
     bad = torch.zeros(64, 3, 2, 36, device="cuda", dtype=torch.bfloat16)

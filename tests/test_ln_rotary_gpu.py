@@ -43,8 +43,16 @@ def test_layer_norm_config3_shape_and_postnorm():
     assert (z.float() - ref).abs().max() < 4e-2
     z2 = dropout_add_layer_norm(x0, x1, g, b, 0.0, 1e-5, prenorm=False)
     assert torch.equal(z, z2)
-    with pytest.raises(RuntimeError, match="dropout"):
-        dropout_add_layer_norm(x0, x1, g, b, 0.1, 1e-5)
+    # dropout_p > 0: z = LN(dropout(x0) + x1) -- the residual stream tells which elements of x0 were kept
+    zd, rd = dropout_add_layer_norm(x0, x1, g, b, 0.25, 1e-5, prenorm=True)
+    kept = ((rd - x1).abs() > 0) | (x0 == 0)
+    frac = 1.0 - kept.float().mean().item()
+    assert 0.24 < frac < 0.26, frac
+    want = torch.where(kept, x0.float() / 0.75, torch.zeros((), device="cuda")) + x1
+    assert (rd - want).abs().max() < 2e-2                        # x0 / (1 - p) is rounded to bf16 before the add
+    assert (zd.float() - torch.nn.functional.layer_norm(rd, (768,))).abs().max() < 4e-2
+    with pytest.raises(RuntimeError, match="rowscale"):
+        dropout_add_layer_norm(x0, x1, g, b, 0.0, 1e-5, rowscale=torch.ones(65536, device="cuda"))
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
