@@ -1,4 +1,4 @@
-"""Batch-sharded (data-parallel) inference over the GPUs of one node.
+"""Batch-sharded (data-parallel) inference -- and data-parallel training -- over the GPUs of one node.
 
 Every operator on the Backpack forward path is independent across the batch dimension (attention and the
 sense-mix only mix along the sequence), so the path shards into independent units with NO data-path
@@ -6,6 +6,11 @@ collective: weights are replicated, `input_ids` is split contig
 NCCL (over NVLink / NVSwitch) is used only for control-plane collectives: proving the replicas hold the
 same weights, the barrier + max-over-ranks timing of the benchmark, and optionally returning the
 last-position argmax ids.  The same code runs on CPU with the gloo backend (tests).
+
+Training is the one place the path has a real exchange step: with the batch sharded, the
+parameter gradients of the replicas must be averaged after every backward.  `allreduce_gradients` does that with a
+few large bucketed all-reduces (NVSwitch makes the cost a matter of launch latency, not link count), which is what
+the reference gets from Lightning's DDP (training/configs/trainer/ddp.yaml).
 """
 from __future__ import annotations
 
@@ -90,3 +95,43 @@ def gather_next_tokens(logits_last: torch.Tensor) -> torch.Tensor:
     out = torch.empty(ids.numel() * dist.get_world_size(), dtype=ids.dtype, device=ids.device)
     dist.all_gather_into_tensor(out, ids)
     return out
+
+
+def allreduce_gradients(model: torch.nn.Module, bucket_bytes: int = 64 << 20, average: bool = True) -> int:
+    """Average (or sum) the parameter gradients over the data-parallel ranks, in place: gradients are packed into
+    flat buckets of about `bucket_bytes` per dtype, each bucket is one all-reduce, and the results are copied back.
+    Tied parameters are visited once.  Returns the number of collectives issued (0 without a process group)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return 0
+    world = dist.get_world_size()
+    grads = [p.grad for p in model.parameters() if p.grad is not None]      # parameters() de-duplicates tied weights
+    calls = 0
+    by_dtype: dict = {}
+    for g in grads:
+        by_dtype.setdefault(g.dtype, []).append(g)
+    for dtype, group in by_dtype.items():
+        bucket, size = [], 0
+        limit = max(1, bucket_bytes // group[0].element_size())
+
+        def flush():
+            nonlocal bucket, size, calls
+            if not bucket:
+                return
+            flat = torch.cat([g.reshape(-1) for g in bucket])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if average:
+                flat /= world
+            offset = 0
+            for g in bucket:
+                g.copy_(flat[offset:offset + g.numel()].view_as(g))
+                offset += g.numel()
+            calls += 1
+            bucket, size = [], 0
+
+        for g in group:
+            if size + g.numel() > limit:
+                flush()
+            bucket.append(g)
+            size += g.numel()
+        flush()
+    return calls

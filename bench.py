@@ -405,6 +405,7 @@ def run_ours(args):
             loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(),
                                                      tids[:, 1:].reshape(-1))
             loss.backward()
+            parallel.allreduce_gradients(tmodel)   # data-parallel training: the one exchange step (no-op at N = 1)
             return loss
 
         for _ in range(2):
@@ -595,8 +596,9 @@ def run_ours(args):
             "note": "forward + backward of the same model in train mode (dropouts 0), next-token cross-entropy on fp32 "
                     "logits, eager launches, no optimizer step: attention backward = bp_fmha_bwd, LayerNorm backward = "
                     "bp_ln_residual_bwd, dgelu + bias gradients = bp_bias_act_bwd, dgrad GEMMs = this library's GEMM, wgrad "
-                    "GEMMs and the recomputed sense-mix backward = cuBLAS through PyTorch.  A variant: the headline "
-                    "metric is the forward"}
+                    "GEMMs and the recomputed sense-mix backward = cuBLAS through PyTorch; at N > 1 the batch is sharded "
+                    "and the gradients are averaged with bucketed NCCL all-reduces (parallel.allreduce_gradients).  A "
+                    "variant: the headline metric is the forward"}
     print(json.dumps(line), flush=True)
 
 

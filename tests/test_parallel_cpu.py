@@ -73,3 +73,50 @@ def test_two_rank_gloo_sharded_forward(diverge):
         assert ok
         assert t == 2.0                 # max over ranks
         assert tok == 6 * 16            # every token processed exactly once
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    try:
+        parallel.init_distributed("gloo")
+        import torch.nn.functional as F
+        from backpacks_flash_attn_b200.models.backpack import BackpackConfig, BackpackLMHeadModel
+        from backpacks_flash_attn_b200.utils.weights import name_seeded_
+        cfg = BackpackConfig(num_content_vectors=4, n_embd=32, n_head=2, n_layer=1, n_positions=16, vocab_size=96,
+                             pad_vocab_size_multiple=8, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+        ids = torch.randint(0, 96, (6, 16), generator=torch.Generator().manual_seed(4321))
+
+        def grads_of(batch, scale):
+            model = name_seeded_(BackpackLMHeadModel(cfg).train())
+            logits = model(batch).logits
+            loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), batch[:, 1:].reshape(-1), reduction="sum")
+            (loss * scale).backward()
+            return model
+
+        n_tok = ids.shape[0] * (ids.shape[1] - 1)
+        mine = parallel.shard_batch(ids, rank, world)
+        model = grads_of(mine, world / n_tok)             # mean over ranks of (world / n) * local sum = global mean
+        calls = parallel.allreduce_gradients(model, bucket_bytes=4096)
+        whole = grads_of(ids, 1.0 / n_tok)                # the same step on the un-sharded batch
+        worst = max((p.grad - w.grad).abs().max().item() for p, w in zip(model.parameters(), whole.parameters()))
+        q.put((rank, calls, worst))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_matches_the_unsharded_step():
+    """Data-parallel training step: sharded batch + bucketed gradient all-reduce == the step on the whole batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, 29631, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, calls, worst in res:
+        assert calls >= 2                 # several buckets at this bucket size
+        assert worst < 1e-5, worst
