@@ -399,11 +399,15 @@ def run_ours(args):
         torch.cuda.empty_cache()
         tids = ids_dev[:tb]
 
+        from backpacks_flash_attn_b200.losses.cross_entropy import CrossEntropyLoss
+        ce = CrossEntropyLoss(inplace_backward=True)     # bp_xentropy_fwd / _bwd: one pass each, in place over the logits
+        # next-token targets for every position; the last one of a sequence is ignored (no copy of the logits)
+        tlabels = torch.cat([tids[:, 1:], torch.full_like(tids[:, :1], -100)], dim=1).reshape(-1)
+
         def train_step():
             tmodel.zero_grad(set_to_none=True)
             logits = tmodel(tids).logits
-            loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(),
-                                                     tids[:, 1:].reshape(-1))
+            loss = ce(logits.view(-1, logits.shape[-1]), tlabels)
             loss.backward()
             parallel.allreduce_gradients(tmodel)   # data-parallel training: the one exchange step (no-op at N = 1)
             return loss
@@ -411,7 +415,7 @@ def run_ours(args):
         for _ in range(2):
             train_step()
         bwd_names = ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_fwd", "bp_ln_residual_bwd", "bp_bias_act_bwd",
-                     "bp_linear_bias_act_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd")
+                     "bp_linear_bias_act_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd", "bp_xentropy_fwd", "bp_xentropy_bwd")
         tt = {n: _lib.KernelTimer(n) for n in bwd_names}
         for t in tt.values():
             t.__enter__()
@@ -593,8 +597,9 @@ def run_ours(args):
                                              "seven (S and dP are recomputed in both)"},
             "ln_residual_bwd": {"ms_per_call": tk["bp_ln_residual_bwd"][1],
                                 "hbm_frac": tb * S * d * 16 / (tk["bp_ln_residual_bwd"][1] * 1e-3) / 1e9 / peak_hbm},
-            "note": "forward + backward of the same model in train mode (dropouts 0), next-token cross-entropy on fp32 "
-                    "logits, eager launches, no optimizer step: attention backward = bp_fmha_bwd, LayerNorm backward = "
+            "note": "forward + backward of the same model in train mode (dropouts 0), next-token cross-entropy by "
+                    "bp_xentropy_fwd / _bwd in place over the bf16 logits, eager launches, no optimizer step: attention "
+                    "backward = bp_fmha_bwd, LayerNorm backward = "
                     "bp_ln_residual_bwd, dgelu + bias gradients = bp_bias_act_bwd, dgrad GEMMs = this library's GEMM, wgrad "
                     "GEMMs and the recomputed sense-mix backward = cuBLAS through PyTorch; at N > 1 the batch is sharded "
                     "and the gradients are averaged with bucketed NCCL all-reduces (parallel.allreduce_gradients).  A "

@@ -10,6 +10,7 @@
  *   flash_attn_cuda.bwd                       csrc/flash_attn/fmha_api.cpp:338-500      -> bp_fmha_bwd
  *   dropout_layer_norm.dropout_add_ln_bwd     csrc/layer_norm/ln_api.cpp:255-440        -> bp_ln_residual_bwd
  *   fused_dense_lib backward epilogues        csrc/fused_dense_lib/fused_dense_cuda.cu:559-787 -> bp_bias_act_bwd
+ *   xentropy_cuda_lib.forward / .backward     csrc/xentropy/interface.cpp:57-58         -> bp_xentropy_fwd / _bwd
  *   (no reference kernel; eager PyTorch at    training/src/models/backpack.py:111-122,313) -> bp_sense_lse_fwd,
  *                                                                                            bp_sense_mix_fwd,
  *                                                                                            bp_sense_mix_table_fwd
@@ -263,6 +264,21 @@ int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, c
 int64_t bp_bias_act_bwd_workspace_bytes(int32_t n);
 int bp_bias_act_bwd(const void* dact, const void* pre, void* dpre, void* dbias, void* workspace,
                     int64_t workspace_bytes, int64_t m, int32_t n, int32_t activation, int32_t dtype, void* stream);
+
+/* Softmax cross-entropy over (rows, vocab) logits, forward and backward (replaces xentropy_cuda_lib.forward /
+ * .backward, csrc/xentropy/interface.cpp:57-58, as driven by SoftmaxCrossEntropyLossFn,
+ * flash_attn/losses/cross_entropy.py:19-109).  logits in f16 / bf16 / f32 with a row stride in elements; labels int64;
+ * losses / lse / grad_losses (rows) f32.  loss = (1 - smoothing) (lse - x[y]) + smoothing (lse - sum(x) / C), 0 where
+ * y == ignore_index; C = total_classes (-1: vocab).  The backward writes g (softmax - (1 - smoothing) onehot -
+ * smoothing / C) into grad_logits, which MAY BE the logits buffer itself (the reference's inplace_backward).
+ * The evaluation-only form that never materialises logits is bp_lm_head_stats_fwd.
+ */
+int bp_xentropy_fwd(const void* logits, const int64_t* labels, float* losses, float* lse, int64_t rows, int32_t vocab,
+                    int64_t row_stride, float smoothing, int64_t ignore_index, int32_t total_classes, int32_t dtype,
+                    void* stream);
+int bp_xentropy_bwd(const float* grad_losses, const void* logits, const float* lse, const int64_t* labels,
+                    void* grad_logits, int64_t rows, int32_t vocab, int64_t row_stride, int64_t grad_row_stride,
+                    float smoothing, int64_t ignore_index, int32_t total_classes, int32_t dtype, void* stream);
 
 /* In-place rotary embedding on q and k of a packed qkv tensor (replaces apply_rotary as driven by
  * ApplyRotaryEmbQKV_.forward, flash_attn/layers/rotary.py:81-105; csrc/rotary/rotary_cuda.cu:5-41).
