@@ -389,42 +389,46 @@ def run_ours(args):
     # ---- variant: a training step (forward + backward with a next-token cross-entropy), SURVEY.md §8f rank 4.  Outside
     #      inference mode, smaller batch (the activations of 12 layers are kept), dropouts 0 (not implemented) ----
     training = None
+    training_error = None
     if args.training_steps > 0:
-        tb = min(B, args.training_batch)
-        tcfg = flash_config(**{**SMALL, "n_positions": max(1024, S), "resid_pdrop": 0.0, "embd_pdrop": 0.0,
-                               "attn_pdrop": 0.0})
-        tmodel = BackpackLMHeadModel(tcfg).to(dev, torch.bfloat16).train()
-        tmodel.load_state_dict(model.state_dict())
-        del model
-        torch.cuda.empty_cache()
-        tids = ids_dev[:tb]
+        try:
+            tb = min(B, args.training_batch)
+            tcfg = flash_config(**{**SMALL, "n_positions": max(1024, S), "resid_pdrop": 0.0, "embd_pdrop": 0.0,
+                                   "attn_pdrop": 0.0})
+            tmodel = BackpackLMHeadModel(tcfg).to(dev, torch.bfloat16).train()
+            tmodel.load_state_dict(model.state_dict())
+            del model
+            torch.cuda.empty_cache()
+            tids = ids_dev[:tb]
 
-        from backpacks_flash_attn_b200.losses.cross_entropy import CrossEntropyLoss
-        ce = CrossEntropyLoss(inplace_backward=True)     # bp_xentropy_fwd / _bwd: one pass each, in place over the logits
-        # next-token targets for every position; the last one of a sequence is ignored (no copy of the logits)
-        tlabels = torch.cat([tids[:, 1:], torch.full_like(tids[:, :1], -100)], dim=1).reshape(-1)
+            from backpacks_flash_attn_b200.losses.cross_entropy import CrossEntropyLoss
+            ce = CrossEntropyLoss(inplace_backward=True)     # bp_xentropy_fwd / _bwd: one pass each, in place over the logits
+            # next-token targets for every position; the last one of a sequence is ignored (no copy of the logits)
+            tlabels = torch.cat([tids[:, 1:], torch.full_like(tids[:, :1], -100)], dim=1).reshape(-1)
 
-        def train_step():
-            tmodel.zero_grad(set_to_none=True)
-            logits = tmodel(tids).logits
-            loss = ce(logits.view(-1, logits.shape[-1]), tlabels)
-            loss.backward()
-            parallel.allreduce_gradients(tmodel)   # data-parallel training: the one exchange step (no-op at N = 1)
-            return loss
+            def train_step():
+                tmodel.zero_grad(set_to_none=True)
+                logits = tmodel(tids).logits
+                loss = ce(logits.view(-1, logits.shape[-1]), tlabels)
+                loss.backward()
+                parallel.allreduce_gradients(tmodel)   # data-parallel training: the one exchange step (no-op at N = 1)
+                return loss
 
-        for _ in range(2):
-            train_step()
-        bwd_names = ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_fwd", "bp_ln_residual_bwd", "bp_bias_act_bwd",
-                     "bp_linear_bias_act_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd", "bp_xentropy_fwd", "bp_xentropy_bwd")
-        tt = {n: _lib.KernelTimer(n) for n in bwd_names}
-        for t in tt.values():
-            t.__enter__()
-        tr_dt = timed_steps(train_step, args.training_steps, parallel, dev)
-        for t in reversed(list(tt.values())):
-            t.__exit__(None, None, None)
-        training = {"dt": tr_dt, "steps": args.training_steps, "batch": tb,
-                    "kernels": {n: (len(t.events) / args.training_steps, t.mean_ms()) for n, t in tt.items() if t.events}}
-        del tmodel
+            for _ in range(2):
+                train_step()
+            bwd_names = ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_fwd", "bp_ln_residual_bwd", "bp_bias_act_bwd",
+                         "bp_linear_bias_act_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd", "bp_xentropy_fwd", "bp_xentropy_bwd")
+            tt = {n: _lib.KernelTimer(n) for n in bwd_names}
+            for t in tt.values():
+                t.__enter__()
+            tr_dt = timed_steps(train_step, args.training_steps, parallel, dev)
+            for t in reversed(list(tt.values())):
+                t.__exit__(None, None, None)
+            training = {"dt": tr_dt, "steps": args.training_steps, "batch": tb,
+                        "kernels": {n: (len(t.events) / args.training_steps, t.mean_ms()) for n, t in tt.items() if t.events}}
+            del tmodel
+        except Exception as exc:   # a variant must never take the headline line down with it
+            training, training_error = None, f"{type(exc).__name__}: {exc}"[:300]
 
     if rank != 0:
         return
@@ -580,6 +584,8 @@ def run_ours(args):
                     "bp_lm_head_stats_fwd (log-sum-exp, arg-max and target logit per row in the GEMM epilogue; no "
                     "(b, s, vocab) tensor), eager launches.  What perplexity evaluation needs; a different result than "
                     "`value` (per-token loss instead of logits), hence a variant"}
+    if training_error is not None:
+        line["variants"]["training_step"] = {"unavailable": training_error}
     if training is not None:
         tb, tms = training["batch"], training["dt"] / training["steps"] * 1e3
         tk = training["kernels"]
