@@ -69,9 +69,12 @@ struct Cfg {
   static constexpr uint32_t offStage = offStr + kStages * kStageBytes;   // [128 rows][DP * 2 B] epilogue staging tile
   static constexpr uint32_t offBar = offStage + BS * DP * 2;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
+  // TMEM columns.  Keys own: T1, T2, dV, dK (256 at head dim 64: full).  Queries own: T1, two T2 buffers, dQ -- the
+  // spare columns double-buffer dP, so both products of step n+1 are issued while step n's dS is being formed.
+  static constexpr int kT2Bufs = kDQ ? 2 : 1;
   static constexpr uint32_t colT1 = 0, colT2 = BT;
   static constexpr uint32_t colA1 = 2 * BT;
-  static constexpr uint32_t colA2 = kDQ ? 2 * BT : 2 * BT + DP;
+  static constexpr uint32_t colA2 = kDQ ? 3 * BT : 2 * BT + DP;
   static constexpr uint32_t kColsUsed = colA2 + DP;
   static constexpr uint32_t kTmemCols = kColsUsed <= 256 ? 256 : 512;
   static constexpr int kCtasPerSm = (kTmemCols == 256 && kSmemBytes <= 113 * 1024) ? 2 : 1;
@@ -100,7 +103,7 @@ struct Params {
 };
 
 struct Barriers {
-  uint64_t stat_full, t1_full, t2_full, x1_ready, x2_ready, acc_full, acc_free;
+  uint64_t stat_full, t1_full, t2_full[2], x1_ready, x2_ready[2], acc_full, acc_free;   // t2_full / x2_ready: per T2 buffer
   uint64_t str_full[3], str_empty[3];
   uint32_t tmem_base;
 };
@@ -299,9 +302,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     tma_prefetch_desc(&tmOut2);
     mbar_init(&bars.stat_full, 1);
     mbar_init(&bars.t1_full, 1);
-    mbar_init(&bars.t2_full, 1);
+    mbar_init(&bars.t2_full[0], 1);
+    mbar_init(&bars.t2_full[1], 1);
     mbar_init(&bars.x1_ready, 256);
-    mbar_init(&bars.x2_ready, 256);
+    mbar_init(&bars.x2_ready[0], 256);
+    mbar_init(&bars.x2_ready[1], 256);
     mbar_init(&bars.acc_full, 1);
     mbar_init(&bars.acc_free, 256);
     for (int i = 0; i < 3; ++i) {
@@ -382,14 +387,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
       }
       umma_commit_w(BBAR(t1_full));
     };
-    auto issue_t2 = [&](uint32_t sB2) {
+    auto issue_t2 = [&](uint32_t sB2, uint32_t buf) {
 #pragma unroll
       for (int kk = 0; kk < DP / 16; ++kk) {
         const uint32_t a = sA2 + (kk >> 2) * C::kStatPanelBytes + (kk & 3) * 32;
         const uint32_t b = sB2 + (kk >> 2) * C::kStrPanelBytes + (kk & 3) * 32;
-        umma_ss_w(tT2, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_t, kk > 0 ? 1u : 0u);
+        umma_ss_w(tT2 + buf * BT, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc_t,
+                  kk > 0 ? 1u : 0u);
       }
-      umma_commit_w(BBAR(t2_full));
+      umma_commit_w(BBAR_I(t2_full, buf));
     };
     uint32_t slot = 0, ph = 0;
     uint32_t sc = 0, ic = 0;
@@ -405,7 +411,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
       tr.rec(9, ic);
       // (T1 / T2 are free: their last readers, the previous item's final products, were issued by this thread)
       issue_t1(smem_a + C::offStr + slot * C::kStageBytes);
-      issue_t2(smem_a + C::offStr + slot * C::kStageBytes + C::kStrTileBytes);
+      issue_t2(smem_a + C::offStr + slot * C::kStageBytes + C::kStrTileBytes, kDQ ? (sc & 1u) : 0u);
       for (int n = 0; n < n_steps; ++n, ++sc) {
         const uint32_t sB1 = smem_a + C::offStr + slot * C::kStageBytes;
         const uint32_t sB2 = sB1 + C::kStrTileBytes;
@@ -439,19 +445,27 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
             tc_fence_after();
           }
           issue_t1(nB1);   // executes behind the product above, which is the last reader of X1 (same issuing thread)
+          // queries own: dP of the next step goes to the other T2 buffer, whose last reader (the dQ product of the
+          // previous step) was issued by this thread before
+          if constexpr (kDQ) issue_t2(nB1 + C::kStrTileBytes, (sc + 1) & 1u);
         }
         tr.rec(2, sc);
         // second half: X2 is in TMEM
-        mbar_spin_a(BBAR(x2_ready), sc & 1);
+        // (queries own: one hand-over barrier per T2 buffer.  With dP of step n+1 available early, a fast softmax warp
+        // can finish step n+1 before a slow one has finished step n; on a single barrier its arrival would be counted
+        // towards step n and release this product too early)
+        mbar_spin_a(BBAR_I(x2_ready, kDQ ? (sc & 1u) : 0u), kDQ ? ((sc >> 1) & 1u) : (sc & 1u));
         tc_fence_after();
         tr.rec(3, sc);
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
-          umma_ts_w(tA2, tT2 + (kk >> 1) * 32 + (kk & 1) * 8,
+          umma_ts_w(tA2, tT2 + (kDQ ? (sc & 1u) * BT : 0u) + (kk >> 1) * 32 + (kk & 1) * 8,
                     make_smem_desc_sw128(sB1 + kk * 16 * 128, C::kStrPanelBytes, 1024), idesc_acc,
                     (n > 0 || kk > 0) ? 1u : 0u);
         umma_commit_w(BBAR_I(str_empty, slot));   // every product that reads this step's streaming tiles has been issued
-        if (more) issue_t2(nB1 + C::kStrTileBytes);
+        if constexpr (!kDQ) {
+          if (more) issue_t2(nB1 + C::kStrTileBytes, 0u);
+        }
         tr.rec(4, sc);
         slot = nslot;
         ph = nph;
@@ -520,7 +534,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
 
         // ---- first half: P = exp2(T1 * scale_log2 - L) ----
         mbar_wait_a(BBAR(t1_full), sc & 1);
-        const bool t2_ready = mbar_test_a(BBAR(t2_full), sc & 1);   // consumed after the exponentials
+        // dP: one barrier per T2 buffer (queries own: buffer sc & 1 completes every other step, so a late waiter can
+        // never confuse the phase of step n with that of step n + 2)
+        const uint32_t bar_t2 = BBAR_I(t2_full, kDQ ? (sc & 1u) : 0u);
+        const uint32_t par_t2 = kDQ ? ((sc >> 1) & 1u) : (sc & 1u);
+        const bool t2_ready = mbar_test_a(bar_t2, par_t2);   // consumed after the exponentials
         if constexpr (!kDQ) {
           if (!stats_ready) mbar_wait_a(BBAR_I(str_full, slot), ph);
         }
@@ -598,12 +616,13 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         tr.rec(4, sc);
 
         // ---- second half: dS = P * (T2 - delta) ----
-        if (!t2_ready) mbar_wait_a(BBAR(t2_full), sc & 1);
+        if (!t2_ready) mbar_wait_a(bar_t2, par_t2);
         tc_fence_after();
         tr.rec(5, sc);
         {
           uint32_t ud[HC];
-          tmem_ld32(tT2, ud);
+          const uint32_t tT2n = tT2 + (kDQ ? (sc & 1u) * BT : 0u);
+          tmem_ld32(tT2n, ud);
           tmem_ld_wait();
           if (partial) {
             // masked columns may hold products with rows of a neighbouring sequence: select, never multiply by zero
@@ -646,11 +665,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
               pk[i / 2 + 1] = pack2<kBF16>(g2, g3);
             }
           }
-          tmem_st16(tT2, pk);
+          tmem_st16(tT2n, pk);
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive_a(BBAR(x2_ready));
+        mbar_arrive_a(BBAR_I(x2_ready, kDQ ? (sc & 1u) : 0u));
         tr.rec(7, sc);
         if (++slot == C::kStages) {
           slot = 0;

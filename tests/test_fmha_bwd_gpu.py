@@ -184,6 +184,29 @@ def test_fmha_bwd_chunk_boundaries(b, h, s):
     _check_bwd(_make_qkv(b, s, h, 64, torch.bfloat16, seed=b * 7 + h), True)
 
 
+@pytest.mark.parametrize("b,h,s,d", [(37, 8, 384, 64), (9, 6, 1100, 128), (64, 12, 512, 64)])
+def test_fmha_bwd_repeated_runs_are_bitwise_identical(b, h, s, d):
+    """Persistent CTAs walk several tiles each and their softmax warps run up to a step apart: a hand-over barrier
+    that a fast warp could lap shows up as non-finite or irreproducible rows (it did once, in the queries-own mode
+    with its double-buffered dP; the barriers are per buffer since).  Pre-filled with NaN, 12 runs, bit-wise equal."""
+    F = _ops()
+    qkv = _make_qkv(b, s, h, d, torch.bfloat16, seed=b + s).reshape(b * s, 3, h, d)
+    cu = torch.arange(0, (b + 1) * s, s, dtype=torch.int32, device="cuda")
+    out, lse = F._flash_attn_forward(qkv[:, 0], qkv[:, 1], qkv[:, 2], torch.empty_like(qkv[:, 0]), cu, cu, s, s,
+                                     d ** -0.5, True)
+    g = torch.randn_like(out)
+    first = None
+    for _ in range(12):
+        dqkv = torch.full_like(qkv, float("nan"))
+        F._flash_attn_backward(g, qkv[:, 0], qkv[:, 1], qkv[:, 2], out, lse, dqkv[:, 0], dqkv[:, 1], dqkv[:, 2], cu, cu,
+                               s, s, d ** -0.5, True)
+        assert torch.isfinite(dqkv.float()).all()
+        if first is None:
+            first = dqkv
+        else:
+            assert torch.equal(dqkv, first)
+
+
 def test_fmha_bwd_through_the_modules():
     """FlashAttention / FlashSelfAttention / MHA(use_flash_attn) are differentiable end to end."""
     from backpacks_flash_attn_b200.flash_attention import FlashAttention
