@@ -387,7 +387,7 @@ def run_ours(args):
             fused_loss = {"dt": fl_dt, "steps": kk, "stats_ms": loss_timer.mean_ms()}
 
     # ---- variant: a training step (forward + backward with a next-token cross-entropy), SURVEY.md §8f rank 4.  Outside
-    #      inference mode, smaller batch (the activations of 12 layers are kept), dropouts 0 (not implemented) ----
+    #      inference mode, same batch as the headline (the activations of 12 layers are kept: ~60 GB), dropouts 0 ----
     training = None
     training_error = None
     if args.training_steps > 0:
@@ -593,6 +593,7 @@ def run_ours(args):
         line["variants"]["training_step"] = {
             "value": tb * S * world / (tms * 1e-3), "unit": "tokens/s", "ms_per_step": tms, "steps": training["steps"],
             "batch_per_gpu": tb,
+            "own_kernel_share": sum(c * ms for c, ms in tk.values()) / tms,
             "kernels": {n: {"calls_per_step": c, "ms_per_call": ms, "ms_per_step": c * ms} for n, (c, ms) in tk.items()},
             "fmha_bwd": {"kernel": "bp_fmha_bwd: bwd_stats_kernel + fmha_bwd_kernel<64, keys own> + fmha_bwd_kernel<64, "
                                    "queries own> (three launches per call)",
@@ -630,7 +631,7 @@ def main():
     ap.add_argument("--fused-loss-steps", type=int, default=30,
                     help="steps of the evaluation-loss variant (0 = skip)")
     ap.add_argument("--training-steps", type=int, default=5, help="steps of the training-step variant (0 = skip)")
-    ap.add_argument("--training-batch", type=int, default=16, help="sequences per GPU in the training-step variant")
+    ap.add_argument("--training-batch", type=int, default=64, help="sequences per GPU in the training-step variant")
     ap.add_argument("--full-logits-steps", type=int, default=3,
                     help="steps of the whole-logits-to-host loop (0 = skip; single GPU only)")
     args = ap.parse_args()

@@ -183,6 +183,30 @@ def bench_bwd_ops(iters, rows=65536, cols=768, inner=3072):
     report(f"bias_act_bwd (bias grad only) {rows}x{cols} bf16", t, tm, 0, rows * cols * 2)
 
 
+def bench_xent(iters, rows=65536, vocab=50264):
+    """bp_xentropy_fwd / bp_xentropy_bwd (in place) at config-3 size: 6.6 GB of bf16 logits."""
+    from backpacks_flash_attn_b200 import _lib
+    x = torch.randn(rows, vocab, device="cuda", dtype=torch.bfloat16)
+    y = torch.randint(0, vocab - 7, (rows,), device="cuda")
+    losses = torch.empty(rows, device="cuda")
+    lse = torch.empty(rows, device="cuda")
+    g = torch.full((rows,), 1.0 / rows, device="cuda")
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    fwd = lambda i: _lib.check(lib.bp_xentropy_fwd(x.data_ptr(), y.data_ptr(), losses.data_ptr(), lse.data_ptr(), rows,
+                                                   vocab, vocab, 0.0, -100, -1, 1, st), "bp_xentropy_fwd")
+    t, tm = time_fn(fwd, 1, iters, inner=2)
+    report(f"xentropy_fwd {rows}x{vocab} bf16", t, tm, 0, rows * vocab * 2)
+    grad = torch.empty_like(x)
+    bwd = lambda i: _lib.check(lib.bp_xentropy_bwd(g.data_ptr(), x.data_ptr(), lse.data_ptr(), y.data_ptr(), grad.data_ptr(),
+                                                   rows, vocab, vocab, vocab, 0.0, -100, -1, 1, st), "bp_xentropy_bwd")
+    t, tm = time_fn(bwd, 1, iters, inner=2)
+    report(f"xentropy_bwd {rows}x{vocab} bf16", t, tm, 0, rows * vocab * 4)
+    ref = lambda i: torch.nn.functional.cross_entropy(x.float(), y)
+    t, tm = time_fn(ref, 1, max(3, iters // 4), inner=1)
+    report("  (comparator, informative) F.cross_entropy on the fp32 upcast, forward only", t, tm, 0, rows * vocab * 2)
+
+
 def bench_sense(iters, b=64, s=1024, nv=16, d=768):
     from backpacks_flash_attn_b200.ops.sense_mix import sense_mix
     from backpacks_flash_attn_b200 import _lib
@@ -292,7 +316,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     for w in a.which.split(","):
         fn = {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms,
-              "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops}[w]
+              "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops, "xent": bench_xent}[w]
         if w in ("fmha", "fmha_bwd") and (a.shape or a.no_comparators):
             b, s_, h, d = (int(x) for x in a.shape.split(",")) if a.shape else (32, 1024, 12, 64)
             fn(a.iters, b=b, s=s_, h=h, d=d, comparators=not a.no_comparators)

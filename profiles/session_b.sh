@@ -1,7 +1,7 @@
 # Round 2, second half: backward kernels (stand-alone timings with comparators, sweep, ncu captures).  bash profiles/session_b.sh
 set -u
 O=gpurun_out; mkdir -p $O
-python benchmarks/bench_kernels.py --which fmha_bwd,bwd_ops > $O/r02w_kernel_bench_bwd.jsonl 2>$O/r02w_kb.err
+python benchmarks/bench_kernels.py --which fmha_bwd,bwd_ops,xent > $O/r02w_kernel_bench_bwd.jsonl 2>$O/r02w_kb.err
 for sh in 64,512,12,64 16,2048,12,64 8,4096,12,64 32,1024,6,128 8,4096,6,128; do
   python benchmarks/bench_kernels.py --which fmha_bwd --shape $sh --no-comparators >> $O/r02w_kernel_bench_bwd.jsonl 2>>$O/r02w_kb.err
 done
