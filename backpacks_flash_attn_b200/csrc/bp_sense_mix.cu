@@ -48,6 +48,11 @@ constexpr int kPolyLse = BP_SENSE_LSE_POLY, kPolyMix = BP_SENSE_MIX_POLY;
 // pass 1: row statistics
 // =============================================================================================
 constexpr int kLseSenses = 4;   // senses per CTA of pass 1 (a CTA per sense spent more time starting up than working)
+// Pass 1 runs FOUR softmax warpgroups: two per query tile, each owning one 64-key half of every 128-key block (the
+// (max, sum) pairs of the two halves of a row are merged once per sense through shared memory).  With one warpgroup
+// per tile (a whole 128-key row per thread) each SM sub-partition hosted two MUFU-bound warps walking a serial chain
+// and the MUFU pipe -- the roofline of this pass -- sat at ~45 %.
+constexpr int kLseThreads = 640;   // 4 service warps + 16 softmax warps
 
 template <int PK>  // 64-column panels covering dk
 struct LseCfg {
@@ -58,7 +63,8 @@ struct LseCfg {
   static constexpr uint32_t kKTileBytes = BN * 128 * PK;
   static constexpr uint32_t offQ = 0;                                  // [QB][2 tiles]
   static constexpr uint32_t offK = offQ + QB * 2 * kQTileBytes;
-  static constexpr uint32_t offBar = offK + kStages * kKTileBytes;
+  static constexpr uint32_t offMerge = offK + kStages * kKTileBytes;   // [2 sense parities][2 tiles][2 halves][128] (m, l)
+  static constexpr uint32_t offBar = offMerge + 2 * 2 * 2 * BM * 8;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
   static constexpr uint32_t kTmemCols = 512;  // S_t[buf] at (t*2+buf)*128
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -84,7 +90,7 @@ struct LseParams {
 // exponential per score, 1/17 of the operator's MMA work): like the attention kernel it keeps a whole 128-key row
 // per thread, takes the row max in eight independent chains, skips 32-key chunks above the diagonal and sums in packed fp32.
 template <int PK, bool kBF16>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kLseThreads, 1)
 sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
   using C = LseCfg<PK>;
   constexpr int BN = C::BN;
@@ -94,7 +100,7 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
   LseBarriers& bars = *reinterpret_cast<LseBarriers*>(smem + C::offBar);
   // roles 0-3 (producers / issuer) run in the highest physical warps, roles 4-11 (softmax) in warps 0-7: the
   // sub-partition arbiter prefers the highest eligible warp id, and the single-thread roles must not starve
-  const int warp = role_warp<12>(), lane = threadIdx.x & 31;
+  const int warp = role_warp<20>(), lane = threadIdx.x & 31;
   const int pair = p.num_pairs - 1 - static_cast<int>(blockIdx.x);
   const int sense0 = blockIdx.y * p.senses_per_cta, batch = blockIdx.z;
   const int n_senses = min(p.senses_per_cta, p.nv - sense0);
@@ -113,7 +119,7 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
     for (int i = 0; i < 2; ++i) mbar_init(&bars.q_full[i], 1), mbar_init(&bars.q_empty[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bars.k_full[i], 1), mbar_init(&bars.k_empty[i], 1);
     for (int t = 0; t < 2; ++t)
-      for (int i = 0; i < 2; ++i) mbar_init(&bars.s_full[t][i], 1), mbar_init(&bars.s_free[t][i], 128);
+      for (int i = 0; i < 2; ++i) mbar_init(&bars.s_full[t][i], 1), mbar_init(&bars.s_free[t][i], 256);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -127,7 +133,7 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
   const int tok0 = batch * S;  // first row of this batch in the flattened (b*s) token dimension
 
   if (warp < 4) {
-    reg_dealloc<56>();
+    // (no setmaxnreg in this kernel: 640 threads x 96 registers fit the register file as compiled)
     if (warp == 0) {
       // ---- producer: per sense the Q tiles of both query tiles (coordinate 1 = which*nv + sense), K ring ----
       const int n_q_tiles = (row0 + BM < S) ? 2 : 1;
@@ -189,25 +195,29 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
       }
     }
   } else {
-    reg_alloc<224>();
-    const int t = (warp >> 2) - 1;
-    const int r = (warp & 3) * 32 + lane;
+    constexpr int HN = BN / 2;         // keys per block and thread
+    constexpr int NCH = HN / 32;
+    const int sr = warp - 4;           // softmax warp 0..15
+    const int t = sr >> 3;             // query tile
+    const int half = (sr >> 2) & 1;    // which 64-key half of every block
+    const int r = (sr & 3) * 32 + lane;
     const int n = n_blk[t];
     if (n > 0) {
       const int row0_t = row0 + t * BM;
       const int qrow = row0_t + r;
-      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t lane_addr = static_cast<uint32_t>((sr & 3) * 32) << 16;
       const float c2 = p.scale_log2;
+      float2* merge = reinterpret_cast<float2*>(smem + C::offMerge);
       int c = 0;   // S tiles consumed (all senses)
       for (int si = 0; si < n_senses; ++si) {
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < n; ++j, ++c) {
           mbar_wait(&bars.s_full[t][c & 1], (c >> 1) & 1);
           tc_fence_after();
-          float s[BN];
-          const uint32_t tS = tmem_base + lane_addr + (t * 2 + (c & 1)) * BN;
+          float s[HN];
+          const uint32_t tS = tmem_base + lane_addr + (t * 2 + (c & 1)) * BN + half * HN;
 #pragma unroll
-          for (int cc = 0; cc < NC; ++cc) {
+          for (int cc = 0; cc < NCH; ++cc) {
             uint32_t u[32];
             tmem_ld32(tS + cc * 32, u);
 #pragma unroll
@@ -216,12 +226,12 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&bars.s_free[t][c & 1]);
-          const int col0 = j * BN;
+          const int col0 = j * BN + half * HN;
           uint32_t dead = 0;   // bit cc: chunk cc is above the diagonal for every row of this warp
-          if (col0 + BN - 1 > row0_t) {  // block touches the diagonal (also covers cols >= seqlen)
-            const int lim = qrow + 1 - col0;   // visible keys of this row inside the block
+          if (col0 + HN - 1 > row0_t) {  // this half block touches the diagonal (also covers cols >= seqlen)
+            const int lim = qrow + 1 - col0;   // visible keys of this row inside the half block
 #pragma unroll
-            for (int cc = 0; cc < NC; ++cc) {
+            for (int cc = 0; cc < NCH; ++cc) {
               if (!__all_sync(0xffffffffu, lim >= (cc + 1) * 32)) {
                 if (__all_sync(0xffffffffu, lim <= cc * 32)) {
                   dead |= 1u << cc;
@@ -236,7 +246,7 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) mx8[k] = -INFINITY;
 #pragma unroll
-          for (int cc = 0; cc < NC; ++cc) {
+          for (int cc = 0; cc < NCH; ++cc) {
             if (!((dead >> cc) & 1u)) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
@@ -247,11 +257,13 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
           }
           const float mxa = fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3]));
           const float mxb = fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]));
-          const float m_new = fmaxf(m, fmaxf(mxa, mxb));  // column 0 is always visible, so m_new is finite
-          const float neg = -m_new * c2;
+          const float m_new = fmaxf(m, fmaxf(mxa, mxb));
+          // the second half of a block may hold no visible key for a row: keep (m, l) = (-inf, 0) without a NaN
+          const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+          const float neg = -m_ref * c2;
           float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int cc = 0; cc < NC; ++cc) {
+          for (int cc = 0; cc < NCH; ++cc) {
             if (!((dead >> cc) & 1u)) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
@@ -264,11 +276,20 @@ sense_lse_kernel(const __grid_constant__ CUtensorMap tmQK, const LseParams p) {
               }
             }
           }
-          l = l * fast_exp2((m - m_new) * c2) + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+          l = l * fast_exp2((m - m_ref) * c2) + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
           m = m_new;
         }
-        if (qrow < S)
-          p.lse[(static_cast<int64_t>(batch) * p.nv + sense0 + si) * S + qrow] = m * p.scale + logf(l);
+        // merge the two halves of the row (once per sense): the odd half publishes, the even half combines and stores
+        float2* slot = merge + ((si & 1) * 4 + t * 2) * BM;
+        if (half == 1) slot[BM + r] = make_float2(m, l);
+        if (t == 0) named_bar_sync(1, 256);
+        else named_bar_sync(2, 256);
+        if (half == 0) {
+          const float2 o = slot[BM + r];
+          const float M = fmaxf(m, o.x);   // the even half always sees key 0: finite
+          const float L = l * fast_exp2((m - M) * c2) + (o.x == -INFINITY ? 0.f : o.y * fast_exp2((o.x - M) * c2));
+          if (qrow < S) p.lse[(static_cast<int64_t>(batch) * p.nv + sense0 + si) * S + qrow] = M * p.scale + logf(L);
+        }
       }
     }
   }
@@ -776,7 +797,7 @@ static int launch_lse(const CUtensorMap& tm, const LseParams& p, int batch, cuda
   while (pp.senses_per_cta > 1 &&
          static_cast<int64_t>(p.num_pairs) * ((p.nv + pp.senses_per_cta - 1) / pp.senses_per_cta) * batch < 4 * sms)
     pp.senses_per_cta >>= 1;
-  kern<<<dim3(p.num_pairs, (p.nv + pp.senses_per_cta - 1) / pp.senses_per_cta, batch), kThreads, C::kSmemBytes, st>>>(tm, pp);
+  kern<<<dim3(p.num_pairs, (p.nv + pp.senses_per_cta - 1) / pp.senses_per_cta, batch), kLseThreads, C::kSmemBytes, st>>>(tm, pp);
   return check_launch("bp_sense_lse_fwd launch");
 }
 
