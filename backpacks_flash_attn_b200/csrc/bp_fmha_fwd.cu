@@ -607,26 +607,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tr.rec(3, cnt);
-        if (j > 0) {
-          // the P buffer and the O accumulator are free once the previous PV product of this tile has completed
-          mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
-          tc_fence_after();
-          tr.rec(4, cnt);
-          if (__any_sync(0xffffffffu, grow)) {
-            // rare path: 16 columns at a time keeps the register footprint next to the live S row small
-#pragma unroll 1
-            for (int c = 0; c < DP / 16; ++c) {
-              uint32_t o[16];
-              tmem_ld16(tO + c * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(tO + c * 16, o);
-            }
-            tmem_st_wait();
-          }
-          l *= alpha;
-        }
+        l *= alpha;   // (alpha = 1 unless the maximum grew: the rescaling of O itself waits for the previous product, below)
 
         const float neg_m = -m_used * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -668,28 +649,47 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         };
+        // The exponentials of the whole block go to registers FIRST; only then does the thread wait for the previous
+        // P.V product of its tile (P buffer and O accumulator free), rescale O in the rare case and store P.  With the
+        // wait in front of the exponentials (rounds 1-2) every block idled here for the hand-over round trip
+        // p_ready -> issuer wake-up -> 8 MMAs -> commit -> wake-up (~700 cycles of a ~2000-cycle block).
+        uint32_t pk[NC][16];
         if (!partial) {
           // common case: one straight-line block, so the scheduler can overlap the chunks' phases
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            uint32_t pk[16];
-            exp_chunk(c, pk);
-            tmem_st16(tP + c * 16, pk);
-          }
+          for (int c = 0; c < NC; ++c) exp_chunk(c, pk[c]);
         } else {
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            uint32_t pk[16];
             if ((dead >> c) & 1u) {
               // above the causal diagonal: P = 0 without a single exponential
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = 0u;
+              for (int i = 0; i < 16; ++i) pk[c][i] = 0u;
             } else {
-              exp_chunk(c, pk);
+              exp_chunk(c, pk[c]);
             }
-            tmem_st16(tP + c * 16, pk);
           }
         }
+        if (j > 0) {
+          // the P buffer and the O accumulator are free once the previous PV product of this tile has completed
+          mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
+          tc_fence_after();
+          tr.rec(4, cnt);
+          if (__any_sync(0xffffffffu, grow)) {
+            // rare path: 16 columns at a time keeps the register footprint small
+#pragma unroll 1
+            for (int c = 0; c < DP / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_st16(tP + c * 16, pk[c]);
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         tmem_st_wait();
         tr.rec(5, cnt);
