@@ -121,8 +121,7 @@ def _flash_attn_backward(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens
     written in place, as flash_attn_interface.py:77-83 does).  Mirrors flash_attn_interface.py:31-47; returns
     (dq, dk, dv)."""
     _lib.require_cuda(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens_q, cu_seqlens_k)
-    if dout.stride(-1) != 1:
-        dout = dout.contiguous()
+    dout = dout.contiguous()   # e.g. the stride-0 gradient of out.sum(); the reference does the same (line 41)
     if q.dtype not in (torch.float16, torch.bfloat16):
         raise RuntimeError("FlashAttention only support fp16 and bf16 data type")
     if any(t.dtype != q.dtype for t in (dout, k, v, out, dq, dk, dv)) or softmax_lse.dtype != torch.float32:

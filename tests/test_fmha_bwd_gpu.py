@@ -233,6 +233,25 @@ def test_fmha_bwd_through_the_modules():
         assert O.max_abs(p1.grad, p2.grad) / scale < 3e-2, n1
 
 
+def test_fmha_bwd_accepts_expanded_and_strided_upstream_gradients():
+    """out.sum().backward() hands the node a stride-0 gradient; a transposed consumer hands it a strided one."""
+    F = _ops()
+    qkv = _make_qkv(2, 200, 3, 64, torch.bfloat16, seed=5).reshape(400, 3, 3, 64)
+    cu = torch.arange(0, 600, 200, dtype=torch.int32, device="cuda")
+    x = qkv.clone().requires_grad_(True)
+    F.flash_attn_unpadded_qkvpacked_func(x, cu, 200, 0.0, causal=True).sum().backward()
+    y = qkv.clone().requires_grad_(True)
+    out = F.flash_attn_unpadded_qkvpacked_func(y, cu, 200, 0.0, causal=True)
+    out.backward(torch.ones_like(out))
+    assert torch.equal(x.grad, y.grad) and torch.isfinite(x.grad.float()).all()
+    z = qkv.clone().requires_grad_(True)
+    w = torch.randn(64, 3, 400, device="cuda").bfloat16()
+    (F.flash_attn_unpadded_qkvpacked_func(z, cu, 200, 0.0, causal=True).permute(2, 1, 0) * w).sum().backward()
+    z2 = qkv.clone().requires_grad_(True)
+    F.flash_attn_unpadded_qkvpacked_func(z2, cu, 200, 0.0, causal=True).backward(w.permute(2, 1, 0).contiguous())
+    assert torch.equal(z.grad, z2.grad)
+
+
 def test_fmha_bwd_rejects_bad_arguments():
     F = _ops()
     qkv = torch.zeros(64, 3, 2, 64, device="cuda", dtype=torch.bfloat16)
