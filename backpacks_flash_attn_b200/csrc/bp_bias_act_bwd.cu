@@ -16,7 +16,7 @@ namespace bp {
 namespace bab {
 
 constexpr int kTX = 32, kTY = 8;          // 32 x 8 threads: 256 columns x 8 rows per pass
-constexpr int kMaxParts = 64;             // row slabs (grid.y) = partial rows in the workspace
+constexpr int kMaxParts = 256;            // row slabs (grid.y) = partial rows in the workspace
 
 template <bool kBF16>
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {

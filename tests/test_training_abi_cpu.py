@@ -28,7 +28,7 @@ def test_workspace_queries(lib):
             == lib.bp_fmha_bwd_workspace_bytes(2, 3, 1000) + 2 * 3 * 256 * 4)
     assert lib.bp_fmha_fwd_dropout_workspace_bytes(2, 3, 130) == 2 * 3 * 256 * 4
     assert lib.bp_ln_bwd_workspace_bytes(768) == 1024 * 2 * 768 * 4
-    assert lib.bp_bias_act_bwd_workspace_bytes(3072) == 64 * 3072 * 4
+    assert lib.bp_bias_act_bwd_workspace_bytes(3072) == 256 * 3072 * 4
 
 
 def test_backward_entry_points_validate_before_touching_the_gpu(lib):
