@@ -45,6 +45,7 @@ namespace fmha_bwd {
 constexpr int BS = 128;   // stationary rows per CTA (= TMEM lanes)
 constexpr int BT = 64;    // streaming rows per step
 constexpr int kStatsWords = 3 * BT;   // words per 64-row block of the statistics workspace
+constexpr int kItemSlots = 4;         // shared-memory ring of decoded work items (producer -> the other roles)
 constexpr float kLog2e = 1.4426950408889634f;
 #ifndef BP_FMHA_BWD_POLY
 #define BP_FMHA_BWD_POLY 2
@@ -67,7 +68,8 @@ struct Cfg {
   static constexpr uint32_t offStat2 = kStatTileBytes;
   static constexpr uint32_t offStr = 2 * kStatTileBytes;
   static constexpr uint32_t offStage = offStr + kStages * kStageBytes;   // [128 rows][DP * 2 B] epilogue staging tile
-  static constexpr uint32_t offBar = offStage + BS * DP * 2;
+  static constexpr uint32_t offItems = offStage + BS * DP * 2;          // ring of decoded work items
+  static constexpr uint32_t offBar = offItems + kItemSlots * 64;
   static constexpr uint32_t kSmemBytes = offBar + 256 + 1024;
   // TMEM columns.  Keys own: T1, T2, dV, dK (256 at head dim 64: full).  Queries own: T1, two T2 buffers, dQ -- the
   // spare columns double-buffer dP, so both products of step n+1 are issued while step n's dS is being formed.
@@ -97,6 +99,8 @@ struct Params {
   int32_t batch, nheads, headdim;
   int32_t num_tiles;         // stationary tiles per sequence
   int32_t chunk_bh;          // (batch, head) pairs per scheduling chunk
+  int32_t num_tickets;       // chunks * chunk_bh * num_tiles
+  unsigned int* sched;       // this launch's ticket counter (zeroed in front of the kernel)
   int32_t is_causal;
   float scale, scale_log2;
   uint64_t* trace;           // debug: per-role event timestamps of CTA 0 (null in production)
@@ -105,6 +109,7 @@ struct Params {
 struct Barriers {
   uint64_t stat_full, t1_full, t2_full[2], x1_ready, x2_ready[2], acc_full, acc_free;   // t2_full / x2_ready: per T2 buffer
   uint64_t str_full[3], str_empty[3];
+  uint64_t item_full[kItemSlots], item_empty[kItemSlots];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Barriers) <= 256, "barrier block");
@@ -224,22 +229,41 @@ bwd_stats_kernel(const void* __restrict__ dout, const void* __restrict__ out, co
 // ------------------------------------------------------------------------------------------------------------------
 // launches 2 and 3
 // ------------------------------------------------------------------------------------------------------------------
-// One work item = one stationary tile (128 rows of one (batch, head)).  The schedule is static: CTA c of G walks the
-// scheduling chunks (chunk_bh (batch, head) pairs x num_tiles tiles = G items, sized to one wave of 2 CTAs per SM, so
-// the CTAs that run together sweep the same K/V/Q/dO in L2) and takes position c of every chunk; under causal masking
-// the tile rank is mirrored in odd chunks, so every CTA alternates heavy and light tiles (rank r and T-1-r add up to a
-// constant number of steps).  Every warp role derives the same item sequence on its own.
+// One work item = one stationary tile (128 rows of one (batch, head)).  Tickets are handed out DYNAMICALLY: the items
+// are numbered chunk by chunk (chunk_bh (batch, head) pairs x num_tiles tiles, sized to one wave of 2 CTAs per SM, so
+// the CTAs that run together sweep the same K/V/Q/dO in L2), heaviest tiles of a chunk first; every CTA starts with
+// ticket blockIdx.x and its producer warp draws the following ones from a per-launch counter (zeroed by a memset in
+// front of the kernel) and publishes the decoded item to the other warp roles through a small shared-memory ring.
+// (The first persistent version used a static mirrored schedule: with 10.4 chunks at config 2 the CTAs ended between
+// 136 and 176 us.)  Which CTA computes a tile does not affect its result: the gradients stay bit-wise reproducible.
 struct Item {
   int valid;
   int bh, batch, head, row0;
   int stat_begin, len_stat, str_begin, len_str;
   int first, n_steps;
+  int end;   // sentinel: no more work for this CTA
 };
+
+__device__ __forceinline__ void put_item(uint32_t a, const Item& it) {
+  sts128(a, it.valid, it.bh, it.batch, it.head);
+  sts128(a + 16, it.row0, it.stat_begin, it.len_stat, it.str_begin);
+  sts128(a + 32, it.len_str, it.first, it.n_steps, it.end);
+}
+__device__ __forceinline__ Item get_item(uint32_t a) {
+  const uint4 x = lds128(a), y = lds128(a + 16), z = lds128(a + 32);
+  Item it;
+  it.valid = x.x; it.bh = x.y; it.batch = x.z; it.head = x.w;
+  it.row0 = y.x; it.stat_begin = y.y; it.len_stat = y.z; it.str_begin = y.w;
+  it.len_str = z.x; it.first = z.y; it.n_steps = z.z; it.end = z.w;
+  return it;
+}
 
 template <bool kDQ>
 __device__ __forceinline__ Item decode_item(const Params& p, int chunk, int pos) {
   Item it;
   it.valid = 0;
+  it.end = 0;
+  it.bh = it.batch = it.head = it.row0 = it.stat_begin = it.len_stat = it.str_begin = it.len_str = it.first = it.n_steps = 0;
   const int total_bh = p.batch * p.nheads;
   const int bh0 = chunk * p.chunk_bh;
   const int gc = min(p.chunk_bh, total_bh - bh0);
@@ -248,7 +272,6 @@ __device__ __forceinline__ Item decode_item(const Params& p, int chunk, int pos)
   it.bh = bh0 + (pos - rank * gc);
   it.batch = it.bh / p.nheads;
   it.head = it.bh - it.batch * p.nheads;
-  if (p.is_causal && (chunk & 1)) rank = p.num_tiles - 1 - rank;
   const int tile = (kDQ && p.is_causal) ? p.num_tiles - 1 - rank : rank;   // rank 0 = most steps
   it.row0 = tile * BS;
   const int q_begin = __ldg(p.cu_q + it.batch), len_q = __ldg(p.cu_q + it.batch + 1) - q_begin;
@@ -281,9 +304,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
   uint64_t cta_t0 = 0;
   if (p.trace && threadIdx.x == 0 && blockIdx.x < 4096) cta_t0 = global_timer_ns();
 #endif
-  const int total_bh = p.batch * p.nheads;
-  const int chunks = (total_bh + p.chunk_bh - 1) / p.chunk_bh;
-  const int pos = blockIdx.x;
+  const int per_chunk = p.chunk_bh * p.num_tiles;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -313,6 +334,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
       mbar_init(&bars.str_full[i], 1);
       mbar_init(&bars.str_empty[i], 1);
     }
+    for (int i = 0; i < kItemSlots; ++i) {
+      mbar_init(&bars.item_full[i], 1);
+      mbar_init(&bars.item_empty[i], 1 + 8);   // one lane of every consumer warp (issuer, 8 softmax warps)
+    }
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -324,6 +349,19 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = bars.tmem_base;
 
+  // every consumer role walks the item ring with its own sequence number
+  const uint32_t items_a = smem_a + C::offItems;
+  uint32_t item_seq = 0;
+  auto next_item = [&]() {
+    const uint32_t islot = item_seq % kItemSlots;
+    mbar_wait_a(BBAR_I(item_full, islot), (item_seq / kItemSlots) & 1);
+    const Item it = get_item(items_a + islot * 64);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(BBAR_I(item_empty, islot));
+    ++item_seq;
+    return it;
+  };
+
   // Barrier phases run on across items: `ic` counts this CTA's items that have steps (stat_full, acc_full, acc_free
   // complete once per such item), `sc` counts steps (t1_full, t2_full, x1_ready, x2_ready), slot / ph walk the ring.
   if (warp == 8) {
@@ -332,9 +370,43 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     uint32_t blk = 0;            // streaming blocks loaded so far
     uint32_t ic = 0;
     Tracer tr(p.trace, 0, blockIdx.x == 0 && lane == 0);
-    for (int ch = 0; ch < chunks; ++ch) {
-      const Item it = decode_item<kDQ>(p, ch, pos);
-      if (!it.valid || it.n_steps == 0) continue;
+    uint32_t seq = 0;            // items published (valid items + the end marker)
+    auto publish = [&](const Item& pit) {
+      const uint32_t islot = seq % kItemSlots;
+      if (seq >= kItemSlots) mbar_wait_a(BBAR_I(item_empty, islot), ((seq / kItemSlots) - 1) & 1);
+      if (lane == 0) {
+        put_item(items_a + islot * 64, pit);
+        mbar_arrive_a(BBAR_I(item_full, islot));
+      }
+      ++seq;
+    };
+    auto draw = [&]() {   // next ticket (lane 0 draws, the warp shares it)
+      unsigned int d = 0;
+      if (lane == 0) d = gridDim.x + atomicAdd(p.sched, 1u);
+      return static_cast<int>(__shfl_sync(0xffffffffu, d, 0));
+    };
+    auto fetch_valid = [&](int& w) {   // the item of ticket w, or of the next ticket that decodes to a valid tile
+      while (w < p.num_tickets) {
+        const Item c = decode_item<kDQ>(p, w / per_chunk, w % per_chunk);
+        if (c.valid) return c;
+        w = draw();
+      }
+      Item fin = decode_item<kDQ>(p, 0, 0);
+      fin.valid = 0;
+      fin.end = 1;
+      return fin;
+    };
+    int w = blockIdx.x;   // the first ticket is static
+    Item cur = fetch_valid(w);
+    publish(cur);
+    while (!cur.end) {
+      const Item it = cur;
+      int w_next = draw();   // drawn early: the counter's round trip hides behind this item's loads
+      if (it.n_steps == 0) {   // nothing to load (the softmax warps write zeros)
+        cur = fetch_valid(w_next);
+        publish(cur);
+        continue;
+      }
       // the stationary tiles of the previous item are free once all of its products have completed
       if (ic > 0) mbar_wait_a(BBAR(acc_full), (ic - 1) & 1);
       mbar_arrive_expect_tx_w(BBAR(stat_full), 2 * C::kStatTileBytes);
@@ -370,6 +442,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
         }
       }
       ++ic;
+      cur = fetch_valid(w_next);
+      publish(cur);
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
@@ -400,9 +474,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     uint32_t slot = 0, ph = 0;
     uint32_t sc = 0, ic = 0;
     Tracer tr(p.trace, 1, blockIdx.x == 0 && lane == 0);
-    for (int ch = 0; ch < chunks; ++ch) {
-      const Item it = decode_item<kDQ>(p, ch, pos);
-      if (!it.valid || it.n_steps == 0) continue;
+    while (true) {
+      const Item it = next_item();
+      if (it.end) break;
+      if (it.n_steps == 0) continue;
       const int n_steps = it.n_steps;
       tr.rec(0, ic);
       mbar_wait_a(BBAR(stat_full), ic & 1);
@@ -490,12 +565,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmStat1, const __grid_consta
     uint32_t sc = 0, ic = 0;
     Tracer tr(p.trace, 2 + g, blockIdx.x == 0 && lane == 0 && (warp & 3) == 0);
     bool store_pending = false;   // (thread 0) a bulk store may still be reading the staging tile
-    Item nxt = decode_item<kDQ>(p, 0, pos);
-    for (int ch = 0; ch < chunks; ++ch) {
-      const Item it = nxt;
-      // the next item is decoded one item ahead: its cu_seqlens loads complete behind this item's work
-      if (ch + 1 < chunks) nxt = decode_item<kDQ>(p, ch + 1, pos);
-      if (!it.valid) continue;
+    while (true) {
+      const Item it = next_item();
+      if (it.end) break;
       const int row0 = it.row0;
       const int row = row0 + r;
       const int len_str = it.len_str;
@@ -799,9 +871,17 @@ int launch(const CUtensorMap& s1, const CUtensorMap& s2, const CUtensorMap& b1, 
     cudaGetLastError();
     return fail(BP_ERR_CUDA, "bp_fmha_bwd: cudaFuncSetAttribute(%u B smem): %s", C::kSmemBytes, cudaGetErrorString(e));
   }
-  // one CTA per position of a scheduling chunk (see decode_item): a single wave that walks all chunks
-  const int total_bh = p.batch * p.nheads;
-  const int64_t grid = static_cast<int64_t>(p.chunk_bh < total_bh ? p.chunk_bh : total_bh) * p.num_tiles;
+  // one resident wave of CTAs; each starts with ticket blockIdx.x and draws the rest from the counter
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int resident = C::kCtasPerSm * sms;
+  const int grid = p.num_tickets < resident ? p.num_tickets : resident;
+  e = cudaMemsetAsync(p.sched, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(BP_ERR_CUDA, "bp_fmha_bwd: cudaMemsetAsync(scheduler counter): %s", cudaGetErrorString(e));
+  }
   kern<<<static_cast<unsigned>(grid), C::kThreads, C::kSmemBytes, stream>>>(s1, s2, b1, b2, o1, o2, p);
   return check_launch(kDQ ? "bp_fmha_bwd (dQ) launch" : "bp_fmha_bwd (dK, dV) launch");
 }
@@ -832,9 +912,11 @@ int drop_threshold(float p) {
 }
 }  // namespace bp
 
+// workspace = [2 ticket counters, padded to 16 bytes][row statistics][dropout column words]
+constexpr int64_t kSchedBytes = 16;
 static int64_t stats_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q) {
   const int64_t s_pad = (static_cast<int64_t>(max_seqlen_q) + 127) / 128 * 128;
-  return static_cast<int64_t>(batch) * nheads * (s_pad / 64) * bp::fmha_bwd::kStatsWords * 4;
+  return kSchedBytes + static_cast<int64_t>(batch) * nheads * (s_pad / 64) * bp::fmha_bwd::kStatsWords * 4;
 }
 
 extern "C" int64_t bp_fmha_bwd_workspace_bytes(int32_t batch, int32_t nheads, int32_t max_seqlen_q) {
@@ -891,7 +973,8 @@ static int fmha_bwd_impl(const void* dout, const void* q, const void* k, const v
   const int s_pad = (max_seqlen_q + 127) / 128 * 128;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf16 = dtype == BP_DTYPE_BF16;
-  float* stats = static_cast<float*>(workspace);
+  unsigned int* sched = static_cast<unsigned int*>(workspace);
+  float* stats = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kSchedBytes);
 
   {
     dim3 grid(batch * nheads, s_pad / 64);
@@ -956,8 +1039,17 @@ static int fmha_bwd_impl(const void* dout, const void* q, const void* k, const v
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
   // keys own: dK, dV
-  p.num_tiles = (max_seqlen_k + fmha_bwd::BS - 1) / fmha_bwd::BS;
-  p.chunk_bh = fmha_bwd::chunk_bh_for(DP, sms, p.num_tiles, batch * nheads);
+  auto set_tiles = [&](int max_seqlen, unsigned int* counter) -> int {
+    p.num_tiles = (max_seqlen + fmha_bwd::BS - 1) / fmha_bwd::BS;
+    p.chunk_bh = fmha_bwd::chunk_bh_for(DP, sms, p.num_tiles, batch * nheads);
+    const int64_t chunks = (static_cast<int64_t>(batch) * nheads + p.chunk_bh - 1) / p.chunk_bh;
+    const int64_t tickets = chunks * p.chunk_bh * p.num_tiles;
+    if (tickets > 0x3fffffff) return fail(BP_ERR_INVALID_ARGUMENT, "bp_fmha_bwd: too many work items");
+    p.num_tickets = static_cast<int32_t>(tickets);
+    p.sched = counter;
+    return BP_OK;
+  };
+  if (int rc0 = set_tiles(max_seqlen_k, sched)) return rc0;
   p.out1 = dv;
   p.o1_row_stride = s_dv[0];
   p.o1_head_stride = s_dv[1];
@@ -977,8 +1069,7 @@ static int fmha_bwd_impl(const void* dout, const void* q, const void* k, const v
   if (rc) return rc;
 
   // queries own: dQ
-  p.num_tiles = (max_seqlen_q + fmha_bwd::BS - 1) / fmha_bwd::BS;
-  p.chunk_bh = fmha_bwd::chunk_bh_for(DP, sms, p.num_tiles, batch * nheads);
+  if (int rc0 = set_tiles(max_seqlen_q, sched + 1)) return rc0;
 #ifdef BP_TRACE
   p.trace = (trace_mode && trace_mode[0] == 'd' && trace_mode[1] == 'q') ? g_trace : nullptr;
 #endif

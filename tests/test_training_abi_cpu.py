@@ -21,8 +21,9 @@ def _aligned(nbytes=256):
 
 
 def test_workspace_queries(lib):
-    # attention backward: per 64-row block 3 x 64 fp32 words (-lse, -delta, dropout word), rows padded to 128
-    assert lib.bp_fmha_bwd_workspace_bytes(2, 3, 1000) == 2 * 3 * (1024 // 64) * 192 * 4
+    # attention backward: two ticket counters (16 bytes), then per 64-row block 3 x 64 fp32 words (-lse, -delta, dropout
+    # word), rows padded to 128
+    assert lib.bp_fmha_bwd_workspace_bytes(2, 3, 1000) == 16 + 2 * 3 * (1024 // 64) * 192 * 4
     assert lib.bp_fmha_bwd_workspace_bytes(0, 3, 1000) == 0
     assert (lib.bp_fmha_bwd_dropout_workspace_bytes(2, 3, 1000, 130)
             == lib.bp_fmha_bwd_workspace_bytes(2, 3, 1000) + 2 * 3 * 256 * 4)
