@@ -46,7 +46,7 @@ SIGNATURES = {
     "bp_linear_bias_residual_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_ln_fwd": [c_void_p] * 6 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_ln_bwd_workspace_bytes": [c_int32],
-    "bp_ln_residual_bwd": [c_void_p] * 9 + [c_int64, c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
+    "bp_ln_residual_bwd": [c_void_p] * 11 + [c_int64, c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_bias_act_bwd_workspace_bytes": [c_int32],
     "bp_bias_act_bwd": [c_void_p] * 5 + [c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_xentropy_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int64, c_float, c_int64, c_int32, c_int32, c_void_p],

@@ -7,7 +7,8 @@
 // (`dx_residual` is the gradient that arrives through the residual output of a pre-norm block.)
 //
 // HBM-bound like the forward: one warp owns a row and keeps it in registers, 16-byte accesses, shuffle reductions; mu
-// and rsigma are recomputed from the row (two more shuffle reductions instead of two more loads).  dgamma / dbeta are
+// and rsigma come from the forward when the caller saved them (two loads instead of two of the four dependent shuffle
+// reductions of a row, and exactly the forward's statistics), else they are recomputed from the row.  dgamma / dbeta are
 // accumulated per lane across the rows a warp visits, reduced across the CTA's warps through shared memory in a fixed
 // order, written as one fp32 partial row per CTA and summed by a second tiny kernel: deterministic, no atomics (the
 // reference uses the same two-stage scheme, ln_bwd_kernels.cuh + ln_bwd_finalize_kernel).
@@ -85,8 +86,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <typename X, typename R, typename W, int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, NV <= 3 ? 2 : 1)
 ln_residual_bwd_kernel(const X* __restrict__ dz, const R* __restrict__ dxres, const R* __restrict__ x,
-                       const W* __restrict__ gamma, X* __restrict__ dx0, R* __restrict__ dx1,
-                       float* __restrict__ part /* [gridDim.x][2][cols] */, int64_t rows, int cols, float eps) {
+                       const W* __restrict__ gamma, const float* __restrict__ mu_in, const float* __restrict__ rs_in,
+                       X* __restrict__ dx0, R* __restrict__ dx1, float* __restrict__ part /* [gridDim.x][2][cols] */,
+                       int64_t rows, int cols, float eps) {
   extern __shared__ float lnb_smem[];   // [kWarpsPerCta][cols] reduction buffer (dgamma, then dbeta), then [cols] gamma
   float* s_gamma = lnb_smem + kWarpsPerCta * cols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -124,18 +126,24 @@ ln_residual_bwd_kernel(const X* __restrict__ dz, const R* __restrict__ dxres, co
         for (int k = 0; k < 8; ++k) sum += xv[i][k];
       }
     }
-    const float mu = warp_sum(sum) * inv_cols;
-    float sq = 0.f;
+    float mu, rs;
+    if (mu_in != nullptr) {   // (uniform branch) the forward's statistics
+      mu = __ldg(mu_in + row);
+      rs = __ldg(rs_in + row);
+    } else {
+      mu = warp_sum(sum) * inv_cols;
+      float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (i * 32 + lane < nvec) {
+      for (int i = 0; i < NV; ++i)
+        if (i * 32 + lane < nvec) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = xv[i][k] - mu;
-          sq += d * d;
+          for (int k = 0; k < 8; ++k) {
+            const float d = xv[i][k] - mu;
+            sq += d * d;
+          }
         }
-      }
-    const float rs = rsqrtf(warp_sum(sq) * inv_cols + eps);
+      rs = rsqrtf(warp_sum(sq) * inv_cols + eps);
+    }
     // y in place of x; dy in place of dz; the two row means
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -227,8 +235,9 @@ ln_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int cols, W* 
 }
 
 template <typename X, typename R, typename W, int NV>
-int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamma, void* dx0, void* dx1, void* dgamma,
-              void* dbeta, float* part, int64_t rows, int cols, float eps, cudaStream_t st) {
+int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamma, const float* mu, const float* rs,
+              void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps,
+              cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -246,7 +255,7 @@ int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamm
     }
   }
   kern<<<grid, kWarpsPerCta * 32, smem, st>>>(static_cast<const X*>(dz), static_cast<const R*>(dxres),
-                                              static_cast<const R*>(x), static_cast<const W*>(gamma),
+                                              static_cast<const R*>(x), static_cast<const W*>(gamma), mu, rs,
                                               static_cast<X*>(dx0), static_cast<R*>(dx1), part, rows, cols, eps);
   if (int rc = check_launch("bp_ln_residual_bwd launch")) return rc;
   ln_bwd_finalize_kernel<W><<<(cols + 31) / 32, dim3(32, 16), 0, st>>>(part, grid, cols, static_cast<W*>(dgamma),
@@ -255,11 +264,11 @@ int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamm
 }
 
 template <typename X, typename R, typename W>
-int launch(const void* dz, const void* dxres, const void* x, const void* gamma, void* dx0, void* dx1, void* dgamma,
-           void* dbeta, float* part, int64_t rows, int cols, float eps, cudaStream_t st) {
+int launch(const void* dz, const void* dxres, const void* x, const void* gamma, const float* mu, const float* rs,
+           void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps, cudaStream_t st) {
   const int nv = (cols / 8 + 31) / 32;
 #define BP_LNB_CASE(N) \
-  if (nv <= N) return launch_nv<X, R, W, N>(dz, dxres, x, gamma, dx0, dx1, dgamma, dbeta, part, rows, cols, eps, st)
+  if (nv <= N) return launch_nv<X, R, W, N>(dz, dxres, x, gamma, mu, rs, dx0, dx1, dgamma, dbeta, part, rows, cols, eps, st)
   BP_LNB_CASE(1);
   BP_LNB_CASE(2);
   BP_LNB_CASE(3);
@@ -277,13 +286,16 @@ extern "C" int64_t bp_ln_bwd_workspace_bytes(int32_t cols) {
   return cols > 0 ? static_cast<int64_t>(bp::lnb::kMaxCtas) * 2 * cols * 4 : 0;
 }
 
-extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma, void* dx0,
+extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma,
+                                  const float* mu, const float* rsigma, void* dx0,
                                   void* dx1, void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes,
                                   int64_t rows, int32_t cols, float epsilon, int32_t x0_dtype, int32_t residual_dtype,
                                   int32_t weight_dtype, void* stream) {
   using namespace bp;
   if (!dz || !x || !gamma || !dx0 || !dgamma || !dbeta || !workspace)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_bwd: null pointer argument");
+  if ((mu == nullptr) != (rsigma == nullptr))
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_bwd: mu and rsigma must be given together (or both NULL)");
   if (rows <= 0 || cols <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_bwd: empty input");
   if (cols % 8 != 0)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_bwd: hidden size must be a multiple of 8 (got %d)", cols);
@@ -299,7 +311,7 @@ extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const
   const int key = x0_dtype * 100 + residual_dtype * 10 + weight_dtype;
 #define BP_LNB_DISPATCH(XD, RD, WD, X, R, W) \
   if (key == XD * 100 + RD * 10 + WD)        \
-  return lnb::launch<X, R, W>(dz, dx_residual, x, gamma, dx0, dx1, dgamma, dbeta, part, rows, cols, epsilon, st)
+  return lnb::launch<X, R, W>(dz, dx_residual, x, gamma, mu, rsigma, dx0, dx1, dgamma, dbeta, part, rows, cols, epsilon, st)
   using bf = __nv_bfloat16;
   using hf = __half;
   BP_LNB_DISPATCH(BP_DTYPE_BF16, BP_DTYPE_F32, BP_DTYPE_BF16, bf, float, bf);

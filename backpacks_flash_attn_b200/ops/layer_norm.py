@@ -10,7 +10,7 @@ import torch.nn as nn
 from .. import _lib
 
 
-def _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, want_residual):
+def _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, want_residual, want_stats=False):
     _lib.require_cuda(x0, x1, gamma, beta)
     cols = x0.shape[-1]
     x0m = x0.reshape(-1, cols)
@@ -34,16 +34,17 @@ def _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, want_re
     # the residual stream only has to be written when it differs from x0 or the caller wants it back
     need_x = want_residual and (x1 is not None or rdtype != x0.dtype)
     x_out = torch.empty((rows, cols), dtype=rdtype, device=x0.device) if need_x else None
+    mu = torch.empty(rows, dtype=torch.float32, device=x0.device) if want_stats else None
+    rs = torch.empty(rows, dtype=torch.float32, device=x0.device) if want_stats else None
     with torch.cuda.device(x0.device):
         st = _lib.load().bp_ln_residual_fwd(
             x0m.data_ptr(), _lib.ptr(x1m), gamma.data_ptr(), beta.data_ptr(), z.data_ptr(), _lib.ptr(x_out),
-            None, None, rows, cols, float(epsilon), _lib.dtype_code(x0.dtype), _lib.dtype_code(rdtype),
+            _lib.ptr(mu), _lib.ptr(rs), rows, cols, float(epsilon), _lib.dtype_code(x0.dtype), _lib.dtype_code(rdtype),
             _lib.dtype_code(gamma.dtype), _lib.stream_ptr(x0.device))
     _lib.check(st, "bp_ln_residual_fwd")
     z = z.reshape(x0.shape)
-    if not want_residual:
-        return z, None
-    return z, (x_out.reshape(x0.shape) if need_x else x0)
+    res = None if not want_residual else (x_out.reshape(x0.shape) if need_x else x0)
+    return (z, res, mu, rs) if want_stats else (z, res)
 
 
 def layer_norm_from_residual(x, weight, bias, epsilon):
@@ -69,12 +70,12 @@ def layer_norm_from_residual(x, weight, bias, epsilon):
 
 class _DropoutAddLayerNormFn(torch.autograd.Function):
     """The autograd node of DropoutAddLayerNormFn (layer_norm.py:104-160) for dropout 0.  The forward keeps the
-    pre-norm sum x (the residual stream it writes anyway) and gamma; mu / rsigma are recomputed in the backward."""
+    pre-norm sum x (the residual stream it writes anyway), gamma and the row statistics mu / rsigma."""
 
     @staticmethod
     def forward(ctx, x0, x1, gamma, beta, epsilon, residual_in_fp32, prenorm):
-        z, x = _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, True)
-        ctx.save_for_backward(x, gamma)
+        z, x, mu, rs = _ln_residual_forward(x0, x1, gamma, beta, epsilon, residual_in_fp32, True, want_stats=True)
+        ctx.save_for_backward(x, gamma, mu, rs)
         ctx.has_x1, ctx.prenorm, ctx.epsilon, ctx.x0_dtype = x1 is not None, prenorm, float(epsilon), x0.dtype
         ctx.set_materialize_grads(False)
         if not prenorm:
@@ -84,7 +85,7 @@ class _DropoutAddLayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz, dx=None):
-        x, gamma = ctx.saved_tensors
+        x, gamma, mu, rs = ctx.saved_tensors
         cols = x.shape[-1]
         rows = x.numel() // cols
         if dz is None:
@@ -102,7 +103,8 @@ class _DropoutAddLayerNormFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             st = lib.bp_ln_residual_bwd(
-                dz.data_ptr(), _lib.ptr(dx), x.data_ptr(), gamma.data_ptr(), dx0.data_ptr(), _lib.ptr(dx1),
+                dz.data_ptr(), _lib.ptr(dx), x.data_ptr(), gamma.data_ptr(), mu.data_ptr(), rs.data_ptr(),
+                dx0.data_ptr(), _lib.ptr(dx1),
                 dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws_bytes, rows, cols, ctx.epsilon,
                 _lib.dtype_code(ctx.x0_dtype), _lib.dtype_code(x.dtype), _lib.dtype_code(gamma.dtype),
                 _lib.stream_ptr(x.device))

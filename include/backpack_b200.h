@@ -246,11 +246,13 @@ int bp_ln_fwd(const void* x, const void* gamma, const void* beta, void* z, float
  *   x_out (x0 itself when the forward wrote none); dx_residual: gradient arriving through the residual output of a
  *   pre-norm block (residual_dtype) or NULL; gamma in weight_dtype.
  *   dx0 (x0_dtype), dx1 (residual_dtype, or NULL when the forward had no x1), dgamma / dbeta (weight_dtype).
- *   mu / rsigma are recomputed from x.  workspace: bp_ln_bwd_workspace_bytes(cols) bytes, 16-byte aligned.
+ *   mu / rsigma (rows) f32: the statistics bp_ln_residual_fwd wrote, or both NULL (they are recomputed from x).
+ *   workspace: bp_ln_bwd_workspace_bytes(cols) bytes, 16-byte aligned.
  * Two launches (row pass + column-sum finalisation); deterministic.
  */
 int64_t bp_ln_bwd_workspace_bytes(int32_t cols);
-int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma, void* dx0, void* dx1,
+int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma,
+                       const float* mu, const float* rsigma, void* dx0, void* dx1,
                        void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes, int64_t rows, int32_t cols,
                        float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype, void* stream);
 

@@ -55,11 +55,13 @@ def test_backward_entry_points_validate_before_touching_the_gpu(lib):
     assert lib.bp_fmha_fwd_dropout(*fwd, -0.1, 7, a, 1 << 20, None) == -1 and "p_dropout" in _lib.last_error()
     assert lib.bp_fmha_fwd_dropout(*fwd, 0.1, 7, None, 0, None) == -1 and "workspace" in _lib.last_error()
     # LayerNorm backward
-    assert lib.bp_ln_residual_bwd(a, None, a, a, a, None, a, a, a, 16, 4, 64, 1e-5, 1, 2, 1, None) == -1
+    assert lib.bp_ln_residual_bwd(a, None, a, a, None, None, a, None, a, a, a, 16, 4, 64, 1e-5, 1, 2, 1, None) == -1
     assert "workspace" in _lib.last_error()
-    assert lib.bp_ln_residual_bwd(a, None, a, a, a, None, a, a, a, 1 << 30, 4, 60, 1e-5, 1, 2, 1, None) == -1
+    assert lib.bp_ln_residual_bwd(a, None, a, a, None, None, a, None, a, a, a, 1 << 30, 4, 60, 1e-5, 1, 2, 1, None) == -1
     assert "multiple of 8" in _lib.last_error()
-    assert lib.bp_ln_residual_bwd(None, None, a, a, a, None, a, a, a, 1 << 30, 4, 64, 1e-5, 1, 2, 1, None) == -1
+    assert lib.bp_ln_residual_bwd(None, None, a, a, None, None, a, None, a, a, a, 1 << 30, 4, 64, 1e-5, 1, 2, 1, None) == -1
+    assert lib.bp_ln_residual_bwd(a, None, a, a, a, None, a, None, a, a, a, 1 << 30, 4, 64, 1e-5, 1, 2, 1, None) == -1
+    assert "together" in _lib.last_error()
     # dgelu / bias gradient
     assert lib.bp_bias_act_bwd(a, None, None, a, a, 1 << 30, 8, 64, 1, 1, None) == -1 and "GELU" in _lib.last_error()
     assert lib.bp_bias_act_bwd(a, None, None, None, a, 1 << 30, 8, 64, 0, 1, None) == -1
