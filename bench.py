@@ -426,6 +426,25 @@ def run_ours(args):
                 t.__exit__(None, None, None)
             training = {"dt": tr_dt, "steps": args.training_steps, "batch": tb,
                         "kernels": {n: (len(t.events) / args.training_steps, t.mean_ms()) for n, t in tt.items() if t.events}}
+            # the same step captured once and replayed as ONE CUDA graph (single GPU: no collective inside the capture)
+            if world == 1:
+                try:
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        train_step()
+                    torch.cuda.current_stream().wait_stream(side)
+                    tmodel.zero_grad(set_to_none=True)
+                    tg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(tg):
+                        graph_loss = train_step()
+                    for _ in range(2):
+                        tg.replay()
+                    training["graph_dt"] = timed_steps(tg.replay, args.training_steps, parallel, dev)
+                    training["graph_loss"] = float(graph_loss.detach())
+                    del tg
+                except Exception as exc:
+                    training["graph_error"] = f"{type(exc).__name__}: {exc}"[:200]
             del tmodel
         except Exception as exc:   # a variant must never take the headline line down with it
             training, training_error = None, f"{type(exc).__name__}: {exc}"[:300]
@@ -593,6 +612,10 @@ def run_ours(args):
         line["variants"]["training_step"] = {
             "value": tb * S * world / (tms * 1e-3), "unit": "tokens/s", "ms_per_step": tms, "steps": training["steps"],
             "batch_per_gpu": tb,
+            "cuda_graph": ({"ms_per_step": training["graph_dt"] / training["steps"] * 1e3,
+                            "value": tb * S * world / (training["graph_dt"] / training["steps"]), "unit": "tokens/s",
+                            "note": "forward + backward captured once, replayed as one CUDA graph"}
+                           if "graph_dt" in training else {"unavailable": training.get("graph_error", "multi-GPU run")}),
             "own_kernel_share": sum(c * ms for c, ms in tk.values()) / tms,
             "kernels": {n: {"calls_per_step": c, "ms_per_call": ms, "ms_per_step": c * ms} for n, (c, ms) in tk.items()},
             "fmha_bwd": {"kernel": "bp_fmha_bwd: bwd_stats_kernel + fmha_bwd_kernel<64, keys own> + fmha_bwd_kernel<64, "
