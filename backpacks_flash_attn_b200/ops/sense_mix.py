@@ -88,7 +88,10 @@ class _SenseMixFn(torch.autograd.Function):
         b, s, _, nv, _ = qk.shape
         step = max(1, _SenseMixFn.chunk_bytes // (4 * nv * s * s * qk.element_size()))
         dqk = torch.empty_like(qk) if ctx.needs_input_grad[0] else None
-        dcontent = torch.empty(content.shape, dtype=content.dtype, device=content.device) if ctx.needs_input_grad[1] else None
+        # (same strides as `content`: the reference hands a transposed view of (b, s, nv, d), and a gradient in that layout
+        # flows back through the transpose / reshape of the content model as a view instead of a 1.6 GB copy)
+        dcontent = (torch.empty_strided(content.shape, content.stride(), dtype=content.dtype, device=content.device)
+                    if ctx.needs_input_grad[1] else None)
         for i in range(0, b, step):
             with torch.enable_grad():
                 q_ = qk[i:i + step].detach().requires_grad_(dqk is not None)
