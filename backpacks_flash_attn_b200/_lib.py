@@ -51,6 +51,7 @@ SIGNATURES = {
     "bp_bias_act_bwd": [c_void_p] * 5 + [c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_xentropy_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int64, c_float, c_int64, c_int32, c_int32, c_void_p],
     "bp_xentropy_bwd": [c_void_p] * 5 + [c_int64, c_int32, c_int64, c_int64, c_float, c_int64, c_int32, c_int32, c_void_p],
+    "bp_sense_softmax_bwd": [c_void_p, c_void_p, c_int64, c_int32, c_float, c_int32, c_void_p],
     "bp_rotary_qk_inplace": [c_void_p] * 5 + [c_int32] * 6 + [c_void_p],
 }
 _RESTYPES = {"bp_last_error": c_char_p, "bp_fmha_bwd_workspace_bytes": c_int64,

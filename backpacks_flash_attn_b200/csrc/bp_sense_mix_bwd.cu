@@ -1,0 +1,173 @@
+// Backward of the Backpack sense-mix, the element-wise half: causal softmax + softmax backward in ONE pass, in place.
+//
+// The reference trains through the eager composition  alpha = softmax(q k^T scale + mask);  o = sum_l alpha_l C_l
+// (training/src/models/backpack.py:116-122, 313), whose autograd graph makes seven full passes over (b, nv, s, s)
+// tensors (mask add, softmax, softmax backward and their saved copies).  The backward of ops/sense_mix.py keeps the five
+// GEMM-shaped products on the library's batched GEMM
+//     S_l = q_l k_l^T      dA_l = dO C_l^T      dC_l = P_l^T dO      dq_l = dS_l k_l      dk_l = dS_l^T q_l
+// and this kernel does everything between them, one warp per score row (row = (sense, batch, query t)), rows of up to
+// 2048 keys held in registers:
+//     P    = softmax_j<=t (scale * S)                 written over S  (16-bit, zeros right of the diagonal)
+//     dS'  = scale * P o (dA - sum_j P o dA)          written over dA (16-bit, zeros right of the diagonal)
+// Only the causal part of a row is read (whatever S and dA hold right of the diagonal is ignored); the whole row is
+// written, because the GEMMs that follow read full rows.  HBM-bound: (1/2 + 1/2 + 1 + 1) x 2 bytes per score.
+#include "bp_common.cuh"
+#include "bp_host.h"
+
+namespace bp {
+namespace smb {
+
+constexpr int kWarps = 8;
+
+template <bool kBF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (kBF16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// NV = 8-wide vectors per lane: rows of up to 256 * NV keys.
+template <bool kBF16, int NV>
+__global__ void __launch_bounds__(kWarps * 32)
+sense_softmax_bwd_kernel(uint16_t* __restrict__ S, uint16_t* __restrict__ dA, int64_t rows, int seqlen, float scale,
+                         float scale_log2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
+  for (int64_t r = warp0; r < rows; r += stride) {
+    const int t = static_cast<int>(r % seqlen);          // causal: keys 0..t
+    uint16_t* srow = S + r * seqlen;
+    uint16_t* drow = dA + r * seqlen;
+    float x[NV][8];
+    uint4 da[NV];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = (lane + 32 * i) * 8;
+      if (c0 < seqlen && c0 <= t) {
+        const uint4 u = *reinterpret_cast<const uint4*>(srow + c0);
+        const uint4 g4 = *reinterpret_cast<const uint4*>(drow + c0);
+        uint32_t w[4] = {g4.x, g4.y, g4.z, g4.w};
+        unpack8<kBF16>(u, x[i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool vis = c0 + k <= t;
+          x[i][k] = vis ? x[i][k] * scale_log2 : -INFINITY;
+          if (!vis) w[k >> 1] &= (k & 1) ? 0x0000FFFFu : 0xFFFF0000u;   // right of the diagonal: ignored
+          m = fmaxf(m, x[i][k]);
+        }
+        da[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        da[i] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[i][k] = -INFINITY;
+      }
+    }
+    m = warp_max(m);                                      // finite: key 0 is always visible
+    float l = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        x[i][k] = exp2f(x[i][k] - m);
+        l += x[i][k];
+      }
+    const float inv = 1.f / warp_sum(l);
+    // P rounded to the storage type first: delta and dS use the values the GEMMs will see (as the eager chain does)
+    uint4 pb[NV];
+    float delta = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      pb[i].x = pack2<kBF16>(x[i][0] * inv, x[i][1] * inv);
+      pb[i].y = pack2<kBF16>(x[i][2] * inv, x[i][3] * inv);
+      pb[i].z = pack2<kBF16>(x[i][4] * inv, x[i][5] * inv);
+      pb[i].w = pack2<kBF16>(x[i][6] * inv, x[i][7] * inv);
+      float g[8];
+      unpack8<kBF16>(pb[i], x[i]);
+      unpack8<kBF16>(da[i], g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) delta = fmaf(x[i][k], g[k], delta);
+    }
+    delta = warp_sum(delta);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = (lane + 32 * i) * 8;
+      if (c0 < seqlen) {
+        float g[8];
+        unpack8<kBF16>(da[i], g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = scale * x[i][k] * (g[k] - delta);
+        uint4 o;
+        o.x = pack2<kBF16>(g[0], g[1]);
+        o.y = pack2<kBF16>(g[2], g[3]);
+        o.z = pack2<kBF16>(g[4], g[5]);
+        o.w = pack2<kBF16>(g[6], g[7]);
+        *reinterpret_cast<uint4*>(srow + c0) = pb[i];
+        *reinterpret_cast<uint4*>(drow + c0) = o;
+      }
+    }
+  }
+}
+
+template <bool kBF16, int NV>
+int launch(void* S, void* dA, int64_t rows, int seqlen, float scale, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (rows + kWarps - 1) / kWarps;
+  const int64_t cap = static_cast<int64_t>(sms) * 32;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  sense_softmax_bwd_kernel<kBF16, NV><<<grid, kWarps * 32, 0, st>>>(
+      static_cast<uint16_t*>(S), static_cast<uint16_t*>(dA), rows, seqlen, scale, scale * 1.4426950408889634f);
+  return check_launch("bp_sense_softmax_bwd launch");
+}
+
+template <bool kBF16>
+int dispatch(void* S, void* dA, int64_t rows, int seqlen, float scale, cudaStream_t st) {
+  if (seqlen <= 256) return launch<kBF16, 1>(S, dA, rows, seqlen, scale, st);
+  if (seqlen <= 512) return launch<kBF16, 2>(S, dA, rows, seqlen, scale, st);
+  if (seqlen <= 1024) return launch<kBF16, 4>(S, dA, rows, seqlen, scale, st);
+  return launch<kBF16, 8>(S, dA, rows, seqlen, scale, st);
+}
+
+}  // namespace smb
+}  // namespace bp
+
+extern "C" int bp_sense_softmax_bwd(void* scores_probs, void* dalpha_dscores, int64_t rows, int32_t seqlen,
+                                    float softmax_scale, int32_t dtype, void* stream) {
+  using namespace bp;
+  if (!scores_probs || !dalpha_dscores) return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: null pointer argument");
+  if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: only fp16 and bf16 are supported (dtype=%d)", dtype);
+  if (rows <= 0 || seqlen <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: empty input");
+  if (seqlen % 8 != 0 || seqlen > 2048)
+    return fail(BP_ERR_UNSUPPORTED, "bp_sense_softmax_bwd: seqlen must be a multiple of 8, at most 2048 (got %d)", seqlen);
+  if (rows % seqlen != 0)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: rows (%lld) must be a multiple of seqlen (%d): square causal score matrices",
+                (long long)rows, seqlen);
+  if (reinterpret_cast<uintptr_t>(scores_probs) % 16 || reinterpret_cast<uintptr_t>(dalpha_dscores) % 16)
+    return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == BP_DTYPE_BF16 ? smb::dispatch<true>(scores_probs, dalpha_dscores, rows, seqlen, softmax_scale, st)
+                                : smb::dispatch<false>(scores_probs, dalpha_dscores, rows, seqlen, softmax_scale, st);
+}

@@ -9,9 +9,11 @@ transposed view the reference's content model returns (backpack.py:276) and the 
 the intervention wrappers build (training/src/models/intervened_models.py:78-101).
 
 Training: `sense_mix` is differentiable.  The forward is the fused kernel (alpha is neither materialised nor kept for
-the backward -- 2.15 GB at Backpack-Small, batch 64); the backward recomputes alpha for a few batch elements at a time
-with the reference's own eager composition under autograd (the reference trains through exactly that composition,
-backpack.py:116-122, 313), so its tensor work runs on cuBLAS: a hand-written sense-mix backward kernel is not built.
+the backward -- 2.15 GB at Backpack-Small, batch 64).  The backward recomputes the scores and is hand-derived: five
+batched library GEMMs per sense with ONE own element-wise pass between them (`bp_sense_softmax_bwd`: causal softmax +
+softmax backward + scale, in place); sequence lengths that pass does not take (not a multiple of 8, above 2048) fall
+back to autograd through the reference's eager composition (backpack.py:116-122, 313).  A fully fused tcgen05
+sense-mix backward (no (b, nv, s, s) tensor at all) is not built.
 
 `sense_mix_table` is the inference form: the sense vectors are gathered inside the kernel from a precomputed
 (vocab, nv, d) table by token id (C_l(x) is context-free, backpack.py:258), so no (b, s, nv, d) tensor exists.
@@ -71,9 +73,74 @@ def _sense_mix_eager(qk, content, scale):
     return torch.sum(alpha @ content, dim=1)
 
 
+def _sense_mix_backward_eager(qk, content, dout, scale, want_dqk, want_dcontent, chunk_bytes=1 << 30):
+    """Gradients by autograd through the eager composition, a few batch elements at a time (any seqlen)."""
+    b, s, _, nv, _ = qk.shape
+    step = max(1, chunk_bytes // (4 * nv * s * s * qk.element_size()))
+    dqk = torch.empty_like(qk) if want_dqk else None
+    dcontent = (torch.empty_strided(content.shape, content.stride(), dtype=content.dtype, device=content.device)
+                if want_dcontent else None)
+    for i in range(0, b, step):
+        with torch.enable_grad():
+            q_ = qk[i:i + step].detach().requires_grad_(want_dqk)
+            c_ = content[i:i + step].detach().requires_grad_(want_dcontent)
+            o = _sense_mix_eager(q_, c_, scale)
+            wanted = [t for t, w in ((q_, want_dqk), (c_, want_dcontent)) if w]
+            grads = list(torch.autograd.grad(o, wanted, dout[i:i + step]))
+        if want_dqk:
+            dqk[i:i + step] = grads.pop(0)
+        if want_dcontent:
+            dcontent[i:i + step] = grads.pop(0)
+    return dqk, dcontent
+
+
+def _sense_mix_backward(qk, content, dout, scale, want_dqk, want_dcontent, chunk_bytes=4 << 30):
+    """Hand-derived backward: per sense l, with P_l = softmax(scale q_l k_l^T + causal mask),
+
+        dA_l = dO C_l^T      dC_l = P_l^T dO      dS_l = scale P_l o (dA_l - rowsum(P_l o dA_l))
+        dq_l = dS_l k_l      dk_l = dS_l^T q_l
+
+    The five products are batched library GEMMs over the batch dimension, reading q / k / content and writing dqk /
+    dcontent through their strides (no permuted copies); everything between them -- mask, softmax, softmax backward,
+    scale -- is ONE pass of `bp_sense_softmax_bwd` over the two (nv, batch, s, s) score tensors, in place.  The
+    autograd chain of the eager composition (what the reference trains through, backpack.py:116-122, 313) makes seven
+    passes over such tensors and three dense (b, nv, s, s, d) products; this makes two and two."""
+    b, s, _, nv, dk = qk.shape
+    dout = dout.contiguous()
+    dqk = torch.empty_like(qk) if want_dqk else None
+    # same strides as `content`: the reference hands a transposed view of (b, s, nv, d), and a gradient in that layout
+    # flows back through the transpose / reshape of the content model as a view instead of a 1.6 GB copy
+    dcontent = (torch.empty_strided(content.shape, content.stride(), dtype=content.dtype, device=content.device)
+                if want_dcontent else None)
+    lib = _lib.load()
+    dt = _lib.dtype_code(qk.dtype)
+    step = max(1, min(b, chunk_bytes // (2 * nv * s * s * qk.element_size())))
+    scores = torch.empty((nv, step, s, s), dtype=qk.dtype, device=qk.device)
+    dalpha = torch.empty_like(scores)
+    with torch.cuda.device(qk.device):
+        stream = _lib.stream_ptr(qk.device)
+        for i in range(0, b, step):
+            nb = min(step, b - i)
+            q, k = qk[i:i + nb, :, 0], qk[i:i + nb, :, 1]            # (nb, s, nv, dk) views
+            c, do = content[i:i + nb], dout[i:i + nb]
+            S = scores.view(-1)[:nv * nb * s * s].view(nv, nb, s, s)      # contiguous also for a short last chunk
+            dA = dalpha.view(-1)[:nv * nb * s * s].view(nv, nb, s, s)
+            for l in range(nv):
+                torch.bmm(q[:, :, l], k[:, :, l].transpose(1, 2), out=S[l])
+                torch.bmm(do, c[:, l].transpose(1, 2), out=dA[l])
+            _lib.check(lib.bp_sense_softmax_bwd(S.data_ptr(), dA.data_ptr(), nv * nb * s, s, scale, dt, stream),
+                       "bp_sense_softmax_bwd")
+            for l in range(nv):
+                if want_dcontent:
+                    torch.bmm(S[l].transpose(1, 2), do, out=dcontent[i:i + nb, l])
+                if want_dqk:
+                    torch.bmm(dA[l], k[:, :, l], out=dqk[i:i + nb, :, 0, l])
+                    torch.bmm(dA[l].transpose(1, 2), q[:, :, l], out=dqk[i:i + nb, :, 1, l])
+    return dqk, dcontent
+
+
 class _SenseMixFn(torch.autograd.Function):
-    """Fused forward; backward by recomputation of the eager composition, a few batch elements at a time."""
-    chunk_bytes = 1 << 30   # bound on the recomputed alpha (and its autograd copies) per chunk
+    """Fused forward (alpha is neither materialised nor saved); backward by recomputation from q, k and content."""
 
     @staticmethod
     def forward(ctx, qk, content, scale):
@@ -85,24 +152,9 @@ class _SenseMixFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         qk, content = ctx.saved_tensors
-        b, s, _, nv, _ = qk.shape
-        step = max(1, _SenseMixFn.chunk_bytes // (4 * nv * s * s * qk.element_size()))
-        dqk = torch.empty_like(qk) if ctx.needs_input_grad[0] else None
-        # (same strides as `content`: the reference hands a transposed view of (b, s, nv, d), and a gradient in that layout
-        # flows back through the transpose / reshape of the content model as a view instead of a 1.6 GB copy)
-        dcontent = (torch.empty_strided(content.shape, content.stride(), dtype=content.dtype, device=content.device)
-                    if ctx.needs_input_grad[1] else None)
-        for i in range(0, b, step):
-            with torch.enable_grad():
-                q_ = qk[i:i + step].detach().requires_grad_(dqk is not None)
-                c_ = content[i:i + step].detach().requires_grad_(dcontent is not None)
-                o = _sense_mix_eager(q_, c_, ctx.scale)
-                wanted = [t for t, g in ((q_, dqk), (c_, dcontent)) if g is not None]
-                grads = list(torch.autograd.grad(o, wanted, dout[i:i + step]))
-            if dqk is not None:
-                dqk[i:i + step] = grads.pop(0)
-            if dcontent is not None:
-                dcontent[i:i + step] = grads.pop(0)
+        s = qk.shape[1]
+        fn = _sense_mix_backward if (s % 8 == 0 and s <= 2048 and content.stride(3) == 1) else _sense_mix_backward_eager
+        dqk, dcontent = fn(qk, content, dout, ctx.scale, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dqk, dcontent, None
 
 

@@ -244,6 +244,33 @@ def bench_sense(iters, b=64, s=1024, nv=16, d=768):
     return rec
 
 
+def bench_sense_bwd(iters, b=64, s=1024, nv=16, d=768):
+    """Sense-mix backward at config-3 size: the hand-derived backward (library GEMMs around bp_sense_softmax_bwd) next
+    to autograd through the reference's eager composition (what the reference trains through), and the element-wise
+    pass alone."""
+    from backpacks_flash_attn_b200.ops.sense_mix import _sense_mix_backward, _sense_mix_backward_eager
+    from backpacks_flash_attn_b200 import _lib
+    qk = torch.randn(b, s, 2, nv, d // nv, device="cuda").bfloat16()
+    content = (torch.randn(b, s, nv, d, device="cuda") * 0.5).bfloat16().transpose(1, 2)
+    dout = torch.randn(b, s, d, device="cuda").bfloat16()
+    scale = (d // nv) ** -0.5
+    causal_flops = b * nv * s * s * (2 * d + 3 * (d // nv))      # five products, causal half of each (2 flops / MAC)
+    it = max(3, iters // 4)
+    t, tm = time_fn(lambda i: _sense_mix_backward(qk, content, dout, scale, True, True), 1, it, warmup=2, inner=1)
+    rec = report(f"sense_mix backward (GEMMs + bp_sense_softmax_bwd) b{b} s{s} k{nv} d{d} bf16", t, tm, causal_flops, 0)
+    te, tme = time_fn(lambda i: _sense_mix_backward_eager(qk, content, dout, scale, True, True), 1, it, warmup=2, inner=1)
+    report("  (comparator) autograd through the eager composition, 1 GB chunks", te, tme, causal_flops, 0,
+           {"speedup_of_ours": te / t})
+    S = torch.randn(nv, b, s, s, device="cuda").bfloat16()
+    dA = torch.randn(nv, b, s, s, device="cuda").bfloat16()
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    f = lambda i: _lib.check(lib.bp_sense_softmax_bwd(S.data_ptr(), dA.data_ptr(), nv * b * s, s, scale, 1, st), "ssb")
+    t1, t1m = time_fn(f, 1, iters, inner=2)
+    report("  bp_sense_softmax_bwd alone (reads the causal half, writes full rows)", t1, t1m, 0, nv * b * s * s * 2 * 3)
+    return rec
+
+
 def bench_ln(iters, rows=65536, cols=768):
     from backpacks_flash_attn_b200.ops.layer_norm import dropout_add_layer_norm
     nvar = 2
@@ -316,7 +343,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     for w in a.which.split(","):
         fn = {"fmha": bench_fmha, "sense": bench_sense, "ln": bench_ln, "gemm": bench_gemm, "gemms": bench_gemms,
-              "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops, "xent": bench_xent}[w]
+              "fmha_bwd": bench_fmha_bwd, "bwd_ops": bench_bwd_ops, "xent": bench_xent, "sense_bwd": bench_sense_bwd}[w]
         if w in ("fmha", "fmha_bwd") and (a.shape or a.no_comparators):
             b, s_, h, d = (int(x) for x in a.shape.split(",")) if a.shape else (32, 1024, 12, 64)
             fn(a.iters, b=b, s=s_, h=h, d=d, comparators=not a.no_comparators)

@@ -1,6 +1,10 @@
 """Top CUDA kernels of one Backpack-Small training step (torch profiler): where the time outside this library goes."""
+import os
 import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torch.profiler import ProfilerActivity, profile
 from backpacks_flash_attn_b200.losses.cross_entropy import CrossEntropyLoss
 from backpacks_flash_attn_b200.models.backpack import BackpackLMHeadModel, flash_config

@@ -14,6 +14,7 @@
  *   (no reference kernel; eager PyTorch at    training/src/models/backpack.py:111-122,313) -> bp_sense_lse_fwd,
  *                                                                                            bp_sense_mix_fwd,
  *                                                                                            bp_sense_mix_table_fwd
+ *   (autograd through the same eager lines in training)                                   -> bp_sense_softmax_bwd
  *
  * Conventions
  *   - plain C types only: device pointers, sizes, strides (in ELEMENTS), a cudaStream_t passed as void*.
@@ -281,6 +282,16 @@ int bp_xentropy_fwd(const void* logits, const int64_t* labels, float* losses, fl
 int bp_xentropy_bwd(const float* grad_losses, const void* logits, const float* lse, const int64_t* labels,
                     void* grad_logits, int64_t rows, int32_t vocab, int64_t row_stride, int64_t grad_row_stride,
                     float smoothing, int64_t ignore_index, int32_t total_classes, int32_t dtype, void* stream);
+
+/* Element-wise half of the sense-mix backward (the backward of `softmax(q k^T scale + causal mask)` inside
+ * ContextSelfAttn.forward, training/src/models/backpack.py:116-122, which the reference leaves to autograd), in place:
+ *   scores_probs   (rows, seqlen) 16-bit: raw scores q.k in, probabilities P = softmax_{j<=t}(scale * scores) out;
+ *   dalpha_dscores (rows, seqlen) 16-bit: dL/dP in, scale * P o (dL/dP - rowsum(P o dL/dP)) out;
+ * row r belongs to query t = r % seqlen (square causal matrices stacked along rows); entries right of the diagonal are
+ * ignored on input and written as zeros.  seqlen % 8 == 0, seqlen <= 2048 (BP_ERR_UNSUPPORTED otherwise).
+ */
+int bp_sense_softmax_bwd(void* scores_probs, void* dalpha_dscores, int64_t rows, int32_t seqlen, float softmax_scale,
+                         int32_t dtype, void* stream);
 
 /* In-place rotary embedding on q and k of a packed qkv tensor (replaces apply_rotary as driven by
  * ApplyRotaryEmbQKV_.forward, flash_attn/layers/rotary.py:81-105; csrc/rotary/rotary_cuda.cu:5-41).
