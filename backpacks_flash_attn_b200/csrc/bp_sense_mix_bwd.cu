@@ -18,6 +18,9 @@ namespace bp {
 namespace smb {
 
 constexpr int kWarps = 8;
+#ifndef BP_SSB_MIN_CTAS
+#define BP_SSB_MIN_CTAS 3   // resident CTAs per SM asked of ptxas for rows of up to 1024 keys (80 registers, no spills)
+#endif
 
 template <bool kBF16>
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -48,7 +51,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // NV = 8-wide vectors per lane: rows of up to 256 * NV keys.
 template <bool kBF16, int NV>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, NV <= 4 ? BP_SSB_MIN_CTAS : 1)
 sense_softmax_bwd_kernel(uint16_t* __restrict__ S, uint16_t* __restrict__ dA, int64_t rows, int seqlen, float scale,
                          float scale_log2) {
   const int lane = threadIdx.x & 31;
@@ -93,17 +96,18 @@ sense_softmax_bwd_kernel(uint16_t* __restrict__ S, uint16_t* __restrict__ dA, in
         l += x[i][k];
       }
     const float inv = 1.f / warp_sum(l);
-    // P rounded to the storage type first: delta and dS use the values the GEMMs will see (as the eager chain does)
-    uint4 pb[NV];
+    // P rounded to the storage type first: delta and dS use the values the GEMMs will see (as the eager chain does).
+    // x keeps the ROUNDED probabilities (re-packing them at the store is exact), so no packed copy stays live.
     float delta = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      pb[i].x = pack2<kBF16>(x[i][0] * inv, x[i][1] * inv);
-      pb[i].y = pack2<kBF16>(x[i][2] * inv, x[i][3] * inv);
-      pb[i].z = pack2<kBF16>(x[i][4] * inv, x[i][5] * inv);
-      pb[i].w = pack2<kBF16>(x[i][6] * inv, x[i][7] * inv);
+      uint4 pb;
+      pb.x = pack2<kBF16>(x[i][0] * inv, x[i][1] * inv);
+      pb.y = pack2<kBF16>(x[i][2] * inv, x[i][3] * inv);
+      pb.z = pack2<kBF16>(x[i][4] * inv, x[i][5] * inv);
+      pb.w = pack2<kBF16>(x[i][6] * inv, x[i][7] * inv);
       float g[8];
-      unpack8<kBF16>(pb[i], x[i]);
+      unpack8<kBF16>(pb, x[i]);
       unpack8<kBF16>(da[i], g);
 #pragma unroll
       for (int k = 0; k < 8; ++k) delta = fmaf(x[i][k], g[k], delta);
@@ -117,12 +121,16 @@ sense_softmax_bwd_kernel(uint16_t* __restrict__ S, uint16_t* __restrict__ dA, in
         unpack8<kBF16>(da[i], g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = scale * x[i][k] * (g[k] - delta);
-        uint4 o;
+        uint4 pb, o;
+        pb.x = pack2<kBF16>(x[i][0], x[i][1]);
+        pb.y = pack2<kBF16>(x[i][2], x[i][3]);
+        pb.z = pack2<kBF16>(x[i][4], x[i][5]);
+        pb.w = pack2<kBF16>(x[i][6], x[i][7]);
         o.x = pack2<kBF16>(g[0], g[1]);
         o.y = pack2<kBF16>(g[2], g[3]);
         o.z = pack2<kBF16>(g[4], g[5]);
         o.w = pack2<kBF16>(g[6], g[7]);
-        *reinterpret_cast<uint4*>(srow + c0) = pb[i];
+        *reinterpret_cast<uint4*>(srow + c0) = pb;
         *reinterpret_cast<uint4*>(drow + c0) = o;
       }
     }
