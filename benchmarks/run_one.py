@@ -1,6 +1,6 @@
 """Run ONE kernel of the library a few times at its BASELINE shape (for `ncu -k regex:...` captures and quick A/B timing).
 
-    python benchmarks/run_one.py fmha|fmha128|sense|sense_table|lse|gemm|ln|dec_attn|dec_sense [reps]
+    python benchmarks/run_one.py fmha|fmha128|sense|sense_table|lse|gemm|ln|dec_attn|dec_sense|sense_softmax_bwd [reps]
 """
 import os
 import sys
@@ -44,6 +44,14 @@ elif which == "dec_sense":
     ids = torch.randint(0, 50257, (b, s), device="cuda")
     q = torch.randn(b, nv, d // nv, device="cuda").bfloat16()
     run = lambda: sense_mix_decode(q, kc, ids, table, s)
+elif which == "sense_softmax_bwd":
+    from backpacks_flash_attn_b200 import _lib
+    b, s, nv = 64, 1024, 16
+    S = torch.randn(nv, b, s, s, device="cuda").bfloat16()
+    dA = torch.randn(nv, b, s, s, device="cuda").bfloat16()
+    lib = _lib.load()
+    run = lambda: _lib.check(lib.bp_sense_softmax_bwd(S.data_ptr(), dA.data_ptr(), nv * b * s, s, 48 ** -0.5, 1,
+                                                      torch.cuda.current_stream().cuda_stream), "bp_sense_softmax_bwd")
 elif which == "gemm":
     from backpacks_flash_attn_b200.ops.fused_dense import linear_bias_act
     x = torch.randn(65536, 768, device="cuda").bfloat16()
