@@ -45,6 +45,10 @@ SIGNATURES = {
     "bp_sense_mix_decode_fwd": [c_void_p] * 6 + [c_int32] * 6 + [c_int64] * 2 + [c_float, c_int32, c_void_p],
     "bp_linear_bias_residual_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_void_p],
     "bp_ln_fwd": [c_void_p] * 6 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
+    "bp_ln_residual_fwd_dropout": [c_void_p] * 8 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_float, c_uint64,
+                                   c_void_p],
+    "bp_ln_residual_bwd_dropout": [c_void_p] * 11 + [c_int64, c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_float,
+                                                     c_uint64, c_void_p],
     "bp_ln_bwd_workspace_bytes": [c_int32],
     "bp_ln_residual_bwd": [c_void_p] * 11 + [c_int64, c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_bias_act_bwd_workspace_bytes": [c_int32],

@@ -24,6 +24,9 @@ int check_launch(const char* what);
 // attention dropout helpers (bp_fmha_bwd.cu): column-word table launch, 8-bit threshold of a probability
 int launch_drop_col_table(uint32_t* table, uint64_t seed, int32_t bh, int32_t s_pad_k, cudaStream_t st);
 int drop_threshold(float p);
+// residual dropout inside the LayerNorm kernels (bp_layer_norm.cu): validates p, derives the hash base of `seed`, the
+// 8-bit threshold shifted to the top byte (0: no dropout) and the 1 / (1 - p_effective) scale
+int ln_drop_args(float p, uint64_t seed, int64_t rows, const char* fn, uint32_t* base, uint32_t* thr24, float* scale);
 
 inline int dtype_size(int dtype) { return dtype == BP_DTYPE_F32 ? 4 : 2; }
 

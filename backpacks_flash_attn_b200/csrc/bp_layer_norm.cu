@@ -1,13 +1,20 @@
-// Residual add + LayerNorm forward (eval mode) for sm_100a.
+// (Dropout +) residual add + LayerNorm forward for sm_100a.
 //
-// Replaces dropout_add_ln_fwd (csrc/layer_norm/ln_api.cpp:83-251, ln_fwd_kernels.cuh:20-191) for the
-// inference path: dropout_p = 0, no rowscale / colscale / subset.  Semantics kept from the reference:
-// x = x0 + x1 in fp32, x stored in the residual dtype, statistics from the fp32 sum (mean, then the
+// Replaces dropout_add_ln_fwd (csrc/layer_norm/ln_api.cpp:83-251, ln_fwd_kernels.cuh:20-191) without rowscale /
+// colscale / subset.  Semantics kept from the reference:
+// x = dropout(x0) + x1 in fp32, x stored in the residual dtype, statistics from the fp32 sum (mean, then the
 // centred second moment), z = gamma * (x - mu) * rsigma + beta rounded once to the input dtype.
+// Dropout (bp_ln_residual_fwd_dropout, training): the keep mask is counter-based like the attention kernels' --
+// keep(row, col) = drop_keep(R[row], C[col]) with one word per row (a register) and one per column (shared memory,
+// computed once per CTA) from bp_common.cuh's hash -- so nothing is stored for the backward, which regenerates it from
+// the seed.  (The reference stores a byte mask per element, ln_fwd_kernels.cuh:96-110; only the distribution is part of
+// the contract.)  ops/layer_norm.layer_norm_dropout_mask restates the mask in Python for the tests.
 //
 // HBM-bound: one warp owns one row and keeps it in registers (cols/32 values per lane), so every byte is
 // read once and written once; 16-byte vector loads/stores, warp-shuffle reductions only, no smem, no
 // block barrier.  Grid is a multiple of the SM count and warps stride over rows.
+#include <type_traits>
+
 #include "bp_common.cuh"
 #include "bp_host.h"
 
@@ -121,14 +128,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 // gamma / beta live in shared memory in their storage type (read back 16 bytes at a time, conflict-free), not
 // in registers: with the row itself (NV x 8 floats) that keeps the kernel under 85 registers, so 24 warps per
 // SM keep enough loads in flight to cover the HBM latency.
-template <typename X, typename R, typename W, int NV, typename Z = X>
+struct DropArgs {
+  uint32_t base = 0, thr24 = 0;   // thr24 == 0: no dropout
+  float scale = 1.f;
+};
+
+template <typename X, typename R, typename W, int NV, typename Z = X, bool kDrop = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const W* __restrict__ gamma,
                        const W* __restrict__ beta, Z* __restrict__ z, R* __restrict__ x_out,
-                       float* __restrict__ mu_out, float* __restrict__ rs_out, int64_t rows, int cols, float eps) {
-  extern __shared__ uint4 ln_smem[];   // [cols] gamma then [cols] beta, in W
+                       float* __restrict__ mu_out, float* __restrict__ rs_out, int64_t rows, int cols, float eps,
+                       DropArgs drop) {
+  extern __shared__ uint4 ln_smem[];   // [cols] gamma then [cols] beta, in W; with dropout [cols] column words
   W* s_gamma = reinterpret_cast<W*>(ln_smem);
   W* s_beta = s_gamma + cols;
+  uint32_t* s_cw = reinterpret_cast<uint32_t*>(s_beta + cols);
+  if constexpr (kDrop)
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s_cw[c] = drop_col_word(drop.base, static_cast<uint32_t>(c));
   const int lane = threadIdx.x & 31;
   const int nvec = cols >> 3;
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -159,11 +175,19 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
       }
     }
     float sum = 0.f;
+    uint32_t rw = 0;
+    if constexpr (kDrop) rw = drop_row_word(drop.base, static_cast<uint32_t>(row));
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = i * 32 + lane;
       if (v < nvec) {
         a[i].to(x[i]);
+        if constexpr (kDrop) {
+          const uint4 c0 = *reinterpret_cast<const uint4*>(s_cw + v * 8), c1 = *reinterpret_cast<const uint4*>(s_cw + v * 8 + 4);
+          const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[i][k] = drop_keep(rw, cw[k], drop.thr24) ? x[i][k] * drop.scale : 0.f;
+        }
         if (x1 != nullptr) {
           float rf[8];
           r[i].to(rf);
@@ -218,36 +242,46 @@ ln_residual_fwd_kernel(const X* __restrict__ x0, const R* __restrict__ x1, const
   }
 }
 
-template <typename X, typename R, typename W, int NV, typename Z = X>
-int launch_nv(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
-              float* rs, int64_t rows, int cols, float eps, cudaStream_t st) {
+template <typename X, typename R, typename W, int NV, typename Z, bool kDrop>
+int launch_kernel(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
+                  float* rs, int64_t rows, int cols, float eps, DropArgs drop, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ctas_needed = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
   const int64_t cap = static_cast<int64_t>(sms) * 3;  // 3 resident CTAs of 256 threads per SM (register-limited)
   const int grid = static_cast<int>(ctas_needed < cap ? ctas_needed : cap);
-  const size_t smem = 2 * static_cast<size_t>(cols) * sizeof(W);
+  const size_t smem = 2 * static_cast<size_t>(cols) * sizeof(W) + (kDrop ? static_cast<size_t>(cols) * 4 : 0);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ln_residual_fwd_kernel<X, R, W, NV, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(ln_residual_fwd_kernel<X, R, W, NV, Z, kDrop>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       cudaGetLastError();
       return fail(BP_ERR_CUDA, "bp_ln_residual_fwd: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     }
   }
-  ln_residual_fwd_kernel<X, R, W, NV, Z><<<grid, kWarpsPerCta * 32, smem, st>>>(
+  ln_residual_fwd_kernel<X, R, W, NV, Z, kDrop><<<grid, kWarpsPerCta * 32, smem, st>>>(
       static_cast<const X*>(x0), static_cast<const R*>(x1), static_cast<const W*>(gamma),
-      static_cast<const W*>(beta), static_cast<Z*>(z), static_cast<R*>(x_out), mu, rs, rows, cols, eps);
+      static_cast<const W*>(beta), static_cast<Z*>(z), static_cast<R*>(x_out), mu, rs, rows, cols, eps, drop);
   return check_launch("bp_ln_residual_fwd launch");
+}
+
+template <typename X, typename R, typename W, int NV, typename Z = X>
+int launch_nv(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
+              float* rs, int64_t rows, int cols, float eps, DropArgs drop, cudaStream_t st) {
+  if constexpr (std::is_same<Z, X>::value) {   // dropout only exists on the residual-add entry point
+    if (drop.thr24 != 0)
+      return launch_kernel<X, R, W, NV, Z, true>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, drop, st);
+  }
+  return launch_kernel<X, R, W, NV, Z, false>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, drop, st);
 }
 
 template <typename X, typename R, typename W, typename Z = X>
 int launch(const void* x0, const void* x1, const void* gamma, const void* beta, void* z, void* x_out, float* mu,
-           float* rs, int64_t rows, int cols, float eps, cudaStream_t st) {
+           float* rs, int64_t rows, int cols, float eps, cudaStream_t st, DropArgs drop = DropArgs()) {
   const int nv = (cols / 8 + 31) / 32;
 #define BP_LN_CASE(N) \
-  if (nv <= N) return launch_nv<X, R, W, N, Z>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, st)
+  if (nv <= N) return launch_nv<X, R, W, N, Z>(x0, x1, gamma, beta, z, x_out, mu, rs, rows, cols, eps, drop, st)
   BP_LN_CASE(1);
   BP_LN_CASE(2);
   BP_LN_CASE(3);
@@ -261,12 +295,23 @@ int launch(const void* x0, const void* x1, const void* gamma, const void* beta, 
 }
 
 }  // namespace ln
+
+int ln_drop_args(float p, uint64_t seed, int64_t rows, const char* fn, uint32_t* base, uint32_t* thr24, float* scale) {
+  if (!(p >= 0.f) || p >= 1.f) return fail(BP_ERR_INVALID_ARGUMENT, "%s: dropout_p must be in [0, 1) (got %f)", fn, (double)p);
+  if (rows > 0xFFFFFFFFll) return fail(BP_ERR_UNSUPPORTED, "%s: dropout supports at most 2^32 - 1 rows", fn);
+  const int thr = drop_threshold(p);
+  *base = drop_base(seed, 0x4C4Eu);   // "LN": keeps these masks apart from the attention kernels' (bh < 2^31 there)
+  *thr24 = static_cast<uint32_t>(thr) << 24;
+  *scale = 256.f / static_cast<float>(256 - thr);
+  return BP_OK;
+}
 }  // namespace bp
 
-extern "C" int bp_ln_residual_fwd(const void* x0, const void* x1, const void* gamma, const void* beta, void* z,
-                                  void* x_out, float* mu, float* rsigma, int64_t rows, int32_t cols,
-                                  float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype,
-                                  void* stream) {
+namespace {
+int ln_residual_fwd_impl(const void* x0, const void* x1, const void* gamma, const void* beta, void* z,
+                         void* x_out, float* mu, float* rsigma, int64_t rows, int32_t cols,
+                         float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype,
+                         bp::ln::DropArgs drop, void* stream) {
   using namespace bp;
   if (!x0 || !gamma || !beta || !z) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_fwd: null pointer argument");
   if (rows <= 0 || cols <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_fwd: empty input");
@@ -278,7 +323,7 @@ extern "C" int bp_ln_residual_fwd(const void* x0, const void* x1, const void* ga
   const int key = x0_dtype * 100 + residual_dtype * 10 + weight_dtype;
 #define BP_LN_DISPATCH(XD, RD, WD, X, R, W) \
   if (key == XD * 100 + RD * 10 + WD)       \
-  return ln::launch<X, R, W>(x0, x1, gamma, beta, z, x_out, mu, rsigma, rows, cols, epsilon, st)
+  return ln::launch<X, R, W>(x0, x1, gamma, beta, z, x_out, mu, rsigma, rows, cols, epsilon, st, drop)
   using bf = __nv_bfloat16;
   using hf = __half;
   BP_LN_DISPATCH(BP_DTYPE_BF16, BP_DTYPE_F32, BP_DTYPE_BF16, bf, float, bf);
@@ -291,6 +336,26 @@ extern "C" int bp_ln_residual_fwd(const void* x0, const void* x1, const void* ga
 #undef BP_LN_DISPATCH
   return fail(BP_ERR_UNSUPPORTED, "bp_ln_residual_fwd: dtype combination (x0=%d, residual=%d, weight=%d) not built",
               x0_dtype, residual_dtype, weight_dtype);
+}
+}  // namespace
+
+extern "C" int bp_ln_residual_fwd(const void* x0, const void* x1, const void* gamma, const void* beta, void* z,
+                                  void* x_out, float* mu, float* rsigma, int64_t rows, int32_t cols,
+                                  float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype,
+                                  void* stream) {
+  return ln_residual_fwd_impl(x0, x1, gamma, beta, z, x_out, mu, rsigma, rows, cols, epsilon, x0_dtype, residual_dtype,
+                              weight_dtype, bp::ln::DropArgs(), stream);
+}
+
+extern "C" int bp_ln_residual_fwd_dropout(const void* x0, const void* x1, const void* gamma, const void* beta, void* z,
+                                          void* x_out, float* mu, float* rsigma, int64_t rows, int32_t cols,
+                                          float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype,
+                                          float dropout_p, uint64_t seed, void* stream) {
+  bp::ln::DropArgs drop;
+  if (int rc = bp::ln_drop_args(dropout_p, seed, rows, "bp_ln_residual_fwd_dropout", &drop.base, &drop.thr24, &drop.scale))
+    return rc;
+  return ln_residual_fwd_impl(x0, x1, gamma, beta, z, x_out, mu, rsigma, rows, cols, epsilon, x0_dtype, residual_dtype,
+                              weight_dtype, drop, stream);
 }
 
 extern "C" int bp_ln_fwd(const void* x, const void* gamma, const void* beta, void* z, float* mu, float* rsigma,

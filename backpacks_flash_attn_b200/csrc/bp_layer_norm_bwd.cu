@@ -1,9 +1,10 @@
 // Residual add + LayerNorm backward for sm_100a.
 //
-// Replaces dropout_add_ln_bwd (csrc/layer_norm/ln_api.cpp:255-440, ln_bwd_kernels.cuh) for dropout_p = 0 without
-// rowscale / colscale / subset.  With x = x0 + x1 the saved pre-norm sum, y = (x - mu) * rsigma, z = gamma * y + beta:
+// Replaces dropout_add_ln_bwd (csrc/layer_norm/ln_api.cpp:255-440, ln_bwd_kernels.cuh) without rowscale / colscale /
+// subset.  With x = dropout(x0) + x1 the saved pre-norm sum, y = (x - mu) * rsigma, z = gamma * y + beta:
 //     dy = dz * gamma;   dx = rsigma * (dy - mean(dy) - y * mean(dy * y)) + dx_residual
-//     dx0 = dx (input dtype), dx1 = dx (residual dtype);   dgamma = sum_rows dz * y,  dbeta = sum_rows dz
+//     dx0 = dx (input dtype; bp_ln_residual_bwd_dropout: keep ? dx / (1 - p) : 0, the forward's mask regenerated from
+//     the seed, bp_layer_norm.cu), dx1 = dx (residual dtype);   dgamma = sum_rows dz * y,  dbeta = sum_rows dz
 // (`dx_residual` is the gradient that arrives through the residual output of a pre-norm block.)
 //
 // HBM-bound like the forward: one warp owns a row and keeps it in registers, 16-byte accesses, shuffle reductions; mu
@@ -83,14 +84,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // X: dtype of dz / dx0; R: dtype of the saved sum x, of dx_residual and of dx1; W: dtype of gamma.
-template <typename X, typename R, typename W, int NV>
+struct DropArgs {
+  uint32_t base = 0, thr24 = 0;   // thr24 == 0: no dropout
+  float scale = 1.f;
+};
+
+template <typename X, typename R, typename W, int NV, bool kDrop>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, NV <= 3 ? 2 : 1)
 ln_residual_bwd_kernel(const X* __restrict__ dz, const R* __restrict__ dxres, const R* __restrict__ x,
                        const W* __restrict__ gamma, const float* __restrict__ mu_in, const float* __restrict__ rs_in,
                        X* __restrict__ dx0, R* __restrict__ dx1, float* __restrict__ part /* [gridDim.x][2][cols] */,
-                       int64_t rows, int cols, float eps) {
-  extern __shared__ float lnb_smem[];   // [kWarpsPerCta][cols] reduction buffer (dgamma, then dbeta), then [cols] gamma
+                       int64_t rows, int cols, float eps, DropArgs drop) {
+  extern __shared__ float lnb_smem[];   // [kWarpsPerCta][cols] reduction buffer (dgamma, then dbeta), then [cols] gamma,
+                                        // with dropout [cols] column words of the keep mask
   float* s_gamma = lnb_smem + kWarpsPerCta * cols;
+  uint32_t* s_cw = reinterpret_cast<uint32_t*>(s_gamma + cols);
+  if constexpr (kDrop)
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s_cw[c] = drop_col_word(drop.base, static_cast<uint32_t>(c));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + warp;
@@ -179,8 +189,18 @@ ln_residual_bwd_kernel(const X* __restrict__ dz, const R* __restrict__ dxres, co
 #pragma unroll
           for (int k = 0; k < 8; ++k) o[k] += r[k];
         }
-        V8<X>::store(dx0 + base + v * 8, o);
-        if (dx1 != nullptr) V8<R>::store(dx1 + base + v * 8, o);
+        if constexpr (!kDrop) {
+          V8<X>::store(dx0 + base + v * 8, o);
+          if (dx1 != nullptr) V8<R>::store(dx1 + base + v * 8, o);
+        } else {
+          if (dx1 != nullptr) V8<R>::store(dx1 + base + v * 8, o);
+          const uint32_t rw = drop_row_word(drop.base, static_cast<uint32_t>(row));
+          const uint4 c0 = *reinterpret_cast<const uint4*>(s_cw + v * 8), c1 = *reinterpret_cast<const uint4*>(s_cw + v * 8 + 4);
+          const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = drop_keep(rw, cw[k], drop.thr24) ? o[k] * drop.scale : 0.f;
+          V8<X>::store(dx0 + base + v * 8, o);
+        }
       }
     }
   }
@@ -234,10 +254,10 @@ ln_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int cols, W* 
   }
 }
 
-template <typename X, typename R, typename W, int NV>
-int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamma, const float* mu, const float* rs,
-              void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps,
-              cudaStream_t st) {
+template <typename X, typename R, typename W, int NV, bool kDrop>
+int launch_kernel(const void* dz, const void* dxres, const void* x, const void* gamma, const float* mu, const float* rs,
+                  void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps,
+                  DropArgs drop, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -245,8 +265,8 @@ int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamm
   int64_t cap = static_cast<int64_t>(sms) * 2;
   if (cap > kMaxCtas) cap = kMaxCtas;
   const int grid = static_cast<int>(ctas_needed < cap ? ctas_needed : cap);
-  const size_t smem = static_cast<size_t>(kWarpsPerCta + 1) * cols * sizeof(float);
-  auto kern = ln_residual_bwd_kernel<X, R, W, NV>;
+  const size_t smem = static_cast<size_t>(kWarpsPerCta + 1 + (kDrop ? 1 : 0)) * cols * sizeof(float);
+  auto kern = ln_residual_bwd_kernel<X, R, W, NV, kDrop>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
@@ -256,19 +276,29 @@ int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamm
   }
   kern<<<grid, kWarpsPerCta * 32, smem, st>>>(static_cast<const X*>(dz), static_cast<const R*>(dxres),
                                               static_cast<const R*>(x), static_cast<const W*>(gamma), mu, rs,
-                                              static_cast<X*>(dx0), static_cast<R*>(dx1), part, rows, cols, eps);
+                                              static_cast<X*>(dx0), static_cast<R*>(dx1), part, rows, cols, eps, drop);
   if (int rc = check_launch("bp_ln_residual_bwd launch")) return rc;
   ln_bwd_finalize_kernel<W><<<(cols + 31) / 32, dim3(32, 16), 0, st>>>(part, grid, cols, static_cast<W*>(dgamma),
                                                                  static_cast<W*>(dbeta));
   return check_launch("bp_ln_residual_bwd (finalize) launch");
 }
 
+template <typename X, typename R, typename W, int NV>
+int launch_nv(const void* dz, const void* dxres, const void* x, const void* gamma, const float* mu, const float* rs,
+              void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps,
+              DropArgs drop, cudaStream_t st) {
+  if (drop.thr24 != 0)
+    return launch_kernel<X, R, W, NV, true>(dz, dxres, x, gamma, mu, rs, dx0, dx1, dgamma, dbeta, part, rows, cols, eps, drop, st);
+  return launch_kernel<X, R, W, NV, false>(dz, dxres, x, gamma, mu, rs, dx0, dx1, dgamma, dbeta, part, rows, cols, eps, drop, st);
+}
+
 template <typename X, typename R, typename W>
 int launch(const void* dz, const void* dxres, const void* x, const void* gamma, const float* mu, const float* rs,
-           void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps, cudaStream_t st) {
+           void* dx0, void* dx1, void* dgamma, void* dbeta, float* part, int64_t rows, int cols, float eps, DropArgs drop,
+           cudaStream_t st) {
   const int nv = (cols / 8 + 31) / 32;
 #define BP_LNB_CASE(N) \
-  if (nv <= N) return launch_nv<X, R, W, N>(dz, dxres, x, gamma, mu, rs, dx0, dx1, dgamma, dbeta, part, rows, cols, eps, st)
+  if (nv <= N) return launch_nv<X, R, W, N>(dz, dxres, x, gamma, mu, rs, dx0, dx1, dgamma, dbeta, part, rows, cols, eps, drop, st)
   BP_LNB_CASE(1);
   BP_LNB_CASE(2);
   BP_LNB_CASE(3);
@@ -286,11 +316,12 @@ extern "C" int64_t bp_ln_bwd_workspace_bytes(int32_t cols) {
   return cols > 0 ? static_cast<int64_t>(bp::lnb::kMaxCtas) * 2 * cols * 4 : 0;
 }
 
-extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma,
-                                  const float* mu, const float* rsigma, void* dx0,
-                                  void* dx1, void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes,
-                                  int64_t rows, int32_t cols, float epsilon, int32_t x0_dtype, int32_t residual_dtype,
-                                  int32_t weight_dtype, void* stream) {
+namespace {
+int ln_residual_bwd_impl(const void* dz, const void* dx_residual, const void* x, const void* gamma,
+                         const float* mu, const float* rsigma, void* dx0,
+                         void* dx1, void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes,
+                         int64_t rows, int32_t cols, float epsilon, int32_t x0_dtype, int32_t residual_dtype,
+                         int32_t weight_dtype, bp::lnb::DropArgs drop, void* stream) {
   using namespace bp;
   if (!dz || !x || !gamma || !dx0 || !dgamma || !dbeta || !workspace)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_ln_residual_bwd: null pointer argument");
@@ -311,7 +342,7 @@ extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const
   const int key = x0_dtype * 100 + residual_dtype * 10 + weight_dtype;
 #define BP_LNB_DISPATCH(XD, RD, WD, X, R, W) \
   if (key == XD * 100 + RD * 10 + WD)        \
-  return lnb::launch<X, R, W>(dz, dx_residual, x, gamma, mu, rsigma, dx0, dx1, dgamma, dbeta, part, rows, cols, epsilon, st)
+  return lnb::launch<X, R, W>(dz, dx_residual, x, gamma, mu, rsigma, dx0, dx1, dgamma, dbeta, part, rows, cols, epsilon, drop, st)
   using bf = __nv_bfloat16;
   using hf = __half;
   BP_LNB_DISPATCH(BP_DTYPE_BF16, BP_DTYPE_F32, BP_DTYPE_BF16, bf, float, bf);
@@ -324,4 +355,27 @@ extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const
 #undef BP_LNB_DISPATCH
   return fail(BP_ERR_UNSUPPORTED, "bp_ln_residual_bwd: dtype combination (x0=%d, residual=%d, weight=%d) not built",
               x0_dtype, residual_dtype, weight_dtype);
+}
+}  // namespace
+
+extern "C" int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, const void* gamma,
+                                  const float* mu, const float* rsigma, void* dx0,
+                                  void* dx1, void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes,
+                                  int64_t rows, int32_t cols, float epsilon, int32_t x0_dtype, int32_t residual_dtype,
+                                  int32_t weight_dtype, void* stream) {
+  return ln_residual_bwd_impl(dz, dx_residual, x, gamma, mu, rsigma, dx0, dx1, dgamma, dbeta, workspace, workspace_bytes,
+                              rows, cols, epsilon, x0_dtype, residual_dtype, weight_dtype, bp::lnb::DropArgs(), stream);
+}
+
+extern "C" int bp_ln_residual_bwd_dropout(const void* dz, const void* dx_residual, const void* x, const void* gamma,
+                                          const float* mu, const float* rsigma, void* dx0,
+                                          void* dx1, void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes,
+                                          int64_t rows, int32_t cols, float epsilon, int32_t x0_dtype,
+                                          int32_t residual_dtype, int32_t weight_dtype, float dropout_p, uint64_t seed,
+                                          void* stream) {
+  bp::lnb::DropArgs drop;
+  if (int rc = bp::ln_drop_args(dropout_p, seed, rows, "bp_ln_residual_bwd_dropout", &drop.base, &drop.thr24, &drop.scale))
+    return rc;
+  return ln_residual_bwd_impl(dz, dx_residual, x, gamma, mu, rsigma, dx0, dx1, dgamma, dbeta, workspace, workspace_bytes,
+                              rows, cols, epsilon, x0_dtype, residual_dtype, weight_dtype, drop, stream);
 }

@@ -174,6 +174,17 @@ def bench_bwd_ops(iters, rows=65536, cols=768, inner=3072):
     t, tm = time_fn(lambda i: torch.autograd.grad((z, r), (x0, x1, w, bb), (g, g2), retain_graph=True), 1, iters)
     # dz (2) + x (4) + dx_residual (4) in, dx0 (2) + dx1 (4) out
     report(f"ln_residual_bwd {rows}x{cols} bf16 / fp32 residual", t, tm, 0, rows * cols * 16)
+    # residual dropout inside the same kernels (training configuration of the reference: resid_pdrop = 0.1)
+    zd, rd = dropout_add_layer_norm(x0, x1, w, bb, 0.1, 1e-5, prenorm=True, seed=1)
+    t, tm = time_fn(lambda i: torch.autograd.grad((zd, rd), (x0, x1, w, bb), (g, g2), retain_graph=True), 1, iters)
+    report(f"ln_residual_bwd with dropout 0.1 {rows}x{cols} bf16 / fp32 residual", t, tm, 0, rows * cols * 16)
+    with torch.no_grad():
+        t, tm = time_fn(lambda i: dropout_add_layer_norm(x0, x1, w, bb, 0.1, 1e-5, prenorm=True, seed=1), 1, iters)
+        report(f"ln_residual_fwd with dropout 0.1 {rows}x{cols}", t, tm, 0, rows * cols * 12)
+        t, tm = time_fn(lambda i: dropout_add_layer_norm(x0, x1, w, bb, 0.0, 1e-5, prenorm=True), 1, iters)
+        report(f"ln_residual_fwd without dropout {rows}x{cols}", t, tm, 0, rows * cols * 12)
+        t, tm = time_fn(lambda i: torch.nn.functional.dropout(x0, 0.1, training=True), 1, iters)
+        report("  (for comparison: the separate F.dropout pass over x0 this replaces, forward only)", t, tm, 0, rows * cols * 4)
     d = torch.randn(rows, inner, device="cuda").bfloat16()
     pre = torch.randn(rows, inner, device="cuda").bfloat16()
     t, tm = time_fn(lambda i: bias_act_backward(d, pre, "gelu_tanh", True), 1, iters)

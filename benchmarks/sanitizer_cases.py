@@ -64,15 +64,15 @@ def sense(b, s, nv, d):
     finite(f"sense_mix b={b} s={s} nv={nv} d={d}", out, qk.grad, content.grad)
 
 
-def layer_norm(rows, cols):
+def layer_norm(rows, cols, p=0.0):
     torch.manual_seed(3)
     x0 = torch.randn(rows, cols, device=dev, dtype=torch.bfloat16, requires_grad=True)
     res = torch.randn(rows, cols, device=dev, dtype=torch.float32, requires_grad=True)
     w = torch.randn(cols, device=dev, dtype=torch.bfloat16, requires_grad=True)
     b = torch.randn(cols, device=dev, dtype=torch.bfloat16, requires_grad=True)
-    z, r = dropout_add_layer_norm(x0, res, w, b, 0.0, 1e-5, prenorm=True, residual_in_fp32=True)
+    z, r = dropout_add_layer_norm(x0, res, w, b, p, 1e-5, prenorm=True, residual_in_fp32=True)
     (z.float().sum() + r.sum()).backward()
-    finite(f"layer norm {rows}x{cols}", z, r, x0.grad, res.grad, w.grad, b.grad)
+    finite(f"layer norm {rows}x{cols} p={p}", z, r, x0.grad, res.grad, w.grad, b.grad)
 
 
 def mlp(rows, n):
@@ -107,6 +107,7 @@ if __name__ == "__main__":
     sense(2, 200, 4, 768)
     layer_norm(300, 768)
     layer_norm(65, 1024)
+    layer_norm(77, 768, p=0.1)
     mlp(300, 256)
     xent(100, 50264)
     xent(33, 1000)

@@ -4,11 +4,11 @@
  * pybind11 extensions the reference's Python op wrappers import (paths relative to the reference repository):
  *
  *   flash_attn_cuda.fwd                       csrc/flash_attn/fmha_api.cpp:189-325      -> bp_fmha_fwd
- *   dropout_layer_norm.dropout_add_ln_fwd     csrc/layer_norm/ln_api.cpp:83-251         -> bp_ln_residual_fwd
+ *   dropout_layer_norm.dropout_add_ln_fwd     csrc/layer_norm/ln_api.cpp:83-251         -> bp_ln_residual_fwd[_dropout]
  *   fused_dense_lib.linear_gelu_forward       csrc/fused_dense_lib/fused_dense.cpp:88-142 -> bp_linear_bias_act_fwd
  *   rotary_emb.apply_rotary                   csrc/rotary/rotary.cpp:12-33              -> bp_rotary_qk_inplace
  *   flash_attn_cuda.bwd                       csrc/flash_attn/fmha_api.cpp:338-500      -> bp_fmha_bwd
- *   dropout_layer_norm.dropout_add_ln_bwd     csrc/layer_norm/ln_api.cpp:255-440        -> bp_ln_residual_bwd
+ *   dropout_layer_norm.dropout_add_ln_bwd     csrc/layer_norm/ln_api.cpp:255-440        -> bp_ln_residual_bwd[_dropout]
  *   fused_dense_lib backward epilogues        csrc/fused_dense_lib/fused_dense_cuda.cu:559-787 -> bp_bias_act_bwd
  *   xentropy_cuda_lib.forward / .backward     csrc/xentropy/interface.cpp:57-58         -> bp_xentropy_fwd / _bwd
  *   (no reference kernel; eager PyTorch at    training/src/models/backpack.py:111-122,313) -> bp_sense_lse_fwd,
@@ -159,7 +159,7 @@ int bp_sense_mix_table_fwd(const void* qk, const void* table, const int64_t* inp
                            int32_t batch, int32_t seqlen, int32_t nv, int32_t dk, int32_t d, int32_t vocab,
                            float softmax_scale, int32_t dtype, void* stream);
 
-/* Residual add + LayerNorm forward, eval mode (replaces dropout_add_ln_fwd with dropout_p = 0, no
+/* Residual add + LayerNorm forward without dropout (replaces dropout_add_ln_fwd with dropout_p = 0, no
  * rowscale/colscale/subset; csrc/layer_norm/ln_api.cpp:83-251, ln_fwd_kernels.cuh:98-188).
  *   x0 (rows, cols) x0_dtype; x1 (rows, cols) residual_dtype or NULL;
  *   x_out = x0 + x1 written in residual_dtype (may be NULL when not needed: prenorm=False);
@@ -256,6 +256,24 @@ int bp_ln_residual_bwd(const void* dz, const void* dx_residual, const void* x, c
                        const float* mu, const float* rsigma, void* dx0, void* dx1,
                        void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes, int64_t rows, int32_t cols,
                        float epsilon, int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype, void* stream);
+
+/* The same two functions with the reference's residual dropout inside the kernel (dropout_add_ln_fwd / _bwd with
+ * dropout_p > 0, ln_fwd_kernels.cuh:96-131, ln_bwd_kernels.cuh): x = dropout(x0) / (1 - p) + x1 in the forward,
+ * dx0 = keep ? dx / (1 - p) : 0 in the backward (dx1 = dx).  The keep mask is a pure function of (seed, row, col) --
+ * one hashed word per row, one per column, bp_common.cuh -- so the forward stores no mask and the backward regenerates
+ * it from the same seed.  dropout_p in [0, 1) is quantised to round(256 p) / 256 (at least 1 / 256 when p > 0);
+ * dropout_p == 0 is exactly bp_ln_residual_fwd / _bwd.  rows < 2^32.
+ */
+int bp_ln_residual_fwd_dropout(const void* x0, const void* x1, const void* gamma, const void* beta,
+                               void* z, void* x_out, float* mu, float* rsigma,
+                               int64_t rows, int32_t cols, float epsilon,
+                               int32_t x0_dtype, int32_t residual_dtype, int32_t weight_dtype,
+                               float dropout_p, uint64_t seed, void* stream);
+int bp_ln_residual_bwd_dropout(const void* dz, const void* dx_residual, const void* x, const void* gamma,
+                               const float* mu, const float* rsigma, void* dx0, void* dx1,
+                               void* dgamma, void* dbeta, void* workspace, int64_t workspace_bytes, int64_t rows,
+                               int32_t cols, float epsilon, int32_t x0_dtype, int32_t residual_dtype,
+                               int32_t weight_dtype, float dropout_p, uint64_t seed, void* stream);
 
 /* Backward of the bias + activation epilogue of bp_linear_bias_act_fwd: what the reference gets from cuBLASLt's
  * BGRADB / DGELU_BGRAD epilogues (csrc/fused_dense_lib/fused_dense_cuda.cu:559-787; flash_attn/ops/fused_dense.py:

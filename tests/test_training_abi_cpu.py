@@ -134,3 +134,42 @@ def test_training_operators_refuse_cpu_tensors(lib):
         CrossEntropyLoss()(torch.zeros(4, 8), torch.zeros(4, dtype=torch.long))
     with pytest.raises(RuntimeError, match="CUDA"):
         SoftmaxCrossEntropyLossFn.apply(torch.zeros(4, 8), torch.zeros(4, dtype=torch.long))
+
+
+def test_layer_norm_dropout_mask_restatement_and_argument_validation(lib):
+    """The Python restatement of the LayerNorm dropout mask against a scalar re-derivation of bp_common.cuh's hash, and
+    the argument checks of the two dropout entry points (before any CUDA call)."""
+    from backpacks_flash_attn_b200 import _lib
+    from backpacks_flash_attn_b200.flash_attn_interface import effective_dropout_p
+    from backpacks_flash_attn_b200.ops.layer_norm import layer_norm_dropout_mask
+
+    def mix(x):
+        x &= 0xFFFFFFFF
+        x ^= x >> 16
+        x = (x * 0x7FEB352D) & 0xFFFFFFFF
+        x ^= x >> 15
+        x = (x * 0x846CA68B) & 0xFFFFFFFF
+        return x ^ (x >> 16)
+
+    seed, rows, cols, p = (123456789 << 20) + 17, 37, 24, 0.3
+    thr = int(effective_dropout_p(p) * 256)
+    base = mix((seed & 0xFFFFFFFF) ^ mix(((seed >> 32) & 0xFFFFFFFF) + 0x4C4E))
+    m = layer_norm_dropout_mask(seed, rows, cols, p)
+    for r in range(rows):
+        rw = mix(base + r * 0x9E3779B1)
+        for c in range(cols):
+            cw = mix((~base & 0xFFFFFFFF) + c * 0x85EBCA77)
+            assert bool(m[r, c]) == ((((rw ^ cw) * 0x2C1B3C6D) & 0xFFFFFFFF) >= (thr << 24))
+    big = layer_norm_dropout_mask(seed, 4096, 768, p)
+    assert abs((1 - big.float().mean().item()) - thr / 256) < 2e-3
+    assert not torch.equal(big, layer_norm_dropout_mask(seed + 1, 4096, 768, p))
+    buf = ctypes.create_string_buffer(256)
+    a = (ctypes.addressof(buf) + 15) // 16 * 16
+    st = lib.bp_ln_residual_fwd_dropout(a, a, a, a, a, a, None, None, 4, 8, 1e-5, 1, 2, 1, 1.0, 5, None)
+    assert st == -1 and "dropout_p" in _lib.last_error()
+    st = lib.bp_ln_residual_fwd_dropout(a, a, a, a, a, a, None, None, 4, 8, 1e-5, 1, 2, 1, -0.1, 5, None)
+    assert st == -1 and "dropout_p" in _lib.last_error()
+    st = lib.bp_ln_residual_bwd_dropout(a, a, a, a, None, None, a, a, a, a, a, 1 << 30, 4, 8, 1e-5, 1, 2, 1, 1.5, 5, None)
+    assert st == -1 and "dropout_p" in _lib.last_error()
+    st = lib.bp_ln_residual_fwd_dropout(a, a, a, a, a, a, None, None, 4, 12, 1e-5, 1, 2, 1, 0.1, 5, None)
+    assert st == -1 and "multiple of 8" in _lib.last_error()
