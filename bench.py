@@ -446,6 +446,23 @@ def run_ours(args):
                     del tg
                 except Exception as exc:
                     training["graph_error"] = f"{type(exc).__name__}: {exc}"[:200]
+            # the reference's training configuration: residual / embedding / attention dropout 0.1, every mask drawn
+            # INSIDE the LayerNorm and attention kernels (bp_ln_residual_*_dropout, bp_fmha_*_dropout)
+            try:
+                for m in tmodel.modules():
+                    if isinstance(m, torch.nn.Dropout):
+                        m.p = 0.1
+                    if hasattr(m, "dropout_p"):
+                        m.dropout_p = 0.1
+                before = dict(_lib.launch_counts)
+                for _ in range(2):
+                    train_step()
+                training["dropout_dt"] = timed_steps(train_step, args.training_steps, parallel, dev)
+                training["dropout_launches"] = {n: _lib.launch_counts.get(n, 0) - before.get(n, 0) for n in
+                                                ("bp_ln_residual_fwd_dropout", "bp_ln_residual_bwd_dropout",
+                                                 "bp_fmha_fwd_dropout", "bp_fmha_bwd")}
+            except Exception as exc:
+                training["dropout_error"] = f"{type(exc).__name__}: {exc}"[:200]
             del tmodel
         except Exception as exc:   # a variant must never take the headline line down with it
             training, training_error = None, f"{type(exc).__name__}: {exc}"[:300]
@@ -617,6 +634,12 @@ def run_ours(args):
                             "value": tb * S * world / (training["graph_dt"] / training["steps"]), "unit": "tokens/s",
                             "note": "forward + backward captured once, replayed as one CUDA graph"}
                            if "graph_dt" in training else {"unavailable": training.get("graph_error", "multi-GPU run")}),
+            "with_dropout": ({"ms_per_step": training["dropout_dt"] / training["steps"] * 1e3,
+                              "value": tb * S * world / (training["dropout_dt"] / training["steps"]), "unit": "tokens/s",
+                              "launches": training["dropout_launches"],
+                              "note": "the reference's training configuration (residual / embedding / attention dropout "
+                                      "0.1): every mask is drawn inside the LayerNorm and attention kernels from a seed"}
+                             if "dropout_dt" in training else {"unavailable": training.get("dropout_error", "not run")}),
             "own_kernel_share": sum(c * ms for c, ms in tk.values()) / tms,
             "kernels": {n: {"calls_per_step": c, "ms_per_call": ms, "ms_per_step": c * ms} for n, (c, ms) in tk.items()},
             "fmha_bwd": {"kernel": "bp_fmha_bwd: bwd_stats_kernel + fmha_bwd_kernel<64, keys own> + fmha_bwd_kernel<64, "
