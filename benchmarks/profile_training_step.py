@@ -1,4 +1,8 @@
-"""Top CUDA kernels of one Backpack-Small training step (torch profiler): where the time outside this library goes."""
+"""Top CUDA kernels of one Backpack-Small training step (torch profiler): where the time outside this library goes.
+
+    python benchmarks/profile_training_step.py [batch]                 # torch profiler table of one step
+    python benchmarks/profile_training_step.py 64 --plain 2             # two bare steps (ncu launch list)
+"""
 import os
 import sys
 
@@ -24,6 +28,11 @@ def step():
     ce(logits.view(-1, logits.shape[-1]), labels).backward()
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "--plain":      # N bare steps, for an ncu launch list of the training step
+    for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 2):
+        step()
+    torch.cuda.synchronize()
+    raise SystemExit(0)
 for _ in range(2):
     step()
 torch.cuda.synchronize()
