@@ -40,6 +40,7 @@ SIGNATURES = {
     "bp_sense_mix_table_fwd": [c_void_p] * 5 + [c_int32] * 6 + [c_float, c_int32, c_void_p],
     "bp_ln_residual_fwd": [c_void_p] * 8 + [c_int64, c_int32, c_float, c_int32, c_int32, c_int32, c_void_p],
     "bp_linear_bias_act_fwd": [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    "bp_linear_bias_act_aux_fwd": [c_void_p] * 5 + [c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "bp_lm_head_stats_fwd": [c_void_p] * 7 + [c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "bp_decode_attn_fwd": [c_void_p] * 4 + [c_int32] * 4 + [c_int64] * 3 + [c_float, c_int32, c_void_p],
     "bp_sense_mix_decode_fwd": [c_void_p] * 6 + [c_int32] * 6 + [c_int64] * 2 + [c_float, c_int32, c_void_p],

@@ -44,6 +44,7 @@ struct Params {
   int32_t m_tiles, n_tiles, k_blocks;
   int32_t act;
   int32_t residual_mode;   // pair kernel: the output map is the fp32 residual stream, updated in place (+=)
+  int32_t aux_mode;        // pair kernel: also store x W^T + bias BEFORE the activation through the auxiliary map
   int32_t group_n;         // pair kernel: n-tiles per tile-order group (see tile_coords)
   // "stats" mode of the pair kernel (bp_lm_head_stats_fwd): the logits are never written; every epilogue thread keeps
   // the running softmax statistics of its row across all n-tiles
@@ -311,7 +312,8 @@ struct Barriers {
 template <bool kBF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::kThreads, 1)
 gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const __grid_constant__ CUtensorMap tmO, const Params p) {
+                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmAux,
+                          const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   pair::Barriers& bars = *reinterpret_cast<pair::Barriers*>(smem + pair::offBar);
@@ -326,6 +328,7 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (!p.stats_mode) tma_prefetch_desc(&tmO);
+    if (p.aux_mode) tma_prefetch_desc(&tmAux);
     for (int i = 0; i < pair::kStages; ++i) mbar_init(&bars.full[i], 1), mbar_init(&bars.empty[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bars.acc_full[i], 1), mbar_init(&bars.acc_empty[i], 512);
     for (int i = 0; i < 8; ++i) mbar_init(&bars.res_full[i][0], 1), mbar_init(&bars.res_full[i][1], 1);
@@ -602,6 +605,29 @@ gemm_bias_act_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
           }
         }
+        if (p.aux_mode) {
+          // training (the reference's save_gelu_in, fused_dense.cpp:88-142): the pre-activation goes out through the
+          // auxiliary map from this staging buffer, the activated values follow through the other one
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint4 w;
+            w.x = pack2<kBF16>(f[g * 8 + 0], f[g * 8 + 1]);
+            w.y = pack2<kBF16>(f[g * 8 + 2], f[g * 8 + 3]);
+            w.z = pack2<kBF16>(f[g * 8 + 4], f[g * 8 + 5]);
+            w.w = pack2<kBF16>(f[g * 8 + 6], f[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(stage + sw128_offset(lane, g)) = w;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          ++chunk_it;
+          stage = my_stage + (chunk_it & 1) * pair::kWarpChunkBytes;
+          if (lane == 0) {
+            tma_store_2d(&tmAux, my_stage + ((chunk_it - 1) & 1) * pair::kWarpChunkBytes, col, m0);
+            tma_store_commit();
+            tma_store_wait_read<1>();   // the other buffer's previous store has been read out
+          }
+          __syncwarp();
+        }
         if (p.act == BP_ACT_GELU_TANH) {
 #pragma unroll
           for (int i = 0; i < 64; i += 2) gelu_tanh_pair(f[i], f[i + 1]);
@@ -639,7 +665,8 @@ namespace gemm {
 
 // shared by both entry points; out == nullptr selects the residual mode (residual updated in place)
 static int launch_linear(const char* fn, const void* x, const void* w, const void* bias, void* out, float* residual,
-                         int64_t m, int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream) {
+                         int64_t m, int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream,
+                         void* pre_out = nullptr) {
   if (!x || !w || (!out && !residual)) return fail(BP_ERR_INVALID_ARGUMENT, "%s: null pointer argument", fn);
   if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
     return fail(BP_ERR_INVALID_ARGUMENT, "%s: only fp16 and bf16 are supported", fn);
@@ -652,7 +679,9 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
   if ((uintptr_t)x % 16 || (uintptr_t)w % 16 || (uintptr_t)out % 16 || (uintptr_t)residual % 16 || (uintptr_t)bias % 4)
     return fail(BP_ERR_INVALID_ARGUMENT, "%s: pointers must be 16-byte aligned", fn);
   if (residual && m < 256) return fail(BP_ERR_UNSUPPORTED, "%s: needs m >= 256 (got %lld)", fn, (long long)m);
-  CUtensorMap tmA, tmB, tmO;
+  if (pre_out && m < 256) return fail(BP_ERR_UNSUPPORTED, "%s: needs m >= 256 (got %lld)", fn, (long long)m);
+  if ((uintptr_t)pre_out % 16) return fail(BP_ERR_INVALID_ARGUMENT, "%s: pointers must be 16-byte aligned", fn);
+  CUtensorMap tmA, tmB, tmO, tmAux;
   {
     const uint64_t da[2] = {(uint64_t)k, (uint64_t)m}, sa[1] = {(uint64_t)k * 2};
     const uint32_t ba[2] = {BK, BM};
@@ -664,6 +693,7 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
   p.k_blocks = (k + BK - 1) / BK;
   p.act = activation;
   p.residual_mode = residual != nullptr ? 1 : 0;
+  p.aux_mode = pre_out != nullptr ? 1 : 0;
   p.n_tiles = (n + BN - 1) / BN;
   p.group_n = p.n_tiles;
   p.stats_mode = 0, p.n_valid = n;
@@ -711,14 +741,17 @@ static int launch_linear(const char* fn, const void* x, const void* w, const voi
       const uint64_t so[1] = {(uint64_t)n * 2};
       const uint32_t bo[2] = {64, 32};
       if (int rc = encode_tensor_map(&tmO, dtype, 2, out, dout, so, bo, true)) return rc;
+      if (pre_out)
+        if (int rc = encode_tensor_map(&tmAux, dtype, 2, pre_out, dout, so, bo, true)) return rc;
     }
+    if (!pre_out) tmAux = tmO;   // never dereferenced
     auto kern = bf ? gemm_bias_act_pair_kernel<true> : gemm_bias_act_pair_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
       return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
     }
-    kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, st>>>(tmA, tmB, tmO, p);   // __cluster_dims__(2,1,1)
+    kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, st>>>(tmA, tmB, tmO, tmAux, p);   // __cluster_dims__(2,1,1)
     return check_launch(fn);
   }
   {
@@ -748,6 +781,17 @@ extern "C" int bp_linear_bias_act_fwd(const void* x, const void* w, const void* 
                                       int32_t n, int32_t k, int32_t activation, int32_t dtype, void* stream) {
   if (!out) return bp::fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_fwd: null pointer argument");
   return bp::gemm::launch_linear("bp_linear_bias_act_fwd", x, w, bias, out, nullptr, m, n, k, activation, dtype, stream);
+}
+
+// The reference's linear_gelu_forward(..., save_gelu_in = true) (csrc/fused_dense_lib/fused_dense.cpp:88-142): the
+// activated output AND the pre-activation x W^T + bias, both from one pass over the accumulators.
+extern "C" int bp_linear_bias_act_aux_fwd(const void* x, const void* w, const void* bias, void* out, void* pre_out,
+                                          int64_t m, int32_t n, int32_t k, int32_t activation, int32_t dtype,
+                                          void* stream) {
+  if (!out || !pre_out) return bp::fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_aux_fwd: null pointer argument");
+  if (out == pre_out) return bp::fail(BP_ERR_INVALID_ARGUMENT, "bp_linear_bias_act_aux_fwd: out and pre_out must differ");
+  return bp::gemm::launch_linear("bp_linear_bias_act_aux_fwd", x, w, bias, out, nullptr, m, n, k, activation, dtype, stream,
+                                 pre_out);
 }
 
 extern "C" int bp_linear_bias_residual_fwd(const void* x, const void* w, const void* bias, float* residual, int64_t m,
@@ -792,6 +836,7 @@ extern "C" int bp_lm_head_stats_fwd(const void* x, const void* w, const int64_t*
   p.k_blocks = (k + BK - 1) / BK;
   p.act = BP_ACT_NONE;
   p.residual_mode = 0;
+  p.aux_mode = 0;
   p.m_tiles = static_cast<int32_t>((m + 255) / 256);
   p.n_tiles = (n_valid + BN - 1) / BN;
   p.group_n = p.n_tiles;
@@ -805,6 +850,6 @@ extern "C" int bp_lm_head_stats_fwd(const void* x, const void* w, const int64_t*
     cudaGetLastError();
     return fail(BP_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
   }
-  kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmO, p);
+  kern<<<2 * clusters, pair::kThreads, pair::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmO, tmO, p);
   return check_launch(fn);
 }

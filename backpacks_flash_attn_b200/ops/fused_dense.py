@@ -30,8 +30,10 @@ def _dense_bias(bias: torch.Tensor | None, n: int) -> torch.Tensor | None:
 
 
 def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
-                    activation: str = "gelu_tanh") -> torch.Tensor:
-    """act(x @ weight.T + bias) through the hand-written tcgen05 GEMM (weight in nn.Linear layout)."""
+                    activation: str = "gelu_tanh", save_pre_act: bool = True) -> torch.Tensor:
+    """act(x @ weight.T + bias) through the hand-written tcgen05 GEMM (weight in nn.Linear layout).  Under autograd
+    with an activation, `save_pre_act` makes the forward kernel also store the pre-activation for the backward (the
+    reference's checkpoint_lvl 0 / 1); otherwise the backward recomputes it with one more GEMM (checkpoint_lvl 2)."""
     _lib.require_cuda(x, weight, bias)
     if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
         raise RuntimeError("linear_bias_act needs fp16/bf16 activations and weights of the same dtype")
@@ -43,7 +45,7 @@ def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
     bias = _dense_bias(bias, n)
     if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
                                     or (bias is not None and bias.requires_grad)):
-        return _LinearBiasActFn.apply(x, weight, bias, activation)
+        return _LinearBiasActFn.apply(x, weight, bias, activation, save_pre_act)
     x2 = x.reshape(-1, k)
     if not x2.is_contiguous():
         x2 = x2.contiguous()
@@ -56,6 +58,21 @@ def linear_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | 
                                                 _lib.stream_ptr(x.device))
     _lib.check(st, "bp_linear_bias_act_fwd")
     return out.reshape(*x.shape[:-1], n)
+
+
+def _linear_bias_act_aux(x2: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, activation: str):
+    """(act(x W^T + b), x W^T + b) from ONE pass of the GEMM (bp_linear_bias_act_aux_fwd: the reference's
+    linear_gelu_forward with save_gelu_in, fused_dense.py:220-222).  x2 (m, k) contiguous, m >= 256."""
+    n, k = weight.shape
+    out = torch.empty((x2.shape[0], n), dtype=x2.dtype, device=x2.device)
+    pre = torch.empty_like(out)
+    act = {"none": _lib.BP_ACT_NONE, "gelu_tanh": _lib.BP_ACT_GELU_TANH}[activation]
+    with torch.cuda.device(x2.device):
+        st = _lib.load().bp_linear_bias_act_aux_fwd(x2.data_ptr(), weight.data_ptr(), _lib.ptr(bias), out.data_ptr(),
+                                                    pre.data_ptr(), x2.shape[0], n, k, act, _lib.dtype_code(x2.dtype),
+                                                    _lib.stream_ptr(x2.device))
+    _lib.check(st, "bp_linear_bias_act_aux_fwd")
+    return out, pre
 
 
 def bias_act_backward(dact: torch.Tensor, pre: torch.Tensor | None, activation: str, want_dbias: bool):
@@ -99,33 +116,42 @@ def _dgrad(dy2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
 
 class _LinearBiasActFn(torch.autograd.Function):
     """act(x W^T + b) with this library's forward GEMM (FusedDenseFunc, fused_dense.py:39-80, and the fc1 half of
-    FusedDenseGeluDenseFunc, :179-300).  Backward: the pre-activation is recomputed by one more GEMM (the
-    reference's checkpoint_lvl = 2 behaviour, fused_dense.py:262-266) because the fused forward kernel never writes
-    it; dgelu + bias gradient are one pass of bp_bias_act_bwd; dgrad on this library's GEMM, wgrad on cuBLAS."""
+    FusedDenseGeluDenseFunc, :179-300).  With an activation the forward kernel also stores the pre-activation through a
+    second output map (the reference's save_gelu_in / checkpoint_lvl 0-1, fused_dense.py:220-222, 262-266) unless
+    `save_pre_act` is False or there are fewer than 256 rows, in which case the backward recomputes it by one more GEMM
+    (checkpoint_lvl = 2).  dgelu + bias gradient are one pass of bp_bias_act_bwd; dgrad on this library's GEMM, wgrad on
+    cuBLAS."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, activation):
+    def forward(ctx, x, weight, bias, activation, save_pre_act=True):
+        n, k = weight.shape
+        pre = None
         with torch.no_grad():
-            out = linear_bias_act(x, weight, bias, activation)
-        ctx.save_for_backward(x, weight, bias)
+            if activation != "none" and save_pre_act and x.numel() // k >= 256:
+                x2 = x.reshape(-1, k)
+                x2 = x2 if x2.is_contiguous() else x2.contiguous()
+                out, pre = _linear_bias_act_aux(x2, weight.contiguous(), bias, activation)
+                out = out.reshape(*x.shape[:-1], n)
+            else:
+                out = linear_bias_act(x, weight, bias, activation)
+        ctx.save_for_backward(x, weight, bias, pre)
         ctx.activation = activation
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, bias = ctx.saved_tensors
+        x, weight, bias, pre = ctx.saved_tensors
         n, k = weight.shape
         x2 = x.reshape(-1, k)
         d2 = dout.reshape(-1, n)
         want_db = bias is not None and ctx.needs_input_grad[2]
-        pre = None
-        if ctx.activation == "gelu_tanh":
+        if ctx.activation == "gelu_tanh" and pre is None:
             with torch.no_grad():
                 pre = linear_bias_act(x2, weight, bias, "none")
         dpre, dbias = bias_act_backward(d2, pre, ctx.activation, want_db)
         dx = _dgrad(dpre, weight).reshape(x.shape) if ctx.needs_input_grad[0] else None
         dw = dpre.t() @ x2 if ctx.needs_input_grad[1] else None
-        return dx, dw, dbias, None
+        return dx, dw, dbias, None, None
 
 
 def linear_bias_residual_(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
@@ -239,11 +265,12 @@ class FusedDense(nn.Linear):
 
 def fused_dense_gelu_dense_func(x, weight1, weight2, bias1=None, bias2=None, save_pre_act=False,
                                 return_residual=False, checkpoint_lvl=0, heuristic=0, process_group=None):
-    """fc2(gelu_tanh(fc1(x))) (fused_dense.py:332-354); save_pre_act / checkpoint_lvl / heuristic only matter to
-    the reference's backward and cuBLASLt algo choice and are accepted for signature compatibility."""
+    """fc2(gelu_tanh(fc1(x))) (fused_dense.py:332-354).  checkpoint_lvl 0 / 1: the fc1 kernel stores the pre-activation
+    for the backward; 2: the backward recomputes it (fused_dense.py:262-266).  `save_pre_act` (an inference-path flag of
+    the reference) and `heuristic` (its cuBLASLt algorithm choice) are accepted for signature compatibility."""
     if process_group is not None:
         raise RuntimeError("tensor parallelism is out of scope for this path (batch sharding only)")
-    hidden = linear_bias_act(x, weight1, bias1, "gelu_tanh")
+    hidden = linear_bias_act(x, weight1, bias1, "gelu_tanh", save_pre_act=checkpoint_lvl != 2)
     out = linear(hidden, weight2, bias2)
     return out if not return_residual else (out, x)
 

@@ -417,7 +417,8 @@ def run_ours(args):
             for _ in range(2):
                 train_step()
             bwd_names = ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_fwd", "bp_ln_residual_bwd", "bp_bias_act_bwd",
-                         "bp_linear_bias_act_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd", "bp_sense_softmax_bwd", "bp_xentropy_fwd",
+                         "bp_linear_bias_act_fwd", "bp_linear_bias_act_aux_fwd", "bp_sense_lse_fwd", "bp_sense_mix_fwd",
+                         "bp_sense_softmax_bwd", "bp_xentropy_fwd",
                          "bp_xentropy_bwd")
             tt = {n: _lib.KernelTimer(n) for n in bwd_names}
             for t in tt.values():
@@ -654,7 +655,7 @@ def run_ours(args):
             "note": "forward + backward of the same model in train mode (dropouts 0), next-token cross-entropy by "
                     "bp_xentropy_fwd / _bwd in place over the bf16 logits, eager launches, no optimizer step: attention "
                     "backward = bp_fmha_bwd, LayerNorm backward = "
-                    "bp_ln_residual_bwd, dgelu + bias gradients = bp_bias_act_bwd, dgrad GEMMs = this library's GEMM, wgrad "
+                    "bp_ln_residual_bwd, dgelu + bias gradients = bp_bias_act_bwd (the fc1 GEMM stores its pre-activation: no recompute), dgrad GEMMs = this library's GEMM, wgrad "
                     "GEMMs = cuBLAS through PyTorch, sense-mix backward = batched cuBLAS GEMMs around bp_sense_softmax_bwd; at N > 1 the batch is sharded "
                     "and the gradients are averaged with bucketed NCCL all-reduces (parallel.allreduce_gradients).  A "
                     "variant: the headline metric is the forward"}

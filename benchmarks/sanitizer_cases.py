@@ -109,6 +109,7 @@ if __name__ == "__main__":
     layer_norm(65, 1024)
     layer_norm(77, 768, p=0.1)
     mlp(300, 256)
+    mlp(200, 128)       # fewer than 256 rows: the backward recomputes the pre-activation
     xent(100, 50264)
     xent(33, 1000)
     print("sanitizer cases: all finite")

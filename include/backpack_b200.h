@@ -179,6 +179,15 @@ int bp_linear_bias_act_fwd(const void* x, const void* w, const void* bias, void*
                            int64_t m, int32_t n, int32_t k, int32_t activation /* bp_activation_t */,
                            int32_t dtype, void* stream);
 
+/* The same GEMM with the pre-activation as a second output: out = act(x W^T + bias), pre_out = x W^T + bias, both
+ * (m, n) row-major in `dtype`, from one pass over the accumulators (replaces linear_gelu_forward with save_gelu_in =
+ * true, csrc/fused_dense_lib/fused_dense.cpp:88-142, which training uses so that the backward need not recompute the
+ * fc1 GEMM: flash_attn/ops/fused_dense.py:220-222).  m >= 256 (BP_ERR_UNSUPPORTED below); out != pre_out.
+ */
+int bp_linear_bias_act_aux_fwd(const void* x, const void* w, const void* bias, void* out, void* pre_out,
+                               int64_t m, int32_t n, int32_t k, int32_t activation /* bp_activation_t */,
+                               int32_t dtype, void* stream);
+
 /* Tied LM head with the softmax statistics fused into the GEMM epilogue: logits = x W^T are never written to HBM
  * (6.6 GB per forward at Backpack-Small / batch 64 / seq 1024).  What evaluation and greedy decoding consume:
  *   lse[i]          = log sum_j exp(logits[i, j])          (the cross-entropy is lse[i] - target_logit[i])

@@ -157,6 +157,50 @@ def test_fused_dense_gelu_dense_backward(in_features, hidden, out_features, dtyp
     assert O.max_abs(x.grad, xr.grad) <= 2 * O.max_abs(x_pt.grad, xr.grad) + 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,k", [(4096, 3072, 768), (1000, 776, 200), (256, 256, 64), (65536, 3072, 768)])
+def test_pre_activation_output_of_the_forward_gemm(dtype, m, n, k):
+    """bp_linear_bias_act_aux_fwd (the reference's linear_gelu_forward with save_gelu_in, fused_dense.py:220-222): the
+    activated output is bit-identical to the plain kernel's, the pre-activation to the activation-free kernel's."""
+    from backpacks_flash_attn_b200.ops.fused_dense import _linear_bias_act_aux, linear_bias_act
+    torch.manual_seed(m + n)
+    x = torch.randn(m, k, device="cuda", dtype=dtype)
+    w = (torch.randn(n, k, device="cuda") * k ** -0.5).to(dtype)
+    b = torch.randn(n, device="cuda", dtype=dtype)
+    out, pre = _linear_bias_act_aux(x, w, b, "gelu_tanh")
+    assert torch.equal(out, linear_bias_act(x, w, b, "gelu_tanh"))
+    assert torch.equal(pre, linear_bias_act(x, w, b, "none"))
+    out2, pre2 = _linear_bias_act_aux(x, w, None, "gelu_tanh")
+    assert torch.equal(out2, linear_bias_act(x, w, None, "gelu_tanh")) and torch.equal(pre2, linear_bias_act(x, w, None, "none"))
+    if m <= 4096:
+        ref = x.float() @ w.float().t() + b.float()
+        assert (pre.float() - ref).abs().max() <= 2 * (F.linear(x, w, b).float() - ref).abs().max() + 1e-3
+
+
+@pytest.mark.parametrize("checkpoint_lvl", [0, 1, 2])
+def test_checkpoint_levels_give_the_same_gradients(checkpoint_lvl):
+    """checkpoint_lvl 0 / 1 keep the pre-activation the forward kernel wrote, 2 recomputes it in the backward
+    (fused_dense.py:262-266): same bits either way, and the launch counters show which path ran."""
+    from backpacks_flash_attn_b200 import _lib
+    from backpacks_flash_attn_b200.ops.fused_dense import FusedDenseGeluDense
+    torch.manual_seed(1)
+    ref = FusedDenseGeluDense(256, 1024, 256, checkpoint_lvl=2, device="cuda", dtype=torch.bfloat16)
+    mod = FusedDenseGeluDense(256, 1024, 256, checkpoint_lvl=checkpoint_lvl, device="cuda", dtype=torch.bfloat16)
+    mod.load_state_dict(ref.state_dict())
+    x = torch.randn(4, 300, 256, device="cuda", dtype=torch.bfloat16)
+    g = torch.randn(4, 300, 256, device="cuda", dtype=torch.bfloat16)
+    grads = []
+    for m_ in (ref, mod):
+        xi = x.clone().requires_grad_()
+        before = dict(_lib.launch_counts)
+        m_(xi).backward(g)
+        used_aux = _lib.launch_counts.get("bp_linear_bias_act_aux_fwd", 0) - before.get("bp_linear_bias_act_aux_fwd", 0)
+        grads.append((xi.grad, m_.fc1.weight.grad, m_.fc1.bias.grad, m_.fc2.weight.grad, used_aux))
+    assert grads[0][4] == 0 and grads[1][4] == (0 if checkpoint_lvl == 2 else 1)
+    for a, c in zip(grads[0][:4], grads[1][:4]):
+        assert torch.equal(a, c)
+
+
 def test_bias_act_backward_kernel_directly():
     from backpacks_flash_attn_b200.ops.fused_dense import bias_act_backward
     torch.manual_seed(1)
