@@ -1,6 +1,7 @@
 """Model-level backward parity: loss.backward() through the fused Backpack model -- attention
-backward (bp_fmha_bwd), LayerNorm backward (bp_ln_residual_bwd), dense backward (bp_bias_act_bwd + GEMMs), the
-recomputing sense-mix node -- against fp32 autograd through the ORACLE's restatement of the reference model, next to
+backward (bp_fmha_bwd), LayerNorm backward (bp_ln_residual_bwd), dense backward (bp_bias_act_bwd + GEMMs, the fc1 GEMM
+storing its pre-activation), the hand-derived sense-mix backward (GEMMs + bp_sense_softmax_bwd) -- against fp32
+autograd through the ORACLE's restatement of the reference model, next to
 the reference's own eager bf16 path.  Rule: the model-level one of tests/models/test_gpt.py:60,70 applied to
 gradients -- our error against fp32 stays below 3x the error of the same-precision eager path."""
 import pytest
@@ -36,7 +37,8 @@ def test_training_step_gradients_match_the_oracle():
     before = dict(_lib.launch_counts)
     loss = _loss(fused(ids).logits, ids)
     loss.backward()
-    for name in ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_bwd", "bp_bias_act_bwd", "bp_sense_mix_fwd"):
+    for name in ("bp_fmha_fwd", "bp_fmha_bwd", "bp_ln_residual_bwd", "bp_bias_act_bwd", "bp_sense_mix_fwd",
+                 "bp_sense_softmax_bwd", "bp_linear_bias_act_aux_fwd"):
         assert _lib.launch_counts.get(name, 0) > before.get(name, 0), f"{name} did not run in the training step"
     loss_e = _loss(eager(ids).logits, ids)
     loss_e.backward()
