@@ -73,13 +73,27 @@ def _sense_mix_eager(qk, content, scale):
     return torch.sum(alpha @ content, dim=1)
 
 
+def _empty_like_layout(t: torch.Tensor) -> torch.Tensor:
+    """An uninitialised tensor with t's strides when t is a permutation of a dense tensor (the transposed view the content
+    model returns), else a plain contiguous one (expanded / overlapping inputs must not alias in the gradient)."""
+    order = sorted(range(t.dim()), key=lambda i: -t.stride(i))
+    expect, dense = 1, True
+    for i in reversed(order):
+        if t.shape[i] != 1 and t.stride(i) != expect:
+            dense = False
+            break
+        expect *= t.shape[i]
+    if dense:
+        return torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
+    return torch.empty(t.shape, dtype=t.dtype, device=t.device)
+
+
 def _sense_mix_backward_eager(qk, content, dout, scale, want_dqk, want_dcontent, chunk_bytes=1 << 30):
     """Gradients by autograd through the eager composition, a few batch elements at a time (any seqlen)."""
     b, s, _, nv, _ = qk.shape
     step = max(1, chunk_bytes // (4 * nv * s * s * qk.element_size()))
     dqk = torch.empty_like(qk) if want_dqk else None
-    dcontent = (torch.empty_strided(content.shape, content.stride(), dtype=content.dtype, device=content.device)
-                if want_dcontent else None)
+    dcontent = _empty_like_layout(content) if want_dcontent else None
     for i in range(0, b, step):
         with torch.enable_grad():
             q_ = qk[i:i + step].detach().requires_grad_(want_dqk)
@@ -110,8 +124,7 @@ def _sense_mix_backward(qk, content, dout, scale, want_dqk, want_dcontent, chunk
     dqk = torch.empty_like(qk) if want_dqk else None
     # same strides as `content`: the reference hands a transposed view of (b, s, nv, d), and a gradient in that layout
     # flows back through the transpose / reshape of the content model as a view instead of a 1.6 GB copy
-    dcontent = (torch.empty_strided(content.shape, content.stride(), dtype=content.dtype, device=content.device)
-                if want_dcontent else None)
+    dcontent = _empty_like_layout(content) if want_dcontent else None
     lib = _lib.load()
     dt = _lib.dtype_code(qk.dtype)
     step = max(1, min(b, chunk_bytes // (2 * nv * s * s * qk.element_size())))

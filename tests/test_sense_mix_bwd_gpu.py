@@ -75,6 +75,25 @@ def test_sense_mix_backward_is_deterministic_and_chunking_is_invisible():
     assert torch.equal(only_q[0], a[0]) and torch.equal(only_c[1], a[1])
 
 
+def test_expanded_and_sliced_content_layouts():
+    """A content tensor that is not a permutation of a dense one (broadcast over the batch, or a slice of a wider tensor)
+    gets a plain contiguous gradient: no aliasing through stride-0 or padded strides."""
+    g = torch.Generator("cuda").manual_seed(8)
+    b, s, nv, d = 3, 128, 4, 256
+    qk = torch.randn(b, s, 2, nv, d // nv, device="cuda", generator=g).bfloat16()
+    dout = torch.randn(b, s, d, device="cuda", generator=g).bfloat16()
+    base = (torch.randn(1, nv, s, d, device="cuda", generator=g) * 0.5).bfloat16()
+    wide = (torch.randn(b, nv, s, 2 * d, device="cuda", generator=g) * 0.5).bfloat16()
+    for src, make in ((base, lambda t: t.expand(b, nv, s, d)), (wide, lambda t: t[..., :d])):
+        leaf = src.clone().requires_grad_()
+        leaf_e = src.clone().requires_grad_()
+        sense_mix(qk, make(leaf)).backward(dout)
+        O.sense_mix_eager(qk, make(leaf_e)).backward(dout)
+        assert leaf.grad.shape == src.shape
+        err = (leaf.grad.float() - leaf_e.grad.float()).abs().max().item()
+        assert err <= 3e-2 * leaf_e.grad.float().abs().max().item() + 1e-3, err
+
+
 def test_unsupported_sequence_lengths_fall_back_to_autograd_through_the_eager_composition():
     qk, content, dout = _inputs(2, 203, 4, 256, torch.bfloat16, seed=4)      # 203 is not a multiple of 8
     before = _lib.launch_counts.get("bp_sense_softmax_bwd", 0)
