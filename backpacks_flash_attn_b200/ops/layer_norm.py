@@ -18,8 +18,7 @@ def layer_norm_dropout_mask(seed: int, rows: int, cols: int, dropout_p: float, d
     csrc/bp_common.cuh (drop_base with the "LN" tag / drop_row_word / drop_col_word / drop_keep) in int64 tensor
     arithmetic.  Plays the role of the dmask the reference's forward returns (layer_norm.py:120-131)."""
     thr = int(effective_dropout_p(dropout_p) * 256)
-    base = _mix32(torch.tensor((seed & _M32) ^ int(_mix32(torch.tensor(((seed >> 32) & _M32) + 0x4C4E))), dtype=torch.int64))
-    base = base.to(device)
+    base = _mix32((seed & _M32) ^ _mix32(((seed >> 32) & _M32) + 0x4C4E))     # drop_base(seed, "LN"): plain integers
     r = torch.arange(rows, dtype=torch.int64, device=device)
     c = torch.arange(cols, dtype=torch.int64, device=device)
     rw = _mix32(base + r * 0x9E3779B1)
