@@ -6,7 +6,7 @@
 // GEMM-shaped products on the library's batched GEMM
 //     S_l = q_l k_l^T      dA_l = dO C_l^T      dC_l = P_l^T dO      dq_l = dS_l k_l      dk_l = dS_l^T q_l
 // and this kernel does everything between them, one warp per score row (row = (sense, batch, query t)), rows of up to
-// 2048 keys held in registers:
+// 2048 keys held in registers (longer rows: a three-pass variant):
 //     P    = softmax_j<=t (scale * S)                 written over S  (16-bit, zeros right of the diagonal)
 //     dS'  = scale * P o (dA - sum_j P o dA)          written over dA (16-bit, zeros right of the diagonal)
 // Only the causal part of a row is read (whatever S and dA hold right of the diagonal is ignored); the whole row is
@@ -140,6 +140,78 @@ sense_softmax_bwd_kernel(uint16_t* __restrict__ S, uint16_t* __restrict__ dA, in
   }
 }
 
+// Rows longer than 2048 keys do not fit in registers: three passes over the causal part of the row (running max and sum;
+// delta; write), each lane re-reading its own 16-byte vectors (L1 / L2 hits: a row is read from HBM once).  In place is
+// still safe: a vector is overwritten by the lane that has just read it, in the last pass only.
+template <bool kBF16>
+__global__ void __launch_bounds__(kWarps * 32)
+sense_softmax_bwd_long_kernel(uint16_t* __restrict__ S, uint16_t* __restrict__ dA, int64_t rows, int seqlen, float scale,
+                              float scale_log2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kWarps;
+  for (int64_t r = warp0; r < rows; r += stride) {
+    const int t = static_cast<int>(r % seqlen);
+    uint16_t* srow = S + r * seqlen;
+    uint16_t* drow = dA + r * seqlen;
+    float m = -INFINITY, l = 0.f;
+    for (int c0 = lane * 8; c0 <= t; c0 += 256) {
+      float x[8];
+      unpack8<kBF16>(*reinterpret_cast<const uint4*>(srow + c0), x);
+      float cm = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        x[k] = (c0 + k <= t) ? x[k] * scale_log2 : -INFINITY;
+        cm = fmaxf(cm, x[k]);
+      }
+      const float mn = fmaxf(m, cm);          // finite: element c0 itself is visible
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += exp2f(x[k] - mn);
+      l = l * exp2f(m - mn) + a;
+      m = mn;
+    }
+    const float mw = warp_max(m);             // lanes without a visible vector hold m = -inf, l = 0
+    l = warp_sum(m == -INFINITY ? 0.f : l * exp2f(m - mw));
+    const float inv = 1.f / l;
+    float delta = 0.f;
+    for (int c0 = lane * 8; c0 <= t; c0 += 256) {
+      float x[8], g[8];
+      unpack8<kBF16>(*reinterpret_cast<const uint4*>(srow + c0), x);
+      unpack8<kBF16>(*reinterpret_cast<const uint4*>(drow + c0), g);
+      float pr[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pr[k] = (c0 + k <= t) ? exp2f(x[k] * scale_log2 - mw) * inv : 0.f;
+      uint4 pb;
+      pb.x = pack2<kBF16>(pr[0], pr[1]), pb.y = pack2<kBF16>(pr[2], pr[3]);
+      pb.z = pack2<kBF16>(pr[4], pr[5]), pb.w = pack2<kBF16>(pr[6], pr[7]);
+      unpack8<kBF16>(pb, pr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) delta = (c0 + k <= t) ? fmaf(pr[k], g[k], delta) : delta;
+    }
+    delta = warp_sum(delta);
+    for (int c0 = lane * 8; c0 < seqlen; c0 += 256) {
+      uint4 pb = make_uint4(0u, 0u, 0u, 0u), o = make_uint4(0u, 0u, 0u, 0u);
+      if (c0 <= t) {
+        float x[8], g[8], pr[8];
+        unpack8<kBF16>(*reinterpret_cast<const uint4*>(srow + c0), x);
+        unpack8<kBF16>(*reinterpret_cast<const uint4*>(drow + c0), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pr[k] = (c0 + k <= t) ? exp2f(x[k] * scale_log2 - mw) * inv : 0.f;
+        pb.x = pack2<kBF16>(pr[0], pr[1]), pb.y = pack2<kBF16>(pr[2], pr[3]);
+        pb.z = pack2<kBF16>(pr[4], pr[5]), pb.w = pack2<kBF16>(pr[6], pr[7]);
+        unpack8<kBF16>(pb, pr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (c0 + k <= t) ? scale * pr[k] * (g[k] - delta) : 0.f;
+        o.x = pack2<kBF16>(g[0], g[1]), o.y = pack2<kBF16>(g[2], g[3]);
+        o.z = pack2<kBF16>(g[4], g[5]), o.w = pack2<kBF16>(g[6], g[7]);
+      }
+      *reinterpret_cast<uint4*>(srow + c0) = pb;
+      *reinterpret_cast<uint4*>(drow + c0) = o;
+    }
+  }
+}
+
 template <bool kBF16, int NV>
 int launch(void* S, void* dA, int64_t rows, int seqlen, float scale, cudaStream_t st) {
   int dev = 0, sms = 148;
@@ -158,7 +230,15 @@ int dispatch(void* S, void* dA, int64_t rows, int seqlen, float scale, cudaStrea
   if (seqlen <= 256) return launch<kBF16, 1>(S, dA, rows, seqlen, scale, st);
   if (seqlen <= 512) return launch<kBF16, 2>(S, dA, rows, seqlen, scale, st);
   if (seqlen <= 1024) return launch<kBF16, 4>(S, dA, rows, seqlen, scale, st);
-  return launch<kBF16, 8>(S, dA, rows, seqlen, scale, st);
+  if (seqlen <= 2048) return launch<kBF16, 8>(S, dA, rows, seqlen, scale, st);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (rows + kWarps - 1) / kWarps;
+  const int64_t cap = static_cast<int64_t>(sms) * 32;
+  sense_softmax_bwd_long_kernel<kBF16><<<static_cast<int>(want < cap ? want : cap), kWarps * 32, 0, st>>>(
+      static_cast<uint16_t*>(S), static_cast<uint16_t*>(dA), rows, seqlen, scale, scale * 1.4426950408889634f);
+  return check_launch("bp_sense_softmax_bwd launch");
 }
 
 }  // namespace smb
@@ -171,8 +251,8 @@ extern "C" int bp_sense_softmax_bwd(void* scores_probs, void* dalpha_dscores, in
   if (dtype != BP_DTYPE_F16 && dtype != BP_DTYPE_BF16)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: only fp16 and bf16 are supported (dtype=%d)", dtype);
   if (rows <= 0 || seqlen <= 0) return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: empty input");
-  if (seqlen % 8 != 0 || seqlen > 2048)
-    return fail(BP_ERR_UNSUPPORTED, "bp_sense_softmax_bwd: seqlen must be a multiple of 8, at most 2048 (got %d)", seqlen);
+  if (seqlen % 8 != 0 || seqlen > 8192)
+    return fail(BP_ERR_UNSUPPORTED, "bp_sense_softmax_bwd: seqlen must be a multiple of 8, at most 8192 (got %d)", seqlen);
   if (rows % seqlen != 0)
     return fail(BP_ERR_INVALID_ARGUMENT, "bp_sense_softmax_bwd: rows (%lld) must be a multiple of seqlen (%d): square causal score matrices",
                 (long long)rows, seqlen);

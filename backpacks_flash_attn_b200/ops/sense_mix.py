@@ -11,7 +11,7 @@ the intervention wrappers build (training/src/models/intervened_models.py:78-101
 Training: `sense_mix` is differentiable.  The forward is the fused kernel (alpha is neither materialised nor kept for
 the backward -- 2.15 GB at Backpack-Small, batch 64).  The backward recomputes the scores and is hand-derived: five
 batched library GEMMs per sense with ONE own element-wise pass between them (`bp_sense_softmax_bwd`: causal softmax +
-softmax backward + scale, in place); sequence lengths that pass does not take (not a multiple of 8, above 2048) fall
+softmax backward + scale, in place); sequence lengths that pass does not take (not a multiple of 8, above 8192) fall
 back to autograd through the reference's eager composition (backpack.py:116-122, 313).  A fully fused tcgen05
 sense-mix backward (no (b, nv, s, s) tensor at all) is not built.
 
@@ -166,7 +166,7 @@ class _SenseMixFn(torch.autograd.Function):
     def backward(ctx, dout):
         qk, content = ctx.saved_tensors
         s = qk.shape[1]
-        fn = _sense_mix_backward if (s % 8 == 0 and s <= 2048 and content.stride(3) == 1) else _sense_mix_backward_eager
+        fn = _sense_mix_backward if (s % 8 == 0 and s <= 8192 and content.stride(3) == 1) else _sense_mix_backward_eager
         dqk, dcontent = fn(qk, content, dout, ctx.scale, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dqk, dcontent, None
 

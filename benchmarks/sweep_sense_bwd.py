@@ -14,7 +14,7 @@ from benchmarks.bench_kernels import time_fn  # noqa: E402
 from backpacks_flash_attn_b200.ops.sense_mix import _sense_mix_backward, _sense_mix_backward_eager  # noqa: E402
 
 d = 768
-for s in (512, 1024, 2048):
+for s in (512, 1024, 2048, 4096):
     for nv in (4, 16, 64):
         b = max(1, 16384 // s)                       # 16 k tokens per call
         qk = torch.randn(b, s, 2, nv, d // nv, device="cuda").bfloat16()

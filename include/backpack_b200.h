@@ -315,7 +315,7 @@ int bp_xentropy_bwd(const float* grad_losses, const void* logits, const float* l
  *   scores_probs   (rows, seqlen) 16-bit: raw scores q.k in, probabilities P = softmax_{j<=t}(scale * scores) out;
  *   dalpha_dscores (rows, seqlen) 16-bit: dL/dP in, scale * P o (dL/dP - rowsum(P o dL/dP)) out;
  * row r belongs to query t = r % seqlen (square causal matrices stacked along rows); entries right of the diagonal are
- * ignored on input and written as zeros.  seqlen % 8 == 0, seqlen <= 2048 (BP_ERR_UNSUPPORTED otherwise).
+ * ignored on input and written as zeros.  seqlen % 8 == 0, seqlen <= 8192 (BP_ERR_UNSUPPORTED otherwise).
  */
 int bp_sense_softmax_bwd(void* scores_probs, void* dalpha_dscores, int64_t rows, int32_t seqlen, float softmax_scale,
                          int32_t dtype, void* stream);

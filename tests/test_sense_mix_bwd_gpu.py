@@ -36,7 +36,7 @@ def _grads(fn, qk, content, dout):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("b,s,nv,d", [(2, 256, 16, 768), (3, 200, 4, 768), (1, 1024, 16, 768), (2, 136, 8, 256),
-                                      (1, 2048, 4, 256), (2, 64, 64, 768)])
+                                      (1, 2048, 4, 256), (2, 64, 64, 768), (1, 4096, 4, 256), (1, 2304, 8, 256)])
 def test_sense_mix_backward_matches_the_oracle(dtype, b, s, nv, d):
     qk, content, dout = _inputs(b, s, nv, d, dtype, seed=s + nv)
     before = _lib.launch_counts.get("bp_sense_softmax_bwd", 0)
@@ -104,7 +104,7 @@ def test_unsupported_sequence_lengths_fall_back_to_autograd_through_the_eager_co
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("mats,s", [(3, 8), (5, 200), (2, 256), (3, 520), (2, 1024), (1, 2048)])
+@pytest.mark.parametrize("mats,s", [(3, 8), (5, 200), (2, 256), (3, 520), (2, 1024), (1, 2048), (1, 2056), (1, 4096)])
 def test_softmax_backward_kernel_directly(dtype, mats, s):
     g = torch.Generator("cuda").manual_seed(s)
     scores = (torch.randn(mats, s, s, device="cuda", generator=g) * 4).to(dtype)
@@ -136,7 +136,7 @@ def test_softmax_backward_kernel_rejects_bad_arguments():
     st = _lib.stream_ptr(t.device)
     dt = _lib.dtype_code(torch.bfloat16)
     assert lib.bp_sense_softmax_bwd(t.data_ptr(), t.data_ptr(), 16, 12, 1.0, dt, st) == -2      # seqlen % 8
-    assert lib.bp_sense_softmax_bwd(t.data_ptr(), t.data_ptr(), 4096, 4096, 1.0, dt, st) == -2  # seqlen > 2048
+    assert lib.bp_sense_softmax_bwd(t.data_ptr(), t.data_ptr(), 8200, 8200, 1.0, dt, st) == -2  # seqlen > 8192
     assert lib.bp_sense_softmax_bwd(t.data_ptr(), t.data_ptr(), 17, 16, 1.0, dt, st) == -1      # rows % seqlen
     assert lib.bp_sense_softmax_bwd(0, t.data_ptr(), 16, 16, 1.0, dt, st) == -1
     assert lib.bp_sense_softmax_bwd(t.data_ptr(), t.data_ptr(), 16, 16, 1.0, 2, st) == -1       # fp32 storage
